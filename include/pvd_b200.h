@@ -1,0 +1,231 @@
+/* pvd_b200.h -- C ABI of the B200-native PyVibDMC walker-propagation path.
+ *
+ * One shared library (pyvibdmc_b200/_lib/libpvd_b200.so, sm_100a) exports exactly the entry
+ * points declared here.  Signatures use plain pointers and sizes only (no torch types); the
+ * Python host (pyvibdmc_b200/_capi.py) binds them with ctypes.  Each entry point cites the
+ * reference interface it replaces (paths relative to /root/reference/pyvibdmc).
+ *
+ * Conventions
+ *   - all arrays are float64 C-contiguous in the reference's layouts: coordinates are
+ *     "AoS" (n, natoms, ndim); per-walker scalars are (n,).
+ *   - every function returns 0 on success, a PVD_E_* code otherwise; pvd_last_error()
+ *     returns a human-readable message for the calling thread's last failure.
+ *   - "host" entry points take host pointers and do H2D / kernel / D2H internally (they are the
+ *     drop-in plug-in calls); pvd_sim_* entry points keep the walker ensemble resident in HBM.
+ *   - a simulation handle is not thread-safe; use one host thread per handle.
+ */
+#ifndef PVD_B200_H
+#define PVD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PVD_ABI_VERSION 1
+
+/* error codes */
+enum {
+    PVD_OK = 0,
+    PVD_E_CUDA = 1,        /* a CUDA runtime call failed (message has the CUDA error string) */
+    PVD_E_ARG = 2,         /* invalid argument */
+    PVD_E_MASSIVE = 3,     /* "Massive walker birth or death event" (pyvibdmc.py:400,413,717) */
+    PVD_E_STATE = 4,       /* call not valid in the handle's current state */
+    PVD_E_NODEVICE = 5     /* no CUDA device available */
+};
+
+/* built-in potentials (replace the user functions called through Potential.getpot,
+ * simulation_utilities/potential_manager.py:71-99) */
+enum {
+    PVD_POT_EXTERNAL = 0,  /* V supplied by the host each step (arbitrary user Python potential) */
+    PVD_POT_HARMONIC = 1,  /* sum_c k_c x_c^2 : sample_potentials/PythonPots/harmonicOscillator1D.py:5-49 */
+    PVD_POT_H2O_PS = 2,    /* Partridge-Schwenke water: FortPots/Partridge_Schwenke_H2O/calc_h2o_pot.f + h2opes_v2.f */
+    PVD_POT_MORSE1D = 3,   /* De (1-exp(-a x))^2 : sample_potentials/PythonPots/morse_osc_1d.py:4-12 */
+    PVD_POT_NN_H4O2 = 4    /* Coulomb descriptor + 15-120-120-120-1 MLP: TensorflowPots/call_sample_model.py:4-9 */
+};
+
+/* built-in trial wave functions (replace ImpSampManager.call_trial / call_derivs,
+ * simulation_utilities/imp_samp_manager.py:92-139,197-224) */
+enum {
+    PVD_TRIAL_NONE = 0,
+    PVD_TRIAL_HARM1D = 1,  /* analytic Gaussian + derivatives: PythonPots/harm_trial_wfn.py:6-40 */
+    PVD_TRIAL_H2O_FD = 2   /* water product wfn, finite-difference derivatives:
+                              FortPots/.../call_trl_h2o.py:63-78 + imp_samp.py:56-76 */
+};
+
+enum { PVD_WEIGHT_DISCRETE = 0, PVD_WEIGHT_CONTINUOUS = 1 };
+enum { PVD_RNG_FP64 = 0, PVD_RNG_FAST = 1 };
+
+#define PVD_MAX_ATOMS 16
+#define PVD_MAX_COMP (3 * PVD_MAX_ATOMS)
+
+/* ------------------------------------------------------------------ library / device */
+int pvd_abi_version(void);
+const char *pvd_last_error(void);
+int pvd_device_count(int *count);
+int pvd_set_device(int device);
+/* FP64 FMA throughput of the current device in FLOP/s, measured with a register-resident
+ * DFMA chain (roofline denominator for the fp64 potential kernels). */
+int pvd_measure_fp64_peak(double *flops_per_s);
+/* Device time (ms) of the most recent host entry point's kernel, measured with CUDA events. */
+int pvd_last_kernel_ms(double *ms);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+int64_t pvd_launch_count(void);
+
+/* ------------------------------------------------------------------ stand-alone host entry points
+ * (the plug-in surface: what a maintainer binds behind Potential.getpot / ImpSamp.*) */
+
+/* replaces water_pot(cds) = calc_hoh_pot(cds, len(cds))  (h2o_potential.py:6-7, calc_h2o_pot.f:1-34).
+ * xyz: (n,3,3) bohr, atoms ordered H,H,O ; v: (n,) Hartree */
+int pvd_pes_h2o(const double *xyz, int64_t n, double *v);
+/* folded PS parameters as uploaded to the device: c[245], scal[8] = reoh,b1,ce,phh1,phh2,deoh,roh,alphaoh */
+int pvd_pes_h2o_params(double *c245, double *scal8);
+
+/* replaces oh_stretch_harm-style functions (harmonicOscillator1D.py:13-17):
+ * v[i] = sum_c k[c] * x[i,c]^2 with k[c] = (0.5*mass)*omega^2 computed by the caller. x: (n,ncomp) */
+int pvd_pes_harmonic(const double *x, int64_t n, int32_t ncomp, const double *k, double *v);
+/* replaces oh_stretch_morse (morse_osc_1d.py:4-12): v = de * (1 - exp(-alpha x))^2 ; x: (n,) */
+int pvd_pes_morse1d(const double *x, int64_t n, double de, double alpha, double *v);
+
+/* replaces DMC_Sim.move_randomly (pyvibdmc.py:540-547): xyz[i,a,:] += N(0, sigma[a]) in place.
+ * Normals come from Philox4x32-10 keyed by `seed`, counter (walker index, step). */
+int pvd_displace(double *xyz, int64_t n, int32_t natoms, int32_t ndim, const double *sigma,
+                 uint64_t seed, uint64_t step, int32_t rng_mode);
+/* raw generator output for statistical tests: z[i,c] exactly as pvd_displace would add with sigma=1 */
+int pvd_normals(double *z, int64_t n, int32_t ncomp, uint64_t seed, uint64_t step, int32_t rng_mode);
+/* Philox4x32-10 known-answer hook: out[4] = philox(ctr[4], key[2]) computed on the device */
+int pvd_philox_kat(const uint32_t *ctr4, const uint32_t *key2, uint32_t *out4);
+
+/* replaces the discrete branch of DMC_Sim.birth_or_death (pyvibdmc.py:391-431) given the
+ * caller's uniforms u (injection mode).  counts: (n,) int32 ; idx: (capacity,) int64 receives
+ * np.repeat(arange(n), counts) ; stats[3] = births, deaths, final_pop.  Returns PVD_E_MASSIVE when
+ * the reference would raise (non-finite / too large weight, population outside [0.5,1.5] n0). */
+int pvd_branch_discrete(const double *v, int64_t n, double vref, double dt, const double *u, int64_t n0,
+                        int32_t *counts, int64_t *idx, int64_t idx_capacity, int64_t *stats3);
+
+/* replaces the continuous branch of birth_or_death + _branch (pyvibdmc.py:432-454, 340-356).
+ * w: (n,) in/out ; src: (n,) int64 out, src[i] = walker whose coords/V/who_from walker i holds
+ * afterwards ; upper = NaN for "no upper threshold" ; stats[3] = n_branched, max_w, min_w (after). */
+int pvd_branch_continuous(double *w, const double *v, int64_t n, double vref, double dt,
+                          double lower, double upper, int64_t *src, double *stats3);
+
+/* replaces calc_vref (pyvibdmc.py:651-661); w may be NULL (discrete). */
+int pvd_calc_vref(const double *v, const double *w, int64_t n, int64_t n0, double alpha, double *vref);
+/* replaces calc_desc_wts (pyvibdmc.py:663-672); w NULL -> discrete counts. out: (n_parent,) */
+int pvd_desc_wts(const int64_t *who_from, const double *w, int64_t n, int64_t n_parent, double *out);
+
+/* replaces ImpSamp.drift with finite differences (imp_samp.py:21-26,56-76 + manager division
+ * by psi, imp_samp_manager.py:117-120) for a built-in trial wfn.
+ * psi: (n,) ; dlog: (n,natoms,ndim) = grad psi / psi ; d2: same shape = d2psi/dx2 / psi.
+ * table: trial-specific parameters (H2O: 2 x ntab doubles = grid row then psi row; HARM1D: {alpha}). */
+int pvd_trial_drift(int32_t trial, const double *xyz, int64_t n, int32_t natoms, int32_t ndim,
+                    const double *table, int64_t ntab, double *psi, double *dlog, double *d2);
+/* replaces ImpSamp.metropolis (imp_samp.py:29-47) + local_kin (:50-53).
+ * acc: (n,) acceptance ratios ; sigma, inv_mass: (natoms,) */
+int pvd_metropolis(const double *x, const double *y, const double *fx, const double *fy,
+                   const double *psi_x, const double *psi_y, int64_t n, int32_t natoms, int32_t ndim,
+                   const double *sigma, const double *inv_mass, double dt, double *acc);
+int pvd_local_kin(const double *d2, int64_t n, int32_t natoms, int32_t ndim, const double *inv_mass, double *ke);
+
+/* replaces sample_h4o2_pot (call_sample_model.py:4-9): Coulomb descriptor (distance_descriptors.py
+ * :102-113,154-168) + Dense(120,swish)x3 + Dense(1,relu), cm^-1 -> Hartree.
+ * weights: packed float32 [W0(15x120) b0(120) W1(120x120) b1 W2(120x120) b2 W3(120) b3(1)] row-major (in,out).
+ * xyz: (n,6,3) bohr, atoms O,H,H,O,H,H. */
+int pvd_nn_h4o2_set_weights(const float *packed, int64_t nfloats);
+int pvd_nn_h4o2(const double *xyz, int64_t n, double *v);
+int pvd_coulomb_descriptor(const double *xyz, int64_t n, int32_t natoms, const double *z, double *desc);
+
+/* ------------------------------------------------------------------ device-resident simulation
+ * replaces the state + per-step body of DMC_Sim.propagate (pyvibdmc.py:701-876). */
+typedef struct pvd_sim pvd_sim;   /* opaque */
+
+typedef struct {
+    int32_t natoms, ndim;
+    int32_t weighting;            /* PVD_WEIGHT_* */
+    int32_t potential;            /* PVD_POT_* */
+    int32_t trial;                /* PVD_TRIAL_* */
+    int32_t rng_mode;             /* PVD_RNG_* */
+    int32_t device;               /* CUDA device ordinal */
+    int32_t rank, world_size;     /* shard id / number of shards (multi-GPU); 0,1 for a single GPU */
+    int64_t num_walkers;          /* N0: target population of THIS shard's share is num_walkers/world_size */
+    int64_t capacity;             /* walker slots per buffer on this device (>= 1.5*N0_local + slack) */
+    double delta_t;
+    double alpha;                 /* 1/(2 dt) unless DEBUG_alpha (pyvibdmc.py:200-203) */
+    double thresh_lower, thresh_upper;   /* continuous weighting; upper = NaN when absent */
+    uint64_t seed;
+    double masses[PVD_MAX_ATOMS];
+    double pot_params[PVD_MAX_COMP]; /* HARMONIC: k[c]; MORSE1D: de, alpha */
+    int64_t stats_ring;           /* length of the per-step statistics ring (>= steps between drains) */
+} pvd_config;
+
+/* per-step record written by the step kernel's finalisation (one per executed step) */
+typedef struct {
+    double vref;                  /* after calc_vref */
+    double pop;                   /* len(walkers) (discrete) or sum(w) (continuous), global */
+    double v_avg, v_max, v_min;   /* of the energies used for weighting, before branching (log lines) */
+    double w_max, w_min;          /* continuous: after branching */
+    double dt_eff;                /* effective time step used (imp-samp) */
+    int64_t births, deaths;       /* discrete ; continuous: births = n_branched */
+    int64_t rejected;             /* imp-samp Metropolis rejections */
+    int64_t step;                 /* propagation step index this record belongs to */
+} pvd_step_stats;
+
+int pvd_sim_create(const pvd_config *cfg, pvd_sim **out);
+int pvd_sim_destroy(pvd_sim *s);
+/* use an externally owned stream (e.g. torch.cuda.current_stream().cuda_stream); 0 = own stream */
+int pvd_sim_set_stream(pvd_sim *s, void *cuda_stream);
+
+/* upload the start ensemble (DMC_Sim._initialize, pyvibdmc.py:155-169,214-219); w may be NULL.
+ * Also evaluates V on the start ensemble and the first Vref (first-step exception, :760-769). */
+int pvd_sim_upload(pvd_sim *s, const double *xyz, int64_t n, const double *w);
+/* PVD_POT_EXTERNAL only: energies of the uploaded start ensemble, computed by the caller's getpot */
+int pvd_sim_set_pots(pvd_sim *s, const double *v, int64_t n);
+/* multi-GPU: after pvd_sim_upload (+ all-reduce of the sums buffer) compute the first Vref */
+int pvd_sim_init_finalize(pvd_sim *s);
+/* trial-wfn parameters for importance sampling (same meaning as pvd_trial_drift's table) */
+int pvd_sim_set_trial_table(pvd_sim *s, const double *table, int64_t ntab);
+/* trainable-potential weights for PVD_POT_NN_H4O2 */
+int pvd_sim_set_nn_weights(pvd_sim *s, const float *packed, int64_t nfloats);
+
+/* enqueue `nsteps` whole time steps (move -> V -> weight/branch -> Vref -> record) without
+ * host synchronisation; branch_mask_every = branch_every (pyvibdmc.py:828-837). */
+int pvd_sim_run(pvd_sim *s, int64_t nsteps, int32_t branch_every);
+/* one step with injected random numbers (parity tests): disp (n,natoms,ndim) already scaled by
+ * sigma, u_branch (n_after_move,) for birth/death, u_metro (n,) for Metropolis (may be NULL). */
+int pvd_sim_step_injected(pvd_sim *s, const double *disp, const double *u_branch, const double *u_metro);
+/* external-potential stepping: move, hand coordinates to the host, take V back and weight/branch */
+int pvd_sim_ext_move(pvd_sim *s, double *xyz_out, int64_t *n_out);
+int pvd_sim_ext_finish(pvd_sim *s, const double *v, int64_t n, int32_t do_branch);
+
+/* multi-GPU split step: local part, then the caller all-reduces `sums` (device pointer to
+ * PVD_NSUMS doubles, obtained from pvd_sim_sums_ptr) over NCCL, then finalisation. */
+#define PVD_MAX_WORLD 8
+#define PVD_NSUMS (8 + 4 * PVD_MAX_WORLD)
+int pvd_sim_sums_ptr(pvd_sim *s, void **device_ptr);
+int pvd_sim_step_local(pvd_sim *s, int32_t do_branch);
+int pvd_sim_step_finalize(pvd_sim *s);
+
+/* descendant weighting (pyvibdmc.py:739-747, 663-672, 856-869) */
+int pvd_sim_dw_begin(pvd_sim *s, int64_t global_offset);
+int pvd_sim_dw_end(pvd_sim *s, double *desc_wts, int64_t n_parent);
+int pvd_sim_dw_parent(pvd_sim *s, double *xyz, double *w, int64_t *n_parent);
+
+/* blocking queries */
+int pvd_sim_sync(pvd_sim *s);
+int pvd_sim_state(pvd_sim *s, int64_t *n, double *vref, int64_t *step, int32_t *err);
+int pvd_sim_download(pvd_sim *s, double *xyz, double *pots, double *w, int64_t *who_from, int64_t capacity, int64_t *n);
+int pvd_sim_stats(pvd_sim *s, int64_t first_step, int64_t count, pvd_step_stats *out);
+/* device time in ms between the first and last kernel of the most recent pvd_sim_run */
+int pvd_sim_last_run_ms(pvd_sim *s, double *ms);
+/* importance-sampling per-walker arrays (f_x, psi, sec) for checkpoints */
+int pvd_sim_download_imp(pvd_sim *s, double *fx, double *psi, double *sec, int64_t capacity);
+/* walker rebalancing between shards: remove the last `count` walkers into host/peer buffers, or append */
+int pvd_sim_export_tail(pvd_sim *s, int64_t count, double *xyz, double *pots, double *w, int64_t *who);
+int pvd_sim_import(pvd_sim *s, int64_t count, const double *xyz, const double *pots, const double *w, const int64_t *who);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PVD_B200_H */

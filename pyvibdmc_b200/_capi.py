@@ -1,0 +1,173 @@
+"""ctypes binding of libpvd_b200.so (C ABI declared in include/pvd_b200.h).
+
+There is no CPU fallback: if the CUDA library cannot be loaded, or no device is present when a
+compute entry point is called, a PvdError is raised.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+__all__ = ["lib", "PvdError", "MassiveEvent", "check", "PvdConfig", "StepStats", "load"]
+
+MASSIVE_MSG = "Massive walker birth or death event!!!!!!! Dying..."
+PVD_OK, PVD_E_CUDA, PVD_E_ARG, PVD_E_MASSIVE, PVD_E_STATE, PVD_E_NODEVICE = range(6)
+POT_EXTERNAL, POT_HARMONIC, POT_H2O_PS, POT_MORSE1D, POT_NN_H4O2 = range(5)
+TRIAL_NONE, TRIAL_HARM1D, TRIAL_H2O_FD = range(3)
+WEIGHT_DISCRETE, WEIGHT_CONTINUOUS = 0, 1
+RNG_FP64, RNG_FAST = 0, 1
+MAX_ATOMS, MAX_COMP, MAX_WORLD = 16, 48, 8
+NSUMS = 8 + 4 * MAX_WORLD
+
+
+class PvdError(RuntimeError):
+    pass
+
+
+class MassiveEvent(ValueError):
+    """Same exception type and text as the reference's population guard (pyvibdmc.py:400,413,717)."""
+
+
+class PvdConfig(C.Structure):
+    _fields_ = [("natoms", C.c_int32), ("ndim", C.c_int32), ("weighting", C.c_int32), ("potential", C.c_int32),
+                ("trial", C.c_int32), ("rng_mode", C.c_int32), ("device", C.c_int32), ("rank", C.c_int32),
+                ("world_size", C.c_int32), ("num_walkers", C.c_int64), ("capacity", C.c_int64),
+                ("delta_t", C.c_double), ("alpha", C.c_double), ("thresh_lower", C.c_double),
+                ("thresh_upper", C.c_double), ("seed", C.c_uint64), ("masses", C.c_double * MAX_ATOMS),
+                ("pot_params", C.c_double * MAX_COMP), ("stats_ring", C.c_int64)]
+
+
+class StepStats(C.Structure):
+    _fields_ = [("vref", C.c_double), ("pop", C.c_double), ("v_avg", C.c_double), ("v_max", C.c_double),
+                ("v_min", C.c_double), ("w_max", C.c_double), ("w_min", C.c_double), ("dt_eff", C.c_double),
+                ("births", C.c_int64), ("deaths", C.c_int64), ("rejected", C.c_int64), ("step", C.c_int64)]
+
+
+STATS_DTYPE = np.dtype([("vref", "f8"), ("pop", "f8"), ("v_avg", "f8"), ("v_max", "f8"), ("v_min", "f8"),
+                        ("w_max", "f8"), ("w_min", "f8"), ("dt_eff", "f8"), ("births", "i8"), ("deaths", "i8"),
+                        ("rejected", "i8"), ("step", "i8")])
+assert STATS_DTYPE.itemsize == C.sizeof(StepStats)
+
+_P = C.c_void_p
+_I64, _I32, _F64, _U64 = C.c_int64, C.c_int32, C.c_double, C.c_uint64
+
+# name -> (restype, argtypes); must list every function declared in include/pvd_b200.h
+SIGNATURES = {
+    "pvd_abi_version": (C.c_int, []),
+    "pvd_last_error": (C.c_char_p, []),
+    "pvd_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "pvd_set_device": (C.c_int, [C.c_int]),
+    "pvd_measure_fp64_peak": (C.c_int, [C.POINTER(_F64)]),
+    "pvd_last_kernel_ms": (C.c_int, [C.POINTER(_F64)]),
+    "pvd_launch_count": (_I64, []),
+    "pvd_pes_h2o": (C.c_int, [_P, _I64, _P]),
+    "pvd_pes_h2o_params": (C.c_int, [_P, _P]),
+    "pvd_pes_harmonic": (C.c_int, [_P, _I64, _I32, _P, _P]),
+    "pvd_pes_morse1d": (C.c_int, [_P, _I64, _F64, _F64, _P]),
+    "pvd_displace": (C.c_int, [_P, _I64, _I32, _I32, _P, _U64, _U64, _I32]),
+    "pvd_normals": (C.c_int, [_P, _I64, _I32, _U64, _U64, _I32]),
+    "pvd_philox_kat": (C.c_int, [_P, _P, _P]),
+    "pvd_branch_discrete": (C.c_int, [_P, _I64, _F64, _F64, _P, _I64, _P, _P, _I64, _P]),
+    "pvd_branch_continuous": (C.c_int, [_P, _P, _I64, _F64, _F64, _F64, _F64, _P, _P]),
+    "pvd_calc_vref": (C.c_int, [_P, _P, _I64, _I64, _F64, C.POINTER(_F64)]),
+    "pvd_desc_wts": (C.c_int, [_P, _P, _I64, _I64, _P]),
+    "pvd_trial_drift": (C.c_int, [_I32, _P, _I64, _I32, _I32, _P, _I64, _P, _P, _P]),
+    "pvd_metropolis": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _P, _F64, _P]),
+    "pvd_local_kin": (C.c_int, [_P, _I64, _I32, _I32, _P, _P]),
+    "pvd_nn_h4o2_set_weights": (C.c_int, [_P, _I64]),
+    "pvd_nn_h4o2": (C.c_int, [_P, _I64, _P]),
+    "pvd_coulomb_descriptor": (C.c_int, [_P, _I64, _I32, _P, _P]),
+    "pvd_sim_create": (C.c_int, [C.POINTER(PvdConfig), C.POINTER(_P)]),
+    "pvd_sim_destroy": (C.c_int, [_P]),
+    "pvd_sim_set_stream": (C.c_int, [_P, _P]),
+    "pvd_sim_upload": (C.c_int, [_P, _P, _I64, _P]),
+    "pvd_sim_set_pots": (C.c_int, [_P, _P, _I64]),
+    "pvd_sim_init_finalize": (C.c_int, [_P]),
+    "pvd_sim_set_trial_table": (C.c_int, [_P, _P, _I64]),
+    "pvd_sim_set_nn_weights": (C.c_int, [_P, _P, _I64]),
+    "pvd_sim_run": (C.c_int, [_P, _I64, _I32]),
+    "pvd_sim_step_injected": (C.c_int, [_P, _P, _P, _P]),
+    "pvd_sim_ext_move": (C.c_int, [_P, _P, C.POINTER(_I64)]),
+    "pvd_sim_ext_finish": (C.c_int, [_P, _P, _I64, _I32]),
+    "pvd_sim_sums_ptr": (C.c_int, [_P, C.POINTER(_P)]),
+    "pvd_sim_step_local": (C.c_int, [_P, _I32]),
+    "pvd_sim_step_finalize": (C.c_int, [_P]),
+    "pvd_sim_dw_begin": (C.c_int, [_P, _I64]),
+    "pvd_sim_dw_end": (C.c_int, [_P, _P, _I64]),
+    "pvd_sim_dw_parent": (C.c_int, [_P, _P, _P, C.POINTER(_I64)]),
+    "pvd_sim_sync": (C.c_int, [_P]),
+    "pvd_sim_state": (C.c_int, [_P, C.POINTER(_I64), C.POINTER(_F64), C.POINTER(_I64), C.POINTER(_I32)]),
+    "pvd_sim_download": (C.c_int, [_P, _P, _P, _P, _P, _I64, C.POINTER(_I64)]),
+    "pvd_sim_stats": (C.c_int, [_P, _I64, _I64, _P]),
+    "pvd_sim_last_run_ms": (C.c_int, [_P, C.POINTER(_F64)]),
+    "pvd_sim_download_imp": (C.c_int, [_P, _P, _P, _P, _I64]),
+    "pvd_sim_export_tail": (C.c_int, [_P, _I64, _P, _P, _P, _P]),
+    "pvd_sim_import": (C.c_int, [_P, _I64, _P, _P, _P, _P]),
+}
+
+_lib = None
+
+
+def load(rebuild_if_stale=True):
+    """Load (building first if the sources are newer) the in-tree CUDA library."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if rebuild_if_stale and _build.is_stale():
+        try:
+            _build.build_library()
+        except Exception as e:  # no nvcc on the box and no prebuilt library
+            if not os.path.exists(path):
+                raise PvdError(f"libpvd_b200.so is missing and could not be built: {e}") from e
+    if not os.path.exists(path):
+        raise PvdError(f"CUDA extension not found at {path}; run `python -m pyvibdmc_b200.build`")
+    try:
+        handle = C.CDLL(path)
+    except OSError as e:
+        raise PvdError(f"cannot load {path}: {e}") from e
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(handle, name)          # AttributeError here == ABI drift: fail loudly
+        fn.restype, fn.argtypes = res, args
+    if handle.pvd_abi_version() != 1:
+        raise PvdError("libpvd_b200.so ABI version mismatch")
+    _lib = handle
+    return _lib
+
+
+class _Lazy:
+    def __getattr__(self, name):
+        return getattr(load(), name)
+
+
+lib = _Lazy()
+
+
+def last_error():
+    return load().pvd_last_error().decode("utf-8", "replace")
+
+
+def check(rc):
+    """Translate a C-ABI status into the reference's exception behaviour."""
+    if rc == PVD_OK:
+        return
+    msg = last_error()
+    if rc == PVD_E_MASSIVE:
+        raise MassiveEvent(msg)
+    if rc == PVD_E_ARG:
+        raise ValueError(msg)
+    raise PvdError(f"[pvd error {rc}] {msg}")
+
+
+def ptr(a):
+    """Raw pointer of a C-contiguous NumPy array (or None)."""
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"], "array must be C-contiguous"
+    return a.ctypes.data
+
+
+def f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)

@@ -1,0 +1,953 @@
+// libpvd_b200: C-ABI implementation (see include/pvd_b200.h).  sm_100a only.
+#include "pvd_common.cuh"
+#include "pvd_rng.cuh"
+#include "pvd_potentials.cuh"
+#include "pvd_step.cuh"
+#include "pvd_generic.cuh"
+#include "pvd_continuous.cuh"
+#include "pvd_impsamp.cuh"
+#include "pvd_nn.cuh"
+
+#include <mutex>
+
+thread_local std::string g_pvd_err;
+std::atomic<long long> g_pvd_launches{0};
+static thread_local double g_last_kernel_ms = 0.0;
+
+// ---------------------------------------------------------------- small RAII helpers (host)
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t b)
+    {
+        if (p) { cudaFree(p); p = nullptr; }
+        bytes = b;
+        return cudaMalloc(&p, b ? b : 1);
+    }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+struct EventPair {
+    cudaEvent_t a = nullptr, b = nullptr;
+    ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+    cudaError_t init() { cudaError_t e = cudaEventCreate(&a); return e != cudaSuccess ? e : cudaEventCreate(&b); }
+};
+
+static int g_num_sms = 0;
+static std::once_flag g_init_once;
+static cudaError_t g_init_err = cudaSuccess;
+static int g_const_device = -1;
+
+static int ensure_device_ready()
+{
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return pvd_fail(PVD_E_NODEVICE, std::string("no CUDA device available: ") + cudaGetErrorString(e));
+    int dev = 0;
+    PVD_CUDA(cudaGetDevice(&dev));
+    if (g_const_device != dev) {          // constants are per-device (one process per GPU in practice)
+        PVD_CUDA(ps_upload_constants());
+        cudaDeviceProp prop;
+        PVD_CUDA(cudaGetDeviceProperties(&prop, dev));
+        g_num_sms = prop.multiProcessorCount;
+        g_const_device = dev;
+    }
+    return PVD_OK;
+}
+static inline int grid_for(long long n, int per_block, int max_waves = 8)
+{
+    long long g = (n + per_block - 1) / per_block;
+    const long long cap = (long long)(g_num_sms > 0 ? g_num_sms : 148) * max_waves;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+extern "C" {
+
+int pvd_abi_version(void) { return PVD_ABI_VERSION; }
+const char *pvd_last_error(void) { return g_pvd_err.c_str(); }
+int64_t pvd_launch_count(void) { return (int64_t)g_pvd_launches.load(); }
+int pvd_last_kernel_ms(double *ms) { PVD_REQUIRE(ms, "ms is NULL"); *ms = g_last_kernel_ms; return PVD_OK; }
+
+int pvd_device_count(int *count)
+{
+    PVD_REQUIRE(count, "count is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { *count = 0; return pvd_fail(PVD_E_NODEVICE, cudaGetErrorString(e)); }
+    *count = n;
+    return PVD_OK;
+}
+int pvd_set_device(int device)
+{
+    PVD_CUDA(cudaSetDevice(device));
+    return ensure_device_ready();
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------- FP64 peak micro-benchmark
+__global__ void __launch_bounds__(256) k_fp64_peak(double *out, int iters, double seed)
+{
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 0.9999999, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    const double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == 123.456) out[0] = s;     // never true; keeps the chain alive
+}
+
+extern "C" int pvd_measure_fp64_peak(double *flops_per_s)
+{
+    PVD_REQUIRE(flops_per_s, "flops_per_s is NULL");
+    if (int rc = ensure_device_ready()) return rc;
+    DevBuf out;
+    PVD_CUDA(out.alloc(8));
+    EventPair ev;
+    PVD_CUDA(ev.init());
+    const int iters = 1 << 14, blocks = g_num_sms * 8;
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        PVD_CUDA(cudaEventRecord(ev.a));
+        k_fp64_peak<<<blocks, 256>>>(out.as<double>(), iters, 1.0);
+        PVD_CHECK_LAUNCH();
+        PVD_CUDA(cudaEventRecord(ev.b));
+        PVD_CUDA(cudaEventSynchronize(ev.b));
+        float ms = 0;
+        PVD_CUDA(cudaEventElapsedTime(&ms, ev.a, ev.b));
+        const double fl = 2.0 * 8.0 * (double)iters * 256.0 * blocks / (ms * 1e-3);
+        if (rep > 0 && fl > best) best = fl;
+    }
+    *flops_per_s = best;
+    return PVD_OK;
+}
+
+// ---------------------------------------------------------------- stand-alone host entry points
+// Shared pattern: H2D, one kernel timed with events, D2H.
+template <class LaunchFn>
+static int run_host_kernel(const void *hin, size_t in_bytes, void *hout, size_t out_bytes, LaunchFn launch)
+{
+    if (int rc = ensure_device_ready()) return rc;
+    DevBuf din, dout;
+    PVD_CUDA(din.alloc(in_bytes));
+    PVD_CUDA(dout.alloc(out_bytes));
+    EventPair ev;
+    PVD_CUDA(ev.init());
+    if (in_bytes) PVD_CUDA(cudaMemcpy(din.p, hin, in_bytes, cudaMemcpyHostToDevice));
+    PVD_CUDA(cudaEventRecord(ev.a));
+    launch(din.p, dout.p);
+    PVD_CHECK_LAUNCH();
+    PVD_CUDA(cudaEventRecord(ev.b));
+    if (out_bytes) PVD_CUDA(cudaMemcpy(hout, dout.p, out_bytes, cudaMemcpyDeviceToHost));
+    PVD_CUDA(cudaEventSynchronize(ev.b));
+    float ms = 0;
+    PVD_CUDA(cudaEventElapsedTime(&ms, ev.a, ev.b));
+    g_last_kernel_ms = ms;
+    return PVD_OK;
+}
+
+extern "C" {
+
+int pvd_pes_h2o(const double *xyz, int64_t n, double *v)
+{
+    PVD_REQUIRE(n >= 0 && (n == 0 || (xyz && v)), "pvd_pes_h2o: bad arguments");
+    if (n == 0) return ensure_device_ready();
+    PotParamsDev pot{};
+    return run_host_kernel(xyz, (size_t)n * 72, v, (size_t)n * 8, [&](void *in, void *out) {
+        k_pot_aos<PotH2O><<<grid_for(n, PVD_TILE, 16), PVD_TILE>>>((const double *)in, n, (double *)out, pot);
+    });
+}
+
+int pvd_pes_h2o_params(double *c245, double *scal8)
+{
+    PVD_REQUIRE(c245 && scal8, "NULL output");
+    ps_fold_host(c245, scal8);
+    return PVD_OK;
+}
+
+int pvd_pes_harmonic(const double *x, int64_t n, int32_t ncomp, const double *k, double *v)
+{
+    PVD_REQUIRE(n >= 0 && ncomp >= 1 && ncomp <= PVD_MAX_COMP && k && (n == 0 || (x && v)), "pvd_pes_harmonic: bad arguments");
+    if (n == 0) return ensure_device_ready();
+    PotParamsDev pot{};
+    for (int c = 0; c < ncomp; ++c) pot.k[c] = k[c];
+    return run_host_kernel(x, (size_t)n * ncomp * 8, v, (size_t)n * 8, [&](void *in, void *out) {
+        k_pot_harm_rt<<<grid_for(n, 256, 16), 256>>>((const double *)in, n, ncomp, pot, (double *)out);
+    });
+}
+
+int pvd_pes_morse1d(const double *x, int64_t n, double de, double alpha, double *v)
+{
+    PVD_REQUIRE(n >= 0 && (n == 0 || (x && v)), "pvd_pes_morse1d: bad arguments");
+    if (n == 0) return ensure_device_ready();
+    PotParamsDev pot{};
+    pot.k[0] = de;
+    pot.k[1] = alpha;
+    return run_host_kernel(x, (size_t)n * 8, v, (size_t)n * 8, [&](void *in, void *out) {
+        k_pot_aos<PotMorse><<<grid_for(n, PVD_TILE, 16), PVD_TILE>>>((const double *)in, n, (double *)out, pot);
+    });
+}
+
+static int displace_impl(double *xyz, int64_t n, int32_t nc, int32_t ndim, const double *sigma, uint64_t seed, uint64_t step,
+                         int32_t rng_mode, bool normals_only)
+{
+    PVD_REQUIRE(n >= 0 && nc >= 1 && nc <= PVD_MAX_COMP && ndim >= 1 && (n == 0 || xyz), "pvd_displace: bad arguments");
+    PVD_REQUIRE(rng_mode == PVD_RNG_FP64 || rng_mode == PVD_RNG_FAST, "pvd_displace: unknown rng_mode");
+    if (int rc = ensure_device_ready()) return rc;
+    if (n == 0) return PVD_OK;
+    // stage AoS -> SoA (stride n), displace, SoA -> AoS
+    DevBuf aos, soa, zbuf, sig;
+    PVD_CUDA(aos.alloc((size_t)n * nc * 8));
+    PVD_CUDA(soa.alloc((size_t)n * nc * 8));
+    PVD_CUDA(sig.alloc(PVD_MAX_ATOMS * 8));
+    double sg[PVD_MAX_ATOMS];
+    for (int a = 0; a < PVD_MAX_ATOMS; ++a) sg[a] = (sigma && a < (nc + ndim - 1) / ndim) ? sigma[a] : 1.0;
+    PVD_CUDA(cudaMemcpy(sig.p, sg, sizeof(sg), cudaMemcpyHostToDevice));
+    EventPair ev;
+    PVD_CUDA(ev.init());
+    const int g = grid_for(n, 256, 16);
+    if (!normals_only) {
+        PVD_CUDA(cudaMemcpy(aos.p, xyz, (size_t)n * nc * 8, cudaMemcpyHostToDevice));
+        k_aos_to_soa<<<g, 256>>>(aos.as<double>(), soa.as<double>(), n, nc, n);
+        PVD_CHECK_LAUNCH();
+    }
+    PVD_CUDA(cudaEventRecord(ev.a));
+    double *zout = normals_only ? soa.as<double>() : nullptr;
+    if (rng_mode == PVD_RNG_FP64)
+        k_displace_soa<PVD_RNG_FP64><<<g, 256>>>(soa.as<double>(), nullptr, 0, n, (long long)step, n, nc, ndim, seed, nullptr, nullptr,
+                                                 sig.as<double>(), zout);
+    else
+        k_displace_soa<PVD_RNG_FAST><<<g, 256>>>(soa.as<double>(), nullptr, 0, n, (long long)step, n, nc, ndim, seed, nullptr, nullptr,
+                                                 sig.as<double>(), zout);
+    PVD_CHECK_LAUNCH();
+    PVD_CUDA(cudaEventRecord(ev.b));
+    k_soa_to_aos<<<g, 256>>>(soa.as<double>(), aos.as<double>(), n, nc, n);
+    PVD_CHECK_LAUNCH();
+    PVD_CUDA(cudaMemcpy(xyz, aos.p, (size_t)n * nc * 8, cudaMemcpyDeviceToHost));
+    float ms = 0;
+    PVD_CUDA(cudaEventElapsedTime(&ms, ev.a, ev.b));
+    g_last_kernel_ms = ms;
+    return PVD_OK;
+}
+
+int pvd_displace(double *xyz, int64_t n, int32_t natoms, int32_t ndim, const double *sigma, uint64_t seed, uint64_t step,
+                 int32_t rng_mode)
+{
+    PVD_REQUIRE(natoms >= 1 && natoms <= PVD_MAX_ATOMS && sigma, "pvd_displace: bad natoms / sigma");
+    return displace_impl(xyz, n, natoms * ndim, ndim, sigma, seed, step, rng_mode, false);
+}
+int pvd_normals(double *z, int64_t n, int32_t ncomp, uint64_t seed, uint64_t step, int32_t rng_mode)
+{
+    return displace_impl(z, n, ncomp, 1 << 20, nullptr, seed, step, rng_mode, true);
+}
+
+}  // extern "C"
+
+__global__ void k_philox_kat(const unsigned *ctr, const unsigned *key, unsigned *out)
+{
+    const uint4 r = philox4x32_10(make_uint4(ctr[0], ctr[1], ctr[2], ctr[3]), make_uint2(key[0], key[1]));
+    out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+
+extern "C" int pvd_philox_kat(const uint32_t *ctr4, const uint32_t *key2, uint32_t *out4)
+{
+    PVD_REQUIRE(ctr4 && key2 && out4, "NULL argument");
+    if (int rc = ensure_device_ready()) return rc;
+    DevBuf b;
+    PVD_CUDA(b.alloc(40));
+    unsigned h[6] = {ctr4[0], ctr4[1], ctr4[2], ctr4[3], key2[0], key2[1]};
+    PVD_CUDA(cudaMemcpy(b.p, h, 24, cudaMemcpyHostToDevice));
+    k_philox_kat<<<1, 1>>>(b.as<unsigned>(), b.as<unsigned>() + 4, b.as<unsigned>() + 6);
+    PVD_CHECK_LAUNCH();
+    PVD_CUDA(cudaMemcpy(out4, b.as<unsigned>() + 6, 16, cudaMemcpyDeviceToHost));
+    return PVD_OK;
+}
+
+// ---------------------------------------------------------------- the simulation handle
+struct pvd_sim {
+    pvd_config cfg;
+    int nc = 0;
+    long long cap = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    // walker arrays (ping-pong for discrete compaction)
+    DevBuf x[2], v[2], who[2], w, f[2], psi[2], lk[2];
+    DevBuf st, err_accum, status, part, ring, sums, sigma_dev;
+    DevBuf inj_disp, inj_u, inj_um, stage, stage2;   // staging for host<->device transposes / injections
+    DevBuf parent_x, parent_w;
+    DevBuf kill_idx, hist, cand, cont_work;
+    DevBuf trial_table;
+    long long parent_n = 0;
+    long long ntrial = 0;
+    int parity = 0;      // state copy the next enqueued step reads
+    int cur = 0;         // buffer holding the current walkers
+    long long n_uploaded = 0;
+    bool uploaded = false, ext_moved = false;
+    int grid = 1;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    PotParamsDev pot{};
+    double sigma[PVD_MAX_ATOMS]{};
+    double inv_mass[PVD_MAX_ATOMS]{};
+};
+
+static StepArgs make_args(pvd_sim *s, int do_branch)
+{
+    StepArgs a{};
+    const int in = s->cur, out = s->cur ^ 1;
+    a.xin = s->x[in].as<double>();
+    a.xout = s->x[out].as<double>();
+    a.vin = s->v[in].as<double>();
+    a.vout = s->v[out].as<double>();
+    a.who_in = s->who[in].as<int>();
+    a.who_out = s->who[out].as<int>();
+    a.w = s->w.as<double>();
+    if (s->cfg.trial != PVD_TRIAL_NONE) {
+        a.fin = s->f[in].as<double>(); a.fout = s->f[out].as<double>();
+        a.psin = s->psi[in].as<double>(); a.psout = s->psi[out].as<double>();
+        a.lkin = s->lk[in].as<double>(); a.lkout = s->lk[out].as<double>();
+    }
+    a.st = s->st.as<DevState>();
+    a.err_accum = s->err_accum.as<unsigned>();
+    a.status = s->status.as<unsigned long long>();
+    a.part = s->part.as<TilePartial>();
+    a.ring = s->ring.as<pvd_step_stats>();
+    a.ring_len = s->cfg.stats_ring;
+    a.sums = s->sums.as<double>();
+    a.kill_idx = s->kill_idx.as<int>();
+    a.hist = s->hist.as<unsigned>();
+    a.cap = s->cap;
+    a.n0 = s->cfg.num_walkers;
+    a.dt = s->cfg.delta_t;
+    a.alpha = s->cfg.alpha;
+    a.lower = s->cfg.thresh_lower;
+    a.upper = s->cfg.thresh_upper;
+    a.seed = s->cfg.seed;
+    a.parity = s->parity;
+    a.do_branch = do_branch;
+    a.world = s->cfg.world_size;
+    a.rank = s->cfg.rank;
+    a.ndim = s->cfg.ndim;
+    a.nc = s->nc;
+    for (int i = 0; i < PVD_MAX_ATOMS; ++i) a.sigma[i] = s->sigma[i];
+    a.pot = s->pot;
+    return a;
+}
+
+static int cont_enqueue_step(pvd_sim *, StepArgs &);
+static int cont_enqueue_branch_only(pvd_sim *, StepArgs &);
+static int imp_enqueue_step(pvd_sim *, StepArgs &, const double *);
+static int imp_initial_drift(pvd_sim *);
+static int nn_enqueue_discrete_step(pvd_sim *, StepArgs &);
+
+#define SIM_CHECK(s) PVD_REQUIRE((s) != nullptr, "NULL simulation handle")
+#define SIM_DEVICE(s) PVD_CUDA(cudaSetDevice((s)->cfg.device))
+
+// launch the potential of the configured kind on resident SoA walkers -> v[cur]
+static int launch_pot_soa(pvd_sim *s)
+{
+    const int g = s->grid;
+    double *x = s->x[s->cur].as<double>(), *v = s->v[s->cur].as<double>();
+    const DevState *st = s->st.as<DevState>();
+    switch (s->cfg.potential) {
+    case PVD_POT_H2O_PS: k_pot_soa<PotH2O><<<g, PVD_TILE, 0, s->stream>>>(x, st, s->parity, s->cap, v, s->pot); break;
+    case PVD_POT_HARMONIC:
+        if (s->nc == 1) k_pot_soa<PotHarm<1>><<<g, PVD_TILE, 0, s->stream>>>(x, st, s->parity, s->cap, v, s->pot);
+        else if (s->nc == 3) k_pot_soa<PotHarm<3>><<<g, PVD_TILE, 0, s->stream>>>(x, st, s->parity, s->cap, v, s->pot);
+        else return pvd_fail(PVD_E_ARG, "built-in harmonic potential supports 1 or 3 components");
+        break;
+    case PVD_POT_MORSE1D: k_pot_soa<PotMorse><<<g, PVD_TILE, 0, s->stream>>>(x, st, s->parity, s->cap, v, s->pot); break;
+    case PVD_POT_NN_H4O2: return nn_launch_soa(s->stream, x, st, s->parity, s->cap, v, g);
+    default: return pvd_fail(PVD_E_STATE, "no built-in potential configured");
+    }
+    PVD_CHECK_LAUNCH();
+    return PVD_OK;
+}
+
+extern "C" {
+
+int pvd_sim_create(const pvd_config *cfg, pvd_sim **out)
+{
+    PVD_REQUIRE(cfg && out, "NULL argument");
+    PVD_REQUIRE(cfg->natoms >= 1 && cfg->natoms <= PVD_MAX_ATOMS && cfg->ndim >= 1 && cfg->ndim <= 3, "bad natoms/ndim");
+    PVD_REQUIRE(cfg->num_walkers >= 1 && cfg->capacity >= 1 && cfg->delta_t > 0, "bad num_walkers/capacity/delta_t");
+    PVD_REQUIRE(cfg->world_size >= 1 && cfg->world_size <= PVD_MAX_WORLD && cfg->rank >= 0 && cfg->rank < cfg->world_size, "bad rank/world_size");
+    PVD_REQUIRE(cfg->weighting == PVD_WEIGHT_DISCRETE || cfg->weighting == PVD_WEIGHT_CONTINUOUS, "bad weighting");
+    PVD_REQUIRE(cfg->stats_ring >= 1, "stats_ring must be >= 1");
+    PVD_CUDA(cudaSetDevice(cfg->device));
+    if (int rc = ensure_device_ready()) return rc;
+    pvd_sim *s = new pvd_sim();
+    s->cfg = *cfg;
+    s->nc = cfg->natoms * cfg->ndim;
+    const int nc = s->nc;
+    if (cfg->potential == PVD_POT_H2O_PS && nc != 9) { delete s; return pvd_fail(PVD_E_ARG, "PS water needs 3 atoms x 3 dims"); }
+    if (cfg->potential == PVD_POT_NN_H4O2 && nc != 18) { delete s; return pvd_fail(PVD_E_ARG, "h4o2 NN needs 6 atoms x 3 dims"); }
+    if (cfg->potential == PVD_POT_MORSE1D && nc != 1) { delete s; return pvd_fail(PVD_E_ARG, "Morse needs 1 component"); }
+    s->cap = (cfg->capacity + 31) / 32 * 32;
+    const long long cap = s->cap;
+    const long long ntiles = (cap + PVD_TILE - 1) / PVD_TILE;
+    for (int a = 0; a < cfg->natoms; ++a) {
+        s->sigma[a] = sqrt(cfg->delta_t / cfg->masses[a]);      // pyvibdmc.py:199
+        s->inv_mass[a] = 1.0 / cfg->masses[a];
+    }
+    for (int c = 0; c < PVD_MAX_COMP; ++c) s->pot.k[c] = cfg->pot_params[c];
+    auto fail = [&](cudaError_t e) { std::string m = cudaGetErrorString(e); delete s; return pvd_fail(PVD_E_CUDA, "pvd_sim_create: " + m); };
+    cudaError_t e;
+#define TRY(x) if ((e = (x)) != cudaSuccess) return fail(e)
+    TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    s->own_stream = true;
+    const bool imp = cfg->trial != PVD_TRIAL_NONE;
+    for (int b = 0; b < 2; ++b) {
+        TRY(s->x[b].alloc((size_t)cap * nc * 8));
+        TRY(s->v[b].alloc((size_t)cap * 8));
+        TRY(s->who[b].alloc((size_t)cap * 4));
+        if (imp) {
+            TRY(s->f[b].alloc((size_t)cap * nc * 8));
+            TRY(s->psi[b].alloc((size_t)cap * 8));
+            TRY(s->lk[b].alloc((size_t)cap * 8));
+        }
+    }
+    if (cfg->weighting == PVD_WEIGHT_CONTINUOUS) {
+        TRY(s->w.alloc((size_t)cap * 8));
+        TRY(s->kill_idx.alloc((size_t)cap * 4));
+        TRY(s->hist.alloc(PVD_HIST_BINS * 4));
+        TRY(cudaMemset(s->hist.p, 0, PVD_HIST_BINS * 4));
+        TRY(s->cand.alloc((size_t)cap * sizeof(ContCand)));
+        TRY(s->cont_work.alloc(sizeof(ContWork)));
+        TRY(cudaMemset(s->cont_work.p, 0, sizeof(ContWork)));
+    }
+    TRY(s->st.alloc(2 * sizeof(DevState)));
+    TRY(cudaMemset(s->st.p, 0, 2 * sizeof(DevState)));
+    TRY(s->err_accum.alloc(4));
+    TRY(cudaMemset(s->err_accum.p, 0, 4));
+    TRY(s->status.alloc((size_t)ntiles * 8));
+    TRY(cudaMemset(s->status.p, 0, (size_t)ntiles * 8));
+    TRY(s->part.alloc((size_t)ntiles * sizeof(TilePartial)));
+    TRY(s->ring.alloc((size_t)cfg->stats_ring * sizeof(pvd_step_stats)));
+    TRY(cudaMemset(s->ring.p, 0, (size_t)cfg->stats_ring * sizeof(pvd_step_stats)));
+    TRY(s->sums.alloc(PVD_NSUMS * 8));
+    TRY(cudaMemset(s->sums.p, 0, PVD_NSUMS * 8));
+    TRY(s->sigma_dev.alloc(PVD_MAX_ATOMS * 8));
+    TRY(cudaMemcpy(s->sigma_dev.p, s->sigma, PVD_MAX_ATOMS * 8, cudaMemcpyHostToDevice));
+    TRY(cudaEventCreate(&s->ev0));
+    TRY(cudaEventCreate(&s->ev1));
+#undef TRY
+    // persistent-style grid: enough CTAs to cover the capacity, at most 8 per SM
+    s->grid = grid_for(cap, PVD_TILE, 8);
+    *out = s;
+    return PVD_OK;
+}
+
+int pvd_sim_destroy(pvd_sim *s)
+{
+    if (!s) return PVD_OK;
+    cudaSetDevice(s->cfg.device);
+    cudaDeviceSynchronize();
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+    return PVD_OK;
+}
+
+int pvd_sim_set_stream(pvd_sim *s, void *cuda_stream)
+{
+    SIM_CHECK(s);
+    SIM_DEVICE(s);
+    PVD_CUDA(cudaStreamSynchronize(s->stream));
+    if (s->own_stream && s->stream) { cudaStreamDestroy(s->stream); s->own_stream = false; }
+    if (cuda_stream) s->stream = (cudaStream_t)cuda_stream;
+    else { PVD_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)); s->own_stream = true; }
+    return PVD_OK;
+}
+
+int pvd_sim_sync(pvd_sim *s)
+{
+    SIM_CHECK(s);
+    SIM_DEVICE(s);
+    PVD_CUDA(cudaStreamSynchronize(s->stream));
+    return PVD_OK;
+}
+
+static int sim_init_sums(pvd_sim *s)
+{
+    const double *w = s->cfg.weighting == PVD_WEIGHT_CONTINUOUS ? s->w.as<double>() : nullptr;
+    k_init_sums<<<1, 1024, 0, s->stream>>>(s->v[s->cur].as<double>(), w, s->st.as<DevState>(), s->parity, 0, s->sums.as<double>(),
+                                           s->cfg.world_size, s->cfg.rank);
+    PVD_CHECK_LAUNCH();
+    return PVD_OK;
+}
+
+int pvd_sim_init_finalize(pvd_sim *s)
+{
+    SIM_CHECK(s);
+    SIM_DEVICE(s);
+    k_init_finalize<<<1, 32, 0, s->stream>>>(s->st.as<DevState>(), s->parity, s->sums.as<double>(), s->cfg.alpha, s->cfg.num_walkers,
+                                             s->cfg.delta_t);
+    PVD_CHECK_LAUNCH();
+    return PVD_OK;
+}
+
+int pvd_sim_upload(pvd_sim *s, const double *xyz, int64_t n, const double *w)
+{
+    SIM_CHECK(s);
+    SIM_DEVICE(s);
+    PVD_REQUIRE(xyz && n >= 1 && n <= s->cap, "pvd_sim_upload: n must be in [1, capacity]");
+    const int nc = s->nc;
+    PVD_CUDA(cudaStreamSynchronize(s->stream));
+    PVD_CUDA(s->stage.alloc((size_t)n * nc * 8));
+    PVD_CUDA(cudaMemcpyAsync(s->stage.p, xyz, (size_t)n * nc * 8, cudaMemcpyHostToDevice, s->stream));
+    s->cur = 0;
+    s->parity = 0;
+    k_aos_to_soa<<<grid_for(n * nc, 256, 16), 256, 0, s->stream>>>(s->stage.as<double>(), s->x[0].as<double>(), n, nc, s->cap);
+    PVD_CHECK_LAUNCH();
+    DevState h[2];
+    memset(h, 0, sizeof(h));
+    h[0].n = n;
+    h[0].dt_eff = s->cfg.delta_t;
+    h[1] = h[0];
+    PVD_CUDA(cudaMemcpyAsync(s->st.p, h, sizeof(h), cudaMemcpyHostToDevice, s->stream));
+    PVD_CUDA(cudaMemsetAsync(s->err_accum.p, 0, 4, s->stream));
+    if (s->cfg.weighting == PVD_WEIGHT_CONTINUOUS) {
+        if (w) PVD_CUDA(cudaMemcpyAsync(s->w.p, w, (size_t)n * 8, cudaMemcpyHostToDevice, s->stream));
+        else {
+            k_fill_double<<<grid_for(n, 256, 16), 256, 0, s->stream>>>(s->w.as<double>(), n, 1.0);
+            PVD_CHECK_LAUNCH();
+        }
+    }
+    PVD_CUDA(cudaStreamSynchronize(s->stream));   // h[] and xyz staging are host stack / caller memory
+    s->n_uploaded = n;
+    s->uploaded = true;
+    s->ext_moved = false;
+    if (s->cfg.potential == PVD_POT_EXTERNAL) return PVD_OK;     // caller continues with pvd_sim_set_pots
+    if (s->cfg.trial != PVD_TRIAL_NONE) {
+        // first-step exception with importance sampling: E_L = V + local kinetic (pyvibdmc.py:763-767)
+        if (int rc = imp_initial_drift(s)) return rc;
+    } else {
+        if (int rc = launch_pot_soa(s)) return rc;
+    }
+    if (int rc = sim_init_sums(s)) return rc;
+    if (s->cfg.world_size == 1) return pvd_sim_init_finalize(s);
+    return PVD_OK;
+}
+
+int pvd_sim_set_pots(pvd_sim *s, const double *v, int64_t n)
+{
+    SIM_CHECK(s);
+    SIM_DEVICE(s);
+    PVD_REQUIRE(s->uploaded && v && n == s->n_uploaded, "pvd_sim_set_pots: call after pvd_sim_upload with the same n");
+    PVD_CUDA(cudaMemcpyAsync(s->v[s->cur].p, v, (size_t)n * 8, cudaMemcpyHostToDevice, s->stream));
+    PVD_CUDA(cudaStreamSynchronize(s->stream));
+    if (int rc = sim_init_sums(s)) return rc;
+    if (s->cfg.world_size == 1) return pvd_sim_init_finalize(s);
+    return PVD_OK;
+}
+
+int pvd_sim_sums_ptr(pvd_sim *s, void **device_ptr)
+{
+    SIM_CHECK(s);
+    PVD_REQUIRE(device_ptr, "NULL argument");
+    *device_ptr = s->sums.p;
+    return PVD_OK;
+}
+
+}  // extern "C"
+
+// one fused step on the stream; `inj` pointers may be null
+static int enqueue_step(pvd_sim *s, int do_branch, const double *inj_disp, const double *inj_u, const double *inj_um)
+{
+    StepArgs a = make_args(s, do_branch);
+    a.inj_disp = inj_disp;
+    a.inj_u = inj_u;
+    const int g = s->grid;
+    const bool cont = s->cfg.weighting == PVD_WEIGHT_CONTINUOUS;
+    const bool fast = s->cfg.rng_mode == PVD_RNG_FAST;
+    if (s->cfg.trial != PVD_TRIAL_NONE) {
+        if (int rc = imp_enqueue_step(s, a, inj_um)) return rc;
+    } else if (cont) {
+        if (int rc = cont_enqueue_step(s, a)) return rc;
+    } else {
+#define LAUNCH_DISC(POT)                                                                            \
+    do {                                                                                            \
+        if (fast) k_step_discrete<POT, PVD_RNG_FAST><<<g, PVD_TILE, 0, s->stream>>>(a);             \
+        else k_step_discrete<POT, PVD_RNG_FP64><<<g, PVD_TILE, 0, s->stream>>>(a);                  \
+    } while (0)
+        switch (s->cfg.potential) {
+        case PVD_POT_H2O_PS: LAUNCH_DISC(PotH2O); break;
+        case PVD_POT_HARMONIC:
+            if (s->nc == 1) LAUNCH_DISC(PotHarm<1>);
+            else if (s->nc == 3) LAUNCH_DISC(PotHarm<3>);
+            else return pvd_fail(PVD_E_ARG, "built-in harmonic potential supports 1 or 3 components");
+            break;
+        case PVD_POT_MORSE1D: LAUNCH_DISC(PotMorse); break;
+        case PVD_POT_NN_H4O2:
+            if (int rc = nn_enqueue_discrete_step(s, a)) return rc;
+            break;
+        default: return pvd_fail(PVD_E_STATE, "pvd_sim_run needs a built-in potential (use the ext_* calls for PVD_POT_EXTERNAL)");
+        }
+#undef LAUNCH_DISC
+        PVD_CHECK_LAUNCH();
+        s->cur ^= 1;
+    }
+    s->parity ^= 1;
+    return PVD_OK;
+}
+
+extern "C" {
+
+int pvd_sim_run(pvd_sim *s, int64_t nsteps, int32_t branch_every)
+{
+    SIM_CHECK(s);
+    SIM_DEVICE(s);
+    PVD_REQUIRE(s->uploaded, "pvd_sim_run: upload walkers first");
+    PVD_REQUIRE(s->cfg.world_size == 1, "pvd_sim_run is single-shard; use step_local/step_finalize for multi-GPU");
+    PVD_REQUIRE(branch_every >= 1, "branch_every must be >= 1");
+    PVD_CUDA(cudaEventRecord(s->ev0, s->stream));
+    for (int64_t k = 0; k < nsteps; ++k) {
+        // host-side step index is only needed for branch_every; the device owns the real counter
+        const int do_branch = (branch_every == 1) ? 1 : -branch_every;   // negative: kernel decides from its step counter
+        if (int rc = enqueue_step(s, do_branch, nullptr, nullptr, nullptr)) return rc;
+    }
+    PVD_CUDA(cudaEventRecord(s->ev1, s->stream));
+    return PVD_OK;
+}
+
+int pvd_sim_last_run_ms(pvd_sim *s, double *ms)
+{
+    SIM_CHECK(s);
+    SIM_DEVICE(s);
+    PVD_REQUIRE(ms, "NULL argument");
+    PVD_CUDA(cudaEventSynchronize(s->ev1));
+    float f = 0;
+    PVD_CUDA(cudaEventElapsedTime(&f, s->ev0, s->ev1));
+    *ms = f;
+    return PVD_OK;
+}
+
+int pvd_sim_step_injected(pvd_sim *s, const double *disp, const double *u_branch, const double *u_metro)
+{
+    SIM_CHECK(s);
+    SIM_DEVICE(s);
+    PVD_REQUIRE(s->uploaded && disp, "pvd_sim_step_injected: upload first / disp required");
+    PVD_CUDA(cudaStreamSynchronize(s->stream));
+    DevState h[2];
+    PVD_CUDA(cudaMemcpy(h, s->st.p, sizeof(h), cudaMemcpyDeviceToHost));
+    const long long n = h[s->parity].n;
+    const int nc = s->nc;
+    if (!s->inj_disp.p) {
+        PVD_CUDA(s->inj_disp.alloc((size_t)s->cap * nc * 8));
+        PVD_CUDA(s->inj_u.alloc((size_t)s->cap * 8));
+        PVD_CUDA(s->inj_um.alloc((size_t)s->cap * 8));
+    }
+    PVD_CUDA(s->stage.alloc((size_t)n * nc * 8));
+    PVD_CUDA(cudaMemcpyAsync(s->stage.p, disp, (size_t)n * nc * 8, cudaMemcpyHostToDevice, s->stream));
+    k_aos_to_soa<<<grid_for(n * nc, 256, 16), 256, 0, s->stream>>>(s->stage.as<double>(), s->inj_disp.as<double>(), n, nc, s->cap);
+    PVD_CHECK_LAUNCH();
+    if (u_branch) PVD_CUDA(cudaMemcpyAsync(s->inj_u.p, u_branch, (size_t)n * 8, cudaMemcpyHostToDevice, s->stream));
+    if (u_metro) PVD_CUDA(cudaMemcpyAsync(s->inj_um.p, u_metro, (size_t)n * 8, cudaMemcpyHostToDevice, s->stream));
+    if (int rc = enqueue_step(s, 1, s->inj_disp.as<double>(), u_branch ? s->inj_u.as<double>() : nullptr,
+                              u_metro ? s->inj_um.as<double>() : nullptr))
+        return rc;
+    PVD_CUDA(cudaStreamSynchronize(s->stream));
+    return PVD_OK;
+}
+
+// ---- external potential: move on the device, V from the caller, weight/branch on the device
+int pvd_sim_ext_move(pvd_sim *s, double *xyz_out, int64_t *n_out)
+{
+    SIM_CHECK(s);
+    SIM_DEVICE(s);
+    PVD_REQUIRE(s->uploaded && xyz_out && n_out, "pvd_sim_ext_move: bad arguments");
+    PVD_REQUIRE(s->cfg.trial == PVD_TRIAL_NONE, "external potentials with built-in importance sampling are not supported");
+    const int nc = s->nc;
+    const int g = s->grid;
+    double *x = s->x[s->cur].as<double>();
+    if (s->cfg.rng_mode == PVD_RNG_FAST)
+        k_displace_soa<PVD_RNG_FAST><<<g, 256, 0, s->stream>>>(x, s->st.as<DevState>(), s->parity, 0, 0, s->cap, nc, s->cfg.ndim,
+                                                              s->cfg.seed, nullptr, nullptr, s->sigma_dev.as<double>(), nullptr);
+    else
+        k_displace_soa<PVD_RNG_FP64><<<g, 256, 0, s->stream>>>(x, s->st.as<DevState>(), s->parity, 0, 0, s->cap, nc, s->cfg.ndim,
+                                                              s->cfg.seed, nullptr, nullptr, s->sigma_dev.as<double>(), nullptr);
+    PVD_CHECK_LAUNCH();
+    DevState h[2];
+    PVD_CUDA(cudaMemcpyAsync(h, s->st.p, sizeof(h), cudaMemcpyDeviceToHost, s->stream));
+    PVD_CUDA(cudaStreamSynchronize(s->stream));
+    const long long n = h[s->parity].n;
+    PVD_CUDA(s->stage.alloc((size_t)n * nc * 8));
+    k_soa_to_aos<<<grid_for(n * nc, 256, 16), 256, 0, s->stream>>>(x, s->stage.as<double>(), n, nc, s->cap);
+    PVD_CHECK_LAUNCH();
+    PVD_CUDA(cudaMemcpyAsync(xyz_out, s->stage.p, (size_t)n * nc * 8, cudaMemcpyDeviceToHost, s->stream));
+    PVD_CUDA(cudaStreamSynchronize(s->stream));
+    *n_out = n;
+    s->ext_moved = true;
+    return PVD_OK;
+}
+
+int pvd_sim_ext_finish(pvd_sim *s, const double *v, int64_t n, int32_t do_branch)
+{
+    SIM_CHECK(s);
+    SIM_DEVICE(s);
+    PVD_REQUIRE(s->ext_moved && v, "pvd_sim_ext_finish: call pvd_sim_ext_move first");
+    PVD_CUDA(cudaMemcpyAsync(s->v[s->cur].p, v, (size_t)n * 8, cudaMemcpyHostToDevice, s->stream));
+    StepArgs a = make_args(s, do_branch);
+    if (s->cfg.weighting == PVD_WEIGHT_CONTINUOUS) {
+        if (int rc = cont_enqueue_branch_only(s, a)) return rc;
+    } else {
+        k_branch_discrete<<<s->grid, PVD_TILE, 0, s->stream>>>(a);
+        PVD_CHECK_LAUNCH();
+        s->cur ^= 1;
+    }
+    s->parity ^= 1;
+    s->ext_moved = false;
+    PVD_CUDA(cudaStreamSynchronize(s->stream));
+    return PVD_OK;
+}
+
+// ---- multi-GPU split step
+int pvd_sim_step_local(pvd_sim *s, int32_t do_branch)
+{
+    SIM_CHECK(s);
+    SIM_DEVICE(s);
+    PVD_REQUIRE(s->uploaded, "upload walkers first");
+    // identical to a fused step; with world_size > 1 the last CTA only publishes the shard's sums
+    return enqueue_step(s, do_branch, nullptr, nullptr, nullptr);
+}
+
+int pvd_sim_step_finalize(pvd_sim *s)
+{
+    SIM_CHECK(s);
+    SIM_DEVICE(s);
+    // enqueue_step already flipped the parity: finalise the step that read parity^1
+    StepArgs a = make_args(s, 1);
+    a.parity = s->parity ^ 1;
+    k_finalize<<<1, 32, 0, s->stream>>>(a, s->cfg.weighting == PVD_WEIGHT_CONTINUOUS ? 1 : 0);
+    PVD_CHECK_LAUNCH();
+    return PVD_OK;
+}
+
+// ---- descendant weighting
+int pvd_sim_dw_begin(pvd_sim *s, int64_t global_offset)
+{
+    SIM_CHECK(s);
+    SIM_DEVICE(s);
+    PVD_REQUIRE(s->uploaded, "upload walkers first");
+    // _parent = copy(coords), _parent_wts = copy(w), who_from = arange(N), _desc_wt = True (pyvibdmc.py:739-745)
+    PVD_CUDA(cudaStreamSynchronize(s->stream));
+    DevState h[2];
+    PVD_CUDA(cudaMemcpy(h, s->st.p, sizeof(h), cudaMemcpyDeviceToHost));
+    const long long n = h[s->parity].n;
+    s->parent_n = n;
+    PVD_CUDA(s->parent_x.alloc((size_t)s->cap * s->nc * 8));
+    PVD_CUDA(cudaMemcpyAsync(s->parent_x.p, s->x[s->cur].p, (size_t)s->cap * s->nc * 8, cudaMemcpyDeviceToDevice, s->stream));
+    if (s->cfg.weighting == PVD_WEIGHT_CONTINUOUS) {
+        PVD_CUDA(s->parent_w.alloc((size_t)s->cap * 8));
+        PVD_CUDA(cudaMemcpyAsync(s->parent_w.p, s->w.p, (size_t)n * 8, cudaMemcpyDeviceToDevice, s->stream));
+    }
+    k_iota_int<<<grid_for(n, 256, 16), 256, 0, s->stream>>>(s->who[s->cur].as<int>(), n, (int)global_offset);
+    PVD_CHECK_LAUNCH();
+    h[0].dw_active = 1;
+    h[1].dw_active = 1;
+    PVD_CUDA(cudaMemcpyAsync(s->st.p, h, sizeof(h), cudaMemcpyHostToDevice, s->stream));
+    PVD_CUDA(cudaStreamSynchronize(s->stream));
+    return PVD_OK;
+}
+
+int pvd_sim_dw_end(pvd_sim *s, double *desc_wts, int64_t n_parent)
+{
+    SIM_CHECK(s);
+    SIM_DEVICE(s);
+    PVD_REQUIRE(desc_wts && n_parent >= 1, "bad arguments");
+    PVD_CUDA(cudaStreamSynchronize(s->stream));
+    DevState h[2];
+    PVD_CUDA(cudaMemcpy(h, s->st.p, sizeof(h), cudaMemcpyDeviceToHost));
+    PVD_REQUIRE(h[s->parity].dw_active, "no descendant-weighting window is open");
+    PVD_CUDA(s->stage2.alloc((size_t)n_parent * 8));
+    PVD_CUDA(cudaMemsetAsync(s->stage2.p, 0, (size_t)n_parent * 8, s->stream));
+    const double *w = s->cfg.weighting == PVD_WEIGHT_CONTINUOUS ? s->w.as<double>() : nullptr;
+    k_desc_wts<<<s->grid, 256, 0, s->stream>>>(s->who[s->cur].as<int>(), w, s->st.as<DevState>(), s->parity, 0, 0, n_parent,
+                                               s->stage2.as<double>());
+    PVD_CHECK_LAUNCH();
+    PVD_CUDA(cudaMemcpyAsync(desc_wts, s->stage2.p, (size_t)n_parent * 8, cudaMemcpyDeviceToHost, s->stream));
+    h[0].dw_active = 0;
+    h[1].dw_active = 0;
+    PVD_CUDA(cudaStreamSynchronize(s->stream));
+    PVD_CUDA(cudaMemcpy(s->st.p, h, sizeof(h), cudaMemcpyHostToDevice));
+    return PVD_OK;
+}
+
+int pvd_sim_dw_parent(pvd_sim *s, double *xyz, double *w, int64_t *n_parent)
+{
+    SIM_CHECK(s);
+    SIM_DEVICE(s);
+    PVD_REQUIRE(n_parent, "NULL argument");
+    *n_parent = s->parent_n;
+    if (!xyz) return PVD_OK;
+    PVD_REQUIRE(s->parent_x.p, "no parent ensemble stored");
+    const long long n = s->parent_n;
+    PVD_CUDA(s->stage.alloc((size_t)n * s->nc * 8));
+    k_soa_to_aos<<<grid_for(n * s->nc, 256, 16), 256, 0, s->stream>>>(s->parent_x.as<double>(), s->stage.as<double>(), n, s->nc, s->cap);
+    PVD_CHECK_LAUNCH();
+    PVD_CUDA(cudaMemcpyAsync(xyz, s->stage.p, (size_t)n * s->nc * 8, cudaMemcpyDeviceToHost, s->stream));
+    if (w && s->parent_w.p) PVD_CUDA(cudaMemcpyAsync(w, s->parent_w.p, (size_t)n * 8, cudaMemcpyDeviceToHost, s->stream));
+    PVD_CUDA(cudaStreamSynchronize(s->stream));
+    return PVD_OK;
+}
+
+// ---- queries
+int pvd_sim_state(pvd_sim *s, int64_t *n, double *vref, int64_t *step, int32_t *err)
+{
+    SIM_CHECK(s);
+    SIM_DEVICE(s);
+    PVD_CUDA(cudaStreamSynchronize(s->stream));
+    DevState h[2];
+    PVD_CUDA(cudaMemcpy(h, s->st.p, sizeof(h), cudaMemcpyDeviceToHost));
+    const DevState &c = h[s->parity];
+    if (n) *n = c.n;
+    if (vref) *vref = c.vref;
+    if (step) *step = c.step;
+    if (err) *err = (int32_t)c.err;
+    if (c.err & (PVD_ERR_WEIGHT | PVD_ERR_POP | PVD_ERR_EMPTY)) return pvd_fail(PVD_E_MASSIVE, PVD_MASSIVE_MSG);
+    if (c.err & PVD_ERR_CAPACITY) return pvd_fail(PVD_E_MASSIVE, std::string(PVD_MASSIVE_MSG) + " (shard capacity exceeded)");
+    return PVD_OK;
+}
+
+int pvd_sim_download(pvd_sim *s, double *xyz, double *pots, double *w, int64_t *who_from, int64_t capacity, int64_t *n_out)
+{
+    SIM_CHECK(s);
+    SIM_DEVICE(s);
+    PVD_CUDA(cudaStreamSynchronize(s->stream));
+    DevState h[2];
+    PVD_CUDA(cudaMemcpy(h, s->st.p, sizeof(h), cudaMemcpyDeviceToHost));
+    const long long n = h[s->parity].n;
+    if (n_out) *n_out = n;
+    PVD_REQUIRE(capacity >= n || (!xyz && !pots && !w && !who_from), "pvd_sim_download: host buffers too small");
+    const int nc = s->nc;
+    if (xyz) {
+        PVD_CUDA(s->stage.alloc((size_t)n * nc * 8));
+        k_soa_to_aos<<<grid_for(n * nc, 256, 16), 256, 0, s->stream>>>(s->x[s->cur].as<double>(), s->stage.as<double>(), n, nc, s->cap);
+        PVD_CHECK_LAUNCH();
+        PVD_CUDA(cudaMemcpyAsync(xyz, s->stage.p, (size_t)n * nc * 8, cudaMemcpyDeviceToHost, s->stream));
+    }
+    if (pots) PVD_CUDA(cudaMemcpyAsync(pots, s->v[s->cur].p, (size_t)n * 8, cudaMemcpyDeviceToHost, s->stream));
+    if (w && s->w.p) PVD_CUDA(cudaMemcpyAsync(w, s->w.p, (size_t)n * 8, cudaMemcpyDeviceToHost, s->stream));
+    if (who_from) {
+        PVD_CUDA(s->stage2.alloc((size_t)n * 8));
+        k_int_to_i64<<<grid_for(n, 256, 16), 256, 0, s->stream>>>(s->who[s->cur].as<int>(), s->stage2.as<long long>(), n);
+        PVD_CHECK_LAUNCH();
+        PVD_CUDA(cudaMemcpyAsync(who_from, s->stage2.p, (size_t)n * 8, cudaMemcpyDeviceToHost, s->stream));
+    }
+    PVD_CUDA(cudaStreamSynchronize(s->stream));
+    return PVD_OK;
+}
+
+int pvd_sim_stats(pvd_sim *s, int64_t first_step, int64_t count, pvd_step_stats *out)
+{
+    SIM_CHECK(s);
+    SIM_DEVICE(s);
+    PVD_REQUIRE(out && count >= 0 && count <= s->cfg.stats_ring && first_step >= 0, "pvd_sim_stats: bad range");
+    PVD_CUDA(cudaStreamSynchronize(s->stream));
+    const long long L = s->cfg.stats_ring;
+    long long done = 0;
+    while (done < count) {
+        const long long pos = (first_step + done) % L;
+        const long long chunk = (count - done < L - pos) ? count - done : L - pos;
+        PVD_CUDA(cudaMemcpy(out + done, s->ring.as<pvd_step_stats>() + pos, (size_t)chunk * sizeof(pvd_step_stats), cudaMemcpyDeviceToHost));
+        done += chunk;
+    }
+    return PVD_OK;
+}
+
+// ---- stand-alone discrete branching (injection mode) built on the branch-only kernel
+int pvd_branch_discrete(const double *v, int64_t n, double vref, double dt, const double *u, int64_t n0, int32_t *counts,
+                        int64_t *idx, int64_t idx_capacity, int64_t *stats3)
+{
+    PVD_REQUIRE(v && u && n >= 1 && n0 >= 1 && stats3, "pvd_branch_discrete: bad arguments");
+    if (int rc = ensure_device_ready()) return rc;
+    const long long cap = ((idx_capacity > n ? idx_capacity : n) + 31) / 32 * 32;
+    const long long ntiles = (n + PVD_TILE - 1) / PVD_TILE;
+    DevBuf dv, du, dst, derr, dstatus, dpart, dring, dsums, dcounts, didx;
+    PVD_CUDA(dv.alloc((size_t)n * 8)); PVD_CUDA(du.alloc((size_t)n * 8));
+    PVD_CUDA(dst.alloc(2 * sizeof(DevState))); PVD_CUDA(derr.alloc(4));
+    PVD_CUDA(dstatus.alloc((size_t)ntiles * 8)); PVD_CUDA(dpart.alloc((size_t)ntiles * sizeof(TilePartial)));
+    PVD_CUDA(dring.alloc(sizeof(pvd_step_stats))); PVD_CUDA(dsums.alloc(PVD_NSUMS * 8));
+    PVD_CUDA(dcounts.alloc((size_t)n * 4)); PVD_CUDA(didx.alloc((size_t)cap * 8));
+    PVD_CUDA(cudaMemcpy(dv.p, v, (size_t)n * 8, cudaMemcpyHostToDevice));
+    PVD_CUDA(cudaMemcpy(du.p, u, (size_t)n * 8, cudaMemcpyHostToDevice));
+    PVD_CUDA(cudaMemset(dstatus.p, 0, (size_t)ntiles * 8));
+    PVD_CUDA(cudaMemset(derr.p, 0, 4));
+    DevState h[2];
+    memset(h, 0, sizeof(h));
+    h[0].n = n; h[0].vref = vref; h[0].dt_eff = dt;
+    PVD_CUDA(cudaMemcpy(dst.p, h, sizeof(h), cudaMemcpyHostToDevice));
+    StepArgs a{};
+    a.vin = dv.as<double>();
+    a.st = dst.as<DevState>(); a.err_accum = derr.as<unsigned>(); a.status = dstatus.as<unsigned long long>();
+    a.part = dpart.as<TilePartial>(); a.ring = dring.as<pvd_step_stats>(); a.ring_len = 1; a.sums = dsums.as<double>();
+    a.inj_u = du.as<double>(); a.counts_out = dcounts.as<int>(); a.idx_out = didx.as<long long>();
+    a.cap = cap; a.n0 = n0; a.dt = dt; a.alpha = 1.0 / (2.0 * dt); a.parity = 0; a.do_branch = 1; a.world = 1; a.rank = 0; a.nc = 0; a.ndim = 1;
+    EventPair ev;
+    PVD_CUDA(ev.init());
+    PVD_CUDA(cudaEventRecord(ev.a));
+    k_branch_discrete<<<grid_for(n, PVD_TILE, 8), PVD_TILE>>>(a);
+    PVD_CHECK_LAUNCH();
+    PVD_CUDA(cudaEventRecord(ev.b));
+    PVD_CUDA(cudaMemcpy(h, dst.p, sizeof(h), cudaMemcpyDeviceToHost));
+    pvd_step_stats r;
+    PVD_CUDA(cudaMemcpy(&r, dring.p, sizeof(r), cudaMemcpyDeviceToHost));
+    float ms = 0;
+    PVD_CUDA(cudaEventElapsedTime(&ms, ev.a, ev.b));
+    g_last_kernel_ms = ms;
+    stats3[0] = r.births; stats3[1] = r.deaths; stats3[2] = (int64_t)r.pop;
+    if (counts) PVD_CUDA(cudaMemcpy(counts, dcounts.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    if (h[1].err) return pvd_fail(PVD_E_MASSIVE, PVD_MASSIVE_MSG);
+    if (idx) {
+        PVD_REQUIRE(idx_capacity >= h[1].n, "pvd_branch_discrete: idx buffer too small");
+        PVD_CUDA(cudaMemcpy(idx, didx.p, (size_t)h[1].n * 8, cudaMemcpyDeviceToHost));
+    }
+    return PVD_OK;
+}
+
+int pvd_calc_vref(const double *v, const double *w, int64_t n, int64_t n0, double alpha, double *vref)
+{
+    PVD_REQUIRE(v && vref && n >= 1 && n0 >= 1, "pvd_calc_vref: bad arguments");
+    if (int rc = ensure_device_ready()) return rc;
+    DevBuf dv, dw, dst, dsums;
+    PVD_CUDA(dv.alloc((size_t)n * 8));
+    PVD_CUDA(cudaMemcpy(dv.p, v, (size_t)n * 8, cudaMemcpyHostToDevice));
+    if (w) { PVD_CUDA(dw.alloc((size_t)n * 8)); PVD_CUDA(cudaMemcpy(dw.p, w, (size_t)n * 8, cudaMemcpyHostToDevice)); }
+    PVD_CUDA(dst.alloc(2 * sizeof(DevState)));
+    PVD_CUDA(dsums.alloc(PVD_NSUMS * 8));
+    k_init_sums<<<1, 1024>>>(dv.as<double>(), w ? dw.as<double>() : nullptr, nullptr, 0, n, dsums.as<double>(), 1, 0);
+    PVD_CHECK_LAUNCH();
+    k_init_finalize<<<1, 32>>>(dst.as<DevState>(), 0, dsums.as<double>(), alpha, n0, 1.0);
+    PVD_CHECK_LAUNCH();
+    DevState h;
+    PVD_CUDA(cudaMemcpy(&h, dst.p, sizeof(h), cudaMemcpyDeviceToHost));
+    *vref = h.vref;
+    return PVD_OK;
+}
+
+int pvd_desc_wts(const int64_t *who_from, const double *w, int64_t n, int64_t n_parent, double *out)
+{
+    PVD_REQUIRE(who_from && out && n >= 0 && n_parent >= 1, "pvd_desc_wts: bad arguments");
+    if (int rc = ensure_device_ready()) return rc;
+    std::vector<int> who32((size_t)n);
+    for (int64_t i = 0; i < n; ++i) who32[(size_t)i] = (int)who_from[i];
+    DevBuf dwho, dw, dout;
+    PVD_CUDA(dwho.alloc((size_t)n * 4));
+    PVD_CUDA(cudaMemcpy(dwho.p, who32.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
+    if (w) { PVD_CUDA(dw.alloc((size_t)n * 8)); PVD_CUDA(cudaMemcpy(dw.p, w, (size_t)n * 8, cudaMemcpyHostToDevice)); }
+    PVD_CUDA(dout.alloc((size_t)n_parent * 8));
+    PVD_CUDA(cudaMemset(dout.p, 0, (size_t)n_parent * 8));
+    k_desc_wts<<<grid_for(n, 256, 16), 256>>>(dwho.as<int>(), w ? dw.as<double>() : nullptr, nullptr, 0, n, 0, n_parent, dout.as<double>());
+    PVD_CHECK_LAUNCH();
+    PVD_CUDA(cudaMemcpy(out, dout.p, (size_t)n_parent * 8, cudaMemcpyDeviceToHost));
+    return PVD_OK;
+}
+
+}  // extern "C"
+
+#include "pvd_api_tail.inl"

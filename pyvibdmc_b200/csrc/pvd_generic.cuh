@@ -1,0 +1,293 @@
+// Layout-generic kernels: AoS<->SoA transposes, stand-alone potential / displacement kernels,
+// and the branch-only step (used when V does not come from the fused producer: external Python
+// potentials, importance sampling, the stand-alone pvd_branch_discrete entry point).
+#pragma once
+#include "pvd_step.cuh"
+
+// ---------------------------------------------------------------- layout
+// host arrays are (n, nc) row-major ("AoS"); device walkers are SoA with stride cap.
+__global__ void k_aos_to_soa(const double *__restrict__ aos, double *__restrict__ soa, long long n, int nc, long long cap)
+{
+    const long long total = n * nc;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const long long i = t / nc;
+        const int c = (int)(t - i * nc);
+        soa[c * cap + i] = aos[t];          // coalesced read; writes are nc interleaved streams
+    }
+}
+__global__ void k_soa_to_aos(const double *__restrict__ soa, double *__restrict__ aos, long long n, int nc, long long cap)
+{
+    const long long total = n * nc;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const long long i = t / nc;
+        const int c = (int)(t - i * nc);
+        aos[t] = soa[c * cap + i];
+    }
+}
+__global__ void k_iota_int(int *p, long long n, int offset)
+{
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x)
+        p[t] = offset + (int)t;
+}
+__global__ void k_int_to_i64(const int *in, long long *out, long long n)
+{
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x)
+        out[t] = in[t];
+}
+__global__ void k_fill_double(double *p, long long n, double v)
+{
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x)
+        p[t] = v;
+}
+
+// ---------------------------------------------------------------- stand-alone potential on an AoS batch
+// One thread per walker.  The (n, NC) tile of a CTA is staged through shared memory with
+// coalesced loads; each thread then reads its own NC values (stride NC doubles: conflict-free
+// for odd NC).
+template <class POT>
+__global__ void __launch_bounds__(PVD_TILE) k_pot_aos(const double *__restrict__ aos, long long n, double *__restrict__ v,
+                                                      const PotParamsDev pot)
+{
+    constexpr int NC = POT::NC;
+    __shared__ double tile[PVD_TILE * NC];
+    for (long long base = (long long)blockIdx.x * PVD_TILE; base < n; base += (long long)gridDim.x * PVD_TILE) {
+        const long long rem = n - base;
+        const int cnt = (int)(rem < PVD_TILE ? rem : PVD_TILE);
+        const double *src = aos + base * NC;
+        for (int t = threadIdx.x; t < cnt * NC; t += PVD_TILE) tile[t] = __ldcs(&src[t]);
+        __syncthreads();
+        if ((int)threadIdx.x < cnt) {
+            double x[NC];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) x[c] = tile[threadIdx.x * NC + c];
+            v[base + threadIdx.x] = POT::eval(x, pot);
+        }
+        __syncthreads();
+    }
+}
+
+// potential on resident SoA walkers (start ensemble, first-step exception pyvibdmc.py:760-762)
+template <class POT>
+__global__ void __launch_bounds__(PVD_TILE) k_pot_soa(const double *__restrict__ x_soa, const DevState *st, int parity,
+                                                      long long cap, double *__restrict__ v, const PotParamsDev pot)
+{
+    constexpr int NC = POT::NC;
+    const long long n = st[parity].n;
+    for (long long i = blockIdx.x * (long long)PVD_TILE + threadIdx.x; i < n; i += (long long)gridDim.x * PVD_TILE) {
+        double x[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) x[c] = x_soa[c * cap + i];
+        v[i] = POT::eval(x, pot);
+    }
+}
+
+// harmonic potential with a run-time number of components (plug-in entry point pvd_pes_harmonic)
+__global__ void k_pot_harm_rt(const double *__restrict__ aos, long long n, int nc, const PotParamsDev pot, double *__restrict__ v)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        double acc = __dmul_rn(pot.k[0], __dmul_rn(aos[i * nc], aos[i * nc]));
+        for (int c = 1; c < nc; ++c) {
+            const double x = aos[i * nc + c];
+            acc = __dadd_rn(acc, __dmul_rn(pot.k[c], __dmul_rn(x, x)));
+        }
+        v[i] = acc;
+    }
+}
+
+// ---------------------------------------------------------------- displacement (move_randomly, pyvibdmc.py:540-547)
+// Generic in the number of components: normals are generated pairwise per walker exactly as in
+// walker_normals<>, so the fused kernels and this kernel produce identical streams.
+template <int RNG>
+__global__ void k_displace_soa(double *__restrict__ x, const DevState *st, int parity, long long n_fixed, long long step_fixed,
+                               long long cap, int nc, int ndim, unsigned long long seed, const double *__restrict__ inj_disp,
+                               const StepArgs *sig_src, const double *__restrict__ sigma_dev, double *__restrict__ z_out)
+{
+    (void)sig_src;
+    const long long n = st ? st[parity].n : n_fixed;
+    const long long step = st ? st[parity].step : step_fixed;
+    if (st && st[parity].err) return;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        for (int k = 0; k < (nc + 1) / 2; ++k) {
+            double z0, z1;
+            if (inj_disp) {
+                z0 = inj_disp[(2 * k) * cap + i];
+                z1 = (2 * k + 1 < nc) ? inj_disp[(2 * k + 1) * cap + i] : 0.0;
+            } else {
+                normal_pair<RNG>(pvd_draw(seed, i, step, PVD_STREAM_DISP, (unsigned)k), z0, z1);
+                z0 = __dmul_rn(sigma_dev[(2 * k) / ndim], z0);
+                if (2 * k + 1 < nc) z1 = __dmul_rn(sigma_dev[(2 * k + 1) / ndim], z1);
+            }
+            if (z_out) {
+                z_out[(2 * k) * cap + i] = z0;
+                if (2 * k + 1 < nc) z_out[(2 * k + 1) * cap + i] = z1;
+            } else {
+                x[(2 * k) * cap + i] = __dadd_rn(x[(2 * k) * cap + i], z0);
+                if (2 * k + 1 < nc) x[(2 * k + 1) * cap + i] = __dadd_rn(x[(2 * k + 1) * cap + i], z1);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- branch-only discrete step
+// Same counting / chained scan / compaction / finalisation as k_step_discrete, but the energies
+// come from memory (a.vin) and every per-walker array is copied memory->memory with a run-time
+// number of components.  dt comes from the device state (importance sampling scales it).
+__global__ void __launch_bounds__(PVD_TILE) k_branch_discrete(const StepArgs a)
+{
+    __shared__ int s_scan[PVD_WARPS + 1];
+    __shared__ long long s_prefix;
+    __shared__ int s_tile;
+    __shared__ int s_last;
+    __shared__ double s_red[11 * PVD_WARPS];
+
+    DevState *sip = &a.st[a.parity];
+    const long long n = sip->n, step = sip->step;
+    const double vref = sip->vref, dt = sip->dt_eff;
+    if (sip->err) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) forward_dead_state(a);
+        return;
+    }
+    if (n <= 0) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) { forward_dead_state(a); a.st[a.parity ^ 1].err |= PVD_ERR_EMPTY; }
+        return;
+    }
+    const int ntiles = (int)((n + PVD_TILE - 1) / PVD_TILE);
+    const bool dw = sip->dw_active != 0;
+    const double n0 = (double)a.n0;
+    const double w_limit = (n0 + n0 * 0.5) + 1.0;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    // branch_every (pyvibdmc.py:139,828): do_branch > 0 always, < 0 every |do_branch| steps, 0 never
+    const bool branch_now = a.do_branch > 0 || (a.do_branch < 0 && (step % (long long)(-a.do_branch)) == 0);
+
+    while (true) {
+        if (threadIdx.x == 0) s_tile = (int)atomicAdd(&sip->ticket, 1u);
+        __syncthreads();
+        const int tile = s_tile;
+        if (tile >= ntiles) break;
+        const long long i = (long long)tile * PVD_TILE + threadIdx.x;
+        const bool active = i < n;
+        const double v = active ? a.vin[i] : 0.0;
+        int cnt = 0;
+        bool bad = false;
+        if (active) {
+            if (branch_now) {
+                double u;
+                if (a.inj_u) u = a.inj_u[i];
+                else { const uint4 r = pvd_draw(a.seed, i, step, PVD_STREAM_BRANCH, 0u); u = u53(r.x, r.y); }
+                cnt = discrete_count(v, vref, dt, u, w_limit, bad);
+            } else cnt = 1;
+            if (a.counts_out) a.counts_out[i] = cnt;
+        }
+        if (bad) atomicOr(a.err_accum, PVD_ERR_WEIGHT);
+
+        int tile_total;
+        const int excl = block_excl_scan(cnt, s_scan, &tile_total);
+        const long long prefix = tile_lookback(a.status, tile, step, tile_total, &s_prefix);
+        const long long o = prefix + excl;
+        if (cnt > 0) {
+            if (o + cnt > a.cap) atomicOr(a.err_accum, PVD_ERR_CAPACITY);
+            else {
+                for (int k = 0; k < cnt; ++k) {
+                    for (int c = 0; c < a.nc; ++c) a.xout[c * a.cap + o + k] = a.xin[c * a.cap + i];
+                    if (a.vout) a.vout[o + k] = v;
+                    if (dw) a.who_out[o + k] = a.who_in[i];
+                    if (a.idx_out) a.idx_out[o + k] = i;
+                    if (a.fin) {
+                        for (int c = 0; c < a.nc; ++c) a.fout[c * a.cap + o + k] = a.fin[c * a.cap + i];
+                        a.psout[o + k] = a.psin[i];
+                        a.lkout[o + k] = a.lkin[i];
+                    }
+                }
+            }
+        }
+        double pcv = warp_sum((double)cnt * v), pc = warp_sum((double)cnt), pv = warp_sum(active ? v : 0.0);
+        double pmin = warp_min(active ? v : INFINITY), pmax = warp_max(active ? v : -INFINITY);
+        int pb = warp_sum_i(cnt > 1 ? cnt - 1 : 0), pd = warp_sum_i((active && cnt == 0) ? 1 : 0);
+        if (lane == 0) {
+            s_red[0 * PVD_WARPS + wid] = pcv; s_red[1 * PVD_WARPS + wid] = pc; s_red[2 * PVD_WARPS + wid] = pv;
+            s_red[3 * PVD_WARPS + wid] = pmin; s_red[4 * PVD_WARPS + wid] = pmax;
+            s_red[5 * PVD_WARPS + wid] = (double)pb; s_red[6 * PVD_WARPS + wid] = (double)pd;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t[7];
+            for (int k = 0; k < 7; ++k) {
+                double acc = s_red[k * PVD_WARPS];
+                for (int w = 1; w < PVD_WARPS; ++w) {
+                    const double y = s_red[k * PVD_WARPS + w];
+                    acc = (k == 3) ? fmin(acc, y) : (k == 4 ? fmax(acc, y) : acc + y);
+                }
+                t[k] = acc;
+            }
+            TilePartial p;
+            p.cv = t[0]; p.c = t[1]; p.v = t[2]; p.vmin = t[3]; p.vmax = t[4];
+            p.wmin = INFINITY; p.wmax = -INFINITY;
+            p.births = (int)t[5]; p.deaths = (int)t[6];
+            const long long rem = n - (long long)tile * PVD_TILE;
+            p.n_in = (int)(rem < PVD_TILE ? rem : PVD_TILE);
+            p.n_acc = p.n_in;
+            a.part[tile] = p;
+            __threadfence();
+            const unsigned d = atomicAdd(&sip->done, 1u);
+            s_last = (d == (unsigned)(ntiles - 1)) ? 1 : 0;
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            long long n_new = 0;
+            if (threadIdx.x == 0) n_new = (long long)(ld_relaxed_u64(&a.status[ntiles - 1]) & 0xffffffffull);
+            reduce_partials_and_publish(a, ntiles, n_new, false, s_red);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- first Vref (pyvibdmc.py:760-769) and stand-alone calc_vref
+// single CTA, fixed-order reduction; writes local sums then (world==1) finalises into st[parity]
+// itself (no step advance): used once after upload.
+__global__ void __launch_bounds__(1024) k_init_sums(const double *__restrict__ v, const double *__restrict__ w,
+                                                    const DevState *st, int parity, long long n_fixed, double *sums, int world, int rank)
+{
+    __shared__ double s1[32], s2[32];
+    const long long n = st ? st[parity].n : n_fixed;
+    double a = 0.0, b = 0.0;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+        const double wi = w ? w[i] : 1.0;
+        a += wi * v[i];
+        b += wi;
+    }
+    a = warp_sum(a); b = warp_sum(b);
+    if ((threadIdx.x & 31) == 0) { s1[threadIdx.x >> 5] = a; s2[threadIdx.x >> 5] = b; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double ta = 0, tb = 0;
+        for (int k = 0; k < (int)(blockDim.x >> 5); ++k) { ta += s1[k]; tb += s2[k]; }
+        for (int k = 0; k < PVD_SUM_EXT + 4 * world; ++k) sums[k] = 0.0;
+        sums[PVD_SUM_CV] = ta;
+        sums[PVD_SUM_C] = tb;
+        (void)rank;
+    }
+}
+__global__ void k_init_finalize(DevState *st, int parity, const double *sums, double alpha, long long n0_, double dt)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const double n0 = (double)n0_;
+        const double v_bar = sums[PVD_SUM_CV] / sums[PVD_SUM_C];
+        const double correction = (sums[PVD_SUM_C] - n0) / n0;
+        DevState &s = st[parity];
+        s.vref = v_bar - (alpha * correction);
+        s.pop_global = sums[PVD_SUM_C];
+        s.dt_eff = dt;
+    }
+}
+
+// descendant weights (calc_desc_wts, pyvibdmc.py:663-672): histogram of who_from (discrete) or
+// weight-sum per parent (continuous)
+__global__ void k_desc_wts(const int *__restrict__ who, const double *__restrict__ w, const DevState *st, int parity,
+                           long long n_fixed, int base, long long n_parent, double *__restrict__ out)
+{
+    const long long n = st ? st[parity].n : n_fixed;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long q = (long long)who[i] - base;
+        if (q >= 0 && q < n_parent) atomicAdd(&out[q], w ? w[i] : 1.0);
+    }
+}
