@@ -174,7 +174,8 @@ typedef struct {
 
 int pvd_sim_create(const pvd_config *cfg, pvd_sim **out);
 int pvd_sim_destroy(pvd_sim *s);
-/* use an externally owned stream (e.g. torch.cuda.current_stream().cuda_stream); 0 = own stream */
+/* use an externally owned stream (e.g. torch.cuda.current_stream().cuda_stream); 0 = legacy default stream.
+ * Until this is called the handle runs on its own non-blocking stream. */
 int pvd_sim_set_stream(pvd_sim *s, void *cuda_stream);
 
 /* upload the start ensemble (DMC_Sim._initialize, pyvibdmc.py:155-169,214-219); w may be NULL.
@@ -204,6 +205,8 @@ int pvd_sim_ext_finish(pvd_sim *s, const double *v, int64_t n, int32_t do_branch
 #define PVD_MAX_WORLD 8
 #define PVD_NSUMS (8 + 4 * PVD_MAX_WORLD)
 int pvd_sim_sums_ptr(pvd_sim *s, void **device_ptr);
+/* use a caller-owned device buffer (e.g. a torch tensor NCCL can reduce) of PVD_NSUMS doubles instead */
+int pvd_sim_set_sums_ptr(pvd_sim *s, void *device_ptr);
 int pvd_sim_step_local(pvd_sim *s, int32_t do_branch);
 int pvd_sim_step_finalize(pvd_sim *s);
 

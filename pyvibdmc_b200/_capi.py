@@ -92,6 +92,7 @@ SIGNATURES = {
     "pvd_sim_ext_move": (C.c_int, [_P, _P, C.POINTER(_I64)]),
     "pvd_sim_ext_finish": (C.c_int, [_P, _P, _I64, _I32]),
     "pvd_sim_sums_ptr": (C.c_int, [_P, C.POINTER(_P)]),
+    "pvd_sim_set_sums_ptr": (C.c_int, [_P, _P]),
     "pvd_sim_step_local": (C.c_int, [_P, _I32]),
     "pvd_sim_step_finalize": (C.c_int, [_P]),
     "pvd_sim_dw_begin": (C.c_int, [_P, _I64]),

@@ -158,7 +158,7 @@ int pvd_pes_h2o(const double *xyz, int64_t n, double *v)
     if (n == 0) return ensure_device_ready();
     PotParamsDev pot{};
     return run_host_kernel(xyz, (size_t)n * 72, v, (size_t)n * 8, [&](void *in, void *out) {
-        k_pot_aos<PotH2O><<<grid_for(n, PVD_TILE, 16), PVD_TILE>>>((const double *)in, n, (double *)out, pot);
+        k_pot_aos<PotH2O><<<grid_for(n, PVD_CTA, 16), PVD_CTA>>>((const double *)in, n, (double *)out, pot);
     });
 }
 
@@ -188,7 +188,7 @@ int pvd_pes_morse1d(const double *x, int64_t n, double de, double alpha, double 
     pot.k[0] = de;
     pot.k[1] = alpha;
     return run_host_kernel(x, (size_t)n * 8, v, (size_t)n * 8, [&](void *in, void *out) {
-        k_pot_aos<PotMorse><<<grid_for(n, PVD_TILE, 16), PVD_TILE>>>((const double *)in, n, (double *)out, pot);
+        k_pot_aos<PotMorse><<<grid_for(n, PVD_CTA, 16), PVD_CTA>>>((const double *)in, n, (double *)out, pot);
     });
 }
 
@@ -276,12 +276,13 @@ struct pvd_sim {
     bool own_stream = false;
     // walker arrays (ping-pong for discrete compaction)
     DevBuf x[2], v[2], who[2], w, f[2], psi[2], lk[2];
-    DevBuf st, err_accum, status, part, ring, sums, sigma_dev;
+    DevBuf st, err_accum, status, part, ring, sums, sigma_dev, tickets;
     DevBuf inj_disp, inj_u, inj_um, stage, stage2;   // staging for host<->device transposes / injections
     DevBuf parent_x, parent_w;
     DevBuf kill_idx, hist, cand, cont_work;
     DevBuf trial_table;
     long long parent_n = 0;
+    void *sums_ext = nullptr;   // caller-owned reduction buffer (multi-GPU)
     long long ntrial = 0;
     int parity = 0;      // state copy the next enqueued step reads
     int cur = 0;         // buffer holding the current walkers
@@ -313,10 +314,11 @@ static StepArgs make_args(pvd_sim *s, int do_branch)
     a.st = s->st.as<DevState>();
     a.err_accum = s->err_accum.as<unsigned>();
     a.status = s->status.as<unsigned long long>();
-    a.part = s->part.as<TilePartial>();
+    a.part = s->part.as<WarpPartial>();
+    a.tickets = s->tickets.as<unsigned>();
     a.ring = s->ring.as<pvd_step_stats>();
     a.ring_len = s->cfg.stats_ring;
-    a.sums = s->sums.as<double>();
+    a.sums = s->sums_ext ? (double *)s->sums_ext : s->sums.as<double>();
     a.kill_idx = s->kill_idx.as<int>();
     a.hist = s->hist.as<unsigned>();
     a.cap = s->cap;
@@ -332,6 +334,7 @@ static StepArgs make_args(pvd_sim *s, int do_branch)
     a.rank = s->cfg.rank;
     a.ndim = s->cfg.ndim;
     a.nc = s->nc;
+    a.flip = s->cfg.weighting == PVD_WEIGHT_DISCRETE ? 1 : 0;
     for (int i = 0; i < PVD_MAX_ATOMS; ++i) a.sigma[i] = s->sigma[i];
     a.pot = s->pot;
     return a;
@@ -353,13 +356,13 @@ static int launch_pot_soa(pvd_sim *s)
     double *x = s->x[s->cur].as<double>(), *v = s->v[s->cur].as<double>();
     const DevState *st = s->st.as<DevState>();
     switch (s->cfg.potential) {
-    case PVD_POT_H2O_PS: k_pot_soa<PotH2O><<<g, PVD_TILE, 0, s->stream>>>(x, st, s->parity, s->cap, v, s->pot); break;
+    case PVD_POT_H2O_PS: k_pot_soa<PotH2O><<<g, PVD_CTA, 0, s->stream>>>(x, st, s->parity, s->cap, v, s->pot); break;
     case PVD_POT_HARMONIC:
-        if (s->nc == 1) k_pot_soa<PotHarm<1>><<<g, PVD_TILE, 0, s->stream>>>(x, st, s->parity, s->cap, v, s->pot);
-        else if (s->nc == 3) k_pot_soa<PotHarm<3>><<<g, PVD_TILE, 0, s->stream>>>(x, st, s->parity, s->cap, v, s->pot);
+        if (s->nc == 1) k_pot_soa<PotHarm<1>><<<g, PVD_CTA, 0, s->stream>>>(x, st, s->parity, s->cap, v, s->pot);
+        else if (s->nc == 3) k_pot_soa<PotHarm<3>><<<g, PVD_CTA, 0, s->stream>>>(x, st, s->parity, s->cap, v, s->pot);
         else return pvd_fail(PVD_E_ARG, "built-in harmonic potential supports 1 or 3 components");
         break;
-    case PVD_POT_MORSE1D: k_pot_soa<PotMorse><<<g, PVD_TILE, 0, s->stream>>>(x, st, s->parity, s->cap, v, s->pot); break;
+    case PVD_POT_MORSE1D: k_pot_soa<PotMorse><<<g, PVD_CTA, 0, s->stream>>>(x, st, s->parity, s->cap, v, s->pot); break;
     case PVD_POT_NN_H4O2: return nn_launch_soa(s->stream, x, st, s->parity, s->cap, v, g);
     default: return pvd_fail(PVD_E_STATE, "no built-in potential configured");
     }
@@ -425,7 +428,11 @@ int pvd_sim_create(const pvd_config *cfg, pvd_sim **out)
     TRY(cudaMemset(s->err_accum.p, 0, 4));
     TRY(s->status.alloc((size_t)ntiles * 8));
     TRY(cudaMemset(s->status.p, 0, (size_t)ntiles * 8));
-    TRY(s->part.alloc((size_t)ntiles * sizeof(TilePartial)));
+    // persistent-style grid: enough CTAs to cover the capacity, at most 8 per SM
+    s->grid = grid_for(cap, PVD_CTA, 8);
+    TRY(s->part.alloc((size_t)s->grid * PVD_WARPS * sizeof(WarpPartial)));
+    TRY(s->tickets.alloc(2 * PVD_WARPS * PVD_TICKET_STRIDE * 4));
+    TRY(cudaMemset(s->tickets.p, 0, 2 * PVD_WARPS * PVD_TICKET_STRIDE * 4));
     TRY(s->ring.alloc((size_t)cfg->stats_ring * sizeof(pvd_step_stats)));
     TRY(cudaMemset(s->ring.p, 0, (size_t)cfg->stats_ring * sizeof(pvd_step_stats)));
     TRY(s->sums.alloc(PVD_NSUMS * 8));
@@ -435,8 +442,6 @@ int pvd_sim_create(const pvd_config *cfg, pvd_sim **out)
     TRY(cudaEventCreate(&s->ev0));
     TRY(cudaEventCreate(&s->ev1));
 #undef TRY
-    // persistent-style grid: enough CTAs to cover the capacity, at most 8 per SM
-    s->grid = grid_for(cap, PVD_TILE, 8);
     *out = s;
     return PVD_OK;
 }
@@ -459,8 +464,7 @@ int pvd_sim_set_stream(pvd_sim *s, void *cuda_stream)
     SIM_DEVICE(s);
     PVD_CUDA(cudaStreamSynchronize(s->stream));
     if (s->own_stream && s->stream) { cudaStreamDestroy(s->stream); s->own_stream = false; }
-    if (cuda_stream) s->stream = (cudaStream_t)cuda_stream;
-    else { PVD_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking)); s->own_stream = true; }
+    s->stream = (cudaStream_t)cuda_stream;      // 0 selects the legacy default stream
     return PVD_OK;
 }
 
@@ -475,7 +479,8 @@ int pvd_sim_sync(pvd_sim *s)
 static int sim_init_sums(pvd_sim *s)
 {
     const double *w = s->cfg.weighting == PVD_WEIGHT_CONTINUOUS ? s->w.as<double>() : nullptr;
-    k_init_sums<<<1, 1024, 0, s->stream>>>(s->v[s->cur].as<double>(), w, s->st.as<DevState>(), s->parity, 0, s->sums.as<double>(),
+    k_init_sums<<<1, 1024, 0, s->stream>>>(s->v[s->cur].as<double>(), w, s->st.as<DevState>(), s->parity, 0,
+                                           s->sums_ext ? (double *)s->sums_ext : s->sums.as<double>(),
                                            s->cfg.world_size, s->cfg.rank);
     PVD_CHECK_LAUNCH();
     return PVD_OK;
@@ -485,7 +490,8 @@ int pvd_sim_init_finalize(pvd_sim *s)
 {
     SIM_CHECK(s);
     SIM_DEVICE(s);
-    k_init_finalize<<<1, 32, 0, s->stream>>>(s->st.as<DevState>(), s->parity, s->sums.as<double>(), s->cfg.alpha, s->cfg.num_walkers,
+    k_init_finalize<<<1, 32, 0, s->stream>>>(s->st.as<DevState>(), s->parity,
+                                             s->sums_ext ? (double *)s->sums_ext : s->sums.as<double>(), s->cfg.alpha, s->cfg.num_walkers,
                                              s->cfg.delta_t);
     PVD_CHECK_LAUNCH();
     return PVD_OK;
@@ -550,7 +556,17 @@ int pvd_sim_sums_ptr(pvd_sim *s, void **device_ptr)
 {
     SIM_CHECK(s);
     PVD_REQUIRE(device_ptr, "NULL argument");
-    *device_ptr = s->sums.p;
+    *device_ptr = s->sums_ext ? s->sums_ext : s->sums.p;
+    return PVD_OK;
+}
+
+int pvd_sim_set_sums_ptr(pvd_sim *s, void *device_ptr)
+{
+    SIM_CHECK(s);
+    SIM_DEVICE(s);
+    PVD_CUDA(cudaStreamSynchronize(s->stream));
+    if (device_ptr) PVD_CUDA(cudaMemcpy(device_ptr, s->sums_ext ? s->sums_ext : s->sums.p, PVD_NSUMS * 8, cudaMemcpyDeviceToDevice));
+    s->sums_ext = device_ptr;
     return PVD_OK;
 }
 
@@ -572,8 +588,8 @@ static int enqueue_step(pvd_sim *s, int do_branch, const double *inj_disp, const
     } else {
 #define LAUNCH_DISC(POT)                                                                            \
     do {                                                                                            \
-        if (fast) k_step_discrete<POT, PVD_RNG_FAST><<<g, PVD_TILE, 0, s->stream>>>(a);             \
-        else k_step_discrete<POT, PVD_RNG_FP64><<<g, PVD_TILE, 0, s->stream>>>(a);                  \
+        if (fast) k_step_discrete<POT, PVD_RNG_FAST><<<g, PVD_CTA, 0, s->stream>>>(a);             \
+        else k_step_discrete<POT, PVD_RNG_FP64><<<g, PVD_CTA, 0, s->stream>>>(a);                  \
     } while (0)
         switch (s->cfg.potential) {
         case PVD_POT_H2O_PS: LAUNCH_DISC(PotH2O); break;
@@ -696,7 +712,7 @@ int pvd_sim_ext_finish(pvd_sim *s, const double *v, int64_t n, int32_t do_branch
     if (s->cfg.weighting == PVD_WEIGHT_CONTINUOUS) {
         if (int rc = cont_enqueue_branch_only(s, a)) return rc;
     } else {
-        k_branch_discrete<<<s->grid, PVD_TILE, 0, s->stream>>>(a);
+        k_branch_discrete<<<s->grid, PVD_CTA, 0, s->stream>>>(a);
         PVD_CHECK_LAUNCH();
         s->cur ^= 1;
     }
@@ -825,6 +841,7 @@ int pvd_sim_download(pvd_sim *s, double *xyz, double *pots, double *w, int64_t *
     if (n_out) *n_out = n;
     PVD_REQUIRE(capacity >= n || (!xyz && !pots && !w && !who_from), "pvd_sim_download: host buffers too small");
     const int nc = s->nc;
+    if (h[s->parity].err) s->cur = h[s->parity].buf;      // dead run: the failing step's input buffer is the valid one
     if (xyz) {
         PVD_CUDA(s->stage.alloc((size_t)n * nc * 8));
         k_soa_to_aos<<<grid_for(n * nc, 256, 16), 256, 0, s->stream>>>(s->x[s->cur].as<double>(), s->stage.as<double>(), n, nc, s->cap);
@@ -868,10 +885,13 @@ int pvd_branch_discrete(const double *v, int64_t n, double vref, double dt, cons
     if (int rc = ensure_device_ready()) return rc;
     const long long cap = ((idx_capacity > n ? idx_capacity : n) + 31) / 32 * 32;
     const long long ntiles = (n + PVD_TILE - 1) / PVD_TILE;
-    DevBuf dv, du, dst, derr, dstatus, dpart, dring, dsums, dcounts, didx;
+    DevBuf dv, du, dst, derr, dstatus, dpart, dring, dsums, dcounts, didx, dtick;
+    const int g = grid_for(n, PVD_CTA, 8);
     PVD_CUDA(dv.alloc((size_t)n * 8)); PVD_CUDA(du.alloc((size_t)n * 8));
     PVD_CUDA(dst.alloc(2 * sizeof(DevState))); PVD_CUDA(derr.alloc(4));
-    PVD_CUDA(dstatus.alloc((size_t)ntiles * 8)); PVD_CUDA(dpart.alloc((size_t)ntiles * sizeof(TilePartial)));
+    PVD_CUDA(dstatus.alloc((size_t)ntiles * 8)); PVD_CUDA(dpart.alloc((size_t)g * PVD_WARPS * sizeof(WarpPartial)));
+    PVD_CUDA(dtick.alloc(2 * PVD_WARPS * PVD_TICKET_STRIDE * 4));
+    PVD_CUDA(cudaMemset(dtick.p, 0, 2 * PVD_WARPS * PVD_TICKET_STRIDE * 4));
     PVD_CUDA(dring.alloc(sizeof(pvd_step_stats))); PVD_CUDA(dsums.alloc(PVD_NSUMS * 8));
     PVD_CUDA(dcounts.alloc((size_t)n * 4)); PVD_CUDA(didx.alloc((size_t)cap * 8));
     PVD_CUDA(cudaMemcpy(dv.p, v, (size_t)n * 8, cudaMemcpyHostToDevice));
@@ -885,13 +905,13 @@ int pvd_branch_discrete(const double *v, int64_t n, double vref, double dt, cons
     StepArgs a{};
     a.vin = dv.as<double>();
     a.st = dst.as<DevState>(); a.err_accum = derr.as<unsigned>(); a.status = dstatus.as<unsigned long long>();
-    a.part = dpart.as<TilePartial>(); a.ring = dring.as<pvd_step_stats>(); a.ring_len = 1; a.sums = dsums.as<double>();
+    a.part = dpart.as<WarpPartial>(); a.tickets = dtick.as<unsigned>(); a.ring = dring.as<pvd_step_stats>(); a.ring_len = 1; a.sums = dsums.as<double>();
     a.inj_u = du.as<double>(); a.counts_out = dcounts.as<int>(); a.idx_out = didx.as<long long>();
     a.cap = cap; a.n0 = n0; a.dt = dt; a.alpha = 1.0 / (2.0 * dt); a.parity = 0; a.do_branch = 1; a.world = 1; a.rank = 0; a.nc = 0; a.ndim = 1;
     EventPair ev;
     PVD_CUDA(ev.init());
     PVD_CUDA(cudaEventRecord(ev.a));
-    k_branch_discrete<<<grid_for(n, PVD_TILE, 8), PVD_TILE>>>(a);
+    k_branch_discrete<<<g, PVD_CTA>>>(a);
     PVD_CHECK_LAUNCH();
     PVD_CUDA(cudaEventRecord(ev.b));
     PVD_CUDA(cudaMemcpy(h, dst.p, sizeof(h), cudaMemcpyDeviceToHost));

@@ -43,8 +43,13 @@ static inline int pvd_fail(int code, const std::string &msg)
 static const char *const PVD_MASSIVE_MSG = "Massive walker birth or death event!!!!!!! Dying...";
 
 // ---------------------------------------------------------------- tiling
-constexpr int PVD_TILE = 256;          // walkers per tile == threads per CTA (one walker per thread)
-constexpr int PVD_WARPS = PVD_TILE / 32;
+// A tile is one warp's worth of walkers.  Every warp of the (persistent) grid takes tiles from
+// ticket counters, one counter per warp slot of a CTA so that no single address sees more than
+// 1/PVD_WARPS of the atomics; nothing in the step kernels uses __syncthreads or shared memory.
+constexpr int PVD_TILE = 32;           // walkers per tile == one warp, one walker per lane
+constexpr int PVD_CTA = 256;           // threads per CTA
+constexpr int PVD_WARPS = PVD_CTA / 32;
+constexpr int PVD_TICKET_STRIDE = 32;  // uints between ticket counters (128 B: one per L2 line)
 
 // error bits kept in DevState::err
 enum : unsigned {
@@ -55,7 +60,7 @@ enum : unsigned {
 };
 
 // Device-resident simulation state.  Two copies are kept (index = step parity): the kernel of
-// step s reads st[s&1] and its finalisation writes st[(s+1)&1], so CTAs that start late never
+// step s reads st[s&1] and its finalisation writes st[(s+1)&1], so warps that start late never
 // observe a half-updated state, and the host never has to synchronise between steps.
 struct DevState {
     long long n;            // walkers on this shard
@@ -66,22 +71,84 @@ struct DevState {
     double eff_time;        // accumulated effective time (pyvibdmc.py:372-378)
     unsigned err;
     int dw_active;          // descendant-weighting window open (who_from is carried)
-    unsigned ticket;        // dynamic tile counter of the step that READS this copy
-    unsigned done;          // finished-tile counter of the step that READS this copy
-    long long n_accept;     // imp-samp: accepted moves in the current step (this shard)
-    long long pad;
+    unsigned done;          // finished-warp counter of the step that READS this copy
+    int buf;                // ping-pong buffer that holds the valid walkers (meaningful to the host when err != 0)
+    long long n_accept;     // imp-samp: accepted moves in the current step (global)
+    long long n_kill;       // continuous: walkers below the lower threshold in the current step
 };
 
-// per-tile partial sums, reduced in a fixed order by the last CTA (deterministic Vref)
-struct TilePartial {
-    double cv;      // sum count*V   (continuous: sum w*V over kept walkers)
-    double c;       // sum count     (continuous: sum w over kept walkers)
-    double v;       // sum V before branching
+// Exact accumulation: floating sums that feed Vref are kept as 128-bit fixed-point integers
+// (quantum 2^-80, range +-2^46), so the result does not depend on which warp processed which tile
+// or in which order partial sums are combined: Vref is bit-reproducible from run to run.
+struct Fx128 {
+    long long hi;
+    unsigned long long lo;
+};
+__device__ __forceinline__ Fx128 fx_zero() { return Fx128{0ll, 0ull}; }
+__device__ __forceinline__ Fx128 fx_add(Fx128 a, Fx128 b)
+{
+    Fx128 r;
+    r.lo = a.lo + b.lo;
+    r.hi = a.hi + b.hi + (long long)(r.lo < a.lo ? 1 : 0);
+    return r;
+}
+// truncating conversion of a finite double (|x| clamped below 2^46) to fixed point
+__device__ __forceinline__ Fx128 fx_from_double(double x)
+{
+    if (!(fabs(x) < 7.0e13)) x = (x != x) ? 0.0 : copysign(7.0e13, x);
+    const long long bits = __double_as_longlong(x);
+    int e = (int)((bits >> 52) & 0x7ff);
+    unsigned long long m = (unsigned long long)bits & 0xFFFFFFFFFFFFFull;
+    if (e) m |= 1ull << 52; else e = 1;
+    const int sh = e - 995;                       // value * 2^80 = m * 2^(e - 1075 + 80)
+    unsigned long long h = 0ull, l = 0ull;
+    if (sh >= 64) h = m << (sh - 64);
+    else if (sh > 0) { l = m << sh; h = m >> (64 - sh); }
+    else if (sh == 0) l = m;
+    else if (sh > -64) l = m >> (-sh);
+    if (bits < 0) { l = ~l + 1ull; h = ~h + (l == 0ull ? 1ull : 0ull); }
+    return Fx128{(long long)h, l};
+}
+__device__ __forceinline__ Fx128 fx_mul_small(Fx128 a, int k)       // k in [0, 2^20)
+{
+    const unsigned long long lo_lo = (a.lo & 0xffffffffull) * (unsigned long long)k;
+    const unsigned long long lo_hi = (a.lo >> 32) * (unsigned long long)k;
+    Fx128 r;
+    r.lo = lo_lo + (lo_hi << 32);
+    const unsigned long long carry = (lo_hi >> 32) + ((r.lo < lo_lo) ? 1ull : 0ull);
+    r.hi = a.hi * (long long)k + (long long)carry;
+    return r;
+}
+__device__ __forceinline__ double fx_to_double(Fx128 a)
+{
+    const bool neg = a.hi < 0;
+    unsigned long long h = (unsigned long long)a.hi, l = a.lo;
+    if (neg) { l = ~l + 1ull; h = ~h + (l == 0ull ? 1ull : 0ull); }
+    const double v = ldexp((double)h, -16) + ldexp((double)l, -80);
+    return neg ? -v : v;
+}
+__device__ __forceinline__ Fx128 fx_warp_sum(Fx128 a)
+{
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        Fx128 b;
+        b.hi = __shfl_xor_sync(0xffffffffu, a.hi, off);
+        b.lo = __shfl_xor_sync(0xffffffffu, a.lo, off);
+        a = fx_add(a, b);
+    }
+    return a;
+}
+
+// per-warp partial sums, combined by the last warp to finish.  cv / v are exact (fixed point);
+// the remaining sums are integer-valued doubles, so every field is order independent.
+struct WarpPartial {
+    Fx128 cv;       // sum count*V   (continuous: sum w*V over kept walkers)
+    Fx128 v;        // sum V before branching
+    Fx128 cw;       // continuous: sum w over kept walkers
+    double c;       // discrete: sum count
     double vmin, vmax;
     double wmin, wmax;
-    int births, deaths;
-    int n_in;       // walkers this tile consumed
-    int n_acc;      // imp-samp accepted
+    double births, deaths, n_in, n_acc;
 };
 
 // ---------------------------------------------------------------- device helpers
@@ -107,37 +174,6 @@ __device__ __forceinline__ bool status_valid(unsigned long long w, long long ste
     return (w >> 34) == (unsigned long long)((step + 1) & 0x3FFFFFFFll) && ((w >> 32) & 3ull) != 0ull;
 }
 
-// block-wide exclusive scan of one int per thread (PVD_TILE threads); returns exclusive prefix,
-// total in *total.  smem: PVD_WARPS+1 ints.
-__device__ __forceinline__ int block_excl_scan(int c, int *smem, int *total)
-{
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    int x = c;
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-        int y = __shfl_up_sync(0xffffffffu, x, off);
-        if (lane >= off) x += y;
-    }
-    if (lane == 31) smem[wid] = x;
-    __syncthreads();
-    if (wid == 0) {
-        int t = lane < PVD_WARPS ? smem[lane] : 0;
-        int s = t;
-#pragma unroll
-        for (int off = 1; off < PVD_WARPS; off <<= 1) {
-            int y = __shfl_up_sync(0xffffffffu, s, off);
-            if (lane >= off) s += y;
-        }
-        if (lane < PVD_WARPS) smem[lane] = s - t;     // exclusive warp offsets
-        if (lane == PVD_WARPS - 1) smem[PVD_WARPS] = s;
-    }
-    __syncthreads();
-    const int excl = x - c + smem[wid];
-    *total = smem[PVD_WARPS];
-    __syncthreads();
-    return excl;
-}
-
 __device__ __forceinline__ double warp_sum(double v)
 {
 #pragma unroll
@@ -156,63 +192,72 @@ __device__ __forceinline__ double warp_max(double v)
     for (int off = 16; off > 0; off >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, off));
     return v;
 }
-__device__ __forceinline__ int warp_sum_i(int v)
+
+// next tile for this warp (-1: none left).  tickets: PVD_WARPS counters, PVD_TICKET_STRIDE apart.
+// Warp slot w of any CTA draws t from counter w and owns tile t*PVD_WARPS + w, so tile ids are
+// handed out in increasing order within each slot class and the smallest unfinished tile is
+// always either running with all its predecessors done or about to be taken (no deadlock even
+// when only part of the grid is resident).
+__device__ __forceinline__ long long warp_take_tile(unsigned *tickets, long long ntiles)
 {
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-    return v;
+    const int lane = threadIdx.x & 31, wslot = (threadIdx.x >> 5) % PVD_WARPS;
+    unsigned t = 0;
+    if (lane == 0) t = atomicAdd(&tickets[wslot * PVD_TICKET_STRIDE], 1u);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    const long long tile = (long long)t * PVD_WARPS + wslot;
+    return tile < ntiles ? tile : -1;
 }
 
-// Tile-level exclusive prefix over the whole grid (single-pass chained scan with decoupled
-// look-back).  Called by all threads; returns the number of output slots used by earlier tiles.
-__device__ __forceinline__ long long tile_lookback(unsigned long long *status, int tile, long long step,
-                                                   int tile_total, long long *smem_prefix)
+// warp-wide inclusive scan of one int per lane
+__device__ __forceinline__ int warp_incl_scan(int c)
 {
-    if (threadIdx.x < 32) {
-        const int lane = threadIdx.x;
-        long long running = 0;
-        if (tile == 0) {
-            if (lane == 0) st_relaxed_u64(&status[0], pack_status(step, PVD_ST_PREFIX, (unsigned)tile_total));
-        } else {
-            if (lane == 0) st_relaxed_u64(&status[tile], pack_status(step, PVD_ST_AGG, (unsigned)tile_total));
-            int look = tile - 1;
-            while (true) {
-                const int idx = look - lane;
-                unsigned long long w = 0;
-                bool ok;
-                do {
-                    if (idx >= 0) {
-                        w = ld_relaxed_u64(&status[idx]);
-                        ok = status_valid(w, step);
-                    } else {
-                        w = pack_status(step, PVD_ST_PREFIX, 0u);   // virtual tile before tile 0
-                        ok = true;
-                    }
-                } while (!__all_sync(0xffffffffu, ok));
-                const bool is_prefix = ((w >> 32) & 3ull) == PVD_ST_PREFIX;
-                const unsigned mask = __ballot_sync(0xffffffffu, is_prefix);
-                const unsigned val = (unsigned)(w & 0xffffffffull);
-                if (mask) {
-                    const int first = __ffs(mask) - 1;              // nearest tile holding an inclusive prefix
-                    long long contrib = lane <= first ? (long long)val : 0ll;
+    const int lane = threadIdx.x & 31;
+    int x = c;
 #pragma unroll
-                    for (int off = 16; off > 0; off >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, off);
-                    running += contrib;
-                    break;
-                }
-                long long contrib = (long long)val;
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, off);
-                running += contrib;
-                look -= 32;
-            }
-            if (lane == 0)
-                st_relaxed_u64(&status[tile], pack_status(step, PVD_ST_PREFIX, (unsigned)(running + tile_total)));
-        }
-        if (lane == 0) *smem_prefix = running;
+    for (int off = 1; off < 32; off <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, off);
+        if (lane >= off) x += y;
     }
-    __syncthreads();
-    const long long p = *smem_prefix;
-    __syncthreads();
-    return p;
+    return x;
+}
+
+// Exclusive prefix of this warp's tile over the whole ensemble: single-pass chained scan with
+// decoupled look-back, one status word per tile, executed by the tile's own warp (all 32 lanes
+// inspect 32 predecessors at a time).  Returns the number of output slots used by earlier tiles.
+__device__ __forceinline__ long long warp_lookback(unsigned long long *status, long long tile, long long step, int tile_total)
+{
+    const int lane = threadIdx.x & 31;
+    long long running = 0;
+    if (tile == 0) {
+        if (lane == 0) st_relaxed_u64(&status[0], pack_status(step, PVD_ST_PREFIX, (unsigned)tile_total));
+        return 0;
+    }
+    if (lane == 0) st_relaxed_u64(&status[tile], pack_status(step, PVD_ST_AGG, (unsigned)tile_total));
+    long long look = tile - 1;
+    while (true) {
+        const long long idx = look - lane;
+        unsigned long long w = pack_status(step, PVD_ST_PREFIX, 0u);    // virtual tiles before tile 0
+        bool ok = true;
+        do {
+            if (idx >= 0) {
+                w = ld_relaxed_u64(&status[idx]);
+                ok = status_valid(w, step);
+            }
+        } while (!__all_sync(0xffffffffu, ok));
+        const bool is_prefix = ((w >> 32) & 3ull) == PVD_ST_PREFIX;
+        const unsigned mask = __ballot_sync(0xffffffffu, is_prefix);
+        const unsigned val = (unsigned)(w & 0xffffffffull);
+        long long contrib;
+        if (mask) {
+            const int first = __ffs(mask) - 1;                          // nearest tile holding an inclusive prefix
+            contrib = lane <= first ? (long long)val : 0ll;
+        } else contrib = (long long)val;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, off);
+        running += contrib;
+        if (mask) break;
+        look -= 32;
+    }
+    if (lane == 0) st_relaxed_u64(&status[tile], pack_status(step, PVD_ST_PREFIX, (unsigned)(running + tile_total)));
+    return running;
 }

@@ -45,16 +45,16 @@ __global__ void k_fill_double(double *p, long long n, double v)
 // coalesced loads; each thread then reads its own NC values (stride NC doubles: conflict-free
 // for odd NC).
 template <class POT>
-__global__ void __launch_bounds__(PVD_TILE) k_pot_aos(const double *__restrict__ aos, long long n, double *__restrict__ v,
+__global__ void __launch_bounds__(PVD_CTA) k_pot_aos(const double *__restrict__ aos, long long n, double *__restrict__ v,
                                                       const PotParamsDev pot)
 {
     constexpr int NC = POT::NC;
-    __shared__ double tile[PVD_TILE * NC];
-    for (long long base = (long long)blockIdx.x * PVD_TILE; base < n; base += (long long)gridDim.x * PVD_TILE) {
+    __shared__ double tile[PVD_CTA * NC];
+    for (long long base = (long long)blockIdx.x * PVD_CTA; base < n; base += (long long)gridDim.x * PVD_CTA) {
         const long long rem = n - base;
-        const int cnt = (int)(rem < PVD_TILE ? rem : PVD_TILE);
+        const int cnt = (int)(rem < PVD_CTA ? rem : PVD_CTA);
         const double *src = aos + base * NC;
-        for (int t = threadIdx.x; t < cnt * NC; t += PVD_TILE) tile[t] = __ldcs(&src[t]);
+        for (int t = threadIdx.x; t < cnt * NC; t += PVD_CTA) tile[t] = __ldcs(&src[t]);
         __syncthreads();
         if ((int)threadIdx.x < cnt) {
             double x[NC];
@@ -68,12 +68,12 @@ __global__ void __launch_bounds__(PVD_TILE) k_pot_aos(const double *__restrict__
 
 // potential on resident SoA walkers (start ensemble, first-step exception pyvibdmc.py:760-762)
 template <class POT>
-__global__ void __launch_bounds__(PVD_TILE) k_pot_soa(const double *__restrict__ x_soa, const DevState *st, int parity,
+__global__ void __launch_bounds__(PVD_CTA) k_pot_soa(const double *__restrict__ x_soa, const DevState *st, int parity,
                                                       long long cap, double *__restrict__ v, const PotParamsDev pot)
 {
     constexpr int NC = POT::NC;
     const long long n = st[parity].n;
-    for (long long i = blockIdx.x * (long long)PVD_TILE + threadIdx.x; i < n; i += (long long)gridDim.x * PVD_TILE) {
+    for (long long i = blockIdx.x * (long long)PVD_CTA + threadIdx.x; i < n; i += (long long)gridDim.x * PVD_CTA) {
         double x[NC];
 #pragma unroll
         for (int c = 0; c < NC; ++c) x[c] = x_soa[c * cap + i];
@@ -132,39 +132,25 @@ __global__ void k_displace_soa(double *__restrict__ x, const DevState *st, int p
 // Same counting / chained scan / compaction / finalisation as k_step_discrete, but the energies
 // come from memory (a.vin) and every per-walker array is copied memory->memory with a run-time
 // number of components.  dt comes from the device state (importance sampling scales it).
-__global__ void __launch_bounds__(PVD_TILE) k_branch_discrete(const StepArgs a)
+__global__ void __launch_bounds__(PVD_CTA) k_branch_discrete(const StepArgs a)
 {
-    __shared__ int s_scan[PVD_WARPS + 1];
-    __shared__ long long s_prefix;
-    __shared__ int s_tile;
-    __shared__ int s_last;
-    __shared__ double s_red[11 * PVD_WARPS];
-
-    DevState *sip = &a.st[a.parity];
+    if (!step_prologue(a)) return;
+    const DevState *sip = &a.st[a.parity];
     const long long n = sip->n, step = sip->step;
     const double vref = sip->vref, dt = sip->dt_eff;
-    if (sip->err) {
-        if (blockIdx.x == 0 && threadIdx.x == 0) forward_dead_state(a);
-        return;
-    }
-    if (n <= 0) {
-        if (blockIdx.x == 0 && threadIdx.x == 0) { forward_dead_state(a); a.st[a.parity ^ 1].err |= PVD_ERR_EMPTY; }
-        return;
-    }
-    const int ntiles = (int)((n + PVD_TILE - 1) / PVD_TILE);
+    const long long ntiles = (n + PVD_TILE - 1) / PVD_TILE;
     const bool dw = sip->dw_active != 0;
     const double n0 = (double)a.n0;
     const double w_limit = (n0 + n0 * 0.5) + 1.0;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    // branch_every (pyvibdmc.py:139,828): do_branch > 0 always, < 0 every |do_branch| steps, 0 never
-    const bool branch_now = a.do_branch > 0 || (a.do_branch < 0 && (step % (long long)(-a.do_branch)) == 0);
+    const int lane = threadIdx.x & 31;
+    const bool branch_now = branch_this_step(a.do_branch, step);
+    unsigned *tickets = step_tickets(a, a.parity);
+    LaneAcc acc;
 
     while (true) {
-        if (threadIdx.x == 0) s_tile = (int)atomicAdd(&sip->ticket, 1u);
-        __syncthreads();
-        const int tile = s_tile;
-        if (tile >= ntiles) break;
-        const long long i = (long long)tile * PVD_TILE + threadIdx.x;
+        const long long tile = warp_take_tile(tickets, ntiles);
+        if (tile < 0) break;
+        const long long i = tile * PVD_TILE + lane;
         const bool active = i < n;
         const double v = active ? a.vin[i] : 0.0;
         int cnt = 0;
@@ -180,10 +166,9 @@ __global__ void __launch_bounds__(PVD_TILE) k_branch_discrete(const StepArgs a)
         }
         if (bad) atomicOr(a.err_accum, PVD_ERR_WEIGHT);
 
-        int tile_total;
-        const int excl = block_excl_scan(cnt, s_scan, &tile_total);
-        const long long prefix = tile_lookback(a.status, tile, step, tile_total, &s_prefix);
-        const long long o = prefix + excl;
+        const int incl = warp_incl_scan(cnt);
+        const int tile_total = __shfl_sync(0xffffffffu, incl, 31);
+        const long long o = warp_lookback(a.status, tile, step, tile_total) + (incl - cnt);
         if (cnt > 0) {
             if (o + cnt > a.cap) atomicOr(a.err_accum, PVD_ERR_CAPACITY);
             else {
@@ -200,45 +185,17 @@ __global__ void __launch_bounds__(PVD_TILE) k_branch_discrete(const StepArgs a)
                 }
             }
         }
-        double pcv = warp_sum((double)cnt * v), pc = warp_sum((double)cnt), pv = warp_sum(active ? v : 0.0);
-        double pmin = warp_min(active ? v : INFINITY), pmax = warp_max(active ? v : -INFINITY);
-        int pb = warp_sum_i(cnt > 1 ? cnt - 1 : 0), pd = warp_sum_i((active && cnt == 0) ? 1 : 0);
-        if (lane == 0) {
-            s_red[0 * PVD_WARPS + wid] = pcv; s_red[1 * PVD_WARPS + wid] = pc; s_red[2 * PVD_WARPS + wid] = pv;
-            s_red[3 * PVD_WARPS + wid] = pmin; s_red[4 * PVD_WARPS + wid] = pmax;
-            s_red[5 * PVD_WARPS + wid] = (double)pb; s_red[6 * PVD_WARPS + wid] = (double)pd;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double t[7];
-            for (int k = 0; k < 7; ++k) {
-                double acc = s_red[k * PVD_WARPS];
-                for (int w = 1; w < PVD_WARPS; ++w) {
-                    const double y = s_red[k * PVD_WARPS + w];
-                    acc = (k == 3) ? fmin(acc, y) : (k == 4 ? fmax(acc, y) : acc + y);
-                }
-                t[k] = acc;
-            }
-            TilePartial p;
-            p.cv = t[0]; p.c = t[1]; p.v = t[2]; p.vmin = t[3]; p.vmax = t[4];
-            p.wmin = INFINITY; p.wmax = -INFINITY;
-            p.births = (int)t[5]; p.deaths = (int)t[6];
-            const long long rem = n - (long long)tile * PVD_TILE;
-            p.n_in = (int)(rem < PVD_TILE ? rem : PVD_TILE);
-            p.n_acc = p.n_in;
-            a.part[tile] = p;
-            __threadfence();
-            const unsigned d = atomicAdd(&sip->done, 1u);
-            s_last = (d == (unsigned)(ntiles - 1)) ? 1 : 0;
-        }
-        __syncthreads();
-        if (s_last) {
-            __threadfence();
-            long long n_new = 0;
-            if (threadIdx.x == 0) n_new = (long long)(ld_relaxed_u64(&a.status[ntiles - 1]) & 0xffffffffull);
-            reduce_partials_and_publish(a, ntiles, n_new, false, s_red);
+        if (active) {
+            const Fx128 fv = fx_from_double(v);
+            acc.v = fx_add(acc.v, fv);
+            if (cnt > 0) acc.cv = fx_add(acc.cv, cnt == 1 ? fv : fx_mul_small(fv, cnt));
+            acc.c += (double)cnt;
+            acc.vmin = fmin(acc.vmin, v); acc.vmax = fmax(acc.vmax, v);
+            acc.births += (double)(cnt > 1 ? cnt - 1 : 0); acc.deaths += (cnt == 0) ? 1.0 : 0.0;
+            acc.n_in += 1.0; acc.n_acc += 1.0;
         }
     }
+    warp_finish_step(a, acc, ntiles, false, -1);
 }
 
 // ---------------------------------------------------------------- first Vref (pyvibdmc.py:760-769) and stand-alone calc_vref

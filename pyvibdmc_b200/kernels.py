@@ -281,6 +281,9 @@ class DeviceSim:
         check(lib.pvd_sim_sums_ptr(self._h, C.byref(p)))
         return p.value
 
+    def set_sums_ptr(self, device_ptr):
+        check(lib.pvd_sim_set_sums_ptr(self._h, C.c_void_p(int(device_ptr) if device_ptr else None)))
+
     def step_local(self, do_branch=1):
         check(lib.pvd_sim_step_local(self._h, int(do_branch)))
 

@@ -140,11 +140,23 @@ def test_free_running_h2o_properties(K, oracle):
 def test_population_guard_raises_like_reference(K, oracle):
     from pyvibdmc_b200 import _capi
     m = np.array([oracle.mass('H'), oracle.mass('H'), oracle.mass('O')])
-    sim = K.DeviceSim(3, 3, m, 1000, 5.0, _capi.POT_H2O_PS, seed=1)
-    bad = EQ[None] * 3.0 + np.zeros((1000, 1, 1))           # absurdly stretched: every walker dies
+    # 10% absurdly stretched walkers drag Vref up; with dt=200 the others get weights e^(+8) > 1.5 N0 + 1
+    sim = K.DeviceSim(3, 3, m, 1000, 200.0, _capi.POT_H2O_PS, seed=1)
+    bad = EQ[None] + np.zeros((1000, 1, 1))
+    bad[:100] *= 3.0
     sim.upload(bad)
     sim.run(3)
-    with pytest.raises(_capi.MassiveEvent, match="Massive walker birth or death"):
+    with pytest.raises(_capi.MassiveEvent, match="Massive walker birth or death event!!!!!!! Dying..."):
+        sim.state()
+    assert sim.state(raise_on_error=False)["step"] == 0      # the failing step did not complete
+    sim.close()
+    # population collapse: every walker far above Vref's reach dies -> population guard
+    sim = K.DeviceSim(3, 3, m, 1000, 5.0, _capi.POT_EXTERNAL, seed=1)
+    sim.upload(EQ[None] + np.zeros((1000, 1, 1)))
+    sim.set_pots(np.zeros(1000))
+    sim.ext_move()
+    sim.ext_finish(np.full(1000, 0.5))                       # w = exp(-2.5): ~92% die
+    with pytest.raises(_capi.MassiveEvent):
         sim.state()
     sim.close()
 
