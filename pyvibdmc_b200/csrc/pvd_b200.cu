@@ -429,8 +429,8 @@ int pvd_sim_create(const pvd_config *cfg, pvd_sim **out)
     TRY(s->status.alloc((size_t)ntiles * 8));
     TRY(cudaMemset(s->status.p, 0, (size_t)ntiles * 8));
     // persistent-style grid: enough CTAs to cover the capacity, at most 8 per SM
-    s->grid = grid_for(cap, PVD_CTA, 8);
-    TRY(s->part.alloc((size_t)s->grid * PVD_WARPS * sizeof(WarpPartial)));
+    s->grid = grid_for(cap, PVD_CTA, 2);
+    TRY(s->part.alloc((size_t)s->grid * sizeof(WarpPartial)));
     TRY(s->tickets.alloc(2 * PVD_WARPS * PVD_TICKET_STRIDE * 4));
     TRY(cudaMemset(s->tickets.p, 0, 2 * PVD_WARPS * PVD_TICKET_STRIDE * 4));
     TRY(s->ring.alloc((size_t)cfg->stats_ring * sizeof(pvd_step_stats)));
@@ -889,7 +889,7 @@ int pvd_branch_discrete(const double *v, int64_t n, double vref, double dt, cons
     const int g = grid_for(n, PVD_CTA, 8);
     PVD_CUDA(dv.alloc((size_t)n * 8)); PVD_CUDA(du.alloc((size_t)n * 8));
     PVD_CUDA(dst.alloc(2 * sizeof(DevState))); PVD_CUDA(derr.alloc(4));
-    PVD_CUDA(dstatus.alloc((size_t)ntiles * 8)); PVD_CUDA(dpart.alloc((size_t)g * PVD_WARPS * sizeof(WarpPartial)));
+    PVD_CUDA(dstatus.alloc((size_t)ntiles * 8)); PVD_CUDA(dpart.alloc((size_t)g * sizeof(WarpPartial)));
     PVD_CUDA(dtick.alloc(2 * PVD_WARPS * PVD_TICKET_STRIDE * 4));
     PVD_CUDA(cudaMemset(dtick.p, 0, 2 * PVD_WARPS * PVD_TICKET_STRIDE * 4));
     PVD_CUDA(dring.alloc(sizeof(pvd_step_stats))); PVD_CUDA(dsums.alloc(PVD_NSUMS * 8));

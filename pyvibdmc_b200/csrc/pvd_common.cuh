@@ -221,18 +221,21 @@ __device__ __forceinline__ int warp_incl_scan(int c)
     return x;
 }
 
-// Exclusive prefix of this warp's tile over the whole ensemble: single-pass chained scan with
-// decoupled look-back, one status word per tile, executed by the tile's own warp (all 32 lanes
-// inspect 32 predecessors at a time).  Returns the number of output slots used by earlier tiles.
-__device__ __forceinline__ long long warp_lookback(unsigned long long *status, long long tile, long long step, int tile_total)
+// Chained scan with decoupled look-back, one status word per tile, driven by the tile's own warp.
+// publish_aggregate() is called as soon as a tile's total is known; resolve_prefix() -- possibly
+// much later, after the warp has already computed its next tile -- walks back over the
+// predecessors' status words (32 at a time) and returns the number of output slots used by
+// earlier tiles, then upgrades the tile's status to an inclusive prefix.
+__device__ __forceinline__ void publish_aggregate(unsigned long long *status, long long tile, long long step, int tile_total)
+{
+    if ((threadIdx.x & 31) == 0)
+        st_relaxed_u64(&status[tile], pack_status(step, tile == 0 ? PVD_ST_PREFIX : PVD_ST_AGG, (unsigned)tile_total));
+}
+__device__ __forceinline__ long long resolve_prefix(unsigned long long *status, long long tile, long long step, int tile_total)
 {
     const int lane = threadIdx.x & 31;
+    if (tile == 0) return 0;
     long long running = 0;
-    if (tile == 0) {
-        if (lane == 0) st_relaxed_u64(&status[0], pack_status(step, PVD_ST_PREFIX, (unsigned)tile_total));
-        return 0;
-    }
-    if (lane == 0) st_relaxed_u64(&status[tile], pack_status(step, PVD_ST_AGG, (unsigned)tile_total));
     long long look = tile - 1;
     while (true) {
         const long long idx = look - lane;
@@ -260,4 +263,9 @@ __device__ __forceinline__ long long warp_lookback(unsigned long long *status, l
     }
     if (lane == 0) st_relaxed_u64(&status[tile], pack_status(step, PVD_ST_PREFIX, (unsigned)(running + tile_total)));
     return running;
+}
+__device__ __forceinline__ long long warp_lookback(unsigned long long *status, long long tile, long long step, int tile_total)
+{
+    publish_aggregate(status, tile, step, tile_total);
+    return resolve_prefix(status, tile, step, tile_total);
 }

@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(PVD_CTA) k_branch_discrete(const StepArgs a)
             acc.n_in += 1.0; acc.n_acc += 1.0;
         }
     }
-    warp_finish_step(a, acc, ntiles, false, -1);
+    cta_finish_step(a, acc, ntiles, false, -1);
 }
 
 // ---------------------------------------------------------------- first Vref (pyvibdmc.py:760-769) and stand-alone calc_vref

@@ -4,9 +4,9 @@
 // counters, moves them (Philox + Box-Muller), evaluates V, draws the integer copy count, and a
 // single-pass chained scan (decoupled look-back, one status word per tile, driven by the tile's own
 // warp) gives each tile its output offset, so each surviving walker is written exactly once,
-// already compacted and in np.repeat order, into the other half of a ping-pong buffer.  No
-// __syncthreads, no shared memory.  The last warp to finish reduces the per-warp partial sums in
-// a fixed order and produces Vref, the population and the per-step log record on the device.
+// already compacted and in np.repeat order, into the other half of a ping-pong buffer.  The
+// tile loop has no __syncthreads and no shared memory.  The last CTA to finish combines the exact
+// (fixed-point) per-CTA partial sums and produces Vref, the population and the per-step log record on the device.
 #pragma once
 #include "pvd_common.cuh"
 #include "pvd_rng.cuh"
@@ -138,56 +138,76 @@ struct LaneAcc {
     double births = 0.0, deaths = 0.0, n_in = 0.0, n_acc = 0.0;
 };
 
-// End of a step kernel, called by every warp of the grid (converged): publish this warp's partial
-// record; the last warp to arrive combines all records (every field is exact / order independent,
-// so Vref is bit-reproducible), publishes the shard's sums and, on a single GPU, finalises the step.
-// n_local_fixed < 0: the new local population is the inclusive prefix of the last tile.
-__device__ inline void warp_finish_step(const StepArgs &a, const LaneAcc &acc, long long ntiles, bool continuous, long long n_local_fixed)
+__device__ __forceinline__ void acc_merge(LaneAcc &r, const WarpPartial &q)
 {
-    const int lane = threadIdx.x & 31;
-    const int gwarp = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
-    const int nwarps = (int)((gridDim.x * (long long)blockDim.x) >> 5);
+    r.cv = fx_add(r.cv, q.cv); r.v = fx_add(r.v, q.v); r.cw = fx_add(r.cw, q.cw);
+    r.c += q.c; r.births += q.births; r.deaths += q.deaths; r.n_in += q.n_in; r.n_acc += q.n_acc;
+    r.vmin = fmin(r.vmin, q.vmin); r.vmax = fmax(r.vmax, q.vmax);
+    r.wmin = fmin(r.wmin, q.wmin); r.wmax = fmax(r.wmax, q.wmax);
+}
+__device__ __forceinline__ WarpPartial acc_warp_reduce(const LaneAcc &acc)
+{
     WarpPartial p;
     p.cv = fx_warp_sum(acc.cv); p.v = fx_warp_sum(acc.v); p.cw = fx_warp_sum(acc.cw);
     p.c = warp_sum(acc.c); p.births = warp_sum(acc.births); p.deaths = warp_sum(acc.deaths);
     p.n_in = warp_sum(acc.n_in); p.n_acc = warp_sum(acc.n_acc);
     p.vmin = warp_min(acc.vmin); p.vmax = warp_max(acc.vmax); p.wmin = warp_min(acc.wmin); p.wmax = warp_max(acc.wmax);
-    unsigned last = 0;
-    if (lane == 0) {
-        a.part[gwarp] = p;
+    return p;
+}
+
+// End of a step kernel, called by every thread of every CTA after its ticket loop (the only CTA
+// barriers of the kernel are here, when the CTA has nothing left to do).  Warps -> CTA record ->
+// the last CTA to arrive combines all CTA records (every field is exact / order independent, so
+// Vref is bit-reproducible), publishes the shard's sums and, on a single GPU, finalises the step.
+// n_local_fixed < 0: the new local population is the inclusive prefix of the last tile.
+__device__ inline void cta_finish_step(const StepArgs &a, const LaneAcc &acc, long long ntiles, bool continuous, long long n_local_fixed)
+{
+    __shared__ WarpPartial s_part[PVD_WARPS];
+    __shared__ unsigned s_last;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const WarpPartial p = acc_warp_reduce(acc);
+    if (lane == 0) s_part[wid] = p;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        LaneAcc r;
+        for (int w = 0; w < PVD_WARPS; ++w) acc_merge(r, s_part[w]);
+        WarpPartial q;
+        q.cv = r.cv; q.v = r.v; q.cw = r.cw; q.c = r.c; q.births = r.births; q.deaths = r.deaths; q.n_in = r.n_in; q.n_acc = r.n_acc;
+        q.vmin = r.vmin; q.vmax = r.vmax; q.wmin = r.wmin; q.wmax = r.wmax;
+        a.part[blockIdx.x] = q;
         __threadfence();
         const unsigned d = atomicAdd(&a.st[a.parity].done, 1u);
-        last = (d == (unsigned)(nwarps - 1)) ? 1u : 0u;
+        s_last = (d == gridDim.x - 1) ? 1u : 0u;
     }
-    last = __shfl_sync(0xffffffffu, last, 0);
-    if (!last) return;
+    __syncthreads();
+    if (!s_last) return;
     __threadfence();
     LaneAcc r;
-    for (int wv = lane; wv < nwarps; wv += 32) {
-        const WarpPartial *q = &a.part[wv];
-        Fx128 t;
-        t.hi = __ldcg(&q->cv.hi); t.lo = __ldcg(&q->cv.lo); r.cv = fx_add(r.cv, t);
-        t.hi = __ldcg(&q->v.hi); t.lo = __ldcg(&q->v.lo); r.v = fx_add(r.v, t);
-        t.hi = __ldcg(&q->cw.hi); t.lo = __ldcg(&q->cw.lo); r.cw = fx_add(r.cw, t);
-        r.c += __ldcg(&q->c); r.births += __ldcg(&q->births); r.deaths += __ldcg(&q->deaths);
-        r.n_in += __ldcg(&q->n_in); r.n_acc += __ldcg(&q->n_acc);
-        r.vmin = fmin(r.vmin, __ldcg(&q->vmin)); r.vmax = fmax(r.vmax, __ldcg(&q->vmax));
-        r.wmin = fmin(r.wmin, __ldcg(&q->wmin)); r.wmax = fmax(r.wmax, __ldcg(&q->wmax));
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += PVD_CTA) {
+        const WarpPartial *q = &a.part[b];
+        WarpPartial t;
+        t.cv.hi = __ldcg(&q->cv.hi); t.cv.lo = __ldcg(&q->cv.lo); t.v.hi = __ldcg(&q->v.hi); t.v.lo = __ldcg(&q->v.lo);
+        t.cw.hi = __ldcg(&q->cw.hi); t.cw.lo = __ldcg(&q->cw.lo);
+        t.c = __ldcg(&q->c); t.births = __ldcg(&q->births); t.deaths = __ldcg(&q->deaths);
+        t.n_in = __ldcg(&q->n_in); t.n_acc = __ldcg(&q->n_acc);
+        t.vmin = __ldcg(&q->vmin); t.vmax = __ldcg(&q->vmax); t.wmin = __ldcg(&q->wmin); t.wmax = __ldcg(&q->wmax);
+        acc_merge(r, t);
     }
-    r.cv = fx_warp_sum(r.cv); r.v = fx_warp_sum(r.v); r.cw = fx_warp_sum(r.cw);
-    r.c = warp_sum(r.c); r.births = warp_sum(r.births); r.deaths = warp_sum(r.deaths);
-    r.n_in = warp_sum(r.n_in); r.n_acc = warp_sum(r.n_acc);
-    r.vmin = warp_min(r.vmin); r.vmax = warp_max(r.vmax); r.wmin = warp_min(r.wmin); r.wmax = warp_max(r.wmax);
-    if (lane == 0) {
+    const WarpPartial pw = acc_warp_reduce(r);
+    if (lane == 0) s_part[wid] = pw;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        LaneAcc f;
+        for (int w = 0; w < PVD_WARPS; ++w) acc_merge(f, s_part[w]);
         double *s = a.sums;
         for (int k = 0; k < PVD_SUM_EXT + 4 * a.world; ++k) s[k] = 0.0;
-        s[PVD_SUM_CV] = fx_to_double(r.cv);
-        s[PVD_SUM_C] = continuous ? fx_to_double(r.cw) : r.c;
-        s[PVD_SUM_V] = fx_to_double(r.v);
-        s[PVD_SUM_BIRTHS] = r.births; s[PVD_SUM_DEATHS] = r.deaths; s[PVD_SUM_NIN] = r.n_in; s[PVD_SUM_NACC] = r.n_acc;
+        s[PVD_SUM_CV] = fx_to_double(f.cv);
+        s[PVD_SUM_C] = continuous ? fx_to_double(f.cw) : f.c;
+        s[PVD_SUM_V] = fx_to_double(f.v);
+        s[PVD_SUM_BIRTHS] = f.births; s[PVD_SUM_DEATHS] = f.deaths; s[PVD_SUM_NIN] = f.n_in; s[PVD_SUM_NACC] = f.n_acc;
         s[PVD_SUM_ERR] = (double)(*a.err_accum);
         double *e = s + PVD_SUM_EXT + 4 * a.rank;
-        e[0] = r.vmin; e[1] = r.vmax; e[2] = r.wmin; e[3] = r.wmax;
+        e[0] = f.vmin; e[1] = f.vmax; e[2] = f.wmin; e[3] = f.wmax;
         long long n_new = n_local_fixed;
         if (n_local_fixed < 0) n_new = (long long)(ld_relaxed_u64(&a.status[ntiles - 1]) & 0xffffffffull);
         a.st[a.parity ^ 1].n = n_new;
@@ -261,10 +281,21 @@ __device__ __forceinline__ bool step_prologue(const StepArgs &a)
     return true;
 }
 
+// One warp's stash for the software pipeline: the tile computed in iteration k is scattered in
+// iteration k+1, after the warp has computed its next tile, so that the look-back (which must see
+// the aggregate of every earlier tile, including tiles that started just before this one) almost
+// never has to wait.
+template <int NC>
+struct TileStash {
+    double x[NC + 1][32];     // components, then V
+    int cnt[32], excl[32], who[32];
+};
+
 template <class POT, int RNG>
-__global__ void __launch_bounds__(PVD_CTA) k_step_discrete(const StepArgs a)
+__global__ void __launch_bounds__(PVD_CTA, 2) k_step_discrete(const StepArgs a)
 {
     constexpr int NC = POT::NC;
+    __shared__ TileStash<NC> s_stash[PVD_WARPS];
     if (!step_prologue(a)) return;
     const DevState *sip = &a.st[a.parity];
     const long long n = sip->n, step = sip->step;
@@ -276,53 +307,69 @@ __global__ void __launch_bounds__(PVD_CTA) k_step_discrete(const StepArgs a)
     const int lane = threadIdx.x & 31;
     const bool branch_now = branch_this_step(a.do_branch, step);
     unsigned *tickets = step_tickets(a, a.parity);
+    TileStash<NC> &stash = s_stash[threadIdx.x >> 5];
     LaneAcc acc;
+    long long pending = -1;
+    int pending_total = 0;
 
     while (true) {
         const long long tile = warp_take_tile(tickets, ntiles);
-        if (tile < 0) break;
-        const long long i = tile * PVD_TILE + lane;
-        const bool active = i < n;
-
-        double x[NC], v;
-        ProduceFused<POT, RNG>::run(a, i, step, active, x, v);
-
-        int cnt = 0;
-        bool bad = false;
-        if (active) {
-            if (branch_now) {
-                double u;
-                if (a.inj_u) u = a.inj_u[i];
-                else { const uint4 r = pvd_draw(a.seed, i, step, PVD_STREAM_BRANCH, 0u); u = u53(r.x, r.y); }
-                cnt = discrete_count(v, vref, a.dt, u, w_limit, bad);
-            } else cnt = 1;
+        double x[NC], v = 0.0;
+        int cnt = 0, incl = 0, tile_total = 0, who = 0;
+        if (tile >= 0) {
+            const long long i = tile * PVD_TILE + lane;
+            const bool active = i < n;
+            ProduceFused<POT, RNG>::run(a, i, step, active, x, v);
+            bool bad = false;
+            if (active) {
+                if (branch_now) {
+                    double u;
+                    if (a.inj_u) u = a.inj_u[i];
+                    else { const uint4 r = pvd_draw(a.seed, i, step, PVD_STREAM_BRANCH, 0u); u = u53(r.x, r.y); }
+                    cnt = discrete_count(v, vref, a.dt, u, w_limit, bad);
+                } else cnt = 1;
+                if (dw) who = a.who_in[i];
+                const Fx128 fv = fx_from_double(v);
+                acc.v = fx_add(acc.v, fv);
+                if (cnt > 0) acc.cv = fx_add(acc.cv, cnt == 1 ? fv : fx_mul_small(fv, cnt));
+                acc.c += (double)cnt;
+                acc.vmin = fmin(acc.vmin, v); acc.vmax = fmax(acc.vmax, v);
+                acc.births += (double)(cnt > 1 ? cnt - 1 : 0); acc.deaths += (cnt == 0) ? 1.0 : 0.0;
+                acc.n_in += 1.0; acc.n_acc += 1.0;
+            }
+            if (bad) atomicOr(a.err_accum, PVD_ERR_WEIGHT);
+            incl = warp_incl_scan(cnt);
+            tile_total = __shfl_sync(0xffffffffu, incl, 31);
+            publish_aggregate(a.status, tile, step, tile_total);       // successors can use it right away
         }
-        if (bad) atomicOr(a.err_accum, PVD_ERR_WEIGHT);
-
-        const int incl = warp_incl_scan(cnt);
-        const int tile_total = __shfl_sync(0xffffffffu, incl, 31);
-        const long long o = warp_lookback(a.status, tile, step, tile_total) + (incl - cnt);
-        if (cnt > 0) {
-            if (o + cnt > a.cap) atomicOr(a.err_accum, PVD_ERR_CAPACITY);
-            else {
-                const int who = dw ? a.who_in[i] : 0;
-                for (int k = 0; k < cnt; ++k) {
+        if (pending >= 0) {
+            // scatter the previous tile: its predecessors have had a whole tile's worth of time to publish
+            const long long o = resolve_prefix(a.status, pending, step, pending_total) + stash.excl[lane];
+            const int pc = stash.cnt[lane];
+            if (pc > 0) {
+                if (o + pc > a.cap) atomicOr(a.err_accum, PVD_ERR_CAPACITY);
+                else {
+                    const double pv = stash.x[NC][lane];
+                    for (int k = 0; k < pc; ++k) {
 #pragma unroll
-                    for (int c = 0; c < NC; ++c) a.xout[c * a.cap + o + k] = x[c];
-                    a.vout[o + k] = v;
-                    if (dw) a.who_out[o + k] = who;
+                        for (int c = 0; c < NC; ++c) a.xout[c * a.cap + o + k] = stash.x[c][lane];
+                        a.vout[o + k] = pv;
+                        if (dw) a.who_out[o + k] = stash.who[lane];
+                    }
                 }
             }
+            __syncwarp();
         }
-        if (active) {
-            const Fx128 fv = fx_from_double(v);
-            acc.v = fx_add(acc.v, fv);
-            if (cnt > 0) acc.cv = fx_add(acc.cv, cnt == 1 ? fv : fx_mul_small(fv, cnt));
-            acc.c += (double)cnt;
-            acc.vmin = fmin(acc.vmin, v); acc.vmax = fmax(acc.vmax, v);
-            acc.births += (double)(cnt > 1 ? cnt - 1 : 0); acc.deaths += (cnt == 0) ? 1.0 : 0.0;
-            acc.n_in += 1.0; acc.n_acc += 1.0;
-        }
+        if (tile < 0) break;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) stash.x[c][lane] = x[c];
+        stash.x[NC][lane] = v;
+        stash.cnt[lane] = cnt;
+        stash.excl[lane] = incl - cnt;
+        stash.who[lane] = who;
+        __syncwarp();
+        pending = tile;
+        pending_total = tile_total;
     }
-    warp_finish_step(a, acc, ntiles, false, -1);
+    cta_finish_step(a, acc, ntiles, false, -1);
 }
