@@ -1,22 +1,408 @@
-// Host-side pieces that need the full pvd_sim definition.
-static int cont_enqueue_step(pvd_sim *, StepArgs &) { return pvd_fail(PVD_E_STATE, "continuous weighting: not built yet"); }
-static int cont_enqueue_branch_only(pvd_sim *, StepArgs &) { return pvd_fail(PVD_E_STATE, "continuous weighting: not built yet"); }
-static int imp_enqueue_step(pvd_sim *, StepArgs &, const double *) { return pvd_fail(PVD_E_STATE, "importance sampling: not built yet"); }
-static int imp_initial_drift(pvd_sim *) { return pvd_fail(PVD_E_STATE, "importance sampling: not built yet"); }
-static int nn_enqueue_discrete_step(pvd_sim *, StepArgs &) { return pvd_fail(PVD_E_STATE, "NN potential: not built yet"); }
+// Host-side pieces that need the full pvd_sim definition: continuous weighting, importance
+// sampling, NN potential glue, and the remaining stand-alone entry points.
+
+// ---------------------------------------------------------------- continuous weighting
+static ContArgs make_cont_args(pvd_sim *s)
+{
+    ContArgs ca{};
+    ca.w = s->w.as<double>();
+    ca.v = s->v[s->cur].as<double>();
+    ca.kill_idx = s->kill_idx.as<int>();
+    ca.copy_dst = s->copy_dst.as<int>();
+    ca.copy_src = s->copy_src.as<int>();
+    ca.cand = s->cand.as<ContCand>();
+    ca.hist = s->hist.as<unsigned>();
+    ca.work = s->cont_work.as<ContWork>();
+    ca.cand_cap = s->cap;
+    ca.lower = s->cfg.thresh_lower;
+    ca.upper = s->cfg.thresh_upper;
+    ca.has_upper = (s->cfg.thresh_upper == s->cfg.thresh_upper) ? 1 : 0;
+    return ca;
+}
+
+// weight update + branching + Vref on energies already stored in v[cur] (in place)
+static int cont_enqueue_branch_only(pvd_sim *s, StepArgs &a)
+{
+    a.xin = a.xout = s->x[s->cur].as<double>();
+    a.vin = a.vout = s->v[s->cur].as<double>();
+    a.who_in = a.who_out = s->who[s->cur].as<int>();
+    a.flip = 0;
+    ContArgs ca = make_cont_args(s);
+    const int g = s->grid;
+    const bool imp = s->cfg.trial != PVD_TRIAL_NONE;
+    k_cont_update<<<g, PVD_CTA, 0, s->stream>>>(a, ca);
+    PVD_CHECK_LAUNCH();
+    k_cont_hist<<<g, PVD_CTA, 0, s->stream>>>(a, ca);
+    PVD_CHECK_LAUNCH();
+    k_cont_collect<<<g, PVD_CTA, 0, s->stream>>>(a, ca);
+    PVD_CHECK_LAUNCH();
+    k_cont_assign<<<1, 1024, 0, s->stream>>>(a, ca, s->cont_queue.as<ContCand>(), s->cont_root.as<int>(), s->cont_skip.as<unsigned char>());
+    PVD_CHECK_LAUNCH();
+    k_cont_copy<<<g, PVD_CTA, 0, s->stream>>>(a, ca, s->x[s->cur].as<double>(), s->v[s->cur].as<double>(), s->who[s->cur].as<int>(),
+                                               imp ? s->f[s->cur].as<double>() : nullptr, imp ? s->psi[s->cur].as<double>() : nullptr,
+                                               imp ? s->lk[s->cur].as<double>() : nullptr, nullptr);
+    PVD_CHECK_LAUNCH();
+    k_cont_finish<<<g, PVD_CTA, 0, s->stream>>>(a, ca);
+    PVD_CHECK_LAUNCH();
+    return PVD_OK;
+}
+
+static int cont_enqueue_step(pvd_sim *s, StepArgs &a)
+{
+    const int g = s->grid;
+    const bool fast = s->cfg.rng_mode == PVD_RNG_FAST;
+    double *x = s->x[s->cur].as<double>(), *v = s->v[s->cur].as<double>();
+    a.xin = x;
+#define LAUNCH_MOVE(POT)                                                                            \
+    do {                                                                                            \
+        if (fast) k_move_pes<POT, PVD_RNG_FAST><<<g, PVD_CTA, 0, s->stream>>>(a, x, v);              \
+        else k_move_pes<POT, PVD_RNG_FP64><<<g, PVD_CTA, 0, s->stream>>>(a, x, v);                   \
+    } while (0)
+    switch (s->cfg.potential) {
+    case PVD_POT_H2O_PS: LAUNCH_MOVE(PotH2O); break;
+    case PVD_POT_HARMONIC:
+        if (s->nc == 1) LAUNCH_MOVE(PotHarm<1>);
+        else if (s->nc == 3) LAUNCH_MOVE(PotHarm<3>);
+        else return pvd_fail(PVD_E_ARG, "built-in harmonic potential supports 1 or 3 components");
+        break;
+    case PVD_POT_MORSE1D: LAUNCH_MOVE(PotMorse); break;
+    default: return pvd_fail(PVD_E_STATE, "continuous weighting on the device needs a built-in fp64 potential");
+    }
+#undef LAUNCH_MOVE
+    PVD_CHECK_LAUNCH();
+    return cont_enqueue_branch_only(s, a);
+}
+
+extern "C" int pvd_branch_continuous(double *w, const double *v, int64_t n, double vref, double dt, double lower, double upper,
+                                     int64_t *src, double *stats3)
+{
+    PVD_REQUIRE(w && v && src && stats3 && n >= 1, "pvd_branch_continuous: bad arguments");
+    if (int rc = ensure_device_ready()) return rc;
+    pvd_config cfg{};
+    cfg.natoms = 1; cfg.ndim = 1; cfg.weighting = PVD_WEIGHT_CONTINUOUS; cfg.potential = PVD_POT_EXTERNAL;
+    cfg.world_size = 1; cfg.num_walkers = n; cfg.capacity = n; cfg.delta_t = dt; cfg.alpha = 1.0 / (2.0 * dt);
+    cfg.thresh_lower = lower; cfg.thresh_upper = upper; cfg.masses[0] = 1.0; cfg.stats_ring = 1;
+    PVD_CUDA(cudaGetDevice(&cfg.device));
+    pvd_sim *s = nullptr;
+    if (int rc = pvd_sim_create(&cfg, &s)) return rc;
+    struct Guard { pvd_sim *s; ~Guard() { pvd_sim_destroy(s); } } guard{s};
+    std::vector<double> x0((size_t)n, 0.0);
+    if (int rc = pvd_sim_upload(s, x0.data(), n, w)) return rc;
+    // state: energies and the injected Vref
+    PVD_CUDA(cudaMemcpy(s->v[s->cur].p, v, (size_t)n * 8, cudaMemcpyHostToDevice));
+    DevState h[2];
+    PVD_CUDA(cudaMemcpy(h, s->st.p, sizeof(h), cudaMemcpyDeviceToHost));
+    h[0].vref = vref; h[0].dt_eff = dt; h[1] = h[0];
+    PVD_CUDA(cudaMemcpy(s->st.p, h, sizeof(h), cudaMemcpyHostToDevice));
+    DevBuf dsrc;
+    PVD_CUDA(dsrc.alloc((size_t)n * 8));
+    k_iota_i64<<<grid_for(n, 256, 16), 256, 0, s->stream>>>(dsrc.as<long long>(), n);
+    PVD_CHECK_LAUNCH();
+    StepArgs a = make_args(s, 1);
+    a.xin = a.xout = s->x[s->cur].as<double>();
+    a.vin = a.vout = s->v[s->cur].as<double>();
+    a.who_in = a.who_out = s->who[s->cur].as<int>();
+    a.flip = 0;
+    ContArgs ca = make_cont_args(s);
+    const int g = s->grid;
+    k_cont_update<<<g, PVD_CTA, 0, s->stream>>>(a, ca); PVD_CHECK_LAUNCH();
+    k_cont_hist<<<g, PVD_CTA, 0, s->stream>>>(a, ca); PVD_CHECK_LAUNCH();
+    k_cont_collect<<<g, PVD_CTA, 0, s->stream>>>(a, ca); PVD_CHECK_LAUNCH();
+    k_cont_assign<<<1, 1024, 0, s->stream>>>(a, ca, s->cont_queue.as<ContCand>(), s->cont_root.as<int>(), s->cont_skip.as<unsigned char>());
+    PVD_CHECK_LAUNCH();
+    k_cont_copy<<<g, PVD_CTA, 0, s->stream>>>(a, ca, s->x[s->cur].as<double>(), s->v[s->cur].as<double>(), s->who[s->cur].as<int>(), nullptr,
+                                               nullptr, nullptr, dsrc.as<long long>());
+    PVD_CHECK_LAUNCH();
+    k_cont_finish<<<g, PVD_CTA, 0, s->stream>>>(a, ca); PVD_CHECK_LAUNCH();
+    PVD_CUDA(cudaStreamSynchronize(s->stream));
+    PVD_CUDA(cudaMemcpy(w, s->w.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    PVD_CUDA(cudaMemcpy(src, dsrc.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    pvd_step_stats r;
+    PVD_CUDA(cudaMemcpy(&r, s->ring.p, sizeof(r), cudaMemcpyDeviceToHost));
+    stats3[0] = (double)r.births; stats3[1] = r.w_max; stats3[2] = r.w_min;
+    return PVD_OK;
+}
+
+// ---------------------------------------------------------------- importance sampling
+static int fill_trial_params(pvd_sim *s, ImpArgs &im)
+{
+    memset(&im, 0, sizeof(im));
+    for (int a = 0; a < PVD_MAX_ATOMS; ++a) im.inv_mass[a] = s->inv_mass[a];
+    im.trial = s->trial_params;
+    im.acc_count = s->acc_count.as<unsigned long long>();
+    if (s->cfg.trial == PVD_TRIAL_H2O_FD && !s->trial_table.p) return pvd_fail(PVD_E_STATE, "water trial wfn: call pvd_sim_set_trial_table first");
+    return PVD_OK;
+}
+
+static int host_trial_params(int32_t trial, const double *table, int64_t ntab, const double *dev_table, TrialParamsDev &p)
+{
+    memset(&p, 0, sizeof(p));
+    p.fd_dx = 0.001;
+    p.fd_dx2 = 0.001 * 0.001;               // Python: dx ** 2
+    if (trial == PVD_TRIAL_HARM1D) {
+        PVD_REQUIRE(table && ntab >= 1, "HARM1D trial needs {alpha}");
+        p.h_alpha = table[0];
+        p.h_pref = pow(table[0] / 3.141592653589793, 0.25);
+        return PVD_OK;
+    }
+    if (trial == PVD_TRIAL_H2O_FD) {
+        // table layout: grid[ntab], psi[ntab], then {ang_alpha, theta_eq}
+        PVD_REQUIRE(table && ntab >= 4, "H2O trial needs the (2, ntab) table followed by {alpha_theta, theta_eq}");
+        p.grid = dev_table;
+        p.wfn = dev_table + ntab;
+        p.ntab = (int)ntab;
+        p.g0 = table[0];
+        p.inv_step = (double)(ntab - 1) / (table[ntab - 1] - table[0]);
+        p.ang_alpha = table[2 * ntab];
+        p.theta_eq = table[2 * ntab + 1];
+        p.ang_pref = pow(p.ang_alpha / 3.141592653589793, 0.25);
+        return PVD_OK;
+    }
+    return pvd_fail(PVD_E_ARG, "unknown trial wave function id");
+}
+
+extern "C" int pvd_sim_set_trial_table(pvd_sim *s, const double *table, int64_t ntab)
+{
+    SIM_CHECK(s);
+    SIM_DEVICE(s);
+    PVD_REQUIRE(s->cfg.trial != PVD_TRIAL_NONE, "this handle was created without a trial wave function");
+    const size_t total = s->cfg.trial == PVD_TRIAL_H2O_FD ? (size_t)(2 * ntab + 2) : (size_t)ntab;
+    PVD_CUDA(s->trial_table.alloc(total * 8));
+    PVD_CUDA(cudaMemcpy(s->trial_table.p, table, total * 8, cudaMemcpyHostToDevice));
+    s->ntrial = ntab;
+    return host_trial_params(s->cfg.trial, table, ntab, s->trial_table.as<double>(), s->trial_params);
+}
+
+#define IMP_DISPATCH(KERNEL_CALL)                                                                                           \
+    do {                                                                                                                    \
+        const int t = s->cfg.trial, p = s->cfg.potential;                                                                   \
+        if (t == PVD_TRIAL_H2O_FD && p == PVD_POT_H2O_PS) { KERNEL_CALL(TrialH2O, PotH2O); }                                 \
+        else if (t == PVD_TRIAL_HARM1D && p == PVD_POT_HARMONIC && s->nc == 1) { KERNEL_CALL(TrialHarm1D, PotHarm<1>); }     \
+        else if (t == PVD_TRIAL_HARM1D && p == PVD_POT_MORSE1D) { KERNEL_CALL(TrialHarm1D, PotMorse); }                      \
+        else return pvd_fail(PVD_E_ARG, "unsupported built-in (trial, potential) combination");                             \
+    } while (0)
+
+static int imp_initial_drift(pvd_sim *s)
+{
+    ImpArgs im;
+    if (int rc = fill_trial_params(s, im)) return rc;
+    StepArgs a = make_args(s, 1);
+    const int g = s->grid;
+    double *x = s->x[s->cur].as<double>(), *f = s->f[s->cur].as<double>(), *psi = s->psi[s->cur].as<double>();
+    double *lk = s->lk[s->cur].as<double>(), *v = s->v[s->cur].as<double>();
+#define CALL_INIT(T, P) k_imp_init<T, P><<<g, PVD_CTA, 0, s->stream>>>(a, im, x, f, psi, lk, v)
+    IMP_DISPATCH(CALL_INIT);
+#undef CALL_INIT
+    PVD_CHECK_LAUNCH();
+    return PVD_OK;
+}
+
+static int imp_enqueue_step(pvd_sim *s, StepArgs &a, const double *inj_um)
+{
+    ImpArgs im;
+    if (int rc = fill_trial_params(s, im)) return rc;
+    im.inj_um = inj_um;
+    const int g = s->grid;
+    const bool fast = s->cfg.rng_mode == PVD_RNG_FAST;
+    double *x = s->x[s->cur].as<double>(), *f = s->f[s->cur].as<double>(), *psi = s->psi[s->cur].as<double>();
+    double *lk = s->lk[s->cur].as<double>(), *v = s->v[s->cur].as<double>();
+#define CALL_MOVE(T, P)                                                                                 \
+    do {                                                                                                \
+        if (fast) k_imp_move<T, P, PVD_RNG_FAST><<<g, PVD_CTA, 0, s->stream>>>(a, im, x, f, psi, lk, v); \
+        else k_imp_move<T, P, PVD_RNG_FP64><<<g, PVD_CTA, 0, s->stream>>>(a, im, x, f, psi, lk, v);      \
+    } while (0)
+    IMP_DISPATCH(CALL_MOVE);
+#undef CALL_MOVE
+    PVD_CHECK_LAUNCH();
+    if (s->cfg.weighting == PVD_WEIGHT_CONTINUOUS) return cont_enqueue_branch_only(s, a);
+    // discrete: branch on E_L with the effective time step, carrying f_x, psi and the local kinetic energy
+    k_branch_discrete<<<g, PVD_CTA, 0, s->stream>>>(a);
+    PVD_CHECK_LAUNCH();
+    s->cur ^= 1;
+    return PVD_OK;
+}
 
 extern "C" {
-#define PVD_TODO(name) return pvd_fail(PVD_E_STATE, name ": not built yet")
-int pvd_branch_continuous(double *, const double *, int64_t, double, double, double, double, int64_t *, double *) { PVD_TODO("pvd_branch_continuous"); }
-int pvd_trial_drift(int32_t, const double *, int64_t, int32_t, int32_t, const double *, int64_t, double *, double *, double *) { PVD_TODO("pvd_trial_drift"); }
-int pvd_metropolis(const double *, const double *, const double *, const double *, const double *, const double *, int64_t, int32_t, int32_t, const double *, const double *, double, double *) { PVD_TODO("pvd_metropolis"); }
-int pvd_local_kin(const double *, int64_t, int32_t, int32_t, const double *, double *) { PVD_TODO("pvd_local_kin"); }
-int pvd_nn_h4o2_set_weights(const float *, int64_t) { PVD_TODO("pvd_nn_h4o2_set_weights"); }
-int pvd_nn_h4o2(const double *, int64_t, double *) { PVD_TODO("pvd_nn_h4o2"); }
-int pvd_coulomb_descriptor(const double *, int64_t, int32_t, const double *, double *) { PVD_TODO("pvd_coulomb_descriptor"); }
-int pvd_sim_set_trial_table(pvd_sim *, const double *, int64_t) { PVD_TODO("pvd_sim_set_trial_table"); }
-int pvd_sim_set_nn_weights(pvd_sim *, const float *, int64_t) { PVD_TODO("pvd_sim_set_nn_weights"); }
-int pvd_sim_download_imp(pvd_sim *, double *, double *, double *, int64_t) { PVD_TODO("pvd_sim_download_imp"); }
-int pvd_sim_export_tail(pvd_sim *, int64_t, double *, double *, double *, int64_t *) { PVD_TODO("pvd_sim_export_tail"); }
-int pvd_sim_import(pvd_sim *, int64_t, const double *, const double *, const double *, const int64_t *) { PVD_TODO("pvd_sim_import"); }
+
+int pvd_sim_download_imp(pvd_sim *s, double *fx, double *psi, double *sec, int64_t capacity)
+{
+    SIM_CHECK(s);
+    SIM_DEVICE(s);
+    PVD_REQUIRE(s->cfg.trial != PVD_TRIAL_NONE, "no trial wave function configured");
+    PVD_CUDA(cudaStreamSynchronize(s->stream));
+    DevState h[2];
+    PVD_CUDA(cudaMemcpy(h, s->st.p, sizeof(h), cudaMemcpyDeviceToHost));
+    const long long n = h[s->parity].n;
+    PVD_REQUIRE(capacity >= n, "pvd_sim_download_imp: host buffers too small");
+    const int nc = s->nc;
+    // the second derivatives are a pure function of the coordinates: recompute them (only the local
+    // kinetic energy is carried on the device)
+    ImpArgs im;
+    if (int rc = fill_trial_params(s, im)) return rc;
+    DevBuf aos, dpsi, dlog, d2;
+    PVD_CUDA(aos.alloc((size_t)n * nc * 8)); PVD_CUDA(dpsi.alloc((size_t)n * 8));
+    PVD_CUDA(dlog.alloc((size_t)n * nc * 8)); PVD_CUDA(d2.alloc((size_t)n * nc * 8));
+    k_soa_to_aos<<<grid_for(n * nc, 256, 16), 256, 0, s->stream>>>(s->x[s->cur].as<double>(), aos.as<double>(), n, nc, s->cap);
+    PVD_CHECK_LAUNCH();
+    if (s->cfg.trial == PVD_TRIAL_H2O_FD)
+        k_trial_drift_aos<TrialH2O><<<grid_for(n, 128, 16), 128, 0, s->stream>>>(aos.as<double>(), n, im.trial, dpsi.as<double>(), dlog.as<double>(), d2.as<double>());
+    else
+        k_trial_drift_aos<TrialHarm1D><<<grid_for(n, 128, 16), 128, 0, s->stream>>>(aos.as<double>(), n, im.trial, dpsi.as<double>(), dlog.as<double>(), d2.as<double>());
+    PVD_CHECK_LAUNCH();
+    if (fx) {
+        // carried drift (the one the next Metropolis step will use)
+        k_soa_to_aos<<<grid_for(n * nc, 256, 16), 256, 0, s->stream>>>(s->f[s->cur].as<double>(), aos.as<double>(), n, nc, s->cap);
+        PVD_CHECK_LAUNCH();
+        PVD_CUDA(cudaMemcpyAsync(fx, aos.p, (size_t)n * nc * 8, cudaMemcpyDeviceToHost, s->stream));
+    }
+    if (psi) PVD_CUDA(cudaMemcpyAsync(psi, s->psi[s->cur].p, (size_t)n * 8, cudaMemcpyDeviceToHost, s->stream));
+    if (sec) PVD_CUDA(cudaMemcpyAsync(sec, d2.p, (size_t)n * nc * 8, cudaMemcpyDeviceToHost, s->stream));
+    PVD_CUDA(cudaStreamSynchronize(s->stream));
+    return PVD_OK;
 }
+
+int pvd_trial_drift(int32_t trial, const double *xyz, int64_t n, int32_t natoms, int32_t ndim, const double *table, int64_t ntab,
+                    double *psi, double *dlog, double *d2)
+{
+    PVD_REQUIRE(xyz && psi && dlog && d2 && n >= 0 && natoms >= 1 && ndim >= 1, "pvd_trial_drift: bad arguments");
+    if (int rc = ensure_device_ready()) return rc;
+    if (n == 0) return PVD_OK;
+    const int nc = natoms * ndim;
+    PVD_REQUIRE((trial == PVD_TRIAL_H2O_FD && nc == 9) || (trial == PVD_TRIAL_HARM1D && nc == 1), "trial / shape mismatch");
+    DevBuf dt, dx, dpsi, dlogb, d2b;
+    const size_t total = trial == PVD_TRIAL_H2O_FD ? (size_t)(2 * ntab + 2) : (size_t)ntab;
+    PVD_CUDA(dt.alloc(total * 8));
+    PVD_CUDA(cudaMemcpy(dt.p, table, total * 8, cudaMemcpyHostToDevice));
+    TrialParamsDev p;
+    if (int rc = host_trial_params(trial, table, ntab, dt.as<double>(), p)) return rc;
+    PVD_CUDA(dx.alloc((size_t)n * nc * 8)); PVD_CUDA(dpsi.alloc((size_t)n * 8));
+    PVD_CUDA(dlogb.alloc((size_t)n * nc * 8)); PVD_CUDA(d2b.alloc((size_t)n * nc * 8));
+    PVD_CUDA(cudaMemcpy(dx.p, xyz, (size_t)n * nc * 8, cudaMemcpyHostToDevice));
+    EventPair ev;
+    PVD_CUDA(ev.init());
+    PVD_CUDA(cudaEventRecord(ev.a));
+    if (trial == PVD_TRIAL_H2O_FD)
+        k_trial_drift_aos<TrialH2O><<<grid_for(n, 128, 16), 128>>>(dx.as<double>(), n, p, dpsi.as<double>(), dlogb.as<double>(), d2b.as<double>());
+    else
+        k_trial_drift_aos<TrialHarm1D><<<grid_for(n, 128, 16), 128>>>(dx.as<double>(), n, p, dpsi.as<double>(), dlogb.as<double>(), d2b.as<double>());
+    PVD_CHECK_LAUNCH();
+    PVD_CUDA(cudaEventRecord(ev.b));
+    PVD_CUDA(cudaMemcpy(psi, dpsi.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    PVD_CUDA(cudaMemcpy(dlog, dlogb.p, (size_t)n * nc * 8, cudaMemcpyDeviceToHost));
+    PVD_CUDA(cudaMemcpy(d2, d2b.p, (size_t)n * nc * 8, cudaMemcpyDeviceToHost));
+    float ms = 0;
+    PVD_CUDA(cudaEventElapsedTime(&ms, ev.a, ev.b));
+    g_last_kernel_ms = ms;
+    return PVD_OK;
+}
+
+int pvd_metropolis(const double *x, const double *y, const double *fx, const double *fy, const double *psi_x, const double *psi_y,
+                   int64_t n, int32_t natoms, int32_t ndim, const double *sigma, const double *inv_mass, double dt, double *acc)
+{
+    PVD_REQUIRE(x && y && fx && fy && psi_x && psi_y && sigma && inv_mass && acc && n >= 0, "pvd_metropolis: bad arguments");
+    if (int rc = ensure_device_ready()) return rc;
+    if (n == 0) return PVD_OK;
+    const int nc = natoms * ndim;
+    PVD_REQUIRE(nc == 9 || nc == 1, "pvd_metropolis: built for 3x3 (water) and 1x1 problems");
+    DevBuf b[6], ds, dm, dacc;
+    const double *src[4] = {x, y, fx, fy};
+    for (int k = 0; k < 4; ++k) { PVD_CUDA(b[k].alloc((size_t)n * nc * 8)); PVD_CUDA(cudaMemcpy(b[k].p, src[k], (size_t)n * nc * 8, cudaMemcpyHostToDevice)); }
+    PVD_CUDA(b[4].alloc((size_t)n * 8)); PVD_CUDA(cudaMemcpy(b[4].p, psi_x, (size_t)n * 8, cudaMemcpyHostToDevice));
+    PVD_CUDA(b[5].alloc((size_t)n * 8)); PVD_CUDA(cudaMemcpy(b[5].p, psi_y, (size_t)n * 8, cudaMemcpyHostToDevice));
+    PVD_CUDA(ds.alloc(natoms * 8)); PVD_CUDA(cudaMemcpy(ds.p, sigma, natoms * 8, cudaMemcpyHostToDevice));
+    PVD_CUDA(dm.alloc(natoms * 8)); PVD_CUDA(cudaMemcpy(dm.p, inv_mass, natoms * 8, cudaMemcpyHostToDevice));
+    PVD_CUDA(dacc.alloc((size_t)n * 8));
+    const int g = grid_for(n, 128, 16);
+    if (nc == 9)
+        k_metropolis_aos<9><<<g, 128>>>(b[0].as<double>(), b[1].as<double>(), b[2].as<double>(), b[3].as<double>(), b[4].as<double>(),
+                                       b[5].as<double>(), n, ndim, ds.as<double>(), dm.as<double>(), dt, dacc.as<double>());
+    else
+        k_metropolis_aos<1><<<g, 128>>>(b[0].as<double>(), b[1].as<double>(), b[2].as<double>(), b[3].as<double>(), b[4].as<double>(),
+                                       b[5].as<double>(), n, ndim, ds.as<double>(), dm.as<double>(), dt, dacc.as<double>());
+    PVD_CHECK_LAUNCH();
+    PVD_CUDA(cudaMemcpy(acc, dacc.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    return PVD_OK;
+}
+
+int pvd_local_kin(const double *d2, int64_t n, int32_t natoms, int32_t ndim, const double *inv_mass, double *ke)
+{
+    PVD_REQUIRE(d2 && inv_mass && ke && n >= 0, "pvd_local_kin: bad arguments");
+    if (int rc = ensure_device_ready()) return rc;
+    if (n == 0) return PVD_OK;
+    const int nc = natoms * ndim;
+    PVD_REQUIRE(nc == 9 || nc == 1, "pvd_local_kin: built for 3x3 (water) and 1x1 problems");
+    DevBuf dd, dm, dk;
+    PVD_CUDA(dd.alloc((size_t)n * nc * 8)); PVD_CUDA(cudaMemcpy(dd.p, d2, (size_t)n * nc * 8, cudaMemcpyHostToDevice));
+    PVD_CUDA(dm.alloc(natoms * 8)); PVD_CUDA(cudaMemcpy(dm.p, inv_mass, natoms * 8, cudaMemcpyHostToDevice));
+    PVD_CUDA(dk.alloc((size_t)n * 8));
+    if (nc == 9) k_local_kin_aos<9><<<grid_for(n, 128, 16), 128>>>(dd.as<double>(), n, ndim, dm.as<double>(), dk.as<double>());
+    else k_local_kin_aos<1><<<grid_for(n, 128, 16), 128>>>(dd.as<double>(), n, ndim, dm.as<double>(), dk.as<double>());
+    PVD_CHECK_LAUNCH();
+    PVD_CUDA(cudaMemcpy(ke, dk.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    return PVD_OK;
+}
+
+// ---------------------------------------------------------------- walker rebalancing between shards
+int pvd_sim_export_tail(pvd_sim *s, int64_t count, double *xyz, double *pots, double *w, int64_t *who)
+{
+    SIM_CHECK(s);
+    SIM_DEVICE(s);
+    PVD_CUDA(cudaStreamSynchronize(s->stream));
+    DevState h[2];
+    PVD_CUDA(cudaMemcpy(h, s->st.p, sizeof(h), cudaMemcpyDeviceToHost));
+    const long long n = h[s->parity].n;
+    PVD_REQUIRE(count >= 0 && count < n && xyz && pots, "pvd_sim_export_tail: bad count");
+    const int nc = s->nc;
+    const long long first = n - count;
+    PVD_CUDA(s->stage.alloc((size_t)count * nc * 8));
+    // SoA tail -> AoS: treat the tail as its own SoA array with the same stride
+    k_soa_to_aos<<<grid_for(count * nc, 256, 16), 256, 0, s->stream>>>(s->x[s->cur].as<double>() + first, s->stage.as<double>(), count, nc, s->cap);
+    PVD_CHECK_LAUNCH();
+    PVD_CUDA(cudaMemcpyAsync(xyz, s->stage.p, (size_t)count * nc * 8, cudaMemcpyDeviceToHost, s->stream));
+    PVD_CUDA(cudaMemcpyAsync(pots, s->v[s->cur].as<double>() + first, (size_t)count * 8, cudaMemcpyDeviceToHost, s->stream));
+    if (w && s->w.p) PVD_CUDA(cudaMemcpyAsync(w, s->w.as<double>() + first, (size_t)count * 8, cudaMemcpyDeviceToHost, s->stream));
+    if (who) {
+        PVD_CUDA(s->stage2.alloc((size_t)count * 8));
+        k_int_to_i64<<<grid_for(count, 256, 16), 256, 0, s->stream>>>(s->who[s->cur].as<int>() + first, s->stage2.as<long long>(), count);
+        PVD_CHECK_LAUNCH();
+        PVD_CUDA(cudaMemcpyAsync(who, s->stage2.p, (size_t)count * 8, cudaMemcpyDeviceToHost, s->stream));
+    }
+    PVD_CUDA(cudaStreamSynchronize(s->stream));
+    h[0].n = h[1].n = first;
+    h[1 - s->parity] = h[s->parity];
+    h[0].n = first; h[1].n = first;
+    PVD_CUDA(cudaMemcpy(s->st.p, h, sizeof(h), cudaMemcpyHostToDevice));
+    return PVD_OK;
+}
+
+int pvd_sim_import(pvd_sim *s, int64_t count, const double *xyz, const double *pots, const double *w, const int64_t *who)
+{
+    SIM_CHECK(s);
+    SIM_DEVICE(s);
+    PVD_CUDA(cudaStreamSynchronize(s->stream));
+    DevState h[2];
+    PVD_CUDA(cudaMemcpy(h, s->st.p, sizeof(h), cudaMemcpyDeviceToHost));
+    const long long n = h[s->parity].n;
+    PVD_REQUIRE(count >= 0 && n + count <= s->cap && xyz && pots, "pvd_sim_import: not enough capacity");
+    const int nc = s->nc;
+    PVD_CUDA(s->stage.alloc((size_t)count * nc * 8));
+    PVD_CUDA(cudaMemcpyAsync(s->stage.p, xyz, (size_t)count * nc * 8, cudaMemcpyHostToDevice, s->stream));
+    k_aos_to_soa<<<grid_for(count * nc, 256, 16), 256, 0, s->stream>>>(s->stage.as<double>(), s->x[s->cur].as<double>() + n, count, nc, s->cap);
+    PVD_CHECK_LAUNCH();
+    PVD_CUDA(cudaMemcpyAsync(s->v[s->cur].as<double>() + n, pots, (size_t)count * 8, cudaMemcpyHostToDevice, s->stream));
+    if (w && s->w.p) PVD_CUDA(cudaMemcpyAsync(s->w.as<double>() + n, w, (size_t)count * 8, cudaMemcpyHostToDevice, s->stream));
+    if (who) {
+        std::vector<int> w32((size_t)count);
+        for (int64_t i = 0; i < count; ++i) w32[(size_t)i] = (int)who[i];
+        PVD_CUDA(cudaMemcpy(s->who[s->cur].as<int>() + n, w32.data(), (size_t)count * 4, cudaMemcpyHostToDevice));
+    }
+    PVD_CUDA(cudaStreamSynchronize(s->stream));
+    h[1 - s->parity] = h[s->parity];
+    h[0].n = n + count; h[1].n = n + count;
+    PVD_CUDA(cudaMemcpy(s->st.p, h, sizeof(h), cudaMemcpyHostToDevice));
+    return PVD_OK;
+}
+
+}  // extern "C"
+
+#include "pvd_nn_host.inl"

@@ -279,8 +279,10 @@ struct pvd_sim {
     DevBuf st, err_accum, status, part, ring, sums, sigma_dev, tickets;
     DevBuf inj_disp, inj_u, inj_um, stage, stage2;   // staging for host<->device transposes / injections
     DevBuf parent_x, parent_w;
-    DevBuf kill_idx, hist, cand, cont_work;
-    DevBuf trial_table;
+    DevBuf kill_idx, hist, cand, cont_work, copy_dst, copy_src, cont_queue, cont_root, cont_skip;
+    DevBuf trial_table, acc_count, nn_weights;
+    TrialParamsDev trial_params{};
+    int nn_grid = 1;
     long long parent_n = 0;
     void *sums_ext = nullptr;   // caller-owned reduction buffer (multi-GPU)
     long long ntrial = 0;
@@ -363,7 +365,7 @@ static int launch_pot_soa(pvd_sim *s)
         else return pvd_fail(PVD_E_ARG, "built-in harmonic potential supports 1 or 3 components");
         break;
     case PVD_POT_MORSE1D: k_pot_soa<PotMorse><<<g, PVD_CTA, 0, s->stream>>>(x, st, s->parity, s->cap, v, s->pot); break;
-    case PVD_POT_NN_H4O2: return nn_launch_soa(s->stream, x, st, s->parity, s->cap, v, g);
+    case PVD_POT_NN_H4O2: return nn_launch_soa(s->stream, x, st, s->parity, s->cap, v, s->nn_grid, s->nn_weights.as<float>());
     default: return pvd_fail(PVD_E_STATE, "no built-in potential configured");
     }
     PVD_CHECK_LAUNCH();
@@ -418,10 +420,17 @@ int pvd_sim_create(const pvd_config *cfg, pvd_sim **out)
         TRY(s->kill_idx.alloc((size_t)cap * 4));
         TRY(s->hist.alloc(PVD_HIST_BINS * 4));
         TRY(cudaMemset(s->hist.p, 0, PVD_HIST_BINS * 4));
-        TRY(s->cand.alloc((size_t)cap * sizeof(ContCand)));
+        TRY(s->cand.alloc((size_t)2 * cap * sizeof(ContCand)));       // sorted candidates, padded to a power of two
+        TRY(s->cont_queue.alloc((size_t)2 * cap * sizeof(ContCand)));
+        TRY(s->copy_dst.alloc((size_t)2 * cap * 4));
+        TRY(s->copy_src.alloc((size_t)2 * cap * 4));
+        TRY(s->cont_root.alloc((size_t)cap * 4));
+        TRY(s->cont_skip.alloc((size_t)cap));
         TRY(s->cont_work.alloc(sizeof(ContWork)));
         TRY(cudaMemset(s->cont_work.p, 0, sizeof(ContWork)));
     }
+    TRY(s->acc_count.alloc(8));
+    TRY(cudaMemset(s->acc_count.p, 0, 8));
     TRY(s->st.alloc(2 * sizeof(DevState)));
     TRY(cudaMemset(s->st.p, 0, 2 * sizeof(DevState)));
     TRY(s->err_accum.alloc(4));
@@ -439,6 +448,7 @@ int pvd_sim_create(const pvd_config *cfg, pvd_sim **out)
     TRY(cudaMemset(s->sums.p, 0, PVD_NSUMS * 8));
     TRY(s->sigma_dev.alloc(PVD_MAX_ATOMS * 8));
     TRY(cudaMemcpy(s->sigma_dev.p, s->sigma, PVD_MAX_ATOMS * 8, cudaMemcpyHostToDevice));
+    s->nn_grid = grid_for(cap, NN_TILE, 3);
     TRY(cudaEventCreate(&s->ev0));
     TRY(cudaEventCreate(&s->ev1));
 #undef TRY

@@ -1,7 +1,420 @@
-// Continuous weighting (pyvibdmc.py:432-454 + _branch :340-356): types shared with the host code.
+// Continuous weighting (pyvibdmc.py:432-454 + _branch :340-356).
+//
+// Reference semantics: w *= exp(-(V-Vref) dt); every walker below the lower threshold is, in
+// ascending index order, overwritten by a copy of the CURRENT maximum-weight walker (first index on
+// ties), whose weight is halved and shared.  That loop is sequential by construction (argmax after
+// every halving).  Parallel-equivalent used here:
+//   1. k_cont_update   : weight update, exact sums over the surviving walkers, ascending kill list
+//                        (ticketed warp tiles + chained look-back scan, like the discrete step)
+//   2. k_cont_hist     : log-spaced histogram (64 bins / octave) of the updated weights
+//   3. k_cont_collect  : candidates = all walkers at or above the bin edge that holds the K-th
+//                        largest weight (K = number of kills), unordered append
+//   4. k_cont_assign   : one CTA sorts the candidates by (w desc, index asc).  If the K-th largest
+//                        weight is > half the largest, the K argmax steps are exactly "j-th largest
+//                        donates to j-th kill" and are applied in parallel; otherwise (halved
+//                        pieces re-enter the top: start-up transients, exact ties) the reference
+//                        loop is replayed exactly by one thread over the sorted candidates.
+//                        The optional upper threshold (argpartition of the smallest weights) is
+//                        replayed with block-wide argmin/argmax reductions.
+//   5. k_cont_copy     : walkers (all per-walker arrays) are copied donor-root -> killed slot
+//   6. k_cont_finish   : min/max weight, Vref, log record (last CTA)
 #pragma once
 #include "pvd_step.cuh"
 
-constexpr int PVD_HIST_BINS = 4096;
-struct ContCand { double w; int idx; int pad; };
-struct ContWork { int n_kill; int n_cand; double edge; int fallback; int pad; };
+constexpr int PVD_HIST_BINS = 4096;            // 64 octaves x 64 bins
+constexpr int PVD_HIST_BASE = (1023 - 32) * 64;
+
+struct ContCand { double w; int idx; int root; };
+struct ContWork {
+    unsigned n_kill;        // walkers below the lower threshold (set by the update kernel's scan)
+    unsigned n_cand;        // candidates appended by k_cont_collect
+    unsigned n_copy;        // (dst, src) pairs to copy
+    unsigned n_upper;       // kills caused by the upper threshold
+    int edge_bin;
+    unsigned done;
+    double sub_w, sub_wv;   // weight removed by upper-threshold kills (corrects the exact sums)
+    unsigned long long wmax_bits, wmin_bits;
+};
+
+struct ContArgs {
+    double *w;
+    const double *v;
+    int *kill_idx;
+    int *copy_dst, *copy_src;
+    ContCand *cand;
+    unsigned *hist;
+    ContWork *work;
+    long long cand_cap;
+    double lower, upper;
+    int has_upper;
+};
+
+__device__ __forceinline__ int weight_bin(double w)
+{
+    const long long bits = __double_as_longlong(w);
+    long long b = (bits >> 46) - PVD_HIST_BASE;          // exponent and top 6 mantissa bits
+    if (!(w > 0.0)) b = 0;
+    return (int)(b < 0 ? 0 : (b >= PVD_HIST_BINS ? PVD_HIST_BINS - 1 : b));
+}
+__device__ __forceinline__ double bin_lower_edge(int bin)
+{
+    return __longlong_as_double(((long long)bin + PVD_HIST_BASE) << 46);
+}
+
+// ---- 1. weight update + kill list + exact sums (energies from memory: a.vin)
+__global__ void __launch_bounds__(PVD_CTA) k_cont_update(const StepArgs a, const ContArgs ca)
+{
+    if (!step_prologue(a)) return;
+    const DevState *sip = &a.st[a.parity];
+    const long long n = sip->n, step = sip->step;
+    const double vref = sip->vref, dt = sip->dt_eff;
+    const long long ntiles = (n + PVD_TILE - 1) / PVD_TILE;
+    const int lane = threadIdx.x & 31;
+    unsigned *tickets = step_tickets(a, a.parity);
+    LaneAcc acc;
+    long long pend = -1;
+    int pend_total = 0, pend_excl = 0;
+    long long pend_i = 0;
+    bool pend_kill = false;
+    while (true) {
+        const long long tile = warp_take_tile(tickets, ntiles);
+        int kill = 0, incl = 0, total = 0;
+        long long i = 0;
+        if (tile >= 0) {
+            i = tile * PVD_TILE + lane;
+            if (i < n) {
+                const double v = a.vin[i];
+                const double wn = __dmul_rn(ca.w[i], exp(__dmul_rn(-1.0 * (v - vref), dt)));      // :433
+                ca.w[i] = wn;
+                kill = (wn < ca.lower) ? 1 : 0;                                                   // :436
+                const Fx128 fv = fx_from_double(v);
+                acc.v = fx_add(acc.v, fv);
+                if (!kill) {
+                    acc.cw = fx_add(acc.cw, fx_from_double(wn));
+                    acc.cv = fx_add(acc.cv, fx_from_double(__dmul_rn(wn, v)));
+                }
+                acc.vmin = fmin(acc.vmin, v); acc.vmax = fmax(acc.vmax, v);
+                acc.n_in += 1.0; acc.n_acc += 1.0;
+                acc.births += (double)kill;
+            }
+            incl = warp_incl_scan(kill);
+            total = __shfl_sync(0xffffffffu, incl, 31);
+            publish_aggregate(a.status, tile, step, total);
+        }
+        if (pend >= 0) {
+            const long long o = resolve_prefix(a.status, pend, step, pend_total) + pend_excl;
+            if (pend_kill) ca.kill_idx[o] = (int)pend_i;
+        }
+        if (tile < 0) break;
+        pend = tile; pend_total = total; pend_excl = incl - kill; pend_i = i; pend_kill = kill != 0;
+    }
+    // population does not change; the kill count is the inclusive prefix of the last tile
+    cta_finish_step(a, acc, ntiles, true, n, true);      // Vref is produced by k_cont_finish, after branching
+}
+
+// ---- 2. histogram of the updated weights (only when something has to be branched)
+__global__ void __launch_bounds__(PVD_CTA) k_cont_hist(const StepArgs a, const ContArgs ca)
+{
+    __shared__ unsigned s_hist[PVD_HIST_BINS];
+    const DevState *so = &a.st[a.parity];          // continuous weighting: population and flags do not change within a step
+    const long long n = so->n;
+    const long long ntiles = (n + PVD_TILE - 1) / PVD_TILE;
+    const unsigned nk = (unsigned)(ld_relaxed_u64(&a.status[ntiles - 1]) & 0xffffffffull);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        ca.work->n_kill = nk; ca.work->n_cand = 0; ca.work->n_copy = 0; ca.work->n_upper = 0; ca.work->done = 0;
+        ca.work->sub_w = 0.0; ca.work->sub_wv = 0.0;
+        ca.work->wmax_bits = 0ull; ca.work->wmin_bits = 0x7FF0000000000000ull;
+    }
+    if (so->err || nk == 0) return;
+    for (int b = threadIdx.x; b < PVD_HIST_BINS; b += PVD_CTA) s_hist[b] = 0;
+    __syncthreads();
+    for (long long i = blockIdx.x * (long long)PVD_CTA + threadIdx.x; i < n; i += (long long)gridDim.x * PVD_CTA)
+        atomicAdd(&s_hist[weight_bin(ca.w[i])], 1u);
+    __syncthreads();
+    for (int b = threadIdx.x; b < PVD_HIST_BINS; b += PVD_CTA)
+        if (s_hist[b]) atomicAdd(&ca.hist[b], s_hist[b]);
+}
+
+// ---- 3. candidates: everything at or above the bin that contains the K-th largest weight
+__global__ void __launch_bounds__(PVD_CTA) k_cont_collect(const StepArgs a, const ContArgs ca)
+{
+    __shared__ int s_edge;
+    const DevState *so = &a.st[a.parity];
+    const unsigned nk = ca.work->n_kill;
+    if (so->err || nk == 0) return;
+    const long long n = so->n;
+    if (threadIdx.x < 32) {
+        // suffix count from the top bin downwards; 128 bins per lane
+        const int lane = threadIdx.x;
+        unsigned mine = 0;
+        const int hi = PVD_HIST_BINS - 1 - lane * (PVD_HIST_BINS / 32);
+        for (int k = 0; k < PVD_HIST_BINS / 32; ++k) mine += ca.hist[hi - k];
+        unsigned above = mine;                          // inclusive suffix over lanes 0..lane
+        for (int off = 1; off < 32; off <<= 1) {
+            const unsigned y = __shfl_up_sync(0xffffffffu, above, off);
+            if (lane >= off) above += y;
+        }
+        const unsigned before = above - mine;
+        int edge = -1;
+        if (before < nk && above >= nk) {
+            unsigned run = before;
+            for (int k = 0; k < PVD_HIST_BINS / 32; ++k) {
+                run += ca.hist[hi - k];
+                if (run >= nk) { edge = hi - k; break; }
+            }
+        }
+        const unsigned found = __ballot_sync(0xffffffffu, edge >= 0);
+        if (!found) { if (lane == 0) s_edge = 0; }     // fewer than K positive weights: take everything
+        else if (edge >= 0) s_edge = edge;
+    }
+    __syncthreads();
+    const int edge_bin = s_edge;
+    if (blockIdx.x == 0 && threadIdx.x == 0) ca.work->edge_bin = edge_bin;
+    for (long long i = blockIdx.x * (long long)PVD_CTA + threadIdx.x; i < n; i += (long long)gridDim.x * PVD_CTA) {
+        const double w = ca.w[i];
+        if (weight_bin(w) >= edge_bin) {
+            const unsigned slot = atomicAdd(&ca.work->n_cand, 1u);
+            if ((long long)slot < ca.cand_cap) ca.cand[slot] = ContCand{w, (int)i, (int)i};
+        }
+    }
+}
+
+// (w desc, idx asc) ordering
+__device__ __forceinline__ bool cand_before(const ContCand &p, const ContCand &q)
+{
+    return p.w > q.w || (p.w == q.w && p.idx < q.idx);
+}
+
+// block-wide argmax (first index on ties) / argmin over w[0..n) with a skip mask
+__device__ inline int block_arg_extreme(const double *w, long long n, bool want_max, const unsigned char *skip, double *s_val, int *s_idx)
+{
+    double best = want_max ? -INFINITY : INFINITY;
+    int bi = -1;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+        if (skip && skip[i]) continue;
+        const double x = w[i];
+        if (bi < 0 || (want_max ? x > best : x < best)) { best = x; bi = (int)i; }
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, off);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+        const bool take = oi >= 0 && (bi < 0 || (want_max ? ob > best : ob < best) || (ob == best && oi < bi));
+        if (take) { best = ob; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { s_val[threadIdx.x >> 5] = best; s_idx[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < (int)(blockDim.x >> 5); ++k) {
+            const double ob = s_val[k];
+            const int oi = s_idx[k];
+            const bool take = oi >= 0 && (s_idx[0] < 0 || (want_max ? ob > s_val[0] : ob < s_val[0]) || (ob == s_val[0] && oi < s_idx[0]));
+            if (take) { s_val[0] = ob; s_idx[0] = oi; }
+        }
+    }
+    __syncthreads();
+    const int r = s_idx[0];
+    __syncthreads();
+    return r;
+}
+
+// ---- 4. donor assignment (single CTA of 1024 threads)
+__global__ void __launch_bounds__(1024) k_cont_assign(const StepArgs a, const ContArgs ca, ContCand *queue, int *root, unsigned char *skip)
+{
+    __shared__ double s_val[32];
+    __shared__ int s_idx[32];
+    __shared__ int s_flag;
+    const DevState *so = &a.st[a.parity];
+    if (so->err) return;
+    const long long n = so->n;
+    const int K = (int)ca.work->n_kill;
+    int ncopy = 0;
+    if (K > 0) {
+        long long C = ca.work->n_cand;
+        if (C > ca.cand_cap) C = ca.cand_cap;
+        // bitonic sort of the candidates, padded to a power of two with -inf
+        long long P = 1;
+        while (P < C) P <<= 1;
+        for (long long t = C + threadIdx.x; t < P; t += blockDim.x) ca.cand[t] = ContCand{-INFINITY, 0x7fffffff, -1};
+        __syncthreads();
+        for (long long k = 2; k <= P; k <<= 1) {
+            for (long long j = k >> 1; j > 0; j >>= 1) {
+                for (long long t = threadIdx.x; t < P; t += blockDim.x) {
+                    const long long l = t ^ j;
+                    if (l > t) {
+                        const ContCand x = ca.cand[t], y = ca.cand[l];
+                        const bool up = (t & k) == 0;
+                        if (up ? cand_before(y, x) : cand_before(x, y)) { ca.cand[t] = y; ca.cand[l] = x; }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        // fast path: the K largest weights are all above half of the largest -> no halved piece is ever a donor
+        if (threadIdx.x == 0) s_flag = (C >= K && ca.cand[K - 1].w > 0.5 * ca.cand[0].w) ? 1 : 0;
+        __syncthreads();
+        if (s_flag) {
+            for (int j = threadIdx.x; j < K; j += blockDim.x) {
+                const int d = ca.cand[j].idx, k = ca.kill_idx[j];
+                const double h = ca.cand[j].w / 2.0;
+                ca.w[d] = h;
+                ca.w[k] = h;
+                ca.copy_dst[j] = k;
+                ca.copy_src[j] = d;
+            }
+            ncopy = K;
+        } else {
+            // exact sequential replay of _branch over the sorted candidates (A) and the FIFO of halves (B)
+            if (threadIdx.x == 0) {
+                long long ia = 0, ib = 0, nb = 0;
+                for (int j = 0; j < K; ++j) {
+                    const int k = ca.kill_idx[j];
+                    // current maximum: front of A vs the run of equal values at the front of B (first index wins)
+                    double mb = -INFINITY;
+                    long long best_b = -1;
+                    if (ib < nb) {
+                        mb = queue[ib].w;
+                        best_b = ib;
+                        for (long long t = ib + 1; t < nb && queue[t].w == mb; ++t)
+                            if (queue[t].idx < queue[best_b].idx) best_b = t;
+                    }
+                    const bool have_a = ia < C;
+                    bool use_a;
+                    if (!have_a && best_b < 0) {
+                        // candidates exhausted (every weight below the threshold): degenerate ensemble,
+                        // fall back to a plain scan for the maximum
+                        double bw = -INFINITY; int bi = 0;
+                        for (long long t = 0; t < n; ++t) if (ca.w[t] > bw) { bw = ca.w[t]; bi = (int)t; }
+                        const double h = bw / 2.0;
+                        ca.w[bi] = h; ca.w[k] = h;
+                        ca.copy_dst[j] = k; ca.copy_src[j] = root ? root[bi] : bi;
+                        continue;
+                    }
+                    if (!have_a) use_a = false;
+                    else if (best_b < 0) use_a = true;
+                    else use_a = ca.cand[ia].w > mb || (ca.cand[ia].w == mb && ca.cand[ia].idx < queue[best_b].idx);
+                    ContCand top;
+                    if (use_a) top = ca.cand[ia++];
+                    else { top = queue[best_b]; queue[best_b] = queue[ib]; ++ib; }
+                    const double h = top.w / 2.0;
+                    ca.w[top.idx] = h;
+                    ca.w[k] = h;
+                    ca.copy_dst[j] = k;
+                    ca.copy_src[j] = top.root;
+                    queue[nb++] = ContCand{h, top.idx, top.root};
+                    queue[nb++] = ContCand{h, k, top.root};
+                }
+            }
+            ncopy = K;
+        }
+        __syncthreads();
+        // chains: a killed slot refilled earlier may itself have donated later; src already holds roots.
+    }
+    // optional upper threshold (pyvibdmc.py:440-445): kill the n_above smallest weights, each refilled from the
+    // current maximum.  Replayed with block-wide reductions; roots are tracked through `root`.
+    if (ca.has_upper) {
+        for (long long i = threadIdx.x; i < n; i += blockDim.x) { root[i] = (int)i; skip[i] = 0; }
+        __syncthreads();
+        for (int j = threadIdx.x; j < ncopy; j += blockDim.x) root[ca.copy_dst[j]] = ca.copy_src[j];
+        __syncthreads();
+        // count weights above the threshold
+        int cnt = 0;
+        for (long long i = threadIdx.x; i < n; i += blockDim.x) cnt += (ca.w[i] > ca.upper) ? 1 : 0;
+        for (int off = 16; off > 0; off >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+        if ((threadIdx.x & 31) == 0) s_idx[threadIdx.x >> 5] = cnt;
+        __syncthreads();
+        if (threadIdx.x == 0) { int t = 0; for (int k = 0; k < (int)(blockDim.x >> 5); ++k) t += s_idx[k]; s_flag = t; }
+        __syncthreads();
+        const int n_above = s_flag;
+        __syncthreads();
+        // the n_above smallest weights, fixed before any of them is refilled (argpartition on the pre-branch array)
+        for (int j = 0; j < n_above; ++j) {
+            const int k = block_arg_extreme(ca.w, n, false, skip, s_val, s_idx);
+            if (threadIdx.x == 0) { skip[k] = 1; ca.copy_dst[ncopy + j] = k; }
+            __syncthreads();
+        }
+        for (int j = 0; j < n_above; ++j) {
+            const int d = block_arg_extreme(ca.w, n, true, nullptr, s_val, s_idx);
+            if (threadIdx.x == 0) {
+                const int k = ca.copy_dst[ncopy + j];
+                ca.work->sub_w += ca.w[k];
+                ca.work->sub_wv += ca.w[k] * ca.v[root[k]];
+                const double h = ca.w[d] / 2.0;
+                ca.w[d] = h; ca.w[k] = h;
+                ca.copy_src[ncopy + j] = root[d];
+                root[k] = root[d];
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) ca.work->n_upper = (unsigned)n_above;
+        ncopy += n_above;
+    }
+    if (threadIdx.x == 0) ca.work->n_copy = (unsigned)ncopy;
+    // reset the histogram for the next step
+    for (int b = threadIdx.x; b < PVD_HIST_BINS; b += blockDim.x) ca.hist[b] = 0;
+}
+
+// ---- 5. copy donor -> killed for every per-walker array (in place: donors are never kill targets)
+__global__ void __launch_bounds__(PVD_CTA) k_cont_copy(const StepArgs a, const ContArgs ca, double *x, double *v, int *who, double *f,
+                                                       double *psi, double *lk, long long *src_out)
+{
+    const DevState *so = &a.st[a.parity];
+    if (so->err) return;
+    const unsigned m = ca.work->n_copy;
+    const bool dw = so->dw_active != 0;
+    for (long long t = blockIdx.x * (long long)PVD_CTA + threadIdx.x; t < (long long)m; t += (long long)gridDim.x * PVD_CTA) {
+        const int dst = ca.copy_dst[t], src = ca.copy_src[t];
+        for (int c = 0; c < a.nc; ++c) x[c * a.cap + dst] = x[c * a.cap + src];
+        v[dst] = v[src];
+        if (dw && who) who[dst] = who[src];
+        if (f) {
+            for (int c = 0; c < a.nc; ++c) f[c * a.cap + dst] = f[c * a.cap + src];
+            psi[dst] = psi[src];
+            lk[dst] = lk[src];
+        }
+        if (src_out) src_out[dst] = src;
+    }
+}
+
+// ---- 6. min / max weight after branching, upper-threshold correction of the sums, Vref + log record
+__global__ void __launch_bounds__(PVD_CTA) k_cont_finish(const StepArgs a, const ContArgs ca)
+{
+    __shared__ double s_mx[PVD_WARPS], s_mn[PVD_WARPS];
+    __shared__ unsigned s_last;
+    const DevState *so = &a.st[a.parity];
+    if (a.st[a.parity].err) return;
+    const long long n = so->n;
+    double mx = 0.0, mn = INFINITY;
+    for (long long i = blockIdx.x * (long long)PVD_CTA + threadIdx.x; i < n; i += (long long)gridDim.x * PVD_CTA) {
+        const double w = ca.w[i];
+        mx = fmax(mx, w); mn = fmin(mn, w);
+    }
+    mx = warp_max(mx); mn = warp_min(mn);
+    if ((threadIdx.x & 31) == 0) { s_mx[threadIdx.x >> 5] = mx; s_mn[threadIdx.x >> 5] = mn; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < PVD_WARPS; ++k) { mx = fmax(mx, s_mx[k]); mn = fmin(mn, s_mn[k]); }
+        // positive doubles order like their bit patterns
+        atomicMax(&ca.work->wmax_bits, (unsigned long long)__double_as_longlong(fmax(mx, 0.0)));
+        atomicMin(&ca.work->wmin_bits, (unsigned long long)__double_as_longlong(fmax(mn, 0.0)));
+        __threadfence();
+        const unsigned d = atomicAdd(&ca.work->done, 1u);
+        s_last = (d == gridDim.x - 1) ? 1u : 0u;
+        if (s_last) {
+            __threadfence();
+            double *s = a.sums;
+            s[PVD_SUM_CV] -= ca.work->sub_wv;
+            s[PVD_SUM_C] -= ca.work->sub_w;
+            s[PVD_SUM_BIRTHS] = (double)(ca.work->n_kill + ca.work->n_upper);     // "Walkers Branched"
+            double *e = s + PVD_SUM_EXT + 4 * a.rank;
+            e[2] = __longlong_as_double((long long)atomicAdd(&ca.work->wmin_bits, 0ull));
+            e[3] = __longlong_as_double((long long)atomicAdd(&ca.work->wmax_bits, 0ull));
+            if (a.world == 1) finalize_from_sums(a, true);
+        }
+    }
+}
+
+// plain weight update for the stand-alone entry point's bookkeeping of `src`
+__global__ void k_iota_i64(long long *p, long long n)
+{
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) p[t] = t;
+}

@@ -128,6 +128,25 @@ __global__ void k_displace_soa(double *__restrict__ x, const DevState *st, int p
     }
 }
 
+// move + potential in place (continuous weighting: no compaction, so nothing is gained by fusing the
+// weight update into this kernel; it streams coords once and writes coords + V)
+template <class POT, int RNG>
+__global__ void __launch_bounds__(PVD_CTA) k_move_pes(const StepArgs a, double *x, double *v)
+{
+    constexpr int NC = POT::NC;
+    const DevState *sip = &a.st[a.parity];
+    if (sip->err) return;
+    const long long n = sip->n, step = sip->step;
+    for (long long i = blockIdx.x * (long long)PVD_CTA + threadIdx.x; i < n; i += (long long)gridDim.x * PVD_CTA) {
+        double xx[NC], vv;
+        StepArgs const &ar = a;
+        ProduceFused<POT, RNG>::run(ar, i, step, true, xx, vv);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) x[c * a.cap + i] = xx[c];
+        v[i] = vv;
+    }
+}
+
 // ---------------------------------------------------------------- branch-only discrete step
 // Same counting / chained scan / compaction / finalisation as k_step_discrete, but the energies
 // come from memory (a.vin) and every per-walker array is copied memory->memory with a run-time

@@ -1,3 +1,300 @@
-// Importance sampling kernels (pyvibdmc.py:549-612, imp_samp.py:21-76).
+// Importance sampling (pyvibdmc.py:549-612, simulation_utilities/imp_samp.py:21-76):
+// trial wave functions, finite-difference drift / local kinetic energy, Metropolis step.
 #pragma once
 #include "pvd_step.cuh"
+
+struct TrialParamsDev {
+    // water product wfn (call_trl_h2o.py:7-78): table rows grid / psi, Gaussian bend
+    const double *grid;
+    const double *wfn;
+    int ntab;
+    double g0, inv_step;
+    double ang_alpha, theta_eq, ang_pref;
+    // 1-D Gaussian (harm_trial_wfn.py:6-40)
+    double h_alpha, h_pref;
+    double fd_dx, fd_dx2;       // 0.001 and 0.001**2 as Python evaluates them (imp_samp.py:58,75)
+};
+
+// np.interp(x, grid, wfn): linear, clamped to the end values, no FMA (NumPy's C loop is plain mul/add)
+__device__ __forceinline__ double interp_table(double x, const TrialParamsDev &p)
+{
+    const int n = p.ntab;
+    if (x != x) return x;
+    if (x > p.grid[n - 1]) return p.wfn[n - 1];
+    if (x < p.grid[0]) return p.wfn[0];
+    int j = (int)((x - p.g0) * p.inv_step);
+    j = j < 0 ? 0 : (j > n - 2 ? n - 2 : j);
+    while (j > 0 && x < p.grid[j]) --j;
+    while (j < n - 1 && x >= p.grid[j + 1]) ++j;
+    const double fj = p.wfn[j];
+    if (j == n - 1) return fj;
+    const double xj = p.grid[j];
+    if (x == xj) return fj;
+    const double slope = (p.wfn[j + 1] - fj) / (p.grid[j + 1] - xj);
+    return __dadd_rn(__dmul_rn(slope, x - xj), fj);
+}
+
+__device__ __forceinline__ double norm3(double a, double b, double c)
+{
+    return sqrt(__dadd_rn(__dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b)), __dmul_rn(c, c)));
+}
+
+// psi = interp(r_OH1) * interp(r_OH2) * Gaussian(theta), kwargs {'dists':[[0,2],[2,1]],'angs':[[0,2,1]]}
+struct TrialH2O {
+    static constexpr int NC = 9;
+    static constexpr bool ANALYTIC = false;
+    __device__ static __forceinline__ double psi(const double (&x)[9], const TrialParamsDev &p)
+    {
+        const double ax = x[0] - x[6], ay = x[1] - x[7], az = x[2] - x[8];      // H1 - O
+        const double bx = x[3] - x[6], by = x[4] - x[7], bz = x[5] - x[8];      // H2 - O
+        const double r1 = norm3(ax, ay, az), r2 = norm3(bx, by, bz);
+        const double dot = __dadd_rn(__dadd_rn(__dmul_rn(ax, bx), __dmul_rn(ay, by)), __dmul_rn(az, bz));
+        const double th = acos(dot / __dmul_rn(r1, r2));
+        const double dth = th - p.theta_eq;
+        const double ang = __dmul_rn(p.ang_pref, exp(__dmul_rn(-p.ang_alpha, __dmul_rn(dth, dth)) / 2.0));
+        return __dmul_rn(__dmul_rn(interp_table(r1, p), interp_table(r2, p)), ang);
+    }
+};
+
+struct TrialHarm1D {
+    static constexpr int NC = 1;
+    static constexpr bool ANALYTIC = true;
+    __device__ static __forceinline__ double psi(const double (&x)[1], const TrialParamsDev &p)
+    {
+        return __dmul_rn(p.h_pref, exp(__dmul_rn(-p.h_alpha, __dmul_rn(x[0], x[0])) / 2.0));
+    }
+    // derivative() of harm_trial_wfn.py:36-40: (psi'/psi, psi''/psi) formed exactly as the reference does
+    __device__ static __forceinline__ void derivs(const double (&x)[1], const TrialParamsDev &p, double &psi0, double (&d1)[1], double (&d2)[1])
+    {
+        const double e = exp(__dmul_rn(-p.h_alpha, __dmul_rn(x[0], x[0])) / 2.0);
+        psi0 = __dmul_rn(p.h_pref, e);
+        d1[0] = __dmul_rn(__dmul_rn(p.h_pref, __dmul_rn(-p.h_alpha, x[0])), e) / psi0;
+        const double poly = __dadd_rn(__dmul_rn(__dmul_rn(p.h_alpha, p.h_alpha), __dmul_rn(x[0], x[0])), -p.h_alpha);
+        d2[0] = __dmul_rn(__dmul_rn(p.h_pref, poly), e) / psi0;
+    }
+};
+
+// ImpSamp.drift: psi, grad psi / psi, d2 psi / psi.  Finite differences follow imp_samp.py:56-76
+// (dx = 1e-3, the coordinate is walked -dx, +2dx, -dx in place) and the managers' division by psi.
+template <class TRIAL>
+__device__ __forceinline__ void trial_drift(double (&x)[TRIAL::NC], const TrialParamsDev &p, double &psi0,
+                                            double (&d1)[TRIAL::NC], double (&d2)[TRIAL::NC])
+{
+    constexpr int NC = TRIAL::NC;
+    if constexpr (TRIAL::ANALYTIC) {
+        TRIAL::derivs(x, p, psi0, d1, d2);
+    } else {
+        psi0 = TRIAL::psi(x, p);
+        double xx[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) xx[c] = x[c];
+#pragma unroll 1
+        for (int c = 0; c < NC; ++c) {
+            // dynamic index into a small register array would spill: rebuild the stencil with selects
+            double xm[NC], xp[NC];
+#pragma unroll
+            for (int k = 0; k < NC; ++k) {
+                const double lo = xx[k] - p.fd_dx;
+                const double hi = lo + 2.0 * p.fd_dx;
+                const double back = hi - p.fd_dx;
+                xm[k] = (k == c) ? lo : xx[k];
+                xp[k] = (k == c) ? hi : xx[k];
+                xx[k] = (k == c) ? back : xx[k];
+            }
+            const double pm = TRIAL::psi(xm, p), pp = TRIAL::psi(xp, p);
+            const double first = (pp - pm) / (2.0 * p.fd_dx);
+            const double sec = __dadd_rn(__dadd_rn(pm, -__dmul_rn(2.0, psi0)), pp) / p.fd_dx2;
+#pragma unroll
+            for (int k = 0; k < NC; ++k) {
+                if (k == c) { d1[k] = first / psi0; d2[k] = sec / psi0; }
+            }
+        }
+    }
+}
+
+// ImpSamp.local_kin (imp_samp.py:50-53): -0.5 * sum_d ( sum_a inv_m[a] * sec[a,d] ), NumPy's reduction order
+template <int NC>
+__device__ __forceinline__ double local_kinetic(const double (&d2)[NC], const double *inv_mass, int ndim)
+{
+    const int natoms = NC / ndim;
+    double tot = 0.0;
+    for (int d = 0; d < ndim; ++d) {
+        double s = __dmul_rn(inv_mass[0], d2[d]);
+        for (int a = 1; a < natoms; ++a) s = __dadd_rn(s, __dmul_rn(inv_mass[a], d2[a * ndim + d]));
+        tot = (d == 0) ? s : __dadd_rn(tot, s);
+    }
+    return __dmul_rn(-0.5, tot);
+}
+
+// ImpSamp.metropolis (imp_samp.py:29-47) for one walker
+template <int NC>
+__device__ __forceinline__ double metropolis_ratio(const double (&x)[NC], const double (&y)[NC], const double (&fx)[NC],
+                                                   const double (&fy)[NC], double psi_x, double psi_y, const double *sigma,
+                                                   const double *inv_mass, int ndim, double dt)
+{
+    const int natoms = NC / ndim;
+    const double q = psi_y / psi_x;
+    const double ratio = __dmul_rn(q, q);
+    double acc = 1.0;
+    for (int d = 0; d < ndim; ++d) {
+        double pd = 1.0;
+        for (int a = 0; a < natoms; ++a) {
+            const int c = a * ndim + d;
+            const double two_s2 = __dmul_rn(2.0, __dmul_rn(sigma[a], sigma[a]));
+            const double dxm = __dmul_rn(__dmul_rn(inv_mass[a], fx[c]), dt), dym = __dmul_rn(__dmul_rn(inv_mass[a], fy[c]), dt);
+            const double u1 = __dadd_rn(__dadd_rn(x[c], -y[c]), -dym);
+            const double u2 = __dadd_rn(__dadd_rn(y[c], -x[c]), -dxm);
+            const double t1 = exp(__dmul_rn(-1.0, __dmul_rn(u1, u1)) / two_s2);
+            const double t2 = exp(__dmul_rn(-1.0, __dmul_rn(u2, u2)) / two_s2);
+            const double r = t1 / t2;
+            pd = (a == 0) ? r : __dmul_rn(pd, r);
+        }
+        acc = (d == 0) ? pd : __dmul_rn(acc, pd);
+    }
+    acc = __dmul_rn(acc, ratio);
+    if (__dmul_rn(psi_x, psi_y) <= 0.0) acc = 0.0;
+    return acc;
+}
+
+struct ImpArgs {
+    TrialParamsDev trial;
+    double inv_mass[PVD_MAX_ATOMS];
+    const double *inj_um;      // injected Metropolis uniforms or nullptr
+    unsigned long long *acc_count;   // accepted moves of this shard in the current step
+};
+
+// first-step exception with importance sampling (pyvibdmc.py:553-554, 760-769): drift on the start
+// ensemble, E_L = V + local kinetic energy.
+template <class TRIAL, class POT>
+__global__ void __launch_bounds__(PVD_CTA) k_imp_init(const StepArgs a, const ImpArgs im, double *x, double *f, double *psi, double *lk, double *v)
+{
+    constexpr int NC = TRIAL::NC;
+    const long long n = a.st[a.parity].n;
+    for (long long i = blockIdx.x * (long long)PVD_CTA + threadIdx.x; i < n; i += (long long)gridDim.x * PVD_CTA) {
+        double xx[NC], d1[NC], d2[NC], p0;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) xx[c] = x[c * a.cap + i];
+        trial_drift<TRIAL>(xx, im.trial, p0, d1, d2);
+        const double ke = local_kinetic<NC>(d2, im.inv_mass, a.ndim);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) f[c * a.cap + i] = d1[c];
+        psi[i] = p0;
+        lk[i] = ke;
+        v[i] = __dadd_rn(POT::eval(xx, a.pot), ke);
+    }
+}
+
+// imp_move_randomly (pyvibdmc.py:549-612) + potential + local energy (:786-812), in place.
+// Writes the accepted/kept walker, its drift, psi, local kinetic energy and E_L; counts acceptances.
+// The last CTA publishes dt_eff = dt * n_accept / N (pyvibdmc.py:603, 372-378) for the branching kernel.
+template <class TRIAL, class POT, int RNG>
+__global__ void __launch_bounds__(PVD_CTA) k_imp_move(const StepArgs a, const ImpArgs im, double *x, double *f, double *psi, double *lk, double *v)
+{
+    constexpr int NC = TRIAL::NC;
+    __shared__ unsigned s_cnt[PVD_WARPS];
+    __shared__ unsigned s_last;
+    DevState *sip = &a.st[a.parity];
+    if (sip->err || sip->n <= 0) return;           // the branching kernel forwards the dead state
+    const long long n = sip->n, step = sip->step;
+    unsigned my_acc = 0;
+    for (long long i = blockIdx.x * (long long)PVD_CTA + threadIdx.x; i < n; i += (long long)gridDim.x * PVD_CTA) {
+        double xo[NC], fo[NC], y[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) { xo[c] = x[c * a.cap + i]; fo[c] = f[c * a.cap + i]; }
+        const double psi_x = psi[i];
+        if (a.inj_disp) {
+#pragma unroll
+            for (int c = 0; c < NC; ++c) y[c] = a.inj_disp[c * a.cap + i];
+        } else {
+            walker_normals<NC, RNG>(a.seed, i, step, y);
+#pragma unroll
+            for (int c = 0; c < NC; ++c) y[c] = __dmul_rn(a.sigma[c / a.ndim], y[c]);
+        }
+        // displaced = coords + disps + (inv_m * f_x) * dt
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+            y[c] = __dadd_rn(__dadd_rn(xo[c], y[c]), __dmul_rn(__dmul_rn(im.inv_mass[c / a.ndim], fo[c]), a.dt));
+        double fy[NC], sy[NC], psi_y;
+        trial_drift<TRIAL>(y, im.trial, psi_y, fy, sy);
+        const double acc = metropolis_ratio<NC>(xo, y, fo, fy, psi_x, psi_y, a.sigma, im.inv_mass, a.ndim, a.dt);
+        double u;
+        if (im.inj_um) u = im.inj_um[i];
+        else { const uint4 r = pvd_draw(a.seed, i, step, PVD_STREAM_METRO, 0u); u = u53(r.x, r.y); }
+        const bool ok = acc > u;
+        double ke = lk[i];
+        if (ok) {
+            ke = local_kinetic<NC>(sy, im.inv_mass, a.ndim);
+#pragma unroll
+            for (int c = 0; c < NC; ++c) { xo[c] = y[c]; x[c * a.cap + i] = y[c]; f[c * a.cap + i] = fy[c]; }
+            psi[i] = psi_y;
+            lk[i] = ke;
+            ++my_acc;
+        }
+        v[i] = __dadd_rn(POT::eval(xo, a.pot), ke);
+    }
+    // acceptance count -> dt_eff
+    for (int off = 16; off > 0; off >>= 1) my_acc += __shfl_xor_sync(0xffffffffu, my_acc, off);
+    if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = my_acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned tot = 0;
+        for (int w = 0; w < PVD_WARPS; ++w) tot += s_cnt[w];
+        atomicAdd(im.acc_count, (unsigned long long)tot);
+        __threadfence();
+        const unsigned d = atomicAdd(&sip->done, 1u);
+        s_last = (d == gridDim.x - 1) ? 1u : 0u;
+        if (s_last) {
+            __threadfence();
+            const unsigned long long nacc = atomicAdd(im.acc_count, 0ull);
+            sip->n_accept = (long long)nacc;
+            if (a.world == 1) sip->dt_eff = __dmul_rn(a.dt, (double)nacc / (double)n);
+            sip->done = 0u;
+            *im.acc_count = 0ull;
+        }
+    }
+}
+
+// multi-GPU: dt_eff from the globally reduced acceptance count (sums[0] = n_accept, sums[1] = n)
+__global__ void k_imp_set_dt(DevState *st, int parity, const double *sums, double dt)
+{
+    if (blockIdx.x == 0 && threadIdx.x == 0) st[parity].dt_eff = __dmul_rn(dt, sums[0] / sums[1]);
+}
+
+// ---------------------------------------------------------------- stand-alone entry points (AoS host layout)
+template <class TRIAL>
+__global__ void k_trial_drift_aos(const double *__restrict__ xyz, long long n, const TrialParamsDev p, double *psi, double *dlog, double *d2)
+{
+    constexpr int NC = TRIAL::NC;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        double x[NC], a1[NC], a2[NC], p0;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) x[c] = xyz[i * NC + c];
+        trial_drift<TRIAL>(x, p, p0, a1, a2);
+        psi[i] = TRIAL::psi(x, p);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) { dlog[i * NC + c] = a1[c]; d2[i * NC + c] = a2[c]; }
+    }
+}
+
+template <int NC>
+__global__ void k_metropolis_aos(const double *x, const double *y, const double *fx, const double *fy, const double *psx,
+                                 const double *psy, long long n, int ndim, const double *sigma, const double *inv_mass, double dt, double *acc)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        double a[NC], b[NC], c[NC], d[NC];
+#pragma unroll
+        for (int k = 0; k < NC; ++k) { a[k] = x[i * NC + k]; b[k] = y[i * NC + k]; c[k] = fx[i * NC + k]; d[k] = fy[i * NC + k]; }
+        acc[i] = metropolis_ratio<NC>(a, b, c, d, psx[i], psy[i], sigma, inv_mass, ndim, dt);
+    }
+}
+
+template <int NC>
+__global__ void k_local_kin_aos(const double *d2, long long n, int ndim, const double *inv_mass, double *ke)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        double a[NC];
+#pragma unroll
+        for (int k = 0; k < NC; ++k) a[k] = d2[i * NC + k];
+        ke[i] = local_kinetic<NC>(a, inv_mass, ndim);
+    }
+}

@@ -95,7 +95,7 @@ __device__ inline void finalize_from_sums(const StepArgs &a, bool continuous)
     so.err = err;
     so.dw_active = si.dw_active;
     so.dt_eff = a.dt;           // imp-samp kernels overwrite this each step before weighting
-    so.eff_time = si.eff_time;
+    so.eff_time = si.eff_time + (a.fin ? si.dt_eff : 0.0);      // accumulated effective time (pyvibdmc.py:372-378)
     so.done = 0u;
     so.n_accept = 0;
     so.n_kill = 0;
@@ -110,7 +110,7 @@ __device__ inline void finalize_from_sums(const StepArgs &a, bool continuous)
     r.dt_eff = si.dt_eff;
     r.births = (long long)s[PVD_SUM_BIRTHS];
     r.deaths = (long long)s[PVD_SUM_DEATHS];
-    r.rejected = (long long)s[PVD_SUM_NIN] - (long long)s[PVD_SUM_NACC];
+    r.rejected = a.fin ? (long long)s[PVD_SUM_NIN] - si.n_accept : 0;
     r.step = si.step;
 }
 
@@ -160,7 +160,8 @@ __device__ __forceinline__ WarpPartial acc_warp_reduce(const LaneAcc &acc)
 // the last CTA to arrive combines all CTA records (every field is exact / order independent, so
 // Vref is bit-reproducible), publishes the shard's sums and, on a single GPU, finalises the step.
 // n_local_fixed < 0: the new local population is the inclusive prefix of the last tile.
-__device__ inline void cta_finish_step(const StepArgs &a, const LaneAcc &acc, long long ntiles, bool continuous, long long n_local_fixed)
+__device__ inline void cta_finish_step(const StepArgs &a, const LaneAcc &acc, long long ntiles, bool continuous, long long n_local_fixed,
+                                       bool defer_finalize = false)
 {
     __shared__ WarpPartial s_part[PVD_WARPS];
     __shared__ unsigned s_last;
@@ -214,7 +215,7 @@ __device__ inline void cta_finish_step(const StepArgs &a, const LaneAcc &acc, lo
         // every warp of this step has drawn its last ticket: re-arm this parity's counters for step s+2
         unsigned *tk = step_tickets(a, a.parity);
         for (int w = 0; w < PVD_WARPS; ++w) tk[w * PVD_TICKET_STRIDE] = 0u;
-        if (a.world == 1) finalize_from_sums(a, continuous);
+        if (a.world == 1 && !defer_finalize) finalize_from_sums(a, continuous);
     }
 }
 

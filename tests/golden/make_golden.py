@@ -217,7 +217,7 @@ def gen_impsamp():
          f_y=f_y, sec_y=sec_y, acc=acc, local_kin=lk, masses=masses, dt=dt,
          grid_first=table[0, 0], grid_last=table[0, -1], grid_n=table.shape[1])
     # trial-wfn table itself is data the product needs (5000-pt grid, rows: r, psi): ship psi row only
-    np.save(os.path.join(ROOT, "pyvibdmc_b200", "sample_potentials", "free_oh_wvfn_table.npy"), table[:2])
+    np.save(os.path.join(ROOT, "pyvibdmc_b200", "sample_potentials", "FortPots", "Partridge_Schwenke_H2O", "free_oh_wvfn_table.npy"), table[:2])
 
 
 # ---------------------------------------------------------------- G. whole-loop trajectories with recorded RNG

@@ -1,0 +1,251 @@
+"""GPU parity tests (-m gpu): continuous weighting, importance sampling, NN potential."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import golden, ROOT
+
+pytestmark = pytest.mark.gpu
+EQ = np.array([[1.81005599, 0., 0.], [-0.45344658, 1.75233806, 0.], [0., 0., 0.]])
+WN = 4.556335281212229e-6
+H2O_DIR = os.path.join(ROOT, "pyvibdmc_b200", "sample_potentials", "FortPots", "Partridge_Schwenke_H2O")
+
+
+@pytest.fixture(scope="module")
+def K():
+    from pyvibdmc_b200 import kernels
+    assert kernels.device_count() > 0
+    return kernels
+
+
+def water_table():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("call_trl_h2o_b200", os.path.join(H2O_DIR, "call_trl_h2o.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.packed_table()
+
+
+class Replay:
+    def __init__(self, g):
+        self.flat, self.sizes, self.k, self.off = g["draw_flat"], g["draw_sizes"], 0, 0
+
+    def take(self, n):
+        assert self.sizes[self.k] == n, (self.k, int(self.sizes[self.k]), n)
+        out = self.flat[self.off:self.off + n]
+        self.k += 1
+        self.off += n
+        return out
+
+    def normal(self, n, a, d):
+        return np.ascontiguousarray(self.take(n * a * d).reshape(n, d, a).transpose(0, 2, 1))
+
+
+# ------------------------------------------------------------------ continuous weighting
+@pytest.mark.parametrize("case", ["low", "ties"])
+def test_branch_continuous_golden_exact(K, case):
+    g = golden("branch_continuous_golden.npz")
+    w, src, nb, mx, mn = K.branch_continuous(g[f"{case}_w0"], g[f"{case}_v"], float(g[f"{case}_vref"]), float(g[f"{case}_dt"]),
+                                             float(g[f"{case}_lower"]), None)
+    assert np.array_equal(w, g[f"{case}_w"]) and np.array_equal(src, g[f"{case}_src"])
+    assert [nb, mx, mn] == list(g[f"{case}_stats"])
+
+
+def test_branch_continuous_upper_threshold_multiset(K):
+    """np.argpartition leaves the order of the killed set unspecified: parity as a multiset (SURVEY hard part 4)."""
+    g = golden("branch_continuous_golden.npz")
+    w, src, nb, mx, mn = K.branch_continuous(g["both_w0"], g["both_v"], float(g["both_vref"]), 5.0, float(g["both_lower"]),
+                                             float(g["both_upper"]))
+    assert np.array_equal(np.sort(w), np.sort(g["both_w"]))
+    assert np.array_equal(np.sort(src), np.sort(g["both_src"]))
+    assert [nb, mx, mn] == list(g["both_stats"])
+    assert abs(w.sum() - g["both_w"].sum()) < 1e-9
+
+
+@pytest.mark.parametrize("n,spread", [(1, 0.1), (33, 0.5), (1000, 0.5), (4000, 2.5), (60000, 0.4), (300000, 0.6)])
+def test_branch_continuous_vs_oracle(K, oracle, n, spread):
+    rng = np.random.default_rng(n)
+    w0 = np.exp(rng.normal(0, spread, size=n))
+    if n > 1:
+        w0[rng.choice(n, max(1, n // 80), replace=False)] = 1e-7
+    v = 0.021 + 0.004 * rng.standard_normal(n)
+    lower = 1.0 / n if n > 1 else 0.5
+    wo, so, nbo, mxo, mno = oracle.branch_continuous(w0, v, 0.021, 5.0, lower, None)
+    w, s, nb, mx, mn = K.branch_continuous(w0, v, 0.021, 5.0, lower, None)
+    assert nb == nbo
+    assert np.array_equal(w, wo) and np.array_equal(s, so)
+    assert (mx, mn) == (mxo, mno)
+
+
+def test_replay_h2o_continuous_trajectory(K):
+    from pyvibdmc_b200 import _capi
+    g = golden("traj_h2o_cont_low_golden.npz")
+    rp = Replay(g)
+    sim = K.DeviceSim(3, 3, g["masses"], 256, 5.0, _capi.POT_H2O_PS, weighting="continuous", thresh_lower=0.3)
+    sim.upload(np.repeat(EQ[None] * 1.01, 256, 0))
+    T = 30
+    vref, pop, wfns = np.zeros(T), np.zeros(T), {}
+    for t in range(T):
+        if t in (5, 15, 25):
+            sim.dw_begin()
+        sim.step_injected(rp.normal(256, 3, 3))
+        st = sim.stats(t, 1)
+        vref[t], pop[t] = st["vref"][0], st["pop"][0]
+        if t + 1 in (9, 19, 29):
+            parent, pw = sim.dw_parent()
+            wfns[t + 1 - 4] = (parent, pw, sim.dw_end(256))
+    assert np.allclose(vref, g["vref"], rtol=1e-10, atol=0) and np.allclose(pop, g["pop"], rtol=1e-12)
+    out = sim.download()
+    assert np.array_equal(out["coords"], g["final_coords"])
+    assert np.allclose(out["wts"], g["final_wts"], rtol=1e-10)
+    for t in (5, 15, 25):
+        assert np.array_equal(wfns[t][0], g[f"wfn{t}_coords"])
+        assert np.allclose(wfns[t][1], g[f"wfn{t}_parent_wts"], rtol=1e-10)
+        assert np.allclose(wfns[t][2], g[f"wfn{t}_desc_wts"], rtol=1e-9, atol=1e-12)
+    sim.close()
+
+
+def test_continuous_free_running_properties(K, oracle):
+    from pyvibdmc_b200 import _capi
+    m = np.array([oracle.mass('H'), oracle.mass('H'), oracle.mass('O')])
+    n0, T = 20000, 400
+    sim = K.DeviceSim(3, 3, m, n0, 5.0, _capi.POT_H2O_PS, weighting="continuous", seed=11)
+    sim.upload(EQ[None] * 1.01 + np.zeros((n0, 1, 1)))
+    sim.run(T)
+    st, out, stats = sim.state(), sim.download(), sim.stats(0, T)
+    assert st["step"] == T and st["n"] == n0 and len(out["wts"]) == n0
+    assert out["wts"].min() >= 1.0 / n0 * 0.5 and np.isfinite(out["wts"]).all()
+    assert abs(stats["pop"][-1] - out["wts"].sum()) < 1e-8 * n0
+    pred = np.average(out["pots"], weights=out["wts"]) - 0.1 * (out["wts"].sum() - n0) / n0
+    assert abs(pred - st["vref"]) < 1e-11 * abs(pred)
+    assert np.max(np.abs(out["pots"] - oracle.water_pot(out["coords"])) / np.maximum(np.abs(out["pots"]), WN)) < 1e-10
+    zpe = stats["vref"][T // 2:].mean() / WN
+    assert 4300 < zpe < 4900, zpe
+    sim.close()
+
+
+# ------------------------------------------------------------------ importance sampling
+def test_water_trial_drift_vs_reference(K):
+    from pyvibdmc_b200 import _capi
+    g = golden("impsamp_water_golden.npz")
+    f, psi, sec = K.trial_drift(_capi.TRIAL_H2O_FD, g["coords"], water_table())
+    assert np.allclose(psi, g["psi"], rtol=1e-13, atol=1e-300)
+    # finite differences amplify last-ulp differences of psi by psi/dx and psi/dx^2
+    assert np.allclose(f, g["f_x"], rtol=1e-8, atol=1e-9 * np.abs(g["f_x"]).max())
+    ok = np.isfinite(g["sec"])
+    assert np.allclose(sec[ok], g["sec"][ok], rtol=1e-5, atol=1e-6 * np.nanmax(np.abs(g["sec"][20:])))
+
+
+def test_metropolis_and_local_kin_vs_reference(K):
+    g = golden("impsamp_water_golden.npz")
+    m = g["masses"]
+    sig = np.sqrt(float(g["dt"]) / m)
+    acc = K.metropolis(g["coords"], g["y"], g["f_x"], g["f_y"], g["psi"], g["psi_y"], sig, 1 / m, float(g["dt"]))
+    ok = np.isfinite(g["acc"])
+    assert np.allclose(acc[ok], g["acc"][ok], rtol=1e-12, atol=1e-300)
+    assert np.array_equal(K.local_kin(g["sec"][20:], 1 / m), g["local_kin"][20:])
+
+
+def test_harm_trial_analytic_vs_reference(K):
+    from pyvibdmc_b200 import _capi
+    g = golden("ho_golden.npz")
+    alpha = float(g["mass"]) * float(g["omega"])
+    d1, psi, d2 = K.trial_drift(_capi.TRIAL_HARM1D, g["x"], np.array([alpha]))
+    assert np.allclose(psi, g["psi"], rtol=1e-15) and np.allclose(d1, g["dpsi"], rtol=1e-14) and np.allclose(d2, g["d2psi"], rtol=1e-13)
+
+
+def test_replay_h2o_impsamp_trajectory(K):
+    from pyvibdmc_b200 import _capi
+    g = golden("traj_h2o_imp_golden.npz")
+    rp = Replay(g)
+    sim = K.DeviceSim(3, 3, g["masses"], 200, 1.0, _capi.POT_H2O_PS, trial=_capi.TRIAL_H2O_FD)
+    sim.set_trial_table(water_table())
+    sim.upload(np.repeat(EQ[None] * 1.01, 200, 0))
+    T, n = 16, 200
+    vref, pop, dts = np.zeros(T), np.zeros(T), np.zeros(T)
+    for t in range(T):
+        disp = rp.normal(n, 3, 3)
+        um = rp.take(n)
+        ub = rp.take(n)
+        sim.step_injected(disp, ub, um)
+        st = sim.stats(t, 1)
+        vref[t], pop[t], dts[t] = st["vref"][0], st["pop"][0], st["dt_eff"][0]
+        n = int(pop[t])
+    assert np.array_equal(pop, g["pop"])
+    assert np.allclose(vref, g["vref"], rtol=1e-8)
+    assert np.allclose(np.cumsum(dts), g["eff_ts"], rtol=1e-13)
+    sim.close()
+
+
+def test_replay_ho_impsamp_analytic_trajectory(K):
+    from pyvibdmc_b200 import _capi
+    g = golden("traj_ho_imp_golden.npz")
+    rp = Replay(g)
+    m, om = float(g["masses"][0]), 3700.0 * WN
+    sim = K.DeviceSim(1, 1, g["masses"], 300, 5.0, _capi.POT_HARMONIC, pot_params=[(0.5 * m) * om ** 2], trial=_capi.TRIAL_HARM1D)
+    sim.set_trial_table(np.array([m * om]))
+    sim.upload(np.zeros((300, 1, 1)))
+    T, n = 40, 300
+    vref, pop = np.zeros(T), np.zeros(T)
+    for t in range(T):
+        disp = rp.normal(n, 1, 1)
+        um, ub = rp.take(n), rp.take(n)
+        sim.step_injected(disp, ub, um)
+        st = sim.stats(t, 1)
+        vref[t], pop[t] = st["vref"][0], st["pop"][0]
+        n = int(pop[t])
+    assert np.array_equal(pop, g["pop"]) and np.allclose(vref, g["vref"], rtol=1e-11)
+    sim.close()
+
+
+def test_impsamp_free_running_zpe(K, oracle):
+    """Importance-sampled water: local energy fluctuates far less than V; ZPE stays near 4634 cm-1."""
+    from pyvibdmc_b200 import _capi
+    m = np.array([oracle.mass('H'), oracle.mass('H'), oracle.mass('O')])
+    sim = K.DeviceSim(3, 3, m, 4000, 1.0, _capi.POT_H2O_PS, trial=_capi.TRIAL_H2O_FD, seed=5)
+    sim.set_trial_table(water_table())
+    sim.upload(EQ[None] * 1.01 + np.zeros((4000, 1, 1)))
+    sim.run(600)
+    st = sim.stats(0, 600)
+    assert sim.state()["step"] == 600
+    assert (st["rejected"] >= 0).all() and st["rejected"].mean() < 0.2 * 4000
+    zpe = st["vref"][300:].mean() / WN
+    assert 4400 < zpe < 4900, zpe
+    sim.close()
+
+
+# ------------------------------------------------------------------ NN potential
+def packed_nn():
+    return np.load(os.path.join(ROOT, "pyvibdmc_b200", "sample_potentials", "TensorflowPots", "sample_h4o2_nn_packed.npy"))
+
+
+def unpack_nn(p):
+    out, off = [], 0
+    for k, n in ((15, 120), (120, 120), (120, 120), (120, 1)):
+        w = p[off:off + k * n].reshape(k, n); off += k * n
+        b = p[off:off + n]; off += n
+        out.append((w, b))
+    return out
+
+
+def test_coulomb_descriptor(K):
+    g = golden("descriptor_golden.npz")
+    assert np.allclose(K.coulomb_descriptor(g["coords"], g["zs"]), g["coulomb"], rtol=1e-14)
+
+
+def test_nn_h4o2_vs_float32_oracle(K, oracle):
+    g = golden("descriptor_golden.npz")
+    p = packed_nn()
+    K.nn_h4o2_set_weights(p)
+    v = K.nn_h4o2(g["coords"])
+    ref = oracle.nn_forward_f32(g["coulomb"], unpack_nn(p))
+    # float32 network: summation order differs between the GPU tile and NumPy's matmul
+    assert np.allclose(v, ref, rtol=2e-4, atol=2e-4 * np.abs(ref).max())
+    assert (v >= 0).all() and v.dtype == np.float64
+    # ragged sizes and a physical sanity value: ~7.6 cm-1 at the water-dimer minimum
+    dimer = np.array([[-1.502169, -0.191359, 1.434927], [-0.601054, -0.596972, -0.000000], [-1.502169, -0.191359, -1.434927],
+                      [1.350759, 0.111656, 0.000000], [2.023531, -0.588557, 0.000000], [0.0, 0.0, 0.0]])
+    for n in (1, 63, 64, 65, 1000):
+        vv = K.nn_h4o2(g["coords"][:n] if n <= len(g["coords"]) else np.tile(g["coords"], (2, 1, 1))[:n])
+        assert np.allclose(vv[:min(n, 512)], v[:min(n, 512)], rtol=1e-6, atol=1e-9)

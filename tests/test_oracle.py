@@ -105,7 +105,7 @@ def test_vref_and_desc_discrete(oracle):
 def test_impsamp_water_pieces(oracle):
     g = golden("impsamp_water_golden.npz")
     table = np.load(os.path.join(os.path.dirname(__file__), "..", "pyvibdmc_b200", "sample_potentials",
-                                 "free_oh_wvfn_table.npy"))
+                                 "FortPots", "Partridge_Schwenke_H2O", "free_oh_wvfn_table.npy"))
     trial = oracle.WaterTrial(table)
     assert np.allclose(trial(g["coords"]), g["psi"], rtol=1e-13, atol=1e-300)
     f, psi, sec = oracle.drift_fd(g["coords"], trial)
@@ -169,7 +169,7 @@ def test_traj_h2o_continuous(oracle, name, thresh):
 def test_traj_h2o_impsamp(oracle):
     g, draws = _replay(oracle, "h2o_imp")
     table = np.load(os.path.join(os.path.dirname(__file__), "..", "pyvibdmc_b200", "sample_potentials",
-                                 "free_oh_wvfn_table.npy"))
+                                 "FortPots", "Partridge_Schwenke_H2O", "free_oh_wvfn_table.npy"))
     out = oracle.dmc_loop(np.repeat(EQ[None] * 1.01, 200, 0), g["masses"], 1.0, 200, 16, oracle.water_pot, draws,
                           equil=4, wfn_every=6, desc_steps=3, trial=oracle.WaterTrial(table))
     assert np.array_equal(out["pop"], g["pop"])
