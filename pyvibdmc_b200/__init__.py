@@ -7,5 +7,7 @@ The compute path is hand-written sm_100a CUDA behind a C ABI (include/pvd_b200.h
 CPU fallback.
 """
 from . import _capi, kernels  # noqa: F401
+from .dmc_sim import DMC_Sim, dmc_restart  # noqa: F401
+from .simulation_utilities import *  # noqa: F401,F403
 
 __version__ = "0.1.0"

@@ -1,0 +1,482 @@
+"""DMC_Sim / dmc_restart: the reference's user API (pyvibdmc/pyvibdmc.py:15-965) driving the B200 path.
+
+Same constructor arguments, attribute names, output files (log text, pickle checkpoints, HDF5
+wave-function dumps and sim_info) and exceptions as the reference.  What differs is where the
+per-time-step work runs: the walker ensemble lives in HBM (kernels.DeviceSim) and every step --
+displacement, potential, weighting / birth-death, Vref, descendant bookkeeping -- is CUDA.  The host
+only intervenes at the reference's "special" steps (checkpoints, wave-function windows) and drains
+the per-step statistics ring to write the log and the Vref / population histories.
+
+Three stepping modes, chosen from the plug-ins handed in:
+  * built-in potential (shipped samples: harmonic, Morse, Partridge-Schwenke water, NN water dimer)
+    -> whole segments of time steps are enqueued at once, no host synchronisation per step;
+  * any other potential callable -> move / weight / branch on the GPU, the callable is handed the
+    coordinates once per step (the reference's plug-in contract: getpot(cds) -> V);
+  * importance sampling with a built-in trial wave function -> fused GPU drift/Metropolis step.
+"""
+import copy
+import os
+import time
+
+import numpy as np
+
+from . import _capi, kernels
+from .simulation_utilities.Constants import Constants, get_atomic_num
+from .simulation_utilities.file_manager import FileManager
+from .simulation_utilities.imp_samp import ImpSamp
+from .simulation_utilities.sim_archive import SimArchivist
+from .simulation_utilities.sim_logger import SimLogger
+
+__all__ = ['DMC_Sim', 'dmc_restart']
+
+MASSIVE = "Massive walker birth or death event!!!!!!! Dying..."
+_NOT_PICKLED = ('potential', 'potential_info', 'impsamp_manager', 'impsamp', 'imp_info', 'adiabatic_dmc', 'ad_obs_func',
+                '_dev', '_potential_obj')
+
+
+class DMC_Sim:
+    """See the reference docstring (pyvibdmc.py:18-65) for the meaning of every argument; the
+    keyword-only extras select the random stream and the device."""
+
+    def __init__(self, sim_name="DMC_Sim", output_folder="exSimResults", weighting='discrete', num_walkers=10000,
+                 num_timesteps=20000, equil_steps=2000, chkpt_every=1000, wfn_every=1000, desc_wt_steps=100, atoms=[],
+                 delta_t=1, potential=None, masses=None, start_structures=None, start_cont_wts=None, branch_every=1,
+                 log_every=1, cur_timestep=0, cont_wt_thresh=None, imp_samp=None, imp_samp_oned=False,
+                 second_impsamp_displacement=False, excited_state_imp_samp=False, adiabatic_dmc=None, fixed_node=None,
+                 DEBUG_alpha=None, DEBUG_save_desc_wt_tracker=None, DEBUG_save_training_every=None,
+                 DEBUG_save_before_bod=False, DEBUG_mass_change=None, *, seed=None, rng='fp64', device=0):
+        self.atoms = atoms
+        self.sim_name = sim_name
+        self.output_folder = output_folder
+        self.num_walkers = num_walkers
+        self.num_timesteps = num_timesteps
+        self.potential_info = vars(potential)
+        self.potential = potential.getpot
+        self._potential_obj = potential
+        self.weighting = weighting.lower()
+        self.desc_wt_time_steps = desc_wt_steps
+        self.branch_every = branch_every
+        self.delta_t = delta_t
+        self.start_structures = start_structures
+        self.start_cont_wts = start_cont_wts
+        self.masses = masses
+        self.equil_steps = equil_steps
+        self.chkpt_every = chkpt_every
+        self.wfn_every = wfn_every
+        self.log_every = log_every
+        self.cur_timestep = cur_timestep
+        self.cont_wt_thresh = cont_wt_thresh
+        self.impsamp_manager = imp_samp
+        self.imp1d = imp_samp_oned
+        self.second_impsamp_displacement = second_impsamp_displacement
+        self.adiabatic_dmc = adiabatic_dmc
+        self.fixed_node = fixed_node
+        self.excited_state_imp_samp = excited_state_imp_samp
+        self._deb_training_every = DEBUG_save_training_every
+        self._deb_save_before_bod = DEBUG_save_before_bod
+        self._deb_desc_wt_tracker = DEBUG_save_desc_wt_tracker
+        self._deb_alpha = DEBUG_alpha
+        self._deb_mass_change = DEBUG_mass_change
+        self._seed = int(np.random.randint(0, 2 ** 31 - 1)) if seed is None else int(seed)
+        self._rng_mode = _capi.RNG_FAST if rng == 'fast' else _capi.RNG_FP64
+        self._device = int(device)
+        self._dev = None
+        # variants of the loop that are outside this implementation's scope
+        for name, val in (("second_impsamp_displacement", second_impsamp_displacement),
+                          ("excited_state_imp_samp", excited_state_imp_samp), ("adiabatic_dmc", adiabatic_dmc),
+                          ("fixed_node", fixed_node), ("DEBUG_save_desc_wt_tracker", DEBUG_save_desc_wt_tracker),
+                          ("DEBUG_save_training_every", DEBUG_save_training_every), ("DEBUG_mass_change", DEBUG_mass_change)):
+            if val:
+                raise NotImplementedError(f"{name} is not implemented on the B200 path")
+        self._initialize()
+
+    # ------------------------------------------------------------------ set-up (pyvibdmc.py:132-297)
+    def _schedule(self):
+        T = self.num_timesteps
+        self._prop_steps = np.arange(self.cur_timestep, T)
+        self._branch_step = np.arange(0, T + self.branch_every, self.branch_every)
+        self._chkpt_step = np.arange(self.chkpt_every, T + self.chkpt_every, self.chkpt_every)
+        self._wfn_save_step = np.arange(self.equil_steps, T + self.wfn_every, self.wfn_every)
+        self._desc_wt_save_step = self._wfn_save_step + self.desc_wt_time_steps
+        self.deb_train_save_step = []
+        self._log_steps = np.arange(0, T, self.log_every)
+
+    def _initialize(self):
+        self._schedule()
+        self._prop_steps = np.arange(0, self.num_timesteps)
+        self._who_from = None
+        self._walker_pots = None
+        self._vref_vs_tau = np.zeros(self.num_timesteps)
+        self._pop_vs_tau = np.zeros(self.num_timesteps)
+
+        if self.start_structures is None:
+            raise Exception("Please supply a starting structure for your chemical system.")
+        elif len(self.start_structures.shape) != 3:
+            raise Exception("Start structure must have format (n,m,d), where n = 1 or num_walkers, m = num atoms, "
+                            "d = dimensions (usually 3)")
+        elif self.start_structures.shape[0] == 1:
+            self._walker_coords = np.repeat(self.start_structures, self.num_walkers, axis=0)
+        elif self.start_structures.shape[0] == self.num_walkers:
+            self._walker_coords = self.start_structures
+        else:
+            print("WARNING: NUMBER OF STARTING GEOMETRIES DOES NOT EQUAL NUM_WALKERS VARIABLE. MAKE SURE THIS IS"
+                  "INTENTIONAL.")
+            self._walker_coords = self.start_structures
+
+        if type(self.atoms) is not list:
+            self.atoms = [self.atoms]
+        if self.masses is None:
+            if '-' in self.atoms[0]:                      # reduced mass: 1-D problem
+                self.masses = np.array([Constants.reduced_mass(self.atoms[0])])
+                self._atm_nums = get_atomic_num(self.atoms[0].split('-'))
+            else:
+                self.masses = np.array([Constants.mass(a) for a in self.atoms])
+                self._atm_nums = get_atomic_num(self.atoms)
+        elif isinstance(self.masses, (int, float)):
+            self.masses = np.array([self.masses])
+            self._atm_nums = [-1]
+        elif isinstance(self.masses, (list, np.ndarray)):
+            self.masses = np.array(self.masses)
+            self._atm_nums = get_atomic_num(self.atoms)
+        if len(self.masses) != len(self.atoms):
+            raise Exception("Your number of atoms list does not match your number of masses you provided.")
+        if self._walker_coords.shape[1] != len(self.atoms):
+            raise Exception("Your number of atoms list does not match the shape of your walkers.")
+
+        self._sigmas = np.sqrt(self.delta_t / self.masses)
+        self._alpha = 1.0 / (2.0 * self.delta_t) if self._deb_alpha is None else self._deb_alpha
+
+        FileManager.create_filesystem(self.output_folder)
+        self._logger = SimLogger(f"{self.output_folder}/{self.sim_name}_log.txt", overwrite=(self.cur_timestep == 0))
+
+        if self.weighting == 'continuous':
+            self._thresh_upper = None
+            self._cont_wts = self.start_cont_wts if self.start_cont_wts is not None else np.ones(self.num_walkers)
+            if self.cont_wt_thresh is None:
+                self._thresh_lower = 1 / self.num_walkers
+            elif isinstance(self.cont_wt_thresh, (int, float)):
+                self._thresh_lower = self.cont_wt_thresh
+            elif isinstance(self.cont_wt_thresh, list):
+                if len(self.cont_wt_thresh) == 2:
+                    self._thresh_lower, self._thresh_upper = self.cont_wt_thresh
+                elif len(self.cont_wt_thresh) == 1:
+                    self._thresh_lower = self.cont_wt_thresh[0]
+            else:
+                raise ValueError("Invalid input for continuous weight threshold")
+        else:
+            self._cont_wts = None
+        self._desc_wt = False
+        self._mass_change_steps = []
+        self._pop_thresh = [self.num_walkers - self.num_walkers * 0.5, self.num_walkers + self.num_walkers * 0.5]
+
+        if 'num_mpi' in self.potential_info.keys():
+            self.potential(self._walker_coords)
+
+        if self.impsamp_manager is not None:
+            self._init_impsamp()
+
+    def _init_impsamp(self):
+        self.imp_info = vars(self.impsamp_manager)
+        if self.delta_t != 1:
+            print("WARNING! Using DT>1 for Imp Samp. Make sure this is not a mistake!!!!")
+        self.f_x = self.psi_1 = self.psi_sec_der = None
+        self.inv_masses_trip = (1 / np.repeat(self.masses, 3)).reshape(len(self.masses), 3)[np.newaxis, ...]
+        self.sigma_trip = np.repeat(self._sigmas, 3).reshape(len(self.masses), 3)[np.newaxis, ...]
+        self.impsamp = ImpSamp(self.impsamp_manager)
+        self.eff_ts = np.zeros(self.num_timesteps)
+        if self.imp1d:
+            self.sigma_trip = self._sigmas
+            self.inv_masses_trip = (1 / self.masses)[np.newaxis]
+
+    def _init_restart(self, add_ts, impsamp):
+        """Extend the histories and step markers for `add_ts` more steps (pyvibdmc.py:299-338)."""
+        self.num_timesteps = self.num_timesteps + add_ts
+        self._schedule()
+        self._vref_vs_tau = np.concatenate((self._vref_vs_tau, np.zeros(add_ts)))
+        self._pop_vs_tau = np.concatenate((self._pop_vs_tau, np.zeros(add_ts)))
+        self._prop_steps = np.arange(self.cur_timestep, self.num_timesteps)
+        if impsamp is not None:
+            self.impsamp_manager = impsamp
+            if self.delta_t != 1:
+                raise ValueError("Delta tau cannot be anything but 1 for importance sampling DMC!!!!")
+            old = getattr(self, 'eff_ts', np.zeros(0))
+            self._init_impsamp()
+            self.eff_ts[:min(len(old), len(self.eff_ts))] = old[:len(self.eff_ts)]
+        else:
+            self.impsamp_manager = None
+        self.adiabatic_dmc = None
+
+    # ------------------------------------------------------------------ public properties
+    @property
+    def vref_vs_tau(self):
+        vref_wvn = self._vref_vs_tau[:self.cur_timestep]
+        return np.column_stack((np.arange(len(vref_wvn)), vref_wvn))
+
+    @property
+    def walkers(self):
+        self._pull_walkers()
+        if self.weighting == 'continuous':
+            return self._walker_coords, self._cont_wts
+        return self._walker_coords
+
+    # ------------------------------------------------------------------ device plumbing
+    def _specs(self):
+        pot = getattr(self._potential_obj, 'gpu_spec', lambda: None)() if self._potential_obj is not None else None
+        trial = None
+        if self.impsamp_manager is not None:
+            trial = getattr(self.impsamp_manager, 'gpu_spec', lambda: None)()
+            if trial is None or pot is None:
+                raise NotImplementedError(
+                    "importance sampling on the B200 path needs a built-in trial wave function and a built-in potential "
+                    "(shipped samples: harm_trial_wfn.trial_harm + derivative, call_trl_h2o.trial_wavefunction with "
+                    "finite differences)")
+        return pot, trial
+
+    def _ensure_device(self):
+        if self._dev is not None:
+            return self._dev
+        pot, trial = self._specs()
+        n_atoms, n_dim = self._walker_coords.shape[1], self._walker_coords.shape[2]
+        pot_id, pot_params = _capi.POT_EXTERNAL, None
+        if pot is not None:
+            pot_id = pot["potential"]
+            if pot_id == _capi.POT_HARMONIC:
+                pot_params = np.full(n_atoms * n_dim, pot["k"])
+            elif pot_id == _capi.POT_MORSE1D:
+                pot_params = [pot["de"], pot["alpha"]]
+        cap = int(1.5 * max(self.num_walkers, len(self._walker_coords))) + 1024
+        self._dev = kernels.DeviceSim(n_atoms, n_dim, self.masses, self.num_walkers, self.delta_t, pot_id,
+                                      weighting=self.weighting, alpha=self._alpha, capacity=cap,
+                                      seed=self._seed + 7919 * int(self.cur_timestep), rng_mode=self._rng_mode,
+                                      trial=(trial["trial"] if trial else _capi.TRIAL_NONE), pot_params=pot_params,
+                                      thresh_lower=getattr(self, '_thresh_lower', None),
+                                      thresh_upper=getattr(self, '_thresh_upper', None), device=self._device,
+                                      stats_ring=max(4096, min(1 << 20, int(self.num_timesteps) + 8)))
+        self._builtin = pot is not None
+        if pot is not None and pot_id == _capi.POT_NN_H4O2:
+            self._dev.set_nn_weights(pot["weights"])
+        if trial:
+            self._dev.set_trial_table(trial["table"], trial.get("ntab"))
+        self._dev.upload(self._walker_coords, self._cont_wts)
+        if not self._builtin:
+            self._dev.set_pots(np.asarray(self.potential(self._walker_coords), dtype=np.float64))
+        self._dev_step0 = int(self.cur_timestep)      # propagation step that device step 0 corresponds to
+        self._host_stale = False
+        return self._dev
+
+    def _pull_walkers(self):
+        """Refresh the host copies of the per-walker arrays from HBM (checkpoints, .walkers, end of run)."""
+        if self._dev is None or not getattr(self, '_host_stale', False):
+            return
+        out = self._dev.download(who_from=self._desc_wt)
+        self._walker_coords, self._walker_pots = out["coords"], out["pots"]
+        if self.weighting == 'continuous':
+            self._cont_wts = out["wts"]
+        if self._desc_wt:
+            self._who_from = out["who_from"]
+        if self.impsamp_manager is not None:
+            self.f_x, self.psi_1, self.psi_sec_der = self._dev.download_imp()
+        self._vref = self._dev.state(raise_on_error=False)["vref"]
+        self._host_stale = False
+
+    def _drain(self, first, count, events):
+        """Copy `count` per-step records starting at propagation step `first` into the histories and the log."""
+        st = self._dev.stats(first - self._dev_step0, count)
+        state = self._dev.state(raise_on_error=False)
+        done = state["step"] - (first - self._dev_step0)            # records that belong to completed steps
+        done = max(0, min(count, done))
+        per_step_s = events.get("seconds", 0.0) / max(count, 1)
+        for k in range(done):
+            step = first + k
+            r = st[k]
+            self._vref_vs_tau[step] = r["vref"]
+            self._pop_vs_tau[step] = r["pop"]
+            if self.impsamp_manager is not None:
+                self.eff_ts[step] = (self.eff_ts[step - 1] if step > 0 else 0.0) + r["dt_eff"]
+            log = step in self._log_set
+            if log:
+                self._logger.write_ts(step)
+            if k == 0 and events.get("chkpt"):
+                self._logger.write_chkpt(step)
+            if k == 0 and events.get("wfn"):
+                self._logger.write_wfn_save(step)
+            if log:
+                if self.impsamp_manager is not None:
+                    prev = self._pop_vs_tau[step - 1] if step > 0 else 0
+                    n_before = int(prev) if (self.weighting == 'discrete' and prev > 0) else len(self._walker_coords)
+                    self._logger.write_rejections(int(r["rejected"]), n_before)
+                    self._logger.write_imp_disp_time(per_step_s)
+                self._logger.write_pot_time(step, events.get("pot_seconds", {}).get(step, per_step_s), r["v_max"], r["v_min"], r["v_avg"])
+            if self.impsamp_manager is not None:
+                self._logger.write_local(r["v_avg"])
+            if log and (step % self.branch_every == 0):
+                if self.weighting == 'discrete':
+                    self._logger.write_branching(step, 'discrete', (int(r["births"]), int(r["deaths"]), int(r["pop"])))
+                else:
+                    self._logger.write_branching(step, 'continuous', (int(r["births"]), r["w_max"], r["w_min"]))
+            if k == count - 1 and events.get("desc"):
+                self._logger.write_desc_wt(step)
+            if step % 10 == 0:
+                self._logger.fl.flush()
+        if done:
+            self.cur_timestep = first + done - 1
+        if state["err"]:
+            self.cur_timestep = first + done
+            raise ValueError(MASSIVE)
+
+    # ------------------------------------------------------------------ the loop (pyvibdmc.py:701-876)
+    def propagate(self):
+        dev = self._ensure_device()
+        T = int(self.num_timesteps)
+        first = int(self._prop_steps[0]) if len(self._prop_steps) else T
+        self._log_set = set(int(s) for s in self._log_steps)
+        chk, wfn = set(int(s) for s in self._chkpt_step), set(int(s) for s in self._wfn_save_step)
+        dw_end = set(int(s) for s in self._desc_wt_save_step)
+        # host-side events: start-of-step {chkpt, wfn window opens}, end-of-step {window closes after step t: t+1 in dw_end}
+        starts = sorted(s for s in (chk | wfn) if first <= s < T)
+        ends = sorted(s for s in dw_end if first < s <= T)
+        t = first
+        self._logger.write_beginning(self.__dict__) if first < T else None
+        while t < T:
+            self.cur_timestep = t
+            events = {}
+            if t in chk:
+                events["chkpt"] = True
+                self._pull_walkers()
+                FileManager.delete_older_checkpoints(self.output_folder, self.sim_name, t)
+                logger, self._logger = self._logger, None
+                SimArchivist.chkpt(self, t)
+                self._logger = logger
+            if t in wfn:
+                events["wfn"] = True
+                n_now = dev.state()["n"]
+                self._desc_wts = np.zeros(n_now)
+                dev.dw_begin()
+                self._desc_wt = True
+                self._dw_n_parent = n_now
+            nxt = min([s for s in starts if s > t] + [s for s in ends if s > t] + [T])
+            tic = time.time()
+            if self._builtin:
+                dev.run(nxt - t, self.branch_every)
+                dev.sync()
+            else:
+                events["pot_seconds"] = self._run_external(dev, t, nxt)
+            events["seconds"] = time.time() - tic
+            self._host_stale = True
+            if nxt in dw_end and self._desc_wt:
+                events["desc"] = True
+            self._drain(t, nxt - t, events)
+            if events.get("desc"):
+                self._desc_wt = False
+                self._desc_wts = dev.dw_end(self._dw_n_parent)
+                self._parent, self._parent_wts = dev.dw_parent()
+                fname = f"{self.output_folder}/wfns/{self.sim_name}_wfn_{nxt - self.desc_wt_time_steps}ts.hdf5"
+                if self.weighting == 'continuous':
+                    SimArchivist.save_h5(fname=fname, keyz=['coords', 'desc_wts', 'parent_wts'],
+                                         valz=[self._parent, self._desc_wts, self._parent_wts])
+                else:
+                    SimArchivist.save_h5(fname=fname, keyz=['coords', 'desc_wts'], valz=[self._parent, self._desc_wts])
+            t = nxt
+            self.cur_timestep = t - 1
+        self._pull_walkers()
+
+    def _run_external(self, dev, t0, t1):
+        """User potential callable: the GPU moves / weights / branches, the callable sees the coordinates
+        once per step (getpot contract, potential_manager.py:71-99)."""
+        pot_seconds = {}
+        for step in range(t0, t1):
+            cds = dev.ext_move()
+            if step in self._log_set:
+                v, pot_seconds[step] = self.potential(cds, timeit=True)
+            else:
+                v = self.potential(cds)
+            do_branch = (step % self.branch_every) == 0
+            dev.ext_finish(np.asarray(v, dtype=np.float64), do_branch)
+            if dev.state(raise_on_error=False)["err"]:
+                break
+        return pot_seconds
+
+    # ------------------------------------------------------------------ run / checkpoint (pyvibdmc.py:878-947)
+    def run(self):
+        try:
+            print("Starting Simulation...")
+        except OSError:
+            pass
+        dmc_time_start = time.time()
+        throw_error = None
+        try:
+            self.propagate()
+            FileManager.delete_older_checkpoints(self.output_folder, self.sim_name, self.cur_timestep)
+        except Exception as e:
+            import traceback
+            print("ERROR! An error occurred while running the DMC simulation. Dumping a final checkpoint...")
+            print("Ignore Approximate ZPE!!!")
+            traceback.print_exc()
+            throw_error = e
+        finally:
+            if self._logger is not None:
+                self._logger.final_chkpt()
+                self._logger.fl.close()
+            self._logger = None
+            try:
+                self._pull_walkers()
+            except Exception:
+                pass
+            SimArchivist.chkpt(self, self.cur_timestep)
+            _vref_wvn = Constants.convert(self._vref_vs_tau, "wavenumbers", to_AU=False)
+            try:
+                print("Simulation Complete")
+                print('Approximate ZPE', np.average(_vref_wvn[len(_vref_wvn) // 4:]))
+            except OSError:
+                pass
+            ts = self.eff_ts if self.impsamp_manager is not None else np.arange(len(_vref_wvn)) * self.delta_t
+            SimArchivist.save_h5(fname=f"{self.output_folder}/{self.sim_name}_sim_info.hdf5",
+                                 keyz=['vref_vs_tau', 'pop_vs_tau', 'atomic_nums', 'atomic_masses'],
+                                 valz=[np.column_stack((ts, self._vref_vs_tau)), np.column_stack((ts, self._pop_vs_tau)),
+                                       self._atm_nums, self.masses])
+            finish = time.time() - dmc_time_start
+        self._logger = SimLogger(f"{self.output_folder}/{self.sim_name}_log.txt")
+        self._logger.finish_sim(finish)
+        if throw_error is not None:
+            raise throw_error
+
+    def __deepcopy__(self, memodict={}):
+        """Checkpoint copy: plug-ins and the device handle are not pickled (pyvibdmc.py:934-947)."""
+        cls = self.__class__
+        res = cls.__new__(cls)
+        memodict[id(self)] = res
+        for k, v in self.__dict__.items():
+            if k == '_logger':
+                res._logger = None            # open file handle; the reference nulls it around chkpt()
+            elif k not in _NOT_PICKLED:
+                setattr(res, k, copy.deepcopy(v, memodict))
+        return res
+
+    def __getstate__(self):
+        return {k: v for k, v in self.__dict__.items() if k not in _NOT_PICKLED}
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        self._dev = None
+        self._potential_obj = None
+
+
+def dmc_restart(potential, chkpt_folder, sim_name, additional_timesteps=0, impsamp=None, imp_samp_oned=False,
+                fixed_node=None):
+    """Reload `{chkpt_folder}/chkpts/{sim_name}_*.pickle` and continue (pyvibdmc.py:949-965)."""
+    if fixed_node is not None:
+        raise NotImplementedError("fixed_node is not implemented on the B200 path")
+    dmc_sim = SimArchivist.reload_sim(chkpt_folder, sim_name)
+    dmc_sim.imp1d = imp_samp_oned
+    dmc_sim.fixed_node = fixed_node
+    dmc_sim._init_restart(additional_timesteps, impsamp)
+    dmc_sim.potential = potential.getpot
+    dmc_sim._potential_obj = potential
+    dmc_sim.potential_info = vars(potential)
+    dmc_sim._dev = None
+    if getattr(dmc_sim, '_desc_wt', False):
+        print("WARNING: the checkpoint was written inside a descendant-weighting window; that window is dropped.")
+        dmc_sim._desc_wt = False
+    dmc_sim._logger = SimLogger(f"{dmc_sim.output_folder}/{dmc_sim.sim_name}_log.txt")
+    FileManager.delete_future_checkpoints(chkpt_folder, sim_name, dmc_sim.cur_timestep)
+    return dmc_sim

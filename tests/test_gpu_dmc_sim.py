@@ -1,0 +1,168 @@
+"""GPU tests (-m gpu) of the drop-in user API: DMC_Sim(...).run(), outputs on disk, restart.
+They mirror the reference's own integration tests (pyvibdmc/tests/test_pyvibdmc.py, test_imp_samp.py)
+but assert results instead of `assert True`."""
+import glob
+import os
+import pickle
+
+import numpy as np
+import pytest
+
+from conftest import golden
+
+pytestmark = pytest.mark.gpu
+WN = 4.556335281212229e-6
+EQ = np.array([[1.81005599, 0., 0.], [-0.45344658, 1.75233806, 0.], [0., 0., 0.]])
+
+
+@pytest.fixture(scope="module")
+def pv():
+    import pyvibdmc_b200 as pv
+    assert pv.kernels.device_count() > 0
+    return pv
+
+
+def sample_dir(pv, *parts):
+    return os.path.join(os.path.dirname(pv.__file__), "sample_potentials", *parts)
+
+
+def ho_potential(pv, cores=2):
+    return pv.Potential(potential_function='oh_stretch_harm', python_file='harmonicOscillator1D.py',
+                        potential_directory=sample_dir(pv, "PythonPots"), num_cores=cores)
+
+
+def water_potential(pv):
+    return pv.Potential(potential_function='water_pot', python_file='h2o_potential.py',
+                        potential_directory=sample_dir(pv, "FortPots", "Partridge_Schwenke_H2O"), num_cores=2)
+
+
+def read_h5(path):
+    from pyvibdmc_b200.simulation_utilities import h5lite
+    return h5lite.read_h5(path)
+
+
+def test_config1_harmonic_full_run_outputs_and_zpe(pv, tmp_path):
+    """BASELINE config 1: 1-D HO, discrete, 1000 walkers, 5000 steps, dt = 10 -> ZPE 1850 cm-1 (+ dt bias)."""
+    out = str(tmp_path / "ho")
+    sim = pv.DMC_Sim(sim_name="ho", output_folder=out, weighting='discrete', num_walkers=1000, num_timesteps=5000,
+                     equil_steps=500, chkpt_every=1000, wfn_every=1000, desc_wt_steps=100, atoms=['O-H'], delta_t=10,
+                     potential=ho_potential(pv), start_structures=np.zeros((1, 1, 1)), log_every=50, seed=11)
+    sim.run()
+    info = read_h5(f"{out}/ho_sim_info.hdf5")
+    assert set(info) == {'vref_vs_tau', 'pop_vs_tau', 'atomic_nums', 'atomic_masses'}
+    assert info['vref_vs_tau'].shape == (5000, 2) and info['pop_vs_tau'].shape == (5000, 2)
+    assert np.array_equal(info['vref_vs_tau'][:, 0], np.arange(5000) * 10)
+    zpe = info['vref_vs_tau'][1250:, 1].mean() / WN
+    assert abs(zpe - 1852.5) < 20, zpe
+    assert info['pop_vs_tau'][:, 1].min() > 500 and info['pop_vs_tau'][:, 1].max() < 1500
+    wf = sorted(os.path.basename(p) for p in glob.glob(f"{out}/wfns/*.hdf5"))
+    assert wf == sorted(f"ho_wfn_{t}ts.hdf5" for t in (500, 1500, 2500, 3500, 4500))
+    w = read_h5(f"{out}/wfns/ho_wfn_1500ts.hdf5")
+    assert set(w) == {'coords', 'desc_wts'} and w['coords'].shape[1:] == (1, 1) and len(w['coords']) == len(w['desc_wts'])
+    assert w['desc_wts'].sum() == info['pop_vs_tau'][1599, 1]          # descendants after 100 steps == population then
+    # only the final checkpoint remains, with the reference's attribute names
+    ck = glob.glob(f"{out}/chkpts/*.pickle")
+    assert [os.path.basename(c) for c in ck] == ["ho_4999.pickle"]
+    obj = pickle.load(open(ck[0], "rb"))
+    ref_attrs = set(golden("traj_ho_disc_golden.npz")["pickle_attrs"].tolist())
+    assert ref_attrs - set(obj.__dict__) <= {'_mass_counter', '_factor_per_change'}, ref_attrs - set(obj.__dict__)
+    assert obj._walker_coords.shape == (int(info['pop_vs_tau'][-1, 1]), 1, 1) and obj.cur_timestep == 4999
+    k = 0.5 * pv.Constants.reduced_mass('O-H') * pv.Constants.convert(3700., 'wavenumbers') ** 2
+    assert np.array_equal(obj._walker_pots, np.squeeze(k * obj._walker_coords ** 2))
+    log = open(f"{out}/ho_log.txt").read()
+    assert "Simulation ho starting at step 0" in log and "Birth/Death at time step 4950:" in log
+    assert "Checkpointing, time step 1000" in log and "Simulation has finished." in log
+    assert np.array_equal(sim.vref_vs_tau[:, 1], info['vref_vs_tau'][:4999, 1])
+
+    # restart from the final checkpoint for 1000 more steps (reference tests/test_pyvibdmc.py:152-169)
+    sim2 = pv.dmc_restart(potential=ho_potential(pv), chkpt_folder=out, sim_name="ho", additional_timesteps=1000)
+    sim2.run()
+    info2 = read_h5(f"{out}/ho_sim_info.hdf5")
+    assert info2['vref_vs_tau'].shape == (6000, 2)
+    assert np.array_equal(info2['vref_vs_tau'][:4999, 1], info['vref_vs_tau'][:4999, 1])
+    assert abs(info2['vref_vs_tau'][5000:, 1].mean() / WN - 1852.5) < 40
+
+
+def test_external_potential_equals_builtin(pv, tmp_path, oracle):
+    """A user callable (host NumPy) and the built-in kernel give the same trajectory for the same seed."""
+    res = []
+    for tag, pot in (("builtin", ho_potential(pv)), ("external", pv.Potential_Direct(potential_function=oracle.oh_stretch_harm))):
+        sim = pv.DMC_Sim(sim_name=tag, output_folder=str(tmp_path / tag), num_walkers=800, num_timesteps=120, equil_steps=20,
+                         chkpt_every=50, wfn_every=40, desc_wt_steps=10, atoms=['O-H'], delta_t=10, potential=pot,
+                         start_structures=np.zeros((1, 1, 1)), seed=5)
+        sim.run()
+        res.append((sim._vref_vs_tau.copy(), sim._pop_vs_tau.copy(), sim.walkers.copy(),
+                    read_h5(str(tmp_path / tag / "wfns" / f"{tag}_wfn_60ts.hdf5"))))
+    assert np.array_equal(res[0][1], res[1][1]) and np.array_equal(res[0][2], res[1][2])
+    assert np.allclose(res[0][0], res[1][0], rtol=1e-13, atol=0)
+    assert np.array_equal(res[0][3]['desc_wts'], res[1][3]['desc_wts'])
+
+
+def test_water_discrete_zpe(pv, tmp_path):
+    out = str(tmp_path / "w")
+    sim = pv.DMC_Sim(sim_name="water", output_folder=out, weighting='discrete', num_walkers=8000, num_timesteps=3000,
+                     equil_steps=500, chkpt_every=500, wfn_every=1000, desc_wt_steps=300, atoms=['H', 'H', 'O'], delta_t=5,
+                     potential=water_potential(pv), start_structures=EQ[None] * 1.01, log_every=100, seed=3)
+    sim.run()
+    info = read_h5(f"{out}/water_sim_info.hdf5")
+    zpe = info['vref_vs_tau'][1000:, 1].mean() / WN
+    assert abs(zpe - 4634.1) < 25, zpe                        # shipped tutorial runs: 4634.1 +- 2.2 (8000 x 5000)
+    assert list(info['atomic_nums']) == [1, 1, 10]            # H, H, O in the reference's mass-table numbering
+    w = read_h5(f"{out}/wfns/water_wfn_1500ts.hdf5")
+    assert w['coords'].shape[1:] == (3, 3)
+
+
+def test_continuous_weighting_with_wfn_dumps(pv, tmp_path):
+    out = str(tmp_path / "c")
+    sim = pv.DMC_Sim(sim_name="cont", output_folder=out, weighting='continuous', num_walkers=4000, num_timesteps=1200,
+                     equil_steps=300, chkpt_every=400, wfn_every=300, desc_wt_steps=50, atoms=['H', 'H', 'O'], delta_t=5,
+                     potential=water_potential(pv), start_structures=EQ[None] * 1.01, log_every=50, seed=9)
+    sim.run()
+    info = read_h5(f"{out}/cont_sim_info.hdf5")
+    assert abs(info['pop_vs_tau'][-1, 1] - 4000) < 400
+    w = read_h5(f"{out}/wfns/cont_wfn_600ts.hdf5")
+    assert set(w) == {'coords', 'desc_wts', 'parent_wts'} and len(w['coords']) == 4000
+    assert abs(w['desc_wts'].sum() - info['pop_vs_tau'][649, 1]) < 1e-6 * 4000
+    coords, wts = sim.walkers
+    assert coords.shape == (4000, 3, 3) and wts.shape == (4000,) and wts.min() > 0
+    zpe = info['vref_vs_tau'][600:, 1].mean() / WN
+    assert 4400 < zpe < 4850, zpe
+    assert "Walkers Branched" in open(f"{out}/cont_log.txt").read()
+
+
+def test_importance_sampling_runs(pv, tmp_path):
+    d = sample_dir(pv, "PythonPots")
+    imp = pv.ImpSampManager_NoMP(trial_function='trial_harm', trial_directory=d, python_file='harm_trial_wfn.py',
+                                 deriv_function='derivative')
+    sim = pv.DMC_Sim(sim_name="hoimp", output_folder=str(tmp_path / "i"), num_walkers=1000, num_timesteps=400, equil_steps=100,
+                     chkpt_every=200, wfn_every=100, desc_wt_steps=20, atoms=['O-H'], delta_t=5, potential=ho_potential(pv),
+                     start_structures=np.zeros((1, 1, 1)), imp_samp=imp, imp_samp_oned=True, seed=2)
+    sim.run()
+    # exact trial wfn => zero-variance estimator: Vref == hbar*omega/2 for every step, population never changes
+    assert np.allclose(sim._vref_vs_tau / WN, 1850.0, atol=1e-6) and (sim._pop_vs_tau == 1000).all()
+    hd = sample_dir(pv, "FortPots", "Partridge_Schwenke_H2O")
+    wimp = pv.ImpSampManager(trial_function='trial_wavefunction', trial_directory=hd, python_file='call_trl_h2o.py',
+                             pot_manager=water_potential(pv), trial_kwargs={'dists': [[0, 2], [2, 1]], 'angs': [[0, 2, 1]]},
+                             deriv_kwargs={'dists': [[0, 2], [2, 1]], 'angs': [[0, 2, 1]]})
+    sim = pv.DMC_Sim(sim_name="wimp", output_folder=str(tmp_path / "wi"), num_walkers=2000, num_timesteps=500, equil_steps=100,
+                     chkpt_every=250, wfn_every=200, desc_wt_steps=20, atoms=['H', 'H', 'O'], delta_t=1,
+                     potential=water_potential(pv), start_structures=EQ[None] * 1.01, imp_samp=wimp, seed=4)
+    sim.run()
+    info = read_h5(str(tmp_path / "wi" / "wimp_sim_info.hdf5"))
+    assert np.all(np.diff(info['vref_vs_tau'][:, 0]) > 0) and info['vref_vs_tau'][-1, 0] <= 500.0   # effective time axis
+    zpe = info['vref_vs_tau'][250:, 1].mean() / WN
+    assert 4450 < zpe < 4850, zpe
+    assert "Metropolis rejected" in open(str(tmp_path / "wi" / "wimp_log.txt")).read()
+
+
+def test_massive_event_raises_and_still_writes_outputs(pv, tmp_path):
+    out = str(tmp_path / "m")
+    bad = np.repeat(EQ[None], 1000, axis=0)
+    bad[:100] *= 3.0
+    sim = pv.DMC_Sim(sim_name="boom", output_folder=out, num_walkers=1000, num_timesteps=50, equil_steps=10, chkpt_every=20,
+                     wfn_every=20, desc_wt_steps=5, atoms=['H', 'H', 'O'], delta_t=200, potential=water_potential(pv),
+                     start_structures=bad, seed=1)
+    with pytest.raises(ValueError, match="Massive walker birth or death event!!!!!!! Dying..."):
+        sim.run()
+    assert os.path.exists(f"{out}/boom_sim_info.hdf5") and len(glob.glob(f"{out}/chkpts/boom_*.pickle")) == 1
+    assert "Final checkpoint is written" in open(f"{out}/boom_log.txt").read()

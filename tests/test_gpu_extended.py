@@ -48,8 +48,13 @@ def test_branch_continuous_golden_exact(K, case):
     g = golden("branch_continuous_golden.npz")
     w, src, nb, mx, mn = K.branch_continuous(g[f"{case}_w0"], g[f"{case}_v"], float(g[f"{case}_vref"]), float(g[f"{case}_dt"]),
                                              float(g[f"{case}_lower"]), None)
-    assert np.array_equal(w, g[f"{case}_w"]) and np.array_equal(src, g[f"{case}_src"])
-    assert [nb, mx, mn] == list(g[f"{case}_stats"])
+    # CUDA's exp and glibc's exp differ in the last bit for some arguments, so updated weights agree to
+    # 2 ulp rather than bitwise (the "ties" case has exp(0) = 1 and is bit-exact); who-copies-whom is exact.
+    assert np.array_equal(src, g[f"{case}_src"])
+    assert np.allclose(w, g[f"{case}_w"], rtol=4.5e-16, atol=0)
+    if case == "ties":
+        assert np.array_equal(w, g[f"{case}_w"])
+    assert nb == int(g[f"{case}_stats"][0]) and np.allclose([mx, mn], g[f"{case}_stats"][1:], rtol=4.5e-16)
 
 
 def test_branch_continuous_upper_threshold_multiset(K):
@@ -57,9 +62,9 @@ def test_branch_continuous_upper_threshold_multiset(K):
     g = golden("branch_continuous_golden.npz")
     w, src, nb, mx, mn = K.branch_continuous(g["both_w0"], g["both_v"], float(g["both_vref"]), 5.0, float(g["both_lower"]),
                                              float(g["both_upper"]))
-    assert np.array_equal(np.sort(w), np.sort(g["both_w"]))
+    assert np.allclose(np.sort(w), np.sort(g["both_w"]), rtol=4.5e-16, atol=0)
     assert np.array_equal(np.sort(src), np.sort(g["both_src"]))
-    assert [nb, mx, mn] == list(g["both_stats"])
+    assert nb == int(g["both_stats"][0]) and np.allclose([mx, mn], g["both_stats"][1:], rtol=4.5e-16)
     assert abs(w.sum() - g["both_w"].sum()) < 1e-9
 
 
@@ -74,8 +79,9 @@ def test_branch_continuous_vs_oracle(K, oracle, n, spread):
     wo, so, nbo, mxo, mno = oracle.branch_continuous(w0, v, 0.021, 5.0, lower, None)
     w, s, nb, mx, mn = K.branch_continuous(w0, v, 0.021, 5.0, lower, None)
     assert nb == nbo
-    assert np.array_equal(w, wo) and np.array_equal(s, so)
-    assert (mx, mn) == (mxo, mno)
+    assert np.array_equal(s, so)                             # donors / copies exactly as the sequential reference loop
+    assert np.allclose(w, wo, rtol=4.5e-16, atol=0)          # weights to 2 ulp (exp implementations differ in the last bit)
+    assert np.allclose([mx, mn], [mxo, mno], rtol=4.5e-16)
 
 
 def test_replay_h2o_continuous_trajectory(K):
