@@ -1,0 +1,135 @@
+"""Walker sharding across GPUs (one process per GPU, torch.distributed / NCCL as plumbing).
+
+The reference has no multi-device path for the loop itself (only Pool.map / MPI futures around the
+potential call: simulation_utilities/potential_manager.py:59-99, mpi_potential_manager.py:69-74).
+Here every rank owns a contiguous shard of the ensemble in its own HBM and runs the same step
+kernels; the only per-step exchange is one all-reduce of PVD_NSUMS doubles
+[sum c*V, sum c, births, deaths, sum V, n_in, err, n_acc, (vmin,vmax,wmin,wmax) x ranks]
+from which every rank derives the same Vref / population.  Shard populations drift
+apart under discrete weighting, so every `rebalance_every` steps walkers are moved from the
+fullest to the emptiest shards (plan_rebalance: pure host logic, tested on CPU with gloo).
+"""
+import os
+
+import numpy as np
+
+from . import _capi, kernels
+
+__all__ = ["plan_rebalance", "shard_bounds", "ShardedSim"]
+
+
+def shard_bounds(n_total, world):
+    """Contiguous split of n_total walkers over `world` ranks (first ranks take the remainder)."""
+    base, rem = divmod(int(n_total), int(world))
+    counts = [base + (1 if r < rem else 0) for r in range(world)]
+    starts = np.concatenate([[0], np.cumsum(counts)[:-1]]).astype(int)
+    return [(int(s), int(c)) for s, c in zip(starts, counts)]
+
+
+def plan_rebalance(pops, tolerance=0.05):
+    """Transfers [(src_rank, dst_rank, count), ...] that bring every shard within `tolerance` of the mean.
+
+    Deterministic and identical on every rank (it only depends on the all-gathered populations):
+    repeatedly move walkers from the fullest shard to the emptiest one."""
+    pops = [int(p) for p in pops]
+    world = len(pops)
+    total = sum(pops)
+    target = [total // world + (1 if r < total % world else 0) for r in range(world)]
+    if total == 0 or max(abs(p - t) for p, t in zip(pops, target)) <= tolerance * max(total / world, 1.0):
+        return []
+    surplus = [p - t for p, t in zip(pops, target)]
+    moves = []
+    while True:
+        src = max(range(world), key=lambda r: (surplus[r], -r))
+        dst = min(range(world), key=lambda r: (surplus[r], r))
+        count = min(surplus[src], -surplus[dst])
+        if count <= 0:
+            break
+        moves.append((src, dst, count))
+        surplus[src] -= count
+        surplus[dst] += count
+    return moves
+
+
+class ShardedSim:
+    """DeviceSim on every rank + the per-step all-reduce.  Requires torch.distributed to be initialised
+    (backend nccl) and one CUDA device per rank."""
+
+    def __init__(self, natoms, ndim, masses, num_walkers, delta_t, potential, weighting="discrete", seed=0,
+                 rng_mode=_capi.RNG_FP64, pot_params=None, thresh_lower=None, thresh_upper=None, rebalance_every=250,
+                 capacity=None, stats_ring=1 << 14):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.local_rank = int(os.environ.get("LOCAL_RANK", self.rank % max(torch.cuda.device_count(), 1)))
+        torch.cuda.set_device(self.local_rank)
+        self.device = torch.device("cuda", self.local_rank)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.num_walkers = int(num_walkers)
+        local = -(-self.num_walkers // self.world)
+        self.sim = kernels.DeviceSim(natoms, ndim, masses, num_walkers, delta_t, potential, weighting=weighting,
+                                     seed=int(seed) + 1000003 * self.rank, rng_mode=rng_mode, pot_params=pot_params,
+                                     thresh_lower=thresh_lower, thresh_upper=thresh_upper, device=self.local_rank,
+                                     rank=self.rank, world_size=self.world,
+                                     capacity=capacity or int(1.6 * local) + 4096, stats_ring=stats_ring)
+        self.sim.set_stream(self.stream.cuda_stream)
+        self.sums = torch.zeros(_capi.NSUMS, dtype=torch.float64, device=self.device)
+        self.sim.set_sums_ptr(self.sums.data_ptr())
+        self.rebalance_every = int(rebalance_every)
+        self.steps_done = 0
+        self.natoms, self.ndim = natoms, ndim
+
+    def upload(self, coords_local, wts_local=None):
+        with self.torch.cuda.stream(self.stream):
+            self.sim.upload(coords_local, wts_local)
+            self.dist.all_reduce(self.sums)
+            self.sim.init_finalize()
+
+    def run(self, nsteps, branch_every=1):
+        with self.torch.cuda.stream(self.stream):
+            for _ in range(int(nsteps)):
+                do_branch = 1 if branch_every == 1 else -int(branch_every)
+                self.sim.step_local(do_branch)
+                self.dist.all_reduce(self.sums)
+                self.sim.step_finalize()
+                self.steps_done += 1
+                if self.rebalance_every and self.steps_done % self.rebalance_every == 0:
+                    self.rebalance()
+
+    def populations(self):
+        torch, dist = self.torch, self.dist
+        n = torch.tensor([self.sim.state(raise_on_error=False)["n"]], dtype=torch.int64, device=self.device)
+        out = [torch.zeros_like(n) for _ in range(self.world)]
+        dist.all_gather(out, n)
+        return [int(t.item()) for t in out]
+
+    def rebalance(self, tolerance=0.05):
+        """Move whole walkers (coords, V, weight, who_from) from over- to under-populated shards."""
+        torch, dist = self.torch, self.dist
+        moves = plan_rebalance(self.populations(), tolerance)
+        nc = self.natoms * self.ndim
+        for src, dst, count in moves:
+            if self.rank == src:
+                xyz = np.empty((count, self.natoms, self.ndim)); pots = np.empty(count)
+                w = np.empty(count); who = np.empty(count, dtype=np.int64)
+                _capi.check(_capi.lib.pvd_sim_export_tail(self.sim._h, count, _capi.ptr(xyz), _capi.ptr(pots), _capi.ptr(w), _capi.ptr(who)))
+                payload = np.concatenate([xyz.reshape(count, nc), pots[:, None], w[:, None], who[:, None].astype(np.float64)], axis=1)
+                dist.send(torch.from_numpy(payload).to(self.device), dst)
+            elif self.rank == dst:
+                buf = torch.empty((count, nc + 3), dtype=torch.float64, device=self.device)
+                dist.recv(buf, src)
+                p = buf.cpu().numpy()
+                xyz = np.ascontiguousarray(p[:, :nc]); pots = np.ascontiguousarray(p[:, nc])
+                w = np.ascontiguousarray(p[:, nc + 1]); who = np.ascontiguousarray(p[:, nc + 2]).astype(np.int64)
+                _capi.check(_capi.lib.pvd_sim_import(self.sim._h, count, _capi.ptr(xyz), _capi.ptr(pots), _capi.ptr(w), _capi.ptr(who)))
+        return moves
+
+    def state(self):
+        return self.sim.state()
+
+    def stats(self, first, count):
+        return self.sim.stats(first, count)
+
+    def close(self):
+        self.sim.close()

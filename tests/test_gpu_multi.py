@@ -1,0 +1,26 @@
+"""GPU test (-m gpu, needs >= 2 devices): walker sharding with the per-step NCCL all-reduce and rebalancing."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_two_gpu_sharded_run():
+    from pyvibdmc_b200 import kernels
+    if kernels.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    here = os.path.dirname(os.path.abspath(__file__))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29617", os.path.join(here, "multi_gpu_worker.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
+    line = [l for l in res.stdout.splitlines() if l.startswith("RESULT ")][-1]
+    out = json.loads(line[7:])
+    assert out["world"] == 2 and out["step"] == 600 and out["same_on_all_ranks"] and out["births_minus_deaths_ok"]
+    assert sum(out["pops"]) == int(out["global_pop_last"]) and 20000 < sum(out["pops"]) < 60000
+    assert abs(out["pops"][0] - out["pops"][1]) < 0.2 * sum(out["pops"])          # rebalancing keeps shards level
+    assert 4350 < out["zpe"] < 4900
