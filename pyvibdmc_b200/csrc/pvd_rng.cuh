@@ -46,13 +46,54 @@ template <int MODE>
 __device__ __forceinline__ void normal_pair(uint4 r, double &z0, double &z1)
 {
     if (MODE == PVD_RNG_FP64) {
-        const double u1 = ((double)((((unsigned long long)r.y << 32) | r.x) >> 11) + 1.0) * 0x1.0p-53;   // (0,1]
-        const double u2 = u53(r.z, r.w);                                                                 // [0,1)
-        const double rad = sqrt(-2.0 * log(u1));
-        double s, c;
-        sincospi(2.0 * u2, &s, &c);
-        z0 = rad * c;
-        z1 = rad * s;
+        // Box-Muller in double, with the transcendental functions specialised for random-bit inputs
+        // (no generic range reduction, no special cases), ~2x fewer instructions than log/sqrt/sincospi:
+        //   u = (1+f) 2^-(e+1): e = leading zeros of y (geometric), f = 52 bits from x and w[19:0]
+        //   angle = 2 pi N / 2^44, N from z and w[31:20]
+        const int e = r.y ? __clz((int)r.y) : 32;
+        const unsigned long long mant = ((unsigned long long)r.x << 20) | (unsigned long long)(r.w & 0xFFFFFu);
+        double m = __longlong_as_double((long long)(0x3FF0000000000000ull | mant));        // [1,2)
+        int k = e + 1;
+        if (m > 1.4142135623730951) { m *= 0.5; --k; }                                   // m in [0.7071, 1.4142]
+        // ln m = 2 atanh(s), s = (m-1)/(m+1); reciprocal by float seed + two Newton steps (rel. error < 2^-80)
+        const double den = m + 1.0;
+        double ri = (double)__frcp_rn((float)den);
+        ri = fma(ri, fma(-den, ri, 1.0), ri);
+        ri = fma(ri, fma(-den, ri, 1.0), ri);
+        const double s = (m - 1.0) * ri, s2 = s * s;
+        double p = 1.0 / 21.0;
+        p = fma(p, s2, 1.0 / 19.0); p = fma(p, s2, 1.0 / 17.0); p = fma(p, s2, 1.0 / 15.0); p = fma(p, s2, 1.0 / 13.0); p = fma(p, s2, 1.0 / 11.0);
+        p = fma(p, s2, 1.0 / 9.0); p = fma(p, s2, 1.0 / 7.0); p = fma(p, s2, 1.0 / 5.0); p = fma(p, s2, 1.0 / 3.0);
+        p = fma(p * s2, s, s);                                                           // atanh(s)
+        const double t = fma((double)k, 1.3862943611198906, -4.0 * p);                   // -2 ln u = 2k ln2 - 4 atanh(s)  (> 0)
+        // sqrt(t) = t * rsqrt(t): float seed + two Newton steps
+        double y = (double)rsqrtf((float)t);
+        y = y * fma(-0.5 * t, y * y, 1.5);
+        y = y * fma(-0.5 * t, y * y, 1.5);
+        const double rad = t * y;
+        // angle: octant o (3 bits) + 41-bit fraction; a in [-pi/4, pi/4], then a quadrant rotation
+        const unsigned long long ang = ((unsigned long long)r.z << 12) | (unsigned long long)(r.w >> 20);   // 44 bits
+        const int o = (int)(ang >> 41);
+        long long frac = (long long)(ang & 0x1FFFFFFFFFFull);
+        if (o & 1) frac -= (1ll << 41);
+        const double a = (double)frac * (0.78539816339744831 * 0x1.0p-41);
+        const double a2 = a * a;
+        double sn = -1.0 / 355687428096000.0;                                             // -1/17!
+        sn = fma(sn, a2, 1.0 / 1307674368000.0); sn = fma(sn, a2, -1.0 / 6227020800.0); sn = fma(sn, a2, 1.0 / 39916800.0);
+        sn = fma(sn, a2, -1.0 / 362880.0); sn = fma(sn, a2, 1.0 / 5040.0); sn = fma(sn, a2, -1.0 / 120.0);
+        sn = fma(sn, a2, 1.0 / 6.0);
+        sn = fma(-sn * a2, a, a);                                                         // sin a
+        double cs = 1.0 / 20922789888000.0;                                               // 1/16!
+        cs = fma(cs, a2, -1.0 / 87178291200.0); cs = fma(cs, a2, 1.0 / 479001600.0); cs = fma(cs, a2, -1.0 / 3628800.0);
+        cs = fma(cs, a2, 1.0 / 40320.0); cs = fma(cs, a2, -1.0 / 720.0); cs = fma(cs, a2, 1.0 / 24.0);
+        cs = fma(cs, a2, -0.5);
+        cs = fma(cs, a2, 1.0);                                                            // cos a
+        const int j = ((o + 1) >> 1) & 3;                                                 // nearest multiple of pi/2
+        const double c0 = (j & 1) ? sn : cs, s0 = (j & 1) ? cs : sn;
+        const double cosv = (j == 1 || j == 2) ? -c0 : c0;
+        const double sinv = (j == 2 || j == 3) ? -s0 : s0;
+        z0 = rad * cosv;
+        z1 = rad * sinv;
     } else {
         // -ln(u), u = m * 2^-(e+1), m in [1,2): e = leading zeros of a 64-bit word, m from the next 24 bits
         unsigned long long w = ((unsigned long long)r.y << 32) | r.x;

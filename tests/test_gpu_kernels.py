@@ -115,6 +115,26 @@ def test_philox_known_answers(K):
         assert tuple(int(x) for x in K.philox(ctr, key)) == out
 
 
+def test_fp64_normals_match_reference_arithmetic(K):
+    """The hand-written -2 ln u / sqrt / sincos of the fp64 Box-Muller against mpmath-free NumPy long-double
+    arithmetic on the same Philox bits (counter layout: slot, call<<24, step, purpose<<24)."""
+    seed, step, n = 0x123456789ABCDEF, 77, 4096
+    z = K.normals(n, 2, seed=seed, step=step, rng_mode=0)
+    ld = np.longdouble
+    worst = 0.0
+    for i in range(0, n, 37):
+        x, y, zz, w = philox_py((i & 0xFFFFFFFF, (i >> 32) | (0 << 24), step & 0xFFFFFFFF, (step >> 32) & 0xFFFFFF),
+                                (seed & 0xFFFFFFFF, seed >> 32))
+        e = 32 if y == 0 else 32 - y.bit_length()
+        f = ((x << 20) | (w & 0xFFFFF)) / ld(2 ** 52)
+        u = (ld(1) + f) * ld(2.0) ** (-(e + 1))
+        v = ld((zz << 12) | (w >> 20)) / ld(2 ** 44)
+        rad = np.sqrt(ld(-2) * np.log(u))
+        ref = np.array([rad * np.cos(2 * ld(np.pi) * v), rad * np.sin(2 * ld(np.pi) * v)], dtype=np.float64)
+        worst = max(worst, np.max(np.abs(z[i] - ref)) / max(float(rad), 1.0))     # error relative to the radius
+    assert worst < 4e-15, worst
+
+
 @pytest.mark.parametrize("mode", [0, 1])
 def test_normals_statistics(K, mode):
     from scipy import stats
