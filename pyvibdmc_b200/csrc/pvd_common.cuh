@@ -200,11 +200,11 @@ __device__ __forceinline__ double warp_max(double v)
 // when only part of the grid is resident).
 __device__ __forceinline__ long long warp_take_tile(unsigned *tickets, long long ntiles)
 {
-    const int lane = threadIdx.x & 31, wslot = (threadIdx.x >> 5) % PVD_WARPS;
+    const int lane = threadIdx.x & 31;
     unsigned t = 0;
-    if (lane == 0) t = atomicAdd(&tickets[wslot * PVD_TICKET_STRIDE], 1u);
+    if (lane == 0) t = atomicAdd(&tickets[0], 1u);
     t = __shfl_sync(0xffffffffu, t, 0);
-    const long long tile = (long long)t * PVD_WARPS + wslot;
+    const long long tile = (long long)t;
     return tile < ntiles ? tile : -1;
 }
 
@@ -241,12 +241,14 @@ __device__ __forceinline__ long long resolve_prefix(unsigned long long *status, 
         const long long idx = look - lane;
         unsigned long long w = pack_status(step, PVD_ST_PREFIX, 0u);    // virtual tiles before tile 0
         bool ok = true;
-        do {
+        while (true) {
             if (idx >= 0) {
                 w = ld_relaxed_u64(&status[idx]);
                 ok = status_valid(w, step);
             }
-        } while (!__all_sync(0xffffffffu, ok));
+            if (__all_sync(0xffffffffu, ok)) break;
+            __nanosleep(64);              // give the issue slots to the warps we are waiting for
+        }
         const bool is_prefix = ((w >> 32) & 3ull) == PVD_ST_PREFIX;
         const unsigned mask = __ballot_sync(0xffffffffu, is_prefix);
         const unsigned val = (unsigned)(w & 0xffffffffull);

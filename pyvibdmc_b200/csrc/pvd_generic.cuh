@@ -113,7 +113,12 @@ __global__ void k_displace_soa(double *__restrict__ x, const DevState *st, int p
                 z0 = inj_disp[(2 * k) * cap + i];
                 z1 = (2 * k + 1 < nc) ? inj_disp[(2 * k + 1) * cap + i] : 0.0;
             } else {
-                normal_pair<RNG>(pvd_draw(seed, i, step, PVD_STREAM_DISP, (unsigned)k), z0, z1);
+                if (RNG == PVD_RNG_FP64) {
+                    const uint4 rr[1] = {pvd_draw(seed, i, step, PVD_STREAM_DISP, (unsigned)k)};
+                    double q0[1], q1[1];
+                    normal_pairs_fp64<1>(rr, q0, q1);
+                    z0 = q0[0]; z1 = q1[0];
+                } else normal_pair<RNG>(pvd_draw(seed, i, step, PVD_STREAM_DISP, (unsigned)k), z0, z1);
                 z0 = __dmul_rn(sigma_dev[(2 * k) / ndim], z0);
                 if (2 * k + 1 < nc) z1 = __dmul_rn(sigma_dev[(2 * k + 1) / ndim], z1);
             }

@@ -63,16 +63,51 @@ static inline cudaError_t ps_upload_constants()
 
 // One (a,b) group: Horner in x3 times the symmetrised x1/x2 monomial.  The group structure is a
 // template parameter so every exponent and coefficient slot is a compile-time constant.
+// Groups are evaluated PS_BATCH at a time with their Horner recurrences advanced in lock-step, so that
+// PS_BATCH independent DFMA chains are in flight (a single chain is latency-bound: one DFMA per ~8 cycles).
+constexpr int PS_BATCH = 5;
+static_assert(PS_NGROUPS % PS_BATCH == 0, "25 groups = 5 batches of 5");
+
+// one Horner step of group Q at power L (no-op when the group has no x3^L coefficient)
+template <int Q, int L>
+__device__ __forceinline__ void ps_step(double &h, double x3)
+{
+    constexpr int len = PS_GLEN[Q];
+    constexpr int idx = PS_GSTART[Q] + (L < len ? L : 0);
+    if constexpr (len - 1 == L) h = c_ps_horner[idx];
+    else if constexpr (len - 1 > L) h = fma(h, x3, c_ps_horner[idx]);
+}
+
+template <int G0, int L>
+__device__ __forceinline__ void ps_batch_level(double x3, double (&h)[PS_BATCH])
+{
+    if constexpr (L >= 0) {
+        ps_step<G0 + 0, L>(h[0], x3);
+        ps_step<G0 + 1, L>(h[1], x3);
+        ps_step<G0 + 2, L>(h[2], x3);
+        ps_step<G0 + 3, L>(h[3], x3);
+        ps_step<G0 + 4, L>(h[4], x3);
+        ps_batch_level<G0, L - 1>(x3, h);
+    }
+}
+
+template <int Q>
+__device__ __forceinline__ double ps_sym(const double (&p1)[9], const double (&p2)[9])
+{
+    constexpr int a = PS_GA[Q], b = PS_GB[Q];
+    if constexpr (a == b) return 2.0 * (p1[a] * p2[a]);
+    else return fma(p1[a], p2[b], p1[b] * p2[a]);
+}
+
 template <int G>
 __device__ __forceinline__ void ps_group(double x3, const double (&p1)[9], const double (&p2)[9], double &acc)
 {
-    constexpr int a = PS_GA[G], b = PS_GB[G], st = PS_GSTART[G], len = PS_GLEN[G];
-    double h = c_ps_horner[st + len - 1];
-#pragma unroll
-    for (int l = len - 2; l >= 0; --l) h = fma(h, x3, c_ps_horner[st + l]);
-    const double sym = (a == b) ? 2.0 * (p1[a] * p2[a]) : fma(p1[a], p2[b], p1[b] * p2[a]);
-    acc = fma(sym, h, acc);
-    if constexpr (G + 1 < PS_NGROUPS) ps_group<G + 1>(x3, p1, p2, acc);
+    double h[PS_BATCH];
+    ps_batch_level<G, PS_GLEN[G] - 1>(x3, h);          // groups are ordered by non-increasing length
+    const double t0 = ps_sym<G + 0>(p1, p2) * h[0], t1 = ps_sym<G + 1>(p1, p2) * h[1];
+    const double t2 = fma(ps_sym<G + 2>(p1, p2), h[2], t0), t3 = fma(ps_sym<G + 3>(p1, p2), h[3], t1);
+    acc += fma(ps_sym<G + 4>(p1, p2), h[4], t2) + t3;
+    if constexpr (G + PS_BATCH < PS_NGROUPS) ps_group<G + PS_BATCH>(x3, p1, p2, acc);
 }
 
 // x: 9 Cartesians, atoms ordered H, H, O (calc_h2o_pot.f:18-19).

@@ -111,15 +111,93 @@ __device__ __forceinline__ void normal_pair(uint4 r, double &z0, double &z1)
     }
 }
 
+// NP Box-Muller pairs at once, fp64, stage by stage across the pairs: every polynomial coefficient is
+// materialised once and used by NP back-to-back independent DFMAs (fewer constant moves, NP-way ILP).
+// Same arithmetic per pair as normal_pair<PVD_RNG_FP64>.
+template <int NP>
+__device__ __forceinline__ void normal_pairs_fp64(const uint4 (&r)[NP], double (&z0)[NP], double (&z1)[NP])
+{
+    double m[NP], kk[NP], s[NP], s2[NP], p[NP], a[NP], a2[NP], sn[NP], cs[NP], rad[NP];
+    int oct[NP];
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+        const int e = r[q].y ? __clz((int)r[q].y) : 32;
+        const unsigned long long mant = ((unsigned long long)r[q].x << 20) | (unsigned long long)(r[q].w & 0xFFFFFu);
+        double mm = __longlong_as_double((long long)(0x3FF0000000000000ull | mant));
+        int k = e + 1;
+        if (mm > 1.4142135623730951) { mm *= 0.5; --k; }
+        m[q] = mm;
+        kk[q] = (double)k;
+        const unsigned long long ang = ((unsigned long long)r[q].z << 12) | (unsigned long long)(r[q].w >> 20);
+        const int o = (int)(ang >> 41);
+        long long frac = (long long)(ang & 0x1FFFFFFFFFFull);
+        if (o & 1) frac -= (1ll << 41);
+        oct[q] = o;
+        a[q] = (double)frac * (0.78539816339744831 * 0x1.0p-41);
+    }
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+        const double den = m[q] + 1.0;
+        double ri = (double)__frcp_rn((float)den);
+        ri = fma(ri, fma(-den, ri, 1.0), ri);
+        ri = fma(ri, fma(-den, ri, 1.0), ri);
+        s[q] = (m[q] - 1.0) * ri;
+        s2[q] = s[q] * s[q];
+        a2[q] = a[q] * a[q];
+        p[q] = 1.0 / 21.0;
+        sn[q] = -1.0 / 355687428096000.0;
+        cs[q] = 1.0 / 20922789888000.0;
+    }
+#define PVD_STAGE(ARR, X, C)                                         \
+    _Pragma("unroll") for (int q = 0; q < NP; ++q) ARR[q] = fma(ARR[q], X[q], C);
+    PVD_STAGE(p, s2, 1.0 / 19.0) PVD_STAGE(p, s2, 1.0 / 17.0) PVD_STAGE(p, s2, 1.0 / 15.0) PVD_STAGE(p, s2, 1.0 / 13.0)
+    PVD_STAGE(p, s2, 1.0 / 11.0) PVD_STAGE(p, s2, 1.0 / 9.0) PVD_STAGE(p, s2, 1.0 / 7.0) PVD_STAGE(p, s2, 1.0 / 5.0)
+    PVD_STAGE(p, s2, 1.0 / 3.0)
+    PVD_STAGE(sn, a2, 1.0 / 1307674368000.0) PVD_STAGE(sn, a2, -1.0 / 6227020800.0) PVD_STAGE(sn, a2, 1.0 / 39916800.0)
+    PVD_STAGE(sn, a2, -1.0 / 362880.0) PVD_STAGE(sn, a2, 1.0 / 5040.0) PVD_STAGE(sn, a2, -1.0 / 120.0) PVD_STAGE(sn, a2, 1.0 / 6.0)
+    PVD_STAGE(cs, a2, -1.0 / 87178291200.0) PVD_STAGE(cs, a2, 1.0 / 479001600.0) PVD_STAGE(cs, a2, -1.0 / 3628800.0)
+    PVD_STAGE(cs, a2, 1.0 / 40320.0) PVD_STAGE(cs, a2, -1.0 / 720.0) PVD_STAGE(cs, a2, 1.0 / 24.0) PVD_STAGE(cs, a2, -0.5)
+    PVD_STAGE(cs, a2, 1.0)
+#undef PVD_STAGE
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+        const double at = fma(p[q] * s2[q], s[q], s[q]);                                   // atanh(s)
+        const double t = fma(kk[q], 1.3862943611198906, -4.0 * at);                        // -2 ln u
+        double y = (double)rsqrtf((float)t);
+        y = y * fma(-0.5 * t, y * y, 1.5);
+        y = y * fma(-0.5 * t, y * y, 1.5);
+        rad[q] = t * y;
+        const double sine = fma(-sn[q] * a2[q], a[q], a[q]);
+        const int j = ((oct[q] + 1) >> 1) & 3;
+        const double c0 = (j & 1) ? sine : cs[q], s0 = (j & 1) ? cs[q] : sine;
+        z0[q] = rad[q] * ((j == 1 || j == 2) ? -c0 : c0);
+        z1[q] = rad[q] * ((j == 2 || j == 3) ? -s0 : s0);
+    }
+}
+
 // NC standard normals for walker `slot` at `step` into z[0..NC)
 template <int NC, int MODE>
 __device__ __forceinline__ void walker_normals(uint64_t seed, long long slot, long long step, double (&z)[NC])
 {
+    constexpr int NP = (NC + 1) / 2;
+    if constexpr (MODE == PVD_RNG_FP64) {
+        uint4 r[NP];
+        double z0[NP], z1[NP];
 #pragma unroll
-    for (int k = 0; k < (NC + 1) / 2; ++k) {
-        double a, b;
-        normal_pair<MODE>(pvd_draw(seed, slot, step, PVD_STREAM_DISP, (unsigned)k), a, b);
-        z[2 * k] = a;
-        if (2 * k + 1 < NC) z[2 * k + 1] = b;
+        for (int k = 0; k < NP; ++k) r[k] = pvd_draw(seed, slot, step, PVD_STREAM_DISP, (unsigned)k);
+        normal_pairs_fp64<NP>(r, z0, z1);
+#pragma unroll
+        for (int k = 0; k < NP; ++k) {
+            z[2 * k] = z0[k];
+            if (2 * k + 1 < NC) z[2 * k + 1] = z1[k];
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < NP; ++k) {
+            double a, b;
+            normal_pair<MODE>(pvd_draw(seed, slot, step, PVD_STREAM_DISP, (unsigned)k), a, b);
+            z[2 * k] = a;
+            if (2 * k + 1 < NC) z[2 * k + 1] = b;
+        }
     }
 }
