@@ -280,7 +280,8 @@ struct pvd_sim {
     DevBuf inj_disp, inj_u, inj_um, stage, stage2;   // staging for host<->device transposes / injections
     DevBuf parent_x, parent_w;
     DevBuf kill_idx, hist, cand, cont_work, copy_dst, copy_src, cont_queue, cont_root, cont_skip;
-    DevBuf trial_table, acc_count, nn_weights;
+    DevBuf trial_table, acc_count;
+    NNDeviceWeights nn_w;
     TrialParamsDev trial_params{};
     int nn_grid = 1;
     long long parent_n = 0;
@@ -365,7 +366,7 @@ static int launch_pot_soa(pvd_sim *s)
         else return pvd_fail(PVD_E_ARG, "built-in harmonic potential supports 1 or 3 components");
         break;
     case PVD_POT_MORSE1D: k_pot_soa<PotMorse><<<g, PVD_CTA, 0, s->stream>>>(x, st, s->parity, s->cap, v, s->pot); break;
-    case PVD_POT_NN_H4O2: return nn_launch_soa(s->stream, x, st, s->parity, s->cap, v, s->nn_grid, s->nn_weights.as<float>());
+    case PVD_POT_NN_H4O2: return nn_launch(s->stream, x, 1, s->cap, st, s->parity, 0, s->cap, v, s->nn_w);
     default: return pvd_fail(PVD_E_STATE, "no built-in potential configured");
     }
     PVD_CHECK_LAUNCH();
@@ -464,6 +465,9 @@ int pvd_sim_destroy(pvd_sim *s)
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
+    if (s->nn_w.packed) cudaFree(s->nn_w.packed);
+    if (s->nn_w.images) cudaFree(s->nn_w.images);
+    if (s->nn_w.vecs) cudaFree(s->nn_w.vecs);
     delete s;
     return PVD_OK;
 }

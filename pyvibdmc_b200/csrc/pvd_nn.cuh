@@ -9,6 +9,8 @@
 // TODO(round 2): move the three 120x120 layers onto tcgen05 (M = 128 walkers, K/N padded to 128,
 // accumulators in TMEM, swish in the epilogue) -- see DESIGN.md.
 #pragma once
+#include <cuda_bf16.h>
+#include <stdlib.h>
 #include "pvd_step.cuh"
 
 constexpr int NN_IN = 15, NN_H = 120, NN_TILE = 64, NN_THREADS = 128;
@@ -102,24 +104,332 @@ __global__ void __launch_bounds__(NN_THREADS) k_nn_h4o2(const double *__restrict
     }
 }
 
+// =====================================================================================================
+// tcgen05 version of the MLP (the only tensor-core use in the library).
+//
+// Tile: 128 walkers per CTA (UMMA M = 128, one walker per TMEM lane / per thread), N = 128 output
+// neurons (120 padded), fp32 accumulators in TMEM (128 columns).  fp32 accuracy is kept by splitting
+// every activation and every weight into three bf16 pieces (a = a1 + a2 + a3) and issuing the six
+// leading cross terms (a1w1, a1w2, a2w1, a2w2, a1w3, a3w1; residual ~2^-17) as kind::f16 MMAs with
+// K = 16.  Operands are K-major, un-swizzled "core matrix" layout in shared memory:
+//     byte(row, k) = (k/8) * (128*16) + (row/8) * 128 + (row%8) * 16 + (k%8) * 2      (LBO = 2048, SBO = 128)
+// so that thread `row` writes its eight consecutive k values as one conflict-free 16-byte store.
+// Per layer: weights image (pre-formatted on the host) -> smem, 6 x K/16 MMAs issued by one thread,
+// tcgen05.commit -> mbarrier, then every thread drains its own TMEM lane (tcgen05.ld 32x32b.x32), adds
+// the bias, applies swish, splits into bf16 pieces and stores the next layer's A operand.
+// =====================================================================================================
+constexpr int TC_M = 128, TC_N = 128, TC_THREADS = 256;
+constexpr int TC_PIECE_BYTES_K128 = 128 * 128 * 2;          // one bf16 operand piece, K = 128
+constexpr int TC_PIECE_BYTES_K16 = 128 * 16 * 2;
+constexpr int TC_IMG_L0 = 3 * TC_PIECE_BYTES_K16;            // weights image, layer 0 (K padded 15 -> 16)
+constexpr int TC_IMG_L12 = 3 * TC_PIECE_BYTES_K128;          // weights image, layers 1 and 2
+constexpr int TC_IMG_TOTAL = TC_IMG_L0 + 2 * TC_IMG_L12;     // bytes of pre-formatted bf16 weight images
+constexpr int TC_VEC_FLOATS = 3 * 128 + 128 + 4;             // b0,b1,b2 (padded), W3 (padded), b3
+constexpr size_t TC_SMEM_BYTES = 6 * TC_PIECE_BYTES_K128 + TC_IMG_L0 + 64;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr)
+{
+    // start address, LBO = 2048 B, SBO = 128 B (all >> 4), version 1 (Blackwell), no swizzle
+    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)(2048 >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+                 :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile("{\n\t.reg .pred P1;\n\tLAB_WAIT:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+                 "@P1 bra DONE;\n\tbra LAB_WAIT;\n\tDONE:\n\t}\n" :: "r"(bar), "r"(parity) : "memory");
+}
+// bulk global -> shared copy completing on an mbarrier (TMA engine, 1-D)
+__device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+// split x into three bf16 pieces (round to nearest even each time)
+__device__ __forceinline__ void split3(float x, unsigned short &h1, unsigned short &h2, unsigned short &h3)
+{
+    const __nv_bfloat16 b1 = __float2bfloat16_rn(x);
+    const float r1 = x - __bfloat162float(b1);
+    const __nv_bfloat16 b2 = __float2bfloat16_rn(r1);
+    const float r2 = r1 - __bfloat162float(b2);
+    const __nv_bfloat16 b3 = __float2bfloat16_rn(r2);
+    h1 = __bfloat16_as_ushort(b1); h2 = __bfloat16_as_ushort(b2); h3 = __bfloat16_as_ushort(b3);
+}
+__device__ __forceinline__ float swish_fast(float z) { return __fdividef(z, 1.0f + __expf(-z)); }
+__device__ __forceinline__ void store_pieces(unsigned char *sA, uint32_t off, const unsigned short (&h1)[8], const unsigned short (&h2)[8],
+                                             const unsigned short (&h3)[8])
+{
+    *reinterpret_cast<uint4 *>(sA + 0 * TC_PIECE_BYTES_K128 + off) = make_uint4(h1[0] | (h1[1] << 16), h1[2] | (h1[3] << 16), h1[4] | (h1[5] << 16), h1[6] | (h1[7] << 16));
+    *reinterpret_cast<uint4 *>(sA + 1 * TC_PIECE_BYTES_K128 + off) = make_uint4(h2[0] | (h2[1] << 16), h2[2] | (h2[3] << 16), h2[4] | (h2[5] << 16), h2[6] | (h2[7] << 16));
+    *reinterpret_cast<uint4 *>(sA + 2 * TC_PIECE_BYTES_K128 + off) = make_uint4(h3[0] | (h3[1] << 16), h3[2] | (h3[3] << 16), h3[4] | (h3[5] << 16), h3[6] | (h3[7] << 16));
+}
+
+// images: [L0 | L1 | L2] bf16 weight images (see host builder); vecs: b0[128] b1[128] b2[128] W3[128] b3
+// 256 threads: warp w owns TMEM lanes (walkers) 32*(w%4).. and the column half w/4 of the 128 outputs.
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_nn_h4o2_tc(const double *__restrict__ xyz, int soa, long long cap, const DevState *st, int parity, long long n_fixed,
+             const unsigned char *__restrict__ images, const float *__restrict__ vecs, double *__restrict__ v)
+{
+    extern __shared__ __align__(1024) unsigned char tc_smem[];
+    unsigned char *sA = tc_smem;                                   // 3 pieces x 32 KB: activations (A operand)
+    unsigned char *sW = tc_smem + 3 * TC_PIECE_BYTES_K128;         // 3 pieces x 32 KB: weights of layer 1 / 2 (B operand)
+    unsigned char *sW0 = tc_smem + 6 * TC_PIECE_BYTES_K128;        // 12 KB: weights of layer 0, resident
+    uint64_t *bar = reinterpret_cast<uint64_t *>(sW0 + TC_IMG_L0);  // [0] MMA done, [1] weights landed, [2] layer-0 weights landed
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sW0 + TC_IMG_L0 + 32);
+    float *s_half = reinterpret_cast<float *>(sW0 + TC_IMG_L0 + 40);   // unused padding keeps alignment
+    (void)s_half;
+    const long long n = st ? st[parity].n : n_fixed;
+    if (st && st[parity].err) return;
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int row = (warp & 3) * 32 + lane;                        // walker of this thread inside the tile
+    const int half = warp >> 2;                                    // which 64 output columns this thread drains
+    const uint32_t mma_bar = smem_u32(&bar[0]), w_bar = smem_u32(&bar[1]), w0_bar = smem_u32(&bar[2]);
+    if (t == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mma_bar));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(w_bar));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(w0_bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(128));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+    if (t == 0) {                                                  // layer-0 weights: loaded once per CTA
+        mbar_expect_tx(w0_bar, TC_IMG_L0);
+        bulk_load(smem_u32(sW0), images, TC_IMG_L0, w0_bar);
+    }
+    // instruction descriptor: D = F32, A = B = BF16, K-major both, N = 128, M = 128
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+    const double zs[6] = {8.0, 1.0, 1.0, 8.0, 1.0, 1.0};
+    uint32_t mma_phase = 0, w_phase = 0;
+    const uint32_t row_off = (uint32_t)((row >> 3) * 128 + (row & 7) * 16);        // this walker's row inside a k-chunk
+    const int pa[6] = {0, 0, 1, 1, 0, 2}, pb[6] = {0, 1, 0, 1, 2, 0};
+
+    for (long long base = (long long)blockIdx.x * TC_M; base < n; base += (long long)gridDim.x * TC_M) {
+        const long long i = base + row;
+        if (t == 0) {                                              // layer-1 weights stream in while the descriptor is computed
+            mbar_expect_tx(w_bar, TC_IMG_L12);
+            for (int p = 0; p < 3; ++p)
+                bulk_load(smem_u32(sW + p * TC_PIECE_BYTES_K128), images + TC_IMG_L0 + p * TC_PIECE_BYTES_K128, TC_PIECE_BYTES_K128, w_bar);
+        }
+        // ---- layer-0 A operand: Coulomb descriptor, 15 features + 1 zero pad; the two threads of a row take 8 features each
+        {
+            float feat[8];
+#pragma unroll
+            for (int p = 0; p < 8; ++p) feat[p] = 0.0f;
+            if (i < n) {
+                double c[18];
+#pragma unroll
+                for (int k = 0; k < 18; ++k) c[k] = soa ? xyz[k * cap + i] : xyz[i * 18 + k];
+                int p = 0;
+#pragma unroll
+                for (int a = 0; a < 6; ++a)
+#pragma unroll
+                    for (int b = a + 1; b < 6; ++b) {
+                        if ((p >> 3) == half) {
+                            const double dx = c[3 * a] - c[3 * b], dy = c[3 * a + 1] - c[3 * b + 1], dz = c[3 * a + 2] - c[3 * b + 2];
+                            feat[p & 7] = (float)(zs[a] * zs[b] * rsqrt(dx * dx + dy * dy + dz * dz));
+                        }
+                        ++p;
+                    }
+            }
+            unsigned short h1[8], h2[8], h3[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) split3(feat[e], h1[e], h2[e], h3[e]);
+            store_pieces(sA, (uint32_t)half * 2048u + row_off, h1, h2, h3);
+        }
+        float out = 0.0f;
+#pragma unroll 1
+        for (int layer = 0; layer < 3; ++layer) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // A stores (generic proxy) -> visible to the MMA (async proxy)
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncthreads();
+            if (t == 0) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const int kblocks = layer == 0 ? 1 : 8;                        // K / 16
+                const unsigned char *wb = layer == 0 ? sW0 : sW;
+                const int wpiece = layer == 0 ? TC_PIECE_BYTES_K16 : TC_PIECE_BYTES_K128;
+                if (layer == 0) mbar_wait(w0_bar, 0);                          // completes once; later waits return immediately
+                else { mbar_wait(w_bar, w_phase); w_phase ^= 1u; }
+                uint32_t accumulate = 0;
+                for (int term = 0; term < 6; ++term)
+                    for (int kb = 0; kb < kblocks; ++kb) {
+                        const uint64_t da = umma_desc(smem_u32(sA + pa[term] * TC_PIECE_BYTES_K128 + kb * 4096));
+                        const uint64_t db = umma_desc(smem_u32(wb + pb[term] * wpiece + kb * 4096));
+                        umma_bf16(tmem, da, db, idesc, accumulate);
+                        accumulate = 1;
+                    }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(mma_bar) : "memory");
+            }
+            mbar_wait(mma_bar, mma_phase);
+            mma_phase ^= 1u;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (t == 0 && layer == 1) {                                        // layer-2 weights replace layer-1's during the epilogue
+                mbar_expect_tx(w_bar, TC_IMG_L12);
+                for (int p = 0; p < 3; ++p)
+                    bulk_load(smem_u32(sW + p * TC_PIECE_BYTES_K128), images + TC_IMG_L0 + TC_IMG_L12 + p * TC_PIECE_BYTES_K128,
+                              TC_PIECE_BYTES_K128, w_bar);
+            }
+            // ---- epilogue: this thread's TMEM lane, its 64 columns, 32 at a time
+            const float *bias = vecs + layer * 128;
+#pragma unroll 1
+            for (int cb = 0; cb < 2; ++cb) {
+                uint32_t r[32];
+                const int col0 = half * 64 + cb * 32;
+                const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)col0;
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                             "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                             "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                             : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                               "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                               "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                               "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                             : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) {
+                    unsigned short h1[8], h2[8], h3[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int j = col0 + ch * 8 + e;
+                        const float hval = swish_fast(__uint_as_float(r[ch * 8 + e]) + __ldg(&bias[j]));
+                        if (layer < 2) split3(hval, h1[e], h2[e], h3[e]);
+                        else out = fmaf(hval, __ldg(&vecs[3 * 128 + j]), out);
+                    }
+                    if (layer < 2) store_pieces(sA, (uint32_t)((col0 >> 3) + ch) * 2048u + row_off, h1, h2, h3);
+                }
+            }
+        }
+        // the two column halves of a walker live in warps w and w+4: combine through shared memory (sA is free now)
+        float *s_out = reinterpret_cast<float *>(sA);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (half == 1) s_out[row] = out;
+        __syncthreads();
+        if (half == 0 && i < n) {
+            const float e = fmaxf(out + s_out[row] + __ldg(&vecs[3 * 128 + 128]), 0.0f);      // + b3, relu
+            v[i] = (double)(e * 4.556335281212229e-6f);
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(128));
+}
+
+// ---------------------------------------------------------------- host side: weight images + launch
+struct NNDeviceWeights {
+    float *packed = nullptr;            // raw packed float32 weights (CUDA-core kernel)
+    unsigned char *images = nullptr;    // bf16-split, core-matrix formatted weight images (tcgen05 kernel)
+    float *vecs = nullptr;              // biases, W3, b3
+};
+
+static inline unsigned short host_bf16_rn(float x)
+{
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    if ((u & 0x7F800000u) == 0x7F800000u) return (unsigned short)(u >> 16);
+    u += 0x7FFFu + ((u >> 16) & 1u);
+    return (unsigned short)(u >> 16);
+}
+static inline float host_bf16_to_f(unsigned short h)
+{
+    uint32_t u = (uint32_t)h << 16;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+
+// images of the B operands: B[n][k] = W[k][n] (K-major), N padded to 128, K padded to 16 / 128
+static void nn_build_images(const float *P, std::vector<unsigned char> &img, std::vector<float> &vecs)
+{
+    img.assign(TC_IMG_TOTAL, 0);
+    vecs.assign(TC_VEC_FLOATS, 0.0f);
+    const int woff[3] = {NN_W0, NN_W1, NN_W2}, boff[3] = {NN_B0, NN_B1, NN_B2}, kreal[3] = {NN_IN, NN_H, NN_H};
+    size_t base = 0;
+    for (int l = 0; l < 3; ++l) {
+        const int kpad = l == 0 ? 16 : 128;
+        const size_t piece = (size_t)128 * kpad * 2;
+        for (int n = 0; n < NN_H; ++n)
+            for (int k = 0; k < kreal[l]; ++k) {
+                const float w = P[woff[l] + k * NN_H + n];
+                const unsigned short h1 = host_bf16_rn(w);
+                const float r1 = w - host_bf16_to_f(h1);
+                const unsigned short h2 = host_bf16_rn(r1);
+                const unsigned short h3 = host_bf16_rn(r1 - host_bf16_to_f(h2));
+                const size_t off = (size_t)(k / 8) * 2048 + (size_t)(n / 8) * 128 + (size_t)(n % 8) * 16 + (size_t)(k % 8) * 2;
+                const unsigned short hs[3] = {h1, h2, h3};
+                for (int p = 0; p < 3; ++p) memcpy(&img[base + p * piece + off], &hs[p], 2);
+            }
+        for (int n = 0; n < NN_H; ++n) vecs[l * 128 + n] = P[boff[l] + n];
+        base += 3 * piece;
+    }
+    for (int n = 0; n < NN_H; ++n) vecs[3 * 128 + n] = P[NN_W3 + n];
+    vecs[3 * 128 + 128] = P[NN_B3];
+}
+
+static int nn_upload_weights(NNDeviceWeights &w, const float *packed)
+{
+    std::vector<unsigned char> img;
+    std::vector<float> vecs;
+    nn_build_images(packed, img, vecs);
+    if (!w.packed) PVD_CUDA(cudaMalloc((void **)&w.packed, (size_t)NN_NPARAM * 4));
+    if (!w.images) PVD_CUDA(cudaMalloc((void **)&w.images, TC_IMG_TOTAL));
+    if (!w.vecs) PVD_CUDA(cudaMalloc((void **)&w.vecs, TC_VEC_FLOATS * 4));
+    PVD_CUDA(cudaMemcpy(w.packed, packed, (size_t)NN_NPARAM * 4, cudaMemcpyHostToDevice));
+    PVD_CUDA(cudaMemcpy(w.images, img.data(), TC_IMG_TOTAL, cudaMemcpyHostToDevice));
+    PVD_CUDA(cudaMemcpy(w.vecs, vecs.data(), TC_VEC_FLOATS * 4, cudaMemcpyHostToDevice));
+    return PVD_OK;
+}
+
 constexpr size_t NN_SMEM_BYTES = 2 * NN_H * NN_TILE * sizeof(float);
+static bool nn_use_cuda_cores()
+{
+    const char *e = getenv("PVD_NN_FP32");      // debugging / cross-check switch: float32 FMA kernel instead of tcgen05
+    return e && e[0] == '1';
+}
 static int nn_prepare_launch()
 {
     static bool done = false;
     if (!done) {
         PVD_CUDA(cudaFuncSetAttribute(k_nn_h4o2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NN_SMEM_BYTES));
+        PVD_CUDA(cudaFuncSetAttribute(k_nn_h4o2_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
         done = true;
     }
     return PVD_OK;
 }
-static float *g_nn_weights = nullptr;     // process-wide copy for the stand-alone entry point
+static NNDeviceWeights g_nn;     // process-wide weights for the stand-alone entry point
 
-static int nn_launch_soa(cudaStream_t stream, const double *x, const DevState *st, int parity, long long cap, double *v, int grid,
-                         const float *weights)
+// coords: soa != 0 -> SoA with stride cap and n from the device state; else AoS with n_fixed walkers
+static int nn_launch(cudaStream_t stream, const double *x, int soa, long long cap, const DevState *st, int parity, long long n_fixed,
+                     long long n_upper, double *v, const NNDeviceWeights &w)
 {
-    if (!weights) return pvd_fail(PVD_E_STATE, "NN potential: weights not set (pvd_sim_set_nn_weights)");
+    if (!w.packed) return pvd_fail(PVD_E_STATE, "NN potential: weights not set");
     if (int rc = nn_prepare_launch()) return rc;
-    k_nn_h4o2<<<grid, NN_THREADS, NN_SMEM_BYTES, stream>>>(x, 1, cap, st, parity, 0, weights, v, nullptr);
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    if (nn_use_cuda_cores()) {
+        long long g = (n_upper + NN_TILE - 1) / NN_TILE;
+        if (g > 3ll * sms) g = 3ll * sms;
+        k_nn_h4o2<<<(int)(g < 1 ? 1 : g), NN_THREADS, NN_SMEM_BYTES, stream>>>(x, soa, cap, st, parity, n_fixed, w.packed, v, nullptr);
+    } else {
+        long long g = (n_upper + TC_M - 1) / TC_M;
+        if (g > sms) g = sms;                                    // persistent: one CTA per SM (192 KB of shared memory each)
+        k_nn_h4o2_tc<<<(int)(g < 1 ? 1 : g), TC_THREADS, TC_SMEM_BYTES, stream>>>(x, soa, cap, st, parity, n_fixed, w.images, w.vecs, v);
+    }
     PVD_CHECK_LAUNCH();
     return PVD_OK;
 }

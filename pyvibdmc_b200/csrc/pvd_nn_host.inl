@@ -14,7 +14,7 @@ static int nn_enqueue_discrete_step(pvd_sim *s, StepArgs &a)
         k_displace_soa<PVD_RNG_FP64><<<g, 256, 0, s->stream>>>(x, s->st.as<DevState>(), s->parity, 0, 0, s->cap, s->nc, s->cfg.ndim, s->cfg.seed,
                                                                nullptr, nullptr, s->sigma_dev.as<double>(), nullptr);
     PVD_CHECK_LAUNCH();
-    if (int rc = nn_launch_soa(s->stream, x, s->st.as<DevState>(), s->parity, s->cap, s->v[s->cur].as<double>(), s->nn_grid, s->nn_weights.as<float>()))
+    if (int rc = nn_launch(s->stream, x, 1, s->cap, s->st.as<DevState>(), s->parity, 0, s->cap, s->v[s->cur].as<double>(), s->nn_w))
         return rc;
     k_branch_discrete<<<g, PVD_CTA, 0, s->stream>>>(a);
     return PVD_OK;
@@ -27,31 +27,28 @@ int pvd_sim_set_nn_weights(pvd_sim *s, const float *packed, int64_t nfloats)
     SIM_CHECK(s);
     SIM_DEVICE(s);
     PVD_REQUIRE(packed && nfloats == NN_NPARAM, "expected 31081 packed float32 weights");
-    PVD_CUDA(s->nn_weights.alloc((size_t)NN_NPARAM * 4));
-    PVD_CUDA(cudaMemcpy(s->nn_weights.p, packed, (size_t)NN_NPARAM * 4, cudaMemcpyHostToDevice));
-    return PVD_OK;
+    return nn_upload_weights(s->nn_w, packed);
 }
 
 int pvd_nn_h4o2_set_weights(const float *packed, int64_t nfloats)
 {
     PVD_REQUIRE(packed && nfloats == NN_NPARAM, "expected 31081 packed float32 weights");
     if (int rc = ensure_device_ready()) return rc;
-    if (!g_nn_weights) PVD_CUDA(cudaMalloc((void **)&g_nn_weights, (size_t)NN_NPARAM * 4));
-    PVD_CUDA(cudaMemcpy(g_nn_weights, packed, (size_t)NN_NPARAM * 4, cudaMemcpyHostToDevice));
-    return PVD_OK;
+    return nn_upload_weights(g_nn, packed);
 }
 
 int pvd_nn_h4o2(const double *xyz, int64_t n, double *v)
 {
     PVD_REQUIRE(n >= 0 && (n == 0 || (xyz && v)), "pvd_nn_h4o2: bad arguments");
     if (int rc = ensure_device_ready()) return rc;
-    if (!g_nn_weights) return pvd_fail(PVD_E_STATE, "pvd_nn_h4o2: call pvd_nn_h4o2_set_weights first");
+    if (!g_nn.packed) return pvd_fail(PVD_E_STATE, "pvd_nn_h4o2: call pvd_nn_h4o2_set_weights first");
     if (n == 0) return PVD_OK;
-    const float *wts = g_nn_weights;
-    if (int rc = nn_prepare_launch()) return rc;
-    return run_host_kernel(xyz, (size_t)n * 18 * 8, v, (size_t)n * 8, [&](void *in, void *out) {
-        k_nn_h4o2<<<grid_for(n, NN_TILE, 3), NN_THREADS, NN_SMEM_BYTES>>>((const double *)in, 0, 0, nullptr, 0, n, wts, (double *)out, nullptr);
+    int rc_launch = PVD_OK;
+    const int rc = run_host_kernel(xyz, (size_t)n * 18 * 8, v, (size_t)n * 8, [&](void *in, void *out) {
+        rc_launch = nn_launch(nullptr, (const double *)in, 0, 0, nullptr, 0, n, n, (double *)out, g_nn);
+        g_pvd_launches.fetch_sub(1);      // run_host_kernel counts the launch itself
     });
+    return rc_launch ? rc_launch : rc;
 }
 
 int pvd_coulomb_descriptor(const double *xyz, int64_t n, int32_t natoms, const double *z, double *desc)

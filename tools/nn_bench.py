@@ -1,0 +1,34 @@
+#!/usr/bin/env python
+"""NN water-dimer potential: walkers/s of the tcgen05 kernel vs the float32 CUDA-core kernel (kernel time from CUDA
+events inside pvd_nn_h4o2, host<->device copies excluded) and the tensor-core roofline fraction
+(61 440 algorithmic flop / walker; 6 bf16 MMAs per product term are executed for fp32 accuracy)."""
+import json
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")))
+from pyvibdmc_b200 import kernels as K  # noqa: E402
+
+dimer = np.array([[-1.502169, -0.191359, 1.434927], [-0.601054, -0.596972, 0.0], [-1.502169, -0.191359, -1.434927],
+                  [1.350759, 0.111656, 0.0], [2.023531, -0.588557, 0.0], [0.0, 0.0, 0.0]]) / 0.529177
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 2_000_000
+x = dimer[None] + np.random.default_rng(0).normal(0, 0.1, size=(n, 6, 3))
+w = np.load(os.path.join(os.path.dirname(K.__file__), "sample_potentials", "TensorflowPots", "sample_h4o2_nn_packed.npy"))
+K.nn_h4o2_set_weights(w)
+out = {}
+for mode in ("tcgen05", "cuda_cores"):
+    os.environ["PVD_NN_FP32"] = "1" if mode == "cuda_cores" else "0"
+    best = 1e9
+    for _ in range(4):
+        v = K.nn_h4o2(x)
+        best = min(best, K.last_kernel_ms())
+    out[mode] = {"ms": best, "walkers_per_s": n / (best * 1e-3), "algorithmic_tflops": n * 61440 / (best * 1e-3) / 1e12,
+                 "mean_cm1": float(v.mean() / 4.556335281212229e-6)}
+peaks = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "MEASURED_PEAKS.json")
+peak = json.load(open(peaks))["bf16_tflops"] if os.path.exists(peaks) else 1590.0
+out["tensor_peak_tflops_bf16"] = peak
+out["tcgen05"]["frac_of_bf16_peak_algorithmic"] = out["tcgen05"]["algorithmic_tflops"] / peak
+out["tcgen05"]["frac_of_bf16_peak_executed_6x"] = 6 * out["tcgen05"]["algorithmic_tflops"] * (128 * 128 * (16 + 128 + 128)) / (15 * 120 + 120 * 120 * 2) / peak
+print(json.dumps(out, indent=1))
