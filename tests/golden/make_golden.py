@@ -301,10 +301,10 @@ def gen_traj():
 def gen_descriptor():
     from pyvibdmc.simulation_utilities.tensorflow_descriptors.distance_descriptors import DistIt
     rng = np.random.default_rng(21)
-    dimer = np.array([[-1.502169, -0.191359, 1.434927], [-0.601054, -0.596972, -0.000000],
-                      [-1.502169, -0.191359, -1.434927], [1.350759, 0.111656, 0.000000],
-                      [2.023531, -0.588557, 0.000000], [0.0, 0.0, 0.0]])
+    dimer = np.array([[1.513632, -0.005249, -0.121857], [0.560102, 0.002812, 0.048059], [1.913196, 0.033035, 0.750687],
+                      [-1.385643, 0.004325, 0.110302], [-1.750594, 0.746224, -0.382028], [-1.746613, -0.774680, -0.324277]])
     cds = (dimer[None] + rng.normal(0, 0.1, size=(512, 6, 3))) / 0.529177
+    cds[0] = dimer / 0.529177                          # the reference's equilibrium dimer (tests/test_analysis.py:77-82)
     coul = DistIt([8, 1, 1] * 2, 'coulomb', force_numpy=True)
     save("descriptor_golden.npz", coords=cds, coulomb=np.asarray(coul.run(cds)), zs=np.array([8, 1, 1] * 2))
 

@@ -166,3 +166,29 @@ def test_massive_event_raises_and_still_writes_outputs(pv, tmp_path):
         sim.run()
     assert os.path.exists(f"{out}/boom_sim_info.hdf5") and len(glob.glob(f"{out}/chkpts/boom_*.pickle")) == 1
     assert "Final checkpoint is written" in open(f"{out}/boom_log.txt").read()
+
+
+def test_nn_water_dimer_dmc(pv, tmp_path):
+    """BASELINE config 5 in miniature: (H2O)2 with the shipped NN surface (Coulomb descriptor + MLP on tcgen05)."""
+    import importlib.util
+    d = sample_dir(pv, "TensorflowPots")
+    spec = importlib.util.spec_from_file_location("call_sample_model_b200", os.path.join(d, "call_sample_model.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    model = mod.load_packed_weights()
+    pot = pv.NN_Potential(potential_function='sample_h4o2_pot', python_file='call_sample_model.py', potential_directory=d,
+                          model=model, pot_kwargs={'descriptor': None, 'batch_size': 100})
+    dimer = np.array([[1.513632, -0.005249, -0.121857], [0.560102, 0.002812, 0.048059], [1.913196, 0.033035, 0.750687],
+                      [-1.385643, 0.004325, 0.110302], [-1.750594, 0.746224, -0.382028], [-1.746613, -0.774680, -0.324277]]) / 0.529177
+    v0 = pot.getpot(dimer[None])
+    assert 0.0 < v0[0] / WN < 50.0                               # ~7.6 cm-1 at the dimer minimum (SURVEY 8c)
+    sim = pv.DMC_Sim(sim_name="dimer", output_folder=str(tmp_path / "nn"), num_walkers=5000, num_timesteps=300, equil_steps=100,
+                     chkpt_every=150, wfn_every=100, desc_wt_steps=20, atoms=['O', 'H', 'H'] * 2, delta_t=5, potential=pot,
+                     start_structures=dimer[None], seed=8, log_every=50)
+    sim.run()
+    assert np.isfinite(sim._vref_vs_tau).all() and 2500 < sim._pop_vs_tau[-1] < 7500
+    zpe = sim._vref_vs_tau[150:].mean() / WN
+    assert 5000 < zpe < 15000, zpe                               # two waters' worth of zero-point energy (~9800 cm-1)
+    coords = sim.walkers
+    assert coords.shape[1:] == (6, 3)
+    assert np.allclose(sim._walker_pots, pot.getpot(coords), rtol=1e-5, atol=1e-9)

@@ -253,9 +253,10 @@ def test_nn_h4o2_vs_float32_oracle(K, oracle, path, monkeypatch):
     # float32 network: summation order differs between GPU and NumPy; bf16x3 splitting leaves ~2^-17 per product
     assert np.allclose(v, ref, rtol=5e-5, atol=5e-5 * np.abs(ref).max()), np.abs(v - ref).max() / np.abs(ref).max()
     assert (v >= 0).all() and v.dtype == np.float64
+    assert abs(v[0] / WN - 7.62) < 0.05                         # equilibrium water dimer (reference tests/test_analysis.py:77-82)
     # ragged sizes and a physical sanity value: ~7.6 cm-1 at the water-dimer minimum
-    dimer = np.array([[-1.502169, -0.191359, 1.434927], [-0.601054, -0.596972, -0.000000], [-1.502169, -0.191359, -1.434927],
-                      [1.350759, 0.111656, 0.000000], [2.023531, -0.588557, 0.000000], [0.0, 0.0, 0.0]])
+    dimer = np.array([[1.513632, -0.005249, -0.121857], [0.560102, 0.002812, 0.048059], [1.913196, 0.033035, 0.750687],
+                      [-1.385643, 0.004325, 0.110302], [-1.750594, 0.746224, -0.382028], [-1.746613, -0.774680, -0.324277]])
     for n in (1, 63, 64, 65, 127, 128, 129, 1000):
         vv = K.nn_h4o2(g["coords"][:n] if n <= len(g["coords"]) else np.tile(g["coords"], (2, 1, 1))[:n])
         assert np.allclose(vv[:min(n, 512)], v[:min(n, 512)], rtol=1e-6, atol=1e-9)

@@ -11,8 +11,8 @@ import numpy as np
 sys.path.insert(0, os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")))
 from pyvibdmc_b200 import kernels as K  # noqa: E402
 
-dimer = np.array([[-1.502169, -0.191359, 1.434927], [-0.601054, -0.596972, 0.0], [-1.502169, -0.191359, -1.434927],
-                  [1.350759, 0.111656, 0.0], [2.023531, -0.588557, 0.0], [0.0, 0.0, 0.0]]) / 0.529177
+dimer = np.array([[1.513632, -0.005249, -0.121857], [0.560102, 0.002812, 0.048059], [1.913196, 0.033035, 0.750687],
+                      [-1.385643, 0.004325, 0.110302], [-1.750594, 0.746224, -0.382028], [-1.746613, -0.774680, -0.324277]]) / 0.529177
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 2_000_000
 x = dimer[None] + np.random.default_rng(0).normal(0, 0.1, size=(n, 6, 3))
 w = np.load(os.path.join(os.path.dirname(K.__file__), "sample_potentials", "TensorflowPots", "sample_h4o2_nn_packed.npy"))
