@@ -109,23 +109,26 @@ __global__ void __launch_bounds__(NN_THREADS) k_nn_h4o2(const double *__restrict
 //
 // Tile: 128 walkers per CTA (UMMA M = 128, one walker per TMEM lane / per thread), N = 128 output
 // neurons (120 padded), fp32 accumulators in TMEM (128 columns).  fp32 accuracy is kept by splitting
-// every activation and every weight into three bf16 pieces (a = a1 + a2 + a3) and issuing the six
-// leading cross terms (a1w1, a1w2, a2w1, a2w2, a1w3, a3w1; residual ~2^-17) as kind::f16 MMAs with
+// every activation and every weight into two bf16 pieces and issuing the four
+// cross terms of a two-piece split (x = x1 + x2: a1w1, a1w2, a2w1, a2w2; residual ~2^-16, tighter than the TF32
+// path TensorFlow itself takes for float32 matmuls on tensor-core GPUs) as kind::f16 MMAs with
 // K = 16.  Operands are K-major, un-swizzled "core matrix" layout in shared memory:
 //     byte(row, k) = (k/8) * (128*16) + (row/8) * 128 + (row%8) * 16 + (k%8) * 2      (LBO = 2048, SBO = 128)
 // so that thread `row` writes its eight consecutive k values as one conflict-free 16-byte store.
-// Per layer: weights image (pre-formatted on the host) -> smem, 6 x K/16 MMAs issued by one thread,
+// All three weight images (pre-formatted on the host, 136 KB) are loaded once per persistent CTA by bulk TMA copies;
+// per layer 4 x K/16 MMAs are issued by one thread,
 // tcgen05.commit -> mbarrier, then every thread drains its own TMEM lane (tcgen05.ld 32x32b.x32), adds
 // the bias, applies swish, splits into bf16 pieces and stores the next layer's A operand.
 // =====================================================================================================
-constexpr int TC_M = 128, TC_N = 128, TC_THREADS = 256;
+constexpr int TC_M = 128, TC_N = 128, TC_THREADS = 512;
 constexpr int TC_PIECE_BYTES_K128 = 128 * 128 * 2;          // one bf16 operand piece, K = 128
 constexpr int TC_PIECE_BYTES_K16 = 128 * 16 * 2;
-constexpr int TC_IMG_L0 = 3 * TC_PIECE_BYTES_K16;            // weights image, layer 0 (K padded 15 -> 16)
-constexpr int TC_IMG_L12 = 3 * TC_PIECE_BYTES_K128;          // weights image, layers 1 and 2
+constexpr int TC_NPIECE = 2;                                 // bf16 pieces per operand (x = x1 + x2, residual ~2^-17)
+constexpr int TC_IMG_L0 = TC_NPIECE * TC_PIECE_BYTES_K16;    // weights image, layer 0 (K padded 15 -> 16)
+constexpr int TC_IMG_L12 = TC_NPIECE * TC_PIECE_BYTES_K128;  // weights image, layers 1 and 2
 constexpr int TC_IMG_TOTAL = TC_IMG_L0 + 2 * TC_IMG_L12;     // bytes of pre-formatted bf16 weight images
 constexpr int TC_VEC_FLOATS = 3 * 128 + 128 + 4;             // b0,b1,b2 (padded), W3 (padded), b3
-constexpr size_t TC_SMEM_BYTES = 6 * TC_PIECE_BYTES_K128 + TC_IMG_L0 + 64;
+constexpr size_t TC_SMEM_BYTES = 3 * TC_IMG_L12 + TC_IMG_L0 + 64 + TC_VEC_FLOATS * 4 + 128 * 4 * 4;   // A, W1, W2, W0, barriers, vectors
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr)
@@ -155,48 +158,49 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
 }
-// split x into three bf16 pieces (round to nearest even each time)
-__device__ __forceinline__ void split3(float x, unsigned short &h1, unsigned short &h2, unsigned short &h3)
+// split two floats into two packed bf16x2 pieces each (round to nearest even at both levels): x = p1 + p2 up to ~2^-17
+__device__ __forceinline__ void split2x2(float x0, float x1, uint32_t &p1, uint32_t &p2)
 {
-    const __nv_bfloat16 b1 = __float2bfloat16_rn(x);
-    const float r1 = x - __bfloat162float(b1);
-    const __nv_bfloat16 b2 = __float2bfloat16_rn(r1);
-    const float r2 = r1 - __bfloat162float(b2);
-    const __nv_bfloat16 b3 = __float2bfloat16_rn(r2);
-    h1 = __bfloat16_as_ushort(b1); h2 = __bfloat16_as_ushort(b2); h3 = __bfloat16_as_ushort(b3);
+    __nv_bfloat162 b = __floats2bfloat162_rn(x0, x1);
+    p1 = *reinterpret_cast<uint32_t *>(&b);
+    const float r0 = x0 - __uint_as_float(p1 << 16), r1 = x1 - __uint_as_float(p1 & 0xFFFF0000u);
+    b = __floats2bfloat162_rn(r0, r1);
+    p2 = *reinterpret_cast<uint32_t *>(&b);
 }
 __device__ __forceinline__ float swish_fast(float z) { return __fdividef(z, 1.0f + __expf(-z)); }
-__device__ __forceinline__ void store_pieces(unsigned char *sA, uint32_t off, const unsigned short (&h1)[8], const unsigned short (&h2)[8],
-                                             const unsigned short (&h3)[8])
+// eight consecutive k values of one row -> one 16-byte store per piece
+__device__ __forceinline__ void store_chunk(unsigned char *sA, uint32_t off, const float (&h)[8])
 {
-    *reinterpret_cast<uint4 *>(sA + 0 * TC_PIECE_BYTES_K128 + off) = make_uint4(h1[0] | (h1[1] << 16), h1[2] | (h1[3] << 16), h1[4] | (h1[5] << 16), h1[6] | (h1[7] << 16));
-    *reinterpret_cast<uint4 *>(sA + 1 * TC_PIECE_BYTES_K128 + off) = make_uint4(h2[0] | (h2[1] << 16), h2[2] | (h2[3] << 16), h2[4] | (h2[5] << 16), h2[6] | (h2[7] << 16));
-    *reinterpret_cast<uint4 *>(sA + 2 * TC_PIECE_BYTES_K128 + off) = make_uint4(h3[0] | (h3[1] << 16), h3[2] | (h3[3] << 16), h3[4] | (h3[5] << 16), h3[6] | (h3[7] << 16));
+    uint32_t a[4], b[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) split2x2(h[2 * q], h[2 * q + 1], a[q], b[q]);
+    *reinterpret_cast<uint4 *>(sA + 0 * TC_PIECE_BYTES_K128 + off) = make_uint4(a[0], a[1], a[2], a[3]);
+    *reinterpret_cast<uint4 *>(sA + 1 * TC_PIECE_BYTES_K128 + off) = make_uint4(b[0], b[1], b[2], b[3]);
 }
 
 // images: [L0 | L1 | L2] bf16 weight images (see host builder); vecs: b0[128] b1[128] b2[128] W3[128] b3
-// 256 threads: warp w owns TMEM lanes (walkers) 32*(w%4).. and the column half w/4 of the 128 outputs.
+// 512 threads: warp w owns TMEM lanes (walkers) 32*(w%4).. and the 32-column quarter w/4 of the 128 outputs,
+// i.e. four threads share a walker during the epilogues (4 warps per scheduler hide the TMEM / SFU latencies).
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_nn_h4o2_tc(const double *__restrict__ xyz, int soa, long long cap, const DevState *st, int parity, long long n_fixed,
              const unsigned char *__restrict__ images, const float *__restrict__ vecs, double *__restrict__ v)
 {
     extern __shared__ __align__(1024) unsigned char tc_smem[];
-    unsigned char *sA = tc_smem;                                   // 3 pieces x 32 KB: activations (A operand)
-    unsigned char *sW = tc_smem + 3 * TC_PIECE_BYTES_K128;         // 3 pieces x 32 KB: weights of layer 1 / 2 (B operand)
-    unsigned char *sW0 = tc_smem + 6 * TC_PIECE_BYTES_K128;        // 12 KB: weights of layer 0, resident
-    uint64_t *bar = reinterpret_cast<uint64_t *>(sW0 + TC_IMG_L0);  // [0] MMA done, [1] weights landed, [2] layer-0 weights landed
+    unsigned char *sA = tc_smem;                                   // 2 pieces x 32 KB: activations (A operand)
+    unsigned char *sW = tc_smem + TC_IMG_L12;                      // 2 x (2 pieces x 32 KB): weights of layers 1 and 2, resident
+    unsigned char *sW0 = tc_smem + 3 * TC_IMG_L12;                 // 8 KB: weights of layer 0, resident
+    uint64_t *bar = reinterpret_cast<uint64_t *>(sW0 + TC_IMG_L0);  // [0] MMA done, [2] weights landed
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sW0 + TC_IMG_L0 + 32);
-    float *s_half = reinterpret_cast<float *>(sW0 + TC_IMG_L0 + 40);   // unused padding keeps alignment
-    (void)s_half;
+    float *s_vec = reinterpret_cast<float *>(sW0 + TC_IMG_L0 + 64);                 // biases, W3, b3
+    float *s_out = s_vec + TC_VEC_FLOATS;                                          // [4 quarters][128 rows] partial outputs
     const long long n = st ? st[parity].n : n_fixed;
     if (st && st[parity].err) return;
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const int row = (warp & 3) * 32 + lane;                        // walker of this thread inside the tile
-    const int half = warp >> 2;                                    // which 64 output columns this thread drains
-    const uint32_t mma_bar = smem_u32(&bar[0]), w_bar = smem_u32(&bar[1]), w0_bar = smem_u32(&bar[2]);
+    const int quarter = warp >> 2;                                 // which 32 output columns this thread drains
+    const uint32_t mma_bar = smem_u32(&bar[0]), w0_bar = smem_u32(&bar[2]);
     if (t == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mma_bar));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(w_bar));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(w0_bar));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -204,30 +208,28 @@ k_nn_h4o2_tc(const double *__restrict__ xyz, int soa, long long cap, const DevSt
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(128));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
+    for (int k = t; k < TC_VEC_FLOATS; k += TC_THREADS) s_vec[k] = vecs[k];
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_slot;
-    if (t == 0) {                                                  // layer-0 weights: loaded once per CTA
-        mbar_expect_tx(w0_bar, TC_IMG_L0);
+    if (t == 0) {                                                  // all weights: loaded once per (persistent) CTA by the TMA engine
+        mbar_expect_tx(w0_bar, TC_IMG_TOTAL);
         bulk_load(smem_u32(sW0), images, TC_IMG_L0, w0_bar);
+        for (int q = 0; q < 2 * TC_NPIECE; ++q)
+            bulk_load(smem_u32(sW + q * TC_PIECE_BYTES_K128), images + TC_IMG_L0 + q * TC_PIECE_BYTES_K128, TC_PIECE_BYTES_K128, w0_bar);
     }
     // instruction descriptor: D = F32, A = B = BF16, K-major both, N = 128, M = 128
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
     const double zs[6] = {8.0, 1.0, 1.0, 8.0, 1.0, 1.0};
-    uint32_t mma_phase = 0, w_phase = 0;
+    uint32_t mma_phase = 0;
     const uint32_t row_off = (uint32_t)((row >> 3) * 128 + (row & 7) * 16);        // this walker's row inside a k-chunk
-    const int pa[6] = {0, 0, 1, 1, 0, 2}, pb[6] = {0, 1, 0, 1, 2, 0};
+    const int pa[4] = {0, 0, 1, 1}, pb[4] = {0, 1, 0, 1};         // cross terms a1w1 + a1w2 + a2w1 + a2w2
 
     for (long long base = (long long)blockIdx.x * TC_M; base < n; base += (long long)gridDim.x * TC_M) {
         const long long i = base + row;
-        if (t == 0) {                                              // layer-1 weights stream in while the descriptor is computed
-            mbar_expect_tx(w_bar, TC_IMG_L12);
-            for (int p = 0; p < 3; ++p)
-                bulk_load(smem_u32(sW + p * TC_PIECE_BYTES_K128), images + TC_IMG_L0 + p * TC_PIECE_BYTES_K128, TC_PIECE_BYTES_K128, w_bar);
-        }
-        // ---- layer-0 A operand: Coulomb descriptor, 15 features + 1 zero pad; the two threads of a row take 8 features each
-        {
+        // ---- layer-0 A operand: Coulomb descriptor, 15 features + 1 zero pad; quarters 0 and 1 take 8 features each
+        if (quarter < 2) {
             float feat[8];
 #pragma unroll
             for (int p = 0; p < 8; ++p) feat[p] = 0.0f;
@@ -240,17 +242,14 @@ k_nn_h4o2_tc(const double *__restrict__ xyz, int soa, long long cap, const DevSt
                 for (int a = 0; a < 6; ++a)
 #pragma unroll
                     for (int b = a + 1; b < 6; ++b) {
-                        if ((p >> 3) == half) {
+                        if ((p >> 3) == quarter) {
                             const double dx = c[3 * a] - c[3 * b], dy = c[3 * a + 1] - c[3 * b + 1], dz = c[3 * a + 2] - c[3 * b + 2];
                             feat[p & 7] = (float)(zs[a] * zs[b] * rsqrt(dx * dx + dy * dy + dz * dz));
                         }
                         ++p;
                     }
             }
-            unsigned short h1[8], h2[8], h3[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) split3(feat[e], h1[e], h2[e], h3[e]);
-            store_pieces(sA, (uint32_t)half * 2048u + row_off, h1, h2, h3);
+            store_chunk(sA, (uint32_t)quarter * 2048u + row_off, feat);
         }
         float out = 0.0f;
 #pragma unroll 1
@@ -261,12 +260,11 @@ k_nn_h4o2_tc(const double *__restrict__ xyz, int soa, long long cap, const DevSt
             if (t == 0) {
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const int kblocks = layer == 0 ? 1 : 8;                        // K / 16
-                const unsigned char *wb = layer == 0 ? sW0 : sW;
+                const unsigned char *wb = layer == 0 ? sW0 : sW + (layer - 1) * TC_IMG_L12;
                 const int wpiece = layer == 0 ? TC_PIECE_BYTES_K16 : TC_PIECE_BYTES_K128;
-                if (layer == 0) mbar_wait(w0_bar, 0);                          // completes once; later waits return immediately
-                else { mbar_wait(w_bar, w_phase); w_phase ^= 1u; }
+                mbar_wait(w0_bar, 0);                                          // completes once; later waits return immediately
                 uint32_t accumulate = 0;
-                for (int term = 0; term < 6; ++term)
+                for (int term = 0; term < 4; ++term)
                     for (int kb = 0; kb < kblocks; ++kb) {
                         const uint64_t da = umma_desc(smem_u32(sA + pa[term] * TC_PIECE_BYTES_K128 + kb * 4096));
                         const uint64_t db = umma_desc(smem_u32(wb + pb[term] * wpiece + kb * 4096));
@@ -278,50 +276,38 @@ k_nn_h4o2_tc(const double *__restrict__ xyz, int soa, long long cap, const DevSt
             mbar_wait(mma_bar, mma_phase);
             mma_phase ^= 1u;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (t == 0 && layer == 1) {                                        // layer-2 weights replace layer-1's during the epilogue
-                mbar_expect_tx(w_bar, TC_IMG_L12);
-                for (int p = 0; p < 3; ++p)
-                    bulk_load(smem_u32(sW + p * TC_PIECE_BYTES_K128), images + TC_IMG_L0 + TC_IMG_L12 + p * TC_PIECE_BYTES_K128,
-                              TC_PIECE_BYTES_K128, w_bar);
-            }
-            // ---- epilogue: this thread's TMEM lane, its 64 columns, 32 at a time
-            const float *bias = vecs + layer * 128;
-#pragma unroll 1
-            for (int cb = 0; cb < 2; ++cb) {
-                uint32_t r[32];
-                const int col0 = half * 64 + cb * 32;
-                const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)col0;
-                asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                             "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                             "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                             : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                               "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                               "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                               "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                             : "r"(taddr));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            // ---- epilogue: this thread's TMEM lane, its 32 columns
+            const float *bias = s_vec + layer * 128;
+            uint32_t r[32];
+            const int col0 = quarter * 32;
+            const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)col0;
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                         "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                           "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                           "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                         : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                for (int ch = 0; ch < 4; ++ch) {
-                    unsigned short h1[8], h2[8], h3[8];
+            for (int ch = 0; ch < 4; ++ch) {
+                float h[8];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const int j = col0 + ch * 8 + e;
-                        const float hval = swish_fast(__uint_as_float(r[ch * 8 + e]) + __ldg(&bias[j]));
-                        if (layer < 2) split3(hval, h1[e], h2[e], h3[e]);
-                        else out = fmaf(hval, __ldg(&vecs[3 * 128 + j]), out);
-                    }
-                    if (layer < 2) store_pieces(sA, (uint32_t)((col0 >> 3) + ch) * 2048u + row_off, h1, h2, h3);
+                for (int e = 0; e < 8; ++e) {
+                    const int j = col0 + ch * 8 + e;
+                    h[e] = swish_fast(__uint_as_float(r[ch * 8 + e]) + bias[j]);
+                    if (layer == 2) out = fmaf(h[e], s_vec[3 * 128 + j], out);
                 }
+                if (layer < 2) store_chunk(sA, (uint32_t)((col0 >> 3) + ch) * 2048u + row_off, h);
             }
         }
-        // the two column halves of a walker live in warps w and w+4: combine through shared memory (sA is free now)
-        float *s_out = reinterpret_cast<float *>(sA);
+        // the four column quarters of a walker live in warps w, w+4, w+8, w+12: combine through shared memory
+        s_out[quarter * 128 + row] = out;
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
-        if (half == 1) s_out[row] = out;
-        __syncthreads();
-        if (half == 0 && i < n) {
-            const float e = fmaxf(out + s_out[row] + __ldg(&vecs[3 * 128 + 128]), 0.0f);      // + b3, relu
+        if (quarter == 0 && i < n) {
+            const float e = fmaxf(s_out[row] + s_out[128 + row] + s_out[256 + row] + s_out[384 + row] + s_vec[3 * 128 + 128], 0.0f);   // + b3, relu
             v[i] = (double)(e * 4.556335281212229e-6f);
         }
         __syncthreads();
@@ -369,13 +355,12 @@ static void nn_build_images(const float *P, std::vector<unsigned char> &img, std
                 const unsigned short h1 = host_bf16_rn(w);
                 const float r1 = w - host_bf16_to_f(h1);
                 const unsigned short h2 = host_bf16_rn(r1);
-                const unsigned short h3 = host_bf16_rn(r1 - host_bf16_to_f(h2));
                 const size_t off = (size_t)(k / 8) * 2048 + (size_t)(n / 8) * 128 + (size_t)(n % 8) * 16 + (size_t)(k % 8) * 2;
-                const unsigned short hs[3] = {h1, h2, h3};
-                for (int p = 0; p < 3; ++p) memcpy(&img[base + p * piece + off], &hs[p], 2);
+                const unsigned short hs[TC_NPIECE] = {h1, h2};
+                for (int p = 0; p < TC_NPIECE; ++p) memcpy(&img[base + p * piece + off], &hs[p], 2);
             }
         for (int n = 0; n < NN_H; ++n) vecs[l * 128 + n] = P[boff[l] + n];
-        base += 3 * piece;
+        base += TC_NPIECE * piece;
     }
     for (int n = 0; n < NN_H; ++n) vecs[3 * 128 + n] = P[NN_W3 + n];
     vecs[3 * 128 + 128] = P[NN_B3];
