@@ -339,6 +339,7 @@ static StepArgs make_args(pvd_sim *s, int do_branch)
     a.nc = s->nc;
     a.flip = s->cfg.weighting == PVD_WEIGHT_DISCRETE ? 1 : 0;
     for (int i = 0; i < PVD_MAX_ATOMS; ++i) a.sigma[i] = s->sigma[i];
+    for (int c = 0; c < PVD_MAX_COMP; ++c) a.sigc[c] = s->sigma[(c / (s->cfg.ndim > 0 ? s->cfg.ndim : 1)) % PVD_MAX_ATOMS];
     a.pot = s->pot;
     return a;
 }
@@ -600,10 +601,13 @@ static int enqueue_step(pvd_sim *s, int do_branch, const double *inj_disp, const
     } else if (cont) {
         if (int rc = cont_enqueue_step(s, a)) return rc;
     } else {
+#ifndef PVD_STEP_KERNEL
+#define PVD_STEP_KERNEL k_step_discrete
+#endif
 #define LAUNCH_DISC(POT)                                                                            \
     do {                                                                                            \
-        if (fast) k_step_discrete<POT, PVD_RNG_FAST><<<g, PVD_CTA, 0, s->stream>>>(a);             \
-        else k_step_discrete<POT, PVD_RNG_FP64><<<g, PVD_CTA, 0, s->stream>>>(a);                  \
+        if (fast) PVD_STEP_KERNEL<POT, PVD_RNG_FAST><<<g, PVD_CTA, 0, s->stream>>>(a);             \
+        else PVD_STEP_KERNEL<POT, PVD_RNG_FP64><<<g, PVD_CTA, 0, s->stream>>>(a);                  \
     } while (0)
         switch (s->cfg.potential) {
         case PVD_POT_H2O_PS: LAUNCH_DISC(PotH2O); break;

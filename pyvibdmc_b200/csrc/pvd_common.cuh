@@ -231,7 +231,9 @@ __device__ __forceinline__ void publish_aggregate(unsigned long long *status, lo
     if ((threadIdx.x & 31) == 0)
         st_relaxed_u64(&status[tile], pack_status(step, tile == 0 ? PVD_ST_PREFIX : PVD_ST_AGG, (unsigned)tile_total));
 }
-__device__ __forceinline__ long long resolve_prefix(unsigned long long *status, long long tile, long long step, int tile_total)
+// have_pre / pre: the caller already loaded this lane's status word of the first window (tile-1-lane) a while ago
+__device__ __forceinline__ long long resolve_prefix(unsigned long long *status, long long tile, long long step, int tile_total,
+                                                    bool have_pre = false, unsigned long long pre = 0ull)
 {
     const int lane = threadIdx.x & 31;
     if (tile == 0) return 0;
@@ -243,9 +245,10 @@ __device__ __forceinline__ long long resolve_prefix(unsigned long long *status, 
         bool ok = true;
         while (true) {
             if (idx >= 0) {
-                w = ld_relaxed_u64(&status[idx]);
+                w = have_pre ? pre : ld_relaxed_u64(&status[idx]);
                 ok = status_valid(w, step);
             }
+            have_pre = false;
             if (__all_sync(0xffffffffu, ok)) break;
             __nanosleep(64);              // give the issue slots to the warps we are waiting for
         }

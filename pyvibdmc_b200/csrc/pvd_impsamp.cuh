@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(PVD_CTA) k_imp_move(const StepArgs a, const Im
         } else {
             walker_normals<NC, RNG>(a.seed, i, step, y);
 #pragma unroll
-            for (int c = 0; c < NC; ++c) y[c] = __dmul_rn(a.sigma[c / a.ndim], y[c]);
+            for (int c = 0; c < NC; ++c) y[c] = __dmul_rn(a.sigc[c], y[c]);
         }
         // displaced = coords + disps + (inv_m * f_x) * dt
 #pragma unroll
