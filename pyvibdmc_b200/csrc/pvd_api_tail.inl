@@ -11,6 +11,9 @@ static ContArgs make_cont_args(pvd_sim *s)
     ca.copy_dst = s->copy_dst.as<int>();
     ca.copy_src = s->copy_src.as<int>();
     ca.cand = s->cand.as<ContCand>();
+    ca.sorted = s->cand_sorted.as<ContCand>();
+    ca.bin_start = s->bin_start.as<unsigned>();
+    ca.bin_fill = s->bin_fill.as<unsigned>();
     ca.hist = s->hist.as<unsigned>();
     ca.work = s->cont_work.as<ContWork>();
     ca.cand_cap = s->cap;
@@ -20,57 +23,73 @@ static ContArgs make_cont_args(pvd_sim *s)
     return ca;
 }
 
-// weight update + branching + Vref on energies already stored in v[cur] (in place)
-static int cont_enqueue_branch_only(pvd_sim *s, StepArgs &a)
+// kill list + histogram are produced by the k_cont_update instance the caller launched; then:
+// ranked candidates -> donor assignment -> copies -> Vref
+static int cont_launch_tail(pvd_sim *s, const StepArgs &a, const ContArgs &ca, long long *src_out)
 {
-    a.xin = a.xout = s->x[s->cur].as<double>();
-    a.vin = a.vout = s->v[s->cur].as<double>();
-    a.who_in = a.who_out = s->who[s->cur].as<int>();
-    a.flip = 0;
-    ContArgs ca = make_cont_args(s);
-    const int g = s->grid;
+    const int g = s->grid_light;
     const bool imp = s->cfg.trial != PVD_TRIAL_NONE;
-    k_cont_update<<<g, PVD_CTA, 0, s->stream>>>(a, ca);
-    PVD_CHECK_LAUNCH();
-    k_cont_hist<<<g, PVD_CTA, 0, s->stream>>>(a, ca);
+    k_cont_prefix<<<1, 1024, 0, s->stream>>>(a, ca);
     PVD_CHECK_LAUNCH();
     k_cont_collect<<<g, PVD_CTA, 0, s->stream>>>(a, ca);
+    PVD_CHECK_LAUNCH();
+    k_cont_rank<<<PVD_HIST_BINS, 1024, PVD_RANK_MAX_BIN * sizeof(ContCand), s->stream>>>(a, ca);
     PVD_CHECK_LAUNCH();
     k_cont_assign<<<1, 1024, 0, s->stream>>>(a, ca, s->cont_queue.as<ContCand>(), s->cont_root.as<int>(), s->cont_skip.as<unsigned char>());
     PVD_CHECK_LAUNCH();
     k_cont_copy<<<g, PVD_CTA, 0, s->stream>>>(a, ca, s->x[s->cur].as<double>(), s->v[s->cur].as<double>(), s->who[s->cur].as<int>(),
                                                imp ? s->f[s->cur].as<double>() : nullptr, imp ? s->psi[s->cur].as<double>() : nullptr,
-                                               imp ? s->lk[s->cur].as<double>() : nullptr, nullptr);
+                                               imp ? s->lk[s->cur].as<double>() : nullptr, src_out);
     PVD_CHECK_LAUNCH();
     k_cont_finish<<<g, PVD_CTA, 0, s->stream>>>(a, ca);
     PVD_CHECK_LAUNCH();
     return PVD_OK;
 }
 
+static void cont_in_place(pvd_sim *s, StepArgs &a)
+{
+    a.xin = a.xout = s->x[s->cur].as<double>();
+    a.vin = a.vout = s->v[s->cur].as<double>();
+    a.who_in = a.who_out = s->who[s->cur].as<int>();
+    a.flip = 0;
+}
+
+// weight update + branching + Vref on energies already stored in v[cur] (in place)
+static int cont_enqueue_branch_only(pvd_sim *s, StepArgs &a, long long *src_out)
+{
+    cont_in_place(s, a);
+    ContArgs ca = make_cont_args(s);
+    ca.tile = PVD_TILE * ContFromMemory::SUB;
+    k_cont_update<ContFromMemory><<<s->grid_light, PVD_CTA, 0, s->stream>>>(a, ca);
+    PVD_CHECK_LAUNCH();
+    return cont_launch_tail(s, a, ca, src_out);
+}
+
+// move + built-in potential + weight update in one kernel, then the branching tail
 static int cont_enqueue_step(pvd_sim *s, StepArgs &a)
 {
-    const int g = s->grid;
     const bool fast = s->cfg.rng_mode == PVD_RNG_FAST;
-    double *x = s->x[s->cur].as<double>(), *v = s->v[s->cur].as<double>();
-    a.xin = x;
-#define LAUNCH_MOVE(POT)                                                                            \
-    do {                                                                                            \
-        if (fast) k_move_pes<POT, PVD_RNG_FAST><<<g, PVD_CTA, 0, s->stream>>>(a, x, v);              \
-        else k_move_pes<POT, PVD_RNG_FP64><<<g, PVD_CTA, 0, s->stream>>>(a, x, v);                   \
+    cont_in_place(s, a);
+    ContArgs ca = make_cont_args(s);
+#define LAUNCH_CONT(POT)                                                                                             \
+    do {                                                                                                             \
+        const int gp = POT::MIN_CTAS >= 4 ? s->grid_light : s->grid;                                                 \
+        if (fast) { ca.tile = PVD_TILE * ContFused<POT, PVD_RNG_FAST>::SUB; k_cont_update<ContFused<POT, PVD_RNG_FAST>><<<gp, PVD_CTA, 0, s->stream>>>(a, ca); } \
+        else { ca.tile = PVD_TILE * ContFused<POT, PVD_RNG_FP64>::SUB; k_cont_update<ContFused<POT, PVD_RNG_FP64>><<<gp, PVD_CTA, 0, s->stream>>>(a, ca); }      \
     } while (0)
     switch (s->cfg.potential) {
-    case PVD_POT_H2O_PS: LAUNCH_MOVE(PotH2O); break;
+    case PVD_POT_H2O_PS: LAUNCH_CONT(PotH2O); break;
     case PVD_POT_HARMONIC:
-        if (s->nc == 1) LAUNCH_MOVE(PotHarm<1>);
-        else if (s->nc == 3) LAUNCH_MOVE(PotHarm<3>);
+        if (s->nc == 1) LAUNCH_CONT(PotHarm<1>);
+        else if (s->nc == 3) LAUNCH_CONT(PotHarm<3>);
         else return pvd_fail(PVD_E_ARG, "built-in harmonic potential supports 1 or 3 components");
         break;
-    case PVD_POT_MORSE1D: LAUNCH_MOVE(PotMorse); break;
+    case PVD_POT_MORSE1D: LAUNCH_CONT(PotMorse); break;
     default: return pvd_fail(PVD_E_STATE, "continuous weighting on the device needs a built-in fp64 potential");
     }
-#undef LAUNCH_MOVE
+#undef LAUNCH_CONT
     PVD_CHECK_LAUNCH();
-    return cont_enqueue_branch_only(s, a);
+    return cont_launch_tail(s, a, ca, nullptr);
 }
 
 extern "C" int pvd_branch_continuous(double *w, const double *v, int64_t n, double vref, double dt, double lower, double upper,
@@ -99,21 +118,7 @@ extern "C" int pvd_branch_continuous(double *w, const double *v, int64_t n, doub
     k_iota_i64<<<grid_for(n, 256, 16), 256, 0, s->stream>>>(dsrc.as<long long>(), n);
     PVD_CHECK_LAUNCH();
     StepArgs a = make_args(s, 1);
-    a.xin = a.xout = s->x[s->cur].as<double>();
-    a.vin = a.vout = s->v[s->cur].as<double>();
-    a.who_in = a.who_out = s->who[s->cur].as<int>();
-    a.flip = 0;
-    ContArgs ca = make_cont_args(s);
-    const int g = s->grid;
-    k_cont_update<<<g, PVD_CTA, 0, s->stream>>>(a, ca); PVD_CHECK_LAUNCH();
-    k_cont_hist<<<g, PVD_CTA, 0, s->stream>>>(a, ca); PVD_CHECK_LAUNCH();
-    k_cont_collect<<<g, PVD_CTA, 0, s->stream>>>(a, ca); PVD_CHECK_LAUNCH();
-    k_cont_assign<<<1, 1024, 0, s->stream>>>(a, ca, s->cont_queue.as<ContCand>(), s->cont_root.as<int>(), s->cont_skip.as<unsigned char>());
-    PVD_CHECK_LAUNCH();
-    k_cont_copy<<<g, PVD_CTA, 0, s->stream>>>(a, ca, s->x[s->cur].as<double>(), s->v[s->cur].as<double>(), s->who[s->cur].as<int>(), nullptr,
-                                               nullptr, nullptr, dsrc.as<long long>());
-    PVD_CHECK_LAUNCH();
-    k_cont_finish<<<g, PVD_CTA, 0, s->stream>>>(a, ca); PVD_CHECK_LAUNCH();
+    if (int rc = cont_enqueue_branch_only(s, a, dsrc.as<long long>())) return rc;
     PVD_CUDA(cudaStreamSynchronize(s->stream));
     PVD_CUDA(cudaMemcpy(w, s->w.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
     PVD_CUDA(cudaMemcpy(src, dsrc.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
@@ -216,7 +221,7 @@ static int imp_enqueue_step(pvd_sim *s, StepArgs &a, const double *inj_um)
     PVD_CHECK_LAUNCH();
     if (s->cfg.weighting == PVD_WEIGHT_CONTINUOUS) return cont_enqueue_branch_only(s, a);
     // discrete: branch on E_L with the effective time step, carrying f_x, psi and the local kinetic energy
-    k_branch_discrete<<<g, PVD_CTA, 0, s->stream>>>(a);
+    k_branch_discrete<<<s->grid_light, PVD_CTA, 0, s->stream>>>(a);
     PVD_CHECK_LAUNCH();
     s->cur ^= 1;
     return PVD_OK;

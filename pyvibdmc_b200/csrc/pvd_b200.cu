@@ -1,4 +1,5 @@
 // libpvd_b200: C-ABI implementation (see include/pvd_b200.h).  sm_100a only.
+#include <stdlib.h>
 #include "pvd_common.cuh"
 #include "pvd_rng.cuh"
 #include "pvd_potentials.cuh"
@@ -279,7 +280,7 @@ struct pvd_sim {
     DevBuf st, err_accum, status, part, ring, sums, sigma_dev, tickets;
     DevBuf inj_disp, inj_u, inj_um, stage, stage2;   // staging for host<->device transposes / injections
     DevBuf parent_x, parent_w;
-    DevBuf kill_idx, hist, cand, cont_work, copy_dst, copy_src, cont_queue, cont_root, cont_skip;
+    DevBuf kill_idx, hist, cand, cand_sorted, bin_start, bin_fill, cont_work, copy_dst, copy_src, cont_queue, cont_root, cont_skip;
     DevBuf trial_table, acc_count;
     NNDeviceWeights nn_w;
     TrialParamsDev trial_params{};
@@ -291,7 +292,8 @@ struct pvd_sim {
     int cur = 0;         // buffer holding the current walkers
     long long n_uploaded = 0;
     bool uploaded = false, ext_moved = false;
-    int grid = 1;
+    int grid = 1, grid_light = 1;
+    int ticket_batch = 1;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     PotParamsDev pot{};
     double sigma[PVD_MAX_ATOMS]{};
@@ -338,6 +340,7 @@ static StepArgs make_args(pvd_sim *s, int do_branch)
     a.ndim = s->cfg.ndim;
     a.nc = s->nc;
     a.flip = s->cfg.weighting == PVD_WEIGHT_DISCRETE ? 1 : 0;
+    a.ticket_batch = s->ticket_batch;
     for (int i = 0; i < PVD_MAX_ATOMS; ++i) a.sigma[i] = s->sigma[i];
     for (int c = 0; c < PVD_MAX_COMP; ++c) a.sigc[c] = s->sigma[(c / (s->cfg.ndim > 0 ? s->cfg.ndim : 1)) % PVD_MAX_ATOMS];
     a.pot = s->pot;
@@ -345,7 +348,7 @@ static StepArgs make_args(pvd_sim *s, int do_branch)
 }
 
 static int cont_enqueue_step(pvd_sim *, StepArgs &);
-static int cont_enqueue_branch_only(pvd_sim *, StepArgs &);
+static int cont_enqueue_branch_only(pvd_sim *, StepArgs &, long long *src_out = nullptr);
 static int imp_enqueue_step(pvd_sim *, StepArgs &, const double *);
 static int imp_initial_drift(pvd_sim *);
 static int nn_enqueue_discrete_step(pvd_sim *, StepArgs &);
@@ -422,7 +425,12 @@ int pvd_sim_create(const pvd_config *cfg, pvd_sim **out)
         TRY(s->kill_idx.alloc((size_t)cap * 4));
         TRY(s->hist.alloc(PVD_HIST_BINS * 4));
         TRY(cudaMemset(s->hist.p, 0, PVD_HIST_BINS * 4));
-        TRY(s->cand.alloc((size_t)2 * cap * sizeof(ContCand)));       // sorted candidates, padded to a power of two
+        TRY(s->cand.alloc((size_t)2 * cap * sizeof(ContCand)));       // candidates (fallback sort pads to a power of two)
+        TRY(s->cand_sorted.alloc((size_t)cap * sizeof(ContCand)));
+        TRY(s->bin_start.alloc(PVD_HIST_BINS * 4));
+        TRY(cudaFuncSetAttribute(k_cont_rank, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PVD_RANK_MAX_BIN * sizeof(ContCand))));
+        TRY(s->bin_fill.alloc(PVD_HIST_BINS * 4));
+        TRY(cudaMemset(s->bin_fill.p, 0, PVD_HIST_BINS * 4));
         TRY(s->cont_queue.alloc((size_t)2 * cap * sizeof(ContCand)));
         TRY(s->copy_dst.alloc((size_t)2 * cap * 4));
         TRY(s->copy_src.alloc((size_t)2 * cap * 4));
@@ -441,7 +449,15 @@ int pvd_sim_create(const pvd_config *cfg, pvd_sim **out)
     TRY(cudaMemset(s->status.p, 0, (size_t)ntiles * 8));
     // persistent-style grid: enough CTAs to cover the capacity, at most 8 per SM
     s->grid = grid_for(cap, PVD_CTA, 2);
-    TRY(s->part.alloc((size_t)s->grid * sizeof(WarpPartial)));
+    {
+        // heavy tiles (fused H2O step: ~9 us of fp64 work per tile) take one tile per ticket; light ones share a ticket
+        const bool heavy = cfg->potential == PVD_POT_H2O_PS && cfg->trial == PVD_TRIAL_NONE && cfg->weighting == PVD_WEIGHT_DISCRETE;
+        const char *e = getenv(heavy ? "PVD_TICKET_BATCH_HEAVY" : "PVD_TICKET_BATCH_LIGHT");
+        s->ticket_batch = e ? atoi(e) : 1;
+        if (s->ticket_batch < 1 || s->ticket_batch > 2) s->ticket_batch = 1;   // > 2 serialises the look-back chain (measured: 250x slower)
+    }
+    s->grid_light = grid_for(cap, PVD_CTA, 4);       // kernels without a heavy potential: more warps per SM hide the memory latency
+    TRY(s->part.alloc((size_t)s->grid_light * sizeof(WarpPartial)));
     TRY(s->tickets.alloc(2 * PVD_WARPS * PVD_TICKET_STRIDE * 4));
     TRY(cudaMemset(s->tickets.p, 0, 2 * PVD_WARPS * PVD_TICKET_STRIDE * 4));
     TRY(s->ring.alloc((size_t)cfg->stats_ring * sizeof(pvd_step_stats)));
@@ -606,8 +622,9 @@ static int enqueue_step(pvd_sim *s, int do_branch, const double *inj_disp, const
 #endif
 #define LAUNCH_DISC(POT)                                                                            \
     do {                                                                                            \
-        if (fast) PVD_STEP_KERNEL<POT, PVD_RNG_FAST><<<g, PVD_CTA, 0, s->stream>>>(a);             \
-        else PVD_STEP_KERNEL<POT, PVD_RNG_FP64><<<g, PVD_CTA, 0, s->stream>>>(a);                  \
+        const int gp = POT::MIN_CTAS >= 4 ? s->grid_light : g;                                      \
+        if (fast) PVD_STEP_KERNEL<POT, PVD_RNG_FAST><<<gp, PVD_CTA, 0, s->stream>>>(a);            \
+        else PVD_STEP_KERNEL<POT, PVD_RNG_FP64><<<gp, PVD_CTA, 0, s->stream>>>(a);                 \
     } while (0)
         switch (s->cfg.potential) {
         case PVD_POT_H2O_PS: LAUNCH_DISC(PotH2O); break;
@@ -730,7 +747,7 @@ int pvd_sim_ext_finish(pvd_sim *s, const double *v, int64_t n, int32_t do_branch
     if (s->cfg.weighting == PVD_WEIGHT_CONTINUOUS) {
         if (int rc = cont_enqueue_branch_only(s, a)) return rc;
     } else {
-        k_branch_discrete<<<s->grid, PVD_CTA, 0, s->stream>>>(a);
+        k_branch_discrete<<<s->grid_light, PVD_CTA, 0, s->stream>>>(a);
         PVD_CHECK_LAUNCH();
         s->cur ^= 1;
     }
@@ -925,7 +942,7 @@ int pvd_branch_discrete(const double *v, int64_t n, double vref, double dt, cons
     a.st = dst.as<DevState>(); a.err_accum = derr.as<unsigned>(); a.status = dstatus.as<unsigned long long>();
     a.part = dpart.as<WarpPartial>(); a.tickets = dtick.as<unsigned>(); a.ring = dring.as<pvd_step_stats>(); a.ring_len = 1; a.sums = dsums.as<double>();
     a.inj_u = du.as<double>(); a.counts_out = dcounts.as<int>(); a.idx_out = didx.as<long long>();
-    a.cap = cap; a.n0 = n0; a.dt = dt; a.alpha = 1.0 / (2.0 * dt); a.parity = 0; a.do_branch = 1; a.world = 1; a.rank = 0; a.nc = 0; a.ndim = 1;
+    a.cap = cap; a.n0 = n0; a.dt = dt; a.alpha = 1.0 / (2.0 * dt); a.parity = 0; a.do_branch = 1; a.world = 1; a.rank = 0; a.nc = 0; a.ndim = 1; a.ticket_batch = 1;
     EventPair ev;
     PVD_CUDA(ev.init());
     PVD_CUDA(cudaEventRecord(ev.a));

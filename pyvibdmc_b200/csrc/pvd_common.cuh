@@ -208,6 +208,26 @@ __device__ __forceinline__ long long warp_take_tile(unsigned *tickets, long long
     return tile < ntiles ? tile : -1;
 }
 
+// Tickets in batches: a ticket t covers tiles [t*batch, (t+1)*batch).  One counter serves about one atomic per
+// 2-2.5 ns whatever the grid, so kernels with light tiles take several tiles per ticket; tile ids are still
+// handed out in increasing order, which is all the look-back needs.
+struct TileFeed {
+    long long next = 0, end = 0;
+};
+__device__ __forceinline__ long long feed_next(TileFeed &f, unsigned *tickets, long long ntiles, int batch)
+{
+    if (f.next >= f.end) {
+        const int lane = threadIdx.x & 31;
+        unsigned t = 0;
+        if (lane == 0) t = atomicAdd(&tickets[0], 1u);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        f.next = (long long)t * batch;
+        f.end = f.next + batch < ntiles ? f.next + batch : ntiles;
+        if (f.next >= ntiles) { f.end = f.next; return -1; }
+    }
+    return f.next++;
+}
+
 // warp-wide inclusive scan of one int per lane
 __device__ __forceinline__ int warp_incl_scan(int c)
 {
@@ -231,9 +251,7 @@ __device__ __forceinline__ void publish_aggregate(unsigned long long *status, lo
     if ((threadIdx.x & 31) == 0)
         st_relaxed_u64(&status[tile], pack_status(step, tile == 0 ? PVD_ST_PREFIX : PVD_ST_AGG, (unsigned)tile_total));
 }
-// have_pre / pre: the caller already loaded this lane's status word of the first window (tile-1-lane) a while ago
-__device__ __forceinline__ long long resolve_prefix(unsigned long long *status, long long tile, long long step, int tile_total,
-                                                    bool have_pre = false, unsigned long long pre = 0ull)
+__device__ __forceinline__ long long resolve_prefix(unsigned long long *status, long long tile, long long step, int tile_total)
 {
     const int lane = threadIdx.x & 31;
     if (tile == 0) return 0;
@@ -245,10 +263,9 @@ __device__ __forceinline__ long long resolve_prefix(unsigned long long *status, 
         bool ok = true;
         while (true) {
             if (idx >= 0) {
-                w = have_pre ? pre : ld_relaxed_u64(&status[idx]);
+                w = ld_relaxed_u64(&status[idx]);
                 ok = status_valid(w, step);
             }
-            have_pre = false;
             if (__all_sync(0xffffffffu, ok)) break;
             __nanosleep(64);              // give the issue slots to the warps we are waiting for
         }

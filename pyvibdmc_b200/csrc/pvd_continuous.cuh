@@ -6,16 +6,22 @@
 // every halving).  Parallel-equivalent used here:
 //   1. k_cont_update   : weight update, exact sums over the surviving walkers, ascending kill list
 //                        (ticketed warp tiles + chained look-back scan, like the discrete step)
-//   2. k_cont_hist     : log-spaced histogram (64 bins / octave) of the updated weights
-//   3. k_cont_collect  : candidates = all walkers at or above the bin edge that holds the K-th
-//                        largest weight (K = number of kills), unordered append
-//   4. k_cont_assign   : one CTA sorts the candidates by (w desc, index asc).  If the K-th largest
-//                        weight is > half the largest, the K argmax steps are exactly "j-th largest
-//                        donates to j-th kill" and are applied in parallel; otherwise (halved
-//                        pieces re-enter the top: start-up transients, exact ties) the reference
-//                        loop is replayed exactly by one thread over the sorted candidates.
-//                        The optional upper threshold (argpartition of the smallest weights) is
-//                        replayed with block-wide argmin/argmax reductions.
+//                        and the log-spaced histogram (64 bins / octave) of the updated weights
+//   3. k_cont_prefix   : suffix sums of the histogram -> the bin that holds the K-th largest weight
+//                        (K = number of kills) and, per bin, where its members start in the
+//                        candidate array
+//      k_cont_collect  : candidates = all walkers at or above that bin, bucketed by bin
+//      k_cont_rank     : one CTA per bin sorts its bucket by (w desc, index asc) with a bitonic
+//                        network in shared memory and writes it to its place in the sorted
+//                        candidate array.  If some bin is too full for that (> 8192: many
+//                        identical weights), the candidates are appended unordered instead and
+//                        k_cont_assign sorts them with a single-CTA bitonic network in global memory.
+//   4. k_cont_assign   : if the K-th largest weight is > half the largest, the K argmax steps are
+//                        exactly "j-th largest donates to j-th kill" and are applied in parallel;
+//                        otherwise (halved pieces re-enter the top: start-up transients) the
+//                        reference loop is replayed exactly by one thread over the sorted
+//                        candidates.  The optional upper threshold (argpartition of the smallest
+//                        weights) is replayed with block-wide argmin/argmax reductions.
 //   5. k_cont_copy     : walkers (all per-walker arrays) are copied donor-root -> killed slot
 //   6. k_cont_finish   : min/max weight, Vref, log record (last CTA)
 #pragma once
@@ -23,6 +29,7 @@
 
 constexpr int PVD_HIST_BINS = 4096;            // 64 octaves x 64 bins
 constexpr int PVD_HIST_BASE = (1023 - 32) * 64;
+constexpr unsigned PVD_RANK_MAX_BIN = 8192;    // fuller bins fall back to the single-CTA sort
 
 struct ContCand { double w; int idx; int root; };
 struct ContWork {
@@ -31,6 +38,7 @@ struct ContWork {
     unsigned n_copy;        // (dst, src) pairs to copy
     unsigned n_upper;       // kills caused by the upper threshold
     int edge_bin;
+    int ranked;             // 1: candidates are bucketed by bin and ranked in parallel; 0: unordered + single-CTA sort
     unsigned done;
     double sub_w, sub_wv;   // weight removed by upper-threshold kills (corrects the exact sums)
     unsigned long long wmax_bits, wmin_bits;
@@ -42,11 +50,15 @@ struct ContArgs {
     int *kill_idx;
     int *copy_dst, *copy_src;
     ContCand *cand;
+    ContCand *sorted;           // candidates in (w desc, idx asc) order (ranked path)
     unsigned *hist;
+    unsigned *bin_start;        // [PVD_HIST_BINS] candidates in higher bins
+    unsigned *bin_fill;         // [PVD_HIST_BINS] running fill of each bin's bucket
     ContWork *work;
     long long cand_cap;
     double lower, upper;
     int has_upper;
+    int tile;                   // walkers per scan tile of the k_cont_update instance that ran
 };
 
 __device__ __forceinline__ int weight_bin(double w)
@@ -61,128 +73,225 @@ __device__ __forceinline__ double bin_lower_edge(int bin)
     return __longlong_as_double(((long long)bin + PVD_HIST_BASE) << 46);
 }
 
-// ---- 1. weight update + kill list + exact sums (energies from memory: a.vin)
-__global__ void __launch_bounds__(PVD_CTA) k_cont_update(const StepArgs a, const ContArgs ca)
+// ---- 1+2. weight update + kill list + exact sums + histogram of the updated weights (energies from memory: a.vin)
+// A tile is PVD_CONT_SUB sub-tiles of 32 walkers (lane l of sub-tile s owns walker tile*256 + s*32 + l): the
+// chained scan sustains only a few hundred tiles per microsecond, so light kernels use large tiles.  The kill
+// flags of a sub-tile are one ballot, which is also all the state the deferred scatter needs.
+// Where the energy of walker i comes from: memory (external / NN / importance-sampled energies)...
+struct ContFromMemory {
+    static constexpr int MIN_CTAS = 4;
+    static constexpr int SUB = 8;
+    __device__ static __forceinline__ double produce(const StepArgs &a, long long i, long long) { return a.vin[i]; }
+};
+// ...or the fused move + built-in potential (in place: continuous weighting never compacts)
+template <class POT, int RNG>
+struct ContFused {
+    static constexpr int MIN_CTAS = POT::MIN_CTAS;
+    static constexpr int SUB = POT::MIN_CTAS >= 4 ? 4 : 1;      // heavy potential: small tiles keep the warps balanced
+    __device__ static __forceinline__ double produce(const StepArgs &a, long long i, long long step)
+    {
+        double x[POT::NC], v;
+        ProduceFused<POT, RNG>::run(a, i, step, true, x, v);
+        double *po = a.xout + i;
+#pragma unroll
+        for (int c = 0; c < POT::NC; ++c) { *po = x[c]; po += a.cap; }
+        a.vout[i] = v;
+        return v;
+    }
+};
+
+template <class PROD>
+__global__ void __launch_bounds__(PVD_CTA, PROD::MIN_CTAS) k_cont_update(const StepArgs a, const ContArgs ca)
 {
+    constexpr int SUB = PROD::SUB, TILE = PVD_TILE * SUB;
+    __shared__ unsigned s_hist[PVD_HIST_BINS];
     if (!step_prologue(a)) return;
+    for (int b = threadIdx.x; b < PVD_HIST_BINS; b += PVD_CTA) s_hist[b] = 0;
+    __syncthreads();
     const DevState *sip = &a.st[a.parity];
     const long long n = sip->n, step = sip->step;
     const double vref = sip->vref, dt = sip->dt_eff;
-    const long long ntiles = (n + PVD_TILE - 1) / PVD_TILE;
+    const long long ntiles = (n + TILE - 1) / TILE;
     const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
     unsigned *tickets = step_tickets(a, a.parity);
     LaneAcc acc;
+    TileFeed feed;
     long long pend = -1;
-    int pend_total = 0, pend_excl = 0;
-    long long pend_i = 0;
-    bool pend_kill = false;
+    int pend_total = 0;
+    unsigned pend_mask[SUB];
     while (true) {
-        const long long tile = warp_take_tile(tickets, ntiles);
-        int kill = 0, incl = 0, total = 0;
-        long long i = 0;
+        const long long tile = feed_next(feed, tickets, ntiles, 1);
+        unsigned mask[SUB];
+        int total = 0;
         if (tile >= 0) {
-            i = tile * PVD_TILE + lane;
-            if (i < n) {
-                const double v = a.vin[i];
-                const double wn = __dmul_rn(ca.w[i], exp(__dmul_rn(-1.0 * (v - vref), dt)));      // :433
-                ca.w[i] = wn;
-                kill = (wn < ca.lower) ? 1 : 0;                                                   // :436
-                const Fx128 fv = fx_from_double(v);
-                acc.v = fx_add(acc.v, fv);
-                if (!kill) {
-                    acc.cw = fx_add(acc.cw, fx_from_double(wn));
-                    acc.cv = fx_add(acc.cv, fx_from_double(__dmul_rn(wn, v)));
+#pragma unroll
+            for (int s = 0; s < SUB; ++s) {
+                const long long i = tile * TILE + s * PVD_TILE + lane;
+                bool kill = false;
+                if (i < n) {
+                    const double v = PROD::produce(a, i, step);
+                    const double wn = __dmul_rn(ca.w[i], exp(__dmul_rn(-1.0 * (v - vref), dt)));      // :433
+                    ca.w[i] = wn;
+                    kill = wn < ca.lower;                                                             // :436
+                    atomicAdd(&s_hist[weight_bin(wn)], 1u);
+                    const Fx128 fv = fx_from_double(v);
+                    acc.v = fx_add(acc.v, fv);
+                    if (!kill) {
+                        acc.cw = fx_add(acc.cw, fx_from_double(wn));
+                        acc.cv = fx_add(acc.cv, fx_from_double(__dmul_rn(wn, v)));
+                    }
+                    acc.vmin = fmin(acc.vmin, v); acc.vmax = fmax(acc.vmax, v);
+                    acc.n_in += 1.0; acc.n_acc += 1.0;
+                    acc.births += kill ? 1.0 : 0.0;
                 }
-                acc.vmin = fmin(acc.vmin, v); acc.vmax = fmax(acc.vmax, v);
-                acc.n_in += 1.0; acc.n_acc += 1.0;
-                acc.births += (double)kill;
+                mask[s] = __ballot_sync(0xffffffffu, kill);
+                total += __popc(mask[s]);
             }
-            incl = warp_incl_scan(kill);
-            total = __shfl_sync(0xffffffffu, incl, 31);
             publish_aggregate(a.status, tile, step, total);
         }
         if (pend >= 0) {
-            const long long o = resolve_prefix(a.status, pend, step, pend_total) + pend_excl;
-            if (pend_kill) ca.kill_idx[o] = (int)pend_i;
+            long long o = resolve_prefix(a.status, pend, step, pend_total);
+#pragma unroll
+            for (int s = 0; s < SUB; ++s) {
+                const unsigned m = pend_mask[s];
+                if ((m >> lane) & 1u) ca.kill_idx[o + __popc(m & lt_mask)] = (int)(pend * TILE + s * PVD_TILE + lane);
+                o += __popc(m);
+            }
         }
         if (tile < 0) break;
-        pend = tile; pend_total = total; pend_excl = incl - kill; pend_i = i; pend_kill = kill != 0;
+        pend = tile; pend_total = total;
+#pragma unroll
+        for (int s = 0; s < SUB; ++s) pend_mask[s] = mask[s];
     }
-    // population does not change; the kill count is the inclusive prefix of the last tile
-    cta_finish_step(a, acc, ntiles, true, n, true);      // Vref is produced by k_cont_finish, after branching
-}
-
-// ---- 2. histogram of the updated weights (only when something has to be branched)
-__global__ void __launch_bounds__(PVD_CTA) k_cont_hist(const StepArgs a, const ContArgs ca)
-{
-    __shared__ unsigned s_hist[PVD_HIST_BINS];
-    const DevState *so = &a.st[a.parity];          // continuous weighting: population and flags do not change within a step
-    const long long n = so->n;
-    const long long ntiles = (n + PVD_TILE - 1) / PVD_TILE;
-    const unsigned nk = (unsigned)(ld_relaxed_u64(&a.status[ntiles - 1]) & 0xffffffffull);
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        ca.work->n_kill = nk; ca.work->n_cand = 0; ca.work->n_copy = 0; ca.work->n_upper = 0; ca.work->done = 0;
-        ca.work->sub_w = 0.0; ca.work->sub_wv = 0.0;
-        ca.work->wmax_bits = 0ull; ca.work->wmin_bits = 0x7FF0000000000000ull;
-    }
-    if (so->err || nk == 0) return;
-    for (int b = threadIdx.x; b < PVD_HIST_BINS; b += PVD_CTA) s_hist[b] = 0;
-    __syncthreads();
-    for (long long i = blockIdx.x * (long long)PVD_CTA + threadIdx.x; i < n; i += (long long)gridDim.x * PVD_CTA)
-        atomicAdd(&s_hist[weight_bin(ca.w[i])], 1u);
     __syncthreads();
     for (int b = threadIdx.x; b < PVD_HIST_BINS; b += PVD_CTA)
         if (s_hist[b]) atomicAdd(&ca.hist[b], s_hist[b]);
-}
-
-// ---- 3. candidates: everything at or above the bin that contains the K-th largest weight
-__global__ void __launch_bounds__(PVD_CTA) k_cont_collect(const StepArgs a, const ContArgs ca)
-{
-    __shared__ int s_edge;
-    const DevState *so = &a.st[a.parity];
-    const unsigned nk = ca.work->n_kill;
-    if (so->err || nk == 0) return;
-    const long long n = so->n;
-    if (threadIdx.x < 32) {
-        // suffix count from the top bin downwards; 128 bins per lane
-        const int lane = threadIdx.x;
-        unsigned mine = 0;
-        const int hi = PVD_HIST_BINS - 1 - lane * (PVD_HIST_BINS / 32);
-        for (int k = 0; k < PVD_HIST_BINS / 32; ++k) mine += ca.hist[hi - k];
-        unsigned above = mine;                          // inclusive suffix over lanes 0..lane
-        for (int off = 1; off < 32; off <<= 1) {
-            const unsigned y = __shfl_up_sync(0xffffffffu, above, off);
-            if (lane >= off) above += y;
-        }
-        const unsigned before = above - mine;
-        int edge = -1;
-        if (before < nk && above >= nk) {
-            unsigned run = before;
-            for (int k = 0; k < PVD_HIST_BINS / 32; ++k) {
-                run += ca.hist[hi - k];
-                if (run >= nk) { edge = hi - k; break; }
-            }
-        }
-        const unsigned found = __ballot_sync(0xffffffffu, edge >= 0);
-        if (!found) { if (lane == 0) s_edge = 0; }     // fewer than K positive weights: take everything
-        else if (edge >= 0) s_edge = edge;
-    }
-    __syncthreads();
-    const int edge_bin = s_edge;
-    if (blockIdx.x == 0 && threadIdx.x == 0) ca.work->edge_bin = edge_bin;
-    for (long long i = blockIdx.x * (long long)PVD_CTA + threadIdx.x; i < n; i += (long long)gridDim.x * PVD_CTA) {
-        const double w = ca.w[i];
-        if (weight_bin(w) >= edge_bin) {
-            const unsigned slot = atomicAdd(&ca.work->n_cand, 1u);
-            if ((long long)slot < ca.cand_cap) ca.cand[slot] = ContCand{w, (int)i, (int)i};
-        }
-    }
+    // population does not change; the kill count is the inclusive prefix of the last tile
+    cta_finish_step(a, acc, ntiles, true, n, true);      // Vref is produced by k_cont_finish, after branching
 }
 
 // (w desc, idx asc) ordering
 __device__ __forceinline__ bool cand_before(const ContCand &p, const ContCand &q)
 {
     return p.w > q.w || (p.w == q.w && p.idx < q.idx);
+}
+
+// ---- 3a. suffix sums of the histogram (one CTA, one bin per 4 threads' worth of work)
+__global__ void __launch_bounds__(1024) k_cont_prefix(const StepArgs a, const ContArgs ca)
+{
+    __shared__ unsigned s_warp[32];
+    __shared__ int s_edge;
+    __shared__ unsigned s_maxbin;
+    const DevState *so = &a.st[a.parity];          // continuous weighting: population and flags do not change within a step
+    const long long ntiles = (so->n + ca.tile - 1) / ca.tile;
+    const unsigned nk = so->err ? 0u : (unsigned)(ld_relaxed_u64(&a.status[ntiles - 1]) & 0xffffffffull);
+    if (threadIdx.x == 0) {
+        ca.work->n_kill = nk; ca.work->n_cand = 0; ca.work->n_copy = 0; ca.work->n_upper = 0; ca.work->done = 0;
+        ca.work->sub_w = 0.0; ca.work->sub_wv = 0.0; ca.work->ranked = 0;
+        ca.work->wmax_bits = 0ull; ca.work->wmin_bits = 0x7FF0000000000000ull;
+    }
+    if (so->err || nk == 0) return;
+    __syncthreads();
+    constexpr int PER = PVD_HIST_BINS / 1024;                 // 4 consecutive bins per thread, highest bins first
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    if (t == 0) { s_edge = -1; s_maxbin = 0u; }
+    unsigned h[PER], mine = 0;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) { h[k] = ca.hist[PVD_HIST_BINS - 1 - (t * PER + k)]; mine += h[k]; }
+    unsigned incl = mine;
+    for (int off = 1; off < 32; off <<= 1) {
+        const unsigned y = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += y;
+    }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        unsigned v = s_warp[lane], x = v;
+        for (int off = 1; off < 32; off <<= 1) {
+            const unsigned y = __shfl_up_sync(0xffffffffu, x, off);
+            if (lane >= off) x += y;
+        }
+        s_warp[lane] = x - v;                                 // exclusive prefix over warps
+    }
+    __syncthreads();
+    unsigned above = s_warp[wid] + incl - mine;               // members of strictly higher bins than this thread's first bin
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        const int bin = PVD_HIST_BINS - 1 - (t * PER + k);
+        ca.bin_start[bin] = above;
+        if (above < nk && above + h[k] >= nk) s_edge = bin;   // exactly one bin satisfies this when enough weights are positive
+        above += h[k];
+    }
+    __syncthreads();
+    const int edge = s_edge < 0 ? 0 : s_edge;                 // fewer than K positive weights: take everything
+    unsigned mb = 0;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        const int bin = PVD_HIST_BINS - 1 - (t * PER + k);
+        if (bin >= edge) mb = max(mb, h[k]);
+    }
+    for (int off = 16; off > 0; off >>= 1) mb = max(mb, __shfl_xor_sync(0xffffffffu, mb, off));
+    if (lane == 0 && mb) atomicMax(&s_maxbin, mb);
+    __syncthreads();
+    if (t == 0) {
+        ca.work->edge_bin = edge;
+        const bool ranked = s_maxbin <= PVD_RANK_MAX_BIN;
+        ca.work->ranked = ranked ? 1 : 0;
+        if (ranked) ca.work->n_cand = ca.bin_start[edge] + ca.hist[edge];
+    }
+}
+
+// ---- 3b. candidates: everything at or above the bin that contains the K-th largest weight
+__global__ void __launch_bounds__(PVD_CTA) k_cont_collect(const StepArgs a, const ContArgs ca)
+{
+    const DevState *so = &a.st[a.parity];
+    const unsigned nk = ca.work->n_kill;
+    if (so->err || nk == 0) return;
+    const long long n = so->n;
+    const int edge_bin = ca.work->edge_bin;
+    const bool ranked = ca.work->ranked != 0;
+    for (long long i = blockIdx.x * (long long)PVD_CTA + threadIdx.x; i < n; i += (long long)gridDim.x * PVD_CTA) {
+        const double w = ca.w[i];
+        const int bin = weight_bin(w);
+        if (bin >= edge_bin) {
+            const unsigned slot = ranked ? ca.bin_start[bin] + atomicAdd(&ca.bin_fill[bin], 1u) : atomicAdd(&ca.work->n_cand, 1u);
+            if ((long long)slot < ca.cand_cap) ca.cand[slot] = ContCand{w, (int)i, (int)i};
+        }
+    }
+}
+
+// ---- 3c. sort inside each bin (one CTA per bin, bitonic network in shared memory) -> sorted candidates
+__global__ void __launch_bounds__(1024) k_cont_rank(const StepArgs a, const ContArgs ca)
+{
+    extern __shared__ __align__(16) unsigned char s_rank_raw[];
+    ContCand *s_c = reinterpret_cast<ContCand *>(s_rank_raw);
+    const DevState *so = &a.st[a.parity];
+    if (so->err || ca.work->n_kill == 0 || !ca.work->ranked) return;
+    const int bin = PVD_HIST_BINS - 1 - (int)blockIdx.x;
+    if (bin < ca.work->edge_bin) return;
+    unsigned cnt = ca.hist[bin];
+    const unsigned start = ca.bin_start[bin];
+    if (cnt == 0 || (long long)start >= ca.cand_cap) return;
+    if ((long long)start + cnt > ca.cand_cap) cnt = (unsigned)(ca.cand_cap - start);
+    unsigned P = 1;
+    while (P < cnt) P <<= 1;
+    for (unsigned t = threadIdx.x; t < P; t += blockDim.x) s_c[t] = t < cnt ? ca.cand[start + t] : ContCand{-INFINITY, 0x7fffffff, -1};
+    __syncthreads();
+    for (unsigned k = 2; k <= P; k <<= 1) {
+        for (unsigned j = k >> 1; j > 0; j >>= 1) {
+            for (unsigned t = threadIdx.x; t < P; t += blockDim.x) {
+                const unsigned l = t ^ j;
+                if (l > t) {
+                    const ContCand x = s_c[t], y = s_c[l];
+                    const bool up = (t & k) == 0;
+                    if (up ? cand_before(y, x) : cand_before(x, y)) { s_c[t] = y; s_c[l] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (unsigned t = threadIdx.x; t < cnt; t += blockDim.x) ca.sorted[start + t] = s_c[t];
 }
 
 // block-wide argmax (first index on ties) / argmin over w[0..n) with a skip mask
@@ -231,31 +340,35 @@ __global__ void __launch_bounds__(1024) k_cont_assign(const StepArgs a, const Co
     if (K > 0) {
         long long C = ca.work->n_cand;
         if (C > ca.cand_cap) C = ca.cand_cap;
-        // bitonic sort of the candidates, padded to a power of two with -inf
-        long long P = 1;
-        while (P < C) P <<= 1;
-        for (long long t = C + threadIdx.x; t < P; t += blockDim.x) ca.cand[t] = ContCand{-INFINITY, 0x7fffffff, -1};
-        __syncthreads();
-        for (long long k = 2; k <= P; k <<= 1) {
-            for (long long j = k >> 1; j > 0; j >>= 1) {
-                for (long long t = threadIdx.x; t < P; t += blockDim.x) {
-                    const long long l = t ^ j;
-                    if (l > t) {
-                        const ContCand x = ca.cand[t], y = ca.cand[l];
-                        const bool up = (t & k) == 0;
-                        if (up ? cand_before(y, x) : cand_before(x, y)) { ca.cand[t] = y; ca.cand[l] = x; }
+        const bool ranked = ca.work->ranked != 0;
+        const ContCand *srt = ranked ? ca.sorted : ca.cand;
+        if (!ranked) {
+            // over-full bin (many identical weights): bitonic sort of the unordered candidates, padded to a power of two with -inf
+            long long P = 1;
+            while (P < C) P <<= 1;
+            for (long long t = C + threadIdx.x; t < P; t += blockDim.x) ca.cand[t] = ContCand{-INFINITY, 0x7fffffff, -1};
+            __syncthreads();
+            for (long long k = 2; k <= P; k <<= 1) {
+                for (long long j = k >> 1; j > 0; j >>= 1) {
+                    for (long long t = threadIdx.x; t < P; t += blockDim.x) {
+                        const long long l = t ^ j;
+                        if (l > t) {
+                            const ContCand x = ca.cand[t], y = ca.cand[l];
+                            const bool up = (t & k) == 0;
+                            if (up ? cand_before(y, x) : cand_before(x, y)) { ca.cand[t] = y; ca.cand[l] = x; }
+                        }
                     }
+                    __syncthreads();
                 }
-                __syncthreads();
             }
         }
         // fast path: the K largest weights are all above half of the largest -> no halved piece is ever a donor
-        if (threadIdx.x == 0) s_flag = (C >= K && ca.cand[K - 1].w > 0.5 * ca.cand[0].w) ? 1 : 0;
+        if (threadIdx.x == 0) s_flag = (C >= K && srt[K - 1].w > 0.5 * srt[0].w) ? 1 : 0;
         __syncthreads();
         if (s_flag) {
             for (int j = threadIdx.x; j < K; j += blockDim.x) {
-                const int d = ca.cand[j].idx, k = ca.kill_idx[j];
-                const double h = ca.cand[j].w / 2.0;
+                const int d = srt[j].idx, k = ca.kill_idx[j];
+                const double h = srt[j].w / 2.0;
                 ca.w[d] = h;
                 ca.w[k] = h;
                 ca.copy_dst[j] = k;
@@ -291,9 +404,9 @@ __global__ void __launch_bounds__(1024) k_cont_assign(const StepArgs a, const Co
                     }
                     if (!have_a) use_a = false;
                     else if (best_b < 0) use_a = true;
-                    else use_a = ca.cand[ia].w > mb || (ca.cand[ia].w == mb && ca.cand[ia].idx < queue[best_b].idx);
+                    else use_a = srt[ia].w > mb || (srt[ia].w == mb && srt[ia].idx < queue[best_b].idx);
                     ContCand top;
-                    if (use_a) top = ca.cand[ia++];
+                    if (use_a) top = srt[ia++];
                     else { top = queue[best_b]; queue[best_b] = queue[ib]; ++ib; }
                     const double h = top.w / 2.0;
                     ca.w[top.idx] = h;
@@ -349,8 +462,8 @@ __global__ void __launch_bounds__(1024) k_cont_assign(const StepArgs a, const Co
         ncopy += n_above;
     }
     if (threadIdx.x == 0) ca.work->n_copy = (unsigned)ncopy;
-    // reset the histogram for the next step
-    for (int b = threadIdx.x; b < PVD_HIST_BINS; b += blockDim.x) ca.hist[b] = 0;
+    // reset the histogram and the bucket fills for the next step
+    for (int b = threadIdx.x; b < PVD_HIST_BINS; b += blockDim.x) { ca.hist[b] = 0; ca.bin_fill[b] = 0; }
 }
 
 // ---- 5. copy donor -> killed for every per-walker array (in place: donors are never kill targets)

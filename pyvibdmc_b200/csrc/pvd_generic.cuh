@@ -133,36 +133,20 @@ __global__ void k_displace_soa(double *__restrict__ x, const DevState *st, int p
     }
 }
 
-// move + potential in place (continuous weighting: no compaction, so nothing is gained by fusing the
-// weight update into this kernel; it streams coords once and writes coords + V)
-template <class POT, int RNG>
-__global__ void __launch_bounds__(PVD_CTA) k_move_pes(const StepArgs a, double *x, double *v)
-{
-    constexpr int NC = POT::NC;
-    const DevState *sip = &a.st[a.parity];
-    if (sip->err) return;
-    const long long n = sip->n, step = sip->step;
-    for (long long i = blockIdx.x * (long long)PVD_CTA + threadIdx.x; i < n; i += (long long)gridDim.x * PVD_CTA) {
-        double xx[NC], vv;
-        StepArgs const &ar = a;
-        ProduceFused<POT, RNG>::run(ar, i, step, true, xx, vv);
-#pragma unroll
-        for (int c = 0; c < NC; ++c) x[c * a.cap + i] = xx[c];
-        v[i] = vv;
-    }
-}
-
 // ---------------------------------------------------------------- branch-only discrete step
 // Same counting / chained scan / compaction / finalisation as k_step_discrete, but the energies
 // come from memory (a.vin) and every per-walker array is copied memory->memory with a run-time
 // number of components.  dt comes from the device state (importance sampling scales it).
-__global__ void __launch_bounds__(PVD_CTA) k_branch_discrete(const StepArgs a)
+// A tile is PVD_BR_SUB sub-tiles of 32 walkers (lane l of sub-tile s owns walker tile*128 + s*32 + l); see k_cont_update.
+constexpr int PVD_BR_SUB = 4;
+constexpr int PVD_BR_TILE = PVD_TILE * PVD_BR_SUB;
+__global__ void __launch_bounds__(PVD_CTA, 3) k_branch_discrete(const StepArgs a)
 {
     if (!step_prologue(a)) return;
     const DevState *sip = &a.st[a.parity];
     const long long n = sip->n, step = sip->step;
     const double vref = sip->vref, dt = sip->dt_eff;
-    const long long ntiles = (n + PVD_TILE - 1) / PVD_TILE;
+    const long long ntiles = (n + PVD_BR_TILE - 1) / PVD_BR_TILE;
     const bool dw = sip->dw_active != 0;
     const double n0 = (double)a.n0;
     const double w_limit = (n0 + n0 * 0.5) + 1.0;
@@ -170,54 +154,82 @@ __global__ void __launch_bounds__(PVD_CTA) k_branch_discrete(const StepArgs a)
     const bool branch_now = branch_this_step(a.do_branch, step);
     unsigned *tickets = step_tickets(a, a.parity);
     LaneAcc acc;
+    TileFeed feed;
+    // the previous tile of this warp, scattered one iteration late (see k_step_discrete)
+    long long pend = -1;
+    int pend_total = 0;
+    int pend_cnt[PVD_BR_SUB], pend_excl[PVD_BR_SUB];
 
     while (true) {
-        const long long tile = warp_take_tile(tickets, ntiles);
-        if (tile < 0) break;
-        const long long i = tile * PVD_TILE + lane;
-        const bool active = i < n;
-        const double v = active ? a.vin[i] : 0.0;
-        int cnt = 0;
-        bool bad = false;
-        if (active) {
-            if (branch_now) {
-                double u;
-                if (a.inj_u) u = a.inj_u[i];
-                else { const uint4 r = pvd_draw(a.seed, i, step, PVD_STREAM_BRANCH, 0u); u = u53(r.x, r.y); }
-                cnt = discrete_count(v, vref, dt, u, w_limit, bad);
-            } else cnt = 1;
-            if (a.counts_out) a.counts_out[i] = cnt;
+        const long long tile = feed_next(feed, tickets, ntiles, 1);
+        int cnt[PVD_BR_SUB], excl[PVD_BR_SUB];
+        int tile_total = 0;
+        if (tile >= 0) {
+            bool bad = false;
+#pragma unroll
+            for (int s = 0; s < PVD_BR_SUB; ++s) {
+                const long long i = tile * PVD_BR_TILE + s * PVD_TILE + lane;
+                int c = 0;
+                if (i < n) {
+                    const double v = a.vin[i];
+                    if (branch_now) {
+                        double u;
+                        bool b1 = false;
+                        if (a.inj_u) u = a.inj_u[i];
+                        else { const uint4 r = pvd_draw(a.seed, i, step, PVD_STREAM_BRANCH, 0u); u = u53(r.x, r.y); }
+                        c = discrete_count(v, vref, dt, u, w_limit, b1);
+                        bad |= b1;
+                    } else c = 1;
+                    if (a.counts_out) a.counts_out[i] = c;
+                    const Fx128 fv = fx_from_double(v);
+                    acc.v = fx_add(acc.v, fv);
+                    if (c > 0) acc.cv = fx_add(acc.cv, c == 1 ? fv : fx_mul_small(fv, c));
+                    acc.c += (double)c;
+                    acc.vmin = fmin(acc.vmin, v); acc.vmax = fmax(acc.vmax, v);
+                    acc.births += (double)(c > 1 ? c - 1 : 0); acc.deaths += (c == 0) ? 1.0 : 0.0;
+                    acc.n_in += 1.0; acc.n_acc += 1.0;
+                }
+                const int incl = warp_incl_scan(c);
+                cnt[s] = c;
+                excl[s] = tile_total + incl - c;
+                tile_total += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            if (bad) atomicOr(a.err_accum, PVD_ERR_WEIGHT);
+            publish_aggregate(a.status, tile, step, tile_total);
         }
-        if (bad) atomicOr(a.err_accum, PVD_ERR_WEIGHT);
-
-        const int incl = warp_incl_scan(cnt);
-        const int tile_total = __shfl_sync(0xffffffffu, incl, 31);
-        const long long o = warp_lookback(a.status, tile, step, tile_total) + (incl - cnt);
-        if (cnt > 0) {
-            if (o + cnt > a.cap) atomicOr(a.err_accum, PVD_ERR_CAPACITY);
-            else {
-                for (int k = 0; k < cnt; ++k) {
-                    for (int c = 0; c < a.nc; ++c) a.xout[c * a.cap + o + k] = a.xin[c * a.cap + i];
-                    if (a.vout) a.vout[o + k] = v;
-                    if (dw) a.who_out[o + k] = a.who_in[i];
-                    if (a.idx_out) a.idx_out[o + k] = i;
+        if (pend >= 0) {
+            const long long base = resolve_prefix(a.status, pend, step, pend_total);
+#pragma unroll
+            for (int s = 0; s < PVD_BR_SUB; ++s) {
+                const int pc = pend_cnt[s];
+                if (pc <= 0) continue;
+                const long long pi_ = pend * PVD_BR_TILE + s * PVD_TILE + lane;
+                const long long o = base + pend_excl[s];
+                if (o + pc > a.cap) { atomicOr(a.err_accum, PVD_ERR_CAPACITY); continue; }
+#pragma unroll 1
+                for (int k = 0; k < pc; ++k) {
+                    const double *pi = a.xin + pi_;
+                    double *po = a.xout + (o + k);
+#pragma unroll 6
+                    for (int c = 0; c < a.nc; ++c) { *po = __ldcs(pi); pi += a.cap; po += a.cap; }
+                    if (a.vout) a.vout[o + k] = a.vin[pi_];
+                    if (dw) a.who_out[o + k] = a.who_in[pi_];
+                    if (a.idx_out) a.idx_out[o + k] = pi_;
                     if (a.fin) {
-                        for (int c = 0; c < a.nc; ++c) a.fout[c * a.cap + o + k] = a.fin[c * a.cap + i];
-                        a.psout[o + k] = a.psin[i];
-                        a.lkout[o + k] = a.lkin[i];
+                        const double *fi = a.fin + pi_;
+                        double *fo = a.fout + (o + k);
+#pragma unroll 6
+                        for (int c = 0; c < a.nc; ++c) { *fo = __ldcs(fi); fi += a.cap; fo += a.cap; }
+                        a.psout[o + k] = a.psin[pi_];
+                        a.lkout[o + k] = a.lkin[pi_];
                     }
                 }
             }
         }
-        if (active) {
-            const Fx128 fv = fx_from_double(v);
-            acc.v = fx_add(acc.v, fv);
-            if (cnt > 0) acc.cv = fx_add(acc.cv, cnt == 1 ? fv : fx_mul_small(fv, cnt));
-            acc.c += (double)cnt;
-            acc.vmin = fmin(acc.vmin, v); acc.vmax = fmax(acc.vmax, v);
-            acc.births += (double)(cnt > 1 ? cnt - 1 : 0); acc.deaths += (cnt == 0) ? 1.0 : 0.0;
-            acc.n_in += 1.0; acc.n_acc += 1.0;
-        }
+        if (tile < 0) break;
+        pend = tile; pend_total = tile_total;
+#pragma unroll
+        for (int s = 0; s < PVD_BR_SUB; ++s) { pend_cnt[s] = cnt[s]; pend_excl[s] = excl[s]; }
     }
     cta_finish_step(a, acc, ntiles, false, -1);
 }

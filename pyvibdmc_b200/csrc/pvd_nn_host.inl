@@ -16,7 +16,7 @@ static int nn_enqueue_discrete_step(pvd_sim *s, StepArgs &a)
     PVD_CHECK_LAUNCH();
     if (int rc = nn_launch(s->stream, x, 1, s->cap, s->st.as<DevState>(), s->parity, 0, s->cap, s->v[s->cur].as<double>(), s->nn_w))
         return rc;
-    k_branch_discrete<<<g, PVD_CTA, 0, s->stream>>>(a);
+    k_branch_discrete<<<s->grid_light, PVD_CTA, 0, s->stream>>>(a);
     return PVD_OK;
 }
 

@@ -150,12 +150,14 @@ struct PotParamsDev {
 
 struct PotH2O {
     static constexpr int NC = 9;
+    static constexpr int MIN_CTAS = 2;       // resident CTAs per SM the fused step kernel is compiled for (register budget)
     __device__ static __forceinline__ double eval(const double (&x)[9], const PotParamsDev &) { return ps_h2o_energy(x); }
 };
 // harmonicOscillator1D.py:13-17 : ((0.5*m)*w^2) * (x*x), summed over components
 template <int NCOMP>
 struct PotHarm {
     static constexpr int NC = NCOMP;
+    static constexpr int MIN_CTAS = 4;       // cheap potential: the step is latency-bound, so run more warps per SM
     __device__ static __forceinline__ double eval(const double (&x)[NCOMP], const PotParamsDev &p)
     {
         double v = __dmul_rn(p.k[0], __dmul_rn(x[0], x[0]));      // no FMA contraction: bit-exact vs NumPy
@@ -167,6 +169,7 @@ struct PotHarm {
 // morse_osc_1d.py:4-12
 struct PotMorse {
     static constexpr int NC = 1;
+    static constexpr int MIN_CTAS = 4;
     __device__ static __forceinline__ double eval(const double (&x)[1], const PotParamsDev &p)
     {
         const double t = 1.0 - exp(-p.k[1] * x[0]);

@@ -49,6 +49,7 @@ struct StepArgs {
     unsigned long long seed;
     int parity, do_branch, world, rank, ndim, nc;
     int flip;                   // 1 when this step writes the other ping-pong buffer
+    int ticket_batch;           // consecutive tiles a warp takes per ticket (1 for heavy tiles, more for light ones)
     double sigma[PVD_MAX_ATOMS];
     double sigc[PVD_MAX_COMP];  // sigma expanded per component (sigc[c] = sigma[c / ndim])
     PotParamsDev pot;
@@ -293,41 +294,16 @@ struct TileStash {
     int cnt[32], excl[32], who[32];
 };
 
-// cp.async (LDGSTS) helpers: 8-byte global -> shared copies that need no destination registers
-__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc)
-{
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
-// With only 16 warps per SM (128 registers per thread) every exposed memory round trip costs issue
-// slots, so the three per-tile round trips are taken off the critical path:
-//   * tickets are drawn two tiles ahead (the atomic returns while a tile is being computed),
-//   * the next tile's coordinates are fetched with cp.async into shared memory while the current
-//     tile is computed (no registers held across the computation),
-//   * the status words of the previous tile's look-back window are requested between the
-//     displacement and the potential and consumed after it.
-#ifndef PVD_RNG_ROLLED
-#define PVD_RNG_ROLLED 0
-#endif
-#ifndef PVD_PF_X
-#define PVD_PF_X 0
-#endif
-#ifndef PVD_PF_TICKET
-#define PVD_PF_TICKET 0
-#endif
-#ifndef PVD_PF_STATUS
-#define PVD_PF_STATUS 0
-#endif
+// Experiments that did NOT help on this kernel (B200, 1e6 walkers, 2 CTAs/SM; kept out of the code): drawing
+// tickets two tiles ahead (+5 us), cp.async prefetch of the next tile's coordinates into shared memory (+8 us),
+// requesting the look-back status words before the potential (+3 us), one 256-walker tile per CTA with
+// block-level scans (+33 us), 3 or 4 CTAs/SM with spills (+2..4 us), two passes over a 3-pair Box-Muller body
+// to shrink the loop below the 32 KB instruction cache (+3.5 us).  What did help: fewer executed instructions.
 template <class POT, int RNG>
-__global__ void __launch_bounds__(PVD_CTA, 2) k_step_discrete(const StepArgs a)
+__global__ void __launch_bounds__(PVD_CTA, POT::MIN_CTAS) k_step_discrete(const StepArgs a)
 {
     constexpr int NC = POT::NC;
-    constexpr bool PF_X = PVD_PF_X != 0, PF_T = PVD_PF_TICKET != 0, PF_S = PVD_PF_STATUS != 0;
     __shared__ TileStash<NC> s_stash[PVD_WARPS];
-    __shared__ double s_pref[PF_X ? PVD_WARPS : 1][NC][32];      // landing zone of the coordinate prefetch
     if (!step_prologue(a)) return;
     const DevState *sip = &a.st[a.parity];
     const long long n = sip->n, step = sip->step;
@@ -340,88 +316,35 @@ __global__ void __launch_bounds__(PVD_CTA, 2) k_step_discrete(const StepArgs a)
     const bool branch_now = branch_this_step(a.do_branch, step);
     unsigned *tickets = step_tickets(a, a.parity);
     TileStash<NC> &stash = s_stash[threadIdx.x >> 5];
-    double (&pref)[NC][32] = s_pref[PF_X ? (threadIdx.x >> 5) : 0];
     LaneAcc acc;
+    TileFeed feed;
     long long pending = -1;
     int pending_total = 0;
 
-    long long tile = warp_take_tile(tickets, ntiles);
-    long long next = (PF_T || PF_X) ? warp_take_tile(tickets, ntiles) : -1;
-    if constexpr (PF_X) {
-        if (tile >= 0 && tile * PVD_TILE + lane < n) {
-#pragma unroll
-            for (int c = 0; c < NC; ++c) cp_async8(&pref[c][lane], &a.xin[c * a.cap + tile * PVD_TILE + lane]);
-        }
-        cp_async_commit();
-    }
-
     while (true) {
+        const long long tile = feed_next(feed, tickets, ntiles, a.ticket_batch);
         double x[NC], v = 0.0;
         int cnt = 0, incl = 0, tile_total = 0, who = 0;
-        unsigned ticket_raw = 0u;
-        unsigned long long pre_status = 0ull;
-        bool have_pre = false;
         if (tile >= 0) {
             const long long i = tile * PVD_TILE + lane;
             const bool active = i < n;
-            if constexpr (PF_X) {
-                cp_async_wait_all();
+            const double *px = a.xin + i;
 #pragma unroll
-                for (int c = 0; c < NC; ++c) x[c] = active ? pref[c][lane] : 1.0 + c;     // idle lanes: harmless geometry
-                if (next >= 0 && next * PVD_TILE + lane < n) {
-#pragma unroll
-                    for (int c = 0; c < NC; ++c) cp_async8(&pref[c][lane], &a.xin[c * a.cap + next * PVD_TILE + lane]);
-                }
-                cp_async_commit();
-            } else {
-                const double *px = a.xin + i;
-#pragma unroll
-                for (int c = 0; c < NC; ++c) {
-                    x[c] = 1.0 + c;                                                   // idle lanes: harmless geometry
-                    if (active) x[c] = __ldcs(px);
-                    px += a.cap;
-                }
-            }
-            if constexpr (PF_T || PF_X) {
-                if (lane == 0) ticket_raw = atomicAdd(&tickets[0], 1u);                // tile after next; consumed at the loop end
+            for (int c = 0; c < NC; ++c) {
+                x[c] = 1.0 + c;                                                   // idle lanes: harmless geometry
+                if (active) x[c] = __ldcs(px);
+                px += a.cap;
             }
             if (active) {
                 if (a.inj_disp) {
 #pragma unroll
                     for (int c = 0; c < NC; ++c) x[c] = x[c] + a.inj_disp[c * a.cap + i];
-                } else if constexpr (PVD_RNG_ROLLED != 0 && NC == 9 && RNG == PVD_RNG_FP64) {
-                    // same stream as walker_normals (pair k -> components 2k, 2k+1), generated as two passes over
-                    // a 3-pair body to keep the hot loop inside the instruction cache (the 6th pair is discarded)
-#pragma unroll 1
-                    for (int h = 0; h < 2; ++h) {
-                        uint4 r[3];
-                        double z0[3], z1[3];
-#pragma unroll
-                        for (int k = 0; k < 3; ++k) r[k] = pvd_draw(a.seed, i, step, PVD_STREAM_DISP, (unsigned)(3 * h + k));
-                        normal_pairs_fp64<3>(r, z0, z1);
-                        if (h == 0) {
-#pragma unroll
-                            for (int k = 0; k < 3; ++k) {
-                                x[2 * k] = __dadd_rn(x[2 * k], __dmul_rn(a.sigc[2 * k], z0[k]));
-                                x[2 * k + 1] = __dadd_rn(x[2 * k + 1], __dmul_rn(a.sigc[2 * k + 1], z1[k]));
-                            }
-                        } else {
-                            x[6] = __dadd_rn(x[6], __dmul_rn(a.sigc[6], z0[0]));
-                            x[7] = __dadd_rn(x[7], __dmul_rn(a.sigc[7], z1[0]));
-                            x[8] = __dadd_rn(x[8], __dmul_rn(a.sigc[8], z0[1]));
-                        }
-                    }
                 } else {
                     double z[NC];
                     walker_normals<NC, RNG>(a.seed, i, step, z);
 #pragma unroll
                     for (int c = 0; c < NC; ++c) x[c] = __dadd_rn(x[c], __dmul_rn(a.sigc[c], z[c]));
                 }
-            }
-            if (PF_S && pending > 0) {
-                const long long idx = pending - 1 - lane;
-                pre_status = idx >= 0 ? ld_relaxed_u64(&a.status[idx]) : pack_status(step, PVD_ST_PREFIX, 0u);
-                have_pre = true;
             }
             v = active ? POT::eval(x, a.pot) : 0.0;
             bool bad = false;
@@ -448,7 +371,7 @@ __global__ void __launch_bounds__(PVD_CTA, 2) k_step_discrete(const StepArgs a)
         }
         if (pending >= 0) {
             // scatter the previous tile: its predecessors have had a whole tile's worth of time to publish
-            const long long o = resolve_prefix(a.status, pending, step, pending_total, have_pre, pre_status) + stash.excl[lane];
+            const long long o = resolve_prefix(a.status, pending, step, pending_total) + stash.excl[lane];
             const int pc = stash.cnt[lane];
             if (pc > 0) {
                 if (o + pc > a.cap) atomicOr(a.err_accum, PVD_ERR_CAPACITY);
@@ -476,11 +399,6 @@ __global__ void __launch_bounds__(PVD_CTA, 2) k_step_discrete(const StepArgs a)
         __syncwarp();
         pending = tile;
         pending_total = tile_total;
-        if constexpr (PF_T || PF_X) {
-            tile = next;
-            const long long t2 = (long long)__shfl_sync(0xffffffffu, ticket_raw, 0);
-            next = t2 < ntiles ? t2 : -1;
-        } else tile = warp_take_tile(tickets, ntiles);
     }
     cta_finish_step(a, acc, ntiles, false, -1);
 }
