@@ -33,7 +33,7 @@ static int cont_launch_tail(pvd_sim *s, const StepArgs &a, const ContArgs &ca, l
     PVD_CHECK_LAUNCH();
     k_cont_collect<<<g, PVD_CTA, 0, s->stream>>>(a, ca);
     PVD_CHECK_LAUNCH();
-    k_cont_rank<<<PVD_HIST_BINS, 1024, PVD_RANK_MAX_BIN * sizeof(ContCand), s->stream>>>(a, ca);
+    k_cont_rank<<<g_num_sms > 0 ? g_num_sms : 148, PVD_RANK_SUB, PVD_RANK_SMEM, s->stream>>>(a, ca);
     PVD_CHECK_LAUNCH();
     k_cont_assign<<<1, 1024, 0, s->stream>>>(a, ca, s->cont_queue.as<ContCand>(), s->cont_root.as<int>(), s->cont_skip.as<unsigned char>());
     PVD_CHECK_LAUNCH();
@@ -139,6 +139,20 @@ static int fill_trial_params(pvd_sim *s, ImpArgs &im)
     return PVD_OK;
 }
 
+// device image of a trial table: the caller's values followed (water product wfn) by the np.interp slopes
+static std::vector<double> trial_table_with_slopes(int32_t trial, const double *table, int64_t ntab, size_t total)
+{
+    std::vector<double> host(table, table + total);
+    if (trial == PVD_TRIAL_H2O_FD) {
+        host.resize(total + (size_t)ntab, 0.0);
+        for (int64_t j = 0; j + 1 < ntab; ++j) {
+            volatile double df = table[ntab + j + 1] - table[ntab + j], dx = table[j + 1] - table[j];
+            host[total + (size_t)j] = df / dx;
+        }
+    }
+    return host;
+}
+
 static int host_trial_params(int32_t trial, const double *table, int64_t ntab, const double *dev_table, TrialParamsDev &p)
 {
     memset(&p, 0, sizeof(p));
@@ -155,8 +169,12 @@ static int host_trial_params(int32_t trial, const double *table, int64_t ntab, c
         PVD_REQUIRE(table && ntab >= 4, "H2O trial needs the (2, ntab) table followed by {alpha_theta, theta_eq}");
         p.grid = dev_table;
         p.wfn = dev_table + ntab;
+        p.slope = dev_table + 2 * ntab + 2;
         p.ntab = (int)ntab;
         p.g0 = table[0];
+        p.g_last = table[ntab - 1];
+        p.w_first = table[ntab];
+        p.w_last = table[2 * ntab - 1];
         p.inv_step = (double)(ntab - 1) / (table[ntab - 1] - table[0]);
         p.ang_alpha = table[2 * ntab];
         p.theta_eq = table[2 * ntab + 1];
@@ -172,8 +190,9 @@ extern "C" int pvd_sim_set_trial_table(pvd_sim *s, const double *table, int64_t 
     SIM_DEVICE(s);
     PVD_REQUIRE(s->cfg.trial != PVD_TRIAL_NONE, "this handle was created without a trial wave function");
     const size_t total = s->cfg.trial == PVD_TRIAL_H2O_FD ? (size_t)(2 * ntab + 2) : (size_t)ntab;
-    PVD_CUDA(s->trial_table.alloc(total * 8));
-    PVD_CUDA(cudaMemcpy(s->trial_table.p, table, total * 8, cudaMemcpyHostToDevice));
+    std::vector<double> host = trial_table_with_slopes(s->cfg.trial, table, ntab, total);
+    PVD_CUDA(s->trial_table.alloc(host.size() * 8));
+    PVD_CUDA(cudaMemcpy(s->trial_table.p, host.data(), host.size() * 8, cudaMemcpyHostToDevice));
     s->ntrial = ntab;
     return host_trial_params(s->cfg.trial, table, ntab, s->trial_table.as<double>(), s->trial_params);
 }
@@ -213,8 +232,14 @@ static int imp_enqueue_step(pvd_sim *s, StepArgs &a, const double *inj_um)
     double *lk = s->lk[s->cur].as<double>(), *v = s->v[s->cur].as<double>();
 #define CALL_MOVE(T, P)                                                                                 \
     do {                                                                                                \
-        if (fast) k_imp_move<T, P, PVD_RNG_FAST><<<g, PVD_CTA, 0, s->stream>>>(a, im, x, f, psi, lk, v); \
-        else k_imp_move<T, P, PVD_RNG_FP64><<<g, PVD_CTA, 0, s->stream>>>(a, im, x, f, psi, lk, v);      \
+        const size_t sm = (size_t)3 * T::NC * PVD_CTA * sizeof(double);                                  \
+        if (fast) {                                                                                     \
+            PVD_CUDA(cudaFuncSetAttribute(k_imp_move<T, P, PVD_RNG_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+            k_imp_move<T, P, PVD_RNG_FAST><<<g, PVD_CTA, sm, s->stream>>>(a, im, x, f, psi, lk, v);      \
+        } else {                                                                                        \
+            PVD_CUDA(cudaFuncSetAttribute(k_imp_move<T, P, PVD_RNG_FP64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+            k_imp_move<T, P, PVD_RNG_FP64><<<g, PVD_CTA, sm, s->stream>>>(a, im, x, f, psi, lk, v);      \
+        }                                                                                               \
     } while (0)
     IMP_DISPATCH(CALL_MOVE);
 #undef CALL_MOVE
@@ -276,8 +301,9 @@ int pvd_trial_drift(int32_t trial, const double *xyz, int64_t n, int32_t natoms,
     PVD_REQUIRE((trial == PVD_TRIAL_H2O_FD && nc == 9) || (trial == PVD_TRIAL_HARM1D && nc == 1), "trial / shape mismatch");
     DevBuf dt, dx, dpsi, dlogb, d2b;
     const size_t total = trial == PVD_TRIAL_H2O_FD ? (size_t)(2 * ntab + 2) : (size_t)ntab;
-    PVD_CUDA(dt.alloc(total * 8));
-    PVD_CUDA(cudaMemcpy(dt.p, table, total * 8, cudaMemcpyHostToDevice));
+    std::vector<double> host = trial_table_with_slopes(trial, table, ntab, total);
+    PVD_CUDA(dt.alloc(host.size() * 8));
+    PVD_CUDA(cudaMemcpy(dt.p, host.data(), host.size() * 8, cudaMemcpyHostToDevice));
     TrialParamsDev p;
     if (int rc = host_trial_params(trial, table, ntab, dt.as<double>(), p)) return rc;
     PVD_CUDA(dx.alloc((size_t)n * nc * 8)); PVD_CUDA(dpsi.alloc((size_t)n * 8));
@@ -308,7 +334,7 @@ int pvd_metropolis(const double *x, const double *y, const double *fx, const dou
     if (int rc = ensure_device_ready()) return rc;
     if (n == 0) return PVD_OK;
     const int nc = natoms * ndim;
-    PVD_REQUIRE(nc == 9 || nc == 1, "pvd_metropolis: built for 3x3 (water) and 1x1 problems");
+    PVD_REQUIRE((nc == 9 && ndim == 3) || (nc == 1 && ndim == 1), "pvd_metropolis: built for 3x3 (water) and 1x1 problems");
     DevBuf b[6], ds, dm, dacc;
     const double *src[4] = {x, y, fx, fy};
     for (int k = 0; k < 4; ++k) { PVD_CUDA(b[k].alloc((size_t)n * nc * 8)); PVD_CUDA(cudaMemcpy(b[k].p, src[k], (size_t)n * nc * 8, cudaMemcpyHostToDevice)); }
@@ -335,7 +361,7 @@ int pvd_local_kin(const double *d2, int64_t n, int32_t natoms, int32_t ndim, con
     if (int rc = ensure_device_ready()) return rc;
     if (n == 0) return PVD_OK;
     const int nc = natoms * ndim;
-    PVD_REQUIRE(nc == 9 || nc == 1, "pvd_local_kin: built for 3x3 (water) and 1x1 problems");
+    PVD_REQUIRE((nc == 9 && ndim == 3) || (nc == 1 && ndim == 1), "pvd_local_kin: built for 3x3 (water) and 1x1 problems");
     DevBuf dd, dm, dk;
     PVD_CUDA(dd.alloc((size_t)n * nc * 8)); PVD_CUDA(cudaMemcpy(dd.p, d2, (size_t)n * nc * 8, cudaMemcpyHostToDevice));
     PVD_CUDA(dm.alloc(natoms * 8)); PVD_CUDA(cudaMemcpy(dm.p, inv_mass, natoms * 8, cudaMemcpyHostToDevice));

@@ -428,7 +428,7 @@ int pvd_sim_create(const pvd_config *cfg, pvd_sim **out)
         TRY(s->cand.alloc((size_t)2 * cap * sizeof(ContCand)));       // candidates (fallback sort pads to a power of two)
         TRY(s->cand_sorted.alloc((size_t)cap * sizeof(ContCand)));
         TRY(s->bin_start.alloc(PVD_HIST_BINS * 4));
-        TRY(cudaFuncSetAttribute(k_cont_rank, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PVD_RANK_MAX_BIN * sizeof(ContCand))));
+        TRY(cudaFuncSetAttribute(k_cont_rank, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PVD_RANK_SMEM));
         TRY(s->bin_fill.alloc(PVD_HIST_BINS * 4));
         TRY(cudaMemset(s->bin_fill.p, 0, PVD_HIST_BINS * 4));
         TRY(s->cont_queue.alloc((size_t)2 * cap * sizeof(ContCand)));

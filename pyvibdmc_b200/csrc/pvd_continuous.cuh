@@ -11,9 +11,9 @@
 //                        (K = number of kills) and, per bin, where its members start in the
 //                        candidate array
 //      k_cont_collect  : candidates = all walkers at or above that bin, bucketed by bin
-//      k_cont_rank     : one CTA per bin sorts its bucket by (w desc, index asc) with a bitonic
-//                        network in shared memory and writes it to its place in the sorted
-//                        candidate array.  If some bin is too full for that (> 8192: many
+//      k_cont_rank     : one CTA per bin orders its bucket by (w desc, index asc) in shared memory
+//                        (1024 sub-buckets + all-pairs rank inside a sub-bucket) and writes it to
+//                        its place in the sorted candidate array.  If some bin is too full for that (> 8192: many
 //                        identical weights), the candidates are appended unordered instead and
 //                        k_cont_assign sorts them with a single-CTA bitonic network in global memory.
 //   4. k_cont_assign   : if the K-th largest weight is > half the largest, the K argmax steps are
@@ -38,6 +38,7 @@ struct ContWork {
     unsigned n_copy;        // (dst, src) pairs to copy
     unsigned n_upper;       // kills caused by the upper threshold
     int edge_bin;
+    int fast;               // 1/2: k_cont_copy pairs j-th largest (sorted / cand array) with the j-th kill itself
     int ranked;             // 1: candidates are bucketed by bin and ranked in parallel; 0: unordered + single-CTA sort
     unsigned done;
     double sub_w, sub_wv;   // weight removed by upper-threshold kills (corrects the exact sums)
@@ -188,7 +189,7 @@ __global__ void __launch_bounds__(1024) k_cont_prefix(const StepArgs a, const Co
     const unsigned nk = so->err ? 0u : (unsigned)(ld_relaxed_u64(&a.status[ntiles - 1]) & 0xffffffffull);
     if (threadIdx.x == 0) {
         ca.work->n_kill = nk; ca.work->n_cand = 0; ca.work->n_copy = 0; ca.work->n_upper = 0; ca.work->done = 0;
-        ca.work->sub_w = 0.0; ca.work->sub_wv = 0.0; ca.work->ranked = 0;
+        ca.work->sub_w = 0.0; ca.work->sub_wv = 0.0; ca.work->ranked = 0; ca.work->fast = 0;
         ca.work->wmax_bits = 0ull; ca.work->wmin_bits = 0x7FF0000000000000ull;
     }
     if (so->err || nk == 0) return;
@@ -261,37 +262,76 @@ __global__ void __launch_bounds__(PVD_CTA) k_cont_collect(const StepArgs a, cons
     }
 }
 
-// ---- 3c. sort inside each bin (one CTA per bin, bitonic network in shared memory) -> sorted candidates
+// ---- 3c. order inside each bin (one CTA per bin) -> sorted candidates
+// The bin's bucket is loaded into shared memory, split into 1024 sub-buckets by the next 10 mantissa bits
+// (weights inside one 1/64-octave bin are close to uniformly spread, so sub-buckets hold a handful of members),
+// and every member's final position is the start of its sub-bucket plus an all-pairs count inside it.
+constexpr int PVD_RANK_SUB = 1024;
+constexpr size_t PVD_RANK_SMEM = (size_t)PVD_RANK_MAX_BIN * (sizeof(ContCand) + sizeof(unsigned short)) + 3 * PVD_RANK_SUB * sizeof(unsigned);
+__device__ __forceinline__ int weight_subbin(double w)
+{
+    return (int)((__double_as_longlong(w) >> 36) & (PVD_RANK_SUB - 1));
+}
 __global__ void __launch_bounds__(1024) k_cont_rank(const StepArgs a, const ContArgs ca)
 {
     extern __shared__ __align__(16) unsigned char s_rank_raw[];
     ContCand *s_c = reinterpret_cast<ContCand *>(s_rank_raw);
+    unsigned *sub_cnt = reinterpret_cast<unsigned *>(s_c + PVD_RANK_MAX_BIN);
+    unsigned *sub_start = sub_cnt + PVD_RANK_SUB;
+    unsigned *sub_fill = sub_start + PVD_RANK_SUB;
+    unsigned short *perm = reinterpret_cast<unsigned short *>(sub_fill + PVD_RANK_SUB);
+    __shared__ unsigned s_warp[32];
     const DevState *so = &a.st[a.parity];
     if (so->err || ca.work->n_kill == 0 || !ca.work->ranked) return;
-    const int bin = PVD_HIST_BINS - 1 - (int)blockIdx.x;
-    if (bin < ca.work->edge_bin) return;
-    unsigned cnt = ca.hist[bin];
-    const unsigned start = ca.bin_start[bin];
-    if (cnt == 0 || (long long)start >= ca.cand_cap) return;
-    if ((long long)start + cnt > ca.cand_cap) cnt = (unsigned)(ca.cand_cap - start);
-    unsigned P = 1;
-    while (P < cnt) P <<= 1;
-    for (unsigned t = threadIdx.x; t < P; t += blockDim.x) s_c[t] = t < cnt ? ca.cand[start + t] : ContCand{-INFINITY, 0x7fffffff, -1};
-    __syncthreads();
-    for (unsigned k = 2; k <= P; k <<= 1) {
-        for (unsigned j = k >> 1; j > 0; j >>= 1) {
-            for (unsigned t = threadIdx.x; t < P; t += blockDim.x) {
-                const unsigned l = t ^ j;
-                if (l > t) {
-                    const ContCand x = s_c[t], y = s_c[l];
-                    const bool up = (t & k) == 0;
-                    if (up ? cand_before(y, x) : cand_before(x, y)) { s_c[t] = y; s_c[l] = x; }
-                }
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    const int edge = ca.work->edge_bin;
+    // CTAs stride over the bins from the top; each CTA needs 150 KB of shared memory, so the grid is kept small
+    for (int bin = PVD_HIST_BINS - 1 - (int)blockIdx.x; bin >= edge; bin -= (int)gridDim.x) {
+        unsigned cnt = ca.hist[bin];
+        const unsigned start = ca.bin_start[bin];
+        if (cnt == 0 || (long long)start >= ca.cand_cap) continue;
+        if ((long long)start + cnt > ca.cand_cap) cnt = (unsigned)(ca.cand_cap - start);
+        __syncthreads();                                      // previous bin's shared arrays are no longer read
+        sub_cnt[t] = 0; sub_fill[t] = 0;                      // blockDim.x == PVD_RANK_SUB
+        for (unsigned e = t; e < cnt; e += blockDim.x) s_c[e] = ca.cand[start + e];
+        __syncthreads();
+        for (unsigned e = t; e < cnt; e += blockDim.x) atomicAdd(&sub_cnt[weight_subbin(s_c[e].w)], 1u);
+        __syncthreads();
+        // members of higher sub-buckets come first: thread t owns sub-bucket 1023 - t
+        const unsigned mine = sub_cnt[PVD_RANK_SUB - 1 - t];
+        unsigned incl = mine;
+        for (int off = 1; off < 32; off <<= 1) {
+            const unsigned y = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += y;
+        }
+        if (lane == 31) s_warp[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            const unsigned v = s_warp[lane];
+            unsigned x = v;
+            for (int off = 1; off < 32; off <<= 1) {
+                const unsigned y = __shfl_up_sync(0xffffffffu, x, off);
+                if (lane >= off) x += y;
             }
-            __syncthreads();
+            s_warp[lane] = x - v;
+        }
+        __syncthreads();
+        sub_start[PVD_RANK_SUB - 1 - t] = s_warp[wid] + incl - mine;
+        __syncthreads();
+        for (unsigned e = t; e < cnt; e += blockDim.x) {
+            const int sk = weight_subbin(s_c[e].w);
+            perm[sub_start[sk] + atomicAdd(&sub_fill[sk], 1u)] = (unsigned short)e;
+        }
+        __syncthreads();
+        for (unsigned p = t; p < cnt; p += blockDim.x) {
+            const ContCand me = s_c[perm[p]];
+            const int sk = weight_subbin(me.w);
+            const unsigned s0 = sub_start[sk], c = sub_cnt[sk];
+            unsigned r = s0;
+            for (unsigned q = s0; q < s0 + c; ++q) r += cand_before(s_c[perm[q]], me) ? 1u : 0u;
+            ca.sorted[start + r] = me;
         }
     }
-    for (unsigned t = threadIdx.x; t < cnt; t += blockDim.x) ca.sorted[start + t] = s_c[t];
 }
 
 // block-wide argmax (first index on ties) / argmin over w[0..n) with a skip mask
@@ -365,7 +405,11 @@ __global__ void __launch_bounds__(1024) k_cont_assign(const StepArgs a, const Co
         // fast path: the K largest weights are all above half of the largest -> no halved piece is ever a donor
         if (threadIdx.x == 0) s_flag = (C >= K && srt[K - 1].w > 0.5 * srt[0].w) ? 1 : 0;
         __syncthreads();
-        if (s_flag) {
+        if (s_flag && !ca.has_upper) {
+            // applied by all CTAs of k_cont_copy straight from the sorted candidates
+            if (threadIdx.x == 0) ca.work->fast = ranked ? 1 : 2;
+            ncopy = K;
+        } else if (s_flag) {
             for (int j = threadIdx.x; j < K; j += blockDim.x) {
                 const int d = srt[j].idx, k = ca.kill_idx[j];
                 const double h = srt[j].w / 2.0;
@@ -474,8 +518,18 @@ __global__ void __launch_bounds__(PVD_CTA) k_cont_copy(const StepArgs a, const C
     if (so->err) return;
     const unsigned m = ca.work->n_copy;
     const bool dw = so->dw_active != 0;
+    const int fast = ca.work->fast;
+    const ContCand *srt = fast == 1 ? ca.sorted : ca.cand;
     for (long long t = blockIdx.x * (long long)PVD_CTA + threadIdx.x; t < (long long)m; t += (long long)gridDim.x * PVD_CTA) {
-        const int dst = ca.copy_dst[t], src = ca.copy_src[t];
+        int dst, src;
+        if (fast) {
+            // j-th largest weight donates to the j-th killed walker (ascending index): halve and share (:340-356)
+            const ContCand d = srt[t];
+            src = d.idx; dst = ca.kill_idx[t];
+            const double h = d.w / 2.0;
+            ca.w[src] = h;
+            ca.w[dst] = h;
+        } else { dst = ca.copy_dst[t]; src = ca.copy_src[t]; }
         for (int c = 0; c < a.nc; ++c) x[c * a.cap + dst] = x[c * a.cap + src];
         v[dst] = v[src];
         if (dw && who) who[dst] = who[src];

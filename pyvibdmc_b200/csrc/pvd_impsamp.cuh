@@ -7,8 +7,10 @@ struct TrialParamsDev {
     // water product wfn (call_trl_h2o.py:7-78): table rows grid / psi, Gaussian bend
     const double *grid;
     const double *wfn;
+    const double *slope;        // (wfn[j+1] - wfn[j]) / (grid[j+1] - grid[j]), formed once on the host exactly as np.interp forms it
     int ntab;
     double g0, inv_step;
+    double g_last, w_first, w_last;
     double ang_alpha, theta_eq, ang_pref;
     // 1-D Gaussian (harm_trial_wfn.py:6-40)
     double h_alpha, h_pref;
@@ -20,8 +22,8 @@ __device__ __forceinline__ double interp_table(double x, const TrialParamsDev &p
 {
     const int n = p.ntab;
     if (x != x) return x;
-    if (x > p.grid[n - 1]) return p.wfn[n - 1];
-    if (x < p.grid[0]) return p.wfn[0];
+    if (x > p.g_last) return p.w_last;
+    if (x < p.g0) return p.w_first;
     int j = (int)((x - p.g0) * p.inv_step);
     j = j < 0 ? 0 : (j > n - 2 ? n - 2 : j);
     while (j > 0 && x < p.grid[j]) --j;
@@ -30,8 +32,7 @@ __device__ __forceinline__ double interp_table(double x, const TrialParamsDev &p
     if (j == n - 1) return fj;
     const double xj = p.grid[j];
     if (x == xj) return fj;
-    const double slope = (p.wfn[j + 1] - fj) / (p.grid[j + 1] - xj);
-    return __dadd_rn(__dmul_rn(slope, x - xj), fj);
+    return __dadd_rn(__dmul_rn(p.slope[j], x - xj), fj);
 }
 
 __device__ __forceinline__ double norm3(double a, double b, double c)
@@ -42,6 +43,7 @@ __device__ __forceinline__ double norm3(double a, double b, double c)
 // psi = interp(r_OH1) * interp(r_OH2) * Gaussian(theta), kwargs {'dists':[[0,2],[2,1]],'angs':[[0,2,1]]}
 struct TrialH2O {
     static constexpr int NC = 9;
+    static constexpr int NDIM = 3;
     static constexpr bool ANALYTIC = false;
     __device__ static __forceinline__ double psi(const double (&x)[9], const TrialParamsDev &p)
     {
@@ -58,6 +60,7 @@ struct TrialH2O {
 
 struct TrialHarm1D {
     static constexpr int NC = 1;
+    static constexpr int NDIM = 1;
     static constexpr bool ANALYTIC = true;
     __device__ static __forceinline__ double psi(const double (&x)[1], const TrialParamsDev &p)
     {
@@ -113,45 +116,97 @@ __device__ __forceinline__ void trial_drift(double (&x)[TRIAL::NC], const TrialP
 }
 
 // ImpSamp.local_kin (imp_samp.py:50-53): -0.5 * sum_d ( sum_a inv_m[a] * sec[a,d] ), NumPy's reduction order
-template <int NC>
-__device__ __forceinline__ double local_kinetic(const double (&d2)[NC], const double *inv_mass, int ndim)
+// (ndim is a template parameter so that every array index is a compile-time constant: no local-memory copies)
+template <int NC, int NDIM>
+__device__ __forceinline__ double local_kinetic(const double (&d2)[NC], const double *inv_mass)
 {
-    const int natoms = NC / ndim;
+    constexpr int ndim = NDIM, natoms = NC / NDIM;
     double tot = 0.0;
+#pragma unroll
     for (int d = 0; d < ndim; ++d) {
         double s = __dmul_rn(inv_mass[0], d2[d]);
+#pragma unroll
         for (int a = 1; a < natoms; ++a) s = __dadd_rn(s, __dmul_rn(inv_mass[a], d2[a * ndim + d]));
         tot = (d == 0) ? s : __dadd_rn(tot, s);
     }
     return __dmul_rn(-0.5, tot);
 }
 
+// In-step variant of trial_drift + local_kinetic: same arithmetic and the same summation order as
+// local_kinetic (s_d accumulates atom by atom, then s_0 + s_1 + s_2), but the second derivatives are folded
+// into three running sums instead of an NC-long array and the stencil walks ONE working copy of the
+// coordinates (x - dx, + 2 dx, - dx, as imp_samp.py:67-71 does), which keeps the kernel inside 128 registers.
+template <class TRIAL>
+__device__ __forceinline__ void trial_drift_ke(double (&xx)[TRIAL::NC], const TrialParamsDev &p, const double *inv_mass, double &psi0,
+                                               double (&d1)[TRIAL::NC], double &ke)
+{
+    constexpr int NC = TRIAL::NC, ND = TRIAL::NDIM;
+    if constexpr (TRIAL::ANALYTIC) {
+        double d2[NC];
+        TRIAL::derivs(xx, p, psi0, d1, d2);
+        ke = local_kinetic<NC, ND>(d2, inv_mass);
+    } else {
+        psi0 = TRIAL::psi(xx, p);
+        double sd[ND];
+#pragma unroll
+        for (int d = 0; d < ND; ++d) sd[d] = 0.0;
+#pragma unroll 1
+        for (int c = 0; c < NC; ++c) {
+            double orig = 0.0;
+#pragma unroll
+            for (int k = 0; k < NC; ++k) orig = (k == c) ? xx[k] : orig;
+            const double lo = orig - p.fd_dx;
+            const double hi = lo + 2.0 * p.fd_dx;
+#pragma unroll
+            for (int k = 0; k < NC; ++k) xx[k] = (k == c) ? lo : xx[k];
+            const double pm = TRIAL::psi(xx, p);
+#pragma unroll
+            for (int k = 0; k < NC; ++k) xx[k] = (k == c) ? hi : xx[k];
+            const double pp = TRIAL::psi(xx, p);
+#pragma unroll
+            for (int k = 0; k < NC; ++k) xx[k] = (k == c) ? hi - p.fd_dx : xx[k];   // the walked value, exactly as trial_drift leaves it
+            const double first = (pp - pm) / (2.0 * p.fd_dx);
+            const double sec = __dadd_rn(__dadd_rn(pm, -__dmul_rn(2.0, psi0)), pp) / p.fd_dx2;
+            const double term = __dmul_rn(inv_mass[c / ND], sec / psi0);
+#pragma unroll
+            for (int k = 0; k < NC; ++k)
+                if (k == c) d1[k] = first / psi0;
+#pragma unroll
+            for (int d = 0; d < ND; ++d)
+                if (d == c % ND) sd[d] = (c < ND) ? term : __dadd_rn(sd[d], term);
+        }
+        double tot = sd[0];
+#pragma unroll
+        for (int d = 1; d < ND; ++d) tot = __dadd_rn(tot, sd[d]);
+        ke = __dmul_rn(-0.5, tot);
+    }
+}
+
 // ImpSamp.metropolis (imp_samp.py:29-47) for one walker
-template <int NC>
+template <int NC, int NDIM>
 __device__ __forceinline__ double metropolis_ratio(const double (&x)[NC], const double (&y)[NC], const double (&fx)[NC],
                                                    const double (&fy)[NC], double psi_x, double psi_y, const double *sigma,
-                                                   const double *inv_mass, int ndim, double dt)
+                                                   const double *inv_mass, double dt)
 {
-    const int natoms = NC / ndim;
+    constexpr int ndim = NDIM, natoms = NC / NDIM;
     const double q = psi_y / psi_x;
     const double ratio = __dmul_rn(q, q);
-    double acc = 1.0;
+    // prod_{a,d} exp(-u1^2 / 2 s^2) / exp(-u2^2 / 2 s^2) = exp( sum (u2^2 - u1^2) / 2 s^2 ): one exponential instead of
+    // 2 * NC (and no intermediate underflow); agrees with the reference's product of ratios to a few ulp
+    double expo = 0.0;
+#pragma unroll
     for (int d = 0; d < ndim; ++d) {
-        double pd = 1.0;
+#pragma unroll
         for (int a = 0; a < natoms; ++a) {
             const int c = a * ndim + d;
-            const double two_s2 = __dmul_rn(2.0, __dmul_rn(sigma[a], sigma[a]));
+            const double inv_two_s2 = 0.5 / __dmul_rn(sigma[a], sigma[a]);
             const double dxm = __dmul_rn(__dmul_rn(inv_mass[a], fx[c]), dt), dym = __dmul_rn(__dmul_rn(inv_mass[a], fy[c]), dt);
             const double u1 = __dadd_rn(__dadd_rn(x[c], -y[c]), -dym);
             const double u2 = __dadd_rn(__dadd_rn(y[c], -x[c]), -dxm);
-            const double t1 = exp(__dmul_rn(-1.0, __dmul_rn(u1, u1)) / two_s2);
-            const double t2 = exp(__dmul_rn(-1.0, __dmul_rn(u2, u2)) / two_s2);
-            const double r = t1 / t2;
-            pd = (a == 0) ? r : __dmul_rn(pd, r);
+            expo = fma((u2 - u1) * (u2 + u1), inv_two_s2, expo);
         }
-        acc = (d == 0) ? pd : __dmul_rn(acc, pd);
     }
-    acc = __dmul_rn(acc, ratio);
+    double acc = __dmul_rn(exp(expo), ratio);
     if (__dmul_rn(psi_x, psi_y) <= 0.0) acc = 0.0;
     return acc;
 }
@@ -166,7 +221,7 @@ struct ImpArgs {
 // first-step exception with importance sampling (pyvibdmc.py:553-554, 760-769): drift on the start
 // ensemble, E_L = V + local kinetic energy.
 template <class TRIAL, class POT>
-__global__ void __launch_bounds__(PVD_CTA) k_imp_init(const StepArgs a, const ImpArgs im, double *x, double *f, double *psi, double *lk, double *v)
+__global__ void __launch_bounds__(PVD_CTA, 2) k_imp_init(const StepArgs a, const ImpArgs im, double *x, double *f, double *psi, double *lk, double *v)
 {
     constexpr int NC = TRIAL::NC;
     const long long n = a.st[a.parity].n;
@@ -175,7 +230,7 @@ __global__ void __launch_bounds__(PVD_CTA) k_imp_init(const StepArgs a, const Im
 #pragma unroll
         for (int c = 0; c < NC; ++c) xx[c] = x[c * a.cap + i];
         trial_drift<TRIAL>(xx, im.trial, p0, d1, d2);
-        const double ke = local_kinetic<NC>(d2, im.inv_mass, a.ndim);
+        const double ke = local_kinetic<NC, TRIAL::NDIM>(d2, im.inv_mass);
 #pragma unroll
         for (int c = 0; c < NC; ++c) f[c * a.cap + i] = d1[c];
         psi[i] = p0;
@@ -188,7 +243,7 @@ __global__ void __launch_bounds__(PVD_CTA) k_imp_init(const StepArgs a, const Im
 // Writes the accepted/kept walker, its drift, psi, local kinetic energy and E_L; counts acceptances.
 // The last CTA publishes dt_eff = dt * n_accept / N (pyvibdmc.py:603, 372-378) for the branching kernel.
 template <class TRIAL, class POT, int RNG>
-__global__ void __launch_bounds__(PVD_CTA) k_imp_move(const StepArgs a, const ImpArgs im, double *x, double *f, double *psi, double *lk, double *v)
+__global__ void __launch_bounds__(PVD_CTA, 2) k_imp_move(const StepArgs a, const ImpArgs im, double *x, double *f, double *psi, double *lk, double *v)
 {
     constexpr int NC = TRIAL::NC;
     __shared__ unsigned s_cnt[PVD_WARPS];
@@ -197,33 +252,52 @@ __global__ void __launch_bounds__(PVD_CTA) k_imp_move(const StepArgs a, const Im
     if (sip->err || sip->n <= 0) return;           // the branching kernel forwards the dead state
     const long long n = sip->n, step = sip->step;
     unsigned my_acc = 0;
+    // the walker's current position and drift, and the proposed position, wait in shared memory (thread-private
+    // columns) while the finite-difference stencil is evaluated on a working copy: they would otherwise pin 54
+    // registers through the heaviest code
+    extern __shared__ __align__(16) unsigned char s_imp_raw[];
+    double (*s_xf)[PVD_CTA] = reinterpret_cast<double (*)[PVD_CTA]>(s_imp_raw);          // [3 * NC][PVD_CTA]
+    const int tid = threadIdx.x;
     for (long long i = blockIdx.x * (long long)PVD_CTA + threadIdx.x; i < n; i += (long long)gridDim.x * PVD_CTA) {
-        double xo[NC], fo[NC], y[NC];
+        double xx[NC];
+        {
+            double xo[NC], fo[NC];
 #pragma unroll
-        for (int c = 0; c < NC; ++c) { xo[c] = x[c * a.cap + i]; fo[c] = f[c * a.cap + i]; }
-        const double psi_x = psi[i];
-        if (a.inj_disp) {
+            for (int c = 0; c < NC; ++c) { xo[c] = x[c * a.cap + i]; fo[c] = f[c * a.cap + i]; }
+            if (a.inj_disp) {
 #pragma unroll
-            for (int c = 0; c < NC; ++c) y[c] = a.inj_disp[c * a.cap + i];
-        } else {
-            walker_normals<NC, RNG>(a.seed, i, step, y);
+                for (int c = 0; c < NC; ++c) xx[c] = a.inj_disp[c * a.cap + i];
+            } else {
+                walker_normals<NC, RNG>(a.seed, i, step, xx);
 #pragma unroll
-            for (int c = 0; c < NC; ++c) y[c] = __dmul_rn(a.sigc[c], y[c]);
+                for (int c = 0; c < NC; ++c) xx[c] = __dmul_rn(a.sigc[c], xx[c]);
+            }
+            // displaced = coords + disps + (inv_m * f_x) * dt
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                xx[c] = __dadd_rn(__dadd_rn(xo[c], xx[c]), __dmul_rn(__dmul_rn(im.inv_mass[c / TRIAL::NDIM], fo[c]), a.dt));
+                s_xf[c][tid] = xo[c];
+                s_xf[NC + c][tid] = fo[c];
+                s_xf[2 * NC + c][tid] = xx[c];
+            }
         }
-        // displaced = coords + disps + (inv_m * f_x) * dt
+        double fy[NC], psi_y, ke_new;
+        trial_drift_ke<TRIAL>(xx, im.trial, im.inv_mass, psi_y, fy, ke_new);
+        double xo[NC], y[NC];
+        double acc;
+        {
+            double fo[NC];
 #pragma unroll
-        for (int c = 0; c < NC; ++c)
-            y[c] = __dadd_rn(__dadd_rn(xo[c], y[c]), __dmul_rn(__dmul_rn(im.inv_mass[c / a.ndim], fo[c]), a.dt));
-        double fy[NC], sy[NC], psi_y;
-        trial_drift<TRIAL>(y, im.trial, psi_y, fy, sy);
-        const double acc = metropolis_ratio<NC>(xo, y, fo, fy, psi_x, psi_y, a.sigma, im.inv_mass, a.ndim, a.dt);
+            for (int c = 0; c < NC; ++c) { xo[c] = s_xf[c][tid]; fo[c] = s_xf[NC + c][tid]; y[c] = s_xf[2 * NC + c][tid]; }
+            acc = metropolis_ratio<NC, TRIAL::NDIM>(xo, y, fo, fy, psi[i], psi_y, a.sigma, im.inv_mass, a.dt);
+        }
         double u;
         if (im.inj_um) u = im.inj_um[i];
         else { const uint4 r = pvd_draw(a.seed, i, step, PVD_STREAM_METRO, 0u); u = u53(r.x, r.y); }
         const bool ok = acc > u;
         double ke = lk[i];
         if (ok) {
-            ke = local_kinetic<NC>(sy, im.inv_mass, a.ndim);
+            ke = ke_new;
 #pragma unroll
             for (int c = 0; c < NC; ++c) { xo[c] = y[c]; x[c * a.cap + i] = y[c]; f[c * a.cap + i] = fy[c]; }
             psi[i] = psi_y;
@@ -284,7 +358,8 @@ __global__ void k_metropolis_aos(const double *x, const double *y, const double 
         double a[NC], b[NC], c[NC], d[NC];
 #pragma unroll
         for (int k = 0; k < NC; ++k) { a[k] = x[i * NC + k]; b[k] = y[i * NC + k]; c[k] = fx[i * NC + k]; d[k] = fy[i * NC + k]; }
-        acc[i] = metropolis_ratio<NC>(a, b, c, d, psx[i], psy[i], sigma, inv_mass, ndim, dt);
+        (void)ndim;
+        acc[i] = metropolis_ratio<NC, (NC == 9 ? 3 : 1)>(a, b, c, d, psx[i], psy[i], sigma, inv_mass, dt);
     }
 }
 
@@ -295,6 +370,7 @@ __global__ void k_local_kin_aos(const double *d2, long long n, int ndim, const d
         double a[NC];
 #pragma unroll
         for (int k = 0; k < NC; ++k) a[k] = d2[i * NC + k];
-        ke[i] = local_kinetic<NC>(a, inv_mass, ndim);
+        (void)ndim;
+        ke[i] = local_kinetic<NC, (NC == 9 ? 3 : 1)>(a, inv_mass);
     }
 }
