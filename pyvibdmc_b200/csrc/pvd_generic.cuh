@@ -98,7 +98,7 @@ __global__ void k_pot_harm_rt(const double *__restrict__ aos, long long n, int n
 // Generic in the number of components: normals are generated pairwise per walker exactly as in
 // walker_normals<>, so the fused kernels and this kernel produce identical streams.
 template <int RNG>
-__global__ void k_displace_soa(double *__restrict__ x, const DevState *st, int parity, long long n_fixed, long long step_fixed,
+__global__ void __launch_bounds__(256, 4) k_displace_soa(double *__restrict__ x, const DevState *st, int parity, long long n_fixed, long long step_fixed,
                                long long cap, int nc, int ndim, unsigned long long seed, const double *__restrict__ inj_disp,
                                const StepArgs *sig_src, const double *__restrict__ sigma_dev, double *__restrict__ z_out)
 {
@@ -106,28 +106,46 @@ __global__ void k_displace_soa(double *__restrict__ x, const DevState *st, int p
     const long long n = st ? st[parity].n : n_fixed;
     const long long step = st ? st[parity].step : step_fixed;
     if (st && st[parity].err) return;
+    const int npairs = (nc + 1) / 2;
+    constexpr int G = 3;                                   // pairs generated together: three independent fp64 chains in flight
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        for (int k = 0; k < (nc + 1) / 2; ++k) {
-            double z0, z1;
+#pragma unroll 1
+        for (int k0 = 0; k0 < npairs; k0 += G) {
+            double z0[G], z1[G];
             if (inj_disp) {
-                z0 = inj_disp[(2 * k) * cap + i];
-                z1 = (2 * k + 1 < nc) ? inj_disp[(2 * k + 1) * cap + i] : 0.0;
+#pragma unroll
+                for (int j = 0; j < G; ++j) {
+                    const int k = k0 + j;
+                    z0[j] = (2 * k < nc) ? inj_disp[(2 * k) * cap + i] : 0.0;
+                    z1[j] = (2 * k + 1 < nc) ? inj_disp[(2 * k + 1) * cap + i] : 0.0;
+                }
             } else {
                 if (RNG == PVD_RNG_FP64) {
-                    const uint4 rr[1] = {pvd_draw(seed, i, step, PVD_STREAM_DISP, (unsigned)k)};
-                    double q0[1], q1[1];
-                    normal_pairs_fp64<1>(rr, q0, q1);
-                    z0 = q0[0]; z1 = q1[0];
-                } else normal_pair<RNG>(pvd_draw(seed, i, step, PVD_STREAM_DISP, (unsigned)k), z0, z1);
-                z0 = __dmul_rn(sigma_dev[(2 * k) / ndim], z0);
-                if (2 * k + 1 < nc) z1 = __dmul_rn(sigma_dev[(2 * k + 1) / ndim], z1);
+                    uint4 rr[G];
+#pragma unroll
+                    for (int j = 0; j < G; ++j) rr[j] = pvd_draw(seed, i, step, PVD_STREAM_DISP, (unsigned)(k0 + j));
+                    normal_pairs_fp64<G>(rr, z0, z1);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < G; ++j) normal_pair<RNG>(pvd_draw(seed, i, step, PVD_STREAM_DISP, (unsigned)(k0 + j)), z0[j], z1[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < G; ++j) {
+                    const int k = k0 + j;
+                    if (2 * k < nc) z0[j] = __dmul_rn(sigma_dev[(2 * k) / ndim], z0[j]);
+                    if (2 * k + 1 < nc) z1[j] = __dmul_rn(sigma_dev[(2 * k + 1) / ndim], z1[j]);
+                }
             }
-            if (z_out) {
-                z_out[(2 * k) * cap + i] = z0;
-                if (2 * k + 1 < nc) z_out[(2 * k + 1) * cap + i] = z1;
-            } else {
-                x[(2 * k) * cap + i] = __dadd_rn(x[(2 * k) * cap + i], z0);
-                if (2 * k + 1 < nc) x[(2 * k + 1) * cap + i] = __dadd_rn(x[(2 * k + 1) * cap + i], z1);
+#pragma unroll
+            for (int j = 0; j < G; ++j) {
+                const int k = k0 + j;
+                if (z_out) {
+                    if (2 * k < nc) z_out[(2 * k) * cap + i] = z0[j];
+                    if (2 * k + 1 < nc) z_out[(2 * k + 1) * cap + i] = z1[j];
+                } else {
+                    if (2 * k < nc) x[(2 * k) * cap + i] = __dadd_rn(x[(2 * k) * cap + i], z0[j]);
+                    if (2 * k + 1 < nc) x[(2 * k + 1) * cap + i] = __dadd_rn(x[(2 * k + 1) * cap + i], z1[j]);
+                }
             }
         }
     }

@@ -2,7 +2,7 @@
 static int nn_enqueue_discrete_step(pvd_sim *s, StepArgs &a)
 {
     // move (in place) -> descriptor + MLP -> branch-only step
-    const int g = s->grid;
+    const int g = s->grid_light;
     double *x = s->x[s->cur].as<double>();
     if (a.inj_disp) {
         k_displace_soa<PVD_RNG_FP64><<<g, 256, 0, s->stream>>>(x, s->st.as<DevState>(), s->parity, 0, 0, s->cap, s->nc, s->cfg.ndim, s->cfg.seed,
