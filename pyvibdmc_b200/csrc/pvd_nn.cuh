@@ -10,6 +10,7 @@
 // accumulators in TMEM, swish in the epilogue) -- see DESIGN.md.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 #include "pvd_step.cuh"
 
@@ -109,8 +110,8 @@ __global__ void __launch_bounds__(NN_THREADS) k_nn_h4o2(const double *__restrict
 //
 // Tile: 128 walkers per CTA (UMMA M = 128, one walker per TMEM lane / per thread), N = 128 output
 // neurons (120 padded), fp32 accumulators in TMEM (128 columns).  fp32 accuracy is kept by splitting
-// every activation and every weight into two bf16 pieces and issuing the four
-// cross terms of a two-piece split (x = x1 + x2: a1w1, a1w2, a2w1, a2w2; residual ~2^-16, tighter than the TF32
+// every activation and every weight into two fp16 pieces and issuing the four
+// cross terms of a two-piece split (x = x1 + x2: a1w1, a1w2, a2w1, a2w2; residual ~2^-22, tighter than the TF32
 // path TensorFlow itself takes for float32 matmuls on tensor-core GPUs) as kind::f16 MMAs with
 // K = 16.  Operands are K-major, un-swizzled "core matrix" layout in shared memory:
 //     byte(row, k) = (k/8) * (128*16) + (row/8) * 128 + (row%8) * 16 + (k%8) * 2      (LBO = 2048, SBO = 128)
@@ -118,15 +119,15 @@ __global__ void __launch_bounds__(NN_THREADS) k_nn_h4o2(const double *__restrict
 // All three weight images (pre-formatted on the host, 136 KB) are loaded once per persistent CTA by bulk TMA copies;
 // per layer 4 x K/16 MMAs are issued by one thread,
 // tcgen05.commit -> mbarrier, then every thread drains its own TMEM lane (tcgen05.ld 32x32b.x32), adds
-// the bias, applies swish, splits into bf16 pieces and stores the next layer's A operand.
+// the bias, applies swish, splits into fp16 pieces and stores the next layer's A operand.
 // =====================================================================================================
 constexpr int TC_M = 128, TC_N = 128, TC_THREADS = 512;
-constexpr int TC_PIECE_BYTES_K128 = 128 * 128 * 2;          // one bf16 operand piece, K = 128
+constexpr int TC_PIECE_BYTES_K128 = 128 * 128 * 2;          // one fp16 operand piece, K = 128
 constexpr int TC_PIECE_BYTES_K16 = 128 * 16 * 2;
-constexpr int TC_NPIECE = 2;                                 // bf16 pieces per operand (x = x1 + x2, residual ~2^-17)
+constexpr int TC_NPIECE = 2;                                 // fp16 pieces per operand (x = x1 + x2, residual ~2^-22)
 constexpr int TC_IMG_L0 = TC_NPIECE * TC_PIECE_BYTES_K16;    // weights image, layer 0 (K padded 15 -> 16)
 constexpr int TC_IMG_L12 = TC_NPIECE * TC_PIECE_BYTES_K128;  // weights image, layers 1 and 2
-constexpr int TC_IMG_TOTAL = TC_IMG_L0 + 2 * TC_IMG_L12;     // bytes of pre-formatted bf16 weight images
+constexpr int TC_IMG_TOTAL = TC_IMG_L0 + 2 * TC_IMG_L12;     // bytes of pre-formatted fp16 weight images
 constexpr int TC_VEC_FLOATS = 3 * 128 + 128 + 4;             // b0,b1,b2 (padded), W3 (padded), b3
 constexpr size_t TC_SMEM_BYTES = 3 * TC_IMG_L12 + TC_IMG_L0 + 64 + TC_VEC_FLOATS * 4 + 128 * 4 * 4;   // A, W1, W2, W0, barriers, vectors
 
@@ -136,7 +137,7 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr)
     // start address, LBO = 2048 B, SBO = 128 B (all >> 4), version 1 (Blackwell), no swizzle
     return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)(2048 >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
 }
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate)
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate)
 {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
@@ -158,16 +159,33 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
 }
-// split two floats into two packed bf16x2 pieces each (round to nearest even at both levels): x = p1 + p2 up to ~2^-17
+// split two floats into two packed fp16x2 pieces each (round to nearest even at both levels): x = p1 + p2 up to ~2^-22.
+// fp16 rather than bf16 pieces: 11 + 11 mantissa bits instead of 8 + 8 at the same tensor-core cost; the values of this
+// network (Coulomb features <= 64 / r, swish activations, trained weights) sit well inside the fp16 range, and the
+// Coulomb features are clamped to +-65504 so that two colliding atoms cannot turn into inf (activations are not: an
+// activation that large means the walker is far outside anything the network was trained on).
+template <bool CLAMP = true>
 __device__ __forceinline__ void split2x2(float x0, float x1, uint32_t &p1, uint32_t &p2)
 {
-    __nv_bfloat162 b = __floats2bfloat162_rn(x0, x1);
+    if (CLAMP) {
+        x0 = fminf(fmaxf(x0, -65504.0f), 65504.0f);
+        x1 = fminf(fmaxf(x1, -65504.0f), 65504.0f);
+    }
+    __half2 b = __floats2half2_rn(x0, x1);
     p1 = *reinterpret_cast<uint32_t *>(&b);
-    const float r0 = x0 - __uint_as_float(p1 << 16), r1 = x1 - __uint_as_float(p1 & 0xFFFF0000u);
-    b = __floats2bfloat162_rn(r0, r1);
+    const float2 f = __half22float2(b);
+    b = __floats2half2_rn(x0 - f.x, x1 - f.y);
     p2 = *reinterpret_cast<uint32_t *>(&b);
 }
-__device__ __forceinline__ float swish_fast(float z) { return __fdividef(z, 1.0f + __expf(-z)); }
+// z * sigmoid(z) with the two SFU ops issued as single instructions (flush-to-zero forms: no denormal fix-up code around
+// them): 6 instructions per activation instead of the ~17 __expf / __fdividef expand to without -use_fast_math.
+__device__ __forceinline__ float swish_fast(float z)
+{
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * -1.4426950408889634f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return z * r;
+}
 // eight consecutive k values of one row -> one 16-byte store per piece
 __device__ __forceinline__ void store_chunk(unsigned char *sA, uint32_t off, const float (&h)[8])
 {
@@ -178,7 +196,7 @@ __device__ __forceinline__ void store_chunk(unsigned char *sA, uint32_t off, con
     *reinterpret_cast<uint4 *>(sA + 1 * TC_PIECE_BYTES_K128 + off) = make_uint4(b[0], b[1], b[2], b[3]);
 }
 
-// images: [L0 | L1 | L2] bf16 weight images (see host builder); vecs: b0[128] b1[128] b2[128] W3[128] b3
+// images: [L0 | L1 | L2] fp16 weight images (see host builder); vecs: b0[128] b1[128] b2[128] W3[128] b3
 // 512 threads: warp w owns TMEM lanes (walkers) 32*(w%4).. and the 32-column quarter w/4 of the 128 outputs,
 // i.e. four threads share a walker during the epilogues (4 warps per scheduler hide the TMEM / SFU latencies).
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -219,8 +237,8 @@ k_nn_h4o2_tc(const double *__restrict__ xyz, int soa, long long cap, const DevSt
         for (int q = 0; q < 2 * TC_NPIECE; ++q)
             bulk_load(smem_u32(sW + q * TC_PIECE_BYTES_K128), images + TC_IMG_L0 + q * TC_PIECE_BYTES_K128, TC_PIECE_BYTES_K128, w0_bar);
     }
-    // instruction descriptor: D = F32, A = B = BF16, K-major both, N = 128, M = 128
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+    // instruction descriptor: D = F32, A = B = F16 (format 0), K-major both, N = 128, M = 128
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
     const double zs[6] = {8.0, 1.0, 1.0, 8.0, 1.0, 1.0};
     uint32_t mma_phase = 0;
     const uint32_t row_off = (uint32_t)((row >> 3) * 128 + (row & 7) * 16);        // this walker's row inside a k-chunk
@@ -268,7 +286,7 @@ k_nn_h4o2_tc(const double *__restrict__ xyz, int soa, long long cap, const DevSt
                     for (int kb = 0; kb < kblocks; ++kb) {
                         const uint64_t da = umma_desc(smem_u32(sA + pa[term] * TC_PIECE_BYTES_K128 + kb * 4096));
                         const uint64_t db = umma_desc(smem_u32(wb + pb[term] * wpiece + kb * 4096));
-                        umma_bf16(tmem, da, db, idesc, accumulate);
+                        umma_f16(tmem, da, db, idesc, accumulate);
                         accumulate = 1;
                     }
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(mma_bar) : "memory");
@@ -316,27 +334,228 @@ k_nn_h4o2_tc(const double *__restrict__ xyz, int soa, long long cap, const DevSt
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(128));
 }
 
+// =====================================================================================================
+// Pipelined tcgen05 version: activations never touch shared memory.  The A operand of every layer lives in
+// TMEM (tcgen05.mma accepts A from tensor memory), written by the epilogue threads with tcgen05.st, so the
+// 64 KB activation buffer is gone and TWO tiles of 128 walkers are in flight per SM:
+//     TMEM columns [256 g, 256 g + 128)        fp32 accumulator of tile slot g        (g = 0, 1)
+//                  [256 g + 128 + 64 p, + 64)  fp16 piece p of the slot's activations (two fp16 per column)
+// Warps 0-7 own slot 0, warps 8-15 slot 1; each group has its own named barrier, its own MMA-completion
+// mbarrier and its own issuing thread, so while one group applies bias + swish on the CUDA cores the tensor
+// core works on the other group's layer.  Inside a group warp w owns TMEM lanes 32 (w % 4).. (one walker per
+// lane) and the 64-column half (w / 4) % 2 of the 128 outputs.
+// =====================================================================================================
+constexpr int TC2_TERMS = 3;                                  // cross terms issued: a1w1 + a1w2 + a2w1 (a2w2 ~ 2^-22, below the split residual;
+                                                              // measured: same error against float64 as with all four)
+constexpr size_t TC2_SMEM_BYTES = 2 * TC_IMG_L12 + TC_IMG_L0 + 64 + TC_VEC_FLOATS * 4 + 2 * 4 * 128 * 4;
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+                 :: "r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&r)[4])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+                 :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void tmem_st2(uint32_t taddr, const uint32_t (&r)[2])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" :: "r"(taddr), "r"(r[0]), "r"(r[1]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+}
+
+// THREADS = 512: a group is 8 warps, a thread drains 64 columns of its walker; THREADS = 1024: 16 warps, 32 columns.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
+k_nn_h4o2_tc2(const double *__restrict__ xyz, int soa, long long cap, const DevState *st, int parity, long long n_fixed,
+              const unsigned char *__restrict__ images, const float *__restrict__ vecs, double *__restrict__ v, int nterms)
+{
+    constexpr int GT = THREADS / 2;                                // threads per group (tile slot)
+    constexpr int NQ = GT / 128;                                   // column parts per walker: 2 or 4
+    constexpr int COLS = 128 / NQ;                                 // output columns per thread
+    constexpr int NFEAT = 16 / NQ;                                 // descriptor features per thread (padded 15 -> 16)
+    extern __shared__ __align__(1024) unsigned char tc_smem[];
+    unsigned char *sW = tc_smem;                                   // 2 x (2 pieces x 32 KB): weights of layers 1 and 2, resident
+    unsigned char *sW0 = tc_smem + 2 * TC_IMG_L12;                 // 8 KB: weights of layer 0, resident
+    uint64_t *bar = reinterpret_cast<uint64_t *>(sW0 + TC_IMG_L0);  // [0], [1]: MMA done (slot 0, 1); [2] weights landed
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sW0 + TC_IMG_L0 + 32);
+    float *s_vec = reinterpret_cast<float *>(sW0 + TC_IMG_L0 + 64);                 // biases, W3, b3
+    float *s_out = s_vec + TC_VEC_FLOATS;                                          // [slot][part][128 rows] partial outputs
+    const long long n = st ? st[parity].n : n_fixed;
+    if (st && st[parity].err) return;
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int g = t / GT;                                          // tile slot / thread group
+    const int part = ((t % GT) >> 7);                              // which COLS output columns this thread drains
+    const int row = (warp & 3) * 32 + lane;                        // walker of this thread inside the tile (== its TMEM lane)
+    const bool leader = (t % GT) == 0;
+    const uint32_t mma_bar = smem_u32(&bar[g]), w0_bar = smem_u32(&bar[2]);
+    if (t == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&bar[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&bar[1])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(w0_bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    for (int k = t; k < TC_VEC_FLOATS; k += THREADS) s_vec[k] = vecs[k];
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+    if (t == 0) {                                                  // all weights: loaded once per (persistent) CTA by the TMA engine
+        mbar_expect_tx(w0_bar, TC_IMG_TOTAL);
+        bulk_load(smem_u32(sW0), images, TC_IMG_L0, w0_bar);
+        for (int q = 0; q < 2 * TC_NPIECE; ++q)
+            bulk_load(smem_u32(sW + q * TC_PIECE_BYTES_K128), images + TC_IMG_L0 + q * TC_PIECE_BYTES_K128, TC_PIECE_BYTES_K128, w0_bar);
+    }
+    // instruction descriptor: D = F32, A = B = F16 (format 0), K-major both, N = 128, M = 128
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+    const double zs[6] = {8.0, 1.0, 1.0, 8.0, 1.0, 1.0};
+    const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;   // TMEM lane field of this warp
+    const uint32_t tD = tmem + (uint32_t)(256 * g);                // accumulator of this slot
+    const uint32_t tA = tD + 128u;                                 // activation pieces of this slot (64 columns each)
+    uint32_t mma_phase = 0;
+
+    for (long long base = ((long long)blockIdx.x * 2 + g) * TC_M; base < n; base += (long long)gridDim.x * 2 * TC_M) {
+        const long long i = base + row;
+        // ---- layer-0 A operand: Coulomb descriptor, 15 features + 1 zero pad; the parts of a walker share the features
+        {
+            float feat[NFEAT];
+#pragma unroll
+            for (int p = 0; p < NFEAT; ++p) feat[p] = 0.0f;
+            if (i < n) {
+                double c[18];
+#pragma unroll
+                for (int k = 0; k < 18; ++k) c[k] = soa ? xyz[k * cap + i] : xyz[i * 18 + k];
+                int p = 0;
+#pragma unroll
+                for (int a = 0; a < 6; ++a)
+#pragma unroll
+                    for (int b = a + 1; b < 6; ++b) {
+                        if (p / NFEAT == part) {
+                            const double dx = c[3 * a] - c[3 * b], dy = c[3 * a + 1] - c[3 * b + 1], dz = c[3 * a + 2] - c[3 * b + 2];
+                            feat[p % NFEAT] = (float)(zs[a] * zs[b] * rsqrt(dx * dx + dy * dy + dz * dz));
+                        }
+                        ++p;
+                    }
+            }
+            uint32_t w1[NFEAT / 2], w2[NFEAT / 2];
+#pragma unroll
+            for (int q = 0; q < NFEAT / 2; ++q) split2x2(feat[2 * q], feat[2 * q + 1], w1[q], w2[q]);
+            const uint32_t fa = tA + lane_sel + (uint32_t)(part * (NFEAT / 2));
+            if constexpr (NFEAT == 8) { tmem_st4(fa, w1); tmem_st4(fa + 64u, w2); }
+            else { tmem_st2(fa, w1); tmem_st2(fa + 64u, w2); }
+        }
+        float out = 0.0f;
+#pragma unroll 1
+        for (int layer = 0; layer < 3; ++layer) {
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");       // this thread's A stores have landed in TMEM
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            asm volatile("bar.sync %0, %1;" :: "r"(1 + g), "n"(GT) : "memory");
+            if (leader) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const int kblocks = layer == 0 ? 1 : 8;                        // K / 16
+                const unsigned char *wb = layer == 0 ? sW0 : sW + (layer - 1) * TC_IMG_L12;
+                const int wpiece = layer == 0 ? TC_PIECE_BYTES_K16 : TC_PIECE_BYTES_K128;
+                mbar_wait(w0_bar, 0);                                          // completes once; later waits return immediately
+                uint32_t accumulate = 0;
+                for (int term = 0; term < nterms; ++term) {                    // cross terms a1w1 + a1w2 + a2w1 (+ a2w2)
+                    const int pa = term >> 1, pb = term & 1;
+                    const uint64_t db0 = umma_desc(smem_u32(wb + pb * wpiece));
+                    for (int kb = 0; kb < kblocks; ++kb) {
+                        umma_f16_ts(tD, tA + (uint32_t)(pa * 64 + kb * 8), db0 + (uint64_t)(kb * (4096 >> 4)), idesc, accumulate);
+                        accumulate = 1;
+                    }
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(mma_bar) : "memory");
+            }
+            mbar_wait(mma_bar, mma_phase);
+            mma_phase ^= 1u;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            // ---- epilogue: this thread's TMEM lane, its COLS columns, 16 at a time, the next chunk's load in flight
+            const float *bias = s_vec + layer * 128;
+            uint32_t r[2][16];
+            tmem_ld16_nowait(tD + lane_sel + (uint32_t)(part * COLS), r[0]);
+#pragma unroll
+            for (int ch = 0; ch < COLS / 16; ++ch) {
+                const int col0 = part * COLS + ch * 16;
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (ch + 1 < COLS / 16) tmem_ld16_nowait(tD + lane_sel + (uint32_t)(col0 + 16), r[(ch + 1) & 1]);
+                float h[16];
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    h[e] = swish_fast(__uint_as_float(r[ch & 1][e]) + bias[col0 + e]);
+                    if (layer == 2) out = fmaf(h[e], s_vec[3 * 128 + col0 + e], out);
+                }
+                if (layer < 2) {
+                    uint32_t w1[8], w2[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) split2x2<false>(h[2 * q], h[2 * q + 1], w1[q], w2[q]);
+                    tmem_st8(tA + lane_sel + (uint32_t)(col0 >> 1), w1);
+                    tmem_st8(tA + 64u + lane_sel + (uint32_t)(col0 >> 1), w2);
+                }
+            }
+        }
+        // the column parts of a walker live in different warps of the group: combine through shared memory
+        s_out[(g * NQ + part) * 128 + row] = out;
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        asm volatile("bar.sync %0, %1;" :: "r"(1 + g), "n"(GT) : "memory");
+        if (part == 0 && i < n) {
+            float e = s_vec[3 * 128 + 128];                                     // b3
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) e += s_out[(g * NQ + q) * 128 + row];
+            v[i] = (double)(fmaxf(e, 0.0f) * 4.556335281212229e-6f);            // relu, cm-1 -> Hartree in float32 like the reference
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512));
+}
+
 // ---------------------------------------------------------------- host side: weight images + launch
 struct NNDeviceWeights {
     float *packed = nullptr;            // raw packed float32 weights (CUDA-core kernel)
-    unsigned char *images = nullptr;    // bf16-split, core-matrix formatted weight images (tcgen05 kernel)
+    unsigned char *images = nullptr;    // fp16-split, core-matrix formatted weight images (tcgen05 kernel)
     float *vecs = nullptr;              // biases, W3, b3
 };
 
-static inline unsigned short host_bf16_rn(float x)
+static inline unsigned short host_f16_rn(float x)
 {
-    uint32_t u;
-    memcpy(&u, &x, 4);
-    if ((u & 0x7F800000u) == 0x7F800000u) return (unsigned short)(u >> 16);
-    u += 0x7FFFu + ((u >> 16) & 1u);
-    return (unsigned short)(u >> 16);
+    const __half h = __float2half_rn(x);
+    unsigned short u;
+    memcpy(&u, &h, 2);
+    return u;
 }
-static inline float host_bf16_to_f(unsigned short h)
+static inline float host_f16_to_f(unsigned short u)
 {
-    uint32_t u = (uint32_t)h << 16;
-    float f;
-    memcpy(&f, &u, 4);
-    return f;
+    __half h;
+    memcpy(&h, &u, 2);
+    return __half2float(h);
 }
 
 // images of the B operands: B[n][k] = W[k][n] (K-major), N padded to 128, K padded to 16 / 128
@@ -352,9 +571,9 @@ static void nn_build_images(const float *P, std::vector<unsigned char> &img, std
         for (int n = 0; n < NN_H; ++n)
             for (int k = 0; k < kreal[l]; ++k) {
                 const float w = P[woff[l] + k * NN_H + n];
-                const unsigned short h1 = host_bf16_rn(w);
-                const float r1 = w - host_bf16_to_f(h1);
-                const unsigned short h2 = host_bf16_rn(r1);
+                const unsigned short h1 = host_f16_rn(w);
+                const float r1 = w - host_f16_to_f(h1);
+                const unsigned short h2 = host_f16_rn(r1);
                 const size_t off = (size_t)(k / 8) * 2048 + (size_t)(n / 8) * 128 + (size_t)(n % 8) * 16 + (size_t)(k % 8) * 2;
                 const unsigned short hs[TC_NPIECE] = {h1, h2};
                 for (int p = 0; p < TC_NPIECE; ++p) memcpy(&img[base + p * piece + off], &hs[p], 2);
@@ -392,6 +611,8 @@ static int nn_prepare_launch()
     if (!done) {
         PVD_CUDA(cudaFuncSetAttribute(k_nn_h4o2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NN_SMEM_BYTES));
         PVD_CUDA(cudaFuncSetAttribute(k_nn_h4o2_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+        PVD_CUDA(cudaFuncSetAttribute(k_nn_h4o2_tc2<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC2_SMEM_BYTES));
+        PVD_CUDA(cudaFuncSetAttribute(k_nn_h4o2_tc2<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC2_SMEM_BYTES));
         done = true;
     }
     return PVD_OK;
@@ -411,9 +632,22 @@ static int nn_launch(cudaStream_t stream, const double *x, int soa, long long ca
         if (g > 3ll * sms) g = 3ll * sms;
         k_nn_h4o2<<<(int)(g < 1 ? 1 : g), NN_THREADS, NN_SMEM_BYTES, stream>>>(x, soa, cap, st, parity, n_fixed, w.packed, v, nullptr);
     } else {
-        long long g = (n_upper + TC_M - 1) / TC_M;
-        if (g > sms) g = sms;                                    // persistent: one CTA per SM (192 KB of shared memory each)
-        k_nn_h4o2_tc<<<(int)(g < 1 ? 1 : g), TC_THREADS, TC_SMEM_BYTES, stream>>>(x, soa, cap, st, parity, n_fixed, w.images, w.vecs, v);
+        const char *e1 = getenv("PVD_NN_TC1");                   // previous generation (activations through shared memory), for A/B runs
+        if (e1 && e1[0] == '1') {
+            long long g = (n_upper + TC_M - 1) / TC_M;
+            if (g > sms) g = sms;                                // persistent: one CTA per SM (192 KB of shared memory each)
+            k_nn_h4o2_tc<<<(int)(g < 1 ? 1 : g), TC_THREADS, TC_SMEM_BYTES, stream>>>(x, soa, cap, st, parity, n_fixed, w.images, w.vecs, v);
+        } else {
+            long long g = (n_upper + 2 * TC_M - 1) / (2 * TC_M);
+            if (g > sms) g = sms;                                // persistent: one CTA per SM (all 512 TMEM columns), two tiles in flight
+            const char *et = getenv("PVD_NN_TERMS");
+            const int nterms = (et && (et[0] == '3' || et[0] == '4')) ? et[0] - '0' : TC2_TERMS;
+            const char *eth = getenv("PVD_NN_THREADS");
+            if (eth && atoi(eth) == 1024)                        // measured: 2.77e9 walkers/s vs 2.88e9 with 512 threads
+                k_nn_h4o2_tc2<1024><<<(int)(g < 1 ? 1 : g), 1024, TC2_SMEM_BYTES, stream>>>(x, soa, cap, st, parity, n_fixed, w.images, w.vecs, v, nterms);
+            else
+                k_nn_h4o2_tc2<512><<<(int)(g < 1 ? 1 : g), 512, TC2_SMEM_BYTES, stream>>>(x, soa, cap, st, parity, n_fixed, w.images, w.vecs, v, nterms);
+        }
     }
     PVD_CHECK_LAUNCH();
     return PVD_OK;
