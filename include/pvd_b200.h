@@ -209,6 +209,11 @@ int pvd_sim_sums_ptr(pvd_sim *s, void **device_ptr);
 int pvd_sim_set_sums_ptr(pvd_sim *s, void *device_ptr);
 int pvd_sim_step_local(pvd_sim *s, int32_t do_branch);
 int pvd_sim_step_finalize(pvd_sim *s);
+/* importance sampling across shards: the acceptance fraction that scales the time step (pyvibdmc.py:372-378, 603) is
+ * global, so the local step is cut after the Metropolis move:
+ *   pvd_sim_imp_move_local -> all-reduce(sums) -> pvd_sim_imp_branch_local -> all-reduce(sums) -> pvd_sim_step_finalize */
+int pvd_sim_imp_move_local(pvd_sim *s);
+int pvd_sim_imp_branch_local(pvd_sim *s, int32_t do_branch);
 
 /* descendant weighting (pyvibdmc.py:739-747, 663-672, 856-869) */
 int pvd_sim_dw_begin(pvd_sim *s, int64_t global_offset);

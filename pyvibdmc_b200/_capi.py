@@ -95,6 +95,8 @@ SIGNATURES = {
     "pvd_sim_set_sums_ptr": (C.c_int, [_P, _P]),
     "pvd_sim_step_local": (C.c_int, [_P, _I32]),
     "pvd_sim_step_finalize": (C.c_int, [_P]),
+    "pvd_sim_imp_move_local": (C.c_int, [_P]),
+    "pvd_sim_imp_branch_local": (C.c_int, [_P, _I32]),
     "pvd_sim_dw_begin": (C.c_int, [_P, _I64]),
     "pvd_sim_dw_end": (C.c_int, [_P, _P, _I64]),
     "pvd_sim_dw_parent": (C.c_int, [_P, _P, _P, C.POINTER(_I64)]),

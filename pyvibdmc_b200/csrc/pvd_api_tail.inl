@@ -206,7 +206,7 @@ extern "C" int pvd_sim_set_trial_table(pvd_sim *s, const double *table, int64_t 
         else return pvd_fail(PVD_E_ARG, "unsupported built-in (trial, potential) combination");                             \
     } while (0)
 
-static int imp_initial_drift(pvd_sim *s)
+static int imp_initial_drift(pvd_sim *s, long long first, long long count)
 {
     ImpArgs im;
     if (int rc = fill_trial_params(s, im)) return rc;
@@ -214,14 +214,14 @@ static int imp_initial_drift(pvd_sim *s)
     const int g = s->grid;
     double *x = s->x[s->cur].as<double>(), *f = s->f[s->cur].as<double>(), *psi = s->psi[s->cur].as<double>();
     double *lk = s->lk[s->cur].as<double>(), *v = s->v[s->cur].as<double>();
-#define CALL_INIT(T, P) k_imp_init<T, P><<<g, PVD_CTA, 0, s->stream>>>(a, im, x, f, psi, lk, v)
+#define CALL_INIT(T, P) k_imp_init<T, P><<<g, PVD_CTA, 0, s->stream>>>(a, im, x, f, psi, lk, v, first, count)
     IMP_DISPATCH(CALL_INIT);
 #undef CALL_INIT
     PVD_CHECK_LAUNCH();
     return PVD_OK;
 }
 
-static int imp_enqueue_step(pvd_sim *s, StepArgs &a, const double *inj_um)
+static int imp_enqueue_move(pvd_sim *s, StepArgs &a, const double *inj_um)
 {
     ImpArgs im;
     if (int rc = fill_trial_params(s, im)) return rc;
@@ -244,6 +244,11 @@ static int imp_enqueue_step(pvd_sim *s, StepArgs &a, const double *inj_um)
     IMP_DISPATCH(CALL_MOVE);
 #undef CALL_MOVE
     PVD_CHECK_LAUNCH();
+    return PVD_OK;
+}
+
+static int imp_enqueue_branch(pvd_sim *s, StepArgs &a)
+{
     if (s->cfg.weighting == PVD_WEIGHT_CONTINUOUS) return cont_enqueue_branch_only(s, a);
     // discrete: branch on E_L with the effective time step, carrying f_x, psi and the local kinetic energy
     k_branch_discrete<<<s->grid_light, PVD_CTA, 0, s->stream>>>(a);
@@ -252,7 +257,39 @@ static int imp_enqueue_step(pvd_sim *s, StepArgs &a, const double *inj_um)
     return PVD_OK;
 }
 
+static int imp_enqueue_step(pvd_sim *s, StepArgs &a, const double *inj_um)
+{
+    if (int rc = imp_enqueue_move(s, a, inj_um)) return rc;
+    return imp_enqueue_branch(s, a);
+}
+
 extern "C" {
+
+// multi-GPU importance sampling: the acceptance fraction that scales the time step (pyvibdmc.py:372-378, 603) is global,
+// so the step is cut after the Metropolis move: move -> all-reduce of `sums` -> branch -> all-reduce -> finalize
+int pvd_sim_imp_move_local(pvd_sim *s)
+{
+    SIM_CHECK(s);
+    SIM_DEVICE(s);
+    PVD_REQUIRE(s->uploaded && s->cfg.trial != PVD_TRIAL_NONE, "pvd_sim_imp_move_local: needs an importance-sampled simulation with walkers");
+    StepArgs a = make_args(s, 1);
+    return imp_enqueue_move(s, a, nullptr);
+}
+
+int pvd_sim_imp_branch_local(pvd_sim *s, int32_t do_branch)
+{
+    SIM_CHECK(s);
+    SIM_DEVICE(s);
+    PVD_REQUIRE(s->uploaded && s->cfg.trial != PVD_TRIAL_NONE, "pvd_sim_imp_branch_local: needs an importance-sampled simulation with walkers");
+    StepArgs a = make_args(s, do_branch);
+    if (s->cfg.world_size > 1) {
+        k_imp_set_dt<<<1, 32, 0, s->stream>>>(s->st.as<DevState>(), s->parity, a.sums, s->cfg.delta_t);
+        PVD_CHECK_LAUNCH();
+    }
+    if (int rc = imp_enqueue_branch(s, a)) return rc;
+    s->parity ^= 1;
+    return PVD_OK;
+}
 
 int pvd_sim_download_imp(pvd_sim *s, double *fx, double *psi, double *sec, int64_t capacity)
 {
@@ -427,6 +464,9 @@ int pvd_sim_import(pvd_sim *s, int64_t count, const double *xyz, const double *p
         for (int64_t i = 0; i < count; ++i) w32[(size_t)i] = (int)who[i];
         PVD_CUDA(cudaMemcpy(s->who[s->cur].as<int>() + n, w32.data(), (size_t)count * 4, cudaMemcpyHostToDevice));
     }
+    // importance sampling: drift, psi and local kinetic energy are functions of the coordinates alone: rebuild them
+    if (s->cfg.trial != PVD_TRIAL_NONE && count > 0)
+        if (int rc = imp_initial_drift(s, n, count)) return rc;
     PVD_CUDA(cudaStreamSynchronize(s->stream));
     h[1 - s->parity] = h[s->parity];
     h[0].n = n + count; h[1].n = n + count;

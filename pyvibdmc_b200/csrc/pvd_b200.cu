@@ -350,7 +350,9 @@ static StepArgs make_args(pvd_sim *s, int do_branch)
 static int cont_enqueue_step(pvd_sim *, StepArgs &);
 static int cont_enqueue_branch_only(pvd_sim *, StepArgs &, long long *src_out = nullptr);
 static int imp_enqueue_step(pvd_sim *, StepArgs &, const double *);
-static int imp_initial_drift(pvd_sim *);
+static int imp_enqueue_move(pvd_sim *, StepArgs &, const double *);
+static int imp_enqueue_branch(pvd_sim *, StepArgs &);
+static int imp_initial_drift(pvd_sim *, long long first = 0, long long count = -1);
 static int nn_enqueue_discrete_step(pvd_sim *, StepArgs &);
 
 #define SIM_CHECK(s) PVD_REQUIRE((s) != nullptr, "NULL simulation handle")

@@ -221,11 +221,13 @@ struct ImpArgs {
 // first-step exception with importance sampling (pyvibdmc.py:553-554, 760-769): drift on the start
 // ensemble, E_L = V + local kinetic energy.
 template <class TRIAL, class POT>
-__global__ void __launch_bounds__(PVD_CTA, 2) k_imp_init(const StepArgs a, const ImpArgs im, double *x, double *f, double *psi, double *lk, double *v)
+__global__ void __launch_bounds__(PVD_CTA, 2) k_imp_init(const StepArgs a, const ImpArgs im, double *x, double *f, double *psi, double *lk, double *v,
+                                                         long long first, long long count)
 {
     constexpr int NC = TRIAL::NC;
-    const long long n = a.st[a.parity].n;
-    for (long long i = blockIdx.x * (long long)PVD_CTA + threadIdx.x; i < n; i += (long long)gridDim.x * PVD_CTA) {
+    // count < 0: the whole shard; else the walkers [first, first + count) (walkers received from another shard)
+    const long long n = count < 0 ? a.st[a.parity].n : first + count;
+    for (long long i = (count < 0 ? 0 : first) + blockIdx.x * (long long)PVD_CTA + threadIdx.x; i < n; i += (long long)gridDim.x * PVD_CTA) {
         double xx[NC], d1[NC], d2[NC], p0;
 #pragma unroll
         for (int c = 0; c < NC; ++c) xx[c] = x[c * a.cap + i];
@@ -322,6 +324,7 @@ __global__ void __launch_bounds__(PVD_CTA, 2) k_imp_move(const StepArgs a, const
             const unsigned long long nacc = atomicAdd(im.acc_count, 0ull);
             sip->n_accept = (long long)nacc;
             if (a.world == 1) sip->dt_eff = __dmul_rn(a.dt, (double)nacc / (double)n);
+            else { a.sums[0] = (double)nacc; a.sums[1] = (double)n; }          // reduced over the shards, then k_imp_set_dt
             sip->done = 0u;
             *im.acc_count = 0ull;
         }
@@ -331,7 +334,10 @@ __global__ void __launch_bounds__(PVD_CTA, 2) k_imp_move(const StepArgs a, const
 // multi-GPU: dt_eff from the globally reduced acceptance count (sums[0] = n_accept, sums[1] = n)
 __global__ void k_imp_set_dt(DevState *st, int parity, const double *sums, double dt)
 {
-    if (blockIdx.x == 0 && threadIdx.x == 0) st[parity].dt_eff = __dmul_rn(dt, sums[0] / sums[1]);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        st[parity].dt_eff = __dmul_rn(dt, sums[0] / sums[1]);
+        st[parity].n_accept = (long long)sums[0];
+    }
 }
 
 // ---------------------------------------------------------------- stand-alone entry points (AoS host layout)

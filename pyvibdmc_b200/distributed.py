@@ -57,7 +57,7 @@ class ShardedSim:
 
     def __init__(self, natoms, ndim, masses, num_walkers, delta_t, potential, weighting="discrete", seed=0,
                  rng_mode=_capi.RNG_FP64, pot_params=None, thresh_lower=None, thresh_upper=None, rebalance_every=250,
-                 capacity=None, stats_ring=1 << 14):
+                 capacity=None, stats_ring=1 << 14, trial=_capi.TRIAL_NONE, trial_table=None):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
@@ -71,9 +71,14 @@ class ShardedSim:
         self.sim = kernels.DeviceSim(natoms, ndim, masses, num_walkers, delta_t, potential, weighting=weighting,
                                      seed=int(seed) + 1000003 * self.rank, rng_mode=rng_mode, pot_params=pot_params,
                                      thresh_lower=thresh_lower, thresh_upper=thresh_upper, device=self.local_rank,
-                                     rank=self.rank, world_size=self.world,
+                                     rank=self.rank, world_size=self.world, trial=trial,
                                      capacity=capacity or int(1.6 * local) + 4096, stats_ring=stats_ring)
         self.sim.set_stream(self.stream.cuda_stream)
+        self.imp = trial != _capi.TRIAL_NONE
+        if self.imp:
+            if weighting != "discrete":
+                raise NotImplementedError("sharded importance sampling is built for discrete weighting")
+            self.sim.set_trial_table(trial_table)
         self.sums = torch.zeros(_capi.NSUMS, dtype=torch.float64, device=self.device)
         self.sim.set_sums_ptr(self.sums.data_ptr())
         self.rebalance_every = int(rebalance_every)
@@ -90,7 +95,13 @@ class ShardedSim:
         with self.torch.cuda.stream(self.stream):
             for _ in range(int(nsteps)):
                 do_branch = 1 if branch_every == 1 else -int(branch_every)
-                self.sim.step_local(do_branch)
+                if self.imp:
+                    # the acceptance fraction that scales dt is global (pyvibdmc.py:372-378): one more tiny all-reduce
+                    self.sim.imp_move_local()
+                    self.dist.all_reduce(self.sums)
+                    self.sim.imp_branch_local(do_branch)
+                else:
+                    self.sim.step_local(do_branch)
                 self.dist.all_reduce(self.sums)
                 self.sim.step_finalize()
                 self.steps_done += 1
@@ -124,6 +135,30 @@ class ShardedSim:
                 w = np.ascontiguousarray(p[:, nc + 1]); who = np.ascontiguousarray(p[:, nc + 2]).astype(np.int64)
                 _capi.check(_capi.lib.pvd_sim_import(self.sim._h, count, _capi.ptr(xyz), _capi.ptr(pots), _capi.ptr(w), _capi.ptr(who)))
         return moves
+
+    # -- descendant weighting across shards: who_from holds GLOBAL parent ids (rank-major order)
+    def dw_begin(self):
+        """Open a descendant-weighting window (pyvibdmc.py:739-747); returns (global offset of this shard's parents, N_parent)."""
+        pops = self.populations()
+        offset = sum(pops[:self.rank])
+        with self.torch.cuda.stream(self.stream):
+            self.sim.dw_begin(offset)
+        self._dw_total = sum(pops)
+        return offset, self._dw_total
+
+    def dw_end(self):
+        """Close the window: descendant weights of ALL parents, identical on every rank (pyvibdmc.py:663-672, 856-869)."""
+        torch = self.torch
+        with torch.cuda.stream(self.stream):
+            local = self.sim.dw_end(self._dw_total)
+            t = torch.from_numpy(local).to(self.device)
+            self.dist.all_reduce(t)
+        self.stream.synchronize()
+        return t.cpu().numpy()
+
+    def dw_parent(self):
+        """This shard's slice of the parent ensemble (coords, weights or None); concatenate in rank order for the global one."""
+        return self.sim.dw_parent()
 
     def state(self):
         return self.sim.state()

@@ -295,6 +295,12 @@ class DeviceSim:
     def step_finalize(self):
         check(lib.pvd_sim_step_finalize(self._h))
 
+    def imp_move_local(self):
+        check(lib.pvd_sim_imp_move_local(self._h))
+
+    def imp_branch_local(self, do_branch=1):
+        check(lib.pvd_sim_imp_branch_local(self._h, int(do_branch)))
+
     # -- descendant weighting
     def dw_begin(self, global_offset=0):
         check(lib.pvd_sim_dw_begin(self._h, int(global_offset)))

@@ -35,12 +35,45 @@ def main():
     dist.all_reduce(hmax, op=dist.ReduceOp.MAX)
     dist.all_reduce(hmin, op=dist.ReduceOp.MIN)
     same = bool(torch.equal(hmax, hmin))
+    # ---- descendant weighting across shards: weights of all parents sum to the global population at window end
+    off, n_par = sim.dw_begin()
+    sim.run(60)
+    dw = sim.dw_end()
+    pops_dw = sim.populations()
+    par_xyz, _ = sim.dw_parent()
+    dw_ok = bool(len(dw) == n_par and abs(dw.sum() - sum(pops_dw)) < 0.5 and (dw >= 0).all() and (dw == np.round(dw)).all())
+    npar_local = torch.tensor([len(par_xyz)], device=sim.device)
+    dist.all_reduce(npar_local)
+    dw_ok = dw_ok and int(npar_local.item()) == n_par
+    sim.close()
+
+    # ---- importance sampling across shards (global acceptance fraction -> dt_eff)
+    import importlib.util
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "pyvibdmc_b200", "sample_potentials", "FortPots", "Partridge_Schwenke_H2O")
+    spec = importlib.util.spec_from_file_location("call_trl_h2o_b200", os.path.join(d, "call_trl_h2o.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    n1, T1 = 8000, 300
+    imp = ShardedSim(3, 3, masses, n1, 1.0, _capi.POT_H2O_PS, seed=23, rebalance_every=100, trial=_capi.TRIAL_H2O_FD, trial_table=mod.packed_table())
+    s1, c1 = shard_bounds(n1, world)[rank]
+    imp.upload(np.repeat(eq[None] * 1.01, c1, axis=0))
+    imp.run(T1)
+    torch.cuda.synchronize()
+    ist = imp.stats(0, T1)
+    h2 = torch.tensor(np.concatenate([ist["vref"], ist["pop"], ist["dt_eff"]]), device=imp.device)
+    h2max, h2min = h2.clone(), h2.clone()
+    dist.all_reduce(h2max, op=dist.ReduceOp.MAX)
+    dist.all_reduce(h2min, op=dist.ReduceOp.MIN)
+    imp_same = bool(torch.equal(h2max, h2min))
+    imp_out = {"same": imp_same, "zpe": float(ist["vref"][T1 // 2:].mean() / 4.556335281212229e-6), "dt_eff_mean": float(ist["dt_eff"][5:].mean()),
+               "pop_last": float(ist["pop"][-1]), "rejected_mean": float(ist["rejected"][5:].mean())}
+    imp.close()
+    sim = None
     if rank == 0:
-        out = {"world": world, "step": st["step"], "pops": pops, "global_pop_last": float(stats["pop"][-1]), "same_on_all_ranks": same,
+        out = {"world": world, "dw_ok": dw_ok, "imp": imp_out, "step": st["step"], "pops": pops, "global_pop_last": float(stats["pop"][-1]), "same_on_all_ranks": same,
                "zpe": float(stats["vref"][T // 2:].mean() / 4.556335281212229e-6), "births_minus_deaths_ok":
                bool(np.array_equal(np.diff(stats["pop"]), (stats["births"] - stats["deaths"])[1:]))}
         print("RESULT " + json.dumps(out))
-    sim.close()
     dist.destroy_process_group()
 
 
