@@ -218,6 +218,10 @@ int pvd_sim_imp_branch_local(pvd_sim *s, int32_t do_branch);
 /* descendant weighting (pyvibdmc.py:739-747, 663-672, 856-869) */
 int pvd_sim_dw_begin(pvd_sim *s, int64_t global_offset);
 int pvd_sim_dw_end(pvd_sim *s, double *desc_wts, int64_t n_parent);
+/* calc_desc_wts without closing the window (DEBUG_save_desc_wt_tracker, pyvibdmc.py:849-852) */
+int pvd_sim_dw_peek(pvd_sim *s, double *desc_wts, int64_t n_parent);
+/* DEBUG_mass_change (pyvibdmc.py:749-753): sigma = sqrt(dt / m) from new masses */
+int pvd_sim_set_masses(pvd_sim *s, const double *masses, int32_t natoms);
 int pvd_sim_dw_parent(pvd_sim *s, double *xyz, double *w, int64_t *n_parent);
 
 /* blocking queries */

@@ -99,6 +99,8 @@ SIGNATURES = {
     "pvd_sim_imp_branch_local": (C.c_int, [_P, _I32]),
     "pvd_sim_dw_begin": (C.c_int, [_P, _I64]),
     "pvd_sim_dw_end": (C.c_int, [_P, _P, _I64]),
+    "pvd_sim_dw_peek": (C.c_int, [_P, _P, _I64]),
+    "pvd_sim_set_masses": (C.c_int, [_P, _P, _I32]),
     "pvd_sim_dw_parent": (C.c_int, [_P, _P, _P, C.POINTER(_I64)]),
     "pvd_sim_sync": (C.c_int, [_P]),
     "pvd_sim_state": (C.c_int, [_P, C.POINTER(_I64), C.POINTER(_F64), C.POINTER(_I64), C.POINTER(_I32)]),

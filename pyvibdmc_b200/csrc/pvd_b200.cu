@@ -808,7 +808,29 @@ int pvd_sim_dw_begin(pvd_sim *s, int64_t global_offset)
     return PVD_OK;
 }
 
-int pvd_sim_dw_end(pvd_sim *s, double *desc_wts, int64_t n_parent)
+static int dw_collect(pvd_sim *s, double *desc_wts, int64_t n_parent, bool close_window);
+int pvd_sim_dw_end(pvd_sim *s, double *desc_wts, int64_t n_parent) { return dw_collect(s, desc_wts, n_parent, true); }
+/* calc_desc_wts without closing the window (DEBUG_save_desc_wt_tracker, pyvibdmc.py:849-852) */
+int pvd_sim_dw_peek(pvd_sim *s, double *desc_wts, int64_t n_parent) { return dw_collect(s, desc_wts, n_parent, false); }
+
+/* DEBUG_mass_change (pyvibdmc.py:749-753): new masses -> new displacement widths sigma = sqrt(dt / m); like the reference,
+ * nothing else (the importance-sampling 1/m factors keep their initial values) */
+int pvd_sim_set_masses(pvd_sim *s, const double *masses, int32_t natoms)
+{
+    SIM_CHECK(s);
+    SIM_DEVICE(s);
+    PVD_REQUIRE(masses && natoms == s->cfg.natoms, "pvd_sim_set_masses: one mass per atom");
+    for (int a = 0; a < natoms; ++a) {
+        PVD_REQUIRE(masses[a] > 0.0, "masses must be positive");
+        s->cfg.masses[a] = masses[a];
+        s->sigma[a] = sqrt(s->cfg.delta_t / masses[a]);
+    }
+    PVD_CUDA(cudaMemcpyAsync(s->sigma_dev.p, s->sigma, PVD_MAX_ATOMS * 8, cudaMemcpyHostToDevice, s->stream));
+    PVD_CUDA(cudaStreamSynchronize(s->stream));
+    return PVD_OK;
+}
+
+static int dw_collect(pvd_sim *s, double *desc_wts, int64_t n_parent, bool close_window)
 {
     SIM_CHECK(s);
     SIM_DEVICE(s);
@@ -824,10 +846,12 @@ int pvd_sim_dw_end(pvd_sim *s, double *desc_wts, int64_t n_parent)
                                                s->stage2.as<double>());
     PVD_CHECK_LAUNCH();
     PVD_CUDA(cudaMemcpyAsync(desc_wts, s->stage2.p, (size_t)n_parent * 8, cudaMemcpyDeviceToHost, s->stream));
-    h[0].dw_active = 0;
-    h[1].dw_active = 0;
     PVD_CUDA(cudaStreamSynchronize(s->stream));
-    PVD_CUDA(cudaMemcpy(s->st.p, h, sizeof(h), cudaMemcpyHostToDevice));
+    if (close_window) {
+        h[0].dw_active = 0;
+        h[1].dw_active = 0;
+        PVD_CUDA(cudaMemcpy(s->st.p, h, sizeof(h), cudaMemcpyHostToDevice));
+    }
     return PVD_OK;
 }
 

@@ -31,7 +31,7 @@ __all__ = ['DMC_Sim', 'dmc_restart']
 
 MASSIVE = "Massive walker birth or death event!!!!!!! Dying..."
 _NOT_PICKLED = ('potential', 'potential_info', 'impsamp_manager', 'impsamp', 'imp_info', 'adiabatic_dmc', 'ad_obs_func',
-                '_dev', '_potential_obj')
+                'fixed_node', 'fixed_node_func', 'g_mat', '_dev', '_potential_obj')
 
 
 class DMC_Sim:
@@ -81,13 +81,19 @@ class DMC_Sim:
         self._rng_mode = _capi.RNG_FAST if rng == 'fast' else _capi.RNG_FP64
         self._device = int(device)
         self._dev = None
-        # variants of the loop that are outside this implementation's scope
+        self._host_rng = np.random.default_rng(self._seed ^ 0x5DEECE66D)      # fixed-node recrossing draws (host side)
+        # variants of the importance-sampling move that have no device kernel yet
         for name, val in (("second_impsamp_displacement", second_impsamp_displacement),
-                          ("excited_state_imp_samp", excited_state_imp_samp), ("adiabatic_dmc", adiabatic_dmc),
-                          ("fixed_node", fixed_node), ("DEBUG_save_desc_wt_tracker", DEBUG_save_desc_wt_tracker),
-                          ("DEBUG_save_training_every", DEBUG_save_training_every), ("DEBUG_mass_change", DEBUG_mass_change)):
+                          ("excited_state_imp_samp", excited_state_imp_samp)):
             if val:
                 raise NotImplementedError(f"{name} is not implemented on the B200 path")
+        # variants that call back into user Python once per step run in the per-step (hosted) mode:
+        # the GPU moves, weights and branches; the host sees the coordinates like a user potential would
+        self._hooked = bool(adiabatic_dmc is not None or fixed_node is not None
+                            or (DEBUG_save_training_every is not None and DEBUG_save_before_bod))
+        if self._hooked and imp_samp is not None:
+            raise NotImplementedError("adiabatic_dmc / fixed_node / DEBUG_save_before_bod together with importance sampling "
+                                      "are not implemented on the B200 path")
         self._initialize()
 
     # ------------------------------------------------------------------ set-up (pyvibdmc.py:132-297)
@@ -98,7 +104,10 @@ class DMC_Sim:
         self._chkpt_step = np.arange(self.chkpt_every, T + self.chkpt_every, self.chkpt_every)
         self._wfn_save_step = np.arange(self.equil_steps, T + self.wfn_every, self.wfn_every)
         self._desc_wt_save_step = self._wfn_save_step + self.desc_wt_time_steps
-        self.deb_train_save_step = []
+        if self._deb_training_every is not None:                                   # pyvibdmc.py:143-147
+            self.deb_train_save_step = np.arange(0, T + self._deb_training_every, self._deb_training_every)
+        else:
+            self.deb_train_save_step = []
         self._log_steps = np.arange(0, T, self.log_every)
 
     def _initialize(self):
@@ -166,7 +175,28 @@ class DMC_Sim:
         else:
             self._cont_wts = None
         self._desc_wt = False
-        self._mass_change_steps = []
+        # Mass change throughout simulation (pyvibdmc.py:236-247)
+        if self._deb_mass_change is not None:
+            change_every = self._deb_mass_change['change_every']
+            self._mass_change_steps = np.arange(0, self.num_timesteps, change_every)[1:]
+            self._factor_per_change = self._deb_mass_change['factor_per_change']
+            if isinstance(self._factor_per_change, (int, float)):
+                self._factor_per_change = np.repeat(self._factor_per_change, len(self._mass_change_steps))
+            if len(self._factor_per_change) != len(self._mass_change_steps):
+                raise ValueError("Number of mass change steps must be equal to mass changes you provide.")
+            self._mass_counter = 0
+        else:
+            self._mass_change_steps = []
+        if self.adiabatic_dmc is not None:                                         # pyvibdmc.py:276-291
+            ad_lam = self.adiabatic_dmc['initial_lambda']
+            ad_lam_dx = self.adiabatic_dmc['lambda_change']
+            ad_eq_time = self.adiabatic_dmc['equil_time']
+            self.ad_obs_func = self.adiabatic_dmc['observable_func']
+            self.ad_lam_array = np.concatenate((np.zeros(ad_eq_time),
+                                                np.arange(ad_lam, ad_lam + (ad_lam_dx * (self.num_timesteps - ad_eq_time)), ad_lam_dx)))
+        if self.fixed_node is not None:                                            # pyvibdmc.py:292-294
+            self.fixed_node_func = self.fixed_node['function']
+            self.g_mat = self.fixed_node['g_matrix']
         self._pop_thresh = [self.num_walkers - self.num_walkers * 0.5, self.num_walkers + self.num_walkers * 0.5]
 
         if 'num_mpi' in self.potential_info.keys():
@@ -222,6 +252,8 @@ class DMC_Sim:
     # ------------------------------------------------------------------ device plumbing
     def _specs(self):
         pot = getattr(self._potential_obj, 'gpu_spec', lambda: None)() if self._potential_obj is not None else None
+        if getattr(self, '_hooked', False):
+            pot = None                 # per-step mode: the plug-in's getpot is called like any user potential
         trial = None
         if self.impsamp_manager is not None:
             trial = getattr(self.impsamp_manager, 'gpu_spec', lambda: None)()
@@ -333,8 +365,11 @@ class DMC_Sim:
         chk, wfn = set(int(s) for s in self._chkpt_step), set(int(s) for s in self._wfn_save_step)
         dw_end = set(int(s) for s in self._desc_wt_save_step)
         # host-side events: start-of-step {chkpt, wfn window opens}, end-of-step {window closes after step t: t+1 in dw_end}
-        starts = sorted(s for s in (chk | wfn) if first <= s < T)
-        ends = sorted(s for s in dw_end if first < s <= T)
+        mass_steps = set(int(s) for s in self._mass_change_steps)
+        train = set(int(s) for s in self.deb_train_save_step) if not self._deb_save_before_bod else set()
+        starts = sorted(s for s in (chk | wfn | mass_steps) if first <= s < T)
+        ends = sorted(set(s for s in dw_end if first < s <= T) | set(s + 1 for s in train if first <= s < T))
+        self._desc_wt_history = []
         t = first
         self._logger.write_beginning(self.__dict__) if first < T else None
         while t < T:
@@ -354,7 +389,14 @@ class DMC_Sim:
                 dev.dw_begin()
                 self._desc_wt = True
                 self._dw_n_parent = n_now
+            if t in mass_steps:                                                    # pyvibdmc.py:749-753
+                self.masses = self.masses * self._factor_per_change[self._mass_counter]
+                self._sigmas = np.sqrt(self.delta_t / self.masses)
+                self._mass_counter += 1
+                dev.set_masses(self.masses)
             nxt = min([s for s in starts if s > t] + [s for s in ends if s > t] + [T])
+            if self._desc_wt and self._deb_desc_wt_tracker:
+                nxt = t + 1                                                        # the tracker records the weights after every step
             tic = time.time()
             if self._builtin:
                 dev.run(nxt - t, self.branch_every)
@@ -366,6 +408,13 @@ class DMC_Sim:
             if nxt in dw_end and self._desc_wt:
                 events["desc"] = True
             self._drain(t, nxt - t, events)
+            if (nxt - 1) in train:                                                 # training data after birth/death (pyvibdmc.py:840-845)
+                out = dev.download()
+                print(f'{out["coords"].shape} walkers collected')
+                SimArchivist.save_h5(fname=f"{self.output_folder}/{self.sim_name}_training_{nxt - 1}ts.hdf5",
+                                     keyz=['coords', 'pots'], valz=[out["coords"], out["pots"]])
+            if self._desc_wt and self._deb_desc_wt_tracker:                        # pyvibdmc.py:849-852
+                self._desc_wt_history.append(dev.dw_peek(self._dw_n_parent))
             if events.get("desc"):
                 self._desc_wt = False
                 self._desc_wts = dev.dw_end(self._dw_n_parent)
@@ -376,6 +425,10 @@ class DMC_Sim:
                                          valz=[self._parent, self._desc_wts, self._parent_wts])
                 else:
                     SimArchivist.save_h5(fname=fname, keyz=['coords', 'desc_wts'], valz=[self._parent, self._desc_wts])
+                if self._deb_desc_wt_tracker:                                      # pyvibdmc.py:868-870
+                    np.save(f"{self.output_folder}/wfns/{self.sim_name}_desc_wt_tracker_{nxt - self.desc_wt_time_steps}ts.npy",
+                            np.array(self._desc_wt_history))
+                    self._desc_wt_history = []
             t = nxt
             self.cur_timestep = t - 1
         self._pull_walkers()
@@ -384,17 +437,47 @@ class DMC_Sim:
         """User potential callable: the GPU moves / weights / branches, the callable sees the coordinates
         once per step (getpot contract, potential_manager.py:71-99)."""
         pot_seconds = {}
+        train_before = set(int(s) for s in self.deb_train_save_step) if self._deb_save_before_bod else set()
         for step in range(t0, t1):
+            if self.fixed_node is not None:                                        # pyvibdmc.py:755-757
+                q_beginning = self.fixed_node_func(dev.download()["coords"], step)
             cds = dev.ext_move()
             if step in self._log_set:
                 v, pot_seconds[step] = self.potential(cds, timeit=True)
             else:
                 v = self.potential(cds)
+            v = np.array(v, dtype=np.float64)
+            if self.fixed_node is not None:                                        # pyvibdmc.py:795-797
+                self._recrossing(q_beginning, self.fixed_node_func(cds, step), cds, v)
+            if step in train_before:                                               # pyvibdmc.py:799-804
+                print(f'{cds.shape} walkers collected')
+                SimArchivist.save_h5(fname=f"{self.output_folder}/{self.sim_name}_training_{step}ts.hdf5",
+                                     keyz=['coords', 'pots'], valz=[cds, v])
+            if self.adiabatic_dmc is not None:                                     # pyvibdmc.py:820-825
+                v = v + self.ad_lam_array[step] * self.ad_obs_func(cds)
             do_branch = (step % self.branch_every) == 0
             dev.ext_finish(np.asarray(v, dtype=np.float64), do_branch)
             if dev.state(raise_on_error=False)["err"]:
                 break
         return pot_seconds
+
+    def _recrossing(self, q_1, q_2, cds, pots):
+        """Fixed-node recrossing correction (pyvibdmc.py:684-699): walkers that probably crossed the node and came back
+        get a prohibitive energy.  In the reference `cds` aliases the moved walkers (move_randomly works in place), so
+        both G-matrix evaluations see the same coordinates; the same holds here."""
+        try:
+            m1 = 1 / self.g_mat(cds)
+            m2 = 1 / self.g_mat(cds)
+            summed = m1 + m2
+            numerator = 2 * q_1 * q_2 * summed
+            denominator = -2 * self.delta_t
+        except Exception:
+            numerator = -1 * 4 * q_1 * q_2
+            sigma_q = np.sqrt(self.delta_t * self.g_mat)
+            denominator = 2 * sigma_q ** 2
+        p_recross = np.exp(numerator / denominator)
+        randz = self._host_rng.random(size=len(cds))
+        pots[randz < p_recross] = 10
 
     # ------------------------------------------------------------------ run / checkpoint (pyvibdmc.py:878-947)
     def run(self):
@@ -434,6 +517,8 @@ class DMC_Sim:
                                  keyz=['vref_vs_tau', 'pop_vs_tau', 'atomic_nums', 'atomic_masses'],
                                  valz=[np.column_stack((ts, self._vref_vs_tau)), np.column_stack((ts, self._pop_vs_tau)),
                                        self._atm_nums, self.masses])
+            if getattr(self, 'adiabatic_dmc', None) is not None:                   # pyvibdmc.py:924-925
+                np.save(f"{self.output_folder}/{self.sim_name}_lambda.npy", self.ad_lam_array)
             finish = time.time() - dmc_time_start
         self._logger = SimLogger(f"{self.output_folder}/{self.sim_name}_log.txt")
         self._logger.finish_sim(finish)
@@ -459,16 +544,20 @@ class DMC_Sim:
         self.__dict__.update(state)
         self._dev = None
         self._potential_obj = None
+        for k in ('adiabatic_dmc', 'fixed_node', 'impsamp_manager'):
+            self.__dict__.setdefault(k, None)
 
 
 def dmc_restart(potential, chkpt_folder, sim_name, additional_timesteps=0, impsamp=None, imp_samp_oned=False,
                 fixed_node=None):
     """Reload `{chkpt_folder}/chkpts/{sim_name}_*.pickle` and continue (pyvibdmc.py:949-965)."""
-    if fixed_node is not None:
-        raise NotImplementedError("fixed_node is not implemented on the B200 path")
     dmc_sim = SimArchivist.reload_sim(chkpt_folder, sim_name)
     dmc_sim.imp1d = imp_samp_oned
     dmc_sim.fixed_node = fixed_node
+    if fixed_node is not None:
+        dmc_sim.fixed_node_func = fixed_node['function']
+        dmc_sim.g_mat = fixed_node['g_matrix']
+    dmc_sim._hooked = bool(fixed_node is not None or (dmc_sim._deb_training_every is not None and dmc_sim._deb_save_before_bod))
     dmc_sim._init_restart(additional_timesteps, impsamp)
     dmc_sim.potential = potential.getpot
     dmc_sim._potential_obj = potential

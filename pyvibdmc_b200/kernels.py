@@ -310,6 +310,15 @@ class DeviceSim:
         check(lib.pvd_sim_dw_end(self._h, ptr(out), int(n_parent)))
         return out
 
+    def dw_peek(self, n_parent):
+        out = np.zeros(int(n_parent))
+        check(lib.pvd_sim_dw_peek(self._h, ptr(out), int(n_parent)))
+        return out
+
+    def set_masses(self, masses):
+        m = f64(masses).reshape(-1)
+        check(lib.pvd_sim_set_masses(self._h, ptr(m), len(m)))
+
     def dw_parent(self):
         n = C.c_int64(0)
         check(lib.pvd_sim_dw_parent(self._h, None, None, C.byref(n)))

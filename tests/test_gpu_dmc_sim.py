@@ -192,3 +192,81 @@ def test_nn_water_dimer_dmc(pv, tmp_path):
     coords = sim.walkers
     assert coords.shape[1:] == (6, 3)
     assert np.allclose(sim._walker_pots, pot.getpot(coords), rtol=1e-5, atol=1e-9)
+
+
+# ------------------------------------------------------------------ loop variants that call back into Python
+def _ho_kw(pv, out, **extra):
+    kw = dict(sim_name="v", output_folder=out, weighting='discrete', num_walkers=2000, num_timesteps=400, equil_steps=100,
+              chkpt_every=1000, wfn_every=200, desc_wt_steps=20, atoms=['O-H'], delta_t=10, potential=ho_potential(pv, cores=1),
+              start_structures=np.zeros((1, 1, 1)), log_every=100, seed=5)
+    kw.update(extra)
+    return kw
+
+
+def test_adiabatic_dmc_shifts_the_reference_energy(pv, tmp_path):
+    """pyvibdmc.py:820-825: V += lambda(t) * W(x).  With W = 1 the energy follows the lambda ramp."""
+    lam0, dlam = 1000 * WN, 5 * WN
+    out = str(tmp_path / "ad")
+    sim = pv.DMC_Sim(**_ho_kw(pv, out, adiabatic_dmc={'initial_lambda': lam0, 'lambda_change': dlam, 'equil_time': 200,
+                                                      'observable_func': lambda c: np.ones(len(c))}))
+    assert np.array_equal(sim.ad_lam_array[:200], np.zeros(200)) and np.allclose(sim.ad_lam_array[200:], lam0 + dlam * np.arange(200))
+    sim.run()
+    v = sim.vref_vs_tau[:, 1] / WN
+    assert abs(v[100:200].mean() - 1852) < 60 and abs(v[300:].mean() - (1852 + 1000 + 5 * 149.5)) < 80
+    assert os.path.exists(f"{out}/v_lambda.npy") and np.array_equal(np.load(f"{out}/v_lambda.npy"), sim.ad_lam_array)
+
+
+def test_fixed_node_gives_the_first_excited_state(pv, tmp_path):
+    """pyvibdmc.py:684-699, 755-757, 795-797: node at x = 0 with the recrossing correction -> 3/2 hbar omega for the HO."""
+    from pyvibdmc_b200.simulation_utilities import Constants
+    mu = Constants.reduced_mass('O-H')
+
+    def node(cds, step):
+        return cds[:, 0, 0]
+
+    def pot_with_node(cds):                       # walkers across the node die (infinite wall), like a user would set it up
+        v = 0.5 * mu * (3700 * WN) ** 2 * cds[:, 0, 0] ** 2
+        v[cds[:, 0, 0] < 0] = 10.0
+        return v
+
+    out = str(tmp_path / "fn")
+    kw = _ho_kw(pv, out, num_walkers=4000, num_timesteps=600, delta_t=5, potential=pv.Potential_Direct(potential_function=pot_with_node),
+                start_structures=np.full((1, 1, 1), 0.2), fixed_node={'function': node, 'g_matrix': 1.0 / mu})
+    sim = pv.DMC_Sim(**kw)
+    sim.run()
+    zpe = sim.vref_vs_tau[200:, 1].mean() / WN
+    assert abs(zpe - 1.5 * 3700) < 150, zpe
+    assert (sim.walkers[:, 0, 0] > 0).mean() > 0.999
+
+
+def test_debug_mass_change_training_dumps_and_tracker(pv, tmp_path):
+    out = str(tmp_path / "dbg")
+    sim = pv.DMC_Sim(**_ho_kw(pv, out, DEBUG_mass_change={'change_every': 200, 'factor_per_change': 4.0},
+                              DEBUG_save_training_every=150, DEBUG_save_desc_wt_tracker=True))
+    m0 = sim.masses.copy()
+    sim.run()
+    assert np.allclose(sim.masses, 4.0 * m0) and np.allclose(sim._sigmas, np.sqrt(10 / (4.0 * m0)))
+    # heavier particle in the same potential: omega halves -> the zero-point energy halves
+    v = sim.vref_vs_tau[:, 1] / WN
+    assert abs(v[100:200].mean() - 1852) < 60 and abs(v[300:].mean() - 1852 / 2) < 60
+    for t in (0, 150, 300):
+        d = read_h5(f"{out}/v_training_{t}ts.hdf5")
+        assert d['coords'].shape[1:] == (1, 1) and len(d['pots']) == len(d['coords']) and 1000 < len(d['coords']) < 3000
+        k = 0.5 * m0[0] * (3700 * WN) ** 2
+        assert np.allclose(d['pots'], k * d['coords'][:, 0, 0] ** 2, rtol=1e-12, atol=0)
+    tr = np.load(f"{out}/wfns/v_desc_wt_tracker_100ts.npy")
+    w = read_h5(f"{out}/wfns/v_wfn_100ts.hdf5")
+    assert tr.shape == (20, len(w['desc_wts'])) and np.array_equal(tr[-1], w['desc_wts'])
+    pop = sim._pop_vs_tau
+    assert np.array_equal(tr.sum(axis=1), pop[100:120])       # every parent's descendants add up to the population, step by step
+
+
+def test_training_dump_before_birth_death(pv, tmp_path):
+    out = str(tmp_path / "bb")
+    sim = pv.DMC_Sim(**_ho_kw(pv, out, num_timesteps=120, DEBUG_save_training_every=50, DEBUG_save_before_bod=True))
+    sim.run()
+    pop = sim._pop_vs_tau
+    for t in (0, 50, 100):
+        d = read_h5(f"{out}/v_training_{t}ts.hdf5")
+        n_before = 2000 if t == 0 else int(pop[t - 1])
+        assert len(d['coords']) == n_before                   # collected after the move, before birth/death of step t

@@ -85,7 +85,13 @@ def test_constructor_validation_matches_reference(tmp_path):
     with pytest.raises(ValueError, match="Invalid input for continuous weight threshold"):
         pv.DMC_Sim(start_structures=np.zeros((1, 1, 1)), weighting='continuous', cont_wt_thresh="x", **kw)
     with pytest.raises(NotImplementedError):
-        pv.DMC_Sim(start_structures=np.zeros((1, 1, 1)), adiabatic_dmc={'initial_lambda': 0}, **kw)
+        pv.DMC_Sim(start_structures=np.zeros((1, 1, 1)), second_impsamp_displacement=True, **kw)
+    with pytest.raises(ValueError, match="Number of mass change steps"):
+        pv.DMC_Sim(start_structures=np.zeros((1, 1, 1)), DEBUG_mass_change={'change_every': 2, 'factor_per_change': np.ones(5)}, **kw)
+    # adiabatic DMC set-up: lambda ramp after the equilibration plateau (reference pyvibdmc.py:276-291)
+    sim = pv.DMC_Sim(start_structures=np.zeros((1, 1, 1)),
+                     adiabatic_dmc={'initial_lambda': -2.0, 'lambda_change': 0.5, 'equil_time': 2, 'observable_func': lambda c: c[:, 0, 0]}, **kw)
+    assert np.array_equal(sim.ad_lam_array, [0, 0, -2.0, -1.5, -1.0]) and sim._hooked
 
 
 def test_step_markers_and_derived_constants(tmp_path, oracle):
