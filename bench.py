@@ -121,6 +121,7 @@ def main():
     ap.add_argument("--walkers", type=int, default=1_000_000, help="walkers per GPU")
     ap.add_argument("--rng", default="fp64", choices=["fp64", "fast"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the per-GPU timings of BASELINE configs 1, 3, 4, 5")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -201,6 +202,42 @@ def main():
     walker_steps = float(stats["pop"].sum())          # sum_t global population (SURVEY 8d metric)
     value = walker_steps / (ms * 1e-3)
 
+    # ---- multi-GPU end to end (every rank: pinned host shard -> device, K steps with the all-reduce, results back to the host)
+    e2e_multi = None
+    if world > 1:
+        host_in = torch.from_numpy(start).pin_memory()
+        cap_out = int(1.5 * n_loc) + 1024
+        host_out = {"coords": torch.empty((cap_out, 3, 3), dtype=torch.float64).pin_memory().numpy(),
+                    "pots": torch.empty(cap_out, dtype=torch.float64).pin_memory().numpy()}
+        tot_ws, tot_s, h2d, d2h = 0.0, 0.0, 0, 0
+        for rep in range(3):
+            s2 = make_sim(n_loc, n0, 99 + rep + 17 * rank)
+            s2.set_sums_ptr(sums_t.data_ptr())
+            torch.cuda.synchronize()
+            dist.barrier()
+            t0 = time.perf_counter()
+            s2.upload(host_in.numpy())
+            dist.all_reduce(sums_t)
+            s2.init_finalize()
+            for _ in range(args.steps):
+                s2.step_local(1)
+                dist.all_reduce(sums_t)
+                s2.step_finalize()
+            out = s2.download(out=host_out)
+            stt = s2.stats(0, args.steps)
+            dt_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            dist.all_reduce(dt_t, op=dist.ReduceOp.MAX)
+            if rep > 0:
+                tot_ws += float(stt["pop"].sum())
+                tot_s += float(dt_t.item())
+                h2d = host_in.numel() * 8 * world
+                d2h = (out["coords"].nbytes + out["pots"].nbytes) * world + stt.nbytes
+            s2.close()
+        sim.set_sums_ptr(sums_t.data_ptr())
+        e2e_multi = {"value": tot_ws / tot_s, "unit": "walker-steps/s", "h2d_bytes_per_step": h2d / args.steps,
+                     "d2h_bytes_per_step": d2h / args.steps,
+                     "what": f"per rank: upload shard (pinned host) + {args.steps} time steps with the NCCL all-reduce + download; max over ranks"}
+
     if rank != 0:
         sim.close()
         if world > 1:
@@ -227,9 +264,12 @@ def main():
             pass
 
     # ---- end to end through the public call: host start structures -> K time steps -> host results
-    e2e = None
+    e2e = e2e_multi
     if world == 1:
         host_in = torch.from_numpy(start).pin_memory()
+        cap_out = int(1.5 * n_loc) + 1024
+        host_out = {"coords": torch.empty((cap_out, 3, 3), dtype=torch.float64).pin_memory().numpy(),
+                    "pots": torch.empty(cap_out, dtype=torch.float64).pin_memory().numpy()}
         reps, tot_ws, tot_s, h2d, d2h = 3, 0.0, 0.0, 0, 0
         for rep in range(reps + 1):
             s2 = make_sim(n_loc, n0, 99 + rep)
@@ -237,7 +277,7 @@ def main():
             t0 = time.perf_counter()
             s2.upload(host_in.numpy())
             s2.run(args.steps)
-            out = s2.download()
+            out = s2.download(out=host_out)
             stt = s2.stats(0, args.steps)
             dt_s = time.perf_counter() - t0
             if rep > 0:
@@ -248,7 +288,7 @@ def main():
             s2.close()
         e2e = {"value": tot_ws / tot_s, "unit": "walker-steps/s", "h2d_bytes_per_step": h2d / args.steps,
                "d2h_bytes_per_step": d2h / args.steps,
-               "what": f"upload start structures (pinned host) + {args.steps} time steps + download walkers, V and per-step Vref/pop"}
+               "what": f"upload start structures (pinned host) + {args.steps} time steps + download walkers and V (pinned host) and per-step Vref/pop"}
 
     # ---- tutorial size (configs[1] as shipped: 20,000 walkers)
     tut = None
@@ -264,6 +304,19 @@ def main():
                "unit": "walker-steps/s"}
         s3.close()
 
+    # ---- the other BASELINE configurations at their per-GPU sizes (parity-test cases; reported, not the headline)
+    others = None
+    if world == 1 and not args.no_other_configs:
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("config_bench", os.path.join(ROOT, "tools", "config_bench.py"))
+        cb = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(cb)
+        sim.close()
+        others = cb.collect(("c1", "c3", "c4", "c5"), large_only=False, steps=100)
+        others["note"] = ("steady-state device-resident loop, CUDA events inside pvd_sim_run; c1 = 1-D HO discrete, c3 = H2O continuous "
+                          "(1e6/GPU), c4 = H2O importance sampling with finite-difference drift (1.25e6/GPU), c5 = (H2O)2 NN PES on tcgen05 "
+                          "(1.25e7/GPU)")
+
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cpu, _ = time_cpu_reference()
@@ -278,7 +331,7 @@ def main():
                        "parallelism": f"walkers sharded over {world} GPU(s), one NCCL all-reduce of {_capi.NSUMS} doubles per step"
                        if world > 1 else "single GPU, one kernel launch per time step"},
             "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
-            "tutorial_20k": tut, "final_population": int(st["n"]),
+            "tutorial_20k": tut, "other_configs": others, "final_population": int(st["n"]),
             "zpe_cm1_last_half": float(stats["vref"][args.steps // 2:].mean() / 4.556335281212229e-6)}
     print(json.dumps(line))
     sim.close()

@@ -338,11 +338,17 @@ class DeviceSim:
             check(rc)
         return dict(n=n.value, vref=vref.value, step=step.value, err=err.value)
 
-    def download(self, who_from=False):
+    def download(self, who_from=False, out=None):
+        """Walkers, energies (weights, who_from) -> host.  `out`: optional {'coords': (cap,A,D) f64, 'pots': (cap,) f64} host
+        buffers to fill (e.g. views of pinned memory) instead of allocating fresh arrays."""
         n = C.c_int64(0)
         check(lib.pvd_sim_download(self._h, None, None, None, None, 0, C.byref(n)))
         nn = n.value
-        xyz, pots = np.empty((nn, self.natoms, self.ndim)), np.empty(nn)
+        if out is not None:
+            xyz, pots = out["coords"][:nn], out["pots"][:nn]
+            assert xyz.flags.c_contiguous and pots.flags.c_contiguous and xyz.dtype == np.float64 and pots.dtype == np.float64
+        else:
+            xyz, pots = np.empty((nn, self.natoms, self.ndim)), np.empty(nn)
         w = np.empty(nn) if self.cfg.weighting == _capi.WEIGHT_CONTINUOUS else None
         who = np.empty(nn, dtype=np.int64) if who_from else None
         check(lib.pvd_sim_download(self._h, ptr(xyz), ptr(pots), ptr(w), ptr(who), nn, C.byref(n)))

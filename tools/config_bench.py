@@ -55,20 +55,13 @@ def timed(sim, equil, steps, reps=3):
     return best
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--quick", action="store_true")
-    ap.add_argument("--only", default="c1,c3,c4,c5")
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--equil", type=int, default=-1, help="override the equilibration length (profiling runs)")
-    ap.add_argument("--large-only", action="store_true")
-    args = ap.parse_args()
-    only = set(args.only.split(","))
-    EQUIL[0] = args.equil
-    sizes = (lambda small, large: (large,) if args.large_only else (small, large))
+def collect(only=("c1", "c3", "c4", "c5"), large_only=False, steps=100, equil=-1, scale=1.0):
+    """Returns {config label: {ms_per_step, walker_steps_per_s, mean_population, mean_vref_cm1}}."""
+    only = set(only)
+    EQUIL[0] = equil
+    sizes = (lambda small, large: (large,) if large_only else (small, large))
     mH, mO = Constants.mass("H"), Constants.mass("O")
     out = {}
-    scale = 0.1 if args.quick else 1.0
 
     if "c1" in only:
         mu = Constants.reduced_mass("O-H")
@@ -76,15 +69,15 @@ def main():
         for n in sizes(1000, int(1e6 * scale)):
             sim = K.DeviceSim(1, 1, [mu], n, 10.0, _capi.POT_HARMONIC, pot_params=[(0.5 * mu) * om ** 2], seed=1)
             sim.upload(np.zeros((n, 1, 1)))
-            out[f"c1_ho_discrete_{n}"] = timed(sim, 200, args.steps * (10 if n < 10000 else 1))
+            out[f"c1_ho_discrete_{n}"] = timed(sim, 200, steps * (10 if n < 10000 else 1))
             sim.close()
 
     if "c3" in only:
         for n in sizes(20000, int(1e6 * scale)):
             sim = K.DeviceSim(3, 3, [mH, mH, mO], n, 5.0, _capi.POT_H2O_PS, weighting="continuous", seed=2)
             sim.upload(np.broadcast_to(EQ * 1.01, (n, 3, 3)).copy())
-            r = timed(sim, 300, args.steps)
-            st = sim.stats(sim.state()["step"] - args.steps, args.steps)
+            r = timed(sim, 300, steps)
+            st = sim.stats(sim.state()["step"] - steps, steps)
             r["branched_per_step"] = float(st["births"].mean())
             out[f"c3_h2o_continuous_{n}"] = r
             sim.close()
@@ -95,7 +88,7 @@ def main():
             sim = K.DeviceSim(3, 3, [mH, mH, mO], n, 1.0, _capi.POT_H2O_PS, trial=_capi.TRIAL_H2O_FD, seed=3)
             sim.set_trial_table(tab)
             sim.upload(np.broadcast_to(EQ * 1.01, (n, 3, 3)).copy())
-            out[f"c4_h2o_impsamp_fd_{n}"] = timed(sim, 200, args.steps)
+            out[f"c4_h2o_impsamp_fd_{n}"] = timed(sim, 200, steps)
             sim.close()
 
     if "c5" in only:
@@ -104,9 +97,20 @@ def main():
             sim = K.DeviceSim(6, 3, [mO, mH, mH] * 2, n, 5.0, _capi.POT_NN_H4O2, seed=4)
             sim.set_nn_weights(w)
             sim.upload(np.broadcast_to(DIMER, (n, 6, 3)).copy())
-            out[f"c5_dimer_nn_{n}"] = timed(sim, 50, max(args.steps // 4, 5), reps=2)
+            out[f"c5_dimer_nn_{n}"] = timed(sim, 50, max(steps // 4, 5), reps=2)
             sim.close()
+    return out
 
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--only", default="c1,c3,c4,c5")
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--equil", type=int, default=-1, help="override the equilibration length (profiling runs)")
+    ap.add_argument("--large-only", action="store_true")
+    args = ap.parse_args()
+    out = collect(args.only.split(","), args.large_only, args.steps, args.equil, 0.1 if args.quick else 1.0)
     print(json.dumps(out, indent=1))
 
 
