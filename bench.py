@@ -121,6 +121,8 @@ def main():
     ap.add_argument("--walkers", type=int, default=1_000_000, help="walkers per GPU")
     ap.add_argument("--rng", default="fp64", choices=["fp64", "fast"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--collective", default="mailbox", choices=["mailbox", "nccl"],
+                    help="per-step exchange for N > 1: NVLink peer-memory mailbox fused into the step kernel, or a NCCL all-reduce")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the per-GPU timings of BASELINE configs 1, 3, 4, 5")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -152,24 +154,36 @@ def main():
         s.set_stream(stream.cuda_stream)
         return s
 
+    def connect(s):
+        if world > 1 and args.collective == "mailbox":
+            handles = [None] * world
+            dist.all_gather_object(handles, s.mailbox_handle())
+            s.mailbox_connect(handles)
+
     sim = make_sim(n_loc, n0, 1234 + rank)
     sums_t = torch.zeros(_capi.NSUMS, dtype=torch.float64, device=dev)
     if world > 1:
         sim.set_sums_ptr(sums_t.data_ptr())
+        connect(sim)
     start = start_ensemble(n_loc)
     sim.upload(start)
     if world > 1:
         dist.all_reduce(sums_t)
         sim.init_finalize()
 
-    def steps(k):
+    def run_steps(s, k):
         if world == 1:
-            sim.run(k)
+            s.run(k)
+        elif args.collective == "mailbox":
+            s.run_mailbox(k)
         else:
             for _ in range(k):
-                sim.step_local(1)
+                s.step_local(1)
                 dist.all_reduce(sums_t)
-                sim.step_finalize()
+                s.step_finalize()
+
+    def steps(k):
+        run_steps(sim, k)
 
     launches0 = K.launch_count()
     steps(args.warmup)
@@ -210,19 +224,17 @@ def main():
         host_out = {"coords": torch.empty((cap_out, 3, 3), dtype=torch.float64).pin_memory().numpy(),
                     "pots": torch.empty(cap_out, dtype=torch.float64).pin_memory().numpy()}
         tot_ws, tot_s, h2d, d2h = 0.0, 0.0, 0, 0
+        s2 = make_sim(n_loc, n0, 99 + 17 * rank)
+        s2.set_sums_ptr(sums_t.data_ptr())
+        connect(s2)
         for rep in range(3):
-            s2 = make_sim(n_loc, n0, 99 + rep + 17 * rank)
-            s2.set_sums_ptr(sums_t.data_ptr())
             torch.cuda.synchronize()
             dist.barrier()
             t0 = time.perf_counter()
             s2.upload(host_in.numpy())
             dist.all_reduce(sums_t)
             s2.init_finalize()
-            for _ in range(args.steps):
-                s2.step_local(1)
-                dist.all_reduce(sums_t)
-                s2.step_finalize()
+            run_steps(s2, args.steps)
             out = s2.download(out=host_out)
             stt = s2.stats(0, args.steps)
             dt_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
@@ -232,11 +244,11 @@ def main():
                 tot_s += float(dt_t.item())
                 h2d = host_in.numel() * 8 * world
                 d2h = (out["coords"].nbytes + out["pots"].nbytes) * world + stt.nbytes
-            s2.close()
+        s2.close()
         sim.set_sums_ptr(sums_t.data_ptr())
         e2e_multi = {"value": tot_ws / tot_s, "unit": "walker-steps/s", "h2d_bytes_per_step": h2d / args.steps,
                      "d2h_bytes_per_step": d2h / args.steps,
-                     "what": f"per rank: upload shard (pinned host) + {args.steps} time steps with the NCCL all-reduce + download; max over ranks"}
+                     "what": f"per rank: upload shard (pinned host) + {args.steps} time steps with the per-step exchange + download; max over ranks"}
 
     if rank != 0:
         sim.close()
@@ -328,7 +340,9 @@ def main():
                        "weighting": "discrete", "walkers_per_gpu": n_loc, "global_walkers": n0, "delta_t": DT,
                        "rng": "philox4x32-10 + " + ("fp64 Box-Muller" if args.rng == "fp64" else "SFU Box-Muller"),
                        "l2": "walker state (2 x 80 MB ping-pong at 1e6 walkers) exceeds the 126 MB L2; no flush needed",
-                       "parallelism": f"walkers sharded over {world} GPU(s), one NCCL all-reduce of {_capi.NSUMS} doubles per step"
+                       "parallelism": (f"walkers sharded over {world} GPU(s); per step {_capi.NSUMS} doubles per shard are exchanged "
+                                       + ("by peer stores over NVLink from the step kernel's last CTA (mailbox), no collective kernel"
+                                          if args.collective == "mailbox" else "by one NCCL all-reduce"))
                        if world > 1 else "single GPU, one kernel launch per time step"},
             "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
             "tutorial_20k": tut, "other_configs": others, "final_population": int(st["n"]),

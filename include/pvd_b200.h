@@ -215,6 +215,14 @@ int pvd_sim_step_finalize(pvd_sim *s);
 int pvd_sim_imp_move_local(pvd_sim *s);
 int pvd_sim_imp_branch_local(pvd_sim *s, int32_t do_branch);
 
+/* the same exchange without a collective kernel: the step kernel's last CTA stores the shard's sums into every peer's
+ * mailbox over NVLink (CUDA IPC mappings), a one-warp kernel waits for the world's stamps and finalises.
+ *   every rank: pvd_sim_mailbox_handle(out 64 bytes) -> all-gather the handles -> pvd_sim_mailbox_connect(all, world)
+ *   then pvd_sim_run_mailbox(nsteps) enqueues whole time steps with no host or NCCL involvement */
+int pvd_sim_mailbox_handle(pvd_sim *s, void *handle64);
+int pvd_sim_mailbox_connect(pvd_sim *s, const void *handles, int32_t n);
+int pvd_sim_run_mailbox(pvd_sim *s, int64_t nsteps, int32_t branch_every);
+
 /* descendant weighting (pyvibdmc.py:739-747, 663-672, 856-869) */
 int pvd_sim_dw_begin(pvd_sim *s, int64_t global_offset);
 int pvd_sim_dw_end(pvd_sim *s, double *desc_wts, int64_t n_parent);

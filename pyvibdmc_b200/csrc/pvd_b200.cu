@@ -294,6 +294,10 @@ struct pvd_sim {
     bool uploaded = false, ext_moved = false;
     int grid = 1, grid_light = 1;
     int ticket_batch = 1;
+    DevBuf mbox;                                   // this rank's mailbox (NVLink collective)
+    double *peer_mbox[PVD_MAX_WORLD]{};            // every rank's mailbox mapped here (own: mbox.p)
+    bool mbox_connected = false, mbox_step = false;
+    unsigned long long mbox_epoch = 0;             // bumped by every upload: stamps of an earlier run can never match
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     PotParamsDev pot{};
     double sigma[PVD_MAX_ATOMS]{};
@@ -341,6 +345,8 @@ static StepArgs make_args(pvd_sim *s, int do_branch)
     a.nc = s->nc;
     a.flip = s->cfg.weighting == PVD_WEIGHT_DISCRETE ? 1 : 0;
     a.ticket_batch = s->ticket_batch;
+    for (int r = 0; r < PVD_MAX_WORLD; ++r) a.mbox[r] = s->mbox_step ? s->peer_mbox[r] : nullptr;
+    a.mbox_epoch = s->mbox_epoch;
     for (int i = 0; i < PVD_MAX_ATOMS; ++i) a.sigma[i] = s->sigma[i];
     for (int c = 0; c < PVD_MAX_COMP; ++c) a.sigc[c] = s->sigma[(c / (s->cfg.ndim > 0 ? s->cfg.ndim : 1)) % PVD_MAX_ATOMS];
     a.pot = s->pot;
@@ -484,6 +490,8 @@ int pvd_sim_destroy(pvd_sim *s)
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
+    for (int r = 0; r < PVD_MAX_WORLD; ++r)
+        if (s->peer_mbox[r] && s->peer_mbox[r] != s->mbox.p) cudaIpcCloseMemHandle(s->peer_mbox[r]);
     if (s->nn_w.packed) cudaFree(s->nn_w.packed);
     if (s->nn_w.images) cudaFree(s->nn_w.images);
     if (s->nn_w.vecs) cudaFree(s->nn_w.vecs);
@@ -541,6 +549,7 @@ int pvd_sim_upload(pvd_sim *s, const double *xyz, int64_t n, const double *w)
     PVD_CUDA(cudaMemcpyAsync(s->stage.p, xyz, (size_t)n * nc * 8, cudaMemcpyHostToDevice, s->stream));
     s->cur = 0;
     s->parity = 0;
+    ++s->mbox_epoch;
     k_aos_to_soa<<<grid_for(n * nc, 256, 16), 256, 0, s->stream>>>(s->stage.as<double>(), s->x[0].as<double>(), n, nc, s->cap);
     PVD_CHECK_LAUNCH();
     DevState h[2];
@@ -781,6 +790,64 @@ int pvd_sim_step_finalize(pvd_sim *s)
     return PVD_OK;
 }
 
+// ---- multi-GPU step with the NVLink mailbox collective (see k_finalize_mailbox)
+int pvd_sim_mailbox_handle(pvd_sim *s, void *handle64)
+{
+    SIM_CHECK(s);
+    SIM_DEVICE(s);
+    PVD_REQUIRE(handle64, "NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    if (!s->mbox.p) {
+        const size_t bytes = (size_t)2 * PVD_MAX_WORLD * PVD_MBOX_STRIDE * 8;
+        PVD_CUDA(s->mbox.alloc(bytes));
+        PVD_CUDA(cudaMemset(s->mbox.p, 0, bytes));
+    }
+    cudaIpcMemHandle_t h;
+    PVD_CUDA(cudaIpcGetMemHandle(&h, s->mbox.p));
+    memcpy(handle64, &h, 64);
+    return PVD_OK;
+}
+
+int pvd_sim_mailbox_connect(pvd_sim *s, const void *handles, int32_t n)
+{
+    SIM_CHECK(s);
+    SIM_DEVICE(s);
+    PVD_REQUIRE(handles && n == s->cfg.world_size && n <= PVD_MAX_WORLD && s->mbox.p, "pvd_sim_mailbox_connect: one handle per rank, after pvd_sim_mailbox_handle");
+    for (int r = 0; r < n; ++r) {
+        if (r == s->cfg.rank) { s->peer_mbox[r] = s->mbox.as<double>(); continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char *)handles + 64 * r, 64);
+        void *p = nullptr;
+        PVD_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        s->peer_mbox[r] = (double *)p;
+    }
+    s->mbox_connected = true;
+    return PVD_OK;
+}
+
+int pvd_sim_run_mailbox(pvd_sim *s, int64_t nsteps, int32_t branch_every)
+{
+    SIM_CHECK(s);
+    SIM_DEVICE(s);
+    PVD_REQUIRE(s->uploaded && s->mbox_connected, "pvd_sim_run_mailbox: upload walkers and connect the mailboxes first");
+    PVD_REQUIRE(s->cfg.trial == PVD_TRIAL_NONE, "importance sampling needs two exchanges per step: use the split step with an all-reduce");
+    PVD_REQUIRE(branch_every >= 1, "branch_every must be >= 1");
+    const int cont = s->cfg.weighting == PVD_WEIGHT_CONTINUOUS ? 1 : 0;
+    PVD_CUDA(cudaEventRecord(s->ev0, s->stream));
+    for (int64_t k = 0; k < nsteps; ++k) {
+        s->mbox_step = true;
+        const int rc = enqueue_step(s, branch_every == 1 ? 1 : -branch_every, nullptr, nullptr, nullptr);
+        if (rc) { s->mbox_step = false; return rc; }
+        StepArgs a = make_args(s, 1);
+        s->mbox_step = false;
+        a.parity = s->parity ^ 1;                  // enqueue_step already flipped the parity
+        k_finalize_mailbox<<<1, 32, 0, s->stream>>>(a, cont);
+        PVD_CHECK_LAUNCH();
+    }
+    PVD_CUDA(cudaEventRecord(s->ev1, s->stream));
+    return PVD_OK;
+}
+
 // ---- descendant weighting
 int pvd_sim_dw_begin(pvd_sim *s, int64_t global_offset)
 {
@@ -888,6 +955,7 @@ int pvd_sim_state(pvd_sim *s, int64_t *n, double *vref, int64_t *step, int32_t *
     if (err) *err = (int32_t)c.err;
     if (c.err & (PVD_ERR_WEIGHT | PVD_ERR_POP | PVD_ERR_EMPTY)) return pvd_fail(PVD_E_MASSIVE, PVD_MASSIVE_MSG);
     if (c.err & PVD_ERR_CAPACITY) return pvd_fail(PVD_E_MASSIVE, std::string(PVD_MASSIVE_MSG) + " (shard capacity exceeded)");
+    if (c.err & PVD_ERR_COMM) return pvd_fail(PVD_E_STATE, "a peer's per-step message did not arrive within 10 s (mailbox collective)");
     return PVD_OK;
 }
 

@@ -56,7 +56,8 @@ enum : unsigned {
     PVD_ERR_WEIGHT = 1u,    // non-finite weight or weight > 1.5 N0 + 1   (pyvibdmc.py:397-400)
     PVD_ERR_POP = 2u,       // population outside [0.5, 1.5] N0            (pyvibdmc.py:409-413, 714-717)
     PVD_ERR_CAPACITY = 4u,  // shard buffer too small for the branched population
-    PVD_ERR_EMPTY = 8u      // no walkers left on this shard
+    PVD_ERR_EMPTY = 8u,     // no walkers left on this shard
+    PVD_ERR_COMM = 16u      // a peer's per-step message did not arrive (mailbox collective)
 };
 
 // Device-resident simulation state.  Two copies are kept (index = step parity): the kernel of

@@ -578,6 +578,10 @@ __global__ void __launch_bounds__(PVD_CTA) k_cont_finish(const StepArgs a, const
             if (a.world == 1) finalize_from_sums(a, true);
         }
     }
+    if (a.world > 1 && a.mbox[0]) {
+        __syncthreads();                       // s_last was written by thread 0
+        if (s_last) mailbox_send(a, a.st[a.parity].step);
+    }
 }
 
 // plain weight update for the stand-alone entry point's bookkeeping of `src`

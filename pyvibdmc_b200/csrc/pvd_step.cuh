@@ -52,6 +52,8 @@ struct StepArgs {
     int ticket_batch;           // consecutive tiles a warp takes per ticket (1 for heavy tiles, more for light ones)
     double sigma[PVD_MAX_ATOMS];
     double sigc[PVD_MAX_COMP];  // sigma expanded per component (sigc[c] = sigma[c / ndim])
+    unsigned long long mbox_epoch; // run epoch (bumped by every upload) folded into the mailbox stamps
+    double *mbox[PVD_MAX_WORLD]; // NVLink mailbox collective: every rank's mailbox mapped into this process (mbox[0] == nullptr: off)
     PotParamsDev pot;
 };
 
@@ -114,6 +116,75 @@ __device__ inline void finalize_from_sums(const StepArgs &a, bool continuous)
     r.deaths = (long long)s[PVD_SUM_DEATHS];
     r.rejected = a.fin ? (long long)s[PVD_SUM_NIN] - si.n_accept : 0;
     r.step = si.step;
+}
+
+__device__ inline void forward_dead_state(const StepArgs &a);
+
+// ---------------------------------------------------------------- per-step collective over NVLink peer memory
+// The only exchange of a time step is PVD_NSUMS doubles per shard.  Instead of a NCCL all-reduce kernel
+// between the step kernel and the finalisation, the last CTA of the step kernel stores its shard's sums straight into
+// every peer's mailbox (slot [step parity][source rank]) over NVLink, fences at system scope and stamps the slot with
+// step + 1; the one-warp finalisation kernel on each GPU waits for the world's stamps, adds the slots in rank order
+// (so every GPU gets bit-identical Vref) and finalises.  Two parities suffice: a rank cannot start step s + 2 before
+// it has finalised s + 1, which needs every peer's s + 1 message, which a peer sends only after finalising s.
+constexpr int PVD_MBOX_STRIDE = PVD_NSUMS + 8;          // doubles per slot; the stamp sits at [PVD_NSUMS]
+__device__ __forceinline__ long long mbox_slot(int parity, int rank) { return ((long long)parity * PVD_MAX_WORLD + rank) * PVD_MBOX_STRIDE; }
+
+// called by ALL threads of the CTA that holds the shard's final sums in a.sums
+__device__ inline void mailbox_send(const StepArgs &a, long long step)
+{
+    const int nmsg = PVD_SUM_EXT + 4 * a.world;
+    const long long slot = mbox_slot(a.parity, a.rank);
+    __syncthreads();
+    for (int t = threadIdx.x; t < a.world * nmsg; t += blockDim.x) {
+        const int peer = t / nmsg, k = t - peer * nmsg;
+        a.mbox[peer][slot + k] = a.sums[k];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < a.world) {
+        unsigned long long *stamp = reinterpret_cast<unsigned long long *>(&a.mbox[threadIdx.x][slot + PVD_NSUMS]);
+        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(stamp), "l"((a.mbox_epoch << 40) | (unsigned long long)(step + 1)) : "memory");
+    }
+}
+
+__global__ void __launch_bounds__(32) k_finalize_mailbox(const StepArgs a, int continuous)
+{
+    const DevState &si = a.st[a.parity];
+    if (si.err) return;                        // the local step already forwarded the dead state
+    const int lane = threadIdx.x;
+    const double *mine = a.mbox[a.rank];
+    const unsigned long long want = (a.mbox_epoch << 40) | (unsigned long long)(si.step + 1);
+    bool ok = true;
+    if (lane < a.world) {
+        const unsigned long long *stamp = reinterpret_cast<const unsigned long long *>(&mine[mbox_slot(a.parity, lane) + PVD_NSUMS]);
+        const long long t0 = clock64();
+        unsigned long long got;
+        do {
+            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(stamp) : "memory");
+            if (got == want) break;
+            if (clock64() - t0 > 20000000000ll) { ok = false; break; }      // ~10 s: a peer died; do not hang the GPU
+        } while (true);
+    }
+    ok = __all_sync(0xffffffffu, ok);
+    __threadfence_system();
+    const int nmsg = PVD_SUM_EXT + 4 * a.world;
+    for (int k = lane; k < nmsg; k += 32) {
+        double v = 0.0;
+        for (int r = 0; r < a.world; ++r) {
+            double x;
+            asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(x) : "l"(&mine[mbox_slot(a.parity, r) + k]) : "memory");
+            v += x;
+        }
+        a.sums[k] = v;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        if (!ok) {
+            forward_dead_state(a);
+            a.st[a.parity ^ 1].err |= PVD_ERR_COMM;
+        } else finalize_from_sums(a, continuous != 0);
+    }
 }
 
 __global__ void k_finalize(const StepArgs a, int continuous)
@@ -219,6 +290,7 @@ __device__ inline void cta_finish_step(const StepArgs &a, const LaneAcc &acc, lo
         for (int w = 0; w < PVD_WARPS; ++w) tk[w * PVD_TICKET_STRIDE] = 0u;
         if (a.world == 1 && !defer_finalize) finalize_from_sums(a, continuous);
     }
+    if (a.world > 1 && a.mbox[0] && !defer_finalize) mailbox_send(a, a.st[a.parity].step);
 }
 
 // ---------------------------------------------------------------- producers: how a tile obtains (x, V)

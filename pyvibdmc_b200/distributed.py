@@ -57,7 +57,7 @@ class ShardedSim:
 
     def __init__(self, natoms, ndim, masses, num_walkers, delta_t, potential, weighting="discrete", seed=0,
                  rng_mode=_capi.RNG_FP64, pot_params=None, thresh_lower=None, thresh_upper=None, rebalance_every=250,
-                 capacity=None, stats_ring=1 << 14, trial=_capi.TRIAL_NONE, trial_table=None):
+                 capacity=None, stats_ring=1 << 14, trial=_capi.TRIAL_NONE, trial_table=None, collective="mailbox"):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
@@ -81,6 +81,13 @@ class ShardedSim:
             self.sim.set_trial_table(trial_table)
         self.sums = torch.zeros(_capi.NSUMS, dtype=torch.float64, device=self.device)
         self.sim.set_sums_ptr(self.sums.data_ptr())
+        # per-step exchange: "mailbox" = peer stores over NVLink fused into the step kernel's last CTA (no collective kernel),
+        # "nccl" = all-reduce between the step kernel and the finalisation.  Importance sampling needs two exchanges -> nccl.
+        self.collective = "nccl" if (self.imp or self.world == 1) else collective
+        if self.collective == "mailbox":
+            handles = [None] * self.world
+            dist.all_gather_object(handles, self.sim.mailbox_handle())
+            self.sim.mailbox_connect(handles)
         self.rebalance_every = int(rebalance_every)
         self.steps_done = 0
         self.natoms, self.ndim = natoms, ndim
@@ -92,6 +99,19 @@ class ShardedSim:
             self.sim.init_finalize()
 
     def run(self, nsteps, branch_every=1):
+        if self.collective == "mailbox":
+            done = 0
+            while done < int(nsteps):                  # whole segments are enqueued by one call; stop at rebalancing points
+                k = int(nsteps) - done
+                if self.rebalance_every:
+                    k = min(k, self.rebalance_every - self.steps_done % self.rebalance_every)
+                self.sim.run_mailbox(k, branch_every)
+                done += k
+                self.steps_done += k
+                if self.rebalance_every and self.steps_done % self.rebalance_every == 0:
+                    with self.torch.cuda.stream(self.stream):
+                        self.rebalance()
+            return
         with self.torch.cuda.stream(self.stream):
             for _ in range(int(nsteps)):
                 do_branch = 1 if branch_every == 1 else -int(branch_every)

@@ -295,6 +295,18 @@ class DeviceSim:
     def step_finalize(self):
         check(lib.pvd_sim_step_finalize(self._h))
 
+    def mailbox_handle(self):
+        buf = C.create_string_buffer(64)
+        check(lib.pvd_sim_mailbox_handle(self._h, buf))
+        return buf.raw
+
+    def mailbox_connect(self, handles):
+        blob = b"".join(handles)
+        check(lib.pvd_sim_mailbox_connect(self._h, C.c_char_p(blob), len(handles)))
+
+    def run_mailbox(self, nsteps, branch_every=1):
+        check(lib.pvd_sim_run_mailbox(self._h, int(nsteps), int(branch_every)))
+
     def imp_move_local(self):
         check(lib.pvd_sim_imp_move_local(self._h))
 
