@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(256, 4) k_displace_soa(double *__restrict__ x,
 // A tile is PVD_BR_SUB sub-tiles of 32 walkers (lane l of sub-tile s owns walker tile*128 + s*32 + l); see k_cont_update.
 constexpr int PVD_BR_SUB = 4;
 constexpr int PVD_BR_TILE = PVD_TILE * PVD_BR_SUB;
-__global__ void __launch_bounds__(PVD_CTA, 3) k_branch_discrete(const StepArgs a)
+__global__ void __launch_bounds__(PVD_CTA, 2) k_branch_discrete(const StepArgs a)
 {
     if (!step_prologue(a)) return;
     const DevState *sip = &a.st[a.parity];
@@ -224,22 +224,45 @@ __global__ void __launch_bounds__(PVD_CTA, 3) k_branch_discrete(const StepArgs a
                 const long long pi_ = pend * PVD_BR_TILE + s * PVD_TILE + lane;
                 const long long o = base + pend_excl[s];
                 if (o + pc > a.cap) { atomicOr(a.err_accum, PVD_ERR_CAPACITY); continue; }
+                // every array is read ONCE (nine components at a time, all loads in flight together) and written pc times
 #pragma unroll 1
-                for (int k = 0; k < pc; ++k) {
-                    const double *pi = a.xin + pi_;
-                    double *po = a.xout + (o + k);
-#pragma unroll 6
-                    for (int c = 0; c < a.nc; ++c) { *po = __ldcs(pi); pi += a.cap; po += a.cap; }
-                    if (a.vout) a.vout[o + k] = a.vin[pi_];
-                    if (dw) a.who_out[o + k] = a.who_in[pi_];
-                    if (a.idx_out) a.idx_out[o + k] = pi_;
-                    if (a.fin) {
-                        const double *fi = a.fin + pi_;
-                        double *fo = a.fout + (o + k);
-#pragma unroll 6
-                        for (int c = 0; c < a.nc; ++c) { *fo = __ldcs(fi); fi += a.cap; fo += a.cap; }
-                        a.psout[o + k] = a.psin[pi_];
-                        a.lkout[o + k] = a.lkin[pi_];
+                for (int c0 = 0; c0 < a.nc; c0 += 9) {
+                    double r[9];
+                    const double *pi = a.xin + pi_ + (long long)c0 * a.cap;
+#pragma unroll
+                    for (int j = 0; j < 9; ++j) { if (c0 + j < a.nc) r[j] = __ldcs(pi); pi += a.cap; }
+#pragma unroll 1
+                    for (int k = 0; k < pc; ++k) {
+                        double *po = a.xout + (o + k) + (long long)c0 * a.cap;
+#pragma unroll
+                        for (int j = 0; j < 9; ++j) { if (c0 + j < a.nc) *po = r[j]; po += a.cap; }
+                    }
+                }
+                if (a.fin) {
+#pragma unroll 1
+                    for (int c0 = 0; c0 < a.nc; c0 += 9) {
+                        double r[9];
+                        const double *fi = a.fin + pi_ + (long long)c0 * a.cap;
+#pragma unroll
+                        for (int j = 0; j < 9; ++j) { if (c0 + j < a.nc) r[j] = __ldcs(fi); fi += a.cap; }
+#pragma unroll 1
+                        for (int k = 0; k < pc; ++k) {
+                            double *fo = a.fout + (o + k) + (long long)c0 * a.cap;
+#pragma unroll
+                            for (int j = 0; j < 9; ++j) { if (c0 + j < a.nc) *fo = r[j]; fo += a.cap; }
+                        }
+                    }
+                }
+                {
+                    const double v = a.vout ? a.vin[pi_] : 0.0;
+                    const int who = dw ? a.who_in[pi_] : 0;
+                    const double ps = a.fin ? a.psin[pi_] : 0.0, lk = a.fin ? a.lkin[pi_] : 0.0;
+#pragma unroll 1
+                    for (int k = 0; k < pc; ++k) {
+                        if (a.vout) a.vout[o + k] = v;
+                        if (dw) a.who_out[o + k] = who;
+                        if (a.idx_out) a.idx_out[o + k] = pi_;
+                        if (a.fin) { a.psout[o + k] = ps; a.lkout[o + k] = lk; }
                     }
                 }
             }

@@ -35,6 +35,16 @@ def main():
     dist.all_reduce(hmax, op=dist.ReduceOp.MAX)
     dist.all_reduce(hmin, op=dist.ReduceOp.MIN)
     same = bool(torch.equal(hmax, hmin))
+    # ---- the NVLink mailbox exchange and the NCCL all-reduce must give bit-identical histories
+    ref = ShardedSim(3, 3, masses, n0, 5.0, _capi.POT_H2O_PS, seed=17, rebalance_every=100, collective="nccl")
+    ref.upload(np.repeat(eq[None] * 1.01, count, axis=0))
+    ref.run(T)
+    torch.cuda.synchronize()
+    rstats = ref.stats(0, T)
+    same_as_nccl = bool(sim.collective == "mailbox" and ref.collective == "nccl" and np.array_equal(rstats["vref"], stats["vref"])
+                        and np.array_equal(rstats["pop"], stats["pop"]))
+    ref.close()
+
     # ---- descendant weighting across shards: weights of all parents sum to the global population at window end
     off, n_par = sim.dw_begin()
     sim.run(60)
@@ -70,7 +80,7 @@ def main():
     imp.close()
     sim = None
     if rank == 0:
-        out = {"world": world, "dw_ok": dw_ok, "imp": imp_out, "step": st["step"], "pops": pops, "global_pop_last": float(stats["pop"][-1]), "same_on_all_ranks": same,
+        out = {"world": world, "dw_ok": dw_ok, "imp": imp_out, "mailbox_equals_nccl": same_as_nccl, "step": st["step"], "pops": pops, "global_pop_last": float(stats["pop"][-1]), "same_on_all_ranks": same,
                "zpe": float(stats["vref"][T // 2:].mean() / 4.556335281212229e-6), "births_minus_deaths_ok":
                bool(np.array_equal(np.diff(stats["pop"]), (stats["births"] - stats["deaths"])[1:]))}
         print("RESULT " + json.dumps(out))

@@ -24,6 +24,7 @@ def test_two_gpu_sharded_run():
     assert sum(out["pops"]) == int(out["global_pop_last"]) and 20000 < sum(out["pops"]) < 60000
     assert abs(out["pops"][0] - out["pops"][1]) < 0.2 * sum(out["pops"])          # rebalancing keeps shards level
     assert 4350 < out["zpe"] < 4900
+    assert out["mailbox_equals_nccl"]                                            # NVLink mailbox exchange == NCCL all-reduce, bit for bit
     assert out["dw_ok"]                                                          # descendant weights of all parents, all-reduced
     imp = out["imp"]                                                             # importance sampling with the global acceptance fraction
     assert imp["same"] and 4350 < imp["zpe"] < 4900 and 0.9 < imp["dt_eff_mean"] <= 1.0 and 4000 < imp["pop_last"] < 12000

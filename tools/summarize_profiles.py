@@ -16,6 +16,8 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
         "sm__ops_path_tensor_op_utchmma_src_bf16_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed",
+        "sm__ops_path_tensor_op_utchmma_src_fp16_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed",
+        "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "smsp__inst_executed_per_warp.ratio", "launch__occupancy_limit_registers",
         "lts__t_bytes.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"]
 
 
@@ -59,11 +61,17 @@ def main():
           "Per-launch times under ncu are cold-cache and serialised: compare SHARES with the bench, not absolutes.", ""]
     lp = os.path.join(G, "launches_r01.csv")
     if os.path.exists(lp):
-        md += ["## Launch list of `python bench.py --steps 30 --warmup 5 --no-cpu-baseline`", "",
-               "(`ncu --metrics gpu__time_duration.sum --clock-control none -c 800`; the 296-CTA launches are the 1e6-walker steps, the "
-               "122-CTA launches the 20 000-walker tutorial steps, `k_fp64_peak` is the roofline micro-benchmark.)", "", launches(lp), ""]
+        md += ["## Launch list of `python bench.py --steps 30 --warmup 5 --no-cpu-baseline --no-other-configs`", "",
+               "(`ncu --metrics gpu__time_duration.sum --clock-control none -c 1200`, see `tools/profile_r01.sh`; the 296-CTA launches are the "
+               "1e6-walker steps, the 122-CTA launches the 20 000-walker tutorial steps, `k_fp64_peak` is the roofline micro-benchmark.)", "",
+               launches(lp), ""]
+    lp = os.path.join(G, "launches_cfg_r01.csv")
+    if os.path.exists(lp):
+        md += ["## Launch list of `python tools/config_bench.py --large-only --steps 6 --equil 30`", "",
+               "(BASELINE configs 1, 3, 4, 5 at their per-GPU sizes: 1e6 HO, 1e6 H2O continuous, 1.25e6 H2O importance sampling, 1.25e7 "
+               "water dimers on the NN surface; kernels shared between configurations are pooled per grid size.)", "", launches(lp), ""]
     summ = {}
-    for name in ("r01_step_discrete", "r01_pot_aos", "r01_nn_tc"):
+    for name in ("r01_step_discrete", "r01_pot_aos", "r01_cont_update", "r01_imp_move", "r01_nn_tc2", "r01_branch_discrete"):
         rep = os.path.join(G, name + ".ncu-rep")
         if os.path.exists(rep):
             summ[name] = raw(rep)
@@ -77,7 +85,7 @@ def main():
                    "dram_read": rd, "dram_write": wr, "algorithmic_bytes_per_launch": 152e6,
                    "note": "writes of the compacted ensemble mostly stay in the 126 MB L2 until the next step reads them"},
                   open(os.path.join(OUT, "r01_step_kernel_traffic.json"), "w"), indent=1)
-    for f in ("zpe_validation.json", "BENCH_local.json"):
+    for f in ("zpe_validation.json", "BENCH_local.json", "BENCH_8gpu.json"):
         src = os.path.join(G, f)
         if os.path.exists(src):
             open(os.path.join(OUT, "r01_" + f), "w").write(open(src).read())
