@@ -84,6 +84,35 @@ def test_branch_continuous_vs_oracle(K, oracle, n, spread):
     assert np.allclose([mx, mn], [mxo, mno], rtol=4.5e-16)
 
 
+@pytest.mark.parametrize("kind", ["one_bin_overfull", "narrow_band", "many_halvings"])
+def test_branch_continuous_sort_paths(K, oracle, kind):
+    """The three donor-ordering paths against the sequential reference loop: (a) more than 8192 candidates in one
+    histogram bin (identical weights) -> single-CTA fallback sort; (b) thousands of candidates inside one 1/64-octave bin ->
+    sub-bucket ranking; (c) K-th largest weight below half the largest -> halved pieces re-enter the top: exact replay."""
+    rng = np.random.default_rng(7)
+    n = 30000
+    if kind == "one_bin_overfull":
+        w0 = np.ones(n)
+        v = np.full(n, 0.021)                                 # exp(0) = 1: weights stay identical -> ties broken by index
+        kill = rng.choice(n, 700, replace=False)
+    elif kind == "narrow_band":
+        w0 = 1.0 + 0.004 * rng.random(n)                      # all inside one histogram bin (1/64 octave = 1.1 %)
+        v = np.full(n, 0.021)
+        kill = rng.choice(n, 5000, replace=False)
+    else:
+        w0 = np.exp(rng.normal(0, 0.2, size=n))
+        w0[rng.choice(n, 5, replace=False)] = 64.0            # a few very heavy walkers must donate repeatedly
+        v = np.full(n, 0.021)
+        kill = rng.choice(n, 400, replace=False)
+    w0[kill] = 1e-9
+    wo, so, nbo, mxo, mno = oracle.branch_continuous(w0, v, 0.021, 5.0, 1.0 / n, None)
+    w, s, nb, mx, mn = K.branch_continuous(w0, v, 0.021, 5.0, 1.0 / n, None)
+    assert nb == nbo == len(kill)
+    assert np.array_equal(s, so)
+    assert np.array_equal(w, wo)                              # exp(0) is exact on both sides: bitwise
+    assert (mx, mn) == (mxo, mno)
+
+
 def test_replay_h2o_continuous_trajectory(K):
     from pyvibdmc_b200 import _capi
     g = golden("traj_h2o_cont_low_golden.npz")
