@@ -110,6 +110,22 @@ __device__ __forceinline__ void ps_group(double x3, const double (&p1)[9], const
     if constexpr (G + PS_BATCH < PS_NGROUPS) ps_group<G + PS_BATCH>(x3, p1, p2, acc);
 }
 
+// 1/sqrt(t) for the squared distances of the PES (t of order 1..100 bohr^2; callers clamp t >= 1e-30 so that two
+// coinciding atoms give a huge finite 1/r instead of NaN)
+__device__ __forceinline__ double ps_rsqrt(double t)
+{
+    double y = (double)rsqrtf((float)t);
+    const double h = 0.5 * t;
+    y = y * fma(-h, y * y, 1.5);
+    y = y * fma(-h, y * y, 1.5);
+    return y;
+}
+__device__ __forceinline__ double ps_sqrt_from(double t, double y)
+{
+    const double r = t * y;
+    return fma(0.5 * y, fma(-r, r, t), r);
+}
+
 // x: 9 Cartesians, atoms ordered H, H, O (calc_h2o_pot.f:18-19).
 // The 244 polynomial terms c_j (x1^a x2^b + x1^b x2^a) x3^l are evaluated as 25 (a,b)-groups,
 // each a Horner polynomial in x3 (SURVEY hard part 6): ~330 DFMA instead of ~1460 flops.
@@ -118,15 +134,19 @@ __device__ __forceinline__ double ps_h2o_energy(const double (&x)[9])
 {
     const double d1x = x[6] - x[0], d1y = x[7] - x[1], d1z = x[8] - x[2];
     const double d2x = x[6] - x[3], d2y = x[7] - x[4], d2z = x[8] - x[5];
-    const double r1s = d1x * d1x + d1y * d1y + d1z * d1z;
-    const double r2s = d2x * d2x + d2y * d2y + d2z * d2z;
+    const double r1s = fmax(d1x * d1x + d1y * d1y + d1z * d1z, 1e-30);
+    const double r2s = fmax(d2x * d2x + d2y * d2y + d2z * d2z, 1e-30);
     const double ct = d1x * d2x + d1y * d2y + d1z * d2z;
-    const double r1 = sqrt(r1s), r2 = sqrt(r2s);
-    const double costh = ct / (r1 * r2);
+    // 1/r and r from one float-seeded Newton iteration chain each (two steps: 22 -> 44 -> 88 bits, then one residual
+    // correction of r): about a third of the instructions of sqrt() + a division, same result to 1-2 ulp
+    const double y1 = ps_rsqrt(r1s), y2 = ps_rsqrt(r2s);
+    const double r1 = ps_sqrt_from(r1s, y1), r2 = ps_sqrt_from(r2s, y2);
+    const double costh = ct * (y1 * y2);
     const double a1 = r1 - c_ps.reoh, a2 = r2 - c_ps.reoh;
     const double x1 = a1 * c_ps.inv_reoh, x2 = a2 * c_ps.inv_reoh;
     const double x3 = costh - c_ps.ce;
-    const double rhh = sqrt(fmax(r1s + r2s - 2.0 * ct, 0.0));
+    const double rhh2 = fmax(r1s + r2s - 2.0 * ct, 1e-30);
+    const double rhh = ps_sqrt_from(rhh2, ps_rsqrt(rhh2));
     const double vhh = c_ps.phh1 * exp(-c_ps.phh2 * rhh);
     const double e1 = exp(-c_ps.alphaoh * (r1 - c_ps.roh));
     const double e2 = exp(-c_ps.alphaoh * (r2 - c_ps.roh));
