@@ -141,6 +141,9 @@ int pvd_coulomb_descriptor(const double *xyz, int64_t n, int32_t natoms, const d
  * replaces the state + per-step body of DMC_Sim.propagate (pyvibdmc.py:701-876). */
 typedef struct pvd_sim pvd_sim;   /* opaque */
 
+enum { PVD_IMP_STANDARD = 0,            /* imp_move_randomly (pyvibdmc.py:549-612) */
+       PVD_IMP_SECOND_DISPLACEMENT = 1  /* imp_move_randomly_second_type (pyvibdmc.py:614-649) */ };
+
 typedef struct {
     int32_t natoms, ndim;
     int32_t weighting;            /* PVD_WEIGHT_* */
@@ -158,6 +161,8 @@ typedef struct {
     double masses[PVD_MAX_ATOMS];
     double pot_params[PVD_MAX_COMP]; /* HARMONIC: k[c]; MORSE1D: de, alpha */
     int64_t stats_ring;           /* length of the per-step statistics ring (>= steps between drains) */
+    int32_t imp_variant;          /* PVD_IMP_*: which importance-sampling move (pyvibdmc.py:549-612 or :614-649) */
+    int32_t reserved_;
 } pvd_config;
 
 /* per-step record written by the step kernel's finalisation (one per executed step) */

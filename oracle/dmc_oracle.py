@@ -289,7 +289,7 @@ class Draws:
 
 
 def dmc_loop(coords, masses, dt, n0, nsteps, potential, draws, weighting='discrete', cont_thresh=(None, None),
-             wts=None, equil=None, wfn_every=None, desc_steps=None, trial=None, imp1d_derivs=None):
+             wts=None, equil=None, wfn_every=None, desc_steps=None, trial=None, imp1d_derivs=None, second_disp=False):
     """Restatement of DMC_Sim.propagate (pyvibdmc.py:701-876) for the BASELINE configs:
     no checkpoints/logging, branch_every=1.  Returns dict(vref, pop, coords, pots, wts, wfns, eff_ts)."""
     coords = np.array(coords, dtype=np.float64)
@@ -336,12 +336,17 @@ def dmc_loop(coords, masses, dt, n0, nsteps, potential, draws, weighting='discre
         if not imp:                                               # :540-547
             coords = coords + draws.normal(sig, coords.shape)
             dt_eff = dt
-        else:                                                     # :549-612
-            if f_x is None:
+        else:                                                     # :549-612 ; second_disp: :614-649
+            disps = draws.normal(sig, coords.shape) if second_disp else None
+            if second_disp:
+                coords = coords + disps                           # the diffusion part is never rejected
                 f_x, psi1, sec = drift(coords)
-            disps = draws.normal(sig, coords.shape)
+            elif f_x is None:
+                f_x, psi1, sec = drift(coords)
+            if not second_disp:
+                disps = draws.normal(sig, coords.shape)
             d_x = inv_m3 * f_x
-            y = coords + disps + d_x * dt
+            y = coords + d_x * dt if second_disp else coords + disps + d_x * dt
             f_y, psi2, sec_y = drift(y)
             d_y = inv_m3 * f_y
             acc = metropolis(sig3, psi1, psi2, coords, y, d_x, d_y, dt)

@@ -16,6 +16,7 @@ MASSIVE_MSG = "Massive walker birth or death event!!!!!!! Dying..."
 PVD_OK, PVD_E_CUDA, PVD_E_ARG, PVD_E_MASSIVE, PVD_E_STATE, PVD_E_NODEVICE = range(6)
 POT_EXTERNAL, POT_HARMONIC, POT_H2O_PS, POT_MORSE1D, POT_NN_H4O2 = range(5)
 TRIAL_NONE, TRIAL_HARM1D, TRIAL_H2O_FD = range(3)
+IMP_STANDARD, IMP_SECOND_DISPLACEMENT = range(2)
 WEIGHT_DISCRETE, WEIGHT_CONTINUOUS = 0, 1
 RNG_FP64, RNG_FAST = 0, 1
 MAX_ATOMS, MAX_COMP, MAX_WORLD = 16, 48, 8
@@ -36,7 +37,8 @@ class PvdConfig(C.Structure):
                 ("world_size", C.c_int32), ("num_walkers", C.c_int64), ("capacity", C.c_int64),
                 ("delta_t", C.c_double), ("alpha", C.c_double), ("thresh_lower", C.c_double),
                 ("thresh_upper", C.c_double), ("seed", C.c_uint64), ("masses", C.c_double * MAX_ATOMS),
-                ("pot_params", C.c_double * MAX_COMP), ("stats_ring", C.c_int64)]
+                ("pot_params", C.c_double * MAX_COMP), ("stats_ring", C.c_int64), ("imp_variant", C.c_int32),
+                ("reserved_", C.c_int32)]
 
 
 class StepStats(C.Structure):

@@ -228,21 +228,23 @@ static int imp_enqueue_move(pvd_sim *s, StepArgs &a, const double *inj_um)
     im.inj_um = inj_um;
     const int g = s->grid;
     const bool fast = s->cfg.rng_mode == PVD_RNG_FAST;
+    const bool second = s->cfg.imp_variant == PVD_IMP_SECOND_DISPLACEMENT;
     double *x = s->x[s->cur].as<double>(), *f = s->f[s->cur].as<double>(), *psi = s->psi[s->cur].as<double>();
     double *lk = s->lk[s->cur].as<double>(), *v = s->v[s->cur].as<double>();
+#define LAUNCH_MOVE(T, P, R, S)                                                                                            \
+    do {                                                                                                                  \
+        PVD_CUDA(cudaFuncSetAttribute(k_imp_move<T, P, R, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));      \
+        k_imp_move<T, P, R, S><<<g, PVD_CTA, sm, s->stream>>>(a, im, x, f, psi, lk, v);                                    \
+    } while (0)
 #define CALL_MOVE(T, P)                                                                                 \
     do {                                                                                                \
         const size_t sm = (size_t)3 * T::NC * PVD_CTA * sizeof(double);                                  \
-        if (fast) {                                                                                     \
-            PVD_CUDA(cudaFuncSetAttribute(k_imp_move<T, P, PVD_RNG_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
-            k_imp_move<T, P, PVD_RNG_FAST><<<g, PVD_CTA, sm, s->stream>>>(a, im, x, f, psi, lk, v);      \
-        } else {                                                                                        \
-            PVD_CUDA(cudaFuncSetAttribute(k_imp_move<T, P, PVD_RNG_FP64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
-            k_imp_move<T, P, PVD_RNG_FP64><<<g, PVD_CTA, sm, s->stream>>>(a, im, x, f, psi, lk, v);      \
-        }                                                                                               \
+        if (second) { if (fast) LAUNCH_MOVE(T, P, PVD_RNG_FAST, true); else LAUNCH_MOVE(T, P, PVD_RNG_FP64, true); }      \
+        else { if (fast) LAUNCH_MOVE(T, P, PVD_RNG_FAST, false); else LAUNCH_MOVE(T, P, PVD_RNG_FP64, false); }           \
     } while (0)
     IMP_DISPATCH(CALL_MOVE);
 #undef CALL_MOVE
+#undef LAUNCH_MOVE
     PVD_CHECK_LAUNCH();
     return PVD_OK;
 }

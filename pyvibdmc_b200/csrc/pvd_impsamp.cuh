@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(PVD_CTA, 2) k_imp_init(const StepArgs a, const
 // imp_move_randomly (pyvibdmc.py:549-612) + potential + local energy (:786-812), in place.
 // Writes the accepted/kept walker, its drift, psi, local kinetic energy and E_L; counts acceptances.
 // The last CTA publishes dt_eff = dt * n_accept / N (pyvibdmc.py:603, 372-378) for the branching kernel.
-template <class TRIAL, class POT, int RNG>
+template <class TRIAL, class POT, int RNG, bool SECOND>
 __global__ void __launch_bounds__(PVD_CTA, 2) k_imp_move(const StepArgs a, const ImpArgs im, double *x, double *f, double *psi, double *lk, double *v)
 {
     constexpr int NC = TRIAL::NC;
@@ -262,24 +262,40 @@ __global__ void __launch_bounds__(PVD_CTA, 2) k_imp_move(const StepArgs a, const
     const int tid = threadIdx.x;
     for (long long i = blockIdx.x * (long long)PVD_CTA + threadIdx.x; i < n; i += (long long)gridDim.x * PVD_CTA) {
         double xx[NC];
-        {
+        double psi_x, ke_x = 0.0;
+        // the Gaussian displacement (injected or Philox + Box-Muller), scaled by sigma
+        if (a.inj_disp) {
+#pragma unroll
+            for (int c = 0; c < NC; ++c) xx[c] = a.inj_disp[c * a.cap + i];
+        } else {
+            walker_normals<NC, RNG>(a.seed, i, step, xx);
+#pragma unroll
+            for (int c = 0; c < NC; ++c) xx[c] = __dmul_rn(a.sigc[c], xx[c]);
+        }
+        if constexpr (!SECOND) {
+            // imp_move_randomly (:549-612): displaced = coords + disps + (inv_m * f_x) * dt, f_x and psi carried from the last step
             double xo[NC], fo[NC];
 #pragma unroll
             for (int c = 0; c < NC; ++c) { xo[c] = x[c * a.cap + i]; fo[c] = f[c * a.cap + i]; }
-            if (a.inj_disp) {
-#pragma unroll
-                for (int c = 0; c < NC; ++c) xx[c] = a.inj_disp[c * a.cap + i];
-            } else {
-                walker_normals<NC, RNG>(a.seed, i, step, xx);
-#pragma unroll
-                for (int c = 0; c < NC; ++c) xx[c] = __dmul_rn(a.sigc[c], xx[c]);
-            }
-            // displaced = coords + disps + (inv_m * f_x) * dt
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
                 xx[c] = __dadd_rn(__dadd_rn(xo[c], xx[c]), __dmul_rn(__dmul_rn(im.inv_mass[c / TRIAL::NDIM], fo[c]), a.dt));
                 s_xf[c][tid] = xo[c];
                 s_xf[NC + c][tid] = fo[c];
+                s_xf[2 * NC + c][tid] = xx[c];
+            }
+            psi_x = psi[i];
+        } else {
+            // imp_move_randomly_second_type (:614-649): the diffusion step is always taken, the drift is evaluated at the
+            // diffused position and only the drift step displaced = x' + (inv_m * f_x') * dt goes through Metropolis
+#pragma unroll
+            for (int c = 0; c < NC; ++c) { xx[c] = __dadd_rn(x[c * a.cap + i], xx[c]); s_xf[c][tid] = xx[c]; }
+            double f1[NC];
+            trial_drift_ke<TRIAL>(xx, im.trial, im.inv_mass, psi_x, f1, ke_x);
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                xx[c] = __dadd_rn(s_xf[c][tid], __dmul_rn(__dmul_rn(im.inv_mass[c / TRIAL::NDIM], f1[c]), a.dt));
+                s_xf[NC + c][tid] = f1[c];
                 s_xf[2 * NC + c][tid] = xx[c];
             }
         }
@@ -291,13 +307,20 @@ __global__ void __launch_bounds__(PVD_CTA, 2) k_imp_move(const StepArgs a, const
             double fo[NC];
 #pragma unroll
             for (int c = 0; c < NC; ++c) { xo[c] = s_xf[c][tid]; fo[c] = s_xf[NC + c][tid]; y[c] = s_xf[2 * NC + c][tid]; }
-            acc = metropolis_ratio<NC, TRIAL::NDIM>(xo, y, fo, fy, psi[i], psi_y, a.sigma, im.inv_mass, a.dt);
+            acc = metropolis_ratio<NC, TRIAL::NDIM>(xo, y, fo, fy, psi_x, psi_y, a.sigma, im.inv_mass, a.dt);
+            if constexpr (SECOND) {
+                // rejected walkers keep x' with ITS drift / psi / kinetic energy: store them now, overwritten below on acceptance
+#pragma unroll
+                for (int c = 0; c < NC; ++c) { x[c * a.cap + i] = xo[c]; f[c * a.cap + i] = fo[c]; }
+                psi[i] = psi_x;
+                lk[i] = ke_x;
+            }
         }
         double u;
         if (im.inj_um) u = im.inj_um[i];
         else { const uint4 r = pvd_draw(a.seed, i, step, PVD_STREAM_METRO, 0u); u = u53(r.x, r.y); }
         const bool ok = acc > u;
-        double ke = lk[i];
+        double ke = SECOND ? ke_x : lk[i];
         if (ok) {
             ke = ke_new;
 #pragma unroll

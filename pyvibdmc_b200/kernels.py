@@ -201,7 +201,8 @@ class DeviceSim:
 
     def __init__(self, natoms, ndim, masses, num_walkers, delta_t, potential, weighting="discrete", alpha=None,
                  capacity=None, seed=0, rng_mode=_capi.RNG_FP64, trial=_capi.TRIAL_NONE, pot_params=None,
-                 thresh_lower=None, thresh_upper=None, device=0, rank=0, world_size=1, stats_ring=1 << 16):
+                 thresh_lower=None, thresh_upper=None, device=0, rank=0, world_size=1, stats_ring=1 << 16,
+                 imp_variant=_capi.IMP_STANDARD):
         cfg = _capi.PvdConfig()
         cfg.natoms, cfg.ndim = int(natoms), int(ndim)
         cfg.weighting = _capi.WEIGHT_CONTINUOUS if weighting == "continuous" else _capi.WEIGHT_DISCRETE
@@ -222,6 +223,7 @@ class DeviceSim:
             for i, p in enumerate(np.asarray(pot_params, dtype=np.float64).reshape(-1)):
                 cfg.pot_params[i] = p
         cfg.stats_ring = int(stats_ring)
+        cfg.imp_variant = int(imp_variant)
         self.cfg = cfg
         self.natoms, self.ndim = int(natoms), int(ndim)
         self.capacity = cfg.capacity

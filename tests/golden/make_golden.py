@@ -297,6 +297,21 @@ def gen_traj():
              imp_samp_oned=True)
 
 
+def gen_traj_variants():
+    """Loop variants of SURVEY 8 f-3: second importance-sampling displacement (pyvibdmc.py:614-649)."""
+    sys.path.insert(0, f"{REF}/pyvibdmc/sample_potentials/PythonPots")
+    import harmonicOscillator1D as ho
+    hopot = pv.Potential_Direct(potential_function=ho.oh_stretch_harm)
+    wpot = pv.Potential_Direct(potential_function=water_pot)
+    run_traj("h2o_imp2", "discrete", 200, 12, ["H", "H", "O"], EQ[None] * 1.01, wpot, 1.0, 8, imp=water_manager(),
+             equil=4, wfn=6, desc=3, second_impsamp_displacement=True)
+    d = f"{REF}/pyvibdmc/sample_potentials/PythonPots"
+    man = pv.ImpSampManager_NoMP(trial_function='trial_harm', trial_directory=d, python_file='harm_trial_wfn.py',
+                                 deriv_function='derivative')
+    run_traj("ho_imp2", "discrete", 300, 40, ['O-H'], np.zeros((1, 1, 1)), hopot, 5.0, 9, imp=man,
+             imp_samp_oned=True, second_impsamp_displacement=True)
+
+
 # ---------------------------------------------------------------- H. NN descriptor
 def gen_descriptor():
     from pyvibdmc.simulation_utilities.tensorflow_descriptors.distance_descriptors import DistIt
@@ -311,7 +326,10 @@ def gen_descriptor():
 
 if __name__ == "__main__":
     try:
-        gen_pes(); gen_ho(); gen_branch_discrete(); gen_branch_continuous(); gen_vref_desc()
-        gen_impsamp(); gen_traj(); gen_descriptor()
+        gens = {"pes": gen_pes, "ho": gen_ho, "branch_discrete": gen_branch_discrete, "branch_continuous": gen_branch_continuous,
+                "vref_desc": gen_vref_desc, "impsamp": gen_impsamp, "traj": gen_traj, "traj_variants": gen_traj_variants,
+                "descriptor": gen_descriptor}
+        for name in (sys.argv[1:] or list(gens)):          # default: everything; or name the generators to (re)run
+            gens[name]()
     finally:
         shutil.rmtree(TMP, ignore_errors=True)

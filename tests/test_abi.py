@@ -29,8 +29,8 @@ def test_library_builds_and_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header():
     from pyvibdmc_b200 import _capi
-    # pvd_config: 9 int32 (+pad) + 2 int64 + 4 double + uint64 + 16 + 48 doubles + int64
-    assert ctypes.sizeof(_capi.PvdConfig) == 40 + 16 + 32 + 8 + 8 * 16 + 8 * 48 + 8
+    # pvd_config: 9 int32 (+pad) + 2 int64 + 4 double + uint64 + 16 + 48 doubles + int64 + 2 int32
+    assert ctypes.sizeof(_capi.PvdConfig) == 40 + 16 + 32 + 8 + 8 * 16 + 8 * 48 + 8 + 8
     assert ctypes.sizeof(_capi.StepStats) == 96
 
 

@@ -270,3 +270,16 @@ def test_training_dump_before_birth_death(pv, tmp_path):
         d = read_h5(f"{out}/v_training_{t}ts.hdf5")
         n_before = 2000 if t == 0 else int(pop[t - 1])
         assert len(d['coords']) == n_before                   # collected after the move, before birth/death of step t
+
+
+def test_second_impsamp_displacement_through_dmc_sim(pv, tmp_path):
+    """pyvibdmc.py:614-649 through the user API: exact trial wfn => zero-variance estimator also with the second move type."""
+    d = sample_dir(pv, "PythonPots")
+    imp = pv.ImpSampManager_NoMP(trial_function='trial_harm', trial_directory=d, python_file='harm_trial_wfn.py',
+                                 deriv_function='derivative')
+    sim = pv.DMC_Sim(sim_name="ho2", output_folder=str(tmp_path / "i2"), num_walkers=1000, num_timesteps=300, equil_steps=100,
+                     chkpt_every=200, wfn_every=100, desc_wt_steps=20, atoms=['O-H'], delta_t=5, potential=ho_potential(pv),
+                     start_structures=np.zeros((1, 1, 1)), imp_samp=imp, imp_samp_oned=True, second_impsamp_displacement=True, seed=2)
+    sim.run()
+    assert np.allclose(sim._vref_vs_tau / WN, 1850.0, atol=1e-6) and (sim._pop_vs_tau == 1000).all()
+    assert sim.walkers.std() > 0.05           # the walkers do move (diffusion is never rejected)
