@@ -177,6 +177,10 @@ typedef struct {
     int64_t step;                 /* propagation step index this record belongs to */
 } pvd_step_stats;
 
+/* sizeof(pvd_config) / sizeof(pvd_step_stats) as this library was compiled: lets a binding check its struct layouts */
+int pvd_sizeof_config(void);
+int pvd_sizeof_step_stats(void);
+
 int pvd_sim_create(const pvd_config *cfg, pvd_sim **out);
 int pvd_sim_destroy(pvd_sim *s);
 /* use an externally owned stream (e.g. torch.cuda.current_stream().cuda_stream); 0 = legacy default stream.

@@ -58,6 +58,8 @@ _I64, _I32, _F64, _U64 = C.c_int64, C.c_int32, C.c_double, C.c_uint64
 # name -> (restype, argtypes); must list every function declared in include/pvd_b200.h
 SIGNATURES = {
     "pvd_abi_version": (C.c_int, []),
+    "pvd_sizeof_config": (C.c_int, []),
+    "pvd_sizeof_step_stats": (C.c_int, []),
     "pvd_last_error": (C.c_char_p, []),
     "pvd_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "pvd_set_device": (C.c_int, [C.c_int]),
@@ -143,6 +145,8 @@ def load(rebuild_if_stale=True):
         fn.restype, fn.argtypes = res, args
     if handle.pvd_abi_version() != 1:
         raise PvdError("libpvd_b200.so ABI version mismatch")
+    if handle.pvd_sizeof_config() != C.sizeof(PvdConfig) or handle.pvd_sizeof_step_stats() != C.sizeof(StepStats):
+        raise PvdError("libpvd_b200.so struct layout differs from the ctypes binding (stale build?)")
     _lib = handle
     return _lib
 

@@ -68,6 +68,8 @@ static inline int grid_for(long long n, int per_block, int max_waves = 8)
 extern "C" {
 
 int pvd_abi_version(void) { return PVD_ABI_VERSION; }
+int pvd_sizeof_config(void) { return (int)sizeof(pvd_config); }
+int pvd_sizeof_step_stats(void) { return (int)sizeof(pvd_step_stats); }
 const char *pvd_last_error(void) { return g_pvd_err.c_str(); }
 int64_t pvd_launch_count(void) { return (int64_t)g_pvd_launches.load(); }
 int pvd_last_kernel_ms(double *ms) { PVD_REQUIRE(ms, "ms is NULL"); *ms = g_last_kernel_ms; return PVD_OK; }
