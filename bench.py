@@ -324,14 +324,20 @@ def main():
         cb = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(cb)
         sim.close()
-        others = cb.collect(("c1", "c3", "c4", "c5"), large_only=False, steps=100)
+        try:
+            others = cb.collect(("c1", "c3", "c4", "c5"), large_only=False, steps=100)
+        except Exception as e:             # never lose the headline line to a side measurement
+            others = {"error": repr(e)}
         others["note"] = ("steady-state device-resident loop, CUDA events inside pvd_sim_run; c1 = 1-D HO discrete, c3 = H2O continuous "
                           "(1e6/GPU), c4 = H2O importance sampling with finite-difference drift (1.25e6/GPU), c5 = (H2O)2 NN PES on tcgen05 "
                           "(1.25e7/GPU)")
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        cpu, _ = time_cpu_reference()
+        try:
+            cpu, _ = time_cpu_reference()
+        except Exception as e:
+            cpu = {"value": None, "unit": "walker-steps/s", "cores": os.cpu_count(), "kind": "port", "sample": "failed: " + repr(e)}
 
     line = {"metric": "walker-steps/s", "value": value, "unit": "walker-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
