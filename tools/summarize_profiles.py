@@ -85,7 +85,7 @@ def main():
                    "dram_read": rd, "dram_write": wr, "algorithmic_bytes_per_launch": 152e6,
                    "note": "writes of the compacted ensemble mostly stay in the 126 MB L2 until the next step reads them"},
                   open(os.path.join(OUT, "r01_step_kernel_traffic.json"), "w"), indent=1)
-    for f in ("zpe_validation.json", "BENCH_local.json", "BENCH_8gpu.json"):
+    for f in ("zpe_validation.json", "BENCH_local.json", "BENCH_8gpu_mailbox.json", "BENCH_8gpu_nccl.json"):
         src = os.path.join(G, f)
         if os.path.exists(src):
             open(os.path.join(OUT, "r01_" + f), "w").write(open(src).read())
