@@ -142,7 +142,8 @@ int pvd_coulomb_descriptor(const double *xyz, int64_t n, int32_t natoms, const d
 typedef struct pvd_sim pvd_sim;   /* opaque */
 
 enum { PVD_IMP_STANDARD = 0,            /* imp_move_randomly (pyvibdmc.py:549-612) */
-       PVD_IMP_SECOND_DISPLACEMENT = 1  /* imp_move_randomly_second_type (pyvibdmc.py:614-649) */ };
+       PVD_IMP_SECOND_DISPLACEMENT = 1, /* imp_move_randomly_second_type (pyvibdmc.py:614-649) */
+       PVD_IMP_EXCITED_STATE = 2        /* excited_state_imp_samp: capped drift + vector score (pyvibdmc.py:562-591, 608-611, 810-811) */ };
 
 typedef struct {
     int32_t natoms, ndim;

@@ -289,7 +289,7 @@ class Draws:
 
 
 def dmc_loop(coords, masses, dt, n0, nsteps, potential, draws, weighting='discrete', cont_thresh=(None, None),
-             wts=None, equil=None, wfn_every=None, desc_steps=None, trial=None, imp1d_derivs=None, second_disp=False):
+             wts=None, equil=None, wfn_every=None, desc_steps=None, trial=None, imp1d_derivs=None, second_disp=False, excited=False):
     """Restatement of DMC_Sim.propagate (pyvibdmc.py:701-876) for the BASELINE configs:
     no checkpoints/logging, branch_every=1.  Returns dict(vref, pop, coords, pots, wts, wfns, eff_ts)."""
     coords = np.array(coords, dtype=np.float64)
@@ -320,6 +320,7 @@ def dmc_loop(coords, masses, dt, n0, nsteps, potential, draws, weighting='discre
                 return d1, psi_fn(c), d2
             return drift_fd(c, trial)
         f_x = psi1 = sec = None
+    vscore = None
     for t in range(T):
         if t in wfn_steps:                                        # :739-745
             parent = coords.copy()
@@ -346,9 +347,30 @@ def dmc_loop(coords, masses, dt, n0, nsteps, potential, draws, weighting='discre
             if not second_disp:
                 disps = draws.normal(sig, coords.shape)
             d_x = inv_m3 * f_x
+            if excited:                                           # :562-574 capped drift, first vector score
+                d_x2 = d_x + 1e-50
+                ms = 1 / inv_m3[:, :, 0]
+                v2 = np.linalg.norm(d_x2, axis=2) ** 2
+                factor = np.divide(-1 + np.sqrt(1 + 2 * ms * v2), ms * v2)
+                d_x2 = factor[:, :, None] * d_x2
+                if vscore is None:
+                    numer = np.sum(np.linalg.norm(d_x2, axis=2) ** 2 * masses[None, :], axis=1)
+                    denom = np.sum(np.linalg.norm(d_x, axis=2) ** 2 * masses[None, :], axis=1)
+                    vscore = np.sqrt(numer / denom)
+                d_x = d_x2
             y = coords + d_x * dt if second_disp else coords + disps + d_x * dt
             f_y, psi2, sec_y = drift(y)
             d_y = inv_m3 * f_y
+            if excited:                                           # :581-591 (note: the factor scales d_y, not the shifted copy)
+                d_y2 = d_y + 1e-50
+                ms = 1 / inv_m3[:, :, 0]
+                v2 = np.linalg.norm(d_y2, axis=2) ** 2
+                factor = np.divide(-1 + np.sqrt(1 + 2 * ms * v2), ms * v2)
+                d_y2 = factor[:, :, None] * d_y
+                numer = np.sum(np.linalg.norm(d_y2, axis=2) ** 2 * masses[None, :], axis=1)
+                denom = np.sum(np.linalg.norm(d_y, axis=2) ** 2 * masses[None, :], axis=1)
+                vscore_new = np.sqrt(numer / denom)
+                d_y = d_y2
             acc = metropolis(sig3, psi1, psi2, coords, y, d_x, d_y, dt)
             u = draws.uniform(len(coords))
             ok = acc > u
@@ -356,17 +378,23 @@ def dmc_loop(coords, masses, dt, n0, nsteps, potential, draws, weighting='discre
             f_x = np.where(ok[:, None, None], f_y, f_x)
             psi1 = np.where(ok, psi2, psi1)
             sec = np.where(ok[:, None, None], sec_y, sec)
+            if excited:
+                vscore = np.where(ok, vscore_new, vscore)         # :608-609
             dt_eff = dt * (np.count_nonzero(ok) / len(coords))    # :603, :372-378
             eff[t] = dt_eff if t == 0 else eff[t - 1] + dt_eff
         pots = potential(coords)                                  # :786-793
         if imp:
             pots = pots + local_kin(inv_m3, sec)                  # :807-809
+            if excited:
+                pots = vref - (vref - pots) * vscore              # :810-811
         if not cont:                                              # :391-431
             u = draws.uniform(len(coords))
             _, idx, _, _, _ = birth_or_death_discrete(pots, vref, dt_eff, u, n0)
             coords, pots = coords[idx], pots[idx]
             if imp:
                 f_x, psi1, sec = f_x[idx], psi1[idx], sec[idx]
+                if excited:
+                    vscore = vscore[idx]                          # :427-428
             if desc_on:
                 who = who[idx]
             vref = calc_vref(pots, n0, alpha)

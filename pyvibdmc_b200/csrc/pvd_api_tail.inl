@@ -51,6 +51,7 @@ static void cont_in_place(pvd_sim *s, StepArgs &a)
     a.xin = a.xout = s->x[s->cur].as<double>();
     a.vin = a.vout = s->v[s->cur].as<double>();
     a.who_in = a.who_out = s->who[s->cur].as<int>();
+    if (s->cfg.imp_variant == PVD_IMP_EXCITED_STATE) a.vsin = a.vsout = s->vs[s->cur].as<double>();
     a.flip = 0;
 }
 
@@ -132,7 +133,8 @@ extern "C" int pvd_branch_continuous(double *w, const double *v, int64_t n, doub
 static int fill_trial_params(pvd_sim *s, ImpArgs &im)
 {
     memset(&im, 0, sizeof(im));
-    for (int a = 0; a < PVD_MAX_ATOMS; ++a) im.inv_mass[a] = s->inv_mass[a];
+    for (int a = 0; a < PVD_MAX_ATOMS; ++a) { im.inv_mass[a] = s->inv_mass[a]; im.mass[a] = s->cfg.masses[a]; }
+    im.vscore = s->cfg.imp_variant == PVD_IMP_EXCITED_STATE ? s->vs[s->cur].as<double>() : nullptr;
     im.trial = s->trial_params;
     im.acc_count = s->acc_count.as<unsigned long long>();
     if (s->cfg.trial == PVD_TRIAL_H2O_FD && !s->trial_table.p) return pvd_fail(PVD_E_STATE, "water trial wfn: call pvd_sim_set_trial_table first");
@@ -228,7 +230,7 @@ static int imp_enqueue_move(pvd_sim *s, StepArgs &a, const double *inj_um)
     im.inj_um = inj_um;
     const int g = s->grid;
     const bool fast = s->cfg.rng_mode == PVD_RNG_FAST;
-    const bool second = s->cfg.imp_variant == PVD_IMP_SECOND_DISPLACEMENT;
+    const int variant = s->cfg.imp_variant;
     double *x = s->x[s->cur].as<double>(), *f = s->f[s->cur].as<double>(), *psi = s->psi[s->cur].as<double>();
     double *lk = s->lk[s->cur].as<double>(), *v = s->v[s->cur].as<double>();
 #define LAUNCH_MOVE(T, P, R, S)                                                                                            \
@@ -239,8 +241,13 @@ static int imp_enqueue_move(pvd_sim *s, StepArgs &a, const double *inj_um)
 #define CALL_MOVE(T, P)                                                                                 \
     do {                                                                                                \
         const size_t sm = (size_t)3 * T::NC * PVD_CTA * sizeof(double);                                  \
-        if (second) { if (fast) LAUNCH_MOVE(T, P, PVD_RNG_FAST, true); else LAUNCH_MOVE(T, P, PVD_RNG_FP64, true); }      \
-        else { if (fast) LAUNCH_MOVE(T, P, PVD_RNG_FAST, false); else LAUNCH_MOVE(T, P, PVD_RNG_FP64, false); }           \
+        if (variant == PVD_IMP_SECOND_DISPLACEMENT) {                                                   \
+            if (fast) LAUNCH_MOVE(T, P, PVD_RNG_FAST, PVD_IMP_SECOND_DISPLACEMENT); else LAUNCH_MOVE(T, P, PVD_RNG_FP64, PVD_IMP_SECOND_DISPLACEMENT); \
+        } else if (variant == PVD_IMP_EXCITED_STATE) {                                                  \
+            if (fast) LAUNCH_MOVE(T, P, PVD_RNG_FAST, PVD_IMP_EXCITED_STATE); else LAUNCH_MOVE(T, P, PVD_RNG_FP64, PVD_IMP_EXCITED_STATE); \
+        } else {                                                                                        \
+            if (fast) LAUNCH_MOVE(T, P, PVD_RNG_FAST, PVD_IMP_STANDARD); else LAUNCH_MOVE(T, P, PVD_RNG_FP64, PVD_IMP_STANDARD); \
+        }                                                                                               \
     } while (0)
     IMP_DISPATCH(CALL_MOVE);
 #undef CALL_MOVE

@@ -278,7 +278,7 @@ struct pvd_sim {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     // walker arrays (ping-pong for discrete compaction)
-    DevBuf x[2], v[2], who[2], w, f[2], psi[2], lk[2];
+    DevBuf x[2], v[2], who[2], w, f[2], psi[2], lk[2], vs[2];
     DevBuf st, err_accum, status, part, ring, sums, sigma_dev, tickets;
     DevBuf inj_disp, inj_u, inj_um, stage, stage2;   // staging for host<->device transposes / injections
     DevBuf parent_x, parent_w;
@@ -321,6 +321,7 @@ static StepArgs make_args(pvd_sim *s, int do_branch)
         a.fin = s->f[in].as<double>(); a.fout = s->f[out].as<double>();
         a.psin = s->psi[in].as<double>(); a.psout = s->psi[out].as<double>();
         a.lkin = s->lk[in].as<double>(); a.lkout = s->lk[out].as<double>();
+        if (s->cfg.imp_variant == PVD_IMP_EXCITED_STATE) { a.vsin = s->vs[in].as<double>(); a.vsout = s->vs[out].as<double>(); }
     }
     a.st = s->st.as<DevState>();
     a.err_accum = s->err_accum.as<unsigned>();
@@ -392,6 +393,8 @@ extern "C" {
 int pvd_sim_create(const pvd_config *cfg, pvd_sim **out)
 {
     PVD_REQUIRE(cfg && out, "NULL argument");
+    PVD_REQUIRE(cfg->imp_variant >= PVD_IMP_STANDARD && cfg->imp_variant <= PVD_IMP_EXCITED_STATE, "unknown imp_variant");
+    PVD_REQUIRE(cfg->imp_variant != PVD_IMP_EXCITED_STATE || (cfg->trial != PVD_TRIAL_NONE && cfg->ndim == 3), "excited-state importance sampling needs a trial wave function over 3-D atoms");
     PVD_REQUIRE(cfg->natoms >= 1 && cfg->natoms <= PVD_MAX_ATOMS && cfg->ndim >= 1 && cfg->ndim <= 3, "bad natoms/ndim");
     PVD_REQUIRE(cfg->num_walkers >= 1 && cfg->capacity >= 1 && cfg->delta_t > 0, "bad num_walkers/capacity/delta_t");
     PVD_REQUIRE(cfg->world_size >= 1 && cfg->world_size <= PVD_MAX_WORLD && cfg->rank >= 0 && cfg->rank < cfg->world_size, "bad rank/world_size");
@@ -428,6 +431,7 @@ int pvd_sim_create(const pvd_config *cfg, pvd_sim **out)
             TRY(s->f[b].alloc((size_t)cap * nc * 8));
             TRY(s->psi[b].alloc((size_t)cap * 8));
             TRY(s->lk[b].alloc((size_t)cap * 8));
+            if (cfg->imp_variant == PVD_IMP_EXCITED_STATE) TRY(s->vs[b].alloc((size_t)cap * 8));
         }
     }
     if (cfg->weighting == PVD_WEIGHT_CONTINUOUS) {

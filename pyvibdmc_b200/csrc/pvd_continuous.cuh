@@ -537,6 +537,7 @@ __global__ void __launch_bounds__(PVD_CTA) k_cont_copy(const StepArgs a, const C
             for (int c = 0; c < a.nc; ++c) f[c * a.cap + dst] = f[c * a.cap + src];
             psi[dst] = psi[src];
             lk[dst] = lk[src];
+            if (a.vsout) a.vsout[dst] = a.vsout[src];
         }
         if (src_out) src_out[dst] = src;
     }

@@ -256,13 +256,14 @@ __global__ void __launch_bounds__(PVD_CTA, 2) k_branch_discrete(const StepArgs a
                 {
                     const double v = a.vout ? a.vin[pi_] : 0.0;
                     const int who = dw ? a.who_in[pi_] : 0;
-                    const double ps = a.fin ? a.psin[pi_] : 0.0, lk = a.fin ? a.lkin[pi_] : 0.0;
+                    const double ps = a.fin ? a.psin[pi_] : 0.0, lk = a.fin ? a.lkin[pi_] : 0.0, vs = a.vsin ? a.vsin[pi_] : 0.0;
 #pragma unroll 1
                     for (int k = 0; k < pc; ++k) {
                         if (a.vout) a.vout[o + k] = v;
                         if (dw) a.who_out[o + k] = who;
                         if (a.idx_out) a.idx_out[o + k] = pi_;
                         if (a.fin) { a.psout[o + k] = ps; a.lkout[o + k] = lk; }
+                        if (a.vsin) a.vsout[o + k] = vs;
                     }
                 }
             }

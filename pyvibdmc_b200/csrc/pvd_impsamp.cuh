@@ -183,10 +183,10 @@ __device__ __forceinline__ void trial_drift_ke(double (&xx)[TRIAL::NC], const Tr
 }
 
 // ImpSamp.metropolis (imp_samp.py:29-47) for one walker
+// dx_ / dy_ are the drift vectors D = (1/m) f (capped for excited-state importance sampling) at x and y
 template <int NC, int NDIM>
-__device__ __forceinline__ double metropolis_ratio(const double (&x)[NC], const double (&y)[NC], const double (&fx)[NC],
-                                                   const double (&fy)[NC], double psi_x, double psi_y, const double *sigma,
-                                                   const double *inv_mass, double dt)
+__device__ __forceinline__ double metropolis_ratio(const double (&x)[NC], const double (&y)[NC], const double (&dx_)[NC],
+                                                   const double (&dy_)[NC], double psi_x, double psi_y, const double *sigma, double dt)
 {
     constexpr int ndim = NDIM, natoms = NC / NDIM;
     const double q = psi_y / psi_x;
@@ -200,7 +200,7 @@ __device__ __forceinline__ double metropolis_ratio(const double (&x)[NC], const 
         for (int a = 0; a < natoms; ++a) {
             const int c = a * ndim + d;
             const double inv_two_s2 = 0.5 / __dmul_rn(sigma[a], sigma[a]);
-            const double dxm = __dmul_rn(__dmul_rn(inv_mass[a], fx[c]), dt), dym = __dmul_rn(__dmul_rn(inv_mass[a], fy[c]), dt);
+            const double dxm = __dmul_rn(dx_[c], dt), dym = __dmul_rn(dy_[c], dt);
             const double u1 = __dadd_rn(__dadd_rn(x[c], -y[c]), -dym);
             const double u2 = __dadd_rn(__dadd_rn(y[c], -x[c]), -dxm);
             expo = fma((u2 - u1) * (u2 + u1), inv_two_s2, expo);
@@ -211,9 +211,42 @@ __device__ __forceinline__ double metropolis_ratio(const double (&x)[NC], const 
     return acc;
 }
 
+// excited_state_imp_samp (pyvibdmc.py:562-591): per atom the drift vector is shortened by
+// factor = (-1 + sqrt(1 + 2 m v^2)) / (m v^2), v^2 = |D + 1e-50|^2; the vector score is sqrt(sum_a m_a |D'_a|^2 / sum_a m_a |D_a|^2).
+// shifted: the reference scales the shifted copy for D_x (:568) but the unshifted vector for D_y (:586).
+template <int NC>
+__device__ __forceinline__ double cap_drift(const double (&d)[NC], const double *inv_mass, const double *mass, bool shifted,
+                                            double (&dc)[NC])
+{
+    static_assert(NC % 3 == 0, "excited-state drift capping is written for 3-D atoms");
+    double numer = 0.0, denom = 0.0;
+#pragma unroll
+    for (int a = 0; a < NC / 3; ++a) {
+        const double ms = 1.0 / inv_mass[a];
+        const double sx = d[3 * a] + 1e-50, sy = d[3 * a + 1] + 1e-50, sz = d[3 * a + 2] + 1e-50;
+        const double nrm = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(sx, sx), __dmul_rn(sy, sy)), __dmul_rn(sz, sz)));
+        const double v2 = __dmul_rn(nrm, nrm);
+        const double msv2 = __dmul_rn(ms, v2);
+        const double factor = (-1.0 + sqrt(__dadd_rn(1.0, __dmul_rn(__dmul_rn(2.0, ms), v2)))) / msv2;
+        dc[3 * a] = __dmul_rn(factor, shifted ? sx : d[3 * a]);
+        dc[3 * a + 1] = __dmul_rn(factor, shifted ? sy : d[3 * a + 1]);
+        dc[3 * a + 2] = __dmul_rn(factor, shifted ? sz : d[3 * a + 2]);
+        const double n2 = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dc[3 * a], dc[3 * a]), __dmul_rn(dc[3 * a + 1], dc[3 * a + 1])),
+                                         __dmul_rn(dc[3 * a + 2], dc[3 * a + 2])));
+        const double n1 = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(d[3 * a], d[3 * a]), __dmul_rn(d[3 * a + 1], d[3 * a + 1])),
+                                         __dmul_rn(d[3 * a + 2], d[3 * a + 2])));
+        const double tn = __dmul_rn(__dmul_rn(n2, n2), mass[a]), td = __dmul_rn(__dmul_rn(n1, n1), mass[a]);
+        numer = (a == 0) ? tn : __dadd_rn(numer, tn);
+        denom = (a == 0) ? td : __dadd_rn(denom, td);
+    }
+    return sqrt(numer / denom);
+}
+
 struct ImpArgs {
     TrialParamsDev trial;
     double inv_mass[PVD_MAX_ATOMS];
+    double mass[PVD_MAX_ATOMS];
+    double *vscore;            // excited-state importance sampling: per-walker vector score (in place), else nullptr
     const double *inj_um;      // injected Metropolis uniforms or nullptr
     unsigned long long *acc_count;   // accepted moves of this shard in the current step
 };
@@ -233,6 +266,14 @@ __global__ void __launch_bounds__(PVD_CTA, 2) k_imp_init(const StepArgs a, const
         for (int c = 0; c < NC; ++c) xx[c] = x[c * a.cap + i];
         trial_drift<TRIAL>(xx, im.trial, p0, d1, d2);
         const double ke = local_kinetic<NC, TRIAL::NDIM>(d2, im.inv_mass);
+        if constexpr (NC % 3 == 0) {
+            if (im.vscore) {                       // vector score of the start ensemble (pyvibdmc.py:570-573)
+                double dr[NC], dcap[NC];
+#pragma unroll
+                for (int c = 0; c < NC; ++c) dr[c] = __dmul_rn(im.inv_mass[c / 3], d1[c]);
+                im.vscore[i] = cap_drift<NC>(dr, im.inv_mass, im.mass, true, dcap);
+            }
+        }
 #pragma unroll
         for (int c = 0; c < NC; ++c) f[c * a.cap + i] = d1[c];
         psi[i] = p0;
@@ -244,14 +285,16 @@ __global__ void __launch_bounds__(PVD_CTA, 2) k_imp_init(const StepArgs a, const
 // imp_move_randomly (pyvibdmc.py:549-612) + potential + local energy (:786-812), in place.
 // Writes the accepted/kept walker, its drift, psi, local kinetic energy and E_L; counts acceptances.
 // The last CTA publishes dt_eff = dt * n_accept / N (pyvibdmc.py:603, 372-378) for the branching kernel.
-template <class TRIAL, class POT, int RNG, bool SECOND>
+template <class TRIAL, class POT, int RNG, int VAR>
 __global__ void __launch_bounds__(PVD_CTA, 2) k_imp_move(const StepArgs a, const ImpArgs im, double *x, double *f, double *psi, double *lk, double *v)
 {
     constexpr int NC = TRIAL::NC;
+    constexpr bool SECOND = VAR == PVD_IMP_SECOND_DISPLACEMENT, EXCITED = VAR == PVD_IMP_EXCITED_STATE && NC % 3 == 0;
     __shared__ unsigned s_cnt[PVD_WARPS];
     __shared__ unsigned s_last;
     DevState *sip = &a.st[a.parity];
     if (sip->err || sip->n <= 0) return;           // the branching kernel forwards the dead state
+    const double vref_now = sip->vref;
     const long long n = sip->n, step = sip->step;
     unsigned my_acc = 0;
     // the walker's current position and drift, and the proposed position, wait in shared memory (thread-private
@@ -277,9 +320,18 @@ __global__ void __launch_bounds__(PVD_CTA, 2) k_imp_move(const StepArgs a, const
             double xo[NC], fo[NC];
 #pragma unroll
             for (int c = 0; c < NC; ++c) { xo[c] = x[c * a.cap + i]; fo[c] = f[c * a.cap + i]; }
+            // slot 1 of the stash holds the drift vector D_x = (1/m) f_x (capped in the excited-state variant)
+#pragma unroll
+            for (int c = 0; c < NC; ++c) fo[c] = __dmul_rn(im.inv_mass[c / TRIAL::NDIM], fo[c]);
+            if constexpr (EXCITED) {
+                double dcap[NC];
+                cap_drift<NC>(fo, im.inv_mass, im.mass, true, dcap);
+#pragma unroll
+                for (int c = 0; c < NC; ++c) fo[c] = dcap[c];
+            }
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
-                xx[c] = __dadd_rn(__dadd_rn(xo[c], xx[c]), __dmul_rn(__dmul_rn(im.inv_mass[c / TRIAL::NDIM], fo[c]), a.dt));
+                xx[c] = __dadd_rn(__dadd_rn(xo[c], xx[c]), __dmul_rn(fo[c], a.dt));
                 s_xf[c][tid] = xo[c];
                 s_xf[NC + c][tid] = fo[c];
                 s_xf[2 * NC + c][tid] = xx[c];
@@ -295,19 +347,31 @@ __global__ void __launch_bounds__(PVD_CTA, 2) k_imp_move(const StepArgs a, const
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
                 xx[c] = __dadd_rn(s_xf[c][tid], __dmul_rn(__dmul_rn(im.inv_mass[c / TRIAL::NDIM], f1[c]), a.dt));
-                s_xf[NC + c][tid] = f1[c];
+                s_xf[NC + c][tid] = f1[c];                                  // the drift itself: rejected walkers keep it
                 s_xf[2 * NC + c][tid] = xx[c];
             }
         }
         double fy[NC], psi_y, ke_new;
         trial_drift_ke<TRIAL>(xx, im.trial, im.inv_mass, psi_y, fy, ke_new);
         double xo[NC], y[NC];
-        double acc;
+        double acc, vs_new = 1.0;
         {
             double fo[NC];
 #pragma unroll
             for (int c = 0; c < NC; ++c) { xo[c] = s_xf[c][tid]; fo[c] = s_xf[NC + c][tid]; y[c] = s_xf[2 * NC + c][tid]; }
-            acc = metropolis_ratio<NC, TRIAL::NDIM>(xo, y, fo, fy, psi_x, psi_y, a.sigma, im.inv_mass, a.dt);
+            double dy[NC];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) dy[c] = __dmul_rn(im.inv_mass[c / TRIAL::NDIM], fy[c]);
+            if constexpr (SECOND) {
+                double dxv[NC];
+#pragma unroll
+                for (int c = 0; c < NC; ++c) dxv[c] = __dmul_rn(im.inv_mass[c / TRIAL::NDIM], fo[c]);
+                acc = metropolis_ratio<NC, TRIAL::NDIM>(xo, y, dxv, dy, psi_x, psi_y, a.sigma, a.dt);
+            } else if constexpr (EXCITED) {
+                double dcap[NC];
+                vs_new = cap_drift<NC>(dy, im.inv_mass, im.mass, false, dcap);
+                acc = metropolis_ratio<NC, TRIAL::NDIM>(xo, y, fo, dcap, psi_x, psi_y, a.sigma, a.dt);
+            } else acc = metropolis_ratio<NC, TRIAL::NDIM>(xo, y, fo, dy, psi_x, psi_y, a.sigma, a.dt);
             if constexpr (SECOND) {
                 // rejected walkers keep x' with ITS drift / psi / kinetic energy: store them now, overwritten below on acceptance
 #pragma unroll
@@ -329,7 +393,13 @@ __global__ void __launch_bounds__(PVD_CTA, 2) k_imp_move(const StepArgs a, const
             lk[i] = ke;
             ++my_acc;
         }
-        v[i] = __dadd_rn(POT::eval(xo, a.pot), ke);
+        double el = __dadd_rn(POT::eval(xo, a.pot), ke);
+        if constexpr (EXCITED) {
+            const double vs = ok ? vs_new : im.vscore[i];
+            if (ok) im.vscore[i] = vs;
+            el = vref_now - (vref_now - el) * vs;                           // pyvibdmc.py:810-811
+        }
+        v[i] = el;
     }
     // acceptance count -> dt_eff
     for (int off = 16; off > 0; off >>= 1) my_acc += __shfl_xor_sync(0xffffffffu, my_acc, off);
@@ -388,7 +458,9 @@ __global__ void k_metropolis_aos(const double *x, const double *y, const double 
 #pragma unroll
         for (int k = 0; k < NC; ++k) { a[k] = x[i * NC + k]; b[k] = y[i * NC + k]; c[k] = fx[i * NC + k]; d[k] = fy[i * NC + k]; }
         (void)ndim;
-        acc[i] = metropolis_ratio<NC, (NC == 9 ? 3 : 1)>(a, b, c, d, psx[i], psy[i], sigma, inv_mass, dt);
+#pragma unroll
+        for (int k = 0; k < NC; ++k) { c[k] = __dmul_rn(inv_mass[k / (NC == 9 ? 3 : 1)], c[k]); d[k] = __dmul_rn(inv_mass[k / (NC == 9 ? 3 : 1)], d[k]); }
+        acc[i] = metropolis_ratio<NC, (NC == 9 ? 3 : 1)>(a, b, c, d, psx[i], psy[i], sigma, dt);
     }
 }
 

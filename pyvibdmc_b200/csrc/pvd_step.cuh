@@ -28,6 +28,8 @@ struct StepArgs {
     double *psout;
     const double *lkin;
     double *lkout;
+    const double *vsin;         // excited-state importance sampling: vector score (pyvibdmc.py:570-573, 608-609), else nullptr
+    double *vsout;
     // control
     DevState *st;               // st[2], indexed by step parity
     unsigned *tickets;          // [2][PVD_WARPS * PVD_TICKET_STRIDE], indexed by step parity

@@ -82,9 +82,8 @@ class DMC_Sim:
         self._device = int(device)
         self._dev = None
         self._host_rng = np.random.default_rng(self._seed ^ 0x5DEECE66D)      # fixed-node recrossing draws (host side)
-        # the one variant of the importance-sampling move that has no device kernel yet
-        if excited_state_imp_samp:
-            raise NotImplementedError("excited_state_imp_samp is not implemented on the B200 path")
+        if excited_state_imp_samp and (imp_samp_oned or second_impsamp_displacement):
+            raise NotImplementedError("excited_state_imp_samp is implemented for 3-D atoms with the standard move only")
         # variants that call back into user Python once per step run in the per-step (hosted) mode:
         # the GPU moves, weights and branches; the host sees the coordinates like a user potential would
         self._hooked = bool(adiabatic_dmc is not None or fixed_node is not None
@@ -282,7 +281,8 @@ class DMC_Sim:
                                       thresh_lower=getattr(self, '_thresh_lower', None),
                                       thresh_upper=getattr(self, '_thresh_upper', None), device=self._device,
                                       stats_ring=max(4096, min(1 << 20, int(self.num_timesteps) + 8)),
-                                      imp_variant=(_capi.IMP_SECOND_DISPLACEMENT if self.second_impsamp_displacement else _capi.IMP_STANDARD))
+                                      imp_variant=(_capi.IMP_SECOND_DISPLACEMENT if self.second_impsamp_displacement else
+                                                   _capi.IMP_EXCITED_STATE if self.excited_state_imp_samp else _capi.IMP_STANDARD))
         self._builtin = pot is not None
         if pot is not None and pot_id == _capi.POT_NN_H4O2:
             self._dev.set_nn_weights(pot["weights"])

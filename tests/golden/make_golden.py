@@ -312,6 +312,13 @@ def gen_traj_variants():
              imp_samp_oned=True, second_impsamp_displacement=True)
 
 
+def gen_traj_excited():
+    """excited_state_imp_samp (pyvibdmc.py:562-591, 810-811): capped drift + vector score."""
+    wpot = pv.Potential_Direct(potential_function=water_pot)
+    run_traj("h2o_imp_exc", "discrete", 200, 12, ["H", "H", "O"], EQ[None] * 1.01, wpot, 1.0, 10, imp=water_manager(),
+             equil=4, wfn=6, desc=3, excited_state_imp_samp=True)
+
+
 # ---------------------------------------------------------------- H. NN descriptor
 def gen_descriptor():
     from pyvibdmc.simulation_utilities.tensorflow_descriptors.distance_descriptors import DistIt
@@ -327,7 +334,7 @@ def gen_descriptor():
 if __name__ == "__main__":
     try:
         gens = {"pes": gen_pes, "ho": gen_ho, "branch_discrete": gen_branch_discrete, "branch_continuous": gen_branch_continuous,
-                "vref_desc": gen_vref_desc, "impsamp": gen_impsamp, "traj": gen_traj, "traj_variants": gen_traj_variants,
+                "vref_desc": gen_vref_desc, "impsamp": gen_impsamp, "traj": gen_traj, "traj_variants": gen_traj_variants, "traj_excited": gen_traj_excited,
                 "descriptor": gen_descriptor}
         for name in (sys.argv[1:] or list(gens)):          # default: everything; or name the generators to (re)run
             gens[name]()

@@ -274,6 +274,28 @@ def test_replay_second_impsamp_displacement_trajectories(K):
     sim.close()
 
 
+def test_replay_excited_state_impsamp_trajectory(K):
+    """excited_state_imp_samp (pyvibdmc.py:562-591, 608-611, 810-811) replayed with the reference's draws."""
+    from pyvibdmc_b200 import _capi
+    g = golden("traj_h2o_imp_exc_golden.npz")
+    rp = Replay(g)
+    sim = K.DeviceSim(3, 3, g["masses"], 200, 1.0, _capi.POT_H2O_PS, trial=_capi.TRIAL_H2O_FD, imp_variant=_capi.IMP_EXCITED_STATE)
+    sim.set_trial_table(water_table())
+    sim.upload(np.repeat(EQ[None] * 1.01, 200, 0))
+    T, n = 12, 200
+    vref, pop, dts = np.zeros(T), np.zeros(T), np.zeros(T)
+    for t in range(T):
+        disp = rp.normal(n, 3, 3)
+        um, ub = rp.take(n), rp.take(n)
+        sim.step_injected(disp, ub, um)
+        st = sim.stats(t, 1)
+        vref[t], pop[t], dts[t] = st["vref"][0], st["pop"][0], st["dt_eff"][0]
+        n = int(pop[t])
+    assert np.array_equal(pop, g["pop"])
+    assert np.allclose(vref, g["vref"], rtol=1e-8) and np.allclose(np.cumsum(dts), g["eff_ts"], rtol=1e-13)
+    sim.close()
+
+
 def test_impsamp_free_running_zpe(K, oracle):
     """Importance-sampled water: local energy fluctuates far less than V; ZPE stays near 4634 cm-1."""
     from pyvibdmc_b200 import _capi

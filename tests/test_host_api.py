@@ -85,7 +85,7 @@ def test_constructor_validation_matches_reference(tmp_path):
     with pytest.raises(ValueError, match="Invalid input for continuous weight threshold"):
         pv.DMC_Sim(start_structures=np.zeros((1, 1, 1)), weighting='continuous', cont_wt_thresh="x", **kw)
     with pytest.raises(NotImplementedError):
-        pv.DMC_Sim(start_structures=np.zeros((1, 1, 1)), excited_state_imp_samp=True, **kw)
+        pv.DMC_Sim(start_structures=np.zeros((1, 1, 1)), excited_state_imp_samp=True, imp_samp_oned=True, **kw)
     with pytest.raises(ValueError, match="Number of mass change steps"):
         pv.DMC_Sim(start_structures=np.zeros((1, 1, 1)), DEBUG_mass_change={'change_every': 2, 'factor_per_change': np.ones(5)}, **kw)
     # adiabatic DMC set-up: lambda ramp after the equilibration plateau (reference pyvibdmc.py:276-291)

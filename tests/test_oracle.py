@@ -196,3 +196,14 @@ def test_traj_second_impsamp_displacement(oracle):
     out = oracle.dmc_loop(np.zeros((300, 1, 1)), g["masses"], 5.0, 300, 40, oracle.oh_stretch_harm, draws,
                           equil=5, wfn_every=10, desc_steps=4, imp1d_derivs=(oracle.trial_harm, oracle.harm_derivs), second_disp=True)
     assert np.array_equal(out["pop"], g["pop"]) and np.allclose(out["vref"], g["vref"], rtol=1e-12)
+
+
+def test_traj_excited_state_impsamp(oracle):
+    """excited_state_imp_samp (pyvibdmc.py:562-591, 608-611, 810-811): capped drift and vector score."""
+    g, draws = _replay(oracle, "h2o_imp_exc")
+    table = np.load(os.path.join(os.path.dirname(__file__), "..", "pyvibdmc_b200", "sample_potentials",
+                                 "FortPots", "Partridge_Schwenke_H2O", "free_oh_wvfn_table.npy"))
+    out = oracle.dmc_loop(np.repeat(EQ[None] * 1.01, 200, 0), g["masses"], 1.0, 200, 12, oracle.water_pot, draws,
+                          equil=4, wfn_every=6, desc_steps=3, trial=oracle.WaterTrial(table), excited=True)
+    assert np.array_equal(out["pop"], g["pop"])
+    assert np.allclose(out["vref"], g["vref"], rtol=1e-9) and np.allclose(out["eff_ts"], g["eff_ts"], rtol=1e-14)
