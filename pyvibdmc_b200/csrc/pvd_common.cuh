@@ -43,13 +43,12 @@ static inline int pvd_fail(int code, const std::string &msg)
 static const char *const PVD_MASSIVE_MSG = "Massive walker birth or death event!!!!!!! Dying...";
 
 // ---------------------------------------------------------------- tiling
-// A tile is one warp's worth of walkers.  Every warp of the (persistent) grid takes tiles from
-// ticket counters, one counter per warp slot of a CTA so that no single address sees more than
-// 1/PVD_WARPS of the atomics; nothing in the step kernels uses __syncthreads or shared memory.
+// A tile is one warp's worth of walkers (light kernels: a few such sub-tiles).  Every warp of the (persistent) grid
+// takes tiles from one ticket counter per step parity; the tile loops of the step kernels have no __syncthreads.
 constexpr int PVD_TILE = 32;           // walkers per tile == one warp, one walker per lane
 constexpr int PVD_CTA = 256;           // threads per CTA
 constexpr int PVD_WARPS = PVD_CTA / 32;
-constexpr int PVD_TICKET_STRIDE = 32;  // uints between ticket counters (128 B: one per L2 line)
+constexpr int PVD_TICKET_STRIDE = 32;  // uints between the two parities' ticket counters (128 B: one per L2 line)
 
 // error bits kept in DevState::err
 enum : unsigned {
@@ -194,21 +193,6 @@ __device__ __forceinline__ double warp_max(double v)
     return v;
 }
 
-// next tile for this warp (-1: none left).  tickets: PVD_WARPS counters, PVD_TICKET_STRIDE apart.
-// Warp slot w of any CTA draws t from counter w and owns tile t*PVD_WARPS + w, so tile ids are
-// handed out in increasing order within each slot class and the smallest unfinished tile is
-// always either running with all its predecessors done or about to be taken (no deadlock even
-// when only part of the grid is resident).
-__device__ __forceinline__ long long warp_take_tile(unsigned *tickets, long long ntiles)
-{
-    const int lane = threadIdx.x & 31;
-    unsigned t = 0;
-    if (lane == 0) t = atomicAdd(&tickets[0], 1u);
-    t = __shfl_sync(0xffffffffu, t, 0);
-    const long long tile = (long long)t;
-    return tile < ntiles ? tile : -1;
-}
-
 // Tickets in batches: a ticket t covers tiles [t*batch, (t+1)*batch).  One counter serves about one atomic per
 // 2-2.5 ns whatever the grid, so kernels with light tiles take several tiles per ticket; tile ids are still
 // handed out in increasing order, which is all the look-back needs.
@@ -286,9 +270,4 @@ __device__ __forceinline__ long long resolve_prefix(unsigned long long *status, 
     }
     if (lane == 0) st_relaxed_u64(&status[tile], pack_status(step, PVD_ST_PREFIX, (unsigned)(running + tile_total)));
     return running;
-}
-__device__ __forceinline__ long long warp_lookback(unsigned long long *status, long long tile, long long step, int tile_total)
-{
-    publish_aggregate(status, tile, step, tile_total);
-    return resolve_prefix(status, tile, step, tile_total);
 }

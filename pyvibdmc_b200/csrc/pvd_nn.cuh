@@ -2,12 +2,11 @@
 // (TensorflowPots/call_sample_model.py:4-9; descriptor: tensorflow_descriptors/distance_descriptors.py
 // :102-113,154-168; model layout read from sample_h4o2_nn.h5: Dense(120,swish) x3, Dense(1,relu), float32).
 //
-// Round-1 implementation: float32 FMA on the CUDA cores.  A CTA of 128 threads owns a tile of 64
-// walkers; activations live in shared memory k-major ([feature][walker]) so that one LDS.128
-// feeds four FMAs, thread j accumulates output neuron j for all 64 walkers in registers, weights
-// stream through L1 (row k of a layer is one coalesced 480-byte read per CTA).
-// TODO(round 2): move the three 120x120 layers onto tcgen05 (M = 128 walkers, K/N padded to 128,
-// accumulators in TMEM, swish in the epilogue) -- see DESIGN.md.
+// Three kernels, newest last in this file:
+//   k_nn_h4o2      float32 FMA on the CUDA cores (cross-check path, PVD_NN_FP32=1): a CTA of 128 threads owns 64
+//                  walkers; activations live in shared memory k-major so that one LDS.128 feeds four FMAs
+//   k_nn_h4o2_tc   tcgen05, activations staged through shared memory, one tile in flight (PVD_NN_TC1=1)
+//   k_nn_h4o2_tc2  tcgen05, activations in TMEM, two tiles in flight (default)
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
