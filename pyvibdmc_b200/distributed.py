@@ -15,7 +15,7 @@ import numpy as np
 
 from . import _capi, kernels
 
-__all__ = ["plan_rebalance", "shard_bounds", "ShardedSim"]
+__all__ = ["plan_rebalance", "shard_bounds", "ShardedSim", "ShardedDevice"]
 
 
 def shard_bounds(n_total, world):
@@ -188,3 +188,96 @@ class ShardedSim:
 
     def close(self):
         self.sim.close()
+
+
+class ShardedDevice:
+    """`kernels.DeviceSim`-shaped facade over ShardedSim, used by DMC_Sim when it runs under torch.distributed:
+    every rank executes the same DMC_Sim code; counts, histories and downloaded arrays are GLOBAL (rank-major order),
+    so each rank could write the reference's output files (DMC_Sim lets rank 0 write into the real folder)."""
+
+    def __init__(self, natoms, ndim, masses, num_walkers, delta_t, potential, weighting="discrete", alpha=None, capacity=None,
+                 seed=0, rng_mode=_capi.RNG_FP64, trial=_capi.TRIAL_NONE, pot_params=None, thresh_lower=None, thresh_upper=None,
+                 device=0, stats_ring=1 << 16, imp_variant=_capi.IMP_STANDARD, trial_table=None, rebalance_every=250):
+        if alpha is not None and abs(alpha - 1.0 / (2.0 * delta_t)) > 1e-15:
+            raise NotImplementedError("DEBUG_alpha with a sharded run")
+        if imp_variant != _capi.IMP_STANDARD:
+            raise NotImplementedError("importance-sampling move variants with a sharded run")
+        self.ss = ShardedSim(natoms, ndim, masses, num_walkers, delta_t, potential, weighting=weighting, seed=seed, rng_mode=rng_mode,
+                             pot_params=pot_params, thresh_lower=thresh_lower, thresh_upper=thresh_upper, stats_ring=stats_ring,
+                             trial=trial, trial_table=trial_table, rebalance_every=rebalance_every)
+        self.natoms, self.ndim, self.cfg = natoms, ndim, self.ss.sim.cfg
+        self.rank, self.world = self.ss.rank, self.ss.world
+
+    # -- helpers
+    def _gather_rows(self, a):
+        """Concatenate per-rank arrays with the same trailing shape along axis 0, rank-major, on every rank."""
+        torch, dist = self.ss.torch, self.ss.dist
+        a = np.ascontiguousarray(a)
+        n = torch.tensor([a.shape[0]], dtype=torch.int64, device=self.ss.device)
+        sizes = [torch.zeros_like(n) for _ in range(self.world)]
+        dist.all_gather(sizes, n)
+        sizes = [int(x.item()) for x in sizes]
+        m = max(sizes + [1])
+        pad = torch.zeros((m,) + a.shape[1:], dtype=torch.from_numpy(a[:0]).dtype, device=self.ss.device)
+        if a.shape[0]:
+            pad[:a.shape[0]] = torch.from_numpy(a).to(self.ss.device)
+        bufs = [torch.empty_like(pad) for _ in range(self.world)]
+        dist.all_gather(bufs, pad)
+        return np.concatenate([b[:k].cpu().numpy() for b, k in zip(bufs, sizes)], axis=0)
+
+    # -- set-up
+    def set_nn_weights(self, packed):
+        self.ss.sim.set_nn_weights(packed)
+
+    def set_trial_table(self, table, ntab=None):
+        pass                                   # handed to ShardedSim at construction
+
+    def upload(self, coords, wts=None):
+        start, count = shard_bounds(len(coords), self.world)[self.rank]
+        self.ss.upload(np.ascontiguousarray(coords[start:start + count]), None if wts is None else np.ascontiguousarray(wts[start:start + count]))
+
+    def set_pots(self, v):
+        raise NotImplementedError("a sharded DMC_Sim needs a built-in potential")
+
+    def set_masses(self, masses):
+        self.ss.sim.set_masses(masses)
+
+    # -- stepping
+    def run(self, nsteps, branch_every=1):
+        self.ss.run(nsteps, branch_every)
+
+    def sync(self):
+        self.ss.stream.synchronize()
+
+    # -- descendant weighting
+    def dw_begin(self):
+        self.ss.dw_begin()
+
+    def dw_end(self, n_parent):
+        return self.ss.dw_end()
+
+    def dw_peek(self, n_parent):
+        raise NotImplementedError("DEBUG_save_desc_wt_tracker with a sharded run")
+
+    def dw_parent(self):
+        xyz, w = self.ss.dw_parent()
+        return self._gather_rows(xyz), (None if w is None else self._gather_rows(w))
+
+    # -- queries (global views)
+    def state(self, raise_on_error=True):
+        st = self.ss.sim.state(raise_on_error=raise_on_error)
+        st["n"] = sum(self.ss.populations())
+        return st
+
+    def stats(self, first_step, count):
+        return self.ss.stats(first_step, count)
+
+    def download(self, who_from=False, out=None):
+        d = self.ss.sim.download(who_from=who_from)
+        return {k: (None if v is None else self._gather_rows(v)) for k, v in d.items()}
+
+    def download_imp(self):
+        return tuple(self._gather_rows(a) for a in self.ss.sim.download_imp())
+
+    def close(self):
+        self.ss.close()

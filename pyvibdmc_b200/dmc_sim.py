@@ -31,6 +31,7 @@ __all__ = ['DMC_Sim', 'dmc_restart']
 
 MASSIVE = "Massive walker birth or death event!!!!!!! Dying..."
 _NOT_PICKLED = ('potential', 'potential_info', 'impsamp_manager', 'impsamp', 'imp_info', 'adiabatic_dmc', 'ad_obs_func',
+                '_world', '_rank',
                 'fixed_node', 'fixed_node_func', 'g_mat', '_dev', '_potential_obj')
 
 
@@ -44,7 +45,7 @@ class DMC_Sim:
                  log_every=1, cur_timestep=0, cont_wt_thresh=None, imp_samp=None, imp_samp_oned=False,
                  second_impsamp_displacement=False, excited_state_imp_samp=False, adiabatic_dmc=None, fixed_node=None,
                  DEBUG_alpha=None, DEBUG_save_desc_wt_tracker=None, DEBUG_save_training_every=None,
-                 DEBUG_save_before_bod=False, DEBUG_mass_change=None, *, seed=None, rng='fp64', device=0):
+                 DEBUG_save_before_bod=False, DEBUG_mass_change=None, *, seed=None, rng='fp64', device=0, distributed=None):
         self.atoms = atoms
         self.sim_name = sim_name
         self.output_folder = output_folder
@@ -81,6 +82,21 @@ class DMC_Sim:
         self._rng_mode = _capi.RNG_FAST if rng == 'fast' else _capi.RNG_FP64
         self._device = int(device)
         self._dev = None
+        # one process per GPU under torch.distributed (torchrun): every rank runs this same object, walkers are sharded,
+        # rank 0 writes the reference's output files, the other ranks write theirs (identical) into a scratch folder
+        self._world, self._rank = 1, 0
+        if distributed or distributed is None:
+            try:
+                import torch.distributed as dist
+                if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                    self._world, self._rank = dist.get_world_size(), dist.get_rank()
+            except ImportError:
+                pass
+            if distributed and self._world == 1:
+                raise RuntimeError("distributed=True needs torch.distributed initialised with more than one rank")
+        if self._rank > 0:
+            import tempfile
+            self.output_folder = tempfile.mkdtemp(prefix=f"pvd_rank{self._rank}_")
         self._host_rng = np.random.default_rng(self._seed ^ 0x5DEECE66D)      # fixed-node recrossing draws (host side)
         if excited_state_imp_samp and (imp_samp_oned or second_impsamp_displacement):
             raise NotImplementedError("excited_state_imp_samp is implemented for 3-D atoms with the standard move only")
@@ -274,6 +290,25 @@ class DMC_Sim:
             elif pot_id == _capi.POT_MORSE1D:
                 pot_params = [pot["de"], pot["alpha"]]
         cap = int(1.5 * max(self.num_walkers, len(self._walker_coords))) + 1024
+        if self._world > 1:
+            if pot is None:
+                raise NotImplementedError("a sharded DMC_Sim needs a built-in potential (walkers never leave the GPUs)")
+            from .distributed import ShardedDevice
+            self._dev = ShardedDevice(n_atoms, n_dim, self.masses, self.num_walkers, self.delta_t, pot_id, weighting=self.weighting,
+                                      alpha=self._alpha, seed=self._seed + 7919 * int(self.cur_timestep), rng_mode=self._rng_mode,
+                                      trial=(trial["trial"] if trial else _capi.TRIAL_NONE), pot_params=pot_params,
+                                      thresh_lower=getattr(self, '_thresh_lower', None), thresh_upper=getattr(self, '_thresh_upper', None),
+                                      stats_ring=max(4096, min(1 << 20, int(self.num_timesteps) + 8)),
+                                      imp_variant=(_capi.IMP_SECOND_DISPLACEMENT if self.second_impsamp_displacement else
+                                                   _capi.IMP_EXCITED_STATE if self.excited_state_imp_samp else _capi.IMP_STANDARD),
+                                      trial_table=(trial["table"] if trial else None))
+            self._builtin = True
+            if pot_id == _capi.POT_NN_H4O2:
+                self._dev.set_nn_weights(pot["weights"])
+            self._dev.upload(self._walker_coords, self._cont_wts)
+            self._dev_step0 = int(self.cur_timestep)
+            self._host_stale = False
+            return self._dev
         self._dev = kernels.DeviceSim(n_atoms, n_dim, self.masses, self.num_walkers, self.delta_t, pot_id,
                                       weighting=self.weighting, alpha=self._alpha, capacity=cap,
                                       seed=self._seed + 7919 * int(self.cur_timestep), rng_mode=self._rng_mode,
@@ -545,6 +580,8 @@ class DMC_Sim:
         self._potential_obj = None
         for k in ('adiabatic_dmc', 'fixed_node', 'impsamp_manager'):
             self.__dict__.setdefault(k, None)
+        self.__dict__.setdefault('_world', 1)
+        self.__dict__.setdefault('_rank', 0)
 
 
 def dmc_restart(potential, chkpt_folder, sim_name, additional_timesteps=0, impsamp=None, imp_samp_oned=False,

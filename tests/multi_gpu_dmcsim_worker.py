@@ -1,0 +1,47 @@
+"""Launched with torchrun by tests/test_gpu_multi.py: the drop-in DMC_Sim API on WORLD_SIZE GPUs (sharded walkers)."""
+import glob
+import json
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    import pyvibdmc_b200 as pv
+    from pyvibdmc_b200.simulation_utilities import h5lite
+    local = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank = dist.get_rank()
+    out = sys.argv[1]
+    eq = np.array([[1.81005599, 0., 0.], [-0.45344658, 1.75233806, 0.], [0., 0., 0.]])
+    d = os.path.join(os.path.dirname(pv.__file__), "sample_potentials", "FortPots", "Partridge_Schwenke_H2O")
+    pot = pv.Potential(potential_function='water_pot', python_file='h2o_potential.py', potential_directory=d, num_cores=1)
+    sim = pv.DMC_Sim(sim_name="w2", output_folder=out, weighting='discrete', num_walkers=20000, num_timesteps=600, equil_steps=100,
+                     chkpt_every=300, wfn_every=200, desc_wt_steps=50, atoms=['H', 'H', 'O'], delta_t=5, potential=pot,
+                     start_structures=eq[None] * 1.01, log_every=100, seed=3)
+    assert sim._world == dist.get_world_size() and (sim.output_folder == out) == (rank == 0)
+    sim.run()
+    walkers = sim.walkers
+    if rank == 0:
+        info = h5lite.read_h5(f"{out}/w2_sim_info.hdf5")
+        wf = sorted(os.path.basename(p) for p in glob.glob(f"{out}/wfns/*.hdf5"))
+        w = h5lite.read_h5(f"{out}/wfns/w2_wfn_300ts.hdf5")
+        pop = info['pop_vs_tau'][:, 1]
+        res = {"world": sim._world, "vref_shape": list(info['vref_vs_tau'].shape), "wfns": wf,
+               "zpe": float(info['vref_vs_tau'][300:, 1].mean() / 4.556335281212229e-6),
+               "desc_sum": float(w['desc_wts'].sum()), "pop_at_window_end": float(pop[349]), "n_parent": int(len(w['coords'])),
+               "pop_at_window_start": float(pop[299]), "final_walkers": int(len(walkers)), "final_pop": float(pop[-1]),
+               "chkpts": sorted(os.path.basename(p) for p in glob.glob(f"{out}/chkpts/*.pickle")),
+               "log_has_steps": "Time step 500" in open(f"{out}/w2_log.txt").read()}
+        print("RESULT " + json.dumps(res))
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -29,3 +29,22 @@ def test_two_gpu_sharded_run():
     imp = out["imp"]                                                             # importance sampling with the global acceptance fraction
     assert imp["same"] and 4350 < imp["zpe"] < 4900 and 0.9 < imp["dt_eff_mean"] <= 1.0 and 4000 < imp["pop_last"] < 12000
     assert 0 < imp["rejected_mean"] < 0.1 * 8000
+
+
+def test_two_gpu_dmc_sim_drop_in(tmp_path):
+    """The user API itself under torchrun: walkers sharded over 2 GPUs, rank 0 writes the reference's files."""
+    from pyvibdmc_b200 import kernels
+    if kernels.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    here = os.path.dirname(os.path.abspath(__file__))
+    out = str(tmp_path / "w2")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29618", os.path.join(here, "multi_gpu_dmcsim_worker.py"), out]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
+    r = json.loads([l for l in res.stdout.splitlines() if l.startswith("RESULT ")][-1][7:])
+    assert r["world"] == 2 and r["vref_shape"] == [600, 2] and r["log_has_steps"]
+    assert r["wfns"] == ["w2_wfn_100ts.hdf5", "w2_wfn_300ts.hdf5", "w2_wfn_500ts.hdf5"]
+    assert r["n_parent"] == int(r["pop_at_window_start"]) and r["desc_sum"] == r["pop_at_window_end"]
+    assert r["final_walkers"] == int(r["final_pop"]) and 4400 < r["zpe"] < 4850
+    assert len(r["chkpts"]) >= 1
