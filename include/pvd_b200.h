@@ -245,6 +245,13 @@ int pvd_sim_dw_parent(pvd_sim *s, double *xyz, double *w, int64_t *n_parent);
 /* blocking queries */
 int pvd_sim_sync(pvd_sim *s);
 int pvd_sim_state(pvd_sim *s, int64_t *n, double *vref, int64_t *step, int32_t *err);
+/* asynchronous snapshot (checkpoints / dumps, pyvibdmc.py:729-736, 861-872): _begin copies the walkers as they are now (in
+ * stream order) and sends them to pinned host memory on a side stream; the compute stream can be given the next time steps
+ * right away; _wait blocks only on the side-stream copy.  With all outputs NULL, _wait returns the walker count and leaves
+ * the snapshot pending. */
+int pvd_sim_snapshot_begin(pvd_sim *s);
+int pvd_sim_snapshot_wait(pvd_sim *s, double *xyz, double *pots, double *w, int64_t *who_from, int64_t capacity, int64_t *n_out,
+                          double *vref_out);
 int pvd_sim_download(pvd_sim *s, double *xyz, double *pots, double *w, int64_t *who_from, int64_t capacity, int64_t *n);
 int pvd_sim_stats(pvd_sim *s, int64_t first_step, int64_t count, pvd_step_stats *out);
 /* device time in ms between the first and last kernel of the most recent pvd_sim_run */

@@ -99,6 +99,8 @@ SIGNATURES = {
     "pvd_sim_set_sums_ptr": (C.c_int, [_P, _P]),
     "pvd_sim_step_local": (C.c_int, [_P, _I32]),
     "pvd_sim_step_finalize": (C.c_int, [_P]),
+    "pvd_sim_snapshot_begin": (C.c_int, [_P]),
+    "pvd_sim_snapshot_wait": (C.c_int, [_P, _P, _P, _P, _P, _I64, C.POINTER(_I64), C.POINTER(_F64)]),
     "pvd_sim_mailbox_handle": (C.c_int, [_P, _P]),
     "pvd_sim_mailbox_connect": (C.c_int, [_P, _P, _I32]),
     "pvd_sim_run_mailbox": (C.c_int, [_P, _I64, _I32]),

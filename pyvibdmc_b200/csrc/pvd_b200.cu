@@ -296,6 +296,14 @@ struct pvd_sim {
     bool uploaded = false, ext_moved = false;
     int grid = 1, grid_light = 1;
     int ticket_batch = 1;
+    // asynchronous snapshot (checkpoints / dumps): device copies on the compute stream, D2H on a side stream into pinned memory
+    DevBuf snap_x, snap_v, snap_w, snap_who, snap_state;
+    void *snap_host = nullptr;
+    size_t snap_host_bytes = 0;
+    cudaStream_t snap_stream = nullptr;
+    cudaEvent_t snap_ready = nullptr, snap_done = nullptr;
+    bool snap_pending = false;
+    int snap_parity = 0;
     DevBuf mbox;                                   // this rank's mailbox (NVLink collective)
     double *peer_mbox[PVD_MAX_WORLD]{};            // every rank's mailbox mapped here (own: mbox.p)
     bool mbox_connected = false, mbox_step = false;
@@ -498,6 +506,10 @@ int pvd_sim_destroy(pvd_sim *s)
     if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
     for (int r = 0; r < PVD_MAX_WORLD; ++r)
         if (s->peer_mbox[r] && s->peer_mbox[r] != s->mbox.p) cudaIpcCloseMemHandle(s->peer_mbox[r]);
+    if (s->snap_host) cudaFreeHost(s->snap_host);
+    if (s->snap_stream) cudaStreamDestroy(s->snap_stream);
+    if (s->snap_ready) cudaEventDestroy(s->snap_ready);
+    if (s->snap_done) cudaEventDestroy(s->snap_done);
     if (s->nn_w.packed) cudaFree(s->nn_w.packed);
     if (s->nn_w.images) cudaFree(s->nn_w.images);
     if (s->nn_w.vecs) cudaFree(s->nn_w.vecs);
@@ -992,6 +1004,83 @@ int pvd_sim_download(pvd_sim *s, double *xyz, double *pots, double *w, int64_t *
         PVD_CUDA(cudaMemcpyAsync(who_from, s->stage2.p, (size_t)n * 8, cudaMemcpyDeviceToHost, s->stream));
     }
     PVD_CUDA(cudaStreamSynchronize(s->stream));
+    return PVD_OK;
+}
+
+// ---- asynchronous snapshot: the walkers as they are NOW (in stream order) travel to the host on a side stream while the
+// compute stream goes on with the next time steps (checkpoints and dumps of the reference, pyvibdmc.py:729-736, 861-872)
+int pvd_sim_snapshot_begin(pvd_sim *s)
+{
+    SIM_CHECK(s);
+    SIM_DEVICE(s);
+    PVD_REQUIRE(s->uploaded, "pvd_sim_snapshot_begin: upload walkers first");
+    PVD_REQUIRE(!s->snap_pending, "a snapshot is already in flight: call pvd_sim_snapshot_wait first");
+    const int nc = s->nc;
+    const size_t cap = (size_t)s->cap;
+    const bool cont = s->w.p != nullptr;
+    if (!s->snap_stream) {
+        PVD_CUDA(cudaStreamCreateWithFlags(&s->snap_stream, cudaStreamNonBlocking));
+        PVD_CUDA(cudaEventCreateWithFlags(&s->snap_ready, cudaEventDisableTiming));
+        PVD_CUDA(cudaEventCreateWithFlags(&s->snap_done, cudaEventDisableTiming));
+        PVD_CUDA(s->snap_x.alloc(cap * nc * 8));
+        PVD_CUDA(s->snap_v.alloc(cap * 8));
+        PVD_CUDA(s->snap_who.alloc(cap * 4));
+        if (cont) PVD_CUDA(s->snap_w.alloc(cap * 8));
+        PVD_CUDA(s->snap_state.alloc(2 * sizeof(DevState)));
+        s->snap_host_bytes = cap * nc * 8 + cap * 8 * 2 + cap * 4 + 2 * sizeof(DevState);
+        PVD_CUDA(cudaMallocHost(&s->snap_host, s->snap_host_bytes));
+    }
+    // device-side copies in stream order (the whole capacity: the population is only known on the device)
+    k_soa_to_aos<<<grid_for((long long)cap * nc, 256, 16), 256, 0, s->stream>>>(s->x[s->cur].as<double>(), s->snap_x.as<double>(), (long long)cap, nc, s->cap);
+    PVD_CHECK_LAUNCH();
+    PVD_CUDA(cudaMemcpyAsync(s->snap_v.p, s->v[s->cur].p, cap * 8, cudaMemcpyDeviceToDevice, s->stream));
+    PVD_CUDA(cudaMemcpyAsync(s->snap_who.p, s->who[s->cur].p, cap * 4, cudaMemcpyDeviceToDevice, s->stream));
+    if (cont) PVD_CUDA(cudaMemcpyAsync(s->snap_w.p, s->w.p, cap * 8, cudaMemcpyDeviceToDevice, s->stream));
+    PVD_CUDA(cudaMemcpyAsync(s->snap_state.p, s->st.p, 2 * sizeof(DevState), cudaMemcpyDeviceToDevice, s->stream));
+    PVD_CUDA(cudaEventRecord(s->snap_ready, s->stream));
+    // device -> pinned host on the side stream
+    PVD_CUDA(cudaStreamWaitEvent(s->snap_stream, s->snap_ready, 0));
+    char *h = (char *)s->snap_host;
+    PVD_CUDA(cudaMemcpyAsync(h, s->snap_x.p, cap * nc * 8, cudaMemcpyDeviceToHost, s->snap_stream));
+    h += cap * nc * 8;
+    PVD_CUDA(cudaMemcpyAsync(h, s->snap_v.p, cap * 8, cudaMemcpyDeviceToHost, s->snap_stream));
+    h += cap * 8;
+    if (cont) PVD_CUDA(cudaMemcpyAsync(h, s->snap_w.p, cap * 8, cudaMemcpyDeviceToHost, s->snap_stream));
+    h += cap * 8;
+    PVD_CUDA(cudaMemcpyAsync(h, s->snap_who.p, cap * 4, cudaMemcpyDeviceToHost, s->snap_stream));
+    h += cap * 4;
+    PVD_CUDA(cudaMemcpyAsync(h, s->snap_state.p, 2 * sizeof(DevState), cudaMemcpyDeviceToHost, s->snap_stream));
+    PVD_CUDA(cudaEventRecord(s->snap_done, s->snap_stream));
+    s->snap_pending = true;
+    s->snap_parity = s->parity;
+    return PVD_OK;
+}
+
+// blocks only until the side-stream copy has landed (the compute stream is not synchronised); any output may be NULL
+int pvd_sim_snapshot_wait(pvd_sim *s, double *xyz, double *pots, double *w, int64_t *who_from, int64_t capacity, int64_t *n_out,
+                          double *vref_out)
+{
+    SIM_CHECK(s);
+    SIM_DEVICE(s);
+    PVD_REQUIRE(s->snap_pending, "no snapshot in flight");
+    PVD_CUDA(cudaEventSynchronize(s->snap_done));
+    const int nc = s->nc;
+    const size_t cap = (size_t)s->cap;
+    const char *h = (const char *)s->snap_host;
+    const DevState *st = reinterpret_cast<const DevState *>(h + cap * nc * 8 + cap * 8 * 2 + cap * 4);
+    const long long n = st[s->snap_parity].n;
+    if (n_out) *n_out = n;
+    if (vref_out) *vref_out = st[s->snap_parity].vref;
+    if (!xyz && !pots && !w && !who_from) return PVD_OK;          // size query: the snapshot stays pending
+    PVD_REQUIRE(capacity >= n, "pvd_sim_snapshot_wait: host buffers too small");
+    if (xyz) memcpy(xyz, h, (size_t)n * nc * 8);
+    if (pots) memcpy(pots, h + cap * nc * 8, (size_t)n * 8);
+    if (w && s->w.p) memcpy(w, h + cap * nc * 8 + cap * 8, (size_t)n * 8);
+    if (who_from) {
+        const int *src = reinterpret_cast<const int *>(h + cap * nc * 8 + cap * 8 * 2);
+        for (long long i = 0; i < n; ++i) who_from[i] = src[i];
+    }
+    s->snap_pending = false;
     return PVD_OK;
 }
 

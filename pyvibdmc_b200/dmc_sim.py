@@ -409,13 +409,18 @@ class DMC_Sim:
         while t < T:
             self.cur_timestep = t
             events = {}
+            async_chk = False
             if t in chk:
                 events["chkpt"] = True
-                self._pull_walkers()
-                FileManager.delete_older_checkpoints(self.output_folder, self.sim_name, t)
-                logger, self._logger = self._logger, None
-                SimArchivist.chkpt(self, t)
-                self._logger = logger
+                # resident single-GPU runs: the checkpoint travels to the host on a side stream while the next segment
+                # of time steps is already running; it is pickled below, after that segment has been enqueued
+                async_chk = (self._builtin and self._world == 1 and self.impsamp_manager is None and t not in wfn
+                             and hasattr(dev, "snapshot_begin"))
+                if async_chk:
+                    dev.snapshot_begin()
+                else:
+                    self._pull_walkers()
+                    self._write_chkpt(t)
             if t in wfn:
                 events["wfn"] = True
                 n_now = dev.state()["n"]
@@ -434,6 +439,14 @@ class DMC_Sim:
             tic = time.time()
             if self._builtin:
                 dev.run(nxt - t, self.branch_every)
+                if async_chk:
+                    snap = dev.snapshot_wait(who_from=self._desc_wt)
+                    self._walker_coords, self._walker_pots, self._vref = snap["coords"], snap["pots"], snap["vref"]
+                    if self.weighting == 'continuous':
+                        self._cont_wts = snap["wts"]
+                    if self._desc_wt:
+                        self._who_from = snap["who_from"]
+                    self._write_chkpt(t)
                 dev.sync()
             else:
                 events["pot_seconds"] = self._run_external(dev, t, nxt)
@@ -466,6 +479,12 @@ class DMC_Sim:
             t = nxt
             self.cur_timestep = t - 1
         self._pull_walkers()
+
+    def _write_chkpt(self, t):
+        FileManager.delete_older_checkpoints(self.output_folder, self.sim_name, t)
+        logger, self._logger = self._logger, None
+        SimArchivist.chkpt(self, t)
+        self._logger = logger
 
     def _run_external(self, dev, t0, t1):
         """User potential callable: the GPU moves / weights / branches, the callable sees the coordinates

@@ -368,6 +368,21 @@ class DeviceSim:
         check(lib.pvd_sim_download(self._h, ptr(xyz), ptr(pots), ptr(w), ptr(who), nn, C.byref(n)))
         return dict(coords=xyz, pots=pots, wts=w, who_from=who)
 
+    def snapshot_begin(self):
+        """Start an asynchronous copy of the ensemble as it is now (stream order) to pinned host memory on a side stream."""
+        check(lib.pvd_sim_snapshot_begin(self._h))
+
+    def snapshot_wait(self, who_from=False):
+        """Collect the snapshot started by snapshot_begin (does not synchronise the compute stream)."""
+        n, vref = C.c_int64(0), C.c_double(0)
+        check(lib.pvd_sim_snapshot_wait(self._h, None, None, None, None, 0, C.byref(n), C.byref(vref)))
+        nn = n.value
+        xyz, pots = np.empty((nn, self.natoms, self.ndim)), np.empty(nn)
+        w = np.empty(nn) if self.cfg.weighting == _capi.WEIGHT_CONTINUOUS else None
+        who = np.empty(nn, dtype=np.int64) if who_from else None
+        check(lib.pvd_sim_snapshot_wait(self._h, ptr(xyz), ptr(pots), ptr(w), ptr(who), nn, C.byref(n), C.byref(vref)))
+        return dict(coords=xyz, pots=pots, wts=w, who_from=who, vref=vref.value)
+
     def stats(self, first_step, count):
         out = np.zeros(int(count), dtype=_capi.STATS_DTYPE)
         if count:

@@ -172,3 +172,29 @@ def test_ho_zpe_free_running(K, oracle):
     zpe = st["vref"][1250:].mean() / WN
     assert abs(zpe - 1852) < 25, zpe
     sim.close()
+
+
+def test_async_snapshot_matches_download(K):
+    """pvd_sim_snapshot_begin/_wait: the ensemble at the moment of _begin, copied on a side stream while later steps run."""
+    from pyvibdmc_b200 import _capi
+    eq = np.array([[1.81005599, 0., 0.], [-0.45344658, 1.75233806, 0.], [0., 0., 0.]])
+    amu = 1.0 / 6.02213670000e23 / 9.10938970000e-28
+    m = np.array([1.00782503, 1.00782503, 15.99491462]) * amu
+    for weighting in ("discrete", "continuous"):
+        sim = K.DeviceSim(3, 3, m, 30000, 5.0, _capi.POT_H2O_PS, weighting=weighting, seed=3)
+        sim.upload(np.repeat(eq[None] * 1.01, 30000, axis=0))
+        sim.run(20)
+        sim.dw_begin()
+        sim.run(5)
+        ref = sim.download(who_from=True)
+        vref = sim.state()["vref"]
+        sim.snapshot_begin()
+        sim.run(40)                                  # the compute stream moves on while the copy is in flight
+        snap = sim.snapshot_wait(who_from=True)
+        assert sim.state()["step"] == 65
+        for k in ("coords", "pots", "who_from") + (("wts",) if weighting == "continuous" else ()):
+            assert np.array_equal(snap[k], ref[k]), k
+        assert snap["vref"] == vref
+        with pytest.raises(Exception):
+            sim.snapshot_wait()                      # nothing in flight any more
+        sim.close()
