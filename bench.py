@@ -325,11 +325,11 @@ def main():
         spec.loader.exec_module(cb)
         sim.close()
         try:
-            others = cb.collect(("c1", "c3", "c4", "c5"), large_only=False, steps=100)
+            others = cb.collect(("c1", "c3", "c4", "c4a", "c5"), large_only=False, steps=100)
         except Exception as e:             # never lose the headline line to a side measurement
             others = {"error": repr(e)}
         others["note"] = ("steady-state device-resident loop, CUDA events inside pvd_sim_run; c1 = 1-D HO discrete, c3 = H2O continuous "
-                          "(1e6/GPU), c4 = H2O importance sampling with finite-difference drift (1.25e6/GPU), c5 = (H2O)2 NN PES on tcgen05 "
+                          "(1e6/GPU), c4 = H2O importance sampling with finite-difference drift (1.25e6/GPU), c4a = the same with the reference's analytic derivatives, c5 = (H2O)2 NN PES on tcgen05 "
                           "(1.25e7/GPU)")
 
     cpu = None

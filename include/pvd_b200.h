@@ -51,8 +51,10 @@ enum {
 enum {
     PVD_TRIAL_NONE = 0,
     PVD_TRIAL_HARM1D = 1,  /* analytic Gaussian + derivatives: PythonPots/harm_trial_wfn.py:6-40 */
-    PVD_TRIAL_H2O_FD = 2   /* water product wfn, finite-difference derivatives:
-                              FortPots/.../call_trl_h2o.py:63-78 + imp_samp.py:56-76 */
+    PVD_TRIAL_H2O_FD = 2,  /* water product wfn, finite-difference derivatives:
+                              FortPots/.../call_trl_h2o.py:63-78 + imp_samp.py:56-76; table = [grid | psi | alpha, theta_eq] */
+    PVD_TRIAL_H2O_AN = 3   /* same wfn, analytic derivatives: call_trl_h2o.py:101-149 (dpsi_dx) + imp_samp_helper.py:10-209;
+                              table = [grid | psi | psi' | psi'' | alpha, theta_eq] */
 };
 
 enum { PVD_WEIGHT_DISCRETE = 0, PVD_WEIGHT_CONTINUOUS = 1 };

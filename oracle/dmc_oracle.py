@@ -110,6 +110,8 @@ class WaterTrial:
 
     def __init__(self, table):               # table rows: grid, psi  (free_oh_wvfn_dense.npy[0:2])
         self.grid, self.wfn = np.asarray(table[0]), np.asarray(table[1])
+        if len(table) >= 4:                  # rows psi', psi'' (analytic derivatives, call_trl_h2o.py:17-18)
+            self.dwfn, self.d2wfn = np.asarray(table[2]), np.asarray(table[3])
         inv_mh, inv_mo = 1 / mass('H'), 1 / mass('O')
         g = inv_mh / self.r1_eq ** 2 + inv_mh / self.r2_eq ** 2 + inv_mo * (
             1 / self.r1_eq ** 2 + 1 / self.r2_eq ** 2 - 2 * np.cos(self.theta_eq) / (self.r1_eq * self.r2_eq))
@@ -123,6 +125,68 @@ class WaterTrial:
         th = np.arccos(np.einsum('ij,ij->i', v1, v2) / (np.linalg.norm(v1, axis=1) * np.linalg.norm(v2, axis=1)))
         ang = (self.alpha / np.pi) ** 0.25 * np.exp(-self.alpha * (th - self.theta_eq) ** 2 / 2)
         return np.interp(r1, self.grid, self.wfn) * np.interp(r2, self.grid, self.wfn) * ang
+
+
+    def derivs_analytic(self, cds):
+        """(grad psi / psi, d2 psi / dx2 / psi): call_trl_h2o.py:101-149 (dpsi_dx) with the chain-rule formulas of
+        imp_samp_helper.py:10-209 written out for dists [[0,2],[2,1]], angs [[0,2,1]].  Needs the 4-row table."""
+        cds = np.asarray(cds, dtype=np.float64)
+        H1, H2, O = cds[:, 0], cds[:, 1], cds[:, 2]
+        r1 = np.linalg.norm(H1 - O, axis=1)
+        r2 = np.linalg.norm(O - H2, axis=1)
+        v1, v2 = H1 - O, H2 - O
+        th = np.arccos(np.einsum('ij,ij->i', v1, v2) / (np.linalg.norm(v1, axis=1) * np.linalg.norm(v2, axis=1)))
+        cth = np.cos(th)
+        pref, al, x = (self.alpha / np.pi) ** 0.25, self.alpha, th - self.theta_eq
+        e = np.exp(-al * x ** 2 / 2)
+        trl = np.array([np.interp(r1, self.grid, self.wfn), np.interp(r2, self.grid, self.wfn), pref * e])
+        dpsi = np.array([np.interp(r1, self.grid, self.dwfn), np.interp(r2, self.grid, self.dwfn), pref * (-al * x) * e]) / trl
+        d2psi = np.array([np.interp(r1, self.grid, self.d2wfn), np.interp(r2, self.grid, self.d2wfn),
+                          pref * (al ** 2 * x ** 2 - al) * e]) / trl
+        n = len(cds)
+        dint, d2int = np.zeros((3, n, 3, 3)), np.zeros((3, n, 3, 3))
+        # bond lengths: dr/dx = +-(xa - xb)/r ; d2r/dx2 = 1/r - (1/r) (dr/dx)^2        (:40-66)
+        for q, (a, b, r) in enumerate(((0, 2, r1), (2, 1, r2))):
+            diff = cds[:, a] - cds[:, b]
+            dint[q][:, a] = diff / r[:, None]
+            dint[q][:, b] = -1 * diff / r[:, None]
+            for atom in (a, b):
+                d2int[q][:, atom] = (1 / r)[:, None] - (1 / r)[:, None] * dint[q][:, atom] ** 2
+        dra, drc, d2ra, d2rc = dint[0], dint[1], d2int[0], d2int[1]
+        rab, rcb = np.linalg.norm(O - H1, axis=1), np.linalg.norm(O - H2, axis=1)
+        # d cos(theta) / dx   (:68-107), vertex = O
+        dc = np.zeros((n, 3, 3))
+        a1, a2, a3 = H2 - O, H1 - O, 2 * O - H1 - H2
+        dc[:, 0] = a1 / (rab * rcb)[:, None] - (cth / rab)[:, None] * dra[:, 0]
+        dc[:, 1] = a2 / (rab * rcb)[:, None] - (cth / rcb)[:, None] * drc[:, 1]
+        dc[:, 2] = a3 / (rab * rcb)[:, None] - (cth / rab)[:, None] * dra[:, 2] - (cth / rcb)[:, None] * drc[:, 2]
+        # d2 cos(theta) / dx2 (:109-160)
+        d2c = np.zeros((n, 3, 3))
+        d2c[:, 0] = ((-2 * a1) / (rab ** 2 * rcb)[:, None] * dra[:, 0] + (2 * cth / rab ** 2)[:, None] * dra[:, 0] ** 2
+                     + (-1 * cth / rab)[:, None] * d2ra[:, 0])
+        d2c[:, 1] = ((-2 * a2) / (rab * rcb ** 2)[:, None] * drc[:, 1] + (2 * cth / rcb ** 2)[:, None] * drc[:, 1] ** 2
+                     + (-1 * cth / rcb)[:, None] * d2rc[:, 1])
+        d2c[:, 2] = (2 / (rab * rcb)[:, None] + (-1 * cth / rab)[:, None] * d2ra[:, 2] + (-1 * cth / rcb)[:, None] * d2rc[:, 2]
+                     + (2 * cth / rab ** 2)[:, None] * dra[:, 2] ** 2 + (2 * cth / rcb ** 2)[:, None] * drc[:, 2] ** 2
+                     + (-2 * a3 / (rab ** 2 * rcb)[:, None]) * dra[:, 2] + (-2 * a3 / (rab * rcb ** 2)[:, None]) * drc[:, 2]
+                     + (2 * cth / (rab * rcb))[:, None] * dra[:, 2] * drc[:, 2])
+        # theta from cos(theta) (:162-209)
+        dth_dc = -1 / np.sqrt(1 - cth ** 2)
+        d2th_dc2 = -1 * cth / ((1 - cth ** 2) ** 1.5)
+        dint[2] = dth_dc[:, None, None] * dc
+        d2int[2] = dc ** 2 * d2th_dc2[:, None, None] + d2c * dth_dc[:, None, None]
+        # chain rule for a direct-product wave function (:10-38)
+        w1, w2 = dpsi[:, :, None, None], d2psi[:, :, None, None]
+        dp = (dint * w1).sum(axis=0)
+        t3 = 2 * sum(dint[q] * dint[(q + 1) % 3] * (w1[q] * w1[(q + 1) % 3]) for q in range(3))
+        d2p = (dint ** 2 * w2).sum(axis=0) + (d2int * w1).sum(axis=0) + t3
+        return dp, d2p
+
+
+def drift_analytic(cds, trial):
+    """ImpSamp.drift with a derivative function (imp_samp_manager.py:206-214): the plug-in already returns ratios."""
+    d1, d2 = trial.derivs_analytic(cds)
+    return d1, trial(np.asarray(cds)), d2
 
 
 # --------------------------------------------------------------------------- importance-sampling math
@@ -289,7 +353,7 @@ class Draws:
 
 
 def dmc_loop(coords, masses, dt, n0, nsteps, potential, draws, weighting='discrete', cont_thresh=(None, None),
-             wts=None, equil=None, wfn_every=None, desc_steps=None, trial=None, imp1d_derivs=None, second_disp=False, excited=False):
+             wts=None, equil=None, wfn_every=None, desc_steps=None, trial=None, imp1d_derivs=None, second_disp=False, excited=False, analytic=False):
     """Restatement of DMC_Sim.propagate (pyvibdmc.py:701-876) for the BASELINE configs:
     no checkpoints/logging, branch_every=1.  Returns dict(vref, pop, coords, pots, wts, wfns, eff_ts)."""
     coords = np.array(coords, dtype=np.float64)
@@ -318,7 +382,7 @@ def dmc_loop(coords, masses, dt, n0, nsteps, potential, draws, weighting='discre
                 psi_fn, der_fn = imp1d_derivs
                 d1, d2 = der_fn(c)
                 return d1, psi_fn(c), d2
-            return drift_fd(c, trial)
+            return drift_analytic(c, trial) if analytic else drift_fd(c, trial)
         f_x = psi1 = sec = None
     vscore = None
     for t in range(T):

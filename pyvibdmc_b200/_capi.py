@@ -15,7 +15,7 @@ __all__ = ["lib", "PvdError", "MassiveEvent", "check", "PvdConfig", "StepStats",
 MASSIVE_MSG = "Massive walker birth or death event!!!!!!! Dying..."
 PVD_OK, PVD_E_CUDA, PVD_E_ARG, PVD_E_MASSIVE, PVD_E_STATE, PVD_E_NODEVICE = range(6)
 POT_EXTERNAL, POT_HARMONIC, POT_H2O_PS, POT_MORSE1D, POT_NN_H4O2 = range(5)
-TRIAL_NONE, TRIAL_HARM1D, TRIAL_H2O_FD = range(3)
+TRIAL_NONE, TRIAL_HARM1D, TRIAL_H2O_FD, TRIAL_H2O_AN = range(4)
 IMP_STANDARD, IMP_SECOND_DISPLACEMENT, IMP_EXCITED_STATE = range(3)
 WEIGHT_DISCRETE, WEIGHT_CONTINUOUS = 0, 1
 RNG_FP64, RNG_FAST = 0, 1

@@ -137,21 +137,30 @@ static int fill_trial_params(pvd_sim *s, ImpArgs &im)
     im.vscore = s->cfg.imp_variant == PVD_IMP_EXCITED_STATE ? s->vs[s->cur].as<double>() : nullptr;
     im.trial = s->trial_params;
     im.acc_count = s->acc_count.as<unsigned long long>();
-    if (s->cfg.trial == PVD_TRIAL_H2O_FD && !s->trial_table.p) return pvd_fail(PVD_E_STATE, "water trial wfn: call pvd_sim_set_trial_table first");
+    if ((s->cfg.trial == PVD_TRIAL_H2O_FD || s->cfg.trial == PVD_TRIAL_H2O_AN) && !s->trial_table.p)
+        return pvd_fail(PVD_E_STATE, "water trial wfn: call pvd_sim_set_trial_table first");
     return PVD_OK;
 }
 
-// device image of a trial table: the caller's values followed (water product wfn) by the np.interp slopes
+// caller's table size (doubles) for a trial id
+static size_t trial_table_doubles(int32_t trial, int64_t ntab)
+{
+    if (trial == PVD_TRIAL_H2O_FD) return (size_t)(2 * ntab + 2);
+    if (trial == PVD_TRIAL_H2O_AN) return (size_t)(4 * ntab + 2);
+    return (size_t)ntab;
+}
+
+// device image of a trial table: the caller's values followed (water product wfn) by the np.interp slopes of every row
 static std::vector<double> trial_table_with_slopes(int32_t trial, const double *table, int64_t ntab, size_t total)
 {
     std::vector<double> host(table, table + total);
-    if (trial == PVD_TRIAL_H2O_FD) {
-        host.resize(total + (size_t)ntab, 0.0);
+    const int rows = trial == PVD_TRIAL_H2O_FD ? 1 : (trial == PVD_TRIAL_H2O_AN ? 3 : 0);
+    host.resize(total + (size_t)rows * ntab, 0.0);
+    for (int r = 0; r < rows; ++r)
         for (int64_t j = 0; j + 1 < ntab; ++j) {
-            volatile double df = table[ntab + j + 1] - table[ntab + j], dx = table[j + 1] - table[j];
-            host[total + (size_t)j] = df / dx;
+            volatile double df = table[(r + 1) * ntab + j + 1] - table[(r + 1) * ntab + j], dx = table[j + 1] - table[j];
+            host[total + (size_t)r * ntab + (size_t)j] = df / dx;
         }
-    }
     return host;
 }
 
@@ -166,20 +175,28 @@ static int host_trial_params(int32_t trial, const double *table, int64_t ntab, c
         p.h_pref = pow(table[0] / 3.141592653589793, 0.25);
         return PVD_OK;
     }
-    if (trial == PVD_TRIAL_H2O_FD) {
-        // table layout: grid[ntab], psi[ntab], then {ang_alpha, theta_eq}
-        PVD_REQUIRE(table && ntab >= 4, "H2O trial needs the (2, ntab) table followed by {alpha_theta, theta_eq}");
+    if (trial == PVD_TRIAL_H2O_FD || trial == PVD_TRIAL_H2O_AN) {
+        // table layout: grid[ntab], psi[ntab], (psi'[ntab], psi''[ntab],) then {ang_alpha, theta_eq}; slopes appended on the device
+        PVD_REQUIRE(table && ntab >= 4, "H2O trial needs the (rows, ntab) table followed by {alpha_theta, theta_eq}");
+        const int64_t rows = trial == PVD_TRIAL_H2O_AN ? 4 : 2;
+        const size_t total = trial_table_doubles(trial, ntab);
         p.grid = dev_table;
         p.wfn = dev_table + ntab;
-        p.slope = dev_table + 2 * ntab + 2;
+        p.slope = dev_table + total;
+        if (trial == PVD_TRIAL_H2O_AN) {
+            p.dwfn = dev_table + 2 * ntab;
+            p.d2wfn = dev_table + 3 * ntab;
+            p.dslope = dev_table + total + ntab;
+            p.d2slope = dev_table + total + 2 * ntab;
+        }
         p.ntab = (int)ntab;
         p.g0 = table[0];
         p.g_last = table[ntab - 1];
         p.w_first = table[ntab];
         p.w_last = table[2 * ntab - 1];
         p.inv_step = (double)(ntab - 1) / (table[ntab - 1] - table[0]);
-        p.ang_alpha = table[2 * ntab];
-        p.theta_eq = table[2 * ntab + 1];
+        p.ang_alpha = table[rows * ntab];
+        p.theta_eq = table[rows * ntab + 1];
         p.ang_pref = pow(p.ang_alpha / 3.141592653589793, 0.25);
         return PVD_OK;
     }
@@ -191,7 +208,7 @@ extern "C" int pvd_sim_set_trial_table(pvd_sim *s, const double *table, int64_t 
     SIM_CHECK(s);
     SIM_DEVICE(s);
     PVD_REQUIRE(s->cfg.trial != PVD_TRIAL_NONE, "this handle was created without a trial wave function");
-    const size_t total = s->cfg.trial == PVD_TRIAL_H2O_FD ? (size_t)(2 * ntab + 2) : (size_t)ntab;
+    const size_t total = trial_table_doubles(s->cfg.trial, ntab);
     std::vector<double> host = trial_table_with_slopes(s->cfg.trial, table, ntab, total);
     PVD_CUDA(s->trial_table.alloc(host.size() * 8));
     PVD_CUDA(cudaMemcpy(s->trial_table.p, host.data(), host.size() * 8, cudaMemcpyHostToDevice));
@@ -203,6 +220,7 @@ extern "C" int pvd_sim_set_trial_table(pvd_sim *s, const double *table, int64_t 
     do {                                                                                                                    \
         const int t = s->cfg.trial, p = s->cfg.potential;                                                                   \
         if (t == PVD_TRIAL_H2O_FD && p == PVD_POT_H2O_PS) { KERNEL_CALL(TrialH2O, PotH2O); }                                 \
+        else if (t == PVD_TRIAL_H2O_AN && p == PVD_POT_H2O_PS) { KERNEL_CALL(TrialH2OAn, PotH2O); }                          \
         else if (t == PVD_TRIAL_HARM1D && p == PVD_POT_HARMONIC && s->nc == 1) { KERNEL_CALL(TrialHarm1D, PotHarm<1>); }     \
         else if (t == PVD_TRIAL_HARM1D && p == PVD_POT_MORSE1D) { KERNEL_CALL(TrialHarm1D, PotMorse); }                      \
         else return pvd_fail(PVD_E_ARG, "unsupported built-in (trial, potential) combination");                             \
@@ -322,6 +340,8 @@ int pvd_sim_download_imp(pvd_sim *s, double *fx, double *psi, double *sec, int64
     PVD_CHECK_LAUNCH();
     if (s->cfg.trial == PVD_TRIAL_H2O_FD)
         k_trial_drift_aos<TrialH2O><<<grid_for(n, 128, 16), 128, 0, s->stream>>>(aos.as<double>(), n, im.trial, dpsi.as<double>(), dlog.as<double>(), d2.as<double>());
+    else if (s->cfg.trial == PVD_TRIAL_H2O_AN)
+        k_trial_drift_aos<TrialH2OAn><<<grid_for(n, 128, 16), 128, 0, s->stream>>>(aos.as<double>(), n, im.trial, dpsi.as<double>(), dlog.as<double>(), d2.as<double>());
     else
         k_trial_drift_aos<TrialHarm1D><<<grid_for(n, 128, 16), 128, 0, s->stream>>>(aos.as<double>(), n, im.trial, dpsi.as<double>(), dlog.as<double>(), d2.as<double>());
     PVD_CHECK_LAUNCH();
@@ -344,9 +364,9 @@ int pvd_trial_drift(int32_t trial, const double *xyz, int64_t n, int32_t natoms,
     if (int rc = ensure_device_ready()) return rc;
     if (n == 0) return PVD_OK;
     const int nc = natoms * ndim;
-    PVD_REQUIRE((trial == PVD_TRIAL_H2O_FD && nc == 9) || (trial == PVD_TRIAL_HARM1D && nc == 1), "trial / shape mismatch");
+    PVD_REQUIRE(((trial == PVD_TRIAL_H2O_FD || trial == PVD_TRIAL_H2O_AN) && nc == 9) || (trial == PVD_TRIAL_HARM1D && nc == 1), "trial / shape mismatch");
     DevBuf dt, dx, dpsi, dlogb, d2b;
-    const size_t total = trial == PVD_TRIAL_H2O_FD ? (size_t)(2 * ntab + 2) : (size_t)ntab;
+    const size_t total = trial_table_doubles(trial, ntab);
     std::vector<double> host = trial_table_with_slopes(trial, table, ntab, total);
     PVD_CUDA(dt.alloc(host.size() * 8));
     PVD_CUDA(cudaMemcpy(dt.p, host.data(), host.size() * 8, cudaMemcpyHostToDevice));
@@ -360,6 +380,8 @@ int pvd_trial_drift(int32_t trial, const double *xyz, int64_t n, int32_t natoms,
     PVD_CUDA(cudaEventRecord(ev.a));
     if (trial == PVD_TRIAL_H2O_FD)
         k_trial_drift_aos<TrialH2O><<<grid_for(n, 128, 16), 128>>>(dx.as<double>(), n, p, dpsi.as<double>(), dlogb.as<double>(), d2b.as<double>());
+    else if (trial == PVD_TRIAL_H2O_AN)
+        k_trial_drift_aos<TrialH2OAn><<<grid_for(n, 128, 16), 128>>>(dx.as<double>(), n, p, dpsi.as<double>(), dlogb.as<double>(), d2b.as<double>());
     else
         k_trial_drift_aos<TrialHarm1D><<<grid_for(n, 128, 16), 128>>>(dx.as<double>(), n, p, dpsi.as<double>(), dlogb.as<double>(), d2b.as<double>());
     PVD_CHECK_LAUNCH();

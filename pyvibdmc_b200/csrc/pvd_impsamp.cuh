@@ -8,6 +8,8 @@ struct TrialParamsDev {
     const double *grid;
     const double *wfn;
     const double *slope;        // (wfn[j+1] - wfn[j]) / (grid[j+1] - grid[j]), formed once on the host exactly as np.interp forms it
+    const double *dwfn, *d2wfn;       // analytic derivatives (call_trl_h2o.py:17-18): tabulated psi', psi'' and their slopes
+    const double *dslope, *d2slope;
     int ntab;
     double g0, inv_step;
     double g_last, w_first, w_last;
@@ -18,22 +20,23 @@ struct TrialParamsDev {
 };
 
 // np.interp(x, grid, wfn): linear, clamped to the end values, no FMA (NumPy's C loop is plain mul/add)
-__device__ __forceinline__ double interp_table(double x, const TrialParamsDev &p)
+__device__ __forceinline__ double interp_rows(double x, const TrialParamsDev &p, const double *row, const double *slope)
 {
     const int n = p.ntab;
     if (x != x) return x;
-    if (x > p.g_last) return p.w_last;
-    if (x < p.g0) return p.w_first;
+    if (x > p.g_last) return row[n - 1];
+    if (x < p.g0) return row[0];
     int j = (int)((x - p.g0) * p.inv_step);
     j = j < 0 ? 0 : (j > n - 2 ? n - 2 : j);
     while (j > 0 && x < p.grid[j]) --j;
     while (j < n - 1 && x >= p.grid[j + 1]) ++j;
-    const double fj = p.wfn[j];
+    const double fj = row[j];
     if (j == n - 1) return fj;
     const double xj = p.grid[j];
     if (x == xj) return fj;
-    return __dadd_rn(__dmul_rn(p.slope[j], x - xj), fj);
+    return __dadd_rn(__dmul_rn(slope[j], x - xj), fj);
 }
+__device__ __forceinline__ double interp_table(double x, const TrialParamsDev &p) { return interp_rows(x, p, p.wfn, p.slope); }
 
 __device__ __forceinline__ double norm3(double a, double b, double c)
 {
@@ -55,6 +58,70 @@ struct TrialH2O {
         const double dth = th - p.theta_eq;
         const double ang = __dmul_rn(p.ang_pref, exp(__dmul_rn(-p.ang_alpha, __dmul_rn(dth, dth)) / 2.0));
         return __dmul_rn(__dmul_rn(interp_table(r1, p), interp_table(r2, p)), ang);
+    }
+};
+
+// The same product wave function with the reference's ANALYTIC derivatives (call_trl_h2o.py:101-149: dpsi_dx, with the
+// chain-rule formulas of ChainRuleHelper, imp_samp_helper.py:10-209, written out for r1 = |H1 - O|, r2 = |O - H2|,
+// theta = angle(H1, O, H2)).  One evaluation instead of the 19-point finite-difference stencil.
+struct TrialH2OAn {
+    static constexpr int NC = 9;
+    static constexpr int NDIM = 3;
+    static constexpr bool ANALYTIC = true;
+    __device__ static __forceinline__ double psi(const double (&x)[9], const TrialParamsDev &p) { return TrialH2O::psi(x, p); }
+    __device__ static __forceinline__ void derivs(const double (&x)[9], const TrialParamsDev &p, double &psi0, double (&d1)[9], double (&d2)[9])
+    {
+        double a[3], b2[3], v2[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { a[j] = x[j] - x[6 + j]; b2[j] = x[6 + j] - x[3 + j]; v2[j] = x[3 + j] - x[6 + j]; }
+        const double r1 = norm3(a[0], a[1], a[2]), r2 = norm3(b2[0], b2[1], b2[2]);
+        const double dot = __dadd_rn(__dadd_rn(__dmul_rn(a[0], v2[0]), __dmul_rn(a[1], v2[1])), __dmul_rn(a[2], v2[2]));
+        const double th = acos(dot / __dmul_rn(r1, r2));
+        const double cth = cos(th);
+        const double xq = th - p.theta_eq, al = p.ang_alpha;
+        const double e = exp(__dmul_rn(-al, __dmul_rn(xq, xq)) / 2.0);
+        const double t0 = interp_table(r1, p), t1 = interp_table(r2, p), t2 = __dmul_rn(p.ang_pref, e);
+        psi0 = __dmul_rn(__dmul_rn(t0, t1), t2);
+        // (dpsi_q/dq) / psi_q and (d2psi_q/dq2) / psi_q for q = r1, r2, theta
+        const double w1[3] = {interp_rows(r1, p, p.dwfn, p.dslope) / t0, interp_rows(r2, p, p.dwfn, p.dslope) / t1,
+                              __dmul_rn(__dmul_rn(p.ang_pref, -al * xq), e) / t2};
+        const double w2[3] = {interp_rows(r1, p, p.d2wfn, p.d2slope) / t0, interp_rows(r2, p, p.d2wfn, p.d2slope) / t1,
+                              __dmul_rn(__dmul_rn(p.ang_pref, al * al * xq * xq - al), e) / t2};
+        const double ir1 = 1.0 / r1, ir2 = 1.0 / r2, irr = 1.0 / (r1 * r2);
+        const double s2 = 1.0 - cth * cth;
+        const double dth_dc = -1.0 / sqrt(s2), d2th_dc2 = -1.0 * cth / (s2 * sqrt(s2));
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            // bond lengths: dq/dx per atom (H1, H2, O) and d2q/dx2 = 1/r - (1/r)(dq/dx)^2 on the two atoms of the bond
+            const double dra0 = a[j] * ir1, dra2 = -1.0 * a[j] * ir1;               // r1 wrt H1, O
+            const double drc2 = b2[j] * ir2, drc1 = -1.0 * b2[j] * ir2;              // r2 wrt O, H2
+            const double d2ra0 = ir1 - ir1 * dra0 * dra0, d2ra2 = ir1 - ir1 * dra2 * dra2;
+            const double d2rc2 = ir2 - ir2 * drc2 * drc2, d2rc1 = ir2 - ir2 * drc1 * drc1;
+            // cos(theta): vertex O; alpha_1 = H2 - O, alpha_2 = H1 - O, alpha_3 = 2 O - H1 - H2
+            const double al1 = v2[j], al2 = a[j], al3 = 2.0 * x[6 + j] - x[j] - x[3 + j];
+            const double dc0 = al1 * irr - (cth * ir1) * dra0;
+            const double dc1 = al2 * irr - (cth * ir2) * drc1;
+            const double dc2 = al3 * irr - (cth * ir1) * dra2 - (cth * ir2) * drc2;
+            const double d2c0 = (-2.0 * al1) * (irr * ir1) * dra0 + (2.0 * cth * ir1 * ir1) * dra0 * dra0 + (-1.0 * cth * ir1) * d2ra0;
+            const double d2c1 = (-2.0 * al2) * (irr * ir2) * drc1 + (2.0 * cth * ir2 * ir2) * drc1 * drc1 + (-1.0 * cth * ir2) * d2rc1;
+            const double d2c2 = 2.0 * irr + (-1.0 * cth * ir1) * d2ra2 + (-1.0 * cth * ir2) * d2rc2 + (2.0 * cth * ir1 * ir1) * dra2 * dra2
+                                + (2.0 * cth * ir2 * ir2) * drc2 * drc2 + (-2.0 * al3 * (irr * ir1)) * dra2 + (-2.0 * al3 * (irr * ir2)) * drc2
+                                + (2.0 * cth * irr) * dra2 * drc2;
+            // internal-coordinate derivatives per atom: q = (r1, r2, theta)
+            const double dq[3][3] = {{dra0, 0.0, dth_dc * dc0}, {0.0, drc1, dth_dc * dc1}, {dra2, drc2, dth_dc * dc2}};   // [atom][q]
+            const double d2q[3][3] = {{d2ra0, 0.0, dc0 * dc0 * d2th_dc2 + d2c0 * dth_dc},
+                                      {0.0, d2rc1, dc1 * dc1 * d2th_dc2 + d2c1 * dth_dc},
+                                      {d2ra2, d2rc2, dc2 * dc2 * d2th_dc2 + d2c2 * dth_dc}};
+#pragma unroll
+            for (int atom = 0; atom < 3; ++atom) {
+                const double *g = dq[atom], *h = d2q[atom];
+                d1[3 * atom + j] = g[0] * w1[0] + g[1] * w1[1] + g[2] * w1[2];
+                const double term1 = g[0] * g[0] * w2[0] + g[1] * g[1] * w2[1] + g[2] * g[2] * w2[2];
+                const double term2 = h[0] * w1[0] + h[1] * w1[1] + h[2] * w1[2];
+                const double term3 = 2.0 * ((g[0] * g[1]) * (w1[0] * w1[1]) + (g[1] * g[2]) * (w1[1] * w1[2]) + (g[2] * g[0]) * (w1[2] * w1[0]));
+                d2[3 * atom + j] = term1 + term2 + term3;
+            }
+        }
     }
 };
 

@@ -143,13 +143,15 @@ def desc_wts(who_from, n_parent, wts=None):
 # ----------------------------------------------------------------------------- importance sampling
 def trial_drift(trial, cds, table, ntab=None):
     """ImpSamp.drift for a built-in trial wfn: returns (grad psi/psi, psi, d2psi/psi).
-    table: HARM1D -> [alpha]; H2O_FD -> [grid(ntab) | psi(ntab) | alpha_theta, theta_eq]."""
+    table: HARM1D -> [alpha]; H2O_FD -> [grid(ntab) | psi(ntab) | alpha_theta, theta_eq];
+    H2O_AN -> [grid | psi | psi' | psi'' | alpha_theta, theta_eq]."""
     cds = f64(cds)
     n, a, d = cds.shape
     table = f64(table).reshape(-1)
     psi, dlog, d2 = np.empty(n), np.empty((n, a, d)), np.empty((n, a, d))
     if ntab is None:
-        ntab = (table.size - 2) // 2 if trial == _capi.TRIAL_H2O_FD else table.size
+        ntab = ((table.size - 2) // 2 if trial == _capi.TRIAL_H2O_FD else (table.size - 2) // 4 if trial == _capi.TRIAL_H2O_AN
+                else table.size)
     check(lib.pvd_trial_drift(int(trial), ptr(cds), n, a, d, ptr(table), int(ntab), ptr(psi), ptr(dlog), ptr(d2)))
     return dlog, psi, d2
 
@@ -256,7 +258,8 @@ class DeviceSim:
     def set_trial_table(self, table, ntab=None):
         t = f64(table).reshape(-1)
         if ntab is None:
-            ntab = (t.size - 2) // 2 if self.cfg.trial == _capi.TRIAL_H2O_FD else t.size
+            ntab = ((t.size - 2) // 2 if self.cfg.trial == _capi.TRIAL_H2O_FD else
+                    (t.size - 2) // 4 if self.cfg.trial == _capi.TRIAL_H2O_AN else t.size)
         check(lib.pvd_sim_set_trial_table(self._h, ptr(t), int(ntab)))
 
     def set_nn_weights(self, packed):

@@ -1,7 +1,8 @@
 """Water product trial wave function on the GPU (replaces FortPots/Partridge_Schwenke_H2O/call_trl_h2o.py:7-78):
 psi = interp(r_OH1) * interp(r_OH2) * Gaussian(theta), the O-H factors linearly interpolated on the shipped
-5000-point grid exactly like np.interp (clamped outside [0.5, 4.0] bohr).  Derivatives come from finite differences
-(ImpSampManager(..., deriv_function=None)), evaluated as a 19-point stencil in registers."""
+5000-point grid exactly like np.interp (clamped outside [0.5, 4.0] bohr).  Derivatives come either from finite differences
+(ImpSampManager(..., deriv_function=None): a 19-point stencil in registers) or analytically (deriv_function='dpsi_dx',
+reference call_trl_h2o.py:101-149 with the ChainRuleHelper formulas of imp_samp_helper.py:10-209 written out on the device)."""
 import os
 
 import numpy as np
@@ -16,7 +17,7 @@ theta_eq = np.deg2rad(104.5080029)
 theta_freq = Constants.convert(1668.4590610594878, 'wavenumbers', to_AU=True)
 inv_mh = 1 / Constants.mass('H')
 inv_mo = 1 / Constants.mass('O')
-_table = np.load(os.path.join(_HERE, "free_oh_wvfn_table.npy"))      # rows: grid (bohr), psi
+_table = np.load(os.path.join(_HERE, "free_oh_wvfn_table.npy"))      # rows: grid (bohr), psi, psi', psi''
 
 
 def gmat():
@@ -27,6 +28,11 @@ def gmat():
 def packed_table():
     """[grid | psi | alpha_theta, theta_eq] as the C ABI expects (pvd_trial_drift / pvd_sim_set_trial_table)."""
     return np.concatenate([_table[0], _table[1], [theta_freq / gmat(), theta_eq]])
+
+
+def packed_table_analytic():
+    """[grid | psi | psi' | psi'' | alpha_theta, theta_eq] for PVD_TRIAL_H2O_AN."""
+    return np.concatenate([_table[0], _table[1], _table[2], _table[3], [theta_freq / gmat(), theta_eq]])
 
 
 def _check(ex_args):
@@ -49,3 +55,19 @@ def _spec(ex_args):
 
 
 trial_wavefunction._pvd_builtin_trial = _spec
+
+
+def dpsi_dx(cds, ex_args=None):
+    """(grad psi / psi, d2 psi / dx2 / psi), analytic (reference call_trl_h2o.py:101-149)."""
+    _check(ex_args)
+    cds = np.ascontiguousarray(cds, dtype=np.float64)
+    d1, _, d2 = _K.trial_drift(_capi.TRIAL_H2O_AN, cds, packed_table_analytic(), ntab=_table.shape[1])
+    return d1, d2
+
+
+def _spec_analytic(ex_args):
+    _check(ex_args)
+    return {"trial": _capi.TRIAL_H2O_AN, "table": packed_table_analytic(), "ntab": _table.shape[1], "fd": False}
+
+
+dpsi_dx._pvd_builtin_trial = _spec_analytic

@@ -35,7 +35,10 @@ class _ImpBase:
 
     def gpu_spec(self):
         """Descriptor of a built-in trial wfn (None for user functions)."""
-        spec = getattr(self._trial_fn, "_pvd_builtin_trial", None)
+        # a built-in derivative function (e.g. the analytic water derivatives) decides the device trial variant
+        spec = getattr(self._deriv_fn, "_pvd_builtin_trial", None) if not self.all_finite else None
+        if spec is None:
+            spec = getattr(self._trial_fn, "_pvd_builtin_trial", None)
         if spec is None:
             return None
         if callable(spec):

@@ -216,8 +216,27 @@ def gen_impsamp():
     save("impsamp_water_golden.npz", coords=cds, psi=psi, f_x=f_x, sec=sec, disp=disp, y=y, psi_y=psi_y,
          f_y=f_y, sec_y=sec_y, acc=acc, local_kin=lk, masses=masses, dt=dt,
          grid_first=table[0, 0], grid_last=table[0, -1], grid_n=table.shape[1])
-    # trial-wfn table itself is data the product needs (5000-pt grid, rows: r, psi): ship psi row only
-    np.save(os.path.join(ROOT, "pyvibdmc_b200", "sample_potentials", "FortPots", "Partridge_Schwenke_H2O", "free_oh_wvfn_table.npy"), table[:2])
+    # trial-wfn table itself is data the product needs (5000-pt grid, rows: r, psi, psi', psi'')
+    np.save(os.path.join(ROOT, "pyvibdmc_b200", "sample_potentials", "FortPots", "Partridge_Schwenke_H2O", "free_oh_wvfn_table.npy"), table)
+
+
+def gen_impsamp_analytic():
+    """Water trial wfn with the reference's ANALYTIC derivatives (call_trl_h2o.py:101-149 + ChainRuleHelper,
+    imp_samp_helper.py:10-209) and a short trajectory that uses them."""
+    rng = np.random.default_rng(12)
+    n = 1500
+    cds = EQ[None] * 1.0 + rng.normal(0, 0.06, size=(n, 3, 3))
+    d = f"{REF}/pyvibdmc/sample_potentials/FortPots/Partridge_Schwenke_H2O"
+    man = pv.ImpSampManager_NoMP(trial_function='trial_wavefunction', trial_directory=d, python_file='call_trl_h2o.py', chdir=True,
+                                 deriv_function='dpsi_dx', trial_kwargs=WAT_ARGS, deriv_kwargs=WAT_ARGS)
+    imp = ImpSamp(man)
+    f_x, psi, sec = imp.drift(cds.copy())
+    save("impsamp_water_analytic_golden.npz", coords=cds, psi=psi, f_x=f_x, sec=sec)
+    table = np.load(f"{d}/free_oh_wvfn_dense.npy")
+    # the analytic path needs the derivative rows of the shipped table too (rows: r, psi, psi', psi'')
+    np.save(os.path.join(ROOT, "pyvibdmc_b200", "sample_potentials", "FortPots", "Partridge_Schwenke_H2O", "free_oh_wvfn_table.npy"), table)
+    wpot = pv.Potential_Direct(potential_function=water_pot)
+    run_traj("h2o_imp_an", "discrete", 200, 12, ["H", "H", "O"], EQ[None] * 1.01, wpot, 1.0, 13, imp=man, equil=4, wfn=6, desc=3)
 
 
 # ---------------------------------------------------------------- G. whole-loop trajectories with recorded RNG
@@ -334,7 +353,7 @@ def gen_descriptor():
 if __name__ == "__main__":
     try:
         gens = {"pes": gen_pes, "ho": gen_ho, "branch_discrete": gen_branch_discrete, "branch_continuous": gen_branch_continuous,
-                "vref_desc": gen_vref_desc, "impsamp": gen_impsamp, "traj": gen_traj, "traj_variants": gen_traj_variants, "traj_excited": gen_traj_excited,
+                "vref_desc": gen_vref_desc, "impsamp": gen_impsamp, "traj": gen_traj, "traj_variants": gen_traj_variants, "traj_excited": gen_traj_excited, "impsamp_analytic": gen_impsamp_analytic,
                 "descriptor": gen_descriptor}
         for name in (sys.argv[1:] or list(gens)):          # default: everything; or name the generators to (re)run
             gens[name]()

@@ -283,3 +283,18 @@ def test_second_impsamp_displacement_through_dmc_sim(pv, tmp_path):
     sim.run()
     assert np.allclose(sim._vref_vs_tau / WN, 1850.0, atol=1e-6) and (sim._pop_vs_tau == 1000).all()
     assert sim.walkers.std() > 0.05           # the walkers do move (diffusion is never rejected)
+
+
+def test_water_importance_sampling_with_analytic_derivatives(pv, tmp_path):
+    """deriv_function='dpsi_dx' (reference call_trl_h2o.py:101-149): same physics as the finite-difference run, one psi evaluation."""
+    hd = sample_dir(pv, "FortPots", "Partridge_Schwenke_H2O")
+    kw = {'dists': [[0, 2], [2, 1]], 'angs': [[0, 2, 1]]}
+    wimp = pv.ImpSampManager(trial_function='trial_wavefunction', trial_directory=hd, python_file='call_trl_h2o.py',
+                             pot_manager=water_potential(pv), deriv_function='dpsi_dx', trial_kwargs=kw, deriv_kwargs=kw)
+    assert wimp.gpu_spec()["trial"] == pv._capi.TRIAL_H2O_AN
+    sim = pv.DMC_Sim(sim_name="wan", output_folder=str(tmp_path / "wa"), num_walkers=4000, num_timesteps=600, equil_steps=100,
+                     chkpt_every=300, wfn_every=200, desc_wt_steps=20, atoms=['H', 'H', 'O'], delta_t=1,
+                     potential=water_potential(pv), start_structures=EQ[None] * 1.01, imp_samp=wimp, seed=4)
+    sim.run()
+    zpe = sim.vref_vs_tau[300:, 1].mean() / WN
+    assert 4500 < zpe < 4800, zpe

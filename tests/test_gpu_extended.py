@@ -296,6 +296,42 @@ def test_replay_excited_state_impsamp_trajectory(K):
     sim.close()
 
 
+def water_table_analytic():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("call_trl_h2o_b200", os.path.join(H2O_DIR, "call_trl_h2o.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.packed_table_analytic()
+
+
+def test_water_trial_analytic_derivatives_vs_reference(K):
+    """a13: dpsi_dx (call_trl_h2o.py:101-149) with ChainRuleHelper (imp_samp_helper.py:10-209) on the device."""
+    from pyvibdmc_b200 import _capi
+    g = golden("impsamp_water_analytic_golden.npz")
+    f, psi, sec = K.trial_drift(_capi.TRIAL_H2O_AN, g["coords"], water_table_analytic())
+    assert np.allclose(psi, g["psi"], rtol=1e-13, atol=1e-300)
+    assert np.allclose(f, g["f_x"], rtol=1e-9, atol=1e-11)
+    assert np.allclose(sec, g["sec"], rtol=1e-8, atol=1e-8)
+    # trajectory of the reference driven by these derivatives, replayed with its recorded draws
+    gt = golden("traj_h2o_imp_an_golden.npz")
+    rp = Replay(gt)
+    sim = K.DeviceSim(3, 3, gt["masses"], 200, 1.0, _capi.POT_H2O_PS, trial=_capi.TRIAL_H2O_AN)
+    sim.set_trial_table(water_table_analytic())
+    sim.upload(np.repeat(EQ[None] * 1.01, 200, 0))
+    T, n = 12, 200
+    vref, pop, dts = np.zeros(T), np.zeros(T), np.zeros(T)
+    for t in range(T):
+        disp = rp.normal(n, 3, 3)
+        um, ub = rp.take(n), rp.take(n)
+        sim.step_injected(disp, ub, um)
+        st = sim.stats(t, 1)
+        vref[t], pop[t], dts[t] = st["vref"][0], st["pop"][0], st["dt_eff"][0]
+        n = int(pop[t])
+    assert np.array_equal(pop, gt["pop"])
+    assert np.allclose(vref, gt["vref"], rtol=1e-9) and np.allclose(np.cumsum(dts), gt["eff_ts"], rtol=1e-13)
+    sim.close()
+
+
 def test_impsamp_free_running_zpe(K, oracle):
     """Importance-sampled water: local energy fluctuates far less than V; ZPE stays near 4634 cm-1."""
     from pyvibdmc_b200 import _capi

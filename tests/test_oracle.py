@@ -207,3 +207,23 @@ def test_traj_excited_state_impsamp(oracle):
                           equil=4, wfn_every=6, desc_steps=3, trial=oracle.WaterTrial(table), excited=True)
     assert np.array_equal(out["pop"], g["pop"])
     assert np.allclose(out["vref"], g["vref"], rtol=1e-9) and np.allclose(out["eff_ts"], g["eff_ts"], rtol=1e-14)
+
+
+def test_water_trial_analytic_derivatives(oracle):
+    """Oracle restatement of dpsi_dx + ChainRuleHelper against the reference's own output, and the loop that uses it."""
+    table = np.load(os.path.join(os.path.dirname(__file__), "..", "pyvibdmc_b200", "sample_potentials",
+                                 "FortPots", "Partridge_Schwenke_H2O", "free_oh_wvfn_table.npy"))
+    g = golden("impsamp_water_analytic_golden.npz")
+    tr = oracle.WaterTrial(table)
+    d1, psi, d2 = oracle.drift_analytic(g["coords"], tr)
+    assert np.allclose(psi, g["psi"], rtol=1e-14) and np.allclose(d1, g["f_x"], rtol=1e-10, atol=1e-12)
+    assert np.allclose(d2, g["sec"], rtol=1e-9, atol=1e-9)
+    # analytic and finite-difference derivatives describe the same function
+    f_fd, _, s_fd = oracle.drift_fd(g["coords"][:200], tr)
+    # (to the accuracy of differencing a piecewise-linear table with dx = 1e-3; second differences of it are noise)
+    assert np.allclose(d1[:200], f_fd, rtol=5e-3, atol=2e-3)
+    gt, draws = _replay(oracle, "h2o_imp_an")
+    out = oracle.dmc_loop(np.repeat(EQ[None] * 1.01, 200, 0), gt["masses"], 1.0, 200, 12, oracle.water_pot, draws,
+                          equil=4, wfn_every=6, desc_steps=3, trial=tr, analytic=True)
+    assert np.array_equal(out["pop"], gt["pop"])
+    assert np.allclose(out["vref"], gt["vref"], rtol=1e-9) and np.allclose(out["eff_ts"], gt["eff_ts"], rtol=1e-14)

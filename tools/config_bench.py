@@ -55,7 +55,7 @@ def timed(sim, equil, steps, reps=3):
     return best
 
 
-def collect(only=("c1", "c3", "c4", "c5"), large_only=False, steps=100, equil=-1, scale=1.0):
+def collect(only=("c1", "c3", "c4", "c4a", "c5"), large_only=False, steps=100, equil=-1, scale=1.0):
     """Returns {config label: {ms_per_step, walker_steps_per_s, mean_population, mean_vref_cm1}}."""
     only = set(only)
     EQUIL[0] = equil
@@ -91,6 +91,17 @@ def collect(only=("c1", "c3", "c4", "c5"), large_only=False, steps=100, equil=-1
             out[f"c4_h2o_impsamp_fd_{n}"] = timed(sim, 200, steps)
             sim.close()
 
+    if "c4a" in only:
+        spec = importlib.util.spec_from_file_location("call_trl_h2o_b200", os.path.join(SP, "FortPots", "Partridge_Schwenke_H2O", "call_trl_h2o.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        for n in sizes(20000, int(1.25e6 * scale)):
+            sim = K.DeviceSim(3, 3, [mH, mH, mO], n, 1.0, _capi.POT_H2O_PS, trial=_capi.TRIAL_H2O_AN, seed=3)
+            sim.set_trial_table(mod.packed_table_analytic())
+            sim.upload(np.broadcast_to(EQ * 1.01, (n, 3, 3)).copy())
+            out[f"c4a_h2o_impsamp_analytic_{n}"] = timed(sim, 200, steps)
+            sim.close()
+
     if "c5" in only:
         w = np.load(os.path.join(SP, "TensorflowPots", "sample_h4o2_nn_packed.npy"))
         for n in sizes(int(1e6 * scale), int(1.25e7 * scale)):
@@ -105,7 +116,7 @@ def collect(only=("c1", "c3", "c4", "c5"), large_only=False, steps=100, equil=-1
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
-    ap.add_argument("--only", default="c1,c3,c4,c5")
+    ap.add_argument("--only", default="c1,c3,c4,c4a,c5")
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--equil", type=int, default=-1, help="override the equilibration length (profiling runs)")
     ap.add_argument("--large-only", action="store_true")
