@@ -114,11 +114,12 @@ struct TrialH2OAn {
                                       {d2ra2, d2rc2, dc2 * dc2 * d2th_dc2 + d2c2 * dth_dc}};
 #pragma unroll
             for (int atom = 0; atom < 3; ++atom) {
-                const double *g = dq[atom], *h = d2q[atom];
-                d1[3 * atom + j] = g[0] * w1[0] + g[1] * w1[1] + g[2] * w1[2];
-                const double term1 = g[0] * g[0] * w2[0] + g[1] * g[1] * w2[1] + g[2] * g[2] * w2[2];
-                const double term2 = h[0] * w1[0] + h[1] * w1[1] + h[2] * w1[2];
-                const double term3 = 2.0 * ((g[0] * g[1]) * (w1[0] * w1[1]) + (g[1] * g[2]) * (w1[1] * w1[2]) + (g[2] * g[0]) * (w1[2] * w1[0]));
+                const double g0 = dq[atom][0], g1 = dq[atom][1], g2 = dq[atom][2];
+                const double h0 = d2q[atom][0], h1 = d2q[atom][1], h2 = d2q[atom][2];
+                d1[3 * atom + j] = g0 * w1[0] + g1 * w1[1] + g2 * w1[2];
+                const double term1 = g0 * g0 * w2[0] + g1 * g1 * w2[1] + g2 * g2 * w2[2];
+                const double term2 = h0 * w1[0] + h1 * w1[1] + h2 * w1[2];
+                const double term3 = 2.0 * ((g0 * g1) * (w1[0] * w1[1]) + (g1 * g2) * (w1[1] * w1[2]) + (g2 * g0) * (w1[2] * w1[0]));
                 d2[3 * atom + j] = term1 + term2 + term3;
             }
         }
