@@ -20,8 +20,10 @@ struct DevBuf {
     void *p = nullptr;
     size_t bytes = 0;
     ~DevBuf() { if (p) cudaFree(p); }
+    // grows only: staging buffers are re-used across calls (cudaFree / cudaMalloc of a 70 MB buffer cost ~2 ms each)
     cudaError_t alloc(size_t b)
     {
+        if (p && b <= bytes) return cudaSuccess;
         if (p) { cudaFree(p); p = nullptr; }
         bytes = b;
         return cudaMalloc(&p, b ? b : 1);
