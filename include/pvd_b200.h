@@ -58,7 +58,11 @@ enum {
 };
 
 enum { PVD_WEIGHT_DISCRETE = 0, PVD_WEIGHT_CONTINUOUS = 1 };
-enum { PVD_RNG_FP64 = 0, PVD_RNG_FAST = 1 };
+/* how the Gaussian displacements of move_randomly (pyvibdmc.py:540-547, np.random.normal) are generated from Philox bits:
+ * FP64 = Box-Muller evaluated in double; FAST = Box-Muller with float32 SFU intrinsics (~1e-6 relative);
+ * ZIGGURAT = 1024-layer ziggurat in double (exact distribution, the method of NumPy's Generator.normal) */
+enum { PVD_RNG_FP64 = 0, PVD_RNG_FAST = 1, PVD_RNG_ZIGGURAT = 2 };
+#define PVD_ZIGGURAT_LAYERS 1024
 
 #define PVD_MAX_ATOMS 16
 #define PVD_MAX_COMP (3 * PVD_MAX_ATOMS)
@@ -97,6 +101,9 @@ int pvd_displace(double *xyz, int64_t n, int32_t natoms, int32_t ndim, const dou
                  uint64_t seed, uint64_t step, int32_t rng_mode);
 /* raw generator output for statistical tests: z[i,c] exactly as pvd_displace would add with sigma=1 */
 int pvd_normals(double *z, int64_t n, int32_t ncomp, uint64_t seed, uint64_t step, int32_t rng_mode);
+/* the ziggurat table the device uses (host-computed at load): x[0..LAYERS] layer abscissae (x[0] = V/f(R), x[1] = R,
+ * x[LAYERS] = 0), f[i] = exp(-x[i]^2/2).  Needs no device: lets a test re-derive the generator on the CPU. */
+int pvd_ziggurat_table(double *x, double *f);
 /* Philox4x32-10 known-answer hook: out[4] = philox(ctr[4], key[2]) computed on the device */
 int pvd_philox_kat(const uint32_t *ctr4, const uint32_t *key2, uint32_t *out4);
 

@@ -18,7 +18,8 @@ POT_EXTERNAL, POT_HARMONIC, POT_H2O_PS, POT_MORSE1D, POT_NN_H4O2 = range(5)
 TRIAL_NONE, TRIAL_HARM1D, TRIAL_H2O_FD, TRIAL_H2O_AN = range(4)
 IMP_STANDARD, IMP_SECOND_DISPLACEMENT, IMP_EXCITED_STATE = range(3)
 WEIGHT_DISCRETE, WEIGHT_CONTINUOUS = 0, 1
-RNG_FP64, RNG_FAST = 0, 1
+RNG_FP64, RNG_FAST, RNG_ZIGGURAT = 0, 1, 2
+ZIGGURAT_LAYERS = 1024
 MAX_ATOMS, MAX_COMP, MAX_WORLD = 16, 48, 8
 NSUMS = 8 + 4 * MAX_WORLD
 
@@ -73,6 +74,7 @@ SIGNATURES = {
     "pvd_displace": (C.c_int, [_P, _I64, _I32, _I32, _P, _U64, _U64, _I32]),
     "pvd_normals": (C.c_int, [_P, _I64, _I32, _U64, _U64, _I32]),
     "pvd_philox_kat": (C.c_int, [_P, _P, _P]),
+    "pvd_ziggurat_table": (C.c_int, [_P, _P]),
     "pvd_branch_discrete": (C.c_int, [_P, _I64, _F64, _F64, _P, _I64, _P, _P, _I64, _P]),
     "pvd_branch_continuous": (C.c_int, [_P, _P, _I64, _F64, _F64, _F64, _F64, _P, _P]),
     "pvd_calc_vref": (C.c_int, [_P, _P, _I64, _I64, _F64, C.POINTER(_F64)]),

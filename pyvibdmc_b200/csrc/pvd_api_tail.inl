@@ -76,6 +76,7 @@ static int cont_enqueue_step(pvd_sim *s, StepArgs &a)
     do {                                                                                                             \
         const int gp = POT::MIN_CTAS >= 4 ? s->grid_light : s->grid;                                                 \
         if (fast) { ca.tile = PVD_TILE * ContFused<POT, PVD_RNG_FAST>::SUB; k_cont_update<ContFused<POT, PVD_RNG_FAST>><<<gp, PVD_CTA, 0, s->stream>>>(a, ca); } \
+        else if (s->cfg.rng_mode == PVD_RNG_ZIGGURAT) { ca.tile = PVD_TILE * ContFused<POT, PVD_RNG_ZIGGURAT>::SUB; k_cont_update<ContFused<POT, PVD_RNG_ZIGGURAT>><<<gp, PVD_CTA, 0, s->stream>>>(a, ca); } \
         else { ca.tile = PVD_TILE * ContFused<POT, PVD_RNG_FP64>::SUB; k_cont_update<ContFused<POT, PVD_RNG_FP64>><<<gp, PVD_CTA, 0, s->stream>>>(a, ca); }      \
     } while (0)
     switch (s->cfg.potential) {

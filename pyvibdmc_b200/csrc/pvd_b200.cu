@@ -36,6 +36,62 @@ struct EventPair {
     cudaError_t init() { cudaError_t e = cudaEventCreate(&a); return e != cudaSuccess ? e : cudaEventCreate(&b); }
 };
 
+// ---------------------------------------------------------------- ziggurat table (host, long double)
+// Layers of equal area V under f(x) = exp(-x^2/2), x >= 0 (Marsaglia & Tsang 2000): x_1 = R, x_{i+1} = f^-1(V/x_i + f(x_i)),
+// closed by x_N = 0; V = R f(R) + int_R^inf f.  R is found by bisection on the closing condition.
+#include <math.h>
+struct ZigHost {
+    double x[PVD_ZIG_N + 1], f[PVD_ZIG_N + 1];
+    double2 xr[PVD_ZIG_N];
+    ZigHost()
+    {
+        static long double xl[PVD_ZIG_N + 1];
+        auto closing = [&](long double R, long double &V) -> long double {
+            const long double fR = expl(-0.5L * R * R);
+            V = R * fR + sqrtl(2.0L * atanl(1.0L)) * erfcl(R / sqrtl(2.0L));     // sqrt(pi/2) erfc(R/sqrt 2)
+            xl[0] = V / fR;
+            xl[1] = R;
+            for (int i = 1; i < PVD_ZIG_N - 1; ++i) {
+                const long double y = V / xl[i] + expl(-0.5L * xl[i] * xl[i]);
+                if (y >= 1.0L) return 1.0L;                                      // reached the top too early: R too small
+                xl[i + 1] = sqrtl(-2.0L * logl(y));
+            }
+            return V / xl[PVD_ZIG_N - 1] + expl(-0.5L * xl[PVD_ZIG_N - 1] * xl[PVD_ZIG_N - 1]) - 1.0L;
+        };
+        long double lo = 2.0L, hi = 7.0L, V = 0.0L;
+        for (int it = 0; it < 200; ++it) {
+            const long double mid = 0.5L * (lo + hi);
+            if (closing(mid, V) > 0.0L) lo = mid; else hi = mid;
+        }
+        closing(hi, V);
+        xl[PVD_ZIG_N] = 0.0L;
+        for (int i = 0; i <= PVD_ZIG_N; ++i) {
+            x[i] = (double)xl[i];
+            f[i] = (double)expl(-0.5L * xl[i] * xl[i]);
+        }
+        f[PVD_ZIG_N] = 1.0;
+        for (int i = 0; i < PVD_ZIG_N; ++i) xr[i] = make_double2(x[i], (double)(xl[i + 1] / xl[i]));
+    }
+};
+static const ZigHost &zig_host()
+{
+    static const ZigHost z;
+    return z;
+}
+static cudaError_t zig_upload()
+{
+    const ZigHost &z = zig_host();
+    cudaError_t e = cudaMemcpyToSymbol(g_zig_xr, z.xr, sizeof(z.xr));
+    return e != cudaSuccess ? e : cudaMemcpyToSymbol(g_zig_f, z.f, sizeof(z.f));
+}
+extern "C" int pvd_ziggurat_table(double *x, double *f)
+{
+    PVD_REQUIRE(x && f, "NULL argument");
+    const ZigHost &z = zig_host();
+    for (int i = 0; i <= PVD_ZIG_N; ++i) { x[i] = z.x[i]; f[i] = z.f[i]; }
+    return PVD_OK;
+}
+
 static int g_num_sms = 0;
 static std::once_flag g_init_once;
 static cudaError_t g_init_err = cudaSuccess;
@@ -51,6 +107,7 @@ static int ensure_device_ready()
     PVD_CUDA(cudaGetDevice(&dev));
     if (g_const_device != dev) {          // constants are per-device (one process per GPU in practice)
         PVD_CUDA(ps_upload_constants());
+        PVD_CUDA(zig_upload());
         cudaDeviceProp prop;
         PVD_CUDA(cudaGetDeviceProperties(&prop, dev));
         g_num_sms = prop.multiProcessorCount;
@@ -201,7 +258,7 @@ static int displace_impl(double *xyz, int64_t n, int32_t nc, int32_t ndim, const
                          int32_t rng_mode, bool normals_only)
 {
     PVD_REQUIRE(n >= 0 && nc >= 1 && nc <= PVD_MAX_COMP && ndim >= 1 && (n == 0 || xyz), "pvd_displace: bad arguments");
-    PVD_REQUIRE(rng_mode == PVD_RNG_FP64 || rng_mode == PVD_RNG_FAST, "pvd_displace: unknown rng_mode");
+    PVD_REQUIRE(rng_mode == PVD_RNG_FP64 || rng_mode == PVD_RNG_FAST || rng_mode == PVD_RNG_ZIGGURAT, "pvd_displace: unknown rng_mode");
     if (int rc = ensure_device_ready()) return rc;
     if (n == 0) return PVD_OK;
     // stage AoS -> SoA (stride n), displace, SoA -> AoS
@@ -225,6 +282,9 @@ static int displace_impl(double *xyz, int64_t n, int32_t nc, int32_t ndim, const
     if (rng_mode == PVD_RNG_FP64)
         k_displace_soa<PVD_RNG_FP64><<<g, 256>>>(soa.as<double>(), nullptr, 0, n, (long long)step, n, nc, ndim, seed, nullptr, nullptr,
                                                  sig.as<double>(), zout);
+    else if (rng_mode == PVD_RNG_ZIGGURAT)
+        k_displace_soa<PVD_RNG_ZIGGURAT><<<g, 256>>>(soa.as<double>(), nullptr, 0, n, (long long)step, n, nc, ndim, seed, nullptr, nullptr,
+                                                     sig.as<double>(), zout);
     else
         k_displace_soa<PVD_RNG_FAST><<<g, 256>>>(soa.as<double>(), nullptr, 0, n, (long long)step, n, nc, ndim, seed, nullptr, nullptr,
                                                  sig.as<double>(), zout);
@@ -655,6 +715,7 @@ static int enqueue_step(pvd_sim *s, int do_branch, const double *inj_disp, const
     do {                                                                                            \
         const int gp = POT::MIN_CTAS >= 4 ? s->grid_light : g;                                      \
         if (fast) PVD_STEP_KERNEL<POT, PVD_RNG_FAST><<<gp, PVD_CTA, 0, s->stream>>>(a);            \
+        else if (s->cfg.rng_mode == PVD_RNG_ZIGGURAT) PVD_STEP_KERNEL<POT, PVD_RNG_ZIGGURAT><<<gp, PVD_CTA, 0, s->stream>>>(a); \
         else PVD_STEP_KERNEL<POT, PVD_RNG_FP64><<<gp, PVD_CTA, 0, s->stream>>>(a);                 \
     } while (0)
         switch (s->cfg.potential) {
@@ -750,6 +811,9 @@ int pvd_sim_ext_move(pvd_sim *s, double *xyz_out, int64_t *n_out)
     if (s->cfg.rng_mode == PVD_RNG_FAST)
         k_displace_soa<PVD_RNG_FAST><<<g, 256, 0, s->stream>>>(x, s->st.as<DevState>(), s->parity, 0, 0, s->cap, nc, s->cfg.ndim,
                                                               s->cfg.seed, nullptr, nullptr, s->sigma_dev.as<double>(), nullptr);
+    else if (s->cfg.rng_mode == PVD_RNG_ZIGGURAT)
+        k_displace_soa<PVD_RNG_ZIGGURAT><<<g, 256, 0, s->stream>>>(x, s->st.as<DevState>(), s->parity, 0, 0, s->cap, nc, s->cfg.ndim,
+                                                                  s->cfg.seed, nullptr, nullptr, s->sigma_dev.as<double>(), nullptr);
     else
         k_displace_soa<PVD_RNG_FP64><<<g, 256, 0, s->stream>>>(x, s->st.as<DevState>(), s->parity, 0, 0, s->cap, nc, s->cfg.ndim,
                                                               s->cfg.seed, nullptr, nullptr, s->sigma_dev.as<double>(), nullptr);

@@ -80,6 +80,7 @@ __device__ __forceinline__ double bin_lower_edge(int bin)
 // flags of a sub-tile are one ballot, which is also all the state the deferred scatter needs.
 // Where the energy of walker i comes from: memory (external / NN / importance-sampled energies)...
 struct ContFromMemory {
+    static constexpr int RNG_MODE = PVD_RNG_FP64;      // draws no normals
     static constexpr int MIN_CTAS = 4;
     static constexpr int SUB = 8;
     __device__ static __forceinline__ double produce(const StepArgs &a, long long i, long long) { return a.vin[i]; }
@@ -87,6 +88,7 @@ struct ContFromMemory {
 // ...or the fused move + built-in potential (in place: continuous weighting never compacts)
 template <class POT, int RNG>
 struct ContFused {
+    static constexpr int RNG_MODE = RNG;
     static constexpr int MIN_CTAS = POT::MIN_CTAS;
     static constexpr int SUB = POT::MIN_CTAS >= 4 ? 4 : 1;      // heavy potential: small tiles keep the warps balanced
     __device__ static __forceinline__ double produce(const StepArgs &a, long long i, long long step)
@@ -108,6 +110,7 @@ __global__ void __launch_bounds__(PVD_CTA, PROD::MIN_CTAS) k_cont_update(const S
     __shared__ unsigned s_hist[PVD_HIST_BINS];
     if (!step_prologue(a)) return;
     for (int b = threadIdx.x; b < PVD_HIST_BINS; b += PVD_CTA) s_hist[b] = 0;
+    if constexpr (PROD::RNG_MODE == PVD_RNG_ZIGGURAT) zig_stage();
     __syncthreads();
     const DevState *sip = &a.st[a.parity];
     const long long n = sip->n, step = sip->step;

@@ -106,6 +106,7 @@ __global__ void __launch_bounds__(256, 4) k_displace_soa(double *__restrict__ x,
     const long long n = st ? st[parity].n : n_fixed;
     const long long step = st ? st[parity].step : step_fixed;
     if (st && st[parity].err) return;
+    if constexpr (RNG == PVD_RNG_ZIGGURAT) zig_stage();
     const int npairs = (nc + 1) / 2;
     constexpr int G = 3;                                   // pairs generated together: three independent fp64 chains in flight
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -125,6 +126,13 @@ __global__ void __launch_bounds__(256, 4) k_displace_soa(double *__restrict__ x,
 #pragma unroll
                     for (int j = 0; j < G; ++j) rr[j] = pvd_draw(seed, i, step, PVD_STREAM_DISP, (unsigned)(k0 + j));
                     normal_pairs_fp64<G>(rr, z0, z1);
+                } else if (RNG == PVD_RNG_ZIGGURAT) {
+#pragma unroll
+                    for (int j = 0; j < G; ++j) {
+                        const uint4 r = pvd_draw(seed, i, step, PVD_STREAM_DISP, (unsigned)(k0 + j));
+                        z0[j] = zig_normal(seed, i, step, 2 * (k0 + j), r.x, r.y);
+                        z1[j] = (2 * (k0 + j) + 1 < nc) ? zig_normal(seed, i, step, 2 * (k0 + j) + 1, r.z, r.w) : 0.0;
+                    }
                 } else {
 #pragma unroll
                     for (int j = 0; j < G; ++j) normal_pair<RNG>(pvd_draw(seed, i, step, PVD_STREAM_DISP, (unsigned)(k0 + j)), z0[j], z1[j]);

@@ -10,6 +10,9 @@ static int nn_enqueue_discrete_step(pvd_sim *s, StepArgs &a)
     } else if (s->cfg.rng_mode == PVD_RNG_FAST)
         k_displace_soa<PVD_RNG_FAST><<<g, 256, 0, s->stream>>>(x, s->st.as<DevState>(), s->parity, 0, 0, s->cap, s->nc, s->cfg.ndim, s->cfg.seed,
                                                                nullptr, nullptr, s->sigma_dev.as<double>(), nullptr);
+    else if (s->cfg.rng_mode == PVD_RNG_ZIGGURAT)
+        k_displace_soa<PVD_RNG_ZIGGURAT><<<g, 256, 0, s->stream>>>(x, s->st.as<DevState>(), s->parity, 0, 0, s->cap, s->nc, s->cfg.ndim, s->cfg.seed,
+                                                                   nullptr, nullptr, s->sigma_dev.as<double>(), nullptr);
     else
         k_displace_soa<PVD_RNG_FP64><<<g, 256, 0, s->stream>>>(x, s->st.as<DevState>(), s->parity, 0, 0, s->cap, s->nc, s->cfg.ndim, s->cfg.seed,
                                                                nullptr, nullptr, s->sigma_dev.as<double>(), nullptr);

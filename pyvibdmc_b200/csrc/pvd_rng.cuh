@@ -175,12 +175,124 @@ __device__ __forceinline__ void normal_pairs_fp64(const uint4 (&r)[NP], double (
     }
 }
 
+// ---------------------------------------------------------------- ziggurat normals (PVD_RNG_ZIGGURAT)
+// Marsaglia & Tsang's ziggurat (J. Stat. Softw. 5(8), 2000) in Doornik's corrected form (layer index, sign and
+// abscissa from DISJOINT random bits), 1024 layers, fp64: the method NumPy's Generator.normal uses (256 layers
+// there).  The distribution is exact (no approximation of any transcendental on the common path): with
+// probability 0.9957 a normal costs one table look-up, one subtraction, one multiplication and one comparison;
+// the rest (wedges: one exp; tail beyond R = 4.03: two logs) is handled per walker after all its components took
+// the common path, so a warp diverges about once per tile of 32 x 9 normals.
+//   bits of one normal (64 of the 128 a Philox call returns): lo[9:0] layer, lo[10] sign, hi:lo[31:12] 52-bit abscissa
+//   retries: stream purpose 16 + component, call = attempt -> still a pure function of (seed; walker, step, component)
+constexpr int PVD_ZIG_N = 1024;
+__device__ double2 g_zig_xr[PVD_ZIG_N];         // {x_i, x_{i+1} / x_i}; x_0 = V / f(R) (base strip), x_1 = R, x_N = 0
+__device__ double g_zig_f[PVD_ZIG_N + 1];       // f(x_i) = exp(-x_i^2 / 2), f(x_N) = 1
+__shared__ double2 s_zig_xr[PVD_ZIG_N];         // per-CTA copy (allocated only in kernels that call zig_stage)
+
+// copy the table into shared memory; every thread of the CTA must call it before the first normal
+__device__ __forceinline__ void zig_stage()
+{
+    for (int i = threadIdx.x; i < PVD_ZIG_N; i += blockDim.x) s_zig_xr[i] = g_zig_xr[i];
+    __syncthreads();
+}
+__device__ __forceinline__ void zig_decode(unsigned lo, unsigned hi, int &layer, double &mag, unsigned &sgn)
+{
+    layer = (int)(lo & (unsigned)(PVD_ZIG_N - 1));
+    sgn = (lo << 21) & 0x80000000u;
+    mag = __hiloint2double((int)(0x3FF00000u | (hi >> 12)), (int)((hi << 20) | (lo >> 12))) - 1.0;      // [0, 1), 52 bits
+}
+__device__ __forceinline__ double zig_signed(double x, unsigned sgn)
+{
+    return __hiloint2double(__double2hiint(x) ^ (int)sgn, __double2loint(x));
+}
+// uniform in (0, 1] with 53 random bits (argument of a logarithm)
+__device__ __forceinline__ double u53_open(unsigned lo, unsigned hi)
+{
+    const unsigned long long r = ((unsigned long long)hi << 32) | lo;
+    return (double)((r >> 11) + 1ull) * 0x1.0p-53;
+}
+// Everything but the common path, for component `comp` whose first candidate (lo, hi) was not accepted outright.
+__device__ __forceinline__ double zig_slow(uint64_t seed, long long slot, long long step, int comp, unsigned lo, unsigned hi)
+{
+    const double R = s_zig_xr[1].x;
+    for (unsigned attempt = 0; attempt < 250u; ++attempt) {
+        int layer;
+        double mag;
+        unsigned sgn;
+        zig_decode(lo, hi, layer, mag, sgn);
+        const double2 t = s_zig_xr[layer];
+        if (mag < t.y) return zig_signed(mag * t.x, sgn);                    // a fresh candidate on the common path
+        uint4 q = pvd_draw(seed, slot, step, 16u + (unsigned)comp, attempt);
+        if (layer == 0) {
+            // tail beyond R (Marsaglia 1964): x = -ln(U1)/R, accept when -2 ln(U2) > x^2
+            for (unsigned more = attempt + 1u;; ++more) {
+                const double xx = -log(u53_open(q.x, q.y)) / R, yy = -log(u53_open(q.z, q.w));
+                if (yy + yy > xx * xx || more >= 250u) return zig_signed(R + xx, sgn);
+                q = pvd_draw(seed, slot, step, 16u + (unsigned)comp, more);
+            }
+        }
+        // wedge of layer i: uniform height between f(x_i) and f(x_{i+1}) against the density
+        const double x = mag * t.x, f0 = g_zig_f[layer], f1 = g_zig_f[layer + 1];
+        if (fma(u53(q.x, q.y), f1 - f0, f0) < exp(-0.5 * x * x)) return zig_signed(x, sgn);
+        lo = q.z;
+        hi = q.w;
+    }
+    return 0.0;    // unreachable in practice (each attempt succeeds with probability > 1/2)
+}
+// one normal, common path or not, decided on the spot (kernels with a run-time number of components)
+__device__ __forceinline__ double zig_normal(uint64_t seed, long long slot, long long step, int comp, unsigned lo, unsigned hi)
+{
+    int layer;
+    double mag;
+    unsigned sgn;
+    zig_decode(lo, hi, layer, mag, sgn);
+    const double2 t = s_zig_xr[layer];
+    if (mag < t.y) return zig_signed(mag * t.x, sgn);
+    return zig_slow(seed, slot, step, comp, lo, hi);
+}
+// NC normals of one walker: all components take the common path first, the exceptions are settled afterwards
+template <int NC>
+__device__ __forceinline__ void walker_normals_zig(uint64_t seed, long long slot, long long step, double (&z)[NC])
+{
+    static_assert(NC <= 32, "one pending bit per component");
+    constexpr int NP = (NC + 1) / 2;
+    unsigned pend = 0u;
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+        const uint4 r = pvd_draw(seed, slot, step, PVD_STREAM_DISP, (unsigned)k);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int c = 2 * k + h;
+            if (c < NC) {
+                int layer;
+                double mag;
+                unsigned sgn;
+                zig_decode(h ? r.z : r.x, h ? r.w : r.y, layer, mag, sgn);
+                const double2 t = s_zig_xr[layer];
+                z[c] = zig_signed(mag * t.x, sgn);
+                if (!(mag < t.y)) pend |= 1u << c;
+            }
+        }
+    }
+    while (pend) {
+        const int c = __ffs((int)pend) - 1;
+        pend &= pend - 1u;
+        const uint4 r = pvd_draw(seed, slot, step, PVD_STREAM_DISP, (unsigned)(c >> 1));
+        const double v = zig_slow(seed, slot, step, c, (c & 1) ? r.z : r.x, (c & 1) ? r.w : r.y);
+#pragma unroll
+        for (int j = 0; j < NC; ++j)
+            if (j == c) z[j] = v;
+    }
+}
+
 // NC standard normals for walker `slot` at `step` into z[0..NC)
 template <int NC, int MODE>
 __device__ __forceinline__ void walker_normals(uint64_t seed, long long slot, long long step, double (&z)[NC])
 {
     constexpr int NP = (NC + 1) / 2;
-    if constexpr (MODE == PVD_RNG_FP64) {
+    if constexpr (MODE == PVD_RNG_ZIGGURAT) {
+        walker_normals_zig<NC>(seed, slot, step, z);
+    } else if constexpr (MODE == PVD_RNG_FP64) {
         uint4 r[NP];
         double z0[NP], z1[NP];
 #pragma unroll

@@ -379,6 +379,7 @@ __global__ void __launch_bounds__(PVD_CTA, POT::MIN_CTAS) k_step_discrete(const 
     constexpr int NC = POT::NC;
     __shared__ TileStash<NC> s_stash[PVD_WARPS];
     if (!step_prologue(a)) return;
+    if constexpr (RNG == PVD_RNG_ZIGGURAT) zig_stage();
     const DevState *sip = &a.st[a.parity];
     const long long n = sip->n, step = sip->step;
     const double vref = sip->vref;
@@ -395,10 +396,11 @@ __global__ void __launch_bounds__(PVD_CTA, POT::MIN_CTAS) k_step_discrete(const 
     long long pending = -1;
     int pending_total = 0;
 
+    long long tile = feed_next(feed, tickets, ntiles, a.ticket_batch);
     while (true) {
-        const long long tile = feed_next(feed, tickets, ntiles, a.ticket_batch);
         double x[NC], v = 0.0;
         int cnt = 0, incl = 0, tile_total = 0, who = 0;
+        unsigned issued = 0u;
         if (tile >= 0) {
             const long long i = tile * PVD_TILE + lane;
             const bool active = i < n;
@@ -442,6 +444,7 @@ __global__ void __launch_bounds__(PVD_CTA, POT::MIN_CTAS) k_step_discrete(const 
             incl = warp_incl_scan(cnt);
             tile_total = __shfl_sync(0xffffffffu, incl, 31);
             publish_aggregate(a.status, tile, step, tile_total);       // successors can use it right away
+            issued = feed_issue(feed, tickets);                        // the next ticket travels while the previous tile is scattered
         }
         if (pending >= 0) {
             // scatter the previous tile: its predecessors have had a whole tile's worth of time to publish
@@ -473,6 +476,7 @@ __global__ void __launch_bounds__(PVD_CTA, POT::MIN_CTAS) k_step_discrete(const 
         __syncwarp();
         pending = tile;
         pending_total = tile_total;
+        tile = feed_take(feed, issued, ntiles, a.ticket_batch);
     }
     cta_finish_step(a, acc, ntiles, false, -1);
 }

@@ -135,7 +135,7 @@ def test_fp64_normals_match_reference_arithmetic(K):
     assert worst < 4e-15, worst
 
 
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 2])
 def test_normals_statistics(K, mode):
     from scipy import stats
     z = K.normals(2_000_000, 9, seed=1234, step=5, rng_mode=mode)

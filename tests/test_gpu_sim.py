@@ -86,15 +86,18 @@ def test_replay_h2o_discrete_trajectory(K):
     sim.close()
 
 
-def test_external_potential_path_matches_fused(K, oracle):
-    """Stepping with a host-side potential (plug-in path) == fused built-in path, same seed."""
+@pytest.mark.parametrize("rng_mode", [0, 2])
+def test_external_potential_path_matches_fused(K, oracle, rng_mode):
+    """Stepping with a host-side potential (plug-in path) == fused built-in path, same seed (Box-Muller and
+    ziggurat: the fused kernel settles a walker's rare non-common-path normals after the common ones, the
+    generic kernel on the spot -- same numbers)."""
     from pyvibdmc_b200 import _capi
     m = np.array([oracle.mass('H'), oracle.mass('H'), oracle.mass('O')])
     start = np.repeat(EQ[None] * 1.01, 2000, 0)
-    a = K.DeviceSim(3, 3, m, 2000, 5.0, _capi.POT_H2O_PS, seed=42)
+    a = K.DeviceSim(3, 3, m, 2000, 5.0, _capi.POT_H2O_PS, seed=42, rng_mode=rng_mode)
     a.upload(start)
     a.run(25)
-    b = K.DeviceSim(3, 3, m, 2000, 5.0, _capi.POT_EXTERNAL, seed=42)
+    b = K.DeviceSim(3, 3, m, 2000, 5.0, _capi.POT_EXTERNAL, seed=42, rng_mode=rng_mode)
     b.upload(start)
     b.set_pots(K.pes_h2o(start))
     for _ in range(25):
