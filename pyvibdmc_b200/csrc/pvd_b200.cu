@@ -711,12 +711,25 @@ static int enqueue_step(pvd_sim *s, int do_branch, const double *inj_disp, const
 #ifndef PVD_STEP_KERNEL
 #define PVD_STEP_KERNEL k_step_discrete
 #endif
+        // Programmatic dependent launch: the next step's CTAs may become resident (and stage their tables) while this
+        // step drains; they read nothing of the walker state before griddepcontrol.wait (see k_step_discrete).
+        static const bool use_pdl = getenv("PVD_NO_PDL") == nullptr;
+        cudaLaunchAttribute pdl_attr[1];
+        pdl_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        pdl_attr[0].val.programmaticStreamSerializationAllowed = 1;
+#define LAUNCH_DISC_R(POT, R)                                                                       \
+    do {                                                                                            \
+        cudaLaunchConfig_t lc{};                                                                    \
+        lc.gridDim = dim3((unsigned)gp); lc.blockDim = dim3(PVD_CTA); lc.dynamicSmemBytes = 0; lc.stream = s->stream; \
+        lc.attrs = pdl_attr; lc.numAttrs = use_pdl ? 1 : 0;                                         \
+        PVD_CUDA(cudaLaunchKernelEx(&lc, PVD_STEP_KERNEL<POT, R>, a));                              \
+    } while (0)
 #define LAUNCH_DISC(POT)                                                                            \
     do {                                                                                            \
         const int gp = POT::MIN_CTAS >= 4 ? s->grid_light : g;                                      \
-        if (fast) PVD_STEP_KERNEL<POT, PVD_RNG_FAST><<<gp, PVD_CTA, 0, s->stream>>>(a);            \
-        else if (s->cfg.rng_mode == PVD_RNG_ZIGGURAT) PVD_STEP_KERNEL<POT, PVD_RNG_ZIGGURAT><<<gp, PVD_CTA, 0, s->stream>>>(a); \
-        else PVD_STEP_KERNEL<POT, PVD_RNG_FP64><<<gp, PVD_CTA, 0, s->stream>>>(a);                 \
+        if (fast) LAUNCH_DISC_R(POT, PVD_RNG_FAST);                                                 \
+        else if (s->cfg.rng_mode == PVD_RNG_ZIGGURAT) LAUNCH_DISC_R(POT, PVD_RNG_ZIGGURAT);         \
+        else LAUNCH_DISC_R(POT, PVD_RNG_FP64);                                                      \
     } while (0)
         switch (s->cfg.potential) {
         case PVD_POT_H2O_PS: LAUNCH_DISC(PotH2O); break;
@@ -732,6 +745,7 @@ static int enqueue_step(pvd_sim *s, int do_branch, const double *inj_disp, const
         default: return pvd_fail(PVD_E_STATE, "pvd_sim_run needs a built-in potential (use the ext_* calls for PVD_POT_EXTERNAL)");
         }
 #undef LAUNCH_DISC
+#undef LAUNCH_DISC_R
         PVD_CHECK_LAUNCH();
         s->cur ^= 1;
     }

@@ -378,8 +378,12 @@ __global__ void __launch_bounds__(PVD_CTA, POT::MIN_CTAS) k_step_discrete(const 
 {
     constexpr int NC = POT::NC;
     __shared__ TileStash<NC> s_stash[PVD_WARPS];
+    if constexpr (RNG == PVD_RNG_ZIGGURAT) zig_stage();           // constant table: independent of the previous step
+    // launched with programmatic stream serialisation: everything above may overlap the previous step's tail;
+    // nothing below may run before that step has completed and its writes are visible
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (!step_prologue(a)) return;
-    if constexpr (RNG == PVD_RNG_ZIGGURAT) zig_stage();
     const DevState *sip = &a.st[a.parity];
     const long long n = sip->n, step = sip->step;
     const double vref = sip->vref;
