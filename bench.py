@@ -119,7 +119,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--walkers", type=int, default=1_000_000, help="walkers per GPU")
-    ap.add_argument("--rng", default="fp64", choices=["fp64", "fast"])
+    ap.add_argument("--rng", default="ziggurat", choices=["ziggurat", "fp64", "fast"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--collective", default="mailbox", choices=["mailbox", "nccl"],
                     help="per-step exchange for N > 1: NVLink peer-memory mailbox fused into the step kernel, or a NCCL all-reduce")
@@ -142,7 +142,7 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
-    rng_mode = _capi.RNG_FAST if args.rng == "fast" else _capi.RNG_FP64
+    rng_mode = _capi.RNG_MODES[args.rng]
     n_loc = args.walkers
     n0 = n_loc * world
     stream = torch.cuda.Stream(device=dev)        # all kernels, NCCL calls and timing events share this stream
@@ -344,7 +344,8 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "h2o_ps_discrete", "potential": "Partridge-Schwenke H2O (shipped Fortran PES, CUDA fp64)",
                        "weighting": "discrete", "walkers_per_gpu": n_loc, "global_walkers": n0, "delta_t": DT,
-                       "rng": "philox4x32-10 + " + ("fp64 Box-Muller" if args.rng == "fp64" else "SFU Box-Muller"),
+                       "rng": "philox4x32-10 + " + {"ziggurat": "fp64 ziggurat (1024 layers)", "fp64": "fp64 Box-Muller",
+                                                       "fast": "SFU Box-Muller"}[args.rng],
                        "l2": "walker state (2 x 80 MB ping-pong at 1e6 walkers) exceeds the 126 MB L2; no flush needed",
                        "parallelism": (f"walkers sharded over {world} GPU(s); per step {_capi.NSUMS} doubles per shard are exchanged "
                                        + ("by peer stores over NVLink from the step kernel's last CTA (mailbox), no collective kernel"

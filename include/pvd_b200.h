@@ -159,7 +159,7 @@ typedef struct {
     int32_t weighting;            /* PVD_WEIGHT_* */
     int32_t potential;            /* PVD_POT_* */
     int32_t trial;                /* PVD_TRIAL_* */
-    int32_t rng_mode;             /* PVD_RNG_* */
+    int32_t rng_mode;             /* PVD_RNG_*; the importance-sampling move draws ZIGGURAT requests with FP64 Box-Muller */
     int32_t device;               /* CUDA device ordinal */
     int32_t rank, world_size;     /* shard id / number of shards (multi-GPU); 0,1 for a single GPU */
     int64_t num_walkers;          /* N0: target population of THIS shard's share is num_walkers/world_size */

@@ -19,6 +19,8 @@ TRIAL_NONE, TRIAL_HARM1D, TRIAL_H2O_FD, TRIAL_H2O_AN = range(4)
 IMP_STANDARD, IMP_SECOND_DISPLACEMENT, IMP_EXCITED_STATE = range(3)
 WEIGHT_DISCRETE, WEIGHT_CONTINUOUS = 0, 1
 RNG_FP64, RNG_FAST, RNG_ZIGGURAT = 0, 1, 2
+RNG_DEFAULT = RNG_ZIGGURAT          # exact normals at the lowest cost (include/pvd_b200.h)
+RNG_MODES = {'ziggurat': RNG_ZIGGURAT, 'fp64': RNG_FP64, 'fast': RNG_FAST}
 ZIGGURAT_LAYERS = 1024
 MAX_ATOMS, MAX_COMP, MAX_WORLD = 16, 48, 8
 NSUMS = 8 + 4 * MAX_WORLD

@@ -470,6 +470,7 @@ int pvd_sim_create(const pvd_config *cfg, pvd_sim **out)
     PVD_REQUIRE(cfg->world_size >= 1 && cfg->world_size <= PVD_MAX_WORLD && cfg->rank >= 0 && cfg->rank < cfg->world_size, "bad rank/world_size");
     PVD_REQUIRE(cfg->weighting == PVD_WEIGHT_DISCRETE || cfg->weighting == PVD_WEIGHT_CONTINUOUS, "bad weighting");
     PVD_REQUIRE(cfg->stats_ring >= 1, "stats_ring must be >= 1");
+    PVD_REQUIRE(cfg->rng_mode >= PVD_RNG_FP64 && cfg->rng_mode <= PVD_RNG_ZIGGURAT, "unknown rng_mode");
     PVD_CUDA(cudaSetDevice(cfg->device));
     if (int rc = ensure_device_ready()) return rc;
     pvd_sim *s = new pvd_sim();

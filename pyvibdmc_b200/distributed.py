@@ -56,7 +56,7 @@ class ShardedSim:
     (backend nccl) and one CUDA device per rank."""
 
     def __init__(self, natoms, ndim, masses, num_walkers, delta_t, potential, weighting="discrete", seed=0,
-                 rng_mode=_capi.RNG_FP64, pot_params=None, thresh_lower=None, thresh_upper=None, rebalance_every=250,
+                 rng_mode=_capi.RNG_DEFAULT, pot_params=None, thresh_lower=None, thresh_upper=None, rebalance_every=250,
                  capacity=None, stats_ring=1 << 14, trial=_capi.TRIAL_NONE, trial_table=None, collective="mailbox"):
         import torch
         import torch.distributed as dist
@@ -196,7 +196,7 @@ class ShardedDevice:
     so each rank could write the reference's output files (DMC_Sim lets rank 0 write into the real folder)."""
 
     def __init__(self, natoms, ndim, masses, num_walkers, delta_t, potential, weighting="discrete", alpha=None, capacity=None,
-                 seed=0, rng_mode=_capi.RNG_FP64, trial=_capi.TRIAL_NONE, pot_params=None, thresh_lower=None, thresh_upper=None,
+                 seed=0, rng_mode=_capi.RNG_DEFAULT, trial=_capi.TRIAL_NONE, pot_params=None, thresh_lower=None, thresh_upper=None,
                  device=0, stats_ring=1 << 16, imp_variant=_capi.IMP_STANDARD, trial_table=None, rebalance_every=250):
         if alpha is not None and abs(alpha - 1.0 / (2.0 * delta_t)) > 1e-15:
             raise NotImplementedError("DEBUG_alpha with a sharded run")

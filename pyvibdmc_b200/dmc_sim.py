@@ -45,7 +45,7 @@ class DMC_Sim:
                  log_every=1, cur_timestep=0, cont_wt_thresh=None, imp_samp=None, imp_samp_oned=False,
                  second_impsamp_displacement=False, excited_state_imp_samp=False, adiabatic_dmc=None, fixed_node=None,
                  DEBUG_alpha=None, DEBUG_save_desc_wt_tracker=None, DEBUG_save_training_every=None,
-                 DEBUG_save_before_bod=False, DEBUG_mass_change=None, *, seed=None, rng='fp64', device=0, distributed=None):
+                 DEBUG_save_before_bod=False, DEBUG_mass_change=None, *, seed=None, rng='ziggurat', device=0, distributed=None):
         self.atoms = atoms
         self.sim_name = sim_name
         self.output_folder = output_folder
@@ -79,7 +79,9 @@ class DMC_Sim:
         self._deb_alpha = DEBUG_alpha
         self._deb_mass_change = DEBUG_mass_change
         self._seed = int(np.random.randint(0, 2 ** 31 - 1)) if seed is None else int(seed)
-        self._rng_mode = _capi.RNG_FAST if rng == 'fast' else _capi.RNG_FP64
+        if rng not in _capi.RNG_MODES:
+            raise ValueError(f"rng must be one of {sorted(_capi.RNG_MODES)}")
+        self._rng_mode = _capi.RNG_MODES[rng]
         self._device = int(device)
         self._dev = None
         # one process per GPU under torch.distributed (torchrun): every rank runs this same object, walkers are sharded,

@@ -75,7 +75,7 @@ def pes_morse1d(x, de, alpha):
 
 
 # ----------------------------------------------------------------------------- random displacement
-def displace(cds, sigmas, seed, step=0, rng_mode=_capi.RNG_FP64):
+def displace(cds, sigmas, seed, step=0, rng_mode=_capi.RNG_DEFAULT):
     """move_randomly (pyvibdmc.py:540-547) on the GPU; returns the displaced copy."""
     out = f64(cds).copy()
     n, a, d = out.shape
@@ -84,7 +84,7 @@ def displace(cds, sigmas, seed, step=0, rng_mode=_capi.RNG_FP64):
     return out
 
 
-def normals(n, ncomp, seed, step=0, rng_mode=_capi.RNG_FP64):
+def normals(n, ncomp, seed, step=0, rng_mode=_capi.RNG_DEFAULT):
     z = np.empty((n, ncomp))
     check(lib.pvd_normals(ptr(z), n, ncomp, int(seed), int(step), int(rng_mode)))
     return z
@@ -202,7 +202,7 @@ class DeviceSim:
     """HBM-resident walker ensemble + per-step kernels (C handle pvd_sim)."""
 
     def __init__(self, natoms, ndim, masses, num_walkers, delta_t, potential, weighting="discrete", alpha=None,
-                 capacity=None, seed=0, rng_mode=_capi.RNG_FP64, trial=_capi.TRIAL_NONE, pot_params=None,
+                 capacity=None, seed=0, rng_mode=_capi.RNG_DEFAULT, trial=_capi.TRIAL_NONE, pot_params=None,
                  thresh_lower=None, thresh_upper=None, device=0, rank=0, world_size=1, stats_ring=1 << 16,
                  imp_variant=_capi.IMP_STANDARD):
         cfg = _capi.PvdConfig()

@@ -25,7 +25,7 @@ def blocked_sem(x, nblocks=20):
     return means.std(ddof=1) / np.sqrt(nblocks)
 
 
-def run(kind, n0, T, dt, seed, rng=_capi.RNG_FP64):
+def run(kind, n0, T, dt, seed, rng=_capi.RNG_DEFAULT):
     if kind == "h2o":
         sim = K.DeviceSim(3, 3, M, n0, dt, _capi.POT_H2O_PS, seed=seed, rng_mode=rng, stats_ring=T + 8)
         sim.upload(np.repeat(EQ[None] * 1.01, n0, axis=0))
@@ -48,6 +48,7 @@ def run(kind, n0, T, dt, seed, rng=_capi.RNG_FP64):
 
 def main():
     out = {"config2_h2o_20000x20000_dt5": [run("h2o", 20000, 20000, 5.0, s) for s in range(5)],
+           "config2_boxmuller_fp64": [run("h2o", 20000, 20000, 5.0, s, _capi.RNG_FP64) for s in range(5)],
            "config2_fast_rng": [run("h2o", 20000, 20000, 5.0, s, _capi.RNG_FAST) for s in range(5)],
            "tutorial_h2o_8000x5000_dt5": [run("h2o", 8000, 5000, 5.0, 100 + s) for s in range(5)],
            "config1_ho_1000x5000_dt10": [run("ho", 1000, 5000, 10.0, s) for s in range(5)],
