@@ -109,6 +109,7 @@ def run_reference_arm(args):
                              "sample": f"{n} walkers x {args.steps} time steps"},
             "e2e": {"value": res["value"], "unit": "walker-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    args.restore_stdout()
     print(json.dumps(line))
 
 
@@ -125,6 +126,15 @@ def main():
                     help="per-step exchange for N > 1: NVLink peer-memory mailbox fused into the step kernel, or a NCCL all-reduce")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the per-GPU timings of BASELINE configs 1, 3, 4, 5")
     args = ap.parse_args()
+    # stdout carries exactly one JSON line: anything a library prints there meanwhile (NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def restore_stdout():
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+    args.restore_stdout = restore_stdout
     if args.impl == "reference":
         return run_reference_arm(args)
     args.warmup = max(args.warmup, 3)
@@ -354,7 +364,8 @@ def main():
             "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
             "tutorial_20k": tut, "other_configs": others, "final_population": int(st["n"]),
             "zpe_cm1_last_half": float(stats["vref"][args.steps // 2:].mean() / 4.556335281212229e-6)}
-    print(json.dumps(line))
+    args.restore_stdout()
+    print(json.dumps(line), flush=True)
     sim.close()
     if world > 1:
         dist.destroy_process_group()

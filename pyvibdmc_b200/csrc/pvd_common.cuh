@@ -272,7 +272,7 @@ __device__ __forceinline__ long long resolve_prefix(unsigned long long *status, 
             if (idx1 >= 0) w1 = ld_relaxed_u64(&status[idx1]);
             ok = status_valid(w0, step) && status_valid(w1, step);
             if (__all_sync(0xffffffffu, ok)) break;
-            __nanosleep(64);              // give the issue slots to the warps we are waiting for
+            __nanosleep(20);              // short back-off (64 ns cost 1.5 us per step at 20 000 walkers: most waiting is in the tail)
         }
         const unsigned m0 = __ballot_sync(0xffffffffu, ((w0 >> 32) & 3ull) == PVD_ST_PREFIX);
         const unsigned m1 = __ballot_sync(0xffffffffu, ((w1 >> 32) & 3ull) == PVD_ST_PREFIX);

@@ -124,10 +124,11 @@ __global__ void __launch_bounds__(PVD_CTA, PROD::MIN_CTAS) k_cont_update(const S
     long long pend = -1;
     int pend_total = 0;
     unsigned pend_mask[SUB];
+    long long tile = feed_next(feed, tickets, ntiles, 1);
     while (true) {
-        const long long tile = feed_next(feed, tickets, ntiles, 1);
         unsigned mask[SUB];
         int total = 0;
+        unsigned issued = 0u;
         if (tile >= 0) {
 #pragma unroll
             for (int s = 0; s < SUB; ++s) {
@@ -153,6 +154,7 @@ __global__ void __launch_bounds__(PVD_CTA, PROD::MIN_CTAS) k_cont_update(const S
                 total += __popc(mask[s]);
             }
             publish_aggregate(a.status, tile, step, total);
+            issued = feed_issue(feed, tickets);                        // the next ticket travels while the previous tile's kill list is written
         }
         if (pend >= 0) {
             long long o = resolve_prefix(a.status, pend, step, pend_total);
@@ -167,6 +169,7 @@ __global__ void __launch_bounds__(PVD_CTA, PROD::MIN_CTAS) k_cont_update(const S
         pend = tile; pend_total = total;
 #pragma unroll
         for (int s = 0; s < SUB; ++s) pend_mask[s] = mask[s];
+        tile = feed_take(feed, issued, ntiles, 1);
     }
     __syncthreads();
     for (int b = threadIdx.x; b < PVD_HIST_BINS; b += PVD_CTA)

@@ -186,10 +186,11 @@ __global__ void __launch_bounds__(PVD_CTA, 2) k_branch_discrete(const StepArgs a
     int pend_total = 0;
     int pend_cnt[PVD_BR_SUB], pend_excl[PVD_BR_SUB];
 
+    long long tile = feed_next(feed, tickets, ntiles, 1);
     while (true) {
-        const long long tile = feed_next(feed, tickets, ntiles, 1);
         int cnt[PVD_BR_SUB], excl[PVD_BR_SUB];
         int tile_total = 0;
+        unsigned issued = 0u;
         if (tile >= 0) {
             bool bad = false;
 #pragma unroll
@@ -222,6 +223,7 @@ __global__ void __launch_bounds__(PVD_CTA, 2) k_branch_discrete(const StepArgs a
             }
             if (bad) atomicOr(a.err_accum, PVD_ERR_WEIGHT);
             publish_aggregate(a.status, tile, step, tile_total);
+            issued = feed_issue(feed, tickets);                        // the next ticket travels while the previous tile is copied
         }
         if (pend >= 0) {
             const long long base = resolve_prefix(a.status, pend, step, pend_total);
@@ -280,6 +282,7 @@ __global__ void __launch_bounds__(PVD_CTA, 2) k_branch_discrete(const StepArgs a
         pend = tile; pend_total = tile_total;
 #pragma unroll
         for (int s = 0; s < PVD_BR_SUB; ++s) { pend_cnt[s] = cnt[s]; pend_excl[s] = excl[s]; }
+        tile = feed_take(feed, issued, ntiles, 1);
     }
     cta_finish_step(a, acc, ntiles, false, -1);
 }
