@@ -103,12 +103,15 @@ __global__ void __launch_bounds__(256, 4) k_displace_soa(double *__restrict__ x,
                                const StepArgs *sig_src, const double *__restrict__ sigma_dev, double *__restrict__ z_out)
 {
     (void)sig_src;
+    __shared__ double s_sig[PVD_MAX_COMP];                 // sigma per component (no integer division in the loop)
     const long long n = st ? st[parity].n : n_fixed;
     const long long step = st ? st[parity].step : step_fixed;
     if (st && st[parity].err) return;
+    for (int c = threadIdx.x; c < nc; c += blockDim.x) s_sig[c] = sigma_dev ? sigma_dev[c / ndim] : 1.0;
     if constexpr (RNG == PVD_RNG_ZIGGURAT) zig_stage();
+    else __syncthreads();
     const int npairs = (nc + 1) / 2;
-    constexpr int G = 3;                                   // pairs generated together: three independent fp64 chains in flight
+    constexpr int G = 3;                                   // pairs generated together: three independent chains in flight
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
 #pragma unroll 1
         for (int k0 = 0; k0 < npairs; k0 += G) {
@@ -121,38 +124,72 @@ __global__ void __launch_bounds__(256, 4) k_displace_soa(double *__restrict__ x,
                     z1[j] = (2 * k + 1 < nc) ? inj_disp[(2 * k + 1) * cap + i] : 0.0;
                 }
             } else {
-                if (RNG == PVD_RNG_FP64) {
-                    uint4 rr[G];
+                uint4 rr[G];
 #pragma unroll
-                    for (int j = 0; j < G; ++j) rr[j] = pvd_draw(seed, i, step, PVD_STREAM_DISP, (unsigned)(k0 + j));
+                for (int j = 0; j < G; ++j) rr[j] = pvd_draw(seed, i, step, PVD_STREAM_DISP, (unsigned)(k0 + j));
+                if (RNG == PVD_RNG_FP64) {
                     normal_pairs_fp64<G>(rr, z0, z1);
                 } else if (RNG == PVD_RNG_ZIGGURAT) {
+                    // common path for the 2G normals of the group, then the rare exceptions (as walker_normals_zig)
+                    unsigned pend = 0u;
 #pragma unroll
                     for (int j = 0; j < G; ++j) {
-                        const uint4 r = pvd_draw(seed, i, step, PVD_STREAM_DISP, (unsigned)(k0 + j));
-                        z0[j] = zig_normal(seed, i, step, 2 * (k0 + j), r.x, r.y);
-                        z1[j] = (2 * (k0 + j) + 1 < nc) ? zig_normal(seed, i, step, 2 * (k0 + j) + 1, r.z, r.w) : 0.0;
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            int layer;
+                            double mag;
+                            unsigned sgn;
+                            zig_decode(h ? rr[j].z : rr[j].x, h ? rr[j].w : rr[j].y, layer, mag, sgn);
+                            const double2 t = s_zig_xr[layer];
+                            (h ? z1[j] : z0[j]) = zig_signed(mag * t.x, sgn);
+                            if (!(mag < t.y) && 2 * (k0 + j) + h < nc) pend |= 1u << (2 * j + h);
+                        }
+                    }
+                    while (pend) {
+                        const int b = __ffs((int)pend) - 1;
+                        pend &= pend - 1u;
+                        const uint4 r = pvd_draw(seed, i, step, PVD_STREAM_DISP, (unsigned)(k0 + (b >> 1)));     // rare: redraw instead of indexing rr[]
+                        const double v = zig_slow(seed, i, step, 2 * k0 + b, (b & 1) ? r.z : r.x, (b & 1) ? r.w : r.y);
+#pragma unroll
+                        for (int j = 0; j < G; ++j) {
+                            if (b == 2 * j) z0[j] = v;
+                            if (b == 2 * j + 1) z1[j] = v;
+                        }
                     }
                 } else {
 #pragma unroll
-                    for (int j = 0; j < G; ++j) normal_pair<RNG>(pvd_draw(seed, i, step, PVD_STREAM_DISP, (unsigned)(k0 + j)), z0[j], z1[j]);
+                    for (int j = 0; j < G; ++j) normal_pair<RNG>(rr[j], z0[j], z1[j]);
                 }
 #pragma unroll
                 for (int j = 0; j < G; ++j) {
                     const int k = k0 + j;
-                    if (2 * k < nc) z0[j] = __dmul_rn(sigma_dev[(2 * k) / ndim], z0[j]);
-                    if (2 * k + 1 < nc) z1[j] = __dmul_rn(sigma_dev[(2 * k + 1) / ndim], z1[j]);
+                    if (2 * k < nc) z0[j] = __dmul_rn(s_sig[2 * k], z0[j]);
+                    if (2 * k + 1 < nc) z1[j] = __dmul_rn(s_sig[2 * k + 1], z1[j]);
                 }
             }
+            double *pz = (z_out ? z_out : x) + (long long)(2 * k0) * cap + i;
+            if (z_out) {
 #pragma unroll
-            for (int j = 0; j < G; ++j) {
-                const int k = k0 + j;
-                if (z_out) {
-                    if (2 * k < nc) z_out[(2 * k) * cap + i] = z0[j];
-                    if (2 * k + 1 < nc) z_out[(2 * k + 1) * cap + i] = z1[j];
-                } else {
-                    if (2 * k < nc) x[(2 * k) * cap + i] = __dadd_rn(x[(2 * k) * cap + i], z0[j]);
-                    if (2 * k + 1 < nc) x[(2 * k + 1) * cap + i] = __dadd_rn(x[(2 * k + 1) * cap + i], z1[j]);
+                for (int j = 0; j < G; ++j) {
+                    const int k = k0 + j;
+                    if (2 * k < nc) pz[0] = z0[j];
+                    if (2 * k + 1 < nc) pz[cap] = z1[j];
+                    pz += 2 * cap;
+                }
+            } else {
+                // all loads of the group first, then the stores
+                double a0[G], a1[G];
+#pragma unroll
+                for (int j = 0; j < G; ++j) {
+                    const int k = k0 + j;
+                    a0[j] = (2 * k < nc) ? pz[(long long)(2 * j) * cap] : 0.0;
+                    a1[j] = (2 * k + 1 < nc) ? pz[(long long)(2 * j + 1) * cap] : 0.0;
+                }
+#pragma unroll
+                for (int j = 0; j < G; ++j) {
+                    const int k = k0 + j;
+                    if (2 * k < nc) pz[(long long)(2 * j) * cap] = __dadd_rn(a0[j], z0[j]);
+                    if (2 * k + 1 < nc) pz[(long long)(2 * j + 1) * cap] = __dadd_rn(a1[j], z1[j]);
                 }
             }
         }
