@@ -940,7 +940,16 @@ int pvd_sim_run_mailbox(pvd_sim *s, int64_t nsteps, int32_t branch_every)
         StepArgs a = make_args(s, 1);
         s->mbox_step = false;
         a.parity = s->parity ^ 1;                  // enqueue_step already flipped the parity
-        k_finalize_mailbox<<<1, 32, 0, s->stream>>>(a, cont);
+        {
+            static const bool use_pdl = getenv("PVD_NO_PDL") == nullptr;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = 1;
+            cudaLaunchConfig_t lc{};
+            lc.gridDim = dim3(1); lc.blockDim = dim3(32); lc.dynamicSmemBytes = 0; lc.stream = s->stream;
+            lc.attrs = at; lc.numAttrs = use_pdl ? 1 : 0;
+            PVD_CUDA(cudaLaunchKernelEx(&lc, k_finalize_mailbox, a, cont));
+        }
         PVD_CHECK_LAUNCH();
     }
     PVD_CUDA(cudaEventRecord(s->ev1, s->stream));

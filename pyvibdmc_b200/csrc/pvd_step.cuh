@@ -152,6 +152,10 @@ __device__ inline void mailbox_send(const StepArgs &a, long long step)
 
 __global__ void __launch_bounds__(32) k_finalize_mailbox(const StepArgs a, int continuous)
 {
+    // programmatic dependent launch on both sides: this warp is resident before the step kernel has drained, and the
+    // next step's CTAs are launched (and stage their tables) while it waits for the peers' messages
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const DevState &si = a.st[a.parity];
     if (si.err) return;                        // the local step already forwarded the dead state
     const int lane = threadIdx.x;
@@ -234,7 +238,7 @@ __device__ __forceinline__ WarpPartial acc_warp_reduce(const LaneAcc &acc)
 // barriers of the kernel are here, when the CTA has nothing left to do).  Warps -> CTA record ->
 // the last CTA to arrive combines all CTA records (every field is exact / order independent, so
 // Vref is bit-reproducible), publishes the shard's sums and, on a single GPU, finalises the step.
-// n_local_fixed < 0: the new local population is the inclusive prefix of the last tile.
+// n_local_fixed < 0: the new local population is the sum of the copy counts.
 __device__ inline void cta_finish_step(const StepArgs &a, const LaneAcc &acc, long long ntiles, bool continuous, long long n_local_fixed,
                                        bool defer_finalize = false)
 {
@@ -285,7 +289,7 @@ __device__ inline void cta_finish_step(const StepArgs &a, const LaneAcc &acc, lo
         double *e = s + PVD_SUM_EXT + 4 * a.rank;
         e[0] = f.vmin; e[1] = f.vmax; e[2] = f.wmin; e[3] = f.wmax;
         long long n_new = n_local_fixed;
-        if (n_local_fixed < 0) n_new = (long long)(ld_relaxed_u64(&a.status[ntiles - 1]) & 0xffffffffull);
+        if (n_local_fixed < 0) n_new = (long long)f.c;      // discrete: the new local population is the sum of the copy counts (exact in double)
         a.st[a.parity ^ 1].n = n_new;
         // every warp of this step has drawn its last ticket: re-arm this parity's counters for step s+2
         unsigned *tk = step_tickets(a, a.parity);

@@ -16,7 +16,7 @@ def one():
     from pyvibdmc_b200.simulation_utilities import Constants
     eq = np.array([[1.81005599, 0., 0.], [-0.45344658, 1.75233806, 0.], [0., 0., 0.]])
     n = int(os.environ.get("AB_WALKERS", "1000000"))
-    rng = {"fast": _capi.RNG_FAST, "zig": _capi.RNG_ZIGGURAT}.get(os.environ.get("AB_RNG"), _capi.RNG_FP64)
+    rng = {"fast": _capi.RNG_FAST, "fp64": _capi.RNG_FP64}.get(os.environ.get("AB_RNG"), _capi.RNG_DEFAULT)
     mH, mO = Constants.mass("H"), Constants.mass("O")
     sim = K.DeviceSim(3, 3, [mH, mH, mO], n, 5.0, _capi.POT_H2O_PS, seed=7, rng_mode=rng)
     sim.upload(np.broadcast_to(eq * 1.01, (n, 3, 3)).copy())
