@@ -71,7 +71,7 @@ def main():
                "(BASELINE configs 1, 3, 4, 5 at their per-GPU sizes: 1e6 HO, 1e6 H2O continuous, 1.25e6 H2O importance sampling, 1.25e7 "
                "water dimers on the NN surface; kernels shared between configurations are pooled per grid size.)", "", launches(lp), ""]
     summ = {}
-    for name in ("r01_step_discrete", "r01_pot_aos", "r01_cont_update", "r01_imp_move", "r01_nn_tc2", "r01_branch_discrete"):
+    for name in ("r01_step_discrete", "r01_pot_aos", "r01_cont_update", "r01_imp_move", "r01_nn_tc2", "r01_branch_discrete", "r01_displace_soa"):
         rep = os.path.join(G, name + ".ncu-rep")
         if os.path.exists(rep):
             summ[name] = raw(rep)
