@@ -29,19 +29,22 @@ static int cont_launch_tail(pvd_sim *s, const StepArgs &a, const ContArgs &ca, l
 {
     const int g = s->grid_light;
     const bool imp = s->cfg.trial != PVD_TRIAL_NONE;
-    k_cont_prefix<<<1, 1024, 0, s->stream>>>(a, ca);
+    // seven short kernels per step: launched with programmatic stream serialisation so that each one's launch latency
+    // overlaps its predecessor's tail (every one of them starts with pdl_wait())
+    PVD_CUDA(launch_pdl(k_cont_prefix, dim3(1), dim3(1024), 0, s->stream, a, ca));
     PVD_CHECK_LAUNCH();
-    k_cont_collect<<<g, PVD_CTA, 0, s->stream>>>(a, ca);
+    PVD_CUDA(launch_pdl(k_cont_collect, dim3((unsigned)g), dim3(PVD_CTA), 0, s->stream, a, ca));
     PVD_CHECK_LAUNCH();
-    k_cont_rank<<<g_num_sms > 0 ? g_num_sms : 148, PVD_RANK_SUB, PVD_RANK_SMEM, s->stream>>>(a, ca);
+    PVD_CUDA(launch_pdl(k_cont_rank, dim3((unsigned)(g_num_sms > 0 ? g_num_sms : 148)), dim3(PVD_RANK_SUB), (size_t)PVD_RANK_SMEM, s->stream, a, ca));
     PVD_CHECK_LAUNCH();
-    k_cont_assign<<<1, 1024, 0, s->stream>>>(a, ca, s->cont_queue.as<ContCand>(), s->cont_root.as<int>(), s->cont_skip.as<unsigned char>());
+    PVD_CUDA(launch_pdl(k_cont_assign, dim3(1), dim3(1024), 0, s->stream, a, ca, s->cont_queue.as<ContCand>(), s->cont_root.as<int>(),
+                        s->cont_skip.as<unsigned char>()));
     PVD_CHECK_LAUNCH();
-    k_cont_copy<<<g, PVD_CTA, 0, s->stream>>>(a, ca, s->x[s->cur].as<double>(), s->v[s->cur].as<double>(), s->who[s->cur].as<int>(),
-                                               imp ? s->f[s->cur].as<double>() : nullptr, imp ? s->psi[s->cur].as<double>() : nullptr,
-                                               imp ? s->lk[s->cur].as<double>() : nullptr, src_out);
+    PVD_CUDA(launch_pdl(k_cont_copy, dim3((unsigned)g), dim3(PVD_CTA), 0, s->stream, a, ca, s->x[s->cur].as<double>(), s->v[s->cur].as<double>(),
+                        s->who[s->cur].as<int>(), imp ? s->f[s->cur].as<double>() : (double *)nullptr,
+                        imp ? s->psi[s->cur].as<double>() : (double *)nullptr, imp ? s->lk[s->cur].as<double>() : (double *)nullptr, src_out));
     PVD_CHECK_LAUNCH();
-    k_cont_finish<<<g, PVD_CTA, 0, s->stream>>>(a, ca);
+    PVD_CUDA(launch_pdl(k_cont_finish, dim3((unsigned)g), dim3(PVD_CTA), 0, s->stream, a, ca));
     PVD_CHECK_LAUNCH();
     return PVD_OK;
 }
@@ -61,7 +64,7 @@ static int cont_enqueue_branch_only(pvd_sim *s, StepArgs &a, long long *src_out)
     cont_in_place(s, a);
     ContArgs ca = make_cont_args(s);
     ca.tile = PVD_TILE * ContFromMemory::SUB;
-    k_cont_update<ContFromMemory><<<s->grid_light, PVD_CTA, 0, s->stream>>>(a, ca);
+    PVD_CUDA(launch_pdl(k_cont_update<ContFromMemory>, dim3((unsigned)s->grid_light), dim3(PVD_CTA), 0, s->stream, a, ca));
     PVD_CHECK_LAUNCH();
     return cont_launch_tail(s, a, ca, src_out);
 }
@@ -75,9 +78,9 @@ static int cont_enqueue_step(pvd_sim *s, StepArgs &a)
 #define LAUNCH_CONT(POT)                                                                                             \
     do {                                                                                                             \
         const int gp = POT::MIN_CTAS >= 4 ? s->grid_light : s->grid;                                                 \
-        if (fast) { ca.tile = PVD_TILE * ContFused<POT, PVD_RNG_FAST>::SUB; k_cont_update<ContFused<POT, PVD_RNG_FAST>><<<gp, PVD_CTA, 0, s->stream>>>(a, ca); } \
-        else if (s->cfg.rng_mode == PVD_RNG_ZIGGURAT) { ca.tile = PVD_TILE * ContFused<POT, PVD_RNG_ZIGGURAT>::SUB; k_cont_update<ContFused<POT, PVD_RNG_ZIGGURAT>><<<gp, PVD_CTA, 0, s->stream>>>(a, ca); } \
-        else { ca.tile = PVD_TILE * ContFused<POT, PVD_RNG_FP64>::SUB; k_cont_update<ContFused<POT, PVD_RNG_FP64>><<<gp, PVD_CTA, 0, s->stream>>>(a, ca); }      \
+        if (fast) { ca.tile = PVD_TILE * ContFused<POT, PVD_RNG_FAST>::SUB; PVD_CUDA(launch_pdl(k_cont_update<ContFused<POT, PVD_RNG_FAST>>, dim3((unsigned)gp), dim3(PVD_CTA), 0, s->stream, a, ca)); } \
+        else if (s->cfg.rng_mode == PVD_RNG_ZIGGURAT) { ca.tile = PVD_TILE * ContFused<POT, PVD_RNG_ZIGGURAT>::SUB; PVD_CUDA(launch_pdl(k_cont_update<ContFused<POT, PVD_RNG_ZIGGURAT>>, dim3((unsigned)gp), dim3(PVD_CTA), 0, s->stream, a, ca)); } \
+        else { ca.tile = PVD_TILE * ContFused<POT, PVD_RNG_FP64>::SUB; PVD_CUDA(launch_pdl(k_cont_update<ContFused<POT, PVD_RNG_FP64>>, dim3((unsigned)gp), dim3(PVD_CTA), 0, s->stream, a, ca)); }      \
     } while (0)
     switch (s->cfg.potential) {
     case PVD_POT_H2O_PS: LAUNCH_CONT(PotH2O); break;

@@ -15,6 +15,25 @@ thread_local std::string g_pvd_err;
 std::atomic<long long> g_pvd_launches{0};
 static thread_local double g_last_kernel_ms = 0.0;
 
+// Launch with programmatic stream serialisation (see pdl_wait in pvd_common.cuh).  Only for kernels that call pdl_wait()
+// before they touch simulation state.  PVD_NO_PDL=1 turns the attribute off (A/B runs).
+template <class... KArgs, class... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args &&...args)
+{
+    static const bool use_pdl = getenv("PVD_NO_PDL") == nullptr;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = grid;
+    lc.blockDim = block;
+    lc.dynamicSmemBytes = smem;
+    lc.stream = stream;
+    lc.attrs = at;
+    lc.numAttrs = use_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&lc, kernel, std::forward<Args>(args)...);
+}
+
 // ---------------------------------------------------------------- small RAII helpers (host)
 struct DevBuf {
     void *p = nullptr;
@@ -713,18 +732,8 @@ static int enqueue_step(pvd_sim *s, int do_branch, const double *inj_disp, const
 #define PVD_STEP_KERNEL k_step_discrete
 #endif
         // Programmatic dependent launch: the next step's CTAs may become resident (and stage their tables) while this
-        // step drains; they read nothing of the walker state before griddepcontrol.wait (see k_step_discrete).
-        static const bool use_pdl = getenv("PVD_NO_PDL") == nullptr;
-        cudaLaunchAttribute pdl_attr[1];
-        pdl_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        pdl_attr[0].val.programmaticStreamSerializationAllowed = 1;
-#define LAUNCH_DISC_R(POT, R)                                                                       \
-    do {                                                                                            \
-        cudaLaunchConfig_t lc{};                                                                    \
-        lc.gridDim = dim3((unsigned)gp); lc.blockDim = dim3(PVD_CTA); lc.dynamicSmemBytes = 0; lc.stream = s->stream; \
-        lc.attrs = pdl_attr; lc.numAttrs = use_pdl ? 1 : 0;                                         \
-        PVD_CUDA(cudaLaunchKernelEx(&lc, PVD_STEP_KERNEL<POT, R>, a));                              \
-    } while (0)
+        // step drains; they read nothing of the walker state before pdl_wait() (see k_step_discrete).
+#define LAUNCH_DISC_R(POT, R) PVD_CUDA(launch_pdl(PVD_STEP_KERNEL<POT, R>, dim3((unsigned)gp), dim3(PVD_CTA), 0, s->stream, a))
 #define LAUNCH_DISC(POT)                                                                            \
     do {                                                                                            \
         const int gp = POT::MIN_CTAS >= 4 ? s->grid_light : g;                                      \
@@ -940,16 +949,7 @@ int pvd_sim_run_mailbox(pvd_sim *s, int64_t nsteps, int32_t branch_every)
         StepArgs a = make_args(s, 1);
         s->mbox_step = false;
         a.parity = s->parity ^ 1;                  // enqueue_step already flipped the parity
-        {
-            static const bool use_pdl = getenv("PVD_NO_PDL") == nullptr;
-            cudaLaunchAttribute at[1];
-            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-            at[0].val.programmaticStreamSerializationAllowed = 1;
-            cudaLaunchConfig_t lc{};
-            lc.gridDim = dim3(1); lc.blockDim = dim3(32); lc.dynamicSmemBytes = 0; lc.stream = s->stream;
-            lc.attrs = at; lc.numAttrs = use_pdl ? 1 : 0;
-            PVD_CUDA(cudaLaunchKernelEx(&lc, k_finalize_mailbox, a, cont));
-        }
+        PVD_CUDA(launch_pdl(k_finalize_mailbox, dim3(1), dim3(32), 0, s->stream, a, cont));
         PVD_CHECK_LAUNCH();
     }
     PVD_CUDA(cudaEventRecord(s->ev1, s->stream));

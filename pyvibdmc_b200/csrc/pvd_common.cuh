@@ -151,6 +151,16 @@ struct WarpPartial {
     double births, deaths, n_in, n_acc;
 };
 
+// Programmatic dependent launch (host side: launch_pdl).  A kernel launched with programmatic stream serialisation may
+// become resident while its predecessor in the stream is still draining; pdl_wait() returns when the predecessor has
+// completed and its writes are visible, and lets this kernel's own successor be launched in turn.  Nothing that reads or
+// writes simulation state may precede it.  Without the launch attribute it returns at once.
+__device__ __forceinline__ void pdl_wait()
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // ---------------------------------------------------------------- device helpers
 __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p)
 {

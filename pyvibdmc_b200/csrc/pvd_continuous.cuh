@@ -108,10 +108,11 @@ __global__ void __launch_bounds__(PVD_CTA, PROD::MIN_CTAS) k_cont_update(const S
 {
     constexpr int SUB = PROD::SUB, TILE = PVD_TILE * SUB;
     __shared__ unsigned s_hist[PVD_HIST_BINS];
-    if (!step_prologue(a)) return;
     for (int b = threadIdx.x; b < PVD_HIST_BINS; b += PVD_CTA) s_hist[b] = 0;
     if constexpr (PROD::RNG_MODE == PVD_RNG_ZIGGURAT) zig_stage();
     __syncthreads();
+    pdl_wait();                                        // everything above is independent of the previous kernel
+    if (!step_prologue(a)) return;
     const DevState *sip = &a.st[a.parity];
     const long long n = sip->n, step = sip->step;
     const double vref = sip->vref, dt = sip->dt_eff;
@@ -187,6 +188,7 @@ __device__ __forceinline__ bool cand_before(const ContCand &p, const ContCand &q
 // ---- 3a. suffix sums of the histogram (one CTA, one bin per 4 threads' worth of work)
 __global__ void __launch_bounds__(1024) k_cont_prefix(const StepArgs a, const ContArgs ca)
 {
+    pdl_wait();
     __shared__ unsigned s_warp[32];
     __shared__ int s_edge;
     __shared__ unsigned s_maxbin;
@@ -252,6 +254,7 @@ __global__ void __launch_bounds__(1024) k_cont_prefix(const StepArgs a, const Co
 // ---- 3b. candidates: everything at or above the bin that contains the K-th largest weight
 __global__ void __launch_bounds__(PVD_CTA) k_cont_collect(const StepArgs a, const ContArgs ca)
 {
+    pdl_wait();
     const DevState *so = &a.st[a.parity];
     const unsigned nk = ca.work->n_kill;
     if (so->err || nk == 0) return;
@@ -280,6 +283,7 @@ __device__ __forceinline__ int weight_subbin(double w)
 }
 __global__ void __launch_bounds__(1024) k_cont_rank(const StepArgs a, const ContArgs ca)
 {
+    pdl_wait();
     extern __shared__ __align__(16) unsigned char s_rank_raw[];
     ContCand *s_c = reinterpret_cast<ContCand *>(s_rank_raw);
     unsigned *sub_cnt = reinterpret_cast<unsigned *>(s_c + PVD_RANK_MAX_BIN);
@@ -375,6 +379,7 @@ __device__ inline int block_arg_extreme(const double *w, long long n, bool want_
 // ---- 4. donor assignment (single CTA of 1024 threads)
 __global__ void __launch_bounds__(1024) k_cont_assign(const StepArgs a, const ContArgs ca, ContCand *queue, int *root, unsigned char *skip)
 {
+    pdl_wait();
     __shared__ double s_val[32];
     __shared__ int s_idx[32];
     __shared__ int s_flag;
@@ -520,6 +525,7 @@ __global__ void __launch_bounds__(1024) k_cont_assign(const StepArgs a, const Co
 __global__ void __launch_bounds__(PVD_CTA) k_cont_copy(const StepArgs a, const ContArgs ca, double *x, double *v, int *who, double *f,
                                                        double *psi, double *lk, long long *src_out)
 {
+    pdl_wait();
     const DevState *so = &a.st[a.parity];
     if (so->err) return;
     const unsigned m = ca.work->n_copy;
@@ -552,6 +558,7 @@ __global__ void __launch_bounds__(PVD_CTA) k_cont_copy(const StepArgs a, const C
 // ---- 6. min / max weight after branching, upper-threshold correction of the sums, Vref + log record
 __global__ void __launch_bounds__(PVD_CTA) k_cont_finish(const StepArgs a, const ContArgs ca)
 {
+    pdl_wait();
     __shared__ double s_mx[PVD_WARPS], s_mn[PVD_WARPS];
     __shared__ unsigned s_last;
     const DevState *so = &a.st[a.parity];

@@ -154,8 +154,7 @@ __global__ void __launch_bounds__(32) k_finalize_mailbox(const StepArgs a, int c
 {
     // programmatic dependent launch on both sides: this warp is resident before the step kernel has drained, and the
     // next step's CTAs are launched (and stage their tables) while it waits for the peers' messages
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    pdl_wait();
     const DevState &si = a.st[a.parity];
     if (si.err) return;                        // the local step already forwarded the dead state
     const int lane = threadIdx.x;
@@ -385,8 +384,7 @@ __global__ void __launch_bounds__(PVD_CTA, POT::MIN_CTAS) k_step_discrete(const 
     if constexpr (RNG == PVD_RNG_ZIGGURAT) zig_stage();           // constant table: independent of the previous step
     // launched with programmatic stream serialisation: everything above may overlap the previous step's tail;
     // nothing below may run before that step has completed and its writes are visible
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    pdl_wait();
     if (!step_prologue(a)) return;
     const DevState *sip = &a.st[a.parity];
     const long long n = sip->n, step = sip->step;
