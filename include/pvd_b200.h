@@ -145,6 +145,16 @@ int pvd_local_kin(const double *d2, int64_t n, int32_t natoms, int32_t ndim, con
 int pvd_nn_h4o2_set_weights(const float *packed, int64_t nfloats);
 int pvd_nn_h4o2(const double *xyz, int64_t n, double *v);
 int pvd_coulomb_descriptor(const double *xyz, int64_t n, int32_t natoms, const double *z, double *desc);
+/* replaces DistIt.run (simulation_utilities/tensorflow_descriptors/distance_descriptors.py:177-213; helpers :88-168) for any
+ * molecule of up to PVD_MAX_ATOMS atoms.  xyz: (n, natoms, 3).  method: 0 distance, 1 coulomb, 2 spf.
+ * pair_scale[npairs] = Z_i Z_j and diag[natoms] = 0.5 Z^2.4 (coulomb only; pairs in itertools.combinations order);
+ * r_eq: distances of the equilibrium structure, per pair when nothing is sorted, else the natoms x natoms matrix of the
+ * equilibrium structure sorted the same way (spf only).  sorted_atoms as a flattened list + offsets (n_atom_lists + 1),
+ * sorted_groups as ngroups x gsize.  full_mat = 0: out is (n, npairs), upper triangle; 1: (n, natoms, natoms).
+ * Bit-identical to the reference's NumPy arithmetic; ties between equal norms keep index order (unspecified there). */
+int pvd_distit(const double *xyz, int64_t n, int32_t natoms, int32_t method, const double *pair_scale, const double *diag,
+               const double *r_eq, const int32_t *atom_lists, const int32_t *atom_list_ofs, int32_t n_atom_lists,
+               const int32_t *groups, int32_t ngroups, int32_t gsize, int32_t full_mat, double *out);
 
 /* ------------------------------------------------------------------ device-resident simulation
  * replaces the state + per-step body of DMC_Sim.propagate (pyvibdmc.py:701-876). */

@@ -308,6 +308,94 @@ def coulomb_descriptor(cds, zs):
     return zs[i0] * zs[i1] / r
 
 
+def distit(cds, zs, method, eq_xyz=None, sorted_atoms=None, sorted_groups=None, full_mat=False, _r_eq=None):
+    """DistIt.run (tensorflow_descriptors/distance_descriptors.py:177-213) restated walker by walker with explicit loops:
+    pair distances in itertools.combinations order (:102-113), Coulomb dressing Z_i Z_j / r and diagonal 0.5 Z^2.4
+    (:154-168), full matrix (:88-100), atoms of each `sorted_atoms` sub-list reordered by descending column norm
+    (:115-132), whole `sorted_groups` swapped by descending sum of their column norms (:134-152), SPF 1 - r_eq / r with
+    r_eq taken from the equilibrium structure sorted the same way (:72-86, 191-213).  Column norms and group sums
+    accumulate sequentially, as NumPy does for these shapes (reduction over a non-last axis; fewer than 8 summands)."""
+    cds = np.asarray(cds, dtype=np.float64)
+    zs = np.asarray(zs)
+    method = method.lower()
+    n, na = cds.shape[0], cds.shape[1]
+    pairs = list(itertools.combinations(range(na), 2))
+    sort = sorted_atoms is not None or sorted_groups is not None
+    zf = zs.astype(np.float64) if method == 'coulomb' else None
+    if method == 'coulomb':
+        rest = np.ones((na, na))
+        np.fill_diagonal(rest, 0.5 * zs ** 0.4)
+        skel = np.outer(zs, zs) * rest
+        diag = np.diag(skel)
+    if method == 'spf' and _r_eq is None:
+        if eq_xyz is None:
+            raise ValueError("eq_xyz is not set but using spf. Fix!")
+        eq = np.asarray(eq_xyz, dtype=np.float64)[None]
+        if sort:
+            _r_eq = distit(eq, zs, 'distance', None, sorted_atoms, sorted_groups, True)[0]
+        else:
+            _r_eq = distit(eq, zs, 'distance')[0]
+    out = []
+    for w in range(n):
+        x = cds[w]
+        vec = np.empty(len(pairs))
+        for p, (i, j) in enumerate(pairs):
+            d = x[i] - x[j]
+            r = np.sqrt((d[0] * d[0] + d[1] * d[1]) + d[2] * d[2])
+            vec[p] = skel[i, j] / r if method == 'coulomb' else r
+        if not sort and not full_mat:
+            out.append(1 - _r_eq / vec if method == 'spf' else vec)
+            continue
+        m = np.zeros((na, na))
+        for p, (i, j) in enumerate(pairs):
+            m[i, j] = m[j, i] = vec[p]
+        if method == 'coulomb':
+            m[np.arange(na), np.arange(na)] = diag
+
+        def colnorm(mat):
+            nrm = np.zeros(na)
+            for j in range(na):
+                acc = 0.0
+                for i in range(na):
+                    acc = acc + mat[i, j] * mat[i, j]
+                nrm[j] = np.sqrt(acc)
+            return nrm
+        if not sort:
+            out.append(m)           # :196-197: an unsorted full matrix is returned as is (for 'spf' too: plain distances)
+            continue
+        if sorted_atoms is not None:
+            nrm = colnorm(m)
+            order = sorted(range(na), key=lambda a: (-nrm[a], a))
+            inds = np.zeros(na, dtype=int)
+            for lst in sorted_atoms:
+                members = [a for a in order if a in lst]
+                for pos, a in zip(lst, members):
+                    inds[pos] = a
+            m = m[np.ix_(inds, inds)]
+        if sorted_groups is not None:
+            nrm = colnorm(m)
+            tot = []
+            for g in sorted_groups:
+                acc = 0.0
+                for a in g:
+                    acc = acc + nrm[a]
+                tot.append(acc)
+            rank = sorted(range(len(sorted_groups)), key=lambda g: (-tot[g], g))
+            inds = np.arange(na)
+            flat = [a for g in sorted_groups for a in g]
+            newflat = [a for g in rank for a in sorted_groups[g]]
+            for pos, a in zip(flat, newflat):
+                inds[pos] = a
+            m = m[np.ix_(inds, inds)]
+        if full_mat:
+            with np.errstate(invalid='ignore', divide='ignore'):
+                out.append(1 - _r_eq / m if method == 'spf' else m)
+        else:
+            v = np.array([m[i, j] for (i, j) in pairs])
+            out.append(1 - np.array([_r_eq[i, j] for (i, j) in pairs]) / v if method == 'spf' else v)
+    return np.array(out)
+
+
 def nn_forward_f32(desc, weights):
     """Keras Sequential[Dense(120,swish)x3, Dense(1,relu)] in float32
     (sample_potentials/TensorflowPots/sample_h4o2_nn.h5; call_sample_model.py:4-9).

@@ -77,6 +77,7 @@ SIGNATURES = {
     "pvd_normals": (C.c_int, [_P, _I64, _I32, _U64, _U64, _I32]),
     "pvd_philox_kat": (C.c_int, [_P, _P, _P]),
     "pvd_ziggurat_table": (C.c_int, [_P, _P]),
+    "pvd_distit": (C.c_int, [_P, _I64, _I32, _I32, _P, _P, _P, _P, _P, _I32, _P, _I32, _I32, _I32, _P]),
     "pvd_branch_discrete": (C.c_int, [_P, _I64, _F64, _F64, _P, _I64, _P, _P, _I64, _P]),
     "pvd_branch_continuous": (C.c_int, [_P, _P, _I64, _F64, _F64, _F64, _F64, _P, _P]),
     "pvd_calc_vref": (C.c_int, [_P, _P, _I64, _I64, _F64, C.POINTER(_F64)]),

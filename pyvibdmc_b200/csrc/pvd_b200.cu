@@ -8,6 +8,7 @@
 #include "pvd_continuous.cuh"
 #include "pvd_impsamp.cuh"
 #include "pvd_nn.cuh"
+#include "pvd_descriptor.cuh"
 
 #include <mutex>
 

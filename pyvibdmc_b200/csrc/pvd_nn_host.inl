@@ -72,4 +72,50 @@ int pvd_coulomb_descriptor(const double *xyz, int64_t n, int32_t natoms, const d
     return PVD_OK;
 }
 
+int pvd_distit(const double *xyz, int64_t n, int32_t natoms, int32_t method, const double *pair_scale, const double *diag,
+               const double *r_eq, const int32_t *atom_lists, const int32_t *atom_list_ofs, int32_t n_atom_lists,
+               const int32_t *groups, int32_t ngroups, int32_t gsize, int32_t full_mat, double *out)
+{
+    PVD_REQUIRE(n >= 0 && natoms >= 2 && natoms <= PVD_MAX_ATOMS && (n == 0 || (xyz && out)), "pvd_distit: bad arguments");
+    PVD_REQUIRE(method >= PVD_DESC_DISTANCE && method <= PVD_DESC_SPF, "pvd_distit: method is 0 (distance), 1 (coulomb) or 2 (spf)");
+    PVD_REQUIRE(method != PVD_DESC_COULOMB || (pair_scale && diag), "pvd_distit: coulomb needs pair_scale and diag");
+    PVD_REQUIRE(n_atom_lists >= 0 && ngroups >= 0 && gsize >= 0 && ngroups * gsize <= natoms, "pvd_distit: bad sorting lists");
+    PVD_REQUIRE(n_atom_lists == 0 || (atom_lists && atom_list_ofs && atom_list_ofs[0] == 0 && atom_list_ofs[n_atom_lists] == natoms),
+                "pvd_distit: sorted_atoms must hold every atom once");
+    PVD_REQUIRE(ngroups == 0 || groups, "pvd_distit: NULL groups");
+    const bool sort = n_atom_lists > 0 || ngroups > 0;
+    PVD_REQUIRE(method != PVD_DESC_SPF || r_eq || (full_mat && !sort), "pvd_distit: spf needs r_eq");
+    if (int rc = ensure_device_ready()) return rc;
+    if (n == 0) return PVD_OK;
+    const int npairs = natoms * (natoms - 1) / 2;
+    static thread_local DistitParams P;          // 6 KB: not on the stack
+    memset(&P, 0, sizeof(P));
+    P.natoms = natoms; P.method = method; P.full_mat = full_mat ? 1 : 0; P.sort = sort ? 1 : 0;
+    P.n_atom_lists = n_atom_lists; P.ngroups = ngroups; P.gsize = gsize;
+    for (int k = 0; k < (n_atom_lists ? natoms : 0); ++k) {
+        PVD_REQUIRE(atom_lists[k] >= 0 && atom_lists[k] < natoms, "pvd_distit: atom index out of range");
+        P.atom_lists[k] = atom_lists[k];
+    }
+    for (int k = 0; k <= n_atom_lists && n_atom_lists; ++k) P.atom_list_ofs[k] = atom_list_ofs[k];
+    for (int k = 0; k < ngroups * gsize; ++k) {
+        PVD_REQUIRE(groups[k] >= 0 && groups[k] < natoms, "pvd_distit: atom index out of range");
+        P.groups[k] = groups[k];
+    }
+    if (method == PVD_DESC_COULOMB) {
+        for (int k = 0; k < npairs; ++k) P.pair_scale[k] = pair_scale[k];
+        for (int k = 0; k < natoms; ++k) P.diag[k] = diag[k];
+    }
+    if (method == PVD_DESC_SPF && r_eq)
+        for (int k = 0; k < (sort ? natoms * natoms : npairs); ++k) P.r_eq[k] = r_eq[k];
+    const size_t per = full_mat ? (size_t)natoms * natoms : (size_t)npairs;
+    DevBuf dx, dp, dout;
+    PVD_CUDA(dx.alloc((size_t)n * natoms * 3 * 8)); PVD_CUDA(dp.alloc(sizeof(P))); PVD_CUDA(dout.alloc((size_t)n * per * 8));
+    PVD_CUDA(cudaMemcpy(dx.p, xyz, (size_t)n * natoms * 3 * 8, cudaMemcpyHostToDevice));
+    PVD_CUDA(cudaMemcpy(dp.p, &P, sizeof(P), cudaMemcpyHostToDevice));
+    k_distit<<<grid_for(n, 128, 16), 128>>>(dx.as<double>(), n, dp.as<DistitParams>(), dout.as<double>());
+    PVD_CHECK_LAUNCH();
+    PVD_CUDA(cudaMemcpy(out, dout.p, (size_t)n * per * 8, cudaMemcpyDeviceToHost));
+    return PVD_OK;
+}
+
 }  // extern "C"

@@ -348,6 +348,26 @@ def gen_descriptor():
     cds[0] = dimer / 0.529177                          # the reference's equilibrium dimer (tests/test_analysis.py:77-82)
     coul = DistIt([8, 1, 1] * 2, 'coulomb', force_numpy=True)
     save("descriptor_golden.npz", coords=cds, coulomb=np.asarray(coul.run(cds)), zs=np.array([8, 1, 1] * 2))
+    # every DistIt variant (distance_descriptors.py:115-152,177-213): method x atom sorting x group sorting x full matrix
+    eq = dimer / 0.529177
+    cases, out = distit_cases(), {"coords": cds[:256], "eq_xyz": eq, "zs": np.array([8, 1, 1] * 2)}
+    for name, kw in cases.items():
+        d = DistIt([8, 1, 1] * 2, force_numpy=True, eq_xyz=eq if kw["method"] == "spf" else None, **kw)
+        out[name] = np.asarray(d.run(cds[:256]))
+    save("distit_golden.npz", **out)
+
+
+def distit_cases():
+    """name -> DistIt keyword arguments; shared with tests/test_descriptors.py (kept literal there)."""
+    sa1, sa2 = [[0], [1, 2], [3], [4, 5]], [[0, 3], [1, 2, 4, 5]]
+    sg1, sg2 = [[0, 1, 2], [3, 4, 5]], [[1, 2], [4, 5]]
+    return {"distance": dict(method="distance"), "spf": dict(method="spf"), "coulomb_full": dict(method="coulomb", full_mat=True),
+            "distance_full": dict(method="distance", full_mat=True), "spf_full": dict(method="spf", full_mat=True),
+            "coulomb_atoms": dict(method="coulomb", sorted_atoms=sa1), "coulomb_atoms2_full": dict(method="coulomb", sorted_atoms=sa2, full_mat=True),
+            "distance_groups": dict(method="distance", sorted_groups=sg1), "coulomb_groups2_full": dict(method="coulomb", sorted_groups=sg2, full_mat=True),
+            "spf_atoms_groups": dict(method="spf", sorted_atoms=sa1, sorted_groups=sg1),
+            "spf_atoms2_full": dict(method="spf", sorted_atoms=sa2, full_mat=True),
+            "coulomb_atoms_groups": dict(method="coulomb", sorted_atoms=sa1, sorted_groups=sg1)}
 
 
 if __name__ == "__main__":

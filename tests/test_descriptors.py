@@ -1,0 +1,67 @@
+"""DistIt descriptors (tensorflow_descriptors/distance_descriptors.py): distance / Coulomb / SPF, atoms sorted within
+sub-lists by column norm, groups swapped by summed column norms, upper triangle or full matrix.  The golden fixture
+holds the unmodified reference's output (tests/golden/make_golden.py: gen_descriptor) for every variant below; the
+oracle restatement and the CUDA kernel behind the drop-in DistIt class must both reproduce it bit for bit."""
+import numpy as np
+import pytest
+
+from conftest import golden
+
+SA1, SA2 = [[0], [1, 2], [3], [4, 5]], [[0, 3], [1, 2, 4, 5]]
+SG1, SG2 = [[0, 1, 2], [3, 4, 5]], [[1, 2], [4, 5]]
+CASES = {"distance": dict(method="distance"), "spf": dict(method="spf"), "coulomb_full": dict(method="coulomb", full_mat=True),
+         "distance_full": dict(method="distance", full_mat=True), "spf_full": dict(method="spf", full_mat=True),
+         "coulomb_atoms": dict(method="coulomb", sorted_atoms=SA1), "coulomb_atoms2_full": dict(method="coulomb", sorted_atoms=SA2, full_mat=True),
+         "distance_groups": dict(method="distance", sorted_groups=SG1), "coulomb_groups2_full": dict(method="coulomb", sorted_groups=SG2, full_mat=True),
+         "spf_atoms_groups": dict(method="spf", sorted_atoms=SA1, sorted_groups=SG1),
+         "spf_atoms2_full": dict(method="spf", sorted_atoms=SA2, full_mat=True),
+         "coulomb_atoms_groups": dict(method="coulomb", sorted_atoms=SA1, sorted_groups=SG1)}
+
+
+def same(a, b):
+    return a.shape == b.shape and np.array_equal(a, b, equal_nan=True)
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_oracle_distit_matches_reference(oracle, name):
+    g = golden("distit_golden.npz")
+    kw = CASES[name]
+    out = oracle.distit(g["coords"][:64], g["zs"], eq_xyz=g["eq_xyz"] if kw["method"] == "spf" else None, **kw)
+    assert same(out, g[name][:64])
+
+
+def test_distit_argument_errors():
+    from pyvibdmc_b200.simulation_utilities.tensorflow_descriptors import DistIt
+    with pytest.raises(ValueError, match="eq_xyz is not set but using spf"):
+        DistIt([8, 1, 1], "spf")
+    with pytest.raises(ValueError, match="Please put all atoms in sorted_atoms list"):
+        DistIt([8, 1, 1], "distance", sorted_atoms=[[0], [1]])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_device_distit_matches_reference(name):
+    from pyvibdmc_b200.simulation_utilities.tensorflow_descriptors import DistIt
+    g = golden("distit_golden.npz")
+    kw = CASES[name]
+    d = DistIt(g["zs"], eq_xyz=g["eq_xyz"] if kw["method"] == "spf" else None, **kw)
+    assert same(np.asarray(d.run(g["coords"])), g[name])
+    assert np.asarray(d.run(g["coords"][:0])).shape == (0,) + g[name].shape[1:]        # empty batch
+    assert same(np.asarray(d.run(g["coords"][:37])), g[name][:37])                     # ragged size
+
+
+@pytest.mark.gpu
+def test_device_distit_larger_molecule_vs_oracle(oracle):
+    """10 atoms, three sorted sub-lists and three groups of three, against the oracle restatement."""
+    from pyvibdmc_b200.simulation_utilities.tensorflow_descriptors import DistIt
+    rng = np.random.default_rng(5)
+    eq = rng.normal(0, 2.0, size=(10, 3))
+    cds = eq[None] + rng.normal(0, 0.3, size=(300, 10, 3))
+    zs = [8, 1, 1, 8, 1, 1, 8, 1, 1, 6]
+    sa, sg = [[0, 3, 6], [1, 2, 4, 5, 7, 8], [9]], [[0, 1, 2], [3, 4, 5], [6, 7, 8]]
+    for method in ("distance", "coulomb", "spf"):
+        for full in (False, True):
+            kw = dict(method=method, sorted_atoms=sa, sorted_groups=sg, full_mat=full)
+            ref = oracle.distit(cds, zs, eq_xyz=eq if method == "spf" else None, **kw)
+            out = np.asarray(DistIt(zs, eq_xyz=eq if method == "spf" else None, **kw).run(cds))
+            assert same(out, ref), (method, full)
