@@ -97,13 +97,17 @@ def run_reference_arm(args):
         return
     from oracle import cpu_reference_loop as R
     cores = os.cpu_count() or 1
-    n = 200_000
-    res = R.time_h2o_discrete(n, args.steps, args.warmup, cores=cores)
+    # bounded sample: as many walkers per step as let the K timed steps finish in about 90 s on this host (at most the
+    # 200 000 of the cpu_baseline leg, at least 20 000 = the tutorial's population, where Pool.map is still efficient)
+    probe = R.time_h2o_discrete(100_000, 2, 1, cores=cores)
+    n = int(min(200_000, max(20_000, probe["value"] * 90.0 / max(args.steps, 1))))
+    res = R.time_h2o_discrete(n, args.steps, min(args.warmup, 5), cores=cores)
     ms = 1e3 * res["seconds"] / max(args.steps, 1)
     line = {"impl": "reference", "metric": "walker-steps/s", "value": res["value"], "unit": "walker-steps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "h2o_ps_discrete", "walkers_per_step": n, "delta_t": DT,
+                       "cpu_warmup_steps": min(args.warmup, 5),
                        "note": "reference CPU path (oracle port: NumPy loop + C PES behind Pool.map), bounded sample"},
             "cpu_baseline": {"value": res["value"], "unit": "walker-steps/s", "cores": cores, "kind": "port",
                              "sample": f"{n} walkers x {args.steps} time steps"},
@@ -116,8 +120,8 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--walkers", type=int, default=1_000_000, help="walkers per GPU")
     ap.add_argument("--rng", default="ziggurat", choices=["ziggurat", "fp64", "fast"])
