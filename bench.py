@@ -2,7 +2,7 @@
 """bench.py -- walker-steps/s of the DMC propagation loop (H2O, shipped Partridge-Schwenke PES,
 discrete weighting: BASELINE.json configs[1] physics) on N B200s.
 
-    python bench.py --gpus 1 --steps 200 --warmup 20
+    python bench.py --gpus 1 --steps 10000 --warmup 100      (the defaults: a timed region of about one second)
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
     python bench.py --impl reference ...     (the reference's CPU path on the host cores)
 
@@ -120,8 +120,8 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
-    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=10000)
+    ap.add_argument("--warmup", type=int, default=100)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--walkers", type=int, default=1_000_000, help="walkers per GPU")
     ap.add_argument("--rng", default="ziggurat", choices=["ziggurat", "fp64", "fast"])
@@ -164,7 +164,7 @@ def main():
 
     def make_sim(nw, nw_global, seed):
         s = K.DeviceSim(3, 3, MASSES, nw_global, DT, _capi.POT_H2O_PS, seed=seed, rng_mode=rng_mode, device=local_rank,
-                        rank=rank, world_size=world, capacity=int(1.5 * nw) + 1024, stats_ring=1 << 14)
+                        rank=rank, world_size=world, capacity=int(1.5 * nw) + 1024, stats_ring=max(1 << 14, args.warmup + args.steps + 8))
         s.set_stream(stream.cuda_stream)
         return s
 
