@@ -375,7 +375,11 @@ struct TileStash {
 // tickets two tiles ahead (+5 us), cp.async prefetch of the next tile's coordinates into shared memory (+8 us),
 // requesting the look-back status words before the potential (+3 us), one 256-walker tile per CTA with
 // block-level scans (+33 us), 3 or 4 CTAs/SM with spills (+2..4 us), two passes over a 3-pair Box-Muller body
-// to shrink the loop below the 32 KB instruction cache (+3.5 us), 64-walker tiles with a double-buffered stash (+9 us).  What did help: fewer executed instructions.
+// to shrink the loop below the 32 KB instruction cache (+3.5 us), 64-walker tiles with a double-buffered stash (+9 us),
+// status words requested right after the potential (+2.7 us), a three-tile-deep pipeline that resolves a tile behind the next
+// tile's random numbers (neutral) or two full tiles late (+6 us), a static first tile per warp (+2.4 us), 192-thread CTAs at
+// three per SM (96 registers, 18 warps: +2 us), a rolled Philox round loop (neutral).  What did help: fewer executed
+// instructions, the ticket overlapped with the scatter, two look-back windows per round trip, dependent launch.
 template <class POT, int RNG>
 __global__ void __launch_bounds__(PVD_CTA, POT::MIN_CTAS) k_step_discrete(const StepArgs a)
 {
