@@ -440,6 +440,8 @@ static StepArgs make_args(pvd_sim *s, int do_branch)
     a.ticket_batch = s->ticket_batch;
     for (int r = 0; r < PVD_MAX_WORLD; ++r) a.mbox[r] = s->mbox_step ? s->peer_mbox[r] : nullptr;
     a.mbox_epoch = s->mbox_epoch;
+    static const bool fold_ok = getenv("PVD_NO_MBOX_FOLD") == nullptr;       // A/B switch
+    a.mbox_fold = (fold_ok && s->mbox_step && s->cfg.weighting == PVD_WEIGHT_DISCRETE && s->cfg.trial == PVD_TRIAL_NONE) ? 1 : 0;
     for (int i = 0; i < PVD_MAX_ATOMS; ++i) a.sigma[i] = s->sigma[i];
     for (int c = 0; c < PVD_MAX_COMP; ++c) a.sigc[c] = s->sigma[(c / (s->cfg.ndim > 0 ? s->cfg.ndim : 1)) % PVD_MAX_ATOMS];
     a.pot = s->pot;
@@ -949,6 +951,7 @@ int pvd_sim_run_mailbox(pvd_sim *s, int64_t nsteps, int32_t branch_every)
         if (rc) { s->mbox_step = false; return rc; }
         StepArgs a = make_args(s, 1);
         s->mbox_step = false;
+        if (a.mbox_fold) continue;                 // discrete steps: the step kernel's last CTA has collected and finalised
         a.parity = s->parity ^ 1;                  // enqueue_step already flipped the parity
         PVD_CUDA(launch_pdl(k_finalize_mailbox, dim3(1), dim3(32), 0, s->stream, a, cont));
         PVD_CHECK_LAUNCH();

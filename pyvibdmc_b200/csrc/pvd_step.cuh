@@ -55,6 +55,7 @@ struct StepArgs {
     double sigma[PVD_MAX_ATOMS];
     double sigc[PVD_MAX_COMP];  // sigma expanded per component (sigc[c] = sigma[c / ndim])
     unsigned long long mbox_epoch; // run epoch (bumped by every upload) folded into the mailbox stamps
+    int mbox_fold;              // 1: the step kernel's last CTA also waits for the peers and finalises (no k_finalize_mailbox launch)
     double *mbox[PVD_MAX_WORLD]; // NVLink mailbox collective: every rank's mailbox mapped into this process (mbox[0] == nullptr: off)
     PotParamsDev pot;
 };
@@ -150,14 +151,11 @@ __device__ inline void mailbox_send(const StepArgs &a, long long step)
     }
 }
 
-__global__ void __launch_bounds__(32) k_finalize_mailbox(const StepArgs a, int continuous)
+// One warp: waits for the world's stamps of this step in its own mailbox, adds the slots in rank order and finalises.
+__device__ inline void mailbox_collect_and_finalize(const StepArgs &a, bool continuous)
 {
-    // programmatic dependent launch on both sides: this warp is resident before the step kernel has drained, and the
-    // next step's CTAs are launched (and stage their tables) while it waits for the peers' messages
-    pdl_wait();
     const DevState &si = a.st[a.parity];
-    if (si.err) return;                        // the local step already forwarded the dead state
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31;
     const double *mine = a.mbox[a.rank];
     const unsigned long long want = (a.mbox_epoch << 40) | (unsigned long long)(si.step + 1);
     bool ok = true;
@@ -188,8 +186,17 @@ __global__ void __launch_bounds__(32) k_finalize_mailbox(const StepArgs a, int c
         if (!ok) {
             forward_dead_state(a);
             a.st[a.parity ^ 1].err |= PVD_ERR_COMM;
-        } else finalize_from_sums(a, continuous != 0);
+        } else finalize_from_sums(a, continuous);
     }
+}
+
+__global__ void __launch_bounds__(32) k_finalize_mailbox(const StepArgs a, int continuous)
+{
+    // programmatic dependent launch on both sides: this warp is resident before the step kernel has drained, and the
+    // next step's CTAs are launched (and stage their tables) while it waits for the peers' messages
+    pdl_wait();
+    if (a.st[a.parity].err) return;            // the local step already forwarded the dead state
+    mailbox_collect_and_finalize(a, continuous != 0);
 }
 
 __global__ void k_finalize(const StepArgs a, int continuous)
@@ -295,7 +302,15 @@ __device__ inline void cta_finish_step(const StepArgs &a, const LaneAcc &acc, lo
         for (int w = 0; w < PVD_WARPS; ++w) tk[w * PVD_TICKET_STRIDE] = 0u;
         if (a.world == 1 && !defer_finalize) finalize_from_sums(a, continuous);
     }
-    if (a.world > 1 && a.mbox[0] && !defer_finalize) mailbox_send(a, a.st[a.parity].step);
+    if (a.world > 1 && a.mbox[0] && !defer_finalize) {
+        mailbox_send(a, a.st[a.parity].step);
+        // discrete steps: the same CTA collects the peers' messages and finalises, which takes a kernel launch and its
+        // dependency wait out of the per-step chain (a.sums is re-used: the local sums have been sent)
+        if (a.mbox_fold) {
+            __syncthreads();
+            if (threadIdx.x < 32) mailbox_collect_and_finalize(a, continuous);
+        }
+    }
 }
 
 // ---------------------------------------------------------------- producers: how a tile obtains (x, V)
