@@ -1,4 +1,4 @@
-// Counter-based random numbers: Philox4x32-10 (Salmon et al., SC'11) + Box-Muller.
+// Counter-based random numbers: Philox4x32-10 (Salmon et al., SC'11) + normals by ziggurat (default) or Box-Muller.
 // Replaces the NumPy global MT19937 stream used by DMC_Sim.move_randomly / birth_or_death
 // (pyvibdmc.py:392,544-546,601).  Streams are addressed by (seed; walker slot, step, purpose),
 // so results do not depend on the launch configuration.

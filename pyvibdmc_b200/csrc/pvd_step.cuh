@@ -1,11 +1,11 @@
 // The per-time-step kernels: replaces the body of DMC_Sim.propagate (pyvibdmc.py:701-876):
 //   move_randomly (:540-547) -> potential (:786-793) -> birth_or_death (:380-454) -> calc_vref (:651-661)
 // Discrete weighting is ONE kernel per step.  Every warp takes tiles of 32 walkers from a ticket
-// counter, moves them (Philox + Box-Muller), evaluates V, draws the integer copy count, and a
+// counter, moves them (Philox bits -> ziggurat or Box-Muller normals), evaluates V, draws the integer copy count, and a
 // single-pass chained scan (decoupled look-back, one status word per tile, driven by the tile's own
 // warp) gives each tile its output offset, so each surviving walker is written exactly once,
 // already compacted and in np.repeat order, into the other half of a ping-pong buffer.  The
-// tile loop has no __syncthreads (shared memory only holds each warp's private stash).  The last CTA to finish combines the exact
+// tile loop has no __syncthreads (shared memory only holds each warp's private stash and the ziggurat table).  The last CTA to finish combines the exact
 // (fixed-point) per-CTA partial sums and produces Vref, the population and the per-step log record on the device.
 #pragma once
 #include "pvd_common.cuh"

@@ -13,7 +13,7 @@ Reference entry points exercised (file:line under /root/reference/pyvibdmc):
   simulation_utilities/imp_samp.py:21-76 drift/metropolis/local_kin/finite_diff
   sample_potentials/PythonPots/harmonicOscillator1D.py:13-17, harm_trial_wfn.py:6-40
   sample_potentials/FortPots/Partridge_Schwenke_H2O/call_trl_h2o.py:63-78
-  simulation_utilities/tensorflow_descriptors/distance_descriptors.py (coulomb)
+  simulation_utilities/tensorflow_descriptors/distance_descriptors.py (coulomb; every DistIt variant: distit_golden.npz)
 """
 import os, sys, ctypes, pickle, tempfile, shutil, warnings
 import numpy as np
