@@ -109,6 +109,24 @@ def ziggurat_numpy(seed, step, n, nc, x, f):
     return z, slow
 
 
+def test_numpy_restatement_is_standard_normal():
+    """No GPU needed: the algorithm the device implements (restated above on the same Philox bits and the same
+    table) produces standard normals -- chi-square over 512 equiprobable bins, tails, moments at 1.8e6 draws."""
+    from scipy import stats
+    x, f = table()
+    z, slow = ziggurat_numpy(0xC0FFEE, 11, 200_000, 9, x, f)
+    z = z.ravel()
+    n, nb = z.size, 512
+    counts = np.bincount(np.searchsorted(stats.norm.ppf(np.arange(1, nb) / nb), z), minlength=nb)
+    chi2 = ((counts - n / nb) ** 2 / (n / nb)).sum()
+    assert stats.chi2.sf(chi2, nb - 1) > 1e-4, chi2
+    for t in (2.0, 3.0, 4.0):
+        p = 2 * stats.norm.sf(t)
+        assert abs((np.abs(z) > t).sum() - n * p) < 5 * np.sqrt(n * p) + 1
+    assert abs(z.mean()) < 5 / np.sqrt(n) and abs(z.var() - 1) < 5 * np.sqrt(2 / n)
+    assert 0.003 < slow.mean() < 0.0056
+
+
 @pytest.fixture(scope="module")
 def K():
     from pyvibdmc_b200 import kernels
