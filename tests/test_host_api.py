@@ -88,6 +88,9 @@ def test_constructor_validation_matches_reference(tmp_path):
         pv.DMC_Sim(start_structures=np.zeros((1, 1, 1)), excited_state_imp_samp=True, imp_samp_oned=True, **kw)
     with pytest.raises(ValueError, match="Number of mass change steps"):
         pv.DMC_Sim(start_structures=np.zeros((1, 1, 1)), DEBUG_mass_change={'change_every': 2, 'factor_per_change': np.ones(5)}, **kw)
+    with pytest.raises(ValueError, match="rng must be one of"):
+        pv.DMC_Sim(start_structures=np.zeros((1, 1, 1)), rng="mt19937", **kw)
+    assert pv.DMC_Sim(start_structures=np.zeros((1, 1, 1)), **kw)._rng_mode == 2      # default: exact fp64 ziggurat normals
     # adiabatic DMC set-up: lambda ramp after the equilibration plateau (reference pyvibdmc.py:276-291)
     sim = pv.DMC_Sim(start_structures=np.zeros((1, 1, 1)),
                      adiabatic_dmc={'initial_lambda': -2.0, 'lambda_change': 0.5, 'equil_time': 2, 'observable_func': lambda c: c[:, 0, 0]}, **kw)
