@@ -34,6 +34,15 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_capi.StepStats) == 96
 
 
+def test_enumerations_match_header():
+    from pyvibdmc_b200 import _capi
+    hdr = open(os.path.join(ROOT, "include", "pvd_b200.h")).read()
+    rng = dict((k, int(v)) for k, v in re.findall(r"(PVD_RNG_[A-Z0-9]+)\s*=\s*(\d+)", hdr))
+    assert rng == {"PVD_RNG_FP64": _capi.RNG_FP64, "PVD_RNG_FAST": _capi.RNG_FAST, "PVD_RNG_ZIGGURAT": _capi.RNG_ZIGGURAT}
+    assert int(re.search(r"#define PVD_ZIGGURAT_LAYERS (\d+)", hdr).group(1)) == _capi.ZIGGURAT_LAYERS
+    assert _capi.RNG_MODES["ziggurat"] == _capi.RNG_DEFAULT
+
+
 def test_no_device_fails_loudly():
     """Without a GPU every compute entry point must raise (no silent CPU fallback)."""
     import numpy as np
@@ -42,6 +51,11 @@ def test_no_device_fails_loudly():
         pytest.skip("a CUDA device is present")
     with pytest.raises(_capi.PvdError):
         kernels.pes_h2o(np.zeros((4, 3, 3)) + np.eye(3))
+    with pytest.raises(_capi.PvdError):
+        kernels.normals(8, 9, seed=1, rng_mode=_capi.RNG_ZIGGURAT)
+    from pyvibdmc_b200.simulation_utilities.tensorflow_descriptors import DistIt
+    with pytest.raises(_capi.PvdError):
+        DistIt([8, 1, 1], "distance").run(np.zeros((4, 3, 3)) + np.eye(3))
 
 
 def test_product_never_imports_oracle():
