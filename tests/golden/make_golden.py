@@ -354,6 +354,15 @@ def gen_descriptor():
     for name, kw in cases.items():
         d = DistIt([8, 1, 1] * 2, force_numpy=True, eq_xyz=eq if kw["method"] == "spf" else None, **kw)
         out[name] = np.asarray(d.run(cds[:256]))
+    # larger molecules (column norms over 10 and 16 rows: NumPy still accumulates them sequentially)
+    r2 = np.random.default_rng(5)
+    eq10 = r2.normal(0, 2.0, size=(10, 3))
+    out["coords10"], out["eq10"], out["zs10"] = eq10[None] + r2.normal(0, 0.3, size=(64, 10, 3)), eq10, np.array([8, 1, 1, 8, 1, 1, 8, 1, 1, 6])
+    d = DistIt(out["zs10"], "spf", eq_xyz=eq10, sorted_atoms=[[0, 3, 6], [1, 2, 4, 5, 7, 8], [9]], sorted_groups=[[0, 1, 2], [3, 4, 5], [6, 7, 8]],
+               full_mat=True, force_numpy=True)
+    out["spf10_atoms_groups_full"] = np.asarray(d.run(out["coords10"]))
+    out["coords16"] = r2.normal(0, 3.0, size=(16, 3))[None] + r2.normal(0, 0.3, size=(32, 16, 3))
+    out["coulomb16_atoms"] = np.asarray(DistIt([1] * 16, "coulomb", sorted_atoms=[list(range(16))], force_numpy=True).run(out["coords16"]))
     save("distit_golden.npz", **out)
 
 

@@ -30,6 +30,29 @@ def test_oracle_distit_matches_reference(oracle, name):
     assert same(out, g[name][:64])
 
 
+LARGE = {"spf10_atoms_groups_full": ("coords10", "zs10", dict(method="spf", sorted_atoms=[[0, 3, 6], [1, 2, 4, 5, 7, 8], [9]],
+                                                                sorted_groups=[[0, 1, 2], [3, 4, 5], [6, 7, 8]], full_mat=True)),
+         "coulomb16_atoms": ("coords16", None, dict(method="coulomb", sorted_atoms=[list(range(16))]))}
+
+
+@pytest.mark.parametrize("name", sorted(LARGE))
+def test_oracle_distit_larger_molecules(oracle, name):
+    g = golden("distit_golden.npz")
+    ck, zk, kw = LARGE[name]
+    zs = g[zk] if zk else [1] * 16
+    assert same(oracle.distit(g[ck], zs, eq_xyz=g["eq10"] if kw["method"] == "spf" else None, **kw), g[name])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(LARGE))
+def test_device_distit_larger_molecules(name):
+    from pyvibdmc_b200.simulation_utilities.tensorflow_descriptors import DistIt
+    g = golden("distit_golden.npz")
+    ck, zk, kw = LARGE[name]
+    zs = g[zk] if zk else [1] * 16
+    assert same(np.asarray(DistIt(zs, eq_xyz=g["eq10"] if kw["method"] == "spf" else None, **kw).run(g[ck])), g[name])
+
+
 def test_distit_argument_errors():
     from pyvibdmc_b200.simulation_utilities.tensorflow_descriptors import DistIt
     with pytest.raises(ValueError, match="eq_xyz is not set but using spf"):
