@@ -26,6 +26,22 @@ __device__ __forceinline__ void desc_colnorm(const double *m, int na, double *nr
         nrm[j] = __dsqrt_rn(acc);
     }
 }
+// np.sum's order on a contiguous axis (pairwise_sum): left to right below 8 summands; from 8 on, eight interleaved partial
+// sums combined as ((0+1)+(2+3))+((4+5)+(6+7)), then the cnt % 8 leftovers
+__device__ __forceinline__ double desc_np_sum(const double *v, int cnt)
+{
+    double acc = 0.0;
+    int k = 0;
+    if (cnt >= 8) {
+        double r[8];
+        for (int q = 0; q < 8; ++q) r[q] = v[q];
+        for (k = 8; k < cnt - cnt % 8; k += 8)
+            for (int q = 0; q < 8; ++q) r[q] = __dadd_rn(r[q], v[k + q]);
+        acc = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])), __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+    }
+    for (; k < cnt; ++k) acc = __dadd_rn(acc, v[k]);
+    return acc;
+}
 // m <- m[inds][:, inds] (distance_descriptors.py:131,151: the matrix is symmetric)
 __device__ __forceinline__ void desc_permute(double *m, double *tmp, int na, const int *inds)
 {
@@ -74,12 +90,21 @@ __global__ void __launch_bounds__(128) k_distit(const double *__restrict__ xyz, 
                 desc_permute(m, tmp, na, inds);
             }
             if (P->ngroups > 0) {
-                // whole groups trade places in order of the descending sum of their members' column norms
-                desc_colnorm(m, na, nrm);
+                // whole groups trade places in order of the descending sum of their members' column norms (:146).  The
+                // reference's fancy-indexed temporary d_mat[:, :, group] lies (member, walker, row) in memory, so this norm
+                // reduces a contiguous axis (np.sum's unrolled order from 8 atoms on, unlike the atom sort's)
+                for (int j = 0; j < na; ++j) {
+                    for (int i = 0; i < na; ++i) tmp[i] = __dmul_rn(m[i * na + j], m[i * na + j]);
+                    nrm[j] = __dsqrt_rn(desc_np_sum(tmp, na));
+                }
                 double tot[PVD_MAX_ATOMS];
                 for (int g = 0; g < P->ngroups; ++g) {
+                    // a strided axis for the reference (left to right) unless there is a single walker
+                    double v[PVD_MAX_ATOMS];
+                    for (int k = 0; k < P->gsize; ++k) v[k] = nrm[P->groups[g * P->gsize + k]];
                     double acc = 0.0;
-                    for (int k = 0; k < P->gsize; ++k) acc = __dadd_rn(acc, nrm[P->groups[g * P->gsize + k]]);
+                    if (n == 1) acc = desc_np_sum(v, P->gsize);
+                    else for (int k = 0; k < P->gsize; ++k) acc = __dadd_rn(acc, v[k]);
                     tot[g] = acc;
                 }
                 for (int a = 0; a < na; ++a) inds[a] = a;

@@ -71,8 +71,6 @@ class DistIt:
             nl = len(self.sorted_atoms)
         if self.sorted_groups is not None:
             groups, (ng, gs) = i32(self.sorted_groups.ravel()), self.sorted_groups.shape
-            if gs >= 8:
-                raise NotImplementedError("groups of 8 or more atoms: NumPy sums their norms pairwise, the kernel sequentially")
         req = None if r_eq is None else f64(r_eq)
         null = lambda a: None if a is None else ptr(a)                                # noqa: E731
         check(lib.pvd_distit(ptr(cds), n, na, _METHODS[method], null(self._pair_scale if method == 'coulomb' else None),

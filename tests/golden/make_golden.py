@@ -363,6 +363,26 @@ def gen_descriptor():
     out["spf10_atoms_groups_full"] = np.asarray(d.run(out["coords10"]))
     out["coords16"] = r2.normal(0, 3.0, size=(16, 3))[None] + r2.normal(0, 0.3, size=(32, 16, 3))
     out["coulomb16_atoms"] = np.asarray(DistIt([1] * 16, "coulomb", sorted_atoms=[list(range(16))], force_numpy=True).run(out["coords16"]))
+    # two groups of eight atoms: np.sum over a contiguous axis of length 8 switches to NumPy's unrolled pairwise order
+    g8 = [list(range(8)), list(range(8, 16))]
+    out["distance16_groups8"] = np.asarray(DistIt([1] * 16, "distance", sorted_groups=g8, force_numpy=True).run(out["coords16"]))
+    out["coulomb16_groups8_full"] = np.asarray(DistIt([8, 1] * 8, "coulomb", sorted_groups=g8, full_mat=True, force_numpy=True).run(out["coords16"]))
+    out["zs16"] = np.array([8, 1] * 8)
+    # mirror-image groups: their totals agree to the last bits, so the swap depends on the ORDER in which NumPy adds the
+    # norms (and the squares inside each norm) -- one third of these walkers change when that order is altered
+    def mirrored(n, h, seed):
+        r = np.random.default_rng(seed)
+        half = r.normal(0, 2.0, size=(n, h, 3))
+        half[:, :, 0] = np.abs(half[:, :, 0]) + 0.5
+        other = half[:, r.permutation(h)].copy()
+        other[:, :, 0] *= -1
+        return np.concatenate([half, other], axis=1)
+    for na, seed in ((16, 11), (10, 4), (6, 6)):
+        c, g2 = mirrored(96, na // 2, seed), [list(range(na // 2)), list(range(na // 2, na))]
+        out[f"mirror{na}"] = c
+        out[f"mirror{na}_groups"] = np.asarray(DistIt([1] * na, "distance", sorted_groups=g2, force_numpy=True).run(c))
+        out[f"mirror{na}_groups_one"] = np.asarray(DistIt([1] * na, "distance", sorted_groups=g2, force_numpy=True).run(c[:1]))
+        out[f"mirror{na}_spf_full"] = np.asarray(DistIt([1] * na, "spf", eq_xyz=c[0], sorted_groups=g2, full_mat=True, force_numpy=True).run(c[1:]))
     save("distit_golden.npz", **out)
 
 

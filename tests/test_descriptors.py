@@ -32,7 +32,11 @@ def test_oracle_distit_matches_reference(oracle, name):
 
 LARGE = {"spf10_atoms_groups_full": ("coords10", "zs10", dict(method="spf", sorted_atoms=[[0, 3, 6], [1, 2, 4, 5, 7, 8], [9]],
                                                                 sorted_groups=[[0, 1, 2], [3, 4, 5], [6, 7, 8]], full_mat=True)),
-         "coulomb16_atoms": ("coords16", None, dict(method="coulomb", sorted_atoms=[list(range(16))]))}
+         "coulomb16_atoms": ("coords16", None, dict(method="coulomb", sorted_atoms=[list(range(16))])),
+         # groups of eight: np.sum switches to its unrolled pairwise order at eight summands
+         "distance16_groups8": ("coords16", None, dict(method="distance", sorted_groups=[list(range(8)), list(range(8, 16))])),
+         "coulomb16_groups8_full": ("coords16", "zs16", dict(method="coulomb", sorted_groups=[list(range(8)), list(range(8, 16))],
+                                                             full_mat=True))}
 
 
 @pytest.mark.parametrize("name", sorted(LARGE))
@@ -41,6 +45,39 @@ def test_oracle_distit_larger_molecules(oracle, name):
     ck, zk, kw = LARGE[name]
     zs = g[zk] if zk else [1] * 16
     assert same(oracle.distit(g[ck], zs, eq_xyz=g["eq10"] if kw["method"] == "spf" else None, **kw), g[name])
+
+
+@pytest.mark.parametrize("gs", [2, 3, 7, 8, 9, 15, 16])
+def test_oracle_group_sum_order_is_numpys(oracle, gs):
+    """The group totals decide the swap, so their last bit matters: np.sum over a contiguous axis adds left to right below
+    eight summands and in its unrolled pairwise order from eight on (distance_descriptors.py:146 sums such an axis)."""
+    rng = np.random.default_rng(gs)
+    a = rng.random((20000, gs)) * rng.choice([1e-3, 1.0, 1e3], size=(20000, gs))
+    assert np.array_equal(np.sum(a, axis=1), np.array([oracle._numpy_sum_order(list(row)) for row in a]))
+
+
+def _mirror_variants(g, na):
+    """(keyword arguments, coordinates, reference output) of the mirror-image cases in the golden file."""
+    c, g2 = g[f"mirror{na}"], [list(range(na // 2)), list(range(na // 2, na))]
+    return [(dict(method="distance", sorted_groups=g2), c, g[f"mirror{na}_groups"]),
+            (dict(method="distance", sorted_groups=g2), c[:1], g[f"mirror{na}_groups_one"]),      # a single walker sums differently
+            (dict(method="spf", eq_xyz=c[0], sorted_groups=g2, full_mat=True), c[1:], g[f"mirror{na}_spf_full"])]
+
+
+@pytest.mark.parametrize("na", [6, 10, 16])
+def test_oracle_distit_mirror_image_groups(oracle, na):
+    """Groups that are mirror images of each other: which one comes first hangs on the last bit of the totals, i.e. on
+    NumPy's summation order inside distance_descriptors.py:146 (contiguous axis for the norms, strided for the totals)."""
+    for kw, c, ref in _mirror_variants(golden("distit_golden.npz"), na):
+        assert same(oracle.distit(c, [1] * na, **kw), ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("na", [6, 10, 16])
+def test_device_distit_mirror_image_groups(na):
+    from pyvibdmc_b200.simulation_utilities.tensorflow_descriptors import DistIt
+    for kw, c, ref in _mirror_variants(golden("distit_golden.npz"), na):
+        assert same(np.asarray(DistIt([1] * na, **kw).run(c)), ref)
 
 
 @pytest.mark.gpu
