@@ -357,7 +357,7 @@ def distit(cds, zs, method, eq_xyz=None, sorted_atoms=None, sorted_groups=None, 
     if method == 'spf' and _r_eq is None:
         if eq_xyz is None:
             raise ValueError("eq_xyz is not set but using spf. Fix!")
-        eq = np.asarray(eq_xyz, dtype=np.float64)[None]
+        eq = np.repeat(np.asarray(eq_xyz, dtype=np.float64)[None], 2, axis=0)     # :75: two copies (matters for :146's order)
         if sort:
             _r_eq = distit(eq, zs, 'distance', None, sorted_atoms, sorted_groups, True)[0]
         else:

@@ -52,7 +52,8 @@ class DistIt:
             raise ValueError("eq_xyz is not set but using spf. Fix!")
         if self.method == 'spf':
             # reference :74-86: r_eq is the equilibrium structure's own distance descriptor, sorted the way the walkers' will be
-            eq = np.asarray(self.eq_xyz, dtype=np.float64)[None]
+            # two copies, as in the reference (:75): with a single walker NumPy would add the group totals in another order
+            eq = np.repeat(np.asarray(self.eq_xyz, dtype=np.float64)[None], 2, axis=0)
             self.r_eq = self._launch(eq, 'distance', full_mat=self.sort_mat, r_eq=None)[0]
 
     def _launch(self, cds, method, full_mat, r_eq):

@@ -383,6 +383,12 @@ def gen_descriptor():
         out[f"mirror{na}_groups"] = np.asarray(DistIt([1] * na, "distance", sorted_groups=g2, force_numpy=True).run(c))
         out[f"mirror{na}_groups_one"] = np.asarray(DistIt([1] * na, "distance", sorted_groups=g2, force_numpy=True).run(c[:1]))
         out[f"mirror{na}_spf_full"] = np.asarray(DistIt([1] * na, "spf", eq_xyz=c[0], sorted_groups=g2, full_mat=True, force_numpy=True).run(c[1:]))
+    # r_eq is made from TWO copies of eq_xyz (:75); this mirror-symmetric equilibrium structure sorts differently when only one
+    # copy is pushed through sort_groups (NumPy adds a single walker's group totals in another order)
+    c = mirrored(41, 8, 123)
+    out["mirror16b"] = c
+    out["mirror16b_spf_full"] = np.asarray(DistIt([1] * 16, "spf", eq_xyz=c[0], sorted_groups=[list(range(8)), list(range(8, 16))],
+                                                  full_mat=True, force_numpy=True).run(c[1:]))
     save("distit_golden.npz", **out)
 
 

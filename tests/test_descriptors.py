@@ -59,7 +59,10 @@ def test_oracle_group_sum_order_is_numpys(oracle, gs):
 def _mirror_variants(g, na):
     """(keyword arguments, coordinates, reference output) of the mirror-image cases in the golden file."""
     c, g2 = g[f"mirror{na}"], [list(range(na // 2)), list(range(na // 2, na))]
-    return [(dict(method="distance", sorted_groups=g2), c, g[f"mirror{na}_groups"]),
+    extra = []
+    if na == 16:       # an equilibrium structure whose own sort differs between one and two copies (the reference uses two, :75)
+        extra = [(dict(method="spf", eq_xyz=g["mirror16b"][0], sorted_groups=g2, full_mat=True), g["mirror16b"][1:], g["mirror16b_spf_full"])]
+    return extra + [(dict(method="distance", sorted_groups=g2), c, g[f"mirror{na}_groups"]),
             (dict(method="distance", sorted_groups=g2), c[:1], g[f"mirror{na}_groups_one"]),      # a single walker sums differently
             (dict(method="spf", eq_xyz=c[0], sorted_groups=g2, full_mat=True), c[1:], g[f"mirror{na}_spf_full"])]
 
@@ -125,3 +128,46 @@ def test_device_distit_larger_molecule_vs_oracle(oracle):
             ref = oracle.distit(cds, zs, eq_xyz=eq if method == "spf" else None, **kw)
             out = np.asarray(DistIt(zs, eq_xyz=eq if method == "spf" else None, **kw).run(cds))
             assert same(out, ref), (method, full)
+
+
+def _random_distit_case(rng):
+    """A random molecule of 3-16 atoms with random sorted sub-lists / groups / method / matrix form; structures are often
+    mirror-symmetric with noise 0, 1e-12, 1e-6 or 0.1, so that the sorts are decided by exact or last-bit ties."""
+    na = int(rng.integers(3, 17))
+    sg = sa = None
+    if rng.random() < 0.7:
+        ng = int(rng.integers(2, min(5, na)))
+        gs = int(rng.integers(1, max(na // ng, 1) + 1))
+        perm = rng.permutation(na)[:ng * gs]
+        sg = [perm[i * gs:(i + 1) * gs].tolist() for i in range(ng)]
+    if rng.random() < 0.6:
+        perm, sa, i = rng.permutation(na).tolist(), [], 0
+        while i < na:
+            ln = int(rng.integers(1, 5))
+            sa.append(sorted(perm[i:i + ln]))
+            i += ln
+    method = ['distance', 'coulomb', 'spf'][int(rng.integers(3))]
+    n = int(rng.choice([1, 2, 5, 40]))
+    base = rng.normal(0, 2.0, size=(na, 3))
+    if rng.random() < 0.6:
+        h = na // 2
+        base[h:2 * h] = base[:h][rng.permutation(h)] * np.array([-1, 1, 1])
+        base[:h, 0] += 0.7
+        base[h:2 * h, 0] -= 0.7
+    cds = base[None] + rng.normal(0, 1, size=(n, na, 3)) * rng.choice([0, 1e-12, 1e-6, 0.1])
+    eq = base + rng.normal(0, 1e-3, size=base.shape) if method == 'spf' else None
+    return rng.choice([1, 6, 8], size=na).tolist(), cds, eq, dict(method=method, sorted_atoms=sa, sorted_groups=sg,
+                                                                  full_mat=bool(rng.random() < 0.5))
+
+
+@pytest.mark.gpu
+def test_device_distit_random_tie_prone_cases_vs_oracle(oracle):
+    """The kernel against the oracle on the inputs of tools/fuzz_oracle_vs_reference.py (which holds the oracle to the
+    reference): same bits, including the single-walker summation order and the lower-index rule on exact ties."""
+    from pyvibdmc_b200.simulation_utilities.tensorflow_descriptors import DistIt
+    rng = np.random.default_rng(2024)
+    for it in range(80):
+        zs, cds, eq, kw = _random_distit_case(rng)
+        ref = oracle.distit(cds, zs, eq_xyz=eq, **kw)
+        out = np.asarray(DistIt(zs, eq_xyz=eq, **kw).run(cds))
+        assert same(out, ref), (it, len(zs), len(cds), kw)
