@@ -151,7 +151,10 @@ int pvd_coulomb_descriptor(const double *xyz, int64_t n, int32_t natoms, const d
  * r_eq: distances of the equilibrium structure, per pair when nothing is sorted, else the natoms x natoms matrix of the
  * equilibrium structure sorted the same way (spf only).  sorted_atoms as a flattened list + offsets (n_atom_lists + 1),
  * sorted_groups as ngroups x gsize.  full_mat = 0: out is (n, npairs), upper triangle; 1: (n, natoms, natoms).
- * Bit-identical to the reference's NumPy arithmetic; ties between equal norms keep index order (unspecified there). */
+ * Bit-identical to the reference's NumPy arithmetic, summation order included: the group sort (:146) adds the squares of a
+ * column in np.sum's unrolled pairwise order from 8 atoms on and the group totals left to right -- pairwise when n == 1,
+ * as NumPy does for a single walker, so pass the batch the reference would see (r_eq comes from TWO copies of eq_xyz, :75).
+ * Ties between exactly equal norms keep index order (the reference's order then depends on the host's SIMD argsort). */
 int pvd_distit(const double *xyz, int64_t n, int32_t natoms, int32_t method, const double *pair_scale, const double *diag,
                const double *r_eq, const int32_t *atom_lists, const int32_t *atom_list_ofs, int32_t n_atom_lists,
                const int32_t *groups, int32_t ngroups, int32_t gsize, int32_t full_mat, double *out);
