@@ -97,6 +97,7 @@ SIGNATURES = {
     "pvd_sim_set_trial_table": (C.c_int, [_P, _P, _I64]),
     "pvd_sim_set_nn_weights": (C.c_int, [_P, _P, _I64]),
     "pvd_sim_run": (C.c_int, [_P, _I64, _I32]),
+    "pvd_sim_set_resident": (C.c_int, [_P, _I32]),
     "pvd_sim_step_injected": (C.c_int, [_P, _P, _P, _P]),
     "pvd_sim_ext_move": (C.c_int, [_P, _P, C.POINTER(_I64)]),
     "pvd_sim_ext_finish": (C.c_int, [_P, _P, _I64, _I32]),

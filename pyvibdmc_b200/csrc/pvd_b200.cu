@@ -4,6 +4,7 @@
 #include "pvd_rng.cuh"
 #include "pvd_potentials.cuh"
 #include "pvd_step.cuh"
+#include "pvd_run.cuh"
 #include "pvd_generic.cuh"
 #include "pvd_continuous.cuh"
 #include "pvd_impsamp.cuh"
@@ -12,6 +13,9 @@
 
 #include <mutex>
 
+#ifndef PVD_RUN_VARIANT_H2O
+#define PVD_RUN_VARIANT_H2O 2563
+#endif
 thread_local std::string g_pvd_err;
 std::atomic<long long> g_pvd_launches{0};
 static thread_local double g_last_kernel_ms = 0.0;
@@ -362,6 +366,12 @@ struct pvd_sim {
     // walker arrays (ping-pong for discrete compaction)
     DevBuf x[2], v[2], who[2], w, f[2], psi[2], lk[2], vs[2];
     DevBuf st, err_accum, status, part, ring, sums, sigma_dev, tickets;
+    DevBuf run_ctl, run_ready;                     // resident multi-step kernel (pvd_run.cuh)
+    unsigned long long run_seq = 0;                // steps finalised by resident launches since the last upload
+    long long ntiles_cap = 0;
+    bool resident = true;                          // pvd_sim_set_resident
+    int resident_mode = 1;                         // 0 off, 1 by ensemble size, 2 always
+    int run_grid = 0, run_minb = 0, run_occ = 0;                // cooperative grid (all CTAs co-resident) and the occupancy variant in use
     DevBuf inj_disp, inj_u, inj_um, stage, stage2;   // staging for host<->device transposes / injections
     DevBuf parent_x, parent_w;
     DevBuf kill_idx, hist, cand, cand_sorted, bin_start, bin_fill, cont_work, copy_dst, copy_src, cont_queue, cont_root, cont_skip;
@@ -448,6 +458,7 @@ static StepArgs make_args(pvd_sim *s, int do_branch)
     return a;
 }
 
+static int run_ctl_reset(pvd_sim *s);
 static int cont_enqueue_step(pvd_sim *, StepArgs &);
 static int cont_enqueue_branch_only(pvd_sim *, StepArgs &, long long *src_out = nullptr);
 static int imp_enqueue_step(pvd_sim *, StepArgs &, const double *);
@@ -552,8 +563,13 @@ int pvd_sim_create(const pvd_config *cfg, pvd_sim **out)
     TRY(cudaMemset(s->st.p, 0, 2 * sizeof(DevState)));
     TRY(s->err_accum.alloc(4));
     TRY(cudaMemset(s->err_accum.p, 0, 4));
-    TRY(s->status.alloc((size_t)ntiles * 8));
-    TRY(cudaMemset(s->status.p, 0, (size_t)ntiles * 8));
+    s->ntiles_cap = ntiles;
+    TRY(s->status.alloc((size_t)2 * ntiles * 8));         // two parities (the resident kernel overlaps consecutive steps)
+    TRY(cudaMemset(s->status.p, 0, (size_t)2 * ntiles * 8));
+    TRY(s->run_ctl.alloc(sizeof(RunCtl)));
+    TRY(s->run_ready.alloc((size_t)2 * ntiles * 4));
+    k_run_ctl_init<<<1, 64>>>(s->run_ctl.as<RunCtl>());
+    TRY(cudaGetLastError());
     // persistent-style grid: enough CTAs to cover the capacity, at most 8 per SM
     s->grid = grid_for(cap, PVD_CTA, 2);
     {
@@ -653,6 +669,7 @@ int pvd_sim_upload(pvd_sim *s, const double *xyz, int64_t n, const double *w)
     s->cur = 0;
     s->parity = 0;
     ++s->mbox_epoch;
+    if (int rc = run_ctl_reset(s)) return rc;
     k_aos_to_soa<<<grid_for(n * nc, 256, 16), 256, 0, s->stream>>>(s->stage.as<double>(), s->x[0].as<double>(), n, nc, s->cap);
     PVD_CHECK_LAUNCH();
     DevState h[2];
@@ -766,6 +783,138 @@ static int enqueue_step(pvd_sim *s, int do_branch, const double *inj_disp, const
     return PVD_OK;
 }
 
+// ---------------------------------------------------------------- resident multi-step launch (pvd_run.cuh)
+typedef void (*run_kernel_t)(const StepArgs, const RunArgs);
+struct RunVariant {
+    run_kernel_t kern = nullptr;
+    int tpb = 0, id = 0;
+    size_t smem = 0;
+};
+
+template <class POT, int TPB, int MINB>
+static RunVariant run_variant_rng(int rng_mode)
+{
+    RunVariant v;
+    v.tpb = TPB;
+    v.id = TPB * 8 + MINB;
+    v.smem = (size_t)(TPB / 32) * sizeof(RunWarpMem<POT::NC>);
+    if (rng_mode == PVD_RNG_FAST) v.kern = k_run_discrete<POT, PVD_RNG_FAST, TPB, MINB>;
+    else if (rng_mode == PVD_RNG_ZIGGURAT) v.kern = k_run_discrete<POT, PVD_RNG_ZIGGURAT, TPB, MINB>;
+    else v.kern = k_run_discrete<POT, PVD_RNG_FP64, TPB, MINB>;
+    return v;
+}
+
+// the kernel variant for this simulation (kern == nullptr when the resident loop does not cover it)
+static RunVariant run_variant_for(const pvd_sim *s)
+{
+    static const bool off = getenv("PVD_NO_RESIDENT") != nullptr;           // A/B switch: one launch per time step
+    if (off || !s->resident || s->cfg.weighting != PVD_WEIGHT_DISCRETE || s->cfg.trial != PVD_TRIAL_NONE) return RunVariant{};
+    // Measured on a B200 (H2O, us per step, one launch per step vs resident): 1 000 walkers 12.4 / 10.8, 20 000 15.8 / 12.4,
+    // 100 000 25.1 / 20.4, 400 000 51.7 / 48.4, 1 000 000 103.5 / 110: the resident kernel removes the fixed cost of a step
+    // but spends more per tile (counters, fences), so above ~600 000 walkers per GPU the step-per-launch kernel is used
+    // unless resident stepping is forced (pvd_sim_set_resident(s, 2) / PVD_RUN_MAX_WALKERS).
+    static const long long max_walkers = [] { const char *e = getenv("PVD_RUN_MAX_WALKERS"); return e ? atoll(e) : 600000ll; }();
+    if (s->resident_mode != 2 && (s->cfg.num_walkers + s->cfg.world_size - 1) / s->cfg.world_size > max_walkers) return RunVariant{};
+    const int rng = s->cfg.rng_mode;
+    switch (s->cfg.potential) {
+    case PVD_POT_H2O_PS: {
+        // occupancy variants of the same kernel (A/B: PVD_RUN_VARIANT = 2562 | 2563 | 3842 | 2564 = threads per CTA, CTAs per SM)
+        static const int want = [] { const char *e = getenv("PVD_RUN_VARIANT"); return e ? atoi(e) : PVD_RUN_VARIANT_H2O; }();
+        if (want == 2562) return run_variant_rng<PotH2O, 256, 2>(rng);
+        if (want == 3842) return run_variant_rng<PotH2O, 384, 2>(rng);
+        if (want == 2564) return run_variant_rng<PotH2O, 256, 4>(rng);
+        return run_variant_rng<PotH2O, 256, 3>(rng);
+    }
+    case PVD_POT_HARMONIC:
+        if (s->nc == 1) return run_variant_rng<PotHarm<1>, 256, 4>(rng);
+        if (s->nc == 3) return run_variant_rng<PotHarm<3>, 256, 4>(rng);
+        return RunVariant{};
+    case PVD_POT_MORSE1D: return run_variant_rng<PotMorse, 256, 4>(rng);
+    default: return RunVariant{};
+    }
+}
+
+// nsteps time steps in one cooperative launch; the caller has checked run_variant_for()
+static int enqueue_run(pvd_sim *s, long long nsteps, int do_branch)
+{
+    if (nsteps <= 0) return PVD_OK;
+    PVD_REQUIRE(nsteps < (1ll << 30), "enqueue_run: at most 2^30 time steps per launch");
+    PVD_REQUIRE(s->cap * s->nc < (1ll << 31), "enqueue_run: 32-bit element offsets need components x capacity < 2^31");
+    const RunVariant rv = run_variant_for(s);
+    PVD_REQUIRE(rv.kern != nullptr, "enqueue_run: configuration not covered by the resident kernel");
+    if (s->run_grid == 0 || s->run_minb != rv.id) {
+        PVD_CUDA(cudaFuncSetAttribute(rv.kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rv.smem));
+        PVD_CUDA(cudaFuncSetAttribute(rv.kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        int occ = 0;
+        PVD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rv.kern, rv.tpb, rv.smem));
+        PVD_REQUIRE(occ >= 1, "resident kernel does not fit an SM");
+        s->run_grid = grid_for(s->cap, rv.tpb, occ);       // never more CTAs than can be co-resident
+        s->run_occ = occ;
+        s->run_minb = rv.id;
+        if (getenv("PVD_RUN_VERBOSE")) fprintf(stderr, "[pvd] resident kernel variant %d: %d CTAs/SM, grid %d x %d threads, %zu B dynamic smem\n", rv.id, occ, s->run_grid, rv.tpb, rv.smem);
+    }
+    StepArgs a = make_args(s, do_branch);
+    RunArgs ra{};
+    ra.ctl = s->run_ctl.as<RunCtl>();
+    ra.ready = s->run_ready.as<unsigned>();
+    ra.ntiles_cap = s->ntiles_cap;
+    ra.nsteps = nsteps;
+    ra.seq0 = s->run_seq;
+    static const int dyn = getenv("PVD_RUN_STATIC") ? 0 : 1;      // A/B switch: tickets (default) or static interleaved tiles
+    ra.dynamic = dyn;
+    static const int single = getenv("PVD_RUN_SINGLE") ? 1 : 0;   // A/B switch: one launch per time step of the same kernel
+    if (single) {
+        // the kernel boundary orders a step's scattered walkers before the next step's loads
+        cudaLaunchAttribute ats[1];
+        ats[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        ats[0].val.programmaticStreamSerializationAllowed = 1;
+        for (long long k = 0; k < nsteps; ++k) {
+            StepArgs ak = make_args(s, do_branch);
+            ra.nsteps = 1;
+            ra.seq0 = s->run_seq;
+            ra.single = 1;
+            cudaLaunchConfig_t lc{};
+            lc.gridDim = dim3((unsigned)s->run_grid);
+            lc.blockDim = dim3((unsigned)rv.tpb);
+            lc.dynamicSmemBytes = rv.smem;
+            lc.stream = s->stream;
+            lc.attrs = ats;
+            lc.numAttrs = 1;
+            PVD_CUDA(cudaLaunchKernelEx(&lc, rv.kern, ak, ra));
+            PVD_CHECK_LAUNCH();
+            s->run_seq += 1;
+            s->cur ^= 1;
+            s->parity ^= 1;
+        }
+        return PVD_OK;
+    }
+    // output-tile counters start from zero in every launch (whatever ran in between: injected steps, rebalancing, uploads)
+    PVD_CUDA(cudaMemsetAsync(s->run_ready.p, 0, (size_t)2 * s->ntiles_cap * 4, s->stream));
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = 1;
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = dim3((unsigned)s->run_grid);
+    lc.blockDim = dim3((unsigned)rv.tpb);
+    lc.dynamicSmemBytes = rv.smem;
+    lc.stream = s->stream;
+    lc.attrs = at;
+    lc.numAttrs = 1;
+    PVD_CUDA(cudaLaunchKernelEx(&lc, rv.kern, a, ra));
+    PVD_CHECK_LAUNCH();
+    s->run_seq += (unsigned long long)nsteps;
+    if (nsteps & 1) { s->cur ^= 1; s->parity ^= 1; }
+    return PVD_OK;
+}
+
+static int run_ctl_reset(pvd_sim *s)
+{
+    k_run_ctl_init<<<1, 64, 0, s->stream>>>(s->run_ctl.as<RunCtl>());
+    PVD_CHECK_LAUNCH();
+    s->run_seq = 0;
+    return PVD_OK;
+}
+
 extern "C" {
 
 int pvd_sim_run(pvd_sim *s, int64_t nsteps, int32_t branch_every)
@@ -776,12 +925,24 @@ int pvd_sim_run(pvd_sim *s, int64_t nsteps, int32_t branch_every)
     PVD_REQUIRE(s->cfg.world_size == 1, "pvd_sim_run is single-shard; use step_local/step_finalize for multi-GPU");
     PVD_REQUIRE(branch_every >= 1, "branch_every must be >= 1");
     PVD_CUDA(cudaEventRecord(s->ev0, s->stream));
-    for (int64_t k = 0; k < nsteps; ++k) {
-        // host-side step index is only needed for branch_every; the device owns the real counter
-        const int do_branch = (branch_every == 1) ? 1 : -branch_every;   // negative: kernel decides from its step counter
-        if (int rc = enqueue_step(s, do_branch, nullptr, nullptr, nullptr)) return rc;
+    const int do_branch = (branch_every == 1) ? 1 : -branch_every;       // negative: the kernel decides from its step counter
+    if (run_variant_for(s).kern) {
+        // discrete weighting with a built-in potential: the whole segment is ONE resident launch
+        if (int rc = enqueue_run(s, nsteps, do_branch)) return rc;
+    } else {
+        for (int64_t k = 0; k < nsteps; ++k)
+            if (int rc = enqueue_step(s, do_branch, nullptr, nullptr, nullptr)) return rc;
     }
     PVD_CUDA(cudaEventRecord(s->ev1, s->stream));
+    return PVD_OK;
+}
+
+int pvd_sim_set_resident(pvd_sim *s, int32_t enable)
+{
+    SIM_CHECK(s);
+    PVD_REQUIRE(enable >= 0 && enable <= 2, "pvd_sim_set_resident: 0 off, 1 automatic (by ensemble size), 2 always");
+    s->resident = enable != 0;
+    s->resident_mode = enable;
     return PVD_OK;
 }
 
@@ -945,6 +1106,15 @@ int pvd_sim_run_mailbox(pvd_sim *s, int64_t nsteps, int32_t branch_every)
     PVD_REQUIRE(branch_every >= 1, "branch_every must be >= 1");
     const int cont = s->cfg.weighting == PVD_WEIGHT_CONTINUOUS ? 1 : 0;
     PVD_CUDA(cudaEventRecord(s->ev0, s->stream));
+    if (run_variant_for(s).kern) {
+        // resident launch: the warp that finalises a step exchanges the sums while the others already move the next step
+        s->mbox_step = true;
+        const int rc = enqueue_run(s, nsteps, branch_every == 1 ? 1 : -branch_every);
+        s->mbox_step = false;
+        if (rc) return rc;
+        PVD_CUDA(cudaEventRecord(s->ev1, s->stream));
+        return PVD_OK;
+    }
     for (int64_t k = 0; k < nsteps; ++k) {
         s->mbox_step = true;
         const int rc = enqueue_step(s, branch_every == 1 ? 1 : -branch_every, nullptr, nullptr, nullptr);

@@ -124,7 +124,7 @@ __device__ __forceinline__ double fx_to_double(Fx128 a)
     const bool neg = a.hi < 0;
     unsigned long long h = (unsigned long long)a.hi, l = a.lo;
     if (neg) { l = ~l + 1ull; h = ~h + (l == 0ull ? 1ull : 0ull); }
-    const double v = ldexp((double)h, -16) + ldexp((double)l, -80);
+    const double v = (double)h * 0x1.0p-16 + (double)l * 0x1.0p-80;      // exact scalings (== ldexp), one rounding in the sum
     return neg ? -v : v;
 }
 __device__ __forceinline__ Fx128 fx_warp_sum(Fx128 a)
@@ -265,7 +265,7 @@ __device__ __forceinline__ void publish_aggregate(unsigned long long *status, lo
     if ((threadIdx.x & 31) == 0)
         st_relaxed_u64(&status[tile], pack_status(step, tile == 0 ? PVD_ST_PREFIX : PVD_ST_AGG, (unsigned)tile_total));
 }
-__device__ __forceinline__ long long resolve_prefix(unsigned long long *status, long long tile, long long step, int tile_total)
+__device__ __forceinline__ long long resolve_prefix(unsigned long long *status, long long tile, long long step, int tile_total, bool *timed_out = nullptr)
 {
     const int lane = threadIdx.x & 31;
     if (tile == 0) return 0;
@@ -277,12 +277,19 @@ __device__ __forceinline__ long long resolve_prefix(unsigned long long *status, 
         const long long idx0 = look - lane, idx1 = look - 32 - lane;
         unsigned long long w0 = pack_status(step, PVD_ST_PREFIX, 0u), w1 = w0;   // virtual tiles before tile 0
         bool ok = true;
+        unsigned spins = 0;
+        long long t0 = 0;
         while (true) {
             if (idx0 >= 0) w0 = ld_relaxed_u64(&status[idx0]);
             if (idx1 >= 0) w1 = ld_relaxed_u64(&status[idx1]);
             ok = status_valid(w0, step) && status_valid(w1, step);
             if (__all_sync(0xffffffffu, ok)) break;
             __nanosleep(20);              // short back-off (64 ns cost 1.5 us per step at 20 000 walkers: most waiting is in the tail)
+            // a predecessor that never publishes (a bug, or a warp that left a dying run) must not hang the device
+            if (++spins >= 4096u) {
+                if (t0 == 0) t0 = clock64();
+                else if (__any_sync(0xffffffffu, clock64() - t0 > 120000000000ll)) { if (timed_out) *timed_out = true; return 0; }
+            }
         }
         const unsigned m0 = __ballot_sync(0xffffffffu, ((w0 >> 32) & 3ull) == PVD_ST_PREFIX);
         const unsigned m1 = __ballot_sync(0xffffffffu, ((w1 >> 32) & 3ull) == PVD_ST_PREFIX);

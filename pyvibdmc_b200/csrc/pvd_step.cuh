@@ -68,14 +68,24 @@ __device__ __forceinline__ unsigned *step_tickets(const StepArgs &a, int parity)
     return a.tickets + parity * (PVD_WARPS * PVD_TICKET_STRIDE);
 }
 
+// DevState as it is in L2 (persistent kernels must not read a copy an earlier step left in L1)
+__device__ __forceinline__ DevState load_state_cg(const DevState *p)
+{
+    DevState s;
+    s.n = __ldcg(&p->n); s.step = __ldcg(&p->step); s.vref = __ldcg(&p->vref); s.pop_global = __ldcg(&p->pop_global);
+    s.dt_eff = __ldcg(&p->dt_eff); s.eff_time = __ldcg(&p->eff_time); s.err = __ldcg(&p->err); s.dw_active = __ldcg(&p->dw_active);
+    s.done = __ldcg(&p->done); s.buf = __ldcg(&p->buf); s.n_accept = __ldcg(&p->n_accept); s.n_kill = __ldcg(&p->n_kill);
+    return s;
+}
+
 // ---------------------------------------------------------------- finalisation
 // Turns the (already globally reduced) sums into Vref / population / log record and publishes the
 // next step's state copy.  Runs in one thread: by the last warp (single GPU) or by k_finalize after
 // the NCCL all-reduce (multi-GPU).
-__device__ inline void finalize_from_sums(const StepArgs &a, bool continuous)
+__device__ inline void finalize_from_sums(const StepArgs &a, bool continuous, int parity)
 {
-    const DevState &si = a.st[a.parity];
-    DevState &so = a.st[a.parity ^ 1];
+    const DevState si = load_state_cg(&a.st[parity]);
+    DevState &so = a.st[parity ^ 1];
     const double *s = a.sums;
     const double tot_c = s[PVD_SUM_C], tot_cv = s[PVD_SUM_CV];
     double vmin = INFINITY, vmax = -INFINITY, wmin = INFINITY, wmax = -INFINITY;
@@ -121,6 +131,8 @@ __device__ inline void finalize_from_sums(const StepArgs &a, bool continuous)
     r.step = si.step;
 }
 
+__device__ inline void finalize_from_sums(const StepArgs &a, bool continuous) { finalize_from_sums(a, continuous, a.parity); }
+__device__ inline void forward_dead_state(const StepArgs &a, int parity);
 __device__ inline void forward_dead_state(const StepArgs &a);
 
 // ---------------------------------------------------------------- per-step collective over NVLink peer memory
@@ -152,15 +164,15 @@ __device__ inline void mailbox_send(const StepArgs &a, long long step)
 }
 
 // One warp: waits for the world's stamps of this step in its own mailbox, adds the slots in rank order and finalises.
-__device__ inline void mailbox_collect_and_finalize(const StepArgs &a, bool continuous)
+__device__ inline void mailbox_collect_and_finalize(const StepArgs &a, bool continuous, int parity, bool *collect_only = nullptr)
 {
-    const DevState &si = a.st[a.parity];
+    const long long cur_step = __ldcg(&a.st[parity].step);
     const int lane = threadIdx.x & 31;
     const double *mine = a.mbox[a.rank];
-    const unsigned long long want = (a.mbox_epoch << 40) | (unsigned long long)(si.step + 1);
+    const unsigned long long want = (a.mbox_epoch << 40) | (unsigned long long)(cur_step + 1);
     bool ok = true;
     if (lane < a.world) {
-        const unsigned long long *stamp = reinterpret_cast<const unsigned long long *>(&mine[mbox_slot(a.parity, lane) + PVD_NSUMS]);
+        const unsigned long long *stamp = reinterpret_cast<const unsigned long long *>(&mine[mbox_slot(parity, lane) + PVD_NSUMS]);
         const long long t0 = clock64();
         unsigned long long got;
         do {
@@ -176,19 +188,21 @@ __device__ inline void mailbox_collect_and_finalize(const StepArgs &a, bool cont
         double v = 0.0;
         for (int r = 0; r < a.world; ++r) {
             double x;
-            asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(x) : "l"(&mine[mbox_slot(a.parity, r) + k]) : "memory");
+            asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(x) : "l"(&mine[mbox_slot(parity, r) + k]) : "memory");
             v += x;
         }
         a.sums[k] = v;
     }
     __syncwarp();
+    if (collect_only) { *collect_only = ok; return; }
     if (lane == 0) {
         if (!ok) {
-            forward_dead_state(a);
-            a.st[a.parity ^ 1].err |= PVD_ERR_COMM;
-        } else finalize_from_sums(a, continuous);
+            forward_dead_state(a, parity);
+            a.st[parity ^ 1].err |= PVD_ERR_COMM;
+        } else finalize_from_sums(a, continuous, parity);
     }
 }
+__device__ inline void mailbox_collect_and_finalize(const StepArgs &a, bool continuous) { mailbox_collect_and_finalize(a, continuous, a.parity); }
 
 __global__ void __launch_bounds__(32) k_finalize_mailbox(const StepArgs a, int continuous)
 {
@@ -208,13 +222,14 @@ __global__ void k_finalize(const StepArgs a, int continuous)
 }
 
 // state forwarding when the run is already dead (error raised in an earlier step)
-__device__ inline void forward_dead_state(const StepArgs &a)
+__device__ inline void forward_dead_state(const StepArgs &a, int parity)
 {
-    const DevState &si = a.st[a.parity];
-    DevState &so = a.st[a.parity ^ 1];
+    const DevState si = load_state_cg(&a.st[parity]);
+    DevState &so = a.st[parity ^ 1];
     so = si;
     so.done = 0u;
 }
+__device__ inline void forward_dead_state(const StepArgs &a) { forward_dead_state(a, a.parity); }
 
 // per-lane running sums of one warp over all the tiles it processed in this step
 struct LaneAcc {

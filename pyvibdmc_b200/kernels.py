@@ -270,6 +270,10 @@ class DeviceSim:
     def run(self, nsteps, branch_every=1):
         check(lib.pvd_sim_run(self._h, int(nsteps), int(branch_every)))
 
+    def set_resident(self, enable=True):
+        """One resident multi-step kernel per run() segment (default) or one launch per time step (same numbers)."""
+        check(lib.pvd_sim_set_resident(self._h, int(enable)))       # False/0 off, True/1 by ensemble size, 2 always
+
     def step_injected(self, disp, u_branch=None, u_metro=None):
         disp = f64(disp)
         ub = None if u_branch is None else f64(u_branch)
