@@ -450,6 +450,9 @@ static StepArgs make_args(pvd_sim *s, int do_branch)
     a.ticket_batch = s->ticket_batch;
     for (int r = 0; r < PVD_MAX_WORLD; ++r) a.mbox[r] = s->mbox_step ? s->peer_mbox[r] : nullptr;
     a.mbox_epoch = s->mbox_epoch;
+    // ranks are only loosely synchronised by the host (checkpoint pickling, file systems): a slow peer is not a dead peer
+    static const long long mbox_ticks = [] { const char *e = getenv("PVD_MBOX_TIMEOUT_S"); const double sec = e ? atof(e) : 120.0; return (long long)((sec > 0 ? sec : 120.0) * 2.0e9); }();
+    a.mbox_timeout_ticks = mbox_ticks;
     static const bool fold_ok = getenv("PVD_NO_MBOX_FOLD") == nullptr;       // A/B switch
     a.mbox_fold = (fold_ok && s->mbox_step && s->cfg.weighting == PVD_WEIGHT_DISCRETE && s->cfg.trial == PVD_TRIAL_NONE) ? 1 : 0;
     for (int i = 0; i < PVD_MAX_ATOMS; ++i) a.sigma[i] = s->sigma[i];
@@ -1237,7 +1240,7 @@ int pvd_sim_state(pvd_sim *s, int64_t *n, double *vref, int64_t *step, int32_t *
     if (err) *err = (int32_t)c.err;
     if (c.err & (PVD_ERR_WEIGHT | PVD_ERR_POP | PVD_ERR_EMPTY)) return pvd_fail(PVD_E_MASSIVE, PVD_MASSIVE_MSG);
     if (c.err & PVD_ERR_CAPACITY) return pvd_fail(PVD_E_MASSIVE, std::string(PVD_MASSIVE_MSG) + " (shard capacity exceeded)");
-    if (c.err & PVD_ERR_COMM) return pvd_fail(PVD_E_STATE, "a peer's per-step message did not arrive within 10 s (mailbox collective)");
+    if (c.err & PVD_ERR_COMM) return pvd_fail(PVD_E_STATE, "a peer's per-step message did not arrive in time (NVLink mailbox exchange; PVD_MBOX_TIMEOUT_S, default 120 s): a rank died or stalled");
     return PVD_OK;
 }
 

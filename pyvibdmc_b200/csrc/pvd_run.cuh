@@ -88,17 +88,19 @@ __device__ __forceinline__ void red_release_add_u32(unsigned *p, unsigned v)
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// Every poll loop of the resident kernel gives up after ~60 s (a peer GPU died, or a bug): the run is marked dead with
-// PVD_ERR_COMM instead of hanging the device.  (The mailbox wait itself gives up after PVD_MBOX_TIMEOUT_TICKS.)
-constexpr long long PVD_RUN_TIMEOUT_TICKS = 120000000000ll;
+// Every poll loop of the resident kernel gives up eventually (a peer GPU died, or a bug): the run is marked dead with
+// PVD_ERR_COMM instead of hanging the device.  The limit is twice the mailbox time-out plus a minute, so that a rank waiting
+// for a slow peer is reported by the exchange itself, not by its bystanders.
 struct SpinGuard {
+    long long limit;
     long long t0 = 0;
     unsigned n = 0;
+    __device__ __forceinline__ explicit SpinGuard(long long lim) : limit(lim) {}
     __device__ __forceinline__ bool expired()
     {
         if (++n < 1024u) return false;
         if (t0 == 0) { t0 = clock64(); return false; }
-        return clock64() - t0 > PVD_RUN_TIMEOUT_TICKS;
+        return clock64() - t0 > limit;
     }
 };
 
@@ -250,6 +252,7 @@ __global__ void __launch_bounds__(TPB, MINB) k_run_discrete(const StepArgs a, co
     if (ra.single) pdl_wait();                                  // everything above overlapped the previous step's tail
 
     const int lane = threadIdx.x & 31;
+    const long long spin_limit = 2 * a.mbox_timeout_ticks + 120000000000ll;
     RunWarpMem<NC> &wm = s_warp[threadIdx.x >> 5];
     RunCtl *ctl = ra.ctl;
     // the state copy this launch starts from is valid by stream order; step number and DW flag are launch constants
@@ -328,7 +331,7 @@ __global__ void __launch_bounds__(TPB, MINB) k_run_discrete(const StepArgs a, co
             if (k == 0) have = (long long)t * PVD_TILE < n;
             else {
                 unsigned *ready_in = ra.ready + (long long)(ps ^ 1) * ra.ntiles_cap;      // written by the previous step
-                SpinGuard guard;
+                SpinGuard guard(spin_limit);
                 while (true) {
                     unsigned r;
                     if (pre) { r = r_pre; pre = false; }          // fetched while the previous tile was being scattered
@@ -378,7 +381,7 @@ __global__ void __launch_bounds__(TPB, MINB) k_run_discrete(const StepArgs a, co
 
             // ---- copy counts need Vref of the previous step
             if (!st_ok) {
-                SpinGuard guard;
+                SpinGuard guard(spin_limit);
                 int got;
                 while ((got = poll_state()) == 0) {
                     if (guard.expired()) PVD_RUN_DIE();
@@ -490,7 +493,7 @@ __global__ void __launch_bounds__(TPB, MINB) k_run_discrete(const StepArgs a, co
             unsigned long long l = 0ull;
             if (lane < 12) l = ld_relaxed_u64(&ctl->acc[ps][lane]);
             else if (lane == 12) {
-                SpinGuard guard;
+                SpinGuard guard(spin_limit);
                 while ((l = ld_relaxed_u64(&ctl->done_seq)) < ra.seq0 + (unsigned long long)k) {
                     if (guard.expired()) break;
                 }
@@ -513,7 +516,7 @@ __global__ void __launch_bounds__(TPB, MINB) k_run_discrete(const StepArgs a, co
                 s[PVD_SUM_NACC] = (double)n;
                 unsigned e = __ldcg(a.err_accum);
                 if (csum_g > a.cap) e |= PVD_ERR_CAPACITY;      // the scatter skipped what did not fit
-                s[PVD_SUM_ERR] = (double)e;
+                s[PVD_SUM_ERR] = err_encode(e);
                 double *ex = s + PVD_SUM_EXT + 4 * a.rank;
                 ex[0] = dkey_inv(L[10]); ex[1] = dkey_inv(L[11]); ex[2] = INFINITY; ex[3] = -INFINITY;
             }
@@ -543,7 +546,7 @@ __global__ void __launch_bounds__(TPB, MINB) k_run_discrete(const StepArgs a, co
                 const double v_bar = tot_cv / tot_c;
                 const double correction = (tot_c - n0) / n0;
                 const double vref_new = v_bar - (a.alpha * correction);
-                unsigned err = (unsigned)s[PVD_SUM_ERR];
+                unsigned err = err_decode(s[PVD_SUM_ERR]);
                 if (tot_c < n0 - n0 * 0.5 || tot_c > n0 + n0 * 0.5) err |= PVD_ERR_POP;
                 if (!(tot_c > 0.0) || csum_g <= 0) err |= PVD_ERR_EMPTY;
                 if (!comm_ok) err |= PVD_ERR_COMM;

@@ -55,6 +55,7 @@ struct StepArgs {
     double sigma[PVD_MAX_ATOMS];
     double sigc[PVD_MAX_COMP];  // sigma expanded per component (sigc[c] = sigma[c / ndim])
     unsigned long long mbox_epoch; // run epoch (bumped by every upload) folded into the mailbox stamps
+    long long mbox_timeout_ticks; // SM clock ticks the exchange waits for a peer's message (PVD_MBOX_TIMEOUT_S, default 120 s)
     int mbox_fold;              // 1: the step kernel's last CTA also waits for the peers and finalises (no k_finalize_mailbox launch)
     double *mbox[PVD_MAX_WORLD]; // NVLink mailbox collective: every rank's mailbox mapped into this process (mbox[0] == nullptr: off)
     PotParamsDev pot;
@@ -62,6 +63,24 @@ struct StepArgs {
 
 constexpr int PVD_SUM_CV = 0, PVD_SUM_C = 1, PVD_SUM_BIRTHS = 2, PVD_SUM_DEATHS = 3, PVD_SUM_V = 4,
               PVD_SUM_NIN = 5, PVD_SUM_ERR = 6, PVD_SUM_NACC = 7, PVD_SUM_EXT = 8;   // + 4*rank: vmin,vmax,wmin,wmax
+
+// Error bits cross the per-step reduction as a SUM of doubles (NCCL all-reduce or the mailbox): bit b travels as 16^b, so
+// that up to PVD_MAX_WORLD ranks raising the same bit cannot carry into another one (2 x CAPACITY must not read as COMM).
+__device__ __forceinline__ double err_encode(unsigned e)
+{
+    double v = 0.0, p = 1.0;
+    for (int b = 0; b < 8; ++b, p *= 16.0)
+        if (e & (1u << b)) v += p;
+    return v;
+}
+__device__ __forceinline__ unsigned err_decode(double v)
+{
+    unsigned e = 0u;
+    unsigned long long u = (unsigned long long)v;
+    for (int b = 0; b < 8; ++b, u >>= 4)
+        if (u & 15ull) e |= 1u << b;
+    return e;
+}
 
 __device__ __forceinline__ unsigned *step_tickets(const StepArgs &a, int parity)
 {
@@ -99,7 +118,7 @@ __device__ inline void finalize_from_sums(const StepArgs &a, bool continuous, in
     const double v_bar = tot_cv / tot_c;
     const double correction = (tot_c - n0) / n0;
     const double vref = v_bar - (a.alpha * correction);
-    unsigned err = si.err | (unsigned)s[PVD_SUM_ERR];
+    unsigned err = si.err | err_decode(s[PVD_SUM_ERR]);
     if (!continuous && (tot_c < n0 - n0 * 0.5 || tot_c > n0 + n0 * 0.5)) err |= PVD_ERR_POP;   // :409-413
     if (!(tot_c > 0.0)) err |= PVD_ERR_EMPTY;
     // a failed step does not count and leaves the pre-step ensemble (input buffer) as the valid one,
@@ -178,7 +197,7 @@ __device__ inline void mailbox_collect_and_finalize(const StepArgs &a, bool cont
         do {
             asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(stamp) : "memory");
             if (got == want) break;
-            if (clock64() - t0 > 20000000000ll) { ok = false; break; }      // ~10 s: a peer died; do not hang the GPU
+            if (clock64() - t0 > a.mbox_timeout_ticks) { ok = false; break; }     // a peer died or fell far behind: do not hang the GPU
         } while (true);
     }
     ok = __all_sync(0xffffffffu, ok);
@@ -306,7 +325,7 @@ __device__ inline void cta_finish_step(const StepArgs &a, const LaneAcc &acc, lo
         s[PVD_SUM_C] = continuous ? fx_to_double(f.cw) : f.c;
         s[PVD_SUM_V] = fx_to_double(f.v);
         s[PVD_SUM_BIRTHS] = f.births; s[PVD_SUM_DEATHS] = f.deaths; s[PVD_SUM_NIN] = f.n_in; s[PVD_SUM_NACC] = f.n_acc;
-        s[PVD_SUM_ERR] = (double)(*a.err_accum);
+        s[PVD_SUM_ERR] = err_encode(*a.err_accum);
         double *e = s + PVD_SUM_EXT + 4 * a.rank;
         e[0] = f.vmin; e[1] = f.vmax; e[2] = f.wmin; e[3] = f.wmax;
         long long n_new = n_local_fixed;

@@ -80,6 +80,7 @@ class ShardedSim:
                 raise NotImplementedError("sharded importance sampling is built for discrete weighting")
             self.sim.set_trial_table(trial_table)
         self.sums = torch.zeros(_capi.NSUMS, dtype=torch.float64, device=self.device)
+        self._gate = torch.zeros(1, dtype=torch.float64, device=self.device)
         self.sim.set_sums_ptr(self.sums.data_ptr())
         # per-step exchange: "mailbox" = peer stores over NVLink fused into the step kernel's last CTA (no collective kernel),
         # "nccl" = all-reduce between the step kernel and the finalisation.  Importance sampling needs two exchanges -> nccl.
@@ -105,6 +106,10 @@ class ShardedSim:
                 k = int(nsteps) - done
                 if self.rebalance_every:
                     k = min(k, self.rebalance_every - self.steps_done % self.rebalance_every)
+                # the mailbox exchange spins on the device for the peers' messages: line the ranks up first (a stream-ordered
+                # all-reduce: the host may have spent seconds on a checkpoint since the last segment)
+                with self.torch.cuda.stream(self.stream):
+                    self.dist.all_reduce(self._gate)
                 self.sim.run_mailbox(k, branch_every)
                 done += k
                 self.steps_done += k
