@@ -241,7 +241,7 @@ int pvd_sim_ext_finish(pvd_sim *s, const double *v, int64_t n, int32_t do_branch
 /* multi-GPU split step: local part, then the caller all-reduces `sums` (device pointer to
  * PVD_NSUMS doubles, obtained from pvd_sim_sums_ptr) over NCCL, then finalisation. */
 #define PVD_MAX_WORLD 8
-#define PVD_NSUMS (8 + 4 * PVD_MAX_WORLD)
+#define PVD_NSUMS (16 + 4 * PVD_MAX_WORLD)
 int pvd_sim_sums_ptr(pvd_sim *s, void **device_ptr);
 /* use a caller-owned device buffer (e.g. a torch tensor NCCL can reduce) of PVD_NSUMS doubles instead */
 int pvd_sim_set_sums_ptr(pvd_sim *s, void *device_ptr);

@@ -23,7 +23,28 @@ RNG_DEFAULT = RNG_ZIGGURAT          # exact normals at the lowest cost (include/
 RNG_MODES = {'ziggurat': RNG_ZIGGURAT, 'fp64': RNG_FP64, 'fast': RNG_FAST}
 ZIGGURAT_LAYERS = 1024
 MAX_ATOMS, MAX_COMP, MAX_WORLD = 16, 48, 8
-NSUMS = 8 + 4 * MAX_WORLD
+NSUMS = 16 + 4 * MAX_WORLD
+# layout of the per-step reduction vector (csrc/pvd_step.cuh): the floating sums travel as three 44-bit chunks of their exact
+# 128-bit fixed-point value (quantum 2^-80) so that a SUM over ranks is exact in any order
+SUM_CV, SUM_C, SUM_V, SUM_BIRTHS, SUM_DEATHS, SUM_NIN, SUM_ERR, SUM_NACC, SUM_EXT = 0, 3, 6, 9, 10, 11, 12, 13, 16
+
+
+def sums_encode(x):
+    """Host restatement of sum_put_double (pvd_step.cuh): a double -> three exactly summable doubles."""
+    from fractions import Fraction
+    i = int(Fraction(float(x)) * (1 << 80))            # truncation towards -inf below 2^-80 (exact for |x| >= 2^-27)
+    i &= (1 << 128) - 1
+    c0, c1, c2 = i & ((1 << 44) - 1), (i >> 44) & ((1 << 44) - 1), i >> 88
+    if c2 >= 1 << 39:
+        c2 -= 1 << 40
+    return [float(c0) * 2.0 ** -80, float(c1) * 2.0 ** -36, float(c2) * 2.0 ** 8]
+
+
+def sums_decode(c):
+    """Host restatement of sum_get: the (reduced) chunks -> the double nearest to the exact total."""
+    from fractions import Fraction
+    tot = Fraction(c[0]) + Fraction(c[1]) + Fraction(c[2])
+    return float(tot)
 
 
 class PvdError(RuntimeError):

@@ -583,8 +583,8 @@ __global__ void __launch_bounds__(PVD_CTA) k_cont_finish(const StepArgs a, const
         if (s_last) {
             __threadfence();
             double *s = a.sums;
-            s[PVD_SUM_CV] -= ca.work->sub_wv;
-            s[PVD_SUM_C] -= ca.work->sub_w;
+            sum_put_double(s, PVD_SUM_CV, sum_get(s, PVD_SUM_CV) - ca.work->sub_wv);
+            sum_put_double(s, PVD_SUM_C, sum_get(s, PVD_SUM_C) - ca.work->sub_w);
             s[PVD_SUM_BIRTHS] = (double)(ca.work->n_kill + ca.work->n_upper);     // "Walkers Branched"
             double *e = s + PVD_SUM_EXT + 4 * a.rank;
             e[2] = __longlong_as_double((long long)atomicAdd(&ca.work->wmin_bits, 0ull));

@@ -345,8 +345,8 @@ __global__ void __launch_bounds__(1024) k_init_sums(const double *__restrict__ v
         double ta = 0, tb = 0;
         for (int k = 0; k < (int)(blockDim.x >> 5); ++k) { ta += s1[k]; tb += s2[k]; }
         for (int k = 0; k < PVD_SUM_EXT + 4 * world; ++k) sums[k] = 0.0;
-        sums[PVD_SUM_CV] = ta;
-        sums[PVD_SUM_C] = tb;
+        sum_put_double(sums, PVD_SUM_CV, ta);
+        sum_put_double(sums, PVD_SUM_C, tb);
         (void)rank;
     }
 }
@@ -354,11 +354,12 @@ __global__ void k_init_finalize(DevState *st, int parity, const double *sums, do
 {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         const double n0 = (double)n0_;
-        const double v_bar = sums[PVD_SUM_CV] / sums[PVD_SUM_C];
-        const double correction = (sums[PVD_SUM_C] - n0) / n0;
+        const double tot_c = sum_get(sums, PVD_SUM_C);
+        const double v_bar = sum_get(sums, PVD_SUM_CV) / tot_c;
+        const double correction = (tot_c - n0) / n0;
         DevState &s = st[parity];
         s.vref = v_bar - (alpha * correction);
-        s.pop_global = sums[PVD_SUM_C];
+        s.pop_global = tot_c;
         s.dt_eff = dt;
     }
 }

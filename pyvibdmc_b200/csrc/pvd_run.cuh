@@ -507,9 +507,9 @@ __global__ void __launch_bounds__(TPB, MINB) k_run_discrete(const StepArgs a, co
                 const Fx128 cv = limb_combine(L[0], L[1], L[2], L[3]), sv = limb_combine(L[4], L[5], L[6], L[7]);
                 const long long deaths_g = (long long)L[9];
                 for (int j = 0; j < PVD_SUM_EXT + 4 * a.world; ++j) s[j] = 0.0;
-                s[PVD_SUM_CV] = fx_to_double(cv);
-                s[PVD_SUM_C] = (double)csum_g;
-                s[PVD_SUM_V] = fx_to_double(sv);
+                sum_put(s, PVD_SUM_CV, cv);
+                sum_put_double(s, PVD_SUM_C, (double)csum_g);
+                sum_put(s, PVD_SUM_V, sv);
                 s[PVD_SUM_DEATHS] = (double)deaths_g;
                 s[PVD_SUM_BIRTHS] = (double)(csum_g - (long long)n + deaths_g);   // sum max(c-1,0) = sum c - #(c >= 1)
                 s[PVD_SUM_NIN] = (double)n;
@@ -542,7 +542,7 @@ __global__ void __launch_bounds__(TPB, MINB) k_run_discrete(const StepArgs a, co
             if (lane == 0) {
                 // the critical part first: Vref and the guards in calc_vref's / birth_or_death's own arithmetic
                 // (pyvibdmc.py:651-661, 409-413; the same expressions as finalize_from_sums), published as one 16-byte word
-                const double tot_c = s[PVD_SUM_C], tot_cv = s[PVD_SUM_CV], n0 = (double)a.n0;
+                const double tot_c = sum_get(s, PVD_SUM_C), tot_cv = sum_get(s, PVD_SUM_CV), n0 = (double)a.n0;
                 const double v_bar = tot_cv / tot_c;
                 const double correction = (tot_c - n0) / n0;
                 const double vref_new = v_bar - (a.alpha * correction);

@@ -61,8 +61,37 @@ struct StepArgs {
     PotParamsDev pot;
 };
 
-constexpr int PVD_SUM_CV = 0, PVD_SUM_C = 1, PVD_SUM_BIRTHS = 2, PVD_SUM_DEATHS = 3, PVD_SUM_V = 4,
-              PVD_SUM_NIN = 5, PVD_SUM_ERR = 6, PVD_SUM_NACC = 7, PVD_SUM_EXT = 8;   // + 4*rank: vmin,vmax,wmin,wmax
+// Layout of the per-step reduction vector (PVD_NSUMS doubles; every rank adds its own, by NCCL or through the mailbox).
+// The three floating sums (sum c*V, sum c or sum w, sum V) travel as THREE doubles each: 44-bit chunks of the exact 128-bit
+// fixed-point value (quantum 2^-80), so that adding the contributions of up to PVD_MAX_WORLD ranks is exact in ANY order --
+// Vref does not depend on how the collective associates (a ring, a tree, the mailbox's rank order: bit-identical), and it is
+// formed from the same fixed-point total on one GPU and on eight.  The rest are integer-valued doubles / per-rank slots.
+constexpr int PVD_SUM_CV = 0, PVD_SUM_C = 3, PVD_SUM_V = 6, PVD_SUM_BIRTHS = 9, PVD_SUM_DEATHS = 10,
+              PVD_SUM_NIN = 11, PVD_SUM_ERR = 12, PVD_SUM_NACC = 13, PVD_SUM_EXT = 16;   // + 4*rank: vmin,vmax,wmin,wmax
+static_assert(PVD_NSUMS == PVD_SUM_EXT + 4 * PVD_MAX_WORLD, "include/pvd_b200.h: PVD_NSUMS");
+
+__device__ __forceinline__ void sum_put(double *s, int slot, Fx128 v)
+{
+    // I = hi * 2^64 + lo (two's complement, units of 2^-80) -> chunks of 44, 44 and the remaining (signed) bits
+    const unsigned long long m44 = (1ull << 44) - 1ull;
+    const unsigned long long c0 = v.lo & m44;
+    const unsigned long long c1 = ((v.lo >> 44) | ((unsigned long long)v.hi << 20)) & m44;
+    const long long c2 = v.hi >> 24;                            // arithmetic shift keeps the sign
+    s[slot] = (double)c0 * 0x1.0p-80;
+    s[slot + 1] = (double)c1 * 0x1.0p-36;
+    s[slot + 2] = (double)c2 * 0x1.0p8;
+}
+__device__ __forceinline__ Fx128 sum_get_fx(const double *s, int slot)
+{
+    // every sum is an exact integer multiple of its quantum (at most 44 + 3 bits)
+    const long long c0 = (long long)(s[slot] * 0x1.0p80), c1 = (long long)(s[slot + 1] * 0x1.0p36), c2 = (long long)(s[slot + 2] * 0x1.0p-8);
+    Fx128 r{0ll, (unsigned long long)c0};
+    r = fx_add(r, Fx128{c1 >> 20, (unsigned long long)c1 << 44});          // c1 * 2^44
+    r = fx_add(r, Fx128{c2 << 24, 0ull});                                   // c2 * 2^88
+    return r;
+}
+__device__ __forceinline__ double sum_get(const double *s, int slot) { return fx_to_double(sum_get_fx(s, slot)); }
+__device__ __forceinline__ void sum_put_double(double *s, int slot, double x) { sum_put(s, slot, fx_from_double(x)); }
 
 // Error bits cross the per-step reduction as a SUM of doubles (NCCL all-reduce or the mailbox): bit b travels as 16^b, so
 // that up to PVD_MAX_WORLD ranks raising the same bit cannot carry into another one (2 x CAPACITY must not read as COMM).
@@ -106,7 +135,7 @@ __device__ inline void finalize_from_sums(const StepArgs &a, bool continuous, in
     const DevState si = load_state_cg(&a.st[parity]);
     DevState &so = a.st[parity ^ 1];
     const double *s = a.sums;
-    const double tot_c = s[PVD_SUM_C], tot_cv = s[PVD_SUM_CV];
+    const double tot_c = sum_get(s, PVD_SUM_C), tot_cv = sum_get(s, PVD_SUM_CV);
     double vmin = INFINITY, vmax = -INFINITY, wmin = INFINITY, wmax = -INFINITY;
     for (int r = 0; r < a.world; ++r) {
         const double *e = s + PVD_SUM_EXT + 4 * r;
@@ -138,7 +167,7 @@ __device__ inline void finalize_from_sums(const StepArgs &a, bool continuous, in
     pvd_step_stats &r = a.ring[si.step % a.ring_len];
     r.vref = vref;
     r.pop = tot_c;
-    r.v_avg = s[PVD_SUM_V] / s[PVD_SUM_NIN];
+    r.v_avg = sum_get(s, PVD_SUM_V) / s[PVD_SUM_NIN];
     r.v_max = vmax;
     r.v_min = vmin;
     r.w_max = wmax;
@@ -321,9 +350,10 @@ __device__ inline void cta_finish_step(const StepArgs &a, const LaneAcc &acc, lo
         for (int w = 0; w < PVD_WARPS; ++w) acc_merge(f, s_part[w]);
         double *s = a.sums;
         for (int k = 0; k < PVD_SUM_EXT + 4 * a.world; ++k) s[k] = 0.0;
-        s[PVD_SUM_CV] = fx_to_double(f.cv);
-        s[PVD_SUM_C] = continuous ? fx_to_double(f.cw) : f.c;
-        s[PVD_SUM_V] = fx_to_double(f.v);
+        sum_put(s, PVD_SUM_CV, f.cv);
+        if (continuous) sum_put(s, PVD_SUM_C, f.cw);
+        else sum_put_double(s, PVD_SUM_C, f.c);
+        sum_put(s, PVD_SUM_V, f.v);
         s[PVD_SUM_BIRTHS] = f.births; s[PVD_SUM_DEATHS] = f.deaths; s[PVD_SUM_NIN] = f.n_in; s[PVD_SUM_NACC] = f.n_acc;
         s[PVD_SUM_ERR] = err_encode(*a.err_accum);
         double *e = s + PVD_SUM_EXT + 4 * a.rank;
