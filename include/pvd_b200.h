@@ -225,11 +225,14 @@ int pvd_sim_set_nn_weights(pvd_sim *s, const float *packed, int64_t nfloats);
 /* enqueue `nsteps` whole time steps (move -> V -> weight/branch -> Vref -> record) without
  * host synchronisation; branch_mask_every = branch_every (pyvibdmc.py:828-837). */
 int pvd_sim_run(pvd_sim *s, int64_t nsteps, int32_t branch_every);
-/* Discrete weighting with a built-in potential runs a whole pvd_sim_run / pvd_sim_run_mailbox segment as ONE resident
- * kernel that overlaps consecutive time steps (csrc/pvd_run.cuh).  enable = 1 (default): for ensembles up to ~600 000
- * walkers per GPU, where it is faster; 2: always; 0: never, i.e. one launch per time step (same numbers bit for bit: the
- * A/B and parity switch).  Replaces the loop `for prop_step in range(...)` of
- * DMC_Sim.propagate (pyvibdmc.py:703) for the steps between two host-side events. */
+/* How a pvd_sim_run / pvd_sim_run_mailbox segment of discrete-weighting steps with a built-in potential is executed.
+ * enable = 1 (default), by ensemble size: up to ~300 000 walkers per GPU ONE resident kernel that overlaps consecutive
+ * time steps (csrc/pvd_run.cuh); above, one launch per step of the deferred-compaction step (csrc/pvd_gather.cuh: the
+ * np.repeat gather of birth_or_death, pyvibdmc.py:415-431, is done by the next step's loads, so no warp waits for
+ * another) plus one materialisation at the end of the segment.  2: the resident kernel always; 3: the deferred-compaction
+ * step always (pvd_sim_step_injected uses it too: parity tests); 0: one self-compacting launch per time step.  All four
+ * give the same numbers bit for bit.  Replaces the loop `for prop_step in range(...)` of DMC_Sim.propagate
+ * (pyvibdmc.py:703) for the steps between two host-side events. */
 int pvd_sim_set_resident(pvd_sim *s, int32_t enable);
 /* one step with injected random numbers (parity tests): disp (n,natoms,ndim) already scaled by
  * sigma, u_branch (n_after_move,) for birth/death, u_metro (n,) for Metropolis (may be NULL). */

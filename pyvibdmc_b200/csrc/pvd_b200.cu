@@ -5,6 +5,7 @@
 #include "pvd_potentials.cuh"
 #include "pvd_step.cuh"
 #include "pvd_run.cuh"
+#include "pvd_gather.cuh"
 #include "pvd_generic.cuh"
 #include "pvd_continuous.cuh"
 #include "pvd_impsamp.cuh"
@@ -372,6 +373,9 @@ struct pvd_sim {
     bool resident = true;                          // pvd_sim_set_resident
     int resident_mode = 1;                         // 0 off, 1 by ensemble size, 2 always
     int run_grid = 0, run_minb = 0, run_occ = 0;                // cooperative grid (all CTAs co-resident) and the occupancy variant in use
+    DevBuf g_cnt[2], g_tincl[2], g_cbase[2], g_meta[2], g_seg;  // deferred-compaction steps (pvd_gather.cuh): per ping-pong buffer
+    int gather_grid = 0, gather_id = 0;
+    size_t gather_smem = 0;
     DevBuf inj_disp, inj_u, inj_um, stage, stage2;   // staging for host<->device transposes / injections
     DevBuf parent_x, parent_w;
     DevBuf kill_idx, hist, cand, cand_sorted, bin_start, bin_fill, cont_work, copy_dst, copy_src, cont_queue, cont_root, cont_skip;
@@ -816,7 +820,9 @@ static RunVariant run_variant_for(const pvd_sim *s)
     // 100 000 25.1 / 20.4, 400 000 51.7 / 48.4, 1 000 000 103.5 / 110: the resident kernel removes the fixed cost of a step
     // but spends more per tile (counters, fences), so above ~600 000 walkers per GPU the step-per-launch kernel is used
     // unless resident stepping is forced (pvd_sim_set_resident(s, 2) / PVD_RUN_MAX_WALKERS).
-    static const long long max_walkers = [] { const char *e = getenv("PVD_RUN_MAX_WALKERS"); return e ? atoll(e) : 600000ll; }();
+    // With the deferred-compaction step (pvd_gather.cuh: 34.1 / 63.8 / 90.2 us at 200 000 / 600 000 / 1 000 000 walkers) the
+    // cross-over moves down to ~300 000 walkers per GPU.
+    static const long long max_walkers = [] { const char *e = getenv("PVD_RUN_MAX_WALKERS"); return e ? atoll(e) : (getenv("PVD_NO_GATHER") ? 600000ll : 300000ll); }();
     if (s->resident_mode != 2 && (s->cfg.num_walkers + s->cfg.world_size - 1) / s->cfg.world_size > max_walkers) return RunVariant{};
     const int rng = s->cfg.rng_mode;
     switch (s->cfg.potential) {
@@ -918,6 +924,109 @@ static int run_ctl_reset(pvd_sim *s)
     return PVD_OK;
 }
 
+// ---------------------------------------------------------------- steps with deferred compaction (pvd_gather.cuh)
+typedef void (*gather_kernel_t)(const StepArgs, const GatherArgs);
+struct GatherVariant {
+    gather_kernel_t kern = nullptr;
+    int minb = 0, id = 0;
+};
+template <class POT, int MINB>
+static GatherVariant gather_variant_rng(int rng_mode, int pot_id)
+{
+    GatherVariant v;
+    v.minb = MINB;
+    v.id = pot_id * 64 + rng_mode * 8 + MINB;
+    if (rng_mode == PVD_RNG_FAST) v.kern = k_step_gather<POT, PVD_RNG_FAST, MINB>;
+    else if (rng_mode == PVD_RNG_ZIGGURAT) v.kern = k_step_gather<POT, PVD_RNG_ZIGGURAT, MINB>;
+    else v.kern = k_step_gather<POT, PVD_RNG_FP64, MINB>;
+    return v;
+}
+
+// the kernel for this simulation (kern == nullptr: not covered, or not selected)
+static GatherVariant gather_variant_for(const pvd_sim *s, bool forced = false)
+{
+    static const bool off = getenv("PVD_NO_GATHER") != nullptr;             // A/B switch: compaction inside the step (k_step_discrete)
+    if (s->cfg.weighting != PVD_WEIGHT_DISCRETE || s->cfg.trial != PVD_TRIAL_NONE) return GatherVariant{};
+    if (!forced && (off || s->resident_mode == 0)) return GatherVariant{};
+    const int rng = s->cfg.rng_mode;
+    switch (s->cfg.potential) {
+    case PVD_POT_H2O_PS: {
+        static const int want = [] { const char *e = getenv("PVD_GATHER_MINB"); return e ? atoi(e) : 2; }();
+        if (want == 3) return gather_variant_rng<PotH2O, 3>(rng, 1);
+        return gather_variant_rng<PotH2O, 2>(rng, 1);
+    }
+    case PVD_POT_HARMONIC:
+        if (s->nc == 1) return gather_variant_rng<PotHarm<1>, 4>(rng, 2);
+        if (s->nc == 3) return gather_variant_rng<PotHarm<3>, 4>(rng, 3);
+        return GatherVariant{};
+    case PVD_POT_MORSE1D: return gather_variant_rng<PotMorse, 4>(rng, 4);
+    default: return GatherVariant{};
+    }
+}
+
+// nsteps time steps, each ONE launch of k_step_gather, then k_gather_materialise: on return (in stream order) the
+// simulation is in exactly the state nsteps launches of k_step_discrete would have left (compacted ensemble in x[cur]).
+static int enqueue_gather_segment(pvd_sim *s, long long nsteps, int do_branch, const GatherVariant &gv,
+                                  const double *inj_disp = nullptr, const double *inj_u = nullptr)
+{
+    if (nsteps <= 0) return PVD_OK;
+    PVD_REQUIRE(s->cap < (1ll << 31), "gather steps: capacity must be below 2^31 walkers per shard");
+    if (s->gather_grid == 0 || s->gather_id != gv.id) {
+        const int grid = grid_for(s->cap, PVD_CTA, gv.minb);
+        PVD_REQUIRE(grid <= PVD_GATHER_MAX_GRID, "gather steps: grid too large");
+        const long long tpc_max = (s->ntiles_cap + grid - 1) / grid;
+        PVD_REQUIRE(tpc_max <= PVD_GATHER_MAX_TPC, "gather steps: shard too large for one chunk per CTA");
+        s->gather_smem = (size_t)((tpc_max < PVD_GATHER_SUBT ? tpc_max : PVD_GATHER_SUBT) * PVD_TILE + tpc_max + grid + 2) * 4;
+        PVD_CUDA(cudaFuncSetAttribute(gv.kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->gather_smem));
+        if (const char *e = getenv("PVD_GATHER_CARVEOUT")) PVD_CUDA(cudaFuncSetAttribute(gv.kern, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
+        PVD_CUDA(cudaFuncSetAttribute(k_gather_materialise, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((PVD_GATHER_MAX_GRID + 2) * 4)));
+        for (int b = 0; b < 2; ++b) {
+            PVD_CUDA(s->g_cnt[b].alloc((size_t)s->cap * 4));
+            PVD_CUDA(s->g_tincl[b].alloc((size_t)s->ntiles_cap * 4));
+            PVD_CUDA(s->g_cbase[b].alloc((size_t)(PVD_GATHER_MAX_GRID + 2) * 4));
+            PVD_CUDA(s->g_meta[b].alloc(sizeof(GatherMeta)));
+        }
+        PVD_CUDA(s->g_seg.alloc(16));
+        s->gather_grid = grid;
+        s->gather_id = gv.id;
+    }
+    const int buf0 = s->cur;
+    MaterialiseArgs m{};
+    for (int b = 0; b < 2; ++b) {
+        m.x[b] = s->x[b].as<double>(); m.v[b] = s->v[b].as<double>(); m.who[b] = s->who[b].as<int>();
+        m.cnt[b] = s->g_cnt[b].as<int>(); m.tincl[b] = s->g_tincl[b].as<int>(); m.cbase[b] = s->g_cbase[b].as<int>();
+        m.meta[b] = s->g_meta[b].as<GatherMeta>();
+    }
+    for (long long k = 0; k < nsteps; ++k) {
+        StepArgs a = make_args(s, do_branch);
+        a.inj_disp = inj_disp;
+        a.inj_u = inj_u;
+        GatherArgs g{};
+        const int in = s->cur, out = s->cur ^ 1;
+        g.cnt_in = s->g_cnt[in].as<int>(); g.cnt_out = s->g_cnt[out].as<int>();
+        g.tincl_in = s->g_tincl[in].as<int>(); g.tincl_out = s->g_tincl[out].as<int>();
+        g.cbase_in = s->g_cbase[in].as<int>(); g.cbase_out = s->g_cbase[out].as<int>();
+        g.meta_in = s->g_meta[in].as<GatherMeta>(); g.meta_out = s->g_meta[out].as<GatherMeta>();
+        g.deferred_in = k > 0 ? 1 : 0;
+        g.seg_step0 = s->g_seg.as<long long>();     // the step counter the segment starts from stays on the device (no host synchronisation)
+        PVD_CUDA(launch_pdl(gv.kern, dim3((unsigned)s->gather_grid), dim3(PVD_CTA), s->gather_smem, s->stream, a, g));
+        PVD_CHECK_LAUNCH();
+        s->cur ^= 1;
+        s->parity ^= 1;
+    }
+    m.st = s->st.as<DevState>();
+    m.cap = s->cap;
+    m.nc = s->nc;
+    m.parity_end = s->parity;
+    m.buf0 = buf0;
+    m.seg_step0 = s->g_seg.as<long long>();
+    const int mg = grid_for(s->cap, PVD_CTA, 8);
+    PVD_CUDA(launch_pdl(k_gather_materialise, dim3((unsigned)mg), dim3(PVD_CTA), (size_t)(s->gather_grid + 2) * 4, s->stream, m));
+    PVD_CHECK_LAUNCH();
+    s->cur ^= 1;
+    return PVD_OK;
+}
+
 extern "C" {
 
 int pvd_sim_run(pvd_sim *s, int64_t nsteps, int32_t branch_every)
@@ -929,9 +1038,13 @@ int pvd_sim_run(pvd_sim *s, int64_t nsteps, int32_t branch_every)
     PVD_REQUIRE(branch_every >= 1, "branch_every must be >= 1");
     PVD_CUDA(cudaEventRecord(s->ev0, s->stream));
     const int do_branch = (branch_every == 1) ? 1 : -branch_every;       // negative: the kernel decides from its step counter
-    if (run_variant_for(s).kern) {
-        // discrete weighting with a built-in potential: the whole segment is ONE resident launch
+    const GatherVariant gv = gather_variant_for(s, s->resident_mode == 3);
+    if (s->resident_mode != 3 && run_variant_for(s).kern) {
+        // discrete weighting with a built-in potential, small ensembles: the whole segment is ONE resident launch
         if (int rc = enqueue_run(s, nsteps, do_branch)) return rc;
+    } else if (gv.kern) {
+        // large ensembles: one launch per step, compaction deferred to the next step's gather
+        if (int rc = enqueue_gather_segment(s, nsteps, do_branch, gv)) return rc;
     } else {
         for (int64_t k = 0; k < nsteps; ++k)
             if (int rc = enqueue_step(s, do_branch, nullptr, nullptr, nullptr)) return rc;
@@ -943,8 +1056,8 @@ int pvd_sim_run(pvd_sim *s, int64_t nsteps, int32_t branch_every)
 int pvd_sim_set_resident(pvd_sim *s, int32_t enable)
 {
     SIM_CHECK(s);
-    PVD_REQUIRE(enable >= 0 && enable <= 2, "pvd_sim_set_resident: 0 off, 1 automatic (by ensemble size), 2 always");
-    s->resident = enable != 0;
+    PVD_REQUIRE(enable >= 0 && enable <= 3, "pvd_sim_set_resident: 0 one self-compacting launch per step, 1 automatic (by ensemble size), 2 resident kernel always, 3 deferred-compaction steps always");
+    s->resident = enable != 0 && enable != 3;
     s->resident_mode = enable;
     return PVD_OK;
 }
@@ -982,8 +1095,12 @@ int pvd_sim_step_injected(pvd_sim *s, const double *disp, const double *u_branch
     PVD_CHECK_LAUNCH();
     if (u_branch) PVD_CUDA(cudaMemcpyAsync(s->inj_u.p, u_branch, (size_t)n * 8, cudaMemcpyHostToDevice, s->stream));
     if (u_metro) PVD_CUDA(cudaMemcpyAsync(s->inj_um.p, u_metro, (size_t)n * 8, cudaMemcpyHostToDevice, s->stream));
-    if (int rc = enqueue_step(s, 1, s->inj_disp.as<double>(), u_branch ? s->inj_u.as<double>() : nullptr,
-                              u_metro ? s->inj_um.as<double>() : nullptr))
+    const GatherVariant gv = s->resident_mode == 3 ? gather_variant_for(s, true) : GatherVariant{};
+    if (gv.kern) {
+        // the deferred-compaction step on injected numbers (a one-step segment): parity tests of the kernel the large runs use
+        if (int rc = enqueue_gather_segment(s, 1, 1, gv, s->inj_disp.as<double>(), u_branch ? s->inj_u.as<double>() : nullptr)) return rc;
+    } else if (int rc = enqueue_step(s, 1, s->inj_disp.as<double>(), u_branch ? s->inj_u.as<double>() : nullptr,
+                                     u_metro ? s->inj_um.as<double>() : nullptr))
         return rc;
     PVD_CUDA(cudaStreamSynchronize(s->stream));
     return PVD_OK;
@@ -1109,6 +1226,16 @@ int pvd_sim_run_mailbox(pvd_sim *s, int64_t nsteps, int32_t branch_every)
     PVD_REQUIRE(branch_every >= 1, "branch_every must be >= 1");
     const int cont = s->cfg.weighting == PVD_WEIGHT_CONTINUOUS ? 1 : 0;
     PVD_CUDA(cudaEventRecord(s->ev0, s->stream));
+    const GatherVariant gv = gather_variant_for(s, s->resident_mode == 3);
+    if (!(s->resident_mode != 3 && run_variant_for(s).kern) && gv.kern) {
+        // large shards: deferred-compaction steps, the last CTA of each exchanges the sums through the mailboxes
+        s->mbox_step = true;
+        const int rc = enqueue_gather_segment(s, nsteps, branch_every == 1 ? 1 : -branch_every, gv);
+        s->mbox_step = false;
+        if (rc) return rc;
+        PVD_CUDA(cudaEventRecord(s->ev1, s->stream));
+        return PVD_OK;
+    }
     if (run_variant_for(s).kern) {
         // resident launch: the warp that finalises a step exchanges the sums while the others already move the next step
         s->mbox_step = true;

@@ -271,8 +271,9 @@ class DeviceSim:
         check(lib.pvd_sim_run(self._h, int(nsteps), int(branch_every)))
 
     def set_resident(self, enable=True):
-        """One resident multi-step kernel per run() segment (default) or one launch per time step (same numbers)."""
-        check(lib.pvd_sim_set_resident(self._h, int(enable)))       # False/0 off, True/1 by ensemble size, 2 always
+        """How run() segments execute (same numbers in every mode): True/1 chosen by ensemble size (default), False/0 one
+        self-compacting launch per time step, 2 the resident multi-step kernel always, 3 deferred-compaction steps always."""
+        check(lib.pvd_sim_set_resident(self._h, int(enable)))
 
     def step_injected(self, disp, u_branch=None, u_metro=None):
         disp = f64(disp)

@@ -12,6 +12,8 @@ n = int(os.environ.get("AB_WALKERS", "1000000"))
 steps = int(os.environ.get("AB_STEPS", "20"))
 mH, mO = Constants.mass("H"), Constants.mass("O")
 sim = K.DeviceSim(3, 3, [mH, mH, mO], n, 5.0, _capi.POT_H2O_PS, seed=7)
+if os.environ.get("AB_MODE"):
+    sim.set_resident(int(os.environ["AB_MODE"]))
 sim.upload(np.broadcast_to(eq * 1.01, (n, 3, 3)).copy())
 sim.run(100)
 sim.sync()

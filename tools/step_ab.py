@@ -19,6 +19,8 @@ def one():
     rng = {"fast": _capi.RNG_FAST, "fp64": _capi.RNG_FP64}.get(os.environ.get("AB_RNG"), _capi.RNG_DEFAULT)
     mH, mO = Constants.mass("H"), Constants.mass("O")
     sim = K.DeviceSim(3, 3, [mH, mH, mO], n, 5.0, _capi.POT_H2O_PS, seed=7, rng_mode=rng)
+    if os.environ.get("AB_MODE"):
+        sim.set_resident(int(os.environ["AB_MODE"]))       # 0 self-compacting step, 2 resident kernel, 3 deferred-compaction steps
     sim.upload(np.broadcast_to(eq * 1.01, (n, 3, 3)).copy())
     sim.run(300)
     sim.sync()
