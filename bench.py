@@ -80,24 +80,56 @@ def other_roofline(label, rate, hbm_peak_gbs, fp64_self):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock, power and clock-event (throttle) reasons sampled DURING the timed region.  NVML in-process (one query
+    costs tens of microseconds, so even a 2 ms timed region gets samples and no nvidia-smi process is forked next to the
+    measurement); falls back to nvidia-smi every 200 ms when the NVML binding is missing."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
+    def __init__(self, index, period_s=0.0005):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+        self.index, self.rows, self.stop_flag, self.period = index, [], threading.Event(), period_s
+        self.nvml = self.handle = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml, self.handle = pynvml, pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.source = "nvml"
+        except Exception:
+            self.nvml, self.source = None, "nvidia-smi"
+
+    @staticmethod
+    def _physical_index(index):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if index < len(ids) and ids[index].isdigit():
+                return int(ids[index])
+        return index
+
+    def _sample_nvml(self):
+        nv, h = self.nvml, self.handle
+        r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+        flag = lambda bit: "Active" if (r & bit) else "Not Active"
+        return [str(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))), str(self.max_mhz),
+                str(nv.nvmlDeviceGetPowerUsage(h) / 1000.0), flag(nv.nvmlClocksEventReasonHwSlowdown),
+                flag(nv.nvmlClocksEventReasonHwThermalSlowdown), flag(nv.nvmlClocksEventReasonSwThermalSlowdown),
+                flag(nv.nvmlClocksEventReasonSwPowerCap)]
 
     def run(self):
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                if self.nvml:
+                    self.rows.append(self._sample_nvml())
+                else:
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                         capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(self.period if self.nvml else 0.2)
 
     def summary(self):
         self.stop_flag.set()
@@ -108,7 +140,7 @@ class ClockSampler(threading.Thread):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for k, n in enumerate(names) if any(r[3 + k].lower().startswith("active") for r in self.rows)]
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "power_w_max": max(float(r[2]) for r in self.rows), "samples": len(self.rows)}
+                "power_w_max": max(float(r[2]) for r in self.rows), "samples": len(self.rows), "source": self.source}
 
 
 def start_ensemble(n):
@@ -576,12 +608,15 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant (only) kernel of the step: k_step_discrete<PotH2O>
+    # ---- roofline of the dominant kernel of the step (one launch per time step; a segment of steps ends with one
+    # k_gather_materialise launch, ~0.5 step's worth of time, which is inside the timed region and billed to the steps)
+    step_kernel = ("k_step_gather<PotH2O>" if n_loc > 300000 and not os.environ.get("PVD_NO_GATHER") else
+                   "k_run_discrete<PotH2O>") if world == 1 or args.collective == "mailbox" else "k_step_discrete<PotH2O>"
     hbm_peak, peak_kind = load_peaks()
     fp64_peak = K.fp64_peak()
     per_gpu_ws_per_s = value / world
     kernel_ms = ms / args.steps                       # one launch per step; events bracket the launches on their stream
-    roofline = {"bound": "fp64", "kernel": "k_step_discrete<PotH2O>", "achieved": per_gpu_ws_per_s * FLOP_PER_WS / 1e12,
+    roofline = {"bound": "fp64", "kernel": step_kernel, "achieved": per_gpu_ws_per_s * FLOP_PER_WS / 1e12,
                 "peak": FP64_NOMINAL / 1e12, "unit": "TFLOP/s", "frac": per_gpu_ws_per_s * FLOP_PER_WS / FP64_NOMINAL,
                 "peak_kind": "nominal FP64 pipe, 148 SM x 64 lanes x 2 x 1.965 GHz (MEASURED_PEAKS.json has no FP64 entry: SURVEY 8d fallback)",
                 "self_measured_peak": fp64_peak / 1e12, "frac_of_self_measured_peak": per_gpu_ws_per_s * FLOP_PER_WS / fp64_peak,
@@ -689,7 +724,7 @@ def main():
                        "parallelism": (f"walkers sharded over {world} GPU(s); per step {_capi.NSUMS} doubles per shard are exchanged "
                                        + ("by peer stores over NVLink from the step kernel's last CTA (mailbox), no collective kernel"
                                           if args.collective == "mailbox" else "by one NCCL all-reduce"))
-                       if world > 1 else "single GPU, one kernel launch per time step",
+                       if world > 1 else "single GPU, one kernel launch per time step (deferred compaction: the next step gathers) + one materialisation per segment",
                        "hardware_warmup": (f"{hw_steps} untimed steps of a scratch ensemble of the same shape before the W warm-up steps "
                                            "(SM clocks and NVLink links out of their idle states)") if hw_steps else "none"},
             "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,

@@ -1008,6 +1008,8 @@ static int enqueue_gather_segment(pvd_sim *s, long long nsteps, int do_branch, c
         g.cbase_in = s->g_cbase[in].as<int>(); g.cbase_out = s->g_cbase[out].as<int>();
         g.meta_in = s->g_meta[in].as<GatherMeta>(); g.meta_out = s->g_meta[out].as<GatherMeta>();
         g.deferred_in = k > 0 ? 1 : 0;
+        static const int stagger = [] { const char *e = getenv("PVD_GATHER_STAGGER_NS"); return e ? atoi(e) : 0; }();
+        g.stagger_ns = stagger;
         g.seg_step0 = s->g_seg.as<long long>();     // the step counter the segment starts from stays on the device (no host synchronisation)
         PVD_CUDA(launch_pdl(gv.kern, dim3((unsigned)s->gather_grid), dim3(PVD_CTA), s->gather_smem, s->stream, a, g));
         PVD_CHECK_LAUNCH();

@@ -13,9 +13,12 @@
 // the compaction needs has two levels: tiles are dealt to CTAs in contiguous chunks (the warps of a CTA share the chunk
 // through a shared-memory ticket), each CTA leaves the inclusive prefix of its tile totals (tincl) when it is done, and
 // the last CTA of the step, which already combines the per-CTA records into Vref, scans the per-CTA totals (cbase).
-// The NEXT step pulls: output tile j (slots 32j..32j+31 of the branched ensemble) finds its chunk in cbase (shared
-// memory), its first source tile in a 32-wide window of tincl, expands the copy counts of the 64 slots from there
-// through shared memory and gathers its walkers -- loads that are contiguous runs, because the map is monotone.
+// The NEXT step pulls: a CTA's output tiles are contiguous and so are their sources (the map is monotone), so the CTA
+// finds the first source tile of its chunk once (chunk in cbase by bisection in shared memory, tile in a 32-wide window
+// of tincl), loads the copy counts from there on, scans them block-wide and writes the source slot of every output
+// slot of the chunk into shared memory (gather_build_map): two round trips to L2 per CTA and step.  A tile then reads
+// its 32 source slots from shared memory and gathers its walkers -- contiguous runs, because the map is monotone.
+// (Doing the pull per tile -- three dependent round trips in front of every tile's loads -- cost 25 us of a 109 us step.)
 // The arithmetic per walker, the random-number addressing (compacted slot, step) and the np.repeat order are those of
 // k_step_discrete: trajectories are bit-identical (tests/test_gpu_gather.py).  A segment of steps ends with
 // k_gather_materialise, which leaves the ensemble compacted in the other buffer exactly as k_step_discrete would have.
@@ -43,70 +46,8 @@ struct GatherArgs {
     GatherMeta *meta_out;
     int deferred_in;        // 0: the input buffer is compacted (first step of a segment)
     long long *seg_step0;   // the first step of a segment leaves [0] the step counter it starts from, [1] the error bits it found
+    int stagger_ns;         // odd warps start their first tile this much later (warps of a scheduler out of phase: see k_step_gather)
 };
-
-// ---------------------------------------------------------------- the pull: where do the walkers of an output tile come from
-// All lanes call it with the same arguments.  Returns the source slot of output slot o0 + lane (-1 beyond the
-// ensemble).  s_src: 32 ints private to the warp.
-__device__ __forceinline__ int gather_sources(const GatherArgs &g, const int *s_cbase, int nchunks, int tpc, int n_slots,
-                                              int o0, int n_out, int *s_src)
-{
-    const int lane = threadIdx.x & 31;
-    // chunk: the last b with cbase[b] <= o0 (empty chunks repeat their successor's base and are skipped by "last")
-    int lo = 0, hi = nchunks - 1;
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (s_cbase[mid] <= o0) lo = mid; else hi = mid - 1;
-    }
-    const int cb = s_cbase[lo];
-    const int rel = o0 - cb;
-    const int ntiles_in = (n_slots + PVD_TILE - 1) / PVD_TILE;
-    const int tb = lo * tpc;
-    const int nt = min(tpc, ntiles_in - tb);
-    // first tile of the chunk whose inclusive prefix exceeds rel: a tile holds about 32 copies, so it is near rel / 32
-    int ws = min(rel >> 5, nt - 1) - 15;
-    ws = max(min(ws, nt - 32), 0);
-    int t0, prev;
-    while (true) {
-        const int idx = ws + lane;
-        const int val = idx < nt ? __ldcg(&g.tincl_in[tb + idx]) : 0x7fffffff;
-        const unsigned m = __ballot_sync(0xffffffffu, val > rel);
-        if (m == 0u) { ws += 32; continue; }                 // (the chunk's last prefix exceeds rel: the window stays inside)
-        const int f = __ffs((int)m) - 1;
-        if (f == 0 && ws > 0) { ws = max(ws - 31, 0); continue; }
-        t0 = ws + f;
-        prev = __shfl_sync(0xffffffffu, val, f > 0 ? f - 1 : 0);
-        if (f == 0) prev = 0;
-        break;
-    }
-    // expand the copy counts from source tile t0 on, 64 slots per round, into the tile's 32 output slots
-    int pos = cb + prev - o0;                                // output slot (relative) of the first copy of the first source: <= 0
-    int k = (tb + t0) * PVD_TILE + lane;
-    const int need = min(PVD_TILE, n_out - o0);
-    s_src[lane] = -1;
-    __syncwarp();
-    while (true) {
-        const int c0 = k < n_slots ? __ldcg(&g.cnt_in[k]) : 0;
-        const int c1 = k + PVD_TILE < n_slots ? __ldcg(&g.cnt_in[k + PVD_TILE]) : 0;
-        const int i0 = warp_incl_scan(c0);
-        const int tot0 = __shfl_sync(0xffffffffu, i0, 31);
-        const int i1 = warp_incl_scan(c1);
-        const int tot1 = __shfl_sync(0xffffffffu, i1, 31);
-        int e = pos + i0 - c0;
-        for (int m = 0; m < c0; ++m, ++e)
-            if ((unsigned)e < (unsigned)PVD_TILE) s_src[e] = k;
-        e = pos + tot0 + i1 - c1;
-        for (int m = 0; m < c1; ++m, ++e)
-            if ((unsigned)e < (unsigned)PVD_TILE) s_src[e] = k + PVD_TILE;
-        pos += tot0 + tot1;
-        k += 2 * PVD_TILE;
-        if (pos >= need || k - lane >= n_slots) break;
-    }
-    __syncwarp();
-    const int src = s_src[lane];
-    __syncwarp();
-    return src;
-}
 
 // ---------------------------------------------------------------- the pull, once per CTA and pass
 // The CTA's output tiles are contiguous, and so are their sources (the map is monotone): instead of three dependent
@@ -189,6 +130,69 @@ __device__ inline void gather_build_map(const GatherArgs &g, const int *s_cbase,
         __syncthreads();                                      // s_tmp[2..] is re-used; after the last round: the map is complete
         if (pos >= n_map || s_cur >= n_slots) break;
     }
+}
+
+// ---------------------------------------------------------------- the pull for ONE output tile (used by the materialisation, a light kernel at full occupancy)
+// All lanes call it with the same arguments.  Returns the source slot of output slot o0 + lane (-1 beyond the
+// ensemble).  s_src: 32 ints private to the warp.
+__device__ __forceinline__ int gather_sources(const GatherArgs &g, const int *s_cbase, int nchunks, int tpc, int n_slots,
+                                              int o0, int n_out, int *s_src)
+{
+    const int lane = threadIdx.x & 31;
+    // chunk: the last b with cbase[b] <= o0 (empty chunks repeat their successor's base and are skipped by "last")
+    int lo = 0, hi = nchunks - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (s_cbase[mid] <= o0) lo = mid; else hi = mid - 1;
+    }
+    const int cb = s_cbase[lo];
+    const int rel = o0 - cb;
+    const int ntiles_in = (n_slots + PVD_TILE - 1) / PVD_TILE;
+    const int tb = lo * tpc;
+    const int nt = min(tpc, ntiles_in - tb);
+    // first tile of the chunk whose inclusive prefix exceeds rel: a tile holds about 32 copies, so it is near rel / 32
+    int ws = min(rel >> 5, nt - 1) - 15;
+    ws = max(min(ws, nt - 32), 0);
+    int t0, prev;
+    while (true) {
+        const int idx = ws + lane;
+        const int val = idx < nt ? __ldcg(&g.tincl_in[tb + idx]) : 0x7fffffff;
+        const unsigned m = __ballot_sync(0xffffffffu, val > rel);
+        if (m == 0u) { ws += 32; continue; }                 // (the chunk's last prefix exceeds rel: the window stays inside)
+        const int f = __ffs((int)m) - 1;
+        if (f == 0 && ws > 0) { ws = max(ws - 31, 0); continue; }
+        t0 = ws + f;
+        prev = __shfl_sync(0xffffffffu, val, f > 0 ? f - 1 : 0);
+        if (f == 0) prev = 0;
+        break;
+    }
+    // expand the copy counts from source tile t0 on, 64 slots per round, into the tile's 32 output slots
+    int pos = cb + prev - o0;                                // output slot (relative) of the first copy of the first source: <= 0
+    int k = (tb + t0) * PVD_TILE + lane;
+    const int need = min(PVD_TILE, n_out - o0);
+    s_src[lane] = -1;
+    __syncwarp();
+    while (true) {
+        const int c0 = k < n_slots ? __ldcg(&g.cnt_in[k]) : 0;
+        const int c1 = k + PVD_TILE < n_slots ? __ldcg(&g.cnt_in[k + PVD_TILE]) : 0;
+        const int i0 = warp_incl_scan(c0);
+        const int tot0 = __shfl_sync(0xffffffffu, i0, 31);
+        const int i1 = warp_incl_scan(c1);
+        const int tot1 = __shfl_sync(0xffffffffu, i1, 31);
+        int e = pos + i0 - c0;
+        for (int m = 0; m < c0; ++m, ++e)
+            if ((unsigned)e < (unsigned)PVD_TILE) s_src[e] = k;
+        e = pos + tot0 + i1 - c1;
+        for (int m = 0; m < c1; ++m, ++e)
+            if ((unsigned)e < (unsigned)PVD_TILE) s_src[e] = k + PVD_TILE;
+        pos += tot0 + tot1;
+        k += 2 * PVD_TILE;
+        if (pos >= need || k - lane >= n_slots) break;
+    }
+    __syncwarp();
+    const int src = s_src[lane];
+    __syncwarp();
+    return src;
 }
 
 // ---------------------------------------------------------------- end of a gather step
@@ -331,6 +335,7 @@ __global__ void __launch_bounds__(PVD_CTA, MINB) k_step_gather(const StepArgs a,
     const int nt = max(min(tpc, ntiles - tb), 0);
     double vmin = INFINITY, vmax = -INFINITY;
     int csum = 0, deaths = 0;                                   // warp-uniform
+    if (g.stagger_ns > 0 && (wid & 1)) __nanosleep((unsigned)g.stagger_ns);
     s_acc_cv[threadIdx.x] = make_ulonglong2(0ull, 0ull);
     s_acc_v[threadIdx.x] = make_ulonglong2(0ull, 0ull);
 
@@ -456,6 +461,7 @@ struct MaterialiseArgs {
     int nc, parity_end, buf0;
 };
 
+// (a version that builds shared-memory maps of 64 tiles per CTA like the step kernel was measured: 68 us instead of 54 us at 1e6 walkers)
 __global__ void __launch_bounds__(PVD_CTA) k_gather_materialise(const MaterialiseArgs m)
 {
     extern __shared__ __align__(16) unsigned char s_dyn[];
