@@ -22,6 +22,11 @@
 // The arithmetic per walker, the random-number addressing (compacted slot, step) and the np.repeat order are those of
 // k_step_discrete: trajectories are bit-identical (tests/test_gpu_gather.py).  A segment of steps ends with
 // k_gather_materialise, which leaves the ensemble compacted in the other buffer exactly as k_step_discrete would have.
+// Tried on this kernel and rejected (B200, 1e6 walkers, us per step against 90.2): cp.async double-buffering of the next
+// tile's coordinates (100.8), three CTAs per SM at 80 registers with 16 bytes of spills (96.7), odd warps started half a
+// tile late (90.8 .. 94.5), and an "early start" protocol in which step k+1 starts on a software flag as soon as step k's
+// prefix is published and only its copy-count stage waits for Vref(k) (96.0: the two GPU-scope fences and the polling
+// cost more than the hardware's dependent-launch hand-over saves; it won 2 us at 200 000 walkers).
 #pragma once
 #include "pvd_step.cuh"
 
