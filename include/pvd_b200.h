@@ -53,8 +53,10 @@ enum {
     PVD_TRIAL_HARM1D = 1,  /* analytic Gaussian + derivatives: PythonPots/harm_trial_wfn.py:6-40 */
     PVD_TRIAL_H2O_FD = 2,  /* water product wfn, finite-difference derivatives:
                               FortPots/.../call_trl_h2o.py:63-78 + imp_samp.py:56-76; table = [grid | psi | alpha, theta_eq] */
-    PVD_TRIAL_H2O_AN = 3   /* same wfn, analytic derivatives: call_trl_h2o.py:101-149 (dpsi_dx) + imp_samp_helper.py:10-209;
+    PVD_TRIAL_H2O_AN = 3,  /* same wfn, analytic derivatives: call_trl_h2o.py:101-149 (dpsi_dx) + imp_samp_helper.py:10-209;
                               table = [grid | psi | psi' | psi'' | alpha, theta_eq] */
+    PVD_TRIAL_EXTERNAL = 4 /* ANY user trial wave function / derivative function: the host answers ImpSampManager.call_trial /
+                              call_derivs (imp_samp_manager.py:92-139, 197-224) once per step, see pvd_sim_imp_ext_* */
 };
 
 enum { PVD_WEIGHT_DISCRETE = 0, PVD_WEIGHT_CONTINUOUS = 1 };
@@ -131,7 +133,8 @@ int pvd_desc_wts(const int64_t *who_from, const double *w, int64_t n, int64_t n_
  * table: trial-specific parameters (H2O: 2 x ntab doubles = grid row then psi row; HARM1D: {alpha}). */
 int pvd_trial_drift(int32_t trial, const double *xyz, int64_t n, int32_t natoms, int32_t ndim,
                     const double *table, int64_t ntab, double *psi, double *dlog, double *d2);
-/* replaces ImpSamp.metropolis (imp_samp.py:29-47) + local_kin (:50-53).
+/* replaces ImpSamp.metropolis (imp_samp.py:29-47) + local_kin (:50-53), for any (natoms x ndim) like the reference
+ * (natoms <= PVD_MAX_ATOMS; 3 x 3 and 1 x 1 run unrolled kernels, every other shape a run-time one, same arithmetic).
  * acc: (n,) acceptance ratios ; sigma, inv_mass: (natoms,) */
 int pvd_metropolis(const double *x, const double *y, const double *fx, const double *fy,
                    const double *psi_x, const double *psi_y, int64_t n, int32_t natoms, int32_t ndim,
@@ -289,6 +292,22 @@ int pvd_sim_stats(pvd_sim *s, int64_t first_step, int64_t count, pvd_step_stats 
 int pvd_sim_last_run_ms(pvd_sim *s, double *ms);
 /* importance-sampling per-walker arrays (f_x, psi, sec) for checkpoints */
 int pvd_sim_download_imp(pvd_sim *s, double *fx, double *psi, double *sec, int64_t capacity);
+
+/* ---- importance sampling with a USER trial wave function (config.trial = PVD_TRIAL_EXTERNAL; any atoms x dims).
+ * Replaces imp_move_randomly (pyvibdmc.py:549-612) around the plug-in call impsamp.drift(cds) (imp_samp.py:21-27), which the
+ * host makes once per step:
+ *   pvd_sim_upload -> pvd_sim_imp_ext_init(f_x, psi, psi''/psi of the start ensemble [, V])       first-step exception (:553-554, 760-769)
+ *   per step: pvd_sim_imp_ext_propose -> displaced coordinates (n, atoms, dims)                   (:556-559, 593)
+ *             host: f_y, psi_2, sec_y = impsamp.drift(displaced)                                  (:595)
+ *             pvd_sim_imp_ext_accept(f_y, psi_2, sec_y)   Metropolis (imp_samp.py:29-47), acceptance, dt_eff (:597-612)
+ *             pvd_sim_imp_ext_finish(V or NULL, n, do_branch)   E_L = V + T_L (:807-809), weighting / branching, Vref
+ * V = NULL evaluates the configured built-in potential on the GPU; with PVD_POT_EXTERNAL the caller downloads the accepted
+ * coordinates (pvd_sim_download) and passes getpot's result.  disp / u_metro / u_branch: injected displacements (n, atoms, dims,
+ * already scaled by sigma), Metropolis and birth/death uniforms -- replays of reference trajectories in the parity tests -- or NULL. */
+int pvd_sim_imp_ext_init(pvd_sim *s, const double *fx, const double *psi, const double *sec, const double *v_or_null);
+int pvd_sim_imp_ext_propose(pvd_sim *s, const double *disp_or_null, double *xyz_out, int64_t *n_out);
+int pvd_sim_imp_ext_accept(pvd_sim *s, const double *fy, const double *psi_y, const double *sec_y, int64_t n, const double *u_metro_or_null);
+int pvd_sim_imp_ext_finish(pvd_sim *s, const double *v_or_null, int64_t n, int32_t do_branch, const double *u_branch_or_null);
 /* walker rebalancing between shards: remove the last `count` walkers into host/peer buffers, or append */
 int pvd_sim_export_tail(pvd_sim *s, int64_t count, double *xyz, double *pots, double *w, int64_t *who);
 int pvd_sim_import(pvd_sim *s, int64_t count, const double *xyz, const double *pots, const double *w, const int64_t *who);

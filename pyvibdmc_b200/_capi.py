@@ -15,7 +15,7 @@ __all__ = ["lib", "PvdError", "MassiveEvent", "check", "PvdConfig", "StepStats",
 MASSIVE_MSG = "Massive walker birth or death event!!!!!!! Dying..."
 PVD_OK, PVD_E_CUDA, PVD_E_ARG, PVD_E_MASSIVE, PVD_E_STATE, PVD_E_NODEVICE = range(6)
 POT_EXTERNAL, POT_HARMONIC, POT_H2O_PS, POT_MORSE1D, POT_NN_H4O2 = range(5)
-TRIAL_NONE, TRIAL_HARM1D, TRIAL_H2O_FD, TRIAL_H2O_AN = range(4)
+TRIAL_NONE, TRIAL_HARM1D, TRIAL_H2O_FD, TRIAL_H2O_AN, TRIAL_EXTERNAL = range(5)
 IMP_STANDARD, IMP_SECOND_DISPLACEMENT, IMP_EXCITED_STATE = range(3)
 WEIGHT_DISCRETE, WEIGHT_CONTINUOUS = 0, 1
 RNG_FP64, RNG_FAST, RNG_ZIGGURAT = 0, 1, 2
@@ -144,6 +144,10 @@ SIGNATURES = {
     "pvd_sim_stats": (C.c_int, [_P, _I64, _I64, _P]),
     "pvd_sim_last_run_ms": (C.c_int, [_P, C.POINTER(_F64)]),
     "pvd_sim_download_imp": (C.c_int, [_P, _P, _P, _P, _I64]),
+    "pvd_sim_imp_ext_init": (C.c_int, [_P, _P, _P, _P, _P]),
+    "pvd_sim_imp_ext_propose": (C.c_int, [_P, _P, _P, C.POINTER(_I64)]),
+    "pvd_sim_imp_ext_accept": (C.c_int, [_P, _P, _P, _P, _I64, _P]),
+    "pvd_sim_imp_ext_finish": (C.c_int, [_P, _P, _I64, _I32, _P]),
     "pvd_sim_export_tail": (C.c_int, [_P, _I64, _P, _P, _P, _P]),
     "pvd_sim_import": (C.c_int, [_P, _I64, _P, _P, _P, _P]),
 }

@@ -406,7 +406,7 @@ int pvd_metropolis(const double *x, const double *y, const double *fx, const dou
     if (int rc = ensure_device_ready()) return rc;
     if (n == 0) return PVD_OK;
     const int nc = natoms * ndim;
-    PVD_REQUIRE((nc == 9 && ndim == 3) || (nc == 1 && ndim == 1), "pvd_metropolis: built for 3x3 (water) and 1x1 problems");
+    PVD_REQUIRE(natoms >= 1 && natoms <= PVD_MAX_ATOMS && ndim >= 1 && nc <= PVD_MAX_COMP, "pvd_metropolis: bad natoms / ndim");
     DevBuf b[6], ds, dm, dacc;
     const double *src[4] = {x, y, fx, fy};
     for (int k = 0; k < 4; ++k) { PVD_CUDA(b[k].alloc((size_t)n * nc * 8)); PVD_CUDA(cudaMemcpy(b[k].p, src[k], (size_t)n * nc * 8, cudaMemcpyHostToDevice)); }
@@ -416,7 +416,10 @@ int pvd_metropolis(const double *x, const double *y, const double *fx, const dou
     PVD_CUDA(dm.alloc(natoms * 8)); PVD_CUDA(cudaMemcpy(dm.p, inv_mass, natoms * 8, cudaMemcpyHostToDevice));
     PVD_CUDA(dacc.alloc((size_t)n * 8));
     const int g = grid_for(n, 128, 16);
-    if (nc == 9)
+    if (!((nc == 9 && ndim == 3) || (nc == 1 && ndim == 1)))       // any other (atoms x dims): the run-time kernel (imp_samp.py:29-47 is shape generic)
+        k_metropolis_rt<<<g, 128>>>(b[0].as<double>(), b[1].as<double>(), b[2].as<double>(), b[3].as<double>(), b[4].as<double>(),
+                                    b[5].as<double>(), n, nc, ndim, ds.as<double>(), dm.as<double>(), dt, dacc.as<double>());
+    else if (nc == 9)
         k_metropolis_aos<9><<<g, 128>>>(b[0].as<double>(), b[1].as<double>(), b[2].as<double>(), b[3].as<double>(), b[4].as<double>(),
                                        b[5].as<double>(), n, ndim, ds.as<double>(), dm.as<double>(), dt, dacc.as<double>());
     else
@@ -433,17 +436,159 @@ int pvd_local_kin(const double *d2, int64_t n, int32_t natoms, int32_t ndim, con
     if (int rc = ensure_device_ready()) return rc;
     if (n == 0) return PVD_OK;
     const int nc = natoms * ndim;
-    PVD_REQUIRE((nc == 9 && ndim == 3) || (nc == 1 && ndim == 1), "pvd_local_kin: built for 3x3 (water) and 1x1 problems");
+    PVD_REQUIRE(natoms >= 1 && natoms <= PVD_MAX_ATOMS && ndim >= 1 && nc <= PVD_MAX_COMP, "pvd_local_kin: bad natoms / ndim");
     DevBuf dd, dm, dk;
     PVD_CUDA(dd.alloc((size_t)n * nc * 8)); PVD_CUDA(cudaMemcpy(dd.p, d2, (size_t)n * nc * 8, cudaMemcpyHostToDevice));
     PVD_CUDA(dm.alloc(natoms * 8)); PVD_CUDA(cudaMemcpy(dm.p, inv_mass, natoms * 8, cudaMemcpyHostToDevice));
     PVD_CUDA(dk.alloc((size_t)n * 8));
-    if (nc == 9) k_local_kin_aos<9><<<grid_for(n, 128, 16), 128>>>(dd.as<double>(), n, ndim, dm.as<double>(), dk.as<double>());
+    if (!((nc == 9 && ndim == 3) || (nc == 1 && ndim == 1)))
+        k_local_kin_rt<<<grid_for(n, 128, 16), 128>>>(dd.as<double>(), n, nc, ndim, dm.as<double>(), dk.as<double>());
+    else if (nc == 9) k_local_kin_aos<9><<<grid_for(n, 128, 16), 128>>>(dd.as<double>(), n, ndim, dm.as<double>(), dk.as<double>());
     else k_local_kin_aos<1><<<grid_for(n, 128, 16), 128>>>(dd.as<double>(), n, ndim, dm.as<double>(), dk.as<double>());
     PVD_CHECK_LAUNCH();
     PVD_CUDA(cudaMemcpy(ke, dk.p, (size_t)n * 8, cudaMemcpyDeviceToHost));
     return PVD_OK;
 }
+
+// ---------------------------------------------------------------- importance sampling with a user trial wave function
+// (PVD_TRIAL_EXTERNAL, csrc/pvd_impext.cuh): the host evaluates psi and its derivatives once per step, the GPU does the rest
+static int impx_buffers(pvd_sim *s)
+{
+    if (s->impx_y.p) return PVD_OK;
+    PVD_CUDA(s->impx_y.alloc((size_t)s->cap * s->nc * 8));
+    PVD_CUDA(s->impx_fy.alloc((size_t)s->cap * s->nc * 8));
+    PVD_CUDA(s->impx_sec.alloc((size_t)s->cap * s->nc * 8));
+    PVD_CUDA(s->impx_psiy.alloc((size_t)s->cap * 8));
+    PVD_CUDA(s->impx_invm.alloc(PVD_MAX_ATOMS * 8));
+    PVD_CUDA(cudaMemcpy(s->impx_invm.p, s->inv_mass, PVD_MAX_ATOMS * 8, cudaMemcpyHostToDevice));
+    return PVD_OK;
+}
+
+extern "C" {
+
+int pvd_sim_imp_ext_init(pvd_sim *s, const double *fx, const double *psi, const double *sec, const double *v)
+{
+    SIM_CHECK(s);
+    SIM_DEVICE(s);
+    PVD_REQUIRE(s->cfg.trial == PVD_TRIAL_EXTERNAL && s->uploaded, "pvd_sim_imp_ext_init: needs trial = PVD_TRIAL_EXTERNAL and uploaded walkers");
+    PVD_REQUIRE(s->cfg.world_size == 1, "importance sampling with a user trial wave function is single-GPU");
+    PVD_REQUIRE(fx && psi && sec && (v || s->cfg.potential != PVD_POT_EXTERNAL), "pvd_sim_imp_ext_init: NULL argument");
+    if (int rc = impx_buffers(s)) return rc;
+    const long long n = s->n_uploaded;
+    const int nc = s->nc;
+    PVD_CUDA(cudaMemcpyAsync(s->impx_fy.p, fx, (size_t)n * nc * 8, cudaMemcpyHostToDevice, s->stream));
+    PVD_CUDA(cudaMemcpyAsync(s->impx_sec.p, sec, (size_t)n * nc * 8, cudaMemcpyHostToDevice, s->stream));
+    PVD_CUDA(cudaMemcpyAsync(s->impx_psiy.p, psi, (size_t)n * 8, cudaMemcpyHostToDevice, s->stream));
+    k_impx_init<<<grid_for(n, 256, 8), 256, 0, s->stream>>>(n, s->cap, nc, s->cfg.ndim, s->impx_invm.as<double>(), s->impx_fy.as<double>(),
+                                                           s->impx_psiy.as<double>(), s->impx_sec.as<double>(), s->f[s->cur].as<double>(),
+                                                           s->psi[s->cur].as<double>(), s->lk[s->cur].as<double>());
+    PVD_CHECK_LAUNCH();
+    // first-step exception: V on the start ensemble, E_L = V + T_L, Vref from it (pyvibdmc.py:760-769)
+    if (v) PVD_CUDA(cudaMemcpyAsync(s->v[s->cur].p, v, (size_t)n * 8, cudaMemcpyHostToDevice, s->stream));
+    else if (int rc = launch_pot_soa(s)) return rc;
+    k_impx_add_lk<<<grid_for(n, 256, 8), 256, 0, s->stream>>>(s->st.as<DevState>(), s->parity, s->v[s->cur].as<double>(), s->lk[s->cur].as<double>());
+    PVD_CHECK_LAUNCH();
+    PVD_CUDA(cudaStreamSynchronize(s->stream));
+    if (int rc = sim_init_sums(s)) return rc;
+    return pvd_sim_init_finalize(s);
+}
+
+int pvd_sim_imp_ext_propose(pvd_sim *s, const double *disp, double *xyz_out, int64_t *n_out)
+{
+    SIM_CHECK(s);
+    SIM_DEVICE(s);
+    PVD_REQUIRE(s->cfg.trial == PVD_TRIAL_EXTERNAL && s->uploaded && s->impx_y.p && xyz_out && n_out, "pvd_sim_imp_ext_propose: call pvd_sim_imp_ext_init first");
+    StepArgs a = make_args(s, 1);
+    if (disp) {
+        // injected displacements (n, atoms, dims), already scaled by sigma: parity replays of reference trajectories
+        PVD_CUDA(cudaStreamSynchronize(s->stream));
+        DevState h0[2];
+        PVD_CUDA(cudaMemcpy(h0, s->st.p, sizeof(h0), cudaMemcpyDeviceToHost));
+        const long long n0 = h0[s->parity].n;
+        if (!s->inj_disp.p) {
+            PVD_CUDA(s->inj_disp.alloc((size_t)s->cap * s->nc * 8));
+            PVD_CUDA(s->inj_u.alloc((size_t)s->cap * 8));
+            PVD_CUDA(s->inj_um.alloc((size_t)s->cap * 8));
+        }
+        PVD_CUDA(s->stage.alloc((size_t)n0 * s->nc * 8));
+        PVD_CUDA(cudaMemcpyAsync(s->stage.p, disp, (size_t)n0 * s->nc * 8, cudaMemcpyHostToDevice, s->stream));
+        k_aos_to_soa<<<grid_for(n0 * s->nc, 256, 16), 256, 0, s->stream>>>(s->stage.as<double>(), s->inj_disp.as<double>(), n0, s->nc, s->cap);
+        PVD_CHECK_LAUNCH();
+        a.inj_disp = s->inj_disp.as<double>();
+    }
+    const int g = grid_for(s->cap, 256, 8);
+    if (s->cfg.rng_mode == PVD_RNG_FAST)
+        k_impx_propose<PVD_RNG_FAST><<<g, 256, 0, s->stream>>>(a, s->impx_invm.as<double>(), s->x[s->cur].as<double>(), s->f[s->cur].as<double>(), s->impx_y.as<double>());
+    else
+        k_impx_propose<PVD_RNG_FP64><<<g, 256, 0, s->stream>>>(a, s->impx_invm.as<double>(), s->x[s->cur].as<double>(), s->f[s->cur].as<double>(), s->impx_y.as<double>());
+    PVD_CHECK_LAUNCH();
+    DevState h[2];
+    PVD_CUDA(cudaMemcpyAsync(h, s->st.p, sizeof(h), cudaMemcpyDeviceToHost, s->stream));
+    PVD_CUDA(cudaStreamSynchronize(s->stream));
+    const long long n = h[s->parity].n;
+    const int nc = s->nc;
+    PVD_CUDA(s->stage.alloc((size_t)n * nc * 8));
+    k_soa_to_aos<<<grid_for(n * nc, 256, 16), 256, 0, s->stream>>>(s->impx_y.as<double>(), s->stage.as<double>(), n, nc, s->cap);
+    PVD_CHECK_LAUNCH();
+    PVD_CUDA(cudaMemcpyAsync(xyz_out, s->stage.p, (size_t)n * nc * 8, cudaMemcpyDeviceToHost, s->stream));
+    PVD_CUDA(cudaStreamSynchronize(s->stream));
+    *n_out = n;
+    s->ext_moved = true;
+    return PVD_OK;
+}
+
+int pvd_sim_imp_ext_accept(pvd_sim *s, const double *fy, const double *psiy, const double *secy, int64_t n, const double *u_metro)
+{
+    SIM_CHECK(s);
+    SIM_DEVICE(s);
+    PVD_REQUIRE(s->cfg.trial == PVD_TRIAL_EXTERNAL && s->ext_moved && fy && psiy && secy, "pvd_sim_imp_ext_accept: call pvd_sim_imp_ext_propose first");
+    const int nc = s->nc;
+    PVD_CUDA(cudaMemcpyAsync(s->impx_fy.p, fy, (size_t)n * nc * 8, cudaMemcpyHostToDevice, s->stream));
+    PVD_CUDA(cudaMemcpyAsync(s->impx_sec.p, secy, (size_t)n * nc * 8, cudaMemcpyHostToDevice, s->stream));
+    PVD_CUDA(cudaMemcpyAsync(s->impx_psiy.p, psiy, (size_t)n * 8, cudaMemcpyHostToDevice, s->stream));
+    const double *um = nullptr;
+    if (u_metro) {
+        if (!s->inj_um.p) PVD_CUDA(s->inj_um.alloc((size_t)s->cap * 8));
+        PVD_CUDA(cudaMemcpyAsync(s->inj_um.p, u_metro, (size_t)n * 8, cudaMemcpyHostToDevice, s->stream));
+        um = s->inj_um.as<double>();
+    }
+    StepArgs a = make_args(s, 1);
+    k_impx_accept<<<grid_for(s->cap, 256, 8), 256, 0, s->stream>>>(a, s->impx_invm.as<double>(), s->x[s->cur].as<double>(), s->f[s->cur].as<double>(),
+                                                                  s->psi[s->cur].as<double>(), s->lk[s->cur].as<double>(), s->impx_y.as<double>(),
+                                                                  s->impx_fy.as<double>(), s->impx_psiy.as<double>(), s->impx_sec.as<double>(), um,
+                                                                  s->acc_count.as<unsigned long long>());
+    PVD_CHECK_LAUNCH();
+    PVD_CUDA(cudaStreamSynchronize(s->stream));
+    return PVD_OK;
+}
+
+int pvd_sim_imp_ext_finish(pvd_sim *s, const double *v, int64_t n, int32_t do_branch, const double *u_branch)
+{
+    SIM_CHECK(s);
+    SIM_DEVICE(s);
+    PVD_REQUIRE(s->cfg.trial == PVD_TRIAL_EXTERNAL && s->ext_moved, "pvd_sim_imp_ext_finish: call pvd_sim_imp_ext_propose / _accept first");
+    PVD_REQUIRE(v || s->cfg.potential != PVD_POT_EXTERNAL, "pvd_sim_imp_ext_finish: an external potential needs its energies");
+    if (v) PVD_CUDA(cudaMemcpyAsync(s->v[s->cur].p, v, (size_t)n * 8, cudaMemcpyHostToDevice, s->stream));
+    else if (int rc = launch_pot_soa(s)) return rc;
+    k_impx_add_lk<<<grid_for(s->cap, 256, 8), 256, 0, s->stream>>>(s->st.as<DevState>(), s->parity, s->v[s->cur].as<double>(), s->lk[s->cur].as<double>());
+    PVD_CHECK_LAUNCH();
+    StepArgs a = make_args(s, do_branch);
+    if (u_branch) {
+        PVD_CUDA(cudaStreamSynchronize(s->stream));
+        DevState h0[2];
+        PVD_CUDA(cudaMemcpy(h0, s->st.p, sizeof(h0), cudaMemcpyDeviceToHost));
+        if (!s->inj_u.p) PVD_CUDA(s->inj_u.alloc((size_t)s->cap * 8));
+        PVD_CUDA(cudaMemcpyAsync(s->inj_u.p, u_branch, (size_t)h0[s->parity].n * 8, cudaMemcpyHostToDevice, s->stream));
+        a.inj_u = s->inj_u.as<double>();
+    }
+    if (int rc = imp_enqueue_branch(s, a)) return rc;
+    s->parity ^= 1;
+    s->ext_moved = false;
+    PVD_CUDA(cudaStreamSynchronize(s->stream));
+    return PVD_OK;
+}
+
+}  // extern "C"
 
 // ---------------------------------------------------------------- walker rebalancing between shards
 int pvd_sim_export_tail(pvd_sim *s, int64_t count, double *xyz, double *pots, double *w, int64_t *who)

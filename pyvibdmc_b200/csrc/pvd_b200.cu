@@ -9,6 +9,7 @@
 #include "pvd_generic.cuh"
 #include "pvd_continuous.cuh"
 #include "pvd_impsamp.cuh"
+#include "pvd_impext.cuh"
 #include "pvd_nn.cuh"
 #include "pvd_descriptor.cuh"
 
@@ -380,6 +381,7 @@ struct pvd_sim {
     DevBuf parent_x, parent_w;
     DevBuf kill_idx, hist, cand, cand_sorted, bin_start, bin_fill, cont_work, copy_dst, copy_src, cont_queue, cont_root, cont_skip;
     DevBuf trial_table, acc_count;
+    DevBuf impx_y, impx_fy, impx_sec, impx_psiy, impx_invm;      // importance sampling with a user trial wave function (pvd_impext.cuh)
     NNDeviceWeights nn_w;
     TrialParamsDev trial_params{};
     int nn_grid = 1;
@@ -697,6 +699,7 @@ int pvd_sim_upload(pvd_sim *s, const double *xyz, int64_t n, const double *w)
     s->n_uploaded = n;
     s->uploaded = true;
     s->ext_moved = false;
+    if (s->cfg.trial == PVD_TRIAL_EXTERNAL) return PVD_OK;       // caller continues with pvd_sim_imp_ext_init (drift terms from the host)
     if (s->cfg.potential == PVD_POT_EXTERNAL) return PVD_OK;     // caller continues with pvd_sim_set_pots
     if (s->cfg.trial != PVD_TRIAL_NONE) {
         // first-step exception with importance sampling: E_L = V + local kinetic (pyvibdmc.py:763-767)

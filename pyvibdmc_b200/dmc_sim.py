@@ -270,13 +270,18 @@ class DMC_Sim:
         if getattr(self, '_hooked', False):
             pot = None                 # per-step mode: the plug-in's getpot is called like any user potential
         trial = None
+        self._hosted_imp = False
         if self.impsamp_manager is not None:
             trial = getattr(self.impsamp_manager, 'gpu_spec', lambda: None)()
             if trial is None or pot is None:
-                raise NotImplementedError(
-                    "importance sampling on the B200 path needs a built-in trial wave function and a built-in potential "
-                    "(shipped samples: harm_trial_wfn.trial_harm + derivative, call_trl_h2o.trial_wavefunction with "
-                    "finite differences)")
+                # ANY trial wave function / derivative function (the reference's plug-in contract, imp_samp_manager.py:92-139,
+                # 197-224) or a user potential next to a shipped trial function: the host answers impsamp.drift once per
+                # step, the GPU proposes, runs the Metropolis step, weights and branches (csrc/pvd_impext.cuh)
+                if self.second_impsamp_displacement or self.excited_state_imp_samp:
+                    raise NotImplementedError("second_impsamp_displacement / excited_state_imp_samp with a user trial wave function "
+                                              "or a user potential: only the shipped sample functions run these variants on the B200 path")
+                trial = {"trial": _capi.TRIAL_EXTERNAL, "table": None}
+                self._hosted_imp = True
         return pot, trial
 
     def _ensure_device(self):
@@ -293,8 +298,9 @@ class DMC_Sim:
                 pot_params = [pot["de"], pot["alpha"]]
         cap = int(1.5 * max(self.num_walkers, len(self._walker_coords))) + 1024
         if self._world > 1:
-            if pot is None:
-                raise NotImplementedError("a sharded DMC_Sim needs a built-in potential (walkers never leave the GPUs)")
+            if pot is None or self._hosted_imp:
+                raise NotImplementedError("a sharded DMC_Sim needs a built-in potential and a built-in trial wave function "
+                                          "(walkers never leave the GPUs)")
             from .distributed import ShardedDevice
             self._dev = ShardedDevice(n_atoms, n_dim, self.masses, self.num_walkers, self.delta_t, pot_id, weighting=self.weighting,
                                       alpha=self._alpha, seed=self._seed + 7919 * int(self.cur_timestep), rng_mode=self._rng_mode,
@@ -320,13 +326,19 @@ class DMC_Sim:
                                       stats_ring=max(4096, min(1 << 20, int(self.num_timesteps) + 8)),
                                       imp_variant=(_capi.IMP_SECOND_DISPLACEMENT if self.second_impsamp_displacement else
                                                    _capi.IMP_EXCITED_STATE if self.excited_state_imp_samp else _capi.IMP_STANDARD))
-        self._builtin = pot is not None
+        self._builtin = pot is not None and not self._hosted_imp      # whole segments of steps without the host
+        self._pot_on_device = pot is not None
         if pot is not None and pot_id == _capi.POT_NN_H4O2:
             self._dev.set_nn_weights(pot["weights"])
-        if trial:
+        if trial and trial.get("table") is not None:
             self._dev.set_trial_table(trial["table"], trial.get("ntab"))
         self._dev.upload(self._walker_coords, self._cont_wts)
-        if not self._builtin:
+        if self._hosted_imp:
+            # first-step exception (pyvibdmc.py:760-769): drift terms and V on the start ensemble, Vref from E_L
+            f_x, psi_1, sec = self.impsamp.drift(self._walker_coords)
+            v0 = None if self._pot_on_device else np.asarray(self.potential(self._walker_coords), dtype=np.float64)
+            self._dev.imp_ext_init(f_x, psi_1, sec, v0)
+        elif not self._builtin:
             self._dev.set_pots(np.asarray(self.potential(self._walker_coords), dtype=np.float64))
         self._dev_step0 = int(self.cur_timestep)      # propagation step that device step 0 corresponds to
         self._host_stale = False
@@ -343,7 +355,10 @@ class DMC_Sim:
         if self._desc_wt:
             self._who_from = out["who_from"]
         if self.impsamp_manager is not None:
-            self.f_x, self.psi_1, self.psi_sec_der = self._dev.download_imp()
+            if getattr(self, '_hosted_imp', False):     # a pure function of the coordinates: ask the plug-in
+                self.f_x, self.psi_1, self.psi_sec_der = self.impsamp.drift(self._walker_coords)
+            else:
+                self.f_x, self.psi_1, self.psi_sec_der = self._dev.download_imp()
         self._vref = self._dev.state(raise_on_error=False)["vref"]
         self._host_stale = False
 
@@ -494,6 +509,24 @@ class DMC_Sim:
         pot_seconds = {}
         train_before = set(int(s) for s in self.deb_train_save_step) if self._deb_save_before_bod else set()
         for step in range(t0, t1):
+            if getattr(self, '_hosted_imp', False):
+                # imp_move_randomly (pyvibdmc.py:549-612) around the plug-in call impsamp.drift(displaced_cds)
+                y = dev.imp_ext_propose()
+                f_y, psi_2, sec_y = self.impsamp.drift(y)
+                dev.imp_ext_accept(f_y, psi_2, sec_y)
+                do_branch = (step % self.branch_every) == 0
+                if self._pot_on_device:
+                    dev.imp_ext_finish(None, do_branch)
+                else:
+                    cds = dev.download()["coords"]
+                    if step in self._log_set:
+                        v, pot_seconds[step] = self.potential(cds, timeit=True)
+                    else:
+                        v = self.potential(cds)
+                    dev.imp_ext_finish(np.array(v, dtype=np.float64), do_branch)
+                if dev.state(raise_on_error=False)["err"]:
+                    break
+                continue
             if self.fixed_node is not None:                                        # pyvibdmc.py:755-757
                 q_beginning = self.fixed_node_func(dev.download()["coords"], step)
             cds = dev.ext_move()

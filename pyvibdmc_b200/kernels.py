@@ -291,6 +291,34 @@ class DeviceSim:
         v = f64(v)
         check(lib.pvd_sim_ext_finish(self._h, ptr(v), len(v), 1 if do_branch else 0))
 
+    # ---- importance sampling with a user trial wave function (trial=_capi.TRIAL_EXTERNAL): the host supplies psi and derivatives
+    def imp_ext_init(self, fx, psi, sec, v=None):
+        """Drift terms (and, for an external potential, V) of the start ensemble: first-step exception (pyvibdmc.py:760-769)."""
+        fx, psi, sec = f64(fx), f64(psi), f64(sec)
+        vv = None if v is None else f64(v)
+        check(lib.pvd_sim_imp_ext_init(self._h, ptr(fx), ptr(psi), ptr(sec), ptr(vv)))
+
+    def imp_ext_propose(self, disp=None):
+        """coords + disps + (1/m) f_x dt for every walker (pyvibdmc.py:593), on the host, for impsamp.drift.
+        disp: injected displacements (parity replays) instead of the Philox normals."""
+        out = np.empty((self.capacity, self.natoms, self.ndim))
+        n = C.c_int64(0)
+        dd = None if disp is None else f64(disp)
+        check(lib.pvd_sim_imp_ext_propose(self._h, ptr(dd), ptr(out), C.byref(n)))
+        return out[:n.value]
+
+    def imp_ext_accept(self, fy, psi_y, sec_y, u_metro=None):
+        """Metropolis step with the drift terms of the displaced walkers (pyvibdmc.py:597-612)."""
+        fy, psi_y, sec_y = f64(fy), f64(psi_y), f64(sec_y)
+        um = None if u_metro is None else f64(u_metro)
+        check(lib.pvd_sim_imp_ext_accept(self._h, ptr(fy), ptr(psi_y), ptr(sec_y), len(psi_y), ptr(um)))
+
+    def imp_ext_finish(self, v=None, do_branch=True, u_branch=None):
+        """E_L = V + T_L, weighting / branching, Vref.  v=None: the configured built-in potential, on the GPU."""
+        vv = None if v is None else f64(v)
+        ub = None if u_branch is None else f64(u_branch)
+        check(lib.pvd_sim_imp_ext_finish(self._h, ptr(vv), 0 if vv is None else len(vv), 1 if do_branch else 0, ptr(ub)))
+
     def sums_ptr(self):
         p = C.c_void_p(None)
         check(lib.pvd_sim_sums_ptr(self._h, C.byref(p)))

@@ -298,3 +298,46 @@ def test_water_importance_sampling_with_analytic_derivatives(pv, tmp_path):
     sim.run()
     zpe = sim.vref_vs_tau[300:, 1].mean() / WN
     assert 4500 < zpe < 4800, zpe
+
+
+USER_TRIAL = '''
+import numpy as np
+
+ALPHA = 1.4 * %r          # a Gaussian that is NOT the exact ground state: the estimator has a variance, walkers branch
+
+
+def my_trial(cds):
+    return np.exp(-0.5 * ALPHA * cds ** 2).squeeze()
+
+
+def my_derivs(cds):
+    x = cds
+    return -ALPHA * x, (ALPHA ** 2 * x ** 2 - ALPHA)
+'''
+
+
+@pytest.mark.parametrize("derivs", ["finite_difference", "user_function"])
+@pytest.mark.parametrize("user_potential", [False, True])
+def test_importance_sampling_with_user_trial_function(pv, tmp_path, derivs, user_potential, oracle):
+    """SURVEY 8b: any trial / derivative callable through ImpSampManager (imp_samp_manager.py:92-139, 197-224), with a shipped
+    or a user potential: the reference's main importance-sampling use case runs on the GPU path (host answers drift once per step)."""
+    m, om = oracle.reduced_mass('O-H'), 3700.0 * WN
+    (tmp_path / "my_trial.py").write_text(USER_TRIAL % (m * om))
+    imp = pv.ImpSampManager_NoMP(trial_function='my_trial', trial_directory=str(tmp_path), python_file='my_trial.py',
+                                 deriv_function=None if derivs == "finite_difference" else 'my_derivs')
+    pot = pv.Potential_Direct(potential_function=lambda c: (0.5 * m * om ** 2 * c ** 2).squeeze()) if user_potential else ho_potential(pv)
+    name = f"uimp_{derivs[0]}{int(user_potential)}"
+    sim = pv.DMC_Sim(sim_name=name, output_folder=str(tmp_path / name), num_walkers=3000, num_timesteps=700, equil_steps=100,
+                     chkpt_every=350, wfn_every=300, desc_wt_steps=20, atoms=['O-H'], delta_t=5, potential=pot,
+                     start_structures=np.zeros((1, 1, 1)), imp_samp=imp, imp_samp_oned=True, seed=3)
+    sim.run()
+    info = read_h5(str(tmp_path / name / f"{name}_sim_info.hdf5"))
+    zpe = info['vref_vs_tau'][200:, 1].mean() / WN
+    assert abs(zpe - 1850.0) < 25, zpe                               # exact 1850: importance sampling removes most of the noise
+    assert np.all(np.diff(info['vref_vs_tau'][:, 0]) > 0) and info['vref_vs_tau'][-1, 0] <= 3500.0    # effective time axis
+    pop = info['pop_vs_tau'][:, 1]
+    assert pop.min() > 1500 and pop.max() < 4500 and pop.std() > 0    # not the zero-variance case: walkers do branch
+    log = open(str(tmp_path / name / f"{name}_log.txt")).read()
+    assert "Metropolis rejected" in log
+    f_x, psi, sec = sim.f_x, sim.psi_1, sim.psi_sec_der
+    assert f_x.shape == sim.walkers.shape and psi.shape == (len(sim.walkers),) and sec.shape == f_x.shape
