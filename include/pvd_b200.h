@@ -243,6 +243,16 @@ int pvd_sim_step_injected(pvd_sim *s, const double *disp, const double *u_branch
 /* external-potential stepping: move, hand coordinates to the host, take V back and weight/branch */
 int pvd_sim_ext_move(pvd_sim *s, double *xyz_out, int64_t *n_out);
 int pvd_sim_ext_finish(pvd_sim *s, const double *v, int64_t n, int32_t do_branch);
+/* Device-tensor potential plug-in (the reference's NN_Potential exists so that user models run on GPUs,
+ * potential_manager.py:177-214): the same per-step contract as pvd_sim_ext_move / _finish, but the coordinates handed to the
+ * callable and the energies it returns stay in HBM.  *xyz_dev: float64 (n, atoms, dims), C order, on the simulation's device,
+ * owned by the handle and valid until the next call on it (wrap it with __cuda_array_interface__ / DLPack, do not free it);
+ * v_dev: float64 (n) on the same device.  pvd_sim_coords_device: the current walkers without a move (first-step energies);
+ * pvd_sim_set_pots_device: device counterpart of pvd_sim_set_pots. */
+int pvd_sim_ext_move_device(pvd_sim *s, void **xyz_dev, int64_t *n_out);
+int pvd_sim_ext_finish_device(pvd_sim *s, const void *v_dev, int64_t n, int32_t do_branch);
+int pvd_sim_coords_device(pvd_sim *s, void **xyz_dev, int64_t *n_out);
+int pvd_sim_set_pots_device(pvd_sim *s, const void *v_dev, int64_t n);
 
 /* multi-GPU split step: local part, then the caller all-reduces `sums` (device pointer to
  * PVD_NSUMS doubles, obtained from pvd_sim_sums_ptr) over NCCL, then finalisation. */

@@ -1112,11 +1112,9 @@ int pvd_sim_step_injected(pvd_sim *s, const double *disp, const double *u_branch
 }
 
 // ---- external potential: move on the device, V from the caller, weight/branch on the device
-int pvd_sim_ext_move(pvd_sim *s, double *xyz_out, int64_t *n_out)
+// moves the walkers (Philox normals) and leaves them as AoS (n, atoms, dims) in the staging buffer on the device
+static int ext_move_impl(pvd_sim *s, long long *n_out)
 {
-    SIM_CHECK(s);
-    SIM_DEVICE(s);
-    PVD_REQUIRE(s->uploaded && xyz_out && n_out, "pvd_sim_ext_move: bad arguments");
     PVD_REQUIRE(s->cfg.trial == PVD_TRIAL_NONE, "external potentials with built-in importance sampling are not supported");
     const int nc = s->nc;
     const int g = s->grid;
@@ -1138,10 +1136,55 @@ int pvd_sim_ext_move(pvd_sim *s, double *xyz_out, int64_t *n_out)
     PVD_CUDA(s->stage.alloc((size_t)n * nc * 8));
     k_soa_to_aos<<<grid_for(n * nc, 256, 16), 256, 0, s->stream>>>(x, s->stage.as<double>(), n, nc, s->cap);
     PVD_CHECK_LAUNCH();
-    PVD_CUDA(cudaMemcpyAsync(xyz_out, s->stage.p, (size_t)n * nc * 8, cudaMemcpyDeviceToHost, s->stream));
-    PVD_CUDA(cudaStreamSynchronize(s->stream));
     *n_out = n;
     s->ext_moved = true;
+    return PVD_OK;
+}
+
+int pvd_sim_ext_move(pvd_sim *s, double *xyz_out, int64_t *n_out)
+{
+    SIM_CHECK(s);
+    SIM_DEVICE(s);
+    PVD_REQUIRE(s->uploaded && xyz_out && n_out, "pvd_sim_ext_move: bad arguments");
+    long long n = 0;
+    if (int rc = ext_move_impl(s, &n)) return rc;
+    PVD_CUDA(cudaMemcpyAsync(xyz_out, s->stage.p, (size_t)n * s->nc * 8, cudaMemcpyDeviceToHost, s->stream));
+    PVD_CUDA(cudaStreamSynchronize(s->stream));
+    *n_out = n;
+    return PVD_OK;
+}
+
+/* device-tensor plug-in: the moved walkers stay in HBM.  *xyz_dev: float64 (n, atoms, dims), C order, on the simulation's device, valid
+ * until the next call on this handle; every kernel that produced it has completed when the call returns. */
+int pvd_sim_ext_move_device(pvd_sim *s, void **xyz_dev, int64_t *n_out)
+{
+    SIM_CHECK(s);
+    SIM_DEVICE(s);
+    PVD_REQUIRE(s->uploaded && xyz_dev && n_out, "pvd_sim_ext_move_device: bad arguments");
+    long long n = 0;
+    if (int rc = ext_move_impl(s, &n)) return rc;
+    PVD_CUDA(cudaStreamSynchronize(s->stream));
+    *xyz_dev = s->stage.p;
+    *n_out = n;
+    return PVD_OK;
+}
+
+/* the walkers as they are (no move), AoS on the device: first-step energies of a device-tensor potential */
+int pvd_sim_coords_device(pvd_sim *s, void **xyz_dev, int64_t *n_out)
+{
+    SIM_CHECK(s);
+    SIM_DEVICE(s);
+    PVD_REQUIRE(s->uploaded && xyz_dev && n_out, "pvd_sim_coords_device: bad arguments");
+    PVD_CUDA(cudaStreamSynchronize(s->stream));
+    DevState h[2];
+    PVD_CUDA(cudaMemcpy(h, s->st.p, sizeof(h), cudaMemcpyDeviceToHost));
+    const long long n = h[s->parity].n;
+    PVD_CUDA(s->stage.alloc((size_t)n * s->nc * 8));
+    k_soa_to_aos<<<grid_for(n * s->nc, 256, 16), 256, 0, s->stream>>>(s->x[s->cur].as<double>(), s->stage.as<double>(), n, s->nc, s->cap);
+    PVD_CHECK_LAUNCH();
+    PVD_CUDA(cudaStreamSynchronize(s->stream));
+    *xyz_dev = s->stage.p;
+    *n_out = n;
     return PVD_OK;
 }
 
@@ -1162,6 +1205,42 @@ int pvd_sim_ext_finish(pvd_sim *s, const double *v, int64_t n, int32_t do_branch
     s->parity ^= 1;
     s->ext_moved = false;
     PVD_CUDA(cudaStreamSynchronize(s->stream));
+    return PVD_OK;
+}
+
+/* v_dev: float64 (n) on the simulation's device (the plug-in's result, e.g. a torch / CuPy array: whatever stream wrote it is
+ * synchronised here, device-wide, before the energies are used) */
+int pvd_sim_ext_finish_device(pvd_sim *s, const void *v_dev, int64_t n, int32_t do_branch)
+{
+    SIM_CHECK(s);
+    SIM_DEVICE(s);
+    PVD_REQUIRE(s->ext_moved && v_dev, "pvd_sim_ext_finish_device: call pvd_sim_ext_move_device first");
+    PVD_CUDA(cudaDeviceSynchronize());
+    PVD_CUDA(cudaMemcpyAsync(s->v[s->cur].p, v_dev, (size_t)n * 8, cudaMemcpyDeviceToDevice, s->stream));
+    StepArgs a = make_args(s, do_branch);
+    if (s->cfg.weighting == PVD_WEIGHT_CONTINUOUS) {
+        if (int rc = cont_enqueue_branch_only(s, a)) return rc;
+    } else {
+        k_branch_discrete<<<s->grid_light, PVD_CTA, 0, s->stream>>>(a);
+        PVD_CHECK_LAUNCH();
+        s->cur ^= 1;
+    }
+    s->parity ^= 1;
+    s->ext_moved = false;
+    PVD_CUDA(cudaStreamSynchronize(s->stream));
+    return PVD_OK;
+}
+
+int pvd_sim_set_pots_device(pvd_sim *s, const void *v_dev, int64_t n)
+{
+    SIM_CHECK(s);
+    SIM_DEVICE(s);
+    PVD_REQUIRE(s->uploaded && v_dev && n == s->n_uploaded, "pvd_sim_set_pots_device: call after pvd_sim_upload with the same n");
+    PVD_CUDA(cudaDeviceSynchronize());
+    PVD_CUDA(cudaMemcpyAsync(s->v[s->cur].p, v_dev, (size_t)n * 8, cudaMemcpyDeviceToDevice, s->stream));
+    PVD_CUDA(cudaStreamSynchronize(s->stream));
+    if (int rc = sim_init_sums(s)) return rc;
+    if (s->cfg.world_size == 1) return pvd_sim_init_finalize(s);
     return PVD_OK;
 }
 

@@ -339,10 +339,18 @@ class DMC_Sim:
             v0 = None if self._pot_on_device else np.asarray(self.potential(self._walker_coords), dtype=np.float64)
             self._dev.imp_ext_init(f_x, psi_1, sec, v0)
         elif not self._builtin:
-            self._dev.set_pots(np.asarray(self.potential(self._walker_coords), dtype=np.float64))
+            if self._device_potential():
+                self._dev.set_pots_device(self._potential_obj.getpot_device(self._dev.coords_device()))
+            else:
+                self._dev.set_pots(np.asarray(self.potential(self._walker_coords), dtype=np.float64))
         self._dev_step0 = int(self.cur_timestep)      # propagation step that device step 0 corresponds to
         self._host_stale = False
         return self._dev
+
+    def _device_potential(self):
+        """A Potential_Direct(device=True) plug-in and no per-step host hook: coordinates and energies never leave HBM."""
+        return (bool(getattr(self._potential_obj, 'device', False)) and hasattr(self._potential_obj, 'getpot_device')
+                and not getattr(self, '_hooked', False) and self._world == 1)
 
     def _pull_walkers(self):
         """Refresh the host copies of the per-walker arrays from HBM (checkpoints, .walkers, end of run)."""
@@ -524,6 +532,17 @@ class DMC_Sim:
                     else:
                         v = self.potential(cds)
                     dev.imp_ext_finish(np.array(v, dtype=np.float64), do_branch)
+                if dev.state(raise_on_error=False)["err"]:
+                    break
+                continue
+            if self._device_potential():
+                # device-tensor plug-in: the callable gets a CUDA view of the moved walkers and returns a device array
+                arr = dev.ext_move_device()
+                if step in self._log_set:
+                    v_dev, pot_seconds[step] = self._potential_obj.getpot_device(arr, timeit=True)
+                else:
+                    v_dev = self._potential_obj.getpot_device(arr)
+                dev.ext_finish_device(v_dev, (step % self.branch_every) == 0)
                 if dev.state(raise_on_error=False)["err"]:
                     break
                 continue

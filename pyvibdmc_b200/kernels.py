@@ -140,6 +140,55 @@ def desc_wts(who_from, n_parent, wts=None):
     return out
 
 
+# ----------------------------------------------------------------------------- device arrays for plug-ins
+class DeviceArray:
+    """A float64 C-ordered array in HBM owned by a simulation handle, handed to device-tensor plug-ins.  It speaks
+    `__cuda_array_interface__` (version 3), so `torch.as_tensor(a, device='cuda')`, `cupy.asarray(a)` and numba see the
+    memory without a copy; `.torch()` does the former."""
+
+    def __init__(self, ptr_, shape, device=0):
+        self.ptr, self.shape, self.device = int(ptr_ or 0), tuple(int(x) for x in shape), int(device)
+
+    @property
+    def __cuda_array_interface__(self):
+        return {"shape": self.shape, "typestr": "<f8", "data": (self.ptr, False), "version": 3, "strides": None, "stream": None}
+
+    def torch(self):
+        import torch
+        return torch.as_tensor(self, device=torch.device("cuda", self.device))
+
+    def __len__(self):
+        return self.shape[0]
+
+
+def device_pointer(arr):
+    """(pointer, number of float64 elements) of a device array: anything with `__cuda_array_interface__` (torch, CuPy,
+    numba, DeviceArray) or `__dlpack__`; float64, contiguous."""
+    if not hasattr(arr, "__cuda_array_interface__") and hasattr(arr, "__dlpack__"):
+        import torch
+        arr = torch.utils.dlpack.from_dlpack(arr)
+    if hasattr(arr, "is_cuda"):                  # a torch tensor: make the dtype / layout right without leaving the device
+        import torch
+        if not arr.is_cuda:
+            raise ValueError("a device-tensor potential must return its energies on the GPU")
+        arr = arr.detach().to(torch.float64).contiguous().reshape(-1)
+        device_pointer._keep = arr               # keep the converted tensor alive until the C call has copied it
+    cai = arr.__cuda_array_interface__
+    if cai["typestr"] != "<f8":
+        raise ValueError("device energies must be float64")
+    if cai.get("strides") is not None:
+        item, expect = 8, []
+        for d in reversed(cai["shape"]):
+            expect.append(item)
+            item *= d
+        if tuple(cai["strides"]) != tuple(reversed(expect)):
+            raise ValueError("device energies must be contiguous")
+    n = 1
+    for d in cai["shape"]:
+        n *= int(d)
+    return int(cai["data"][0]), n
+
+
 # ----------------------------------------------------------------------------- importance sampling
 def trial_drift(trial, cds, table, ntab=None):
     """ImpSamp.drift for a built-in trial wfn: returns (grad psi/psi, psi, d2psi/psi).
@@ -290,6 +339,26 @@ class DeviceSim:
     def ext_finish(self, v, do_branch=True):
         v = f64(v)
         check(lib.pvd_sim_ext_finish(self._h, ptr(v), len(v), 1 if do_branch else 0))
+
+    # ---- device-tensor potential plug-in: coordinates and energies stay in HBM
+    def ext_move_device(self):
+        """Move the walkers; returns a DeviceArray (n, atoms, dims) float64 view of them in HBM (valid until the next call)."""
+        p, n = C.c_void_p(None), C.c_int64(0)
+        check(lib.pvd_sim_ext_move_device(self._h, C.byref(p), C.byref(n)))
+        return DeviceArray(p.value, (n.value, self.natoms, self.ndim), self.cfg.device)
+
+    def coords_device(self):
+        p, n = C.c_void_p(None), C.c_int64(0)
+        check(lib.pvd_sim_coords_device(self._h, C.byref(p), C.byref(n)))
+        return DeviceArray(p.value, (n.value, self.natoms, self.ndim), self.cfg.device)
+
+    def ext_finish_device(self, v_dev, do_branch=True):
+        ptr_, n = device_pointer(v_dev)
+        check(lib.pvd_sim_ext_finish_device(self._h, C.c_void_p(ptr_), n, 1 if do_branch else 0))
+
+    def set_pots_device(self, v_dev):
+        ptr_, n = device_pointer(v_dev)
+        check(lib.pvd_sim_set_pots_device(self._h, C.c_void_p(ptr_), n))
 
     # ---- importance sampling with a user trial wave function (trial=_capi.TRIAL_EXTERNAL): the host supplies psi and derivatives
     def imp_ext_init(self, fx, psi, sec, v=None):

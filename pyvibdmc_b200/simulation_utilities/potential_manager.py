@@ -184,13 +184,20 @@ class NN_Potential(Potential_NoMP):
 
 
 class Potential_Direct(_TimestepMixin):
-    """Potential_Direct(potential_function: callable, pot_kwargs=None, pass_timestep=False)
-    (potential_manager.py:217-253)."""
+    """Potential_Direct(potential_function: callable, pot_kwargs=None, pass_timestep=False) (potential_manager.py:217-253).
 
-    def __init__(self, potential_function, pot_kwargs=None, pass_timestep=False):
+    device=True (B200 extension): the callable is a GPU model.  It receives the walkers as a CUDA tensor
+    -- a zero-copy `torch.Tensor` view (n, atoms, 3) float64 of the simulation's buffer in HBM (`as_torch=False`: the raw
+    `kernels.DeviceArray`, which speaks `__cuda_array_interface__`, for CuPy / numba) -- and returns the energies as a device
+    array (torch / CuPy / anything with `__cuda_array_interface__` or `__dlpack__`), float64 Hartree, shape (n,).  Nothing
+    crosses PCIe: the reference's NN_Potential exists precisely so that user models run on GPUs (:177-214)."""
+
+    def __init__(self, potential_function, pot_kwargs=None, pass_timestep=False, device=False, as_torch=True):
         self.potential_function = potential_function
         self.pot_kwargs = pot_kwargs
         self.pass_timestep = pass_timestep
+        self.device = bool(device)
+        self.as_torch = bool(as_torch)
         self._init_timestep()
 
     def gpu_spec(self):
@@ -198,5 +205,18 @@ class Potential_Direct(_TimestepMixin):
 
     def getpot(self, cds, timeit=False):
         start = time.time()
+        if self.device and not hasattr(cds, "__cuda_array_interface__"):
+            # host coordinates (e.g. the reference-style call on sim.walkers): through the GPU model and back
+            import torch
+            cds = torch.as_tensor(np.ascontiguousarray(cds, dtype=np.float64), device="cuda")
+            v = self.potential_function(cds, self.pot_kwargs) if self.pot_kwargs is not None else self.potential_function(cds)
+            return self._finish_call(v.detach().cpu().numpy() if hasattr(v, "detach") else np.asarray(v), start, timeit)
+        v = self.potential_function(cds, self.pot_kwargs) if self.pot_kwargs is not None else self.potential_function(cds)
+        return self._finish_call(v, start, timeit)
+
+    def getpot_device(self, dev_array, timeit=False):
+        """dev_array: kernels.DeviceArray of the walkers in HBM -> device array of energies (stays on the GPU)."""
+        start = time.time()
+        cds = dev_array.torch() if self.as_torch else dev_array
         v = self.potential_function(cds, self.pot_kwargs) if self.pot_kwargs is not None else self.potential_function(cds)
         return self._finish_call(v, start, timeit)

@@ -341,3 +341,56 @@ def test_importance_sampling_with_user_trial_function(pv, tmp_path, derivs, user
     assert "Metropolis rejected" in log
     f_x, psi, sec = sim.f_x, sim.psi_1, sim.psi_sec_der
     assert f_x.shape == sim.walkers.shape and psi.shape == (len(sim.walkers),) and sec.shape == f_x.shape
+
+
+def test_device_tensor_potential_plugin(pv, tmp_path, oracle):
+    """Potential_Direct(device=True): the callable receives a zero-copy CUDA tensor view of the walkers and returns a CUDA
+    tensor; the run is identical (same seed, same arithmetic in float64) to the same potential evaluated by the host path."""
+    import torch
+    m, om = oracle.reduced_mass('O-H'), 3700.0 * WN
+    k = 0.5 * m * om ** 2
+    seen = {}
+
+    def gpu_model(cds):
+        assert isinstance(cds, torch.Tensor) and cds.is_cuda and cds.dtype == torch.float64 and cds.shape[1:] == (1, 1)
+        seen["ptr"] = cds.data_ptr()
+        return (k * cds * cds).reshape(-1)
+
+    runs = []
+    for dev_flag in (True, False):
+        pot = pv.Potential_Direct(potential_function=gpu_model, device=True) if dev_flag else \
+            pv.Potential_Direct(potential_function=lambda c: (k * c * c).squeeze())
+        name = f"devpot{int(dev_flag)}"
+        sim = pv.DMC_Sim(sim_name=name, output_folder=str(tmp_path / name), num_walkers=2000, num_timesteps=300, equil_steps=50,
+                         chkpt_every=150, wfn_every=100, desc_wt_steps=20, atoms=['O-H'], delta_t=10, potential=pot,
+                         start_structures=np.zeros((1, 1, 1)), seed=6)
+        sim.run()
+        runs.append((sim._vref_vs_tau.copy(), sim._pop_vs_tau.copy(), sim.walkers.copy()))
+    assert "ptr" in seen                                            # the model really ran on device memory
+    assert np.array_equal(runs[0][1], runs[1][1]) and np.array_equal(runs[0][2], runs[1][2])
+    assert np.allclose(runs[0][0], runs[1][0], rtol=1e-13)
+    zpe = runs[0][0][100:].mean() / WN
+    assert abs(zpe - 1852) < 40, zpe
+
+
+def test_device_array_interfaces(pv):
+    """kernels.DeviceArray speaks __cuda_array_interface__; device_pointer accepts torch tensors, DLPack capsules' owners and DeviceArray."""
+    import torch
+    K, capi = pv.kernels, pv._capi
+    sim = K.DeviceSim(3, 3, [1837.15, 1837.15, 29156.9], 500, 5.0, capi.POT_EXTERNAL, seed=1)
+    start = EQ[None] * 1.01 + np.random.default_rng(0).normal(0, 0.01, (500, 3, 3))
+    sim.upload(start)
+    arr = sim.coords_device()
+    t = arr.torch()
+    assert t.shape == (500, 3, 3) and t.is_cuda and np.array_equal(t.cpu().numpy(), start)
+    v = torch.from_numpy(K.pes_h2o(start)).cuda()
+    sim.set_pots_device(v)
+    moved = sim.ext_move_device().torch().clone()
+    assert torch.all(torch.abs(moved - torch.from_numpy(start).cuda()) < 1.0)
+    v2 = torch.from_numpy(K.pes_h2o(moved.cpu().numpy())).cuda()
+    sim.ext_finish_device(v2.to(torch.float32).to(torch.float64))       # any float64 CUDA tensor; dtype / layout checked
+    st = sim.state()
+    assert st["step"] == 1 and 250 < st["n"] < 750
+    with pytest.raises(ValueError):
+        K.device_pointer(torch.zeros(4, dtype=torch.float64))          # a host tensor is refused
+    sim.close()
