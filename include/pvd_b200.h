@@ -279,6 +279,9 @@ int pvd_sim_run_mailbox(pvd_sim *s, int64_t nsteps, int32_t branch_every);
 
 /* descendant weighting (pyvibdmc.py:739-747, 663-672, 856-869) */
 int pvd_sim_dw_begin(pvd_sim *s, int64_t global_offset);
+/* dmc_restart inside an open window (pyvibdmc.py:299-338: _who_from / _parent / _parent_wts travel in the checkpoint): who_from
+ * (n) of the uploaded walkers and the parent ensemble (n_parent, atoms, dims) [+ parent weights] back onto the device. */
+int pvd_sim_dw_resume(pvd_sim *s, const int64_t *who_from, int64_t n, const double *parent_xyz, const double *parent_w, int64_t n_parent);
 int pvd_sim_dw_end(pvd_sim *s, double *desc_wts, int64_t n_parent);
 /* calc_desc_wts without closing the window (DEBUG_save_desc_wt_tracker, pyvibdmc.py:849-852) */
 int pvd_sim_dw_peek(pvd_sim *s, double *desc_wts, int64_t n_parent);

@@ -1371,6 +1371,36 @@ int pvd_sim_dw_begin(pvd_sim *s, int64_t global_offset)
     return PVD_OK;
 }
 
+/* Re-opens a descendant-weighting window from a checkpoint written inside one (pyvibdmc.py:299-338 keeps _who_from, _parent,
+ * _parent_wts in the pickle): who_from of the current walkers and the parent ensemble go back to the device. */
+int pvd_sim_dw_resume(pvd_sim *s, const int64_t *who_from, int64_t n, const double *parent_xyz, const double *parent_w, int64_t n_parent)
+{
+    SIM_CHECK(s);
+    SIM_DEVICE(s);
+    PVD_REQUIRE(s->uploaded && who_from && parent_xyz && n == s->n_uploaded && n_parent >= 1 && n_parent <= s->cap, "pvd_sim_dw_resume: bad arguments");
+    PVD_CUDA(cudaStreamSynchronize(s->stream));
+    std::vector<int> w32((size_t)n);
+    for (int64_t i = 0; i < n; ++i) w32[(size_t)i] = (int)who_from[i];
+    PVD_CUDA(cudaMemcpy(s->who[s->cur].p, w32.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
+    PVD_CUDA(s->parent_x.alloc((size_t)s->cap * s->nc * 8));
+    PVD_CUDA(s->stage.alloc((size_t)n_parent * s->nc * 8));
+    PVD_CUDA(cudaMemcpy(s->stage.p, parent_xyz, (size_t)n_parent * s->nc * 8, cudaMemcpyHostToDevice));
+    k_aos_to_soa<<<grid_for(n_parent * s->nc, 256, 16), 256, 0, s->stream>>>(s->stage.as<double>(), s->parent_x.as<double>(), n_parent, s->nc, s->cap);
+    PVD_CHECK_LAUNCH();
+    if (s->cfg.weighting == PVD_WEIGHT_CONTINUOUS && parent_w) {
+        PVD_CUDA(s->parent_w.alloc((size_t)s->cap * 8));
+        PVD_CUDA(cudaMemcpy(s->parent_w.p, parent_w, (size_t)n_parent * 8, cudaMemcpyHostToDevice));
+    }
+    s->parent_n = n_parent;
+    DevState h[2];
+    PVD_CUDA(cudaStreamSynchronize(s->stream));
+    PVD_CUDA(cudaMemcpy(h, s->st.p, sizeof(h), cudaMemcpyDeviceToHost));
+    h[0].dw_active = 1;
+    h[1].dw_active = 1;
+    PVD_CUDA(cudaMemcpy(s->st.p, h, sizeof(h), cudaMemcpyHostToDevice));
+    return PVD_OK;
+}
+
 static int dw_collect(pvd_sim *s, double *desc_wts, int64_t n_parent, bool close_window);
 int pvd_sim_dw_end(pvd_sim *s, double *desc_wts, int64_t n_parent) { return dw_collect(s, desc_wts, n_parent, true); }
 /* calc_desc_wts without closing the window (DEBUG_save_desc_wt_tracker, pyvibdmc.py:849-852) */

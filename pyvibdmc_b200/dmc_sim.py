@@ -86,19 +86,8 @@ class DMC_Sim:
         self._dev = None
         # one process per GPU under torch.distributed (torchrun): every rank runs this same object, walkers are sharded,
         # rank 0 writes the reference's output files, the other ranks write theirs (identical) into a scratch folder
-        self._world, self._rank = 1, 0
-        if distributed or distributed is None:
-            try:
-                import torch.distributed as dist
-                if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-                    self._world, self._rank = dist.get_world_size(), dist.get_rank()
-            except ImportError:
-                pass
-            if distributed and self._world == 1:
-                raise RuntimeError("distributed=True needs torch.distributed initialised with more than one rank")
-        if self._rank > 0:
-            import tempfile
-            self.output_folder = tempfile.mkdtemp(prefix=f"pvd_rank{self._rank}_")
+        self._distributed_arg = distributed
+        self._detect_world(distributed)
         self._host_rng = np.random.default_rng(self._seed ^ 0x5DEECE66D)      # fixed-node recrossing draws (host side)
         if excited_state_imp_samp and (imp_samp_oned or second_impsamp_displacement):
             raise NotImplementedError("excited_state_imp_samp is implemented for 3-D atoms with the standard move only")
@@ -251,6 +240,28 @@ class DMC_Sim:
             self.impsamp_manager = None
         self.adiabatic_dmc = None
 
+    def _detect_world(self, distributed=None):
+        """One process per GPU under torch.distributed (torchrun): world size, rank, this rank's GPU and -- for ranks > 0 -- a
+        scratch output folder (rank 0 writes the reference's files).  Called by the constructor AND by dmc_restart: the pickle
+        of a checkpoint carries neither the world nor the device."""
+        self._world, self._rank = 1, 0
+        if distributed or distributed is None:
+            try:
+                import torch.distributed as dist
+                if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                    self._world, self._rank = dist.get_world_size(), dist.get_rank()
+            except ImportError:
+                pass
+            if distributed and self._world == 1:
+                raise RuntimeError("distributed=True needs torch.distributed initialised with more than one rank")
+        if self._world > 1 and "LOCAL_RANK" in os.environ:
+            self._device = int(os.environ["LOCAL_RANK"])
+        if self._rank > 0:
+            import tempfile
+            self.output_folder = tempfile.mkdtemp(prefix=f"pvd_rank{self._rank}_")
+            os.makedirs(os.path.join(self.output_folder, "wfns"), exist_ok=True)
+            os.makedirs(os.path.join(self.output_folder, "chkpts"), exist_ok=True)
+
     # ------------------------------------------------------------------ public properties
     @property
     def vref_vs_tau(self):
@@ -343,6 +354,9 @@ class DMC_Sim:
                 self._dev.set_pots_device(self._potential_obj.getpot_device(self._dev.coords_device()))
             else:
                 self._dev.set_pots(np.asarray(self.potential(self._walker_coords), dtype=np.float64))
+        if getattr(self, '_desc_wt', False) and getattr(self, '_parent', None) is not None and len(self._who_from) == len(self._walker_coords):
+            self._dev.dw_resume(self._who_from, self._parent, getattr(self, '_parent_wts', None))      # dmc_restart inside a window
+            self._dw_n_parent = len(self._parent)
         self._dev_step0 = int(self.cur_timestep)      # propagation step that device step 0 corresponds to
         self._host_stale = False
         return self._dev
@@ -506,6 +520,8 @@ class DMC_Sim:
         self._pull_walkers()
 
     def _write_chkpt(self, t):
+        if self._desc_wt and self._dev is not None and self._world == 1:
+            self._parent, self._parent_wts = self._dev.dw_parent()         # an open window travels in the pickle (pyvibdmc.py:299-338)
         FileManager.delete_older_checkpoints(self.output_folder, self.sim_name, t)
         logger, self._logger = self._logger, None
         SimArchivist.chkpt(self, t)
@@ -610,6 +626,8 @@ class DMC_Sim:
             self._logger = None
             try:
                 self._pull_walkers()
+                if self._desc_wt and self._dev is not None and self._world == 1:
+                    self._parent, self._parent_wts = self._dev.dw_parent()     # an open window travels in the pickle
             except Exception:
                 pass
             SimArchivist.chkpt(self, self.cur_timestep)
@@ -672,9 +690,14 @@ def dmc_restart(potential, chkpt_folder, sim_name, additional_timesteps=0, impsa
     dmc_sim._potential_obj = potential
     dmc_sim.potential_info = vars(potential)
     dmc_sim._dev = None
+    # under torchrun every rank reloads rank 0's pickle: world, rank, GPU and the scratch folder of ranks > 0 are this process's own
+    dmc_sim._detect_world(getattr(dmc_sim, '_distributed_arg', None))
     if getattr(dmc_sim, '_desc_wt', False):
-        print("WARNING: the checkpoint was written inside a descendant-weighting window; that window is dropped.")
-        dmc_sim._desc_wt = False
+        # the checkpoint was written inside a descendant-weighting window: it is resumed (_who_from, _parent and _parent_wts are in
+        # the pickle, pyvibdmc.py:299-338), unless the run is sharded (who_from holds global parent ids there)
+        if dmc_sim._world > 1 or getattr(dmc_sim, '_parent', None) is None or getattr(dmc_sim, '_who_from', None) is None:
+            print("WARNING: the checkpoint was written inside a descendant-weighting window; that window is dropped.")
+            dmc_sim._desc_wt = False
     dmc_sim._logger = SimLogger(f"{dmc_sim.output_folder}/{dmc_sim.sim_name}_log.txt")
     FileManager.delete_future_checkpoints(chkpt_folder, sim_name, dmc_sim.cur_timestep)
     return dmc_sim

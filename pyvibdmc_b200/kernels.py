@@ -424,6 +424,13 @@ class DeviceSim:
     def dw_begin(self, global_offset=0):
         check(lib.pvd_sim_dw_begin(self._h, int(global_offset)))
 
+    def dw_resume(self, who_from, parent, parent_wts=None):
+        """Re-open a descendant-weighting window from checkpointed who_from / parent arrays (dmc_restart inside a window)."""
+        who = np.ascontiguousarray(who_from, dtype=np.int64)
+        par = f64(parent)
+        pw = None if parent_wts is None else f64(parent_wts)
+        check(lib.pvd_sim_dw_resume(self._h, ptr(who), len(who), ptr(par), ptr(pw), len(par)))
+
     def dw_end(self, n_parent):
         out = np.zeros(int(n_parent))
         check(lib.pvd_sim_dw_end(self._h, ptr(out), int(n_parent)))

@@ -394,3 +394,33 @@ def test_device_array_interfaces(pv):
     with pytest.raises(ValueError):
         K.device_pointer(torch.zeros(4, dtype=torch.float64))          # a host tensor is refused
     sim.close()
+
+
+@pytest.mark.parametrize("weighting", ["discrete", "continuous"])
+def test_restart_inside_descendant_weighting_window(pv, tmp_path, weighting):
+    """pyvibdmc.py:299-338: a checkpoint written while a descendant-weighting window is open carries _who_from / _parent(_wts);
+    dmc_restart resumes the window and the wave function file of that window is written after the restart."""
+    out = str(tmp_path / f"dwr_{weighting}")
+    kw = dict(sim_name="dwr", output_folder=out, weighting=weighting, num_walkers=2000, num_timesteps=125, equil_steps=20,
+              chkpt_every=1000, wfn_every=100, desc_wt_steps=50, atoms=['O-H'], delta_t=10, potential=ho_potential(pv),
+              start_structures=np.zeros((1, 1, 1)), seed=13)
+    sim = pv.DMC_Sim(**kw)
+    sim.run()                                           # ends at step 124, inside the window opened at step 120 (equil + wfn_every)
+    assert [os.path.basename(f) for f in glob.glob(f"{out}/wfns/*.hdf5")] == ["dwr_wfn_20ts.hdf5"]
+    ck = pickle.load(open(glob.glob(f"{out}/chkpts/dwr_*.pickle")[0], "rb"))
+    assert ck._desc_wt and len(ck._who_from) == len(ck._walker_coords) and ck._parent is not None
+    n_parent = len(ck._parent)
+    assert n_parent == (int(sim._pop_vs_tau[119]) if weighting == 'discrete' else 2000) and ck._who_from.max() < n_parent
+    sim2 = pv.dmc_restart(potential=ho_potential(pv), chkpt_folder=out, sim_name="dwr", additional_timesteps=100)
+    sim2.run()
+    w = read_h5(f"{out}/wfns/dwr_wfn_120ts.hdf5")
+    assert np.array_equal(w['coords'], ck._parent) and len(w['desc_wts']) == n_parent
+    info = read_h5(f"{out}/dwr_sim_info.hdf5")
+    if weighting == "discrete":
+        assert w['desc_wts'].sum() == info['pop_vs_tau'][169, 1]         # descendants at the window's last step
+        # walkers that had already died out before the checkpoint have no descendants afterwards either
+        alive = np.zeros(n_parent, bool)
+        alive[ck._who_from] = True
+        assert np.all(w['desc_wts'][~alive] == 0) and w['desc_wts'][alive].sum() == w['desc_wts'].sum()
+    else:
+        assert abs(w['desc_wts'].sum() - info['pop_vs_tau'][169, 1]) < 1e-6 * 2000 and 'parent_wts' in w
