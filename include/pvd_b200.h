@@ -324,6 +324,13 @@ int pvd_sim_imp_ext_finish(pvd_sim *s, const double *v_or_null, int64_t n, int32
 /* walker rebalancing between shards: remove the last `count` walkers into host/peer buffers, or append */
 int pvd_sim_export_tail(pvd_sim *s, int64_t count, double *xyz, double *pots, double *w, int64_t *who);
 int pvd_sim_import(pvd_sim *s, int64_t count, const double *xyz, const double *pots, const double *w, const int64_t *who);
+/* The same transfers GPU to GPU (SURVEY 8e "periodic P2P walker rebalancing"): the last `count` walkers are packed into one device
+ * buffer of `ncols` float64 per walker -- x[atoms*dims] | V | w | who_from | and, with importance sampling, f_x[atoms*dims] | psi |
+ * T_L (| vector score): the companions travel with their walker -- which the caller sends over NVLink (NCCL send / recv on device
+ * pointers, no host staging) and the receiver appends with pvd_sim_import_device.  *payload_dev is owned by the handle and valid
+ * until the next call on it. */
+int pvd_sim_export_tail_device(pvd_sim *s, int64_t count, void **payload_dev, int32_t *ncols);
+int pvd_sim_import_device(pvd_sim *s, int64_t count, const void *payload_dev, int32_t ncols);
 
 #ifdef __cplusplus
 }

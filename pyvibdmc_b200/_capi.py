@@ -155,6 +155,8 @@ SIGNATURES = {
     "pvd_sim_imp_ext_finish": (C.c_int, [_P, _P, _I64, _I32, _P]),
     "pvd_sim_export_tail": (C.c_int, [_P, _I64, _P, _P, _P, _P]),
     "pvd_sim_import": (C.c_int, [_P, _I64, _P, _P, _P, _P]),
+    "pvd_sim_export_tail_device": (C.c_int, [_P, _I64, C.POINTER(C.c_void_p), C.POINTER(_I32)]),
+    "pvd_sim_import_device": (C.c_int, [_P, _I64, _P, _I32]),
 }
 
 _lib = None

@@ -654,6 +654,97 @@ int pvd_sim_import(pvd_sim *s, int64_t count, const double *xyz, const double *p
     return PVD_OK;
 }
 
+// ---- the same transfers without the host: walkers are packed into / unpacked from one device buffer, which travels GPU to GPU
+// (NCCL send / recv over NVLink on the caller's side).  Row layout (float64): x[nc] | V | w | who_from | then, with importance
+// sampling, f_x[nc] | psi | T_L (| vector score) -- the companions travel with their walker instead of being recomputed.
+static int payload_cols(const pvd_sim *s)
+{
+    int c = s->nc + 3;
+    if (s->cfg.trial != PVD_TRIAL_NONE) c += s->nc + 2 + (s->cfg.imp_variant == PVD_IMP_EXCITED_STATE ? 1 : 0);
+    return c;
+}
+
+struct PackArgs {
+    double *x, *v, *w, *f, *psi, *lk, *vs;
+    int *who;
+    long long cap;
+    int nc, ncols, imp;
+};
+
+__global__ void k_pack_walkers(PackArgs a, long long first, long long count, double *payload, int unpack)
+{
+    const long long total = count * a.ncols;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long i = e / a.ncols;
+        const int j = (int)(e - i * a.ncols);
+        const long long wk = first + i;
+        double *p = payload + e;
+        if (j < a.nc) { double *q = a.x + (long long)j * a.cap + wk; if (unpack) *q = *p; else *p = *q; continue; }
+        int k = j - a.nc;
+        if (k == 0) { if (unpack) a.v[wk] = *p; else *p = a.v[wk]; continue; }
+        if (k == 1) { if (a.w) { if (unpack) a.w[wk] = *p; else *p = a.w[wk]; } else if (!unpack) *p = 1.0; continue; }
+        if (k == 2) { if (unpack) a.who[wk] = (int)*p; else *p = (double)a.who[wk]; continue; }
+        k -= 3;
+        if (k < a.nc) { double *q = a.f + (long long)k * a.cap + wk; if (unpack) *q = *p; else *p = *q; continue; }
+        k -= a.nc;
+        double *q = k == 0 ? a.psi + wk : k == 1 ? a.lk + wk : a.vs + wk;
+        if (unpack) *q = *p; else *p = *q;
+    }
+}
+
+static PackArgs pack_args(pvd_sim *s)
+{
+    PackArgs a{};
+    a.x = s->x[s->cur].as<double>(); a.v = s->v[s->cur].as<double>(); a.w = s->w.as<double>(); a.who = s->who[s->cur].as<int>();
+    a.cap = s->cap; a.nc = s->nc; a.ncols = payload_cols(s);
+    a.imp = s->cfg.trial != PVD_TRIAL_NONE;
+    if (a.imp) { a.f = s->f[s->cur].as<double>(); a.psi = s->psi[s->cur].as<double>(); a.lk = s->lk[s->cur].as<double>(); a.vs = s->vs[s->cur].as<double>(); }
+    return a;
+}
+
+int pvd_sim_export_tail_device(pvd_sim *s, int64_t count, void **payload_dev, int32_t *ncols)
+{
+    SIM_CHECK(s);
+    SIM_DEVICE(s);
+    PVD_REQUIRE(payload_dev && ncols, "NULL argument");
+    PVD_CUDA(cudaStreamSynchronize(s->stream));
+    DevState h[2];
+    PVD_CUDA(cudaMemcpy(h, s->st.p, sizeof(h), cudaMemcpyDeviceToHost));
+    const long long n = h[s->parity].n;
+    PVD_REQUIRE(count >= 0 && count < n, "pvd_sim_export_tail_device: bad count");
+    const PackArgs a = pack_args(s);
+    PVD_CUDA(s->xfer.alloc((size_t)count * a.ncols * 8));
+    k_pack_walkers<<<grid_for(count * a.ncols, 256, 16), 256, 0, s->stream>>>(a, n - count, count, s->xfer.as<double>(), 0);
+    PVD_CHECK_LAUNCH();
+    PVD_CUDA(cudaStreamSynchronize(s->stream));
+    h[1 - s->parity] = h[s->parity];
+    h[0].n = n - count; h[1].n = n - count;
+    PVD_CUDA(cudaMemcpy(s->st.p, h, sizeof(h), cudaMemcpyHostToDevice));
+    *payload_dev = s->xfer.p;
+    *ncols = a.ncols;
+    return PVD_OK;
+}
+
+int pvd_sim_import_device(pvd_sim *s, int64_t count, const void *payload_dev, int32_t ncols)
+{
+    SIM_CHECK(s);
+    SIM_DEVICE(s);
+    PVD_CUDA(cudaDeviceSynchronize());            // the payload was written by the caller's stream (NCCL recv)
+    DevState h[2];
+    PVD_CUDA(cudaMemcpy(h, s->st.p, sizeof(h), cudaMemcpyDeviceToHost));
+    const long long n = h[s->parity].n;
+    const PackArgs a = pack_args(s);
+    PVD_REQUIRE(payload_dev && count >= 0 && n + count <= s->cap, "pvd_sim_import_device: not enough capacity");
+    PVD_REQUIRE(ncols == a.ncols, "pvd_sim_import_device: payload layout does not match this simulation");
+    k_pack_walkers<<<grid_for(count * a.ncols, 256, 16), 256, 0, s->stream>>>(a, n, count, (double *)payload_dev, 1);
+    PVD_CHECK_LAUNCH();
+    PVD_CUDA(cudaStreamSynchronize(s->stream));
+    h[1 - s->parity] = h[s->parity];
+    h[0].n = n + count; h[1].n = n + count;
+    PVD_CUDA(cudaMemcpy(s->st.p, h, sizeof(h), cudaMemcpyHostToDevice));
+    return PVD_OK;
+}
+
 }  // extern "C"
 
 #include "pvd_nn_host.inl"

@@ -379,6 +379,7 @@ struct pvd_sim {
     size_t gather_smem = 0;
     DevBuf inj_disp, inj_u, inj_um, stage, stage2;   // staging for host<->device transposes / injections
     DevBuf parent_x, parent_w;
+    DevBuf xfer;                                   // packed walkers on their way to / from another shard (device-to-device rebalancing)
     DevBuf kill_idx, hist, cand, cand_sorted, bin_start, bin_fill, cont_work, copy_dst, copy_src, cont_queue, cont_root, cont_skip;
     DevBuf trial_table, acc_count;
     DevBuf impx_y, impx_fy, impx_sec, impx_psiy, impx_invm;      // importance sampling with a user trial wave function (pvd_impext.cuh)

@@ -136,29 +136,27 @@ class ShardedSim:
     def populations(self):
         torch, dist = self.torch, self.dist
         n = torch.tensor([self.sim.state(raise_on_error=False)["n"]], dtype=torch.int64, device=self.device)
-        out = [torch.zeros_like(n) for _ in range(self.world)]
-        dist.all_gather(out, n)
-        return [int(t.item()) for t in out]
+        out = torch.zeros(self.world, dtype=torch.int64, device=self.device)
+        dist.all_gather_into_tensor(out, n)
+        return [int(v) for v in out.tolist()]                   # one device-to-host read for the whole world
 
     def rebalance(self, tolerance=0.05):
-        """Move whole walkers (coords, V, weight, who_from) from over- to under-populated shards."""
+        """Move whole walkers (coords, V, weight, who_from and the importance-sampling companions) from over- to under-populated
+        shards, GPU to GPU: packed on the device, NCCL send / recv over NVLink on device pointers, unpacked on the device."""
         torch, dist = self.torch, self.dist
         moves = plan_rebalance(self.populations(), tolerance)
-        nc = self.natoms * self.ndim
         for src, dst, count in moves:
             if self.rank == src:
-                xyz = np.empty((count, self.natoms, self.ndim)); pots = np.empty(count)
-                w = np.empty(count); who = np.empty(count, dtype=np.int64)
-                _capi.check(_capi.lib.pvd_sim_export_tail(self.sim._h, count, _capi.ptr(xyz), _capi.ptr(pots), _capi.ptr(w), _capi.ptr(who)))
-                payload = np.concatenate([xyz.reshape(count, nc), pots[:, None], w[:, None], who[:, None].astype(np.float64)], axis=1)
-                dist.send(torch.from_numpy(payload).to(self.device), dst)
+                payload = self.sim.export_tail_device(count).torch()
+                dist.send(payload, dst)
+                torch.cuda.synchronize(self.device)             # the buffer belongs to the simulation handle: sent before it is re-used
             elif self.rank == dst:
-                buf = torch.empty((count, nc + 3), dtype=torch.float64, device=self.device)
+                ncols = self.natoms * self.ndim + 3
+                if self.sim.cfg.trial != _capi.TRIAL_NONE:
+                    ncols += self.natoms * self.ndim + 2 + (1 if self.sim.cfg.imp_variant == _capi.IMP_EXCITED_STATE else 0)
+                buf = torch.empty((count, ncols), dtype=torch.float64, device=self.device)
                 dist.recv(buf, src)
-                p = buf.cpu().numpy()
-                xyz = np.ascontiguousarray(p[:, :nc]); pots = np.ascontiguousarray(p[:, nc])
-                w = np.ascontiguousarray(p[:, nc + 1]); who = np.ascontiguousarray(p[:, nc + 2]).astype(np.int64)
-                _capi.check(_capi.lib.pvd_sim_import(self.sim._h, count, _capi.ptr(xyz), _capi.ptr(pots), _capi.ptr(w), _capi.ptr(who)))
+                self.sim.import_device(buf)
         return moves
 
     # -- descendant weighting across shards (SURVEY 8e): who_from holds GLOBAL parent ids (rank-major order)

@@ -340,6 +340,20 @@ class DeviceSim:
         v = f64(v)
         check(lib.pvd_sim_ext_finish(self._h, ptr(v), len(v), 1 if do_branch else 0))
 
+    # ---- walkers to / from another shard without the host
+    def export_tail_device(self, count):
+        """Pack the last `count` walkers (coordinates, V, weight, who_from, importance-sampling companions) into one device
+        buffer and drop them from this shard; returns a DeviceArray (count, ncols)."""
+        p, nc = C.c_void_p(None), C.c_int32(0)
+        check(lib.pvd_sim_export_tail_device(self._h, int(count), C.byref(p), C.byref(nc)))
+        return DeviceArray(p.value, (int(count), nc.value), self.cfg.device)
+
+    def import_device(self, payload):
+        """Append walkers packed by export_tail_device on another shard (any device array (count, ncols))."""
+        ptr_, n = device_pointer(payload)
+        cols = int(payload.shape[1])
+        check(lib.pvd_sim_import_device(self._h, n // cols, C.c_void_p(ptr_), cols))
+
     # ---- device-tensor potential plug-in: coordinates and energies stay in HBM
     def ext_move_device(self):
         """Move the walkers; returns a DeviceArray (n, atoms, dims) float64 view of them in HBM (valid until the next call)."""

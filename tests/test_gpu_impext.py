@@ -141,3 +141,34 @@ def test_metropolis_and_local_kin_any_shape(K, oracle):
         assert np.allclose(got, ref, rtol=1e-11, atol=0), (na, nd)
         assert np.array_equal(got == 0.0, ref == 0.0)
         assert np.allclose(K.local_kin(sec, inv), oracle.local_kin(inv_trip, sec), rtol=1e-14, atol=0), (na, nd)
+
+
+def test_device_to_device_walker_transfer(K, oracle):
+    """Rebalancing payloads: export_tail_device / import_device move whole walkers -- coordinates, V, who_from and the
+    importance-sampling companions -- between two simulation handles without touching the host; same result as the host path."""
+    from pyvibdmc_b200 import _capi
+    m, om = oracle.reduced_mass('O-H'), 3700.0 * WN
+    mk = lambda seed: K.DeviceSim(1, 1, [m], 4000, 5.0, _capi.POT_HARMONIC, pot_params=[(0.5 * m) * om ** 2], trial=_capi.TRIAL_HARM1D,
+                                  seed=seed, capacity=9000)
+    a, b = mk(1), mk(2)
+    for s in (a, b):
+        s.set_trial_table(np.array([1.3 * m * om]))       # not the exact ground state: the walkers differ
+        s.upload(np.random.default_rng(7).normal(0, 0.05, (3000, 1, 1)))
+        s.run(5)
+    da, db = a.download(), b.download()
+    fa, pa, _ = a.download_imp()
+    fb, pb, _ = b.download_imp()
+    na, nb, count = len(da["coords"]), len(db["coords"]), 700
+    payload = a.export_tail_device(count)
+    assert payload.shape == (count, 1 + 3 + 1 + 2)
+    b.import_device(payload.torch())
+    assert a.state()["n"] == na - count and b.state()["n"] == nb + count
+    da2, db2 = a.download(), b.download()
+    fb2, pb2, _ = b.download_imp()
+    assert np.array_equal(da2["coords"], da["coords"][:na - count])
+    assert np.array_equal(db2["coords"], np.concatenate([db["coords"], da["coords"][na - count:]]))
+    assert np.array_equal(db2["pots"], np.concatenate([db["pots"], da["pots"][na - count:]]))
+    assert np.array_equal(fb2, np.concatenate([fb, fa[na - count:]])) and np.array_equal(pb2, np.concatenate([pb, pa[na - count:]]))
+    b.run(3)                                              # the enlarged shard keeps running
+    assert b.state()["step"] == 8
+    a.close(); b.close()
