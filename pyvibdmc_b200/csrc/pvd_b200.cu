@@ -1275,7 +1275,7 @@ int pvd_sim_mailbox_handle(pvd_sim *s, void *handle64)
     PVD_REQUIRE(handle64, "NULL argument");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     if (!s->mbox.p) {
-        const size_t bytes = (size_t)2 * PVD_MAX_WORLD * PVD_MBOX_STRIDE * 8;
+        const size_t bytes = (size_t)2 * PVD_MAX_WORLD * PVD_MBOX_STRIDE * 16;      // 16-byte entries {value, stamp ^ value}
         PVD_CUDA(s->mbox.alloc(bytes));
         PVD_CUDA(cudaMemset(s->mbox.p, 0, bytes));
     }

@@ -525,18 +525,7 @@ __global__ void __launch_bounds__(TPB, MINB) k_run_discrete(const StepArgs a, co
             if (a.world > 1 && a.mbox[0]) {
                 // several GPUs: the shard's sums go to every peer's mailbox, the world's sums come back (pvd_step.cuh); the
                 // other warps of the grid are busy with the move + potential of step k + 1 meanwhile
-                const int nmsg = PVD_SUM_EXT + 4 * a.world;
-                const long long slot = mbox_slot(ps, a.rank);
-                for (int m = lane; m < a.world * nmsg; m += 32) {
-                    const int peer = m / nmsg, kk = m - peer * nmsg;
-                    a.mbox[peer][slot + kk] = s[kk];
-                }
-                __threadfence_system();
-                __syncwarp();
-                if (lane < a.world) {
-                    unsigned long long *stamp = reinterpret_cast<unsigned long long *>(&a.mbox[lane][slot + PVD_NSUMS]);
-                    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(stamp), "l"((a.mbox_epoch << 40) | (unsigned long long)(gstep + 1)) : "memory");
-                }
+                mailbox_post(a, ps, gstep, lane, 32);
                 mailbox_collect_and_finalize(a, false, ps, &comm_ok);
             }
             if (lane == 0) {

@@ -186,64 +186,82 @@ __device__ inline void forward_dead_state(const StepArgs &a);
 // ---------------------------------------------------------------- per-step collective over NVLink peer memory
 // The only exchange of a time step is PVD_NSUMS doubles per shard.  Instead of a NCCL all-reduce kernel
 // between the step kernel and the finalisation, the last CTA of the step kernel stores its shard's sums straight into
-// every peer's mailbox (slot [step parity][source rank]) over NVLink, fences at system scope and stamps the slot with
-// step + 1; the one-warp finalisation kernel on each GPU waits for the world's stamps, adds the slots in rank order
-// (so every GPU gets bit-identical Vref) and finalises.  Two parities suffice: a rank cannot start step s + 2 before
-// it has finalised s + 1, which needs every peer's s + 1 message, which a peer sends only after finalising s.
-constexpr int PVD_MBOX_STRIDE = PVD_NSUMS + 8;          // doubles per slot; the stamp sits at [PVD_NSUMS]
+// every peer's mailbox (slot [step parity][source rank]) over NVLink; one warp on each GPU waits for the world's messages,
+// adds the slots in rank order (so every GPU gets bit-identical Vref) and finalises.  Two parities suffice: a rank cannot
+// start step s + 2 before it has finalised s + 1, which needs every peer's s + 1 message, which a peer sends only after
+// finalising s.
+// Every value is its own message: one 16-byte store {bits(value), stamp ^ bits(value)} with stamp = (run epoch, step + 1).
+// The reader accepts an entry when word1 ^ word0 equals the stamp it expects -- so there is no data-then-fence-then-flag
+// sequence on either side (the two system-scope fences were most of the exchange's latency), and an entry whose two halves
+// arrived from different steps (if a 16-byte store were ever torn) cannot pass: it would need old value == new value.
+constexpr int PVD_MBOX_STRIDE = PVD_NSUMS + 8;          // 16-byte entries per slot
 __device__ __forceinline__ long long mbox_slot(int parity, int rank) { return ((long long)parity * PVD_MAX_WORLD + rank) * PVD_MBOX_STRIDE; }
+__device__ __forceinline__ unsigned long long mbox_stamp(const StepArgs &a, long long step) { return (a.mbox_epoch << 40) | (unsigned long long)(step + 1); }
+
+// posts a.sums to every rank's mailbox; called by `nthreads` threads (tid = 0 .. nthreads-1) after a.sums is complete and visible to them
+__device__ inline void mailbox_post(const StepArgs &a, int parity, long long step, int tid, int nthreads)
+{
+    const int nmsg = PVD_SUM_EXT + 4 * a.world;
+    const long long slot = mbox_slot(parity, a.rank);
+    const unsigned long long stamp = mbox_stamp(a, step);
+    for (int t = tid; t < a.world * nmsg; t += nthreads) {
+        const int peer = t / nmsg, k = t - peer * nmsg;
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(a.sums[k]);
+        unsigned long long *dst = reinterpret_cast<unsigned long long *>(a.mbox[peer]) + 2 * (slot + k);
+        asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(bits), "l"(stamp ^ bits) : "memory");
+    }
+}
 
 // called by ALL threads of the CTA that holds the shard's final sums in a.sums
 __device__ inline void mailbox_send(const StepArgs &a, long long step)
 {
-    const int nmsg = PVD_SUM_EXT + 4 * a.world;
-    const long long slot = mbox_slot(a.parity, a.rank);
     __syncthreads();
-    for (int t = threadIdx.x; t < a.world * nmsg; t += blockDim.x) {
-        const int peer = t / nmsg, k = t - peer * nmsg;
-        a.mbox[peer][slot + k] = a.sums[k];
-    }
-    __threadfence_system();
-    __syncthreads();
-    if ((int)threadIdx.x < a.world) {
-        unsigned long long *stamp = reinterpret_cast<unsigned long long *>(&a.mbox[threadIdx.x][slot + PVD_NSUMS]);
-        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(stamp), "l"((a.mbox_epoch << 40) | (unsigned long long)(step + 1)) : "memory");
-    }
+    mailbox_post(a, a.parity, step, (int)threadIdx.x, (int)blockDim.x);
 }
 
-// One warp: waits for the world's stamps of this step in its own mailbox, adds the slots in rank order and finalises.
+// One warp: waits for the world's messages of this step in its own mailbox, adds them in rank order into a.sums; false: a peer's
+// message did not arrive in time (a peer died or fell far behind: the device is never hung).
+__device__ inline bool mailbox_collect(const StepArgs &a, int parity, long long cur_step)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned long long *mine = reinterpret_cast<const unsigned long long *>(a.mbox[a.rank]);
+    const unsigned long long want = mbox_stamp(a, cur_step);
+    const int nmsg = PVD_SUM_EXT + 4 * a.world;
+    bool ok = true;
+    const long long t0 = clock64();
+    for (int k = lane; k < nmsg; k += 32) {
+        // all ranks' entries of this value are requested together; only the late ones are asked for again
+        unsigned long long bits[PVD_MAX_WORLD];
+        unsigned pending = (1u << a.world) - 1u;
+        while (pending) {
+            unsigned long long w0[PVD_MAX_WORLD], w1[PVD_MAX_WORLD];
+#pragma unroll
+            for (int r = 0; r < PVD_MAX_WORLD; ++r)
+                if (pending & (1u << r))
+                    asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0[r]), "=l"(w1[r]) : "l"(mine + 2 * (mbox_slot(parity, r) + k)) : "memory");
+#pragma unroll
+            for (int r = 0; r < PVD_MAX_WORLD; ++r)
+                if ((pending & (1u << r)) && (w1[r] ^ w0[r]) == want) { bits[r] = w0[r]; pending &= ~(1u << r); }
+            if (pending && clock64() - t0 > a.mbox_timeout_ticks) { ok = false; break; }
+        }
+        double v = 0.0;
+#pragma unroll
+        for (int r = 0; r < PVD_MAX_WORLD; ++r)
+            if (r < a.world && !(pending & (1u << r))) v += __longlong_as_double((long long)bits[r]);
+        a.sums[k] = v;
+    }
+    ok = __all_sync(0xffffffffu, ok);
+    __syncwarp();
+    return ok;
+}
+
+// One warp: collect, then finalise (lane 0).
 __device__ inline void mailbox_collect_and_finalize(const StepArgs &a, bool continuous, int parity, bool *collect_only = nullptr)
 {
     const long long cur_step = __ldcg(&a.st[parity].step);
-    const int lane = threadIdx.x & 31;
-    const double *mine = a.mbox[a.rank];
-    const unsigned long long want = (a.mbox_epoch << 40) | (unsigned long long)(cur_step + 1);
-    bool ok = true;
-    if (lane < a.world) {
-        const unsigned long long *stamp = reinterpret_cast<const unsigned long long *>(&mine[mbox_slot(parity, lane) + PVD_NSUMS]);
-        const long long t0 = clock64();
-        unsigned long long got;
-        do {
-            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(stamp) : "memory");
-            if (got == want) break;
-            if (clock64() - t0 > a.mbox_timeout_ticks) { ok = false; break; }     // a peer died or fell far behind: do not hang the GPU
-        } while (true);
-    }
-    ok = __all_sync(0xffffffffu, ok);
-    __threadfence_system();
-    const int nmsg = PVD_SUM_EXT + 4 * a.world;
-    for (int k = lane; k < nmsg; k += 32) {
-        double v = 0.0;
-        for (int r = 0; r < a.world; ++r) {
-            double x;
-            asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(x) : "l"(&mine[mbox_slot(parity, r) + k]) : "memory");
-            v += x;
-        }
-        a.sums[k] = v;
-    }
-    __syncwarp();
+    const bool ok = mailbox_collect(a, parity, cur_step);
     if (collect_only) { *collect_only = ok; return; }
-    if (lane == 0) {
+    if ((threadIdx.x & 31) == 0) {
         if (!ok) {
             forward_dead_state(a, parity);
             a.st[parity ^ 1].err |= PVD_ERR_COMM;
