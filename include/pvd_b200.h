@@ -146,6 +146,10 @@ int pvd_local_kin(const double *d2, int64_t n, int32_t natoms, int32_t ndim, con
  * weights: packed float32 [W0(15x120) b0(120) W1(120x120) b1 W2(120x120) b2 W3(120) b3(1)] row-major (in,out).
  * xyz: (n,6,3) bohr, atoms O,H,H,O,H,H. */
 int pvd_nn_h4o2_set_weights(const float *packed, int64_t nfloats);
+/* kernel selection for the network (negative = keep): path 0 tcgen05 / two tiles in flight (default), 1 tcgen05 / one tile,
+ * 2 float32 FMA on CUDA cores (float32-accurate cross-check); terms 3 | 4; threads 512 | 1024.  Looked up at launch from a
+ * process-wide setting, never from the environment (which only provides the initial values). */
+int pvd_nn_config(int32_t path, int32_t terms, int32_t threads);
 int pvd_nn_h4o2(const double *xyz, int64_t n, double *v);
 int pvd_coulomb_descriptor(const double *xyz, int64_t n, int32_t natoms, const double *z, double *desc);
 /* replaces DistIt.run (simulation_utilities/tensorflow_descriptors/distance_descriptors.py:177-213; helpers :88-168) for any

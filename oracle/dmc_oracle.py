@@ -440,6 +440,17 @@ def nn_forward_f32(desc, weights):
     return x.reshape(-1).astype(np.float64) * WAVENUMBERS
 
 
+def nn_forward_f64(desc, weights):
+    """The same network evaluated in float64 on the float32 weights and the float32-rounded descriptor: the value every
+    float32 implementation (TensorFlow's, the NumPy one above, the tcgen05 kernel) approximates; the pin of tests/golden/
+    nn_h4o2_f64_golden.npz."""
+    x = np.asarray(desc, dtype=np.float32).astype(np.float64)
+    for li, (k, b) in enumerate(weights):
+        z = x @ k.astype(np.float64) + b.astype(np.float64)
+        x = z / (1.0 + np.exp(-z)) if li < len(weights) - 1 else np.maximum(z, 0.0)
+    return x.reshape(-1) * WAVENUMBERS
+
+
 # --------------------------------------------------------------------------- the loop itself
 class Draws:
     """Random-number source for dmc_loop: either NumPy's legacy global stream (like the

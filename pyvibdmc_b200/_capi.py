@@ -107,6 +107,7 @@ SIGNATURES = {
     "pvd_metropolis": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _P, _F64, _P]),
     "pvd_local_kin": (C.c_int, [_P, _I64, _I32, _I32, _P, _P]),
     "pvd_nn_h4o2_set_weights": (C.c_int, [_P, _I64]),
+    "pvd_nn_config": (C.c_int, [_I32, _I32, _I32]),
     "pvd_nn_h4o2": (C.c_int, [_P, _I64, _P]),
     "pvd_coulomb_descriptor": (C.c_int, [_P, _I64, _I32, _P, _P]),
     "pvd_sim_create": (C.c_int, [C.POINTER(PvdConfig), C.POINTER(_P)]),

@@ -599,11 +599,27 @@ static int nn_upload_weights(NNDeviceWeights &w, const float *packed)
 }
 
 constexpr size_t NN_SMEM_BYTES = 2 * NN_H * NN_TILE * sizeof(float);
-static bool nn_use_cuda_cores()
+// Which kernel evaluates the network: chosen once (environment at first use, or pvd_nn_config), never looked up per launch.
+struct NNPathCfg {
+    int path = 0;        // 0 tcgen05, two tiles in flight (default); 1 tcgen05, one tile (activations through shared memory); 2 float32 FMA on CUDA cores
+    int terms = TC2_TERMS;
+    int threads = 512;
+    bool init = false;
+};
+static NNPathCfg g_nn_cfg;
+static const NNPathCfg &nn_cfg()
 {
-    const char *e = getenv("PVD_NN_FP32");      // debugging / cross-check switch: float32 FMA kernel instead of tcgen05
-    return e && e[0] == '1';
+    if (!g_nn_cfg.init) {
+        const char *e = getenv("PVD_NN_FP32"), *e1 = getenv("PVD_NN_TC1"), *et = getenv("PVD_NN_TERMS"), *eth = getenv("PVD_NN_THREADS");
+        if (e && e[0] == '1') g_nn_cfg.path = 2;
+        else if (e1 && e1[0] == '1') g_nn_cfg.path = 1;
+        if (et && (et[0] == '3' || et[0] == '4')) g_nn_cfg.terms = et[0] - '0';
+        if (eth && atoi(eth) == 1024) g_nn_cfg.threads = 1024;
+        g_nn_cfg.init = true;
+    }
+    return g_nn_cfg;
 }
+static bool nn_use_cuda_cores() { return nn_cfg().path == 2; }
 static int nn_prepare_launch()
 {
     static bool done = false;
@@ -631,18 +647,15 @@ static int nn_launch(cudaStream_t stream, const double *x, int soa, long long ca
         if (g > 3ll * sms) g = 3ll * sms;
         k_nn_h4o2<<<(int)(g < 1 ? 1 : g), NN_THREADS, NN_SMEM_BYTES, stream>>>(x, soa, cap, st, parity, n_fixed, w.packed, v, nullptr);
     } else {
-        const char *e1 = getenv("PVD_NN_TC1");                   // previous generation (activations through shared memory), for A/B runs
-        if (e1 && e1[0] == '1') {
+        if (nn_cfg().path == 1) {                                // previous generation (activations through shared memory), for A/B runs
             long long g = (n_upper + TC_M - 1) / TC_M;
             if (g > sms) g = sms;                                // persistent: one CTA per SM (192 KB of shared memory each)
             k_nn_h4o2_tc<<<(int)(g < 1 ? 1 : g), TC_THREADS, TC_SMEM_BYTES, stream>>>(x, soa, cap, st, parity, n_fixed, w.images, w.vecs, v);
         } else {
             long long g = (n_upper + 2 * TC_M - 1) / (2 * TC_M);
             if (g > sms) g = sms;                                // persistent: one CTA per SM (all 512 TMEM columns), two tiles in flight
-            const char *et = getenv("PVD_NN_TERMS");
-            const int nterms = (et && (et[0] == '3' || et[0] == '4')) ? et[0] - '0' : TC2_TERMS;
-            const char *eth = getenv("PVD_NN_THREADS");
-            if (eth && atoi(eth) == 1024)                        // measured: 2.77e9 walkers/s vs 2.88e9 with 512 threads
+            const int nterms = nn_cfg().terms;
+            if (nn_cfg().threads == 1024)                        // measured: 2.77e9 walkers/s vs 2.88e9 with 512 threads
                 k_nn_h4o2_tc2<1024><<<(int)(g < 1 ? 1 : g), 1024, TC2_SMEM_BYTES, stream>>>(x, soa, cap, st, parity, n_fixed, w.images, w.vecs, v, nterms);
             else
                 k_nn_h4o2_tc2<512><<<(int)(g < 1 ? 1 : g), 512, TC2_SMEM_BYTES, stream>>>(x, soa, cap, st, parity, n_fixed, w.images, w.vecs, v, nterms);

@@ -33,6 +33,20 @@ int pvd_sim_set_nn_weights(pvd_sim *s, const float *packed, int64_t nfloats)
     return nn_upload_weights(s->nn_w, packed);
 }
 
+/* which kernel evaluates the network (process-wide; negative = leave as it is): path 0 tcgen05 with two tiles in flight
+ * (default), 1 tcgen05 with one tile, 2 float32 FMA on CUDA cores (float32-accurate cross-check); terms 3 | 4 cross terms of
+ * the fp16 split; threads 512 | 1024 per CTA of the default path.  The environment (PVD_NN_FP32 / _TC1 / _TERMS / _THREADS) only
+ * sets the initial values, once. */
+int pvd_nn_config(int32_t path, int32_t terms, int32_t threads)
+{
+    PVD_REQUIRE(path <= 2 && (terms < 0 || terms == 3 || terms == 4) && (threads < 0 || threads == 512 || threads == 1024), "pvd_nn_config: bad arguments");
+    (void)nn_cfg();
+    if (path >= 0) g_nn_cfg.path = path;
+    if (terms >= 0) g_nn_cfg.terms = terms;
+    if (threads >= 0) g_nn_cfg.threads = threads;
+    return PVD_OK;
+}
+
 int pvd_nn_h4o2_set_weights(const float *packed, int64_t nfloats)
 {
     PVD_REQUIRE(packed && nfloats == NN_NPARAM, "expected 31081 packed float32 weights");

@@ -225,6 +225,16 @@ def local_kin(d2, inv_mass):
 
 
 # ----------------------------------------------------------------------------- NN potential
+NN_PATHS = {"tcgen05": 0, "tcgen05_one_tile": 1, "cuda_cores": 2}
+
+
+def nn_config(path=None, terms=None, threads=None):
+    """Which kernel evaluates the NN PES (process-wide): path 'tcgen05' (default) | 'tcgen05_one_tile' | 'cuda_cores' (float32 FMA,
+    float32-accurate cross-check); terms 3 | 4 cross terms of the fp16 split; threads 512 | 1024."""
+    check(lib.pvd_nn_config(-1 if path is None else NN_PATHS.get(path, path), -1 if terms is None else int(terms),
+                            -1 if threads is None else int(threads)))
+
+
 def nn_h4o2_set_weights(packed):
     p = np.ascontiguousarray(packed, dtype=np.float32)
     check(lib.pvd_nn_h4o2_set_weights(ptr(p), p.size))

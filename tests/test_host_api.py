@@ -137,3 +137,22 @@ def test_log_lines_have_the_reference_format(tmp_path):
     for line in mine:
         if line.strip() and not line.startswith("Checkpointing"):
             assert generic(line) in ref_patterns, line
+
+
+def test_nn_model_from_keras_h5_without_tensorflow():
+    """NN_Potential(model=<path to the Keras .h5>) needs no pre-packing: the in-tree HDF5 reader walks the model file
+    (build container only: the reference's sample model is not shipped in this repo)."""
+    import importlib.util
+    import pyvibdmc_b200 as pv
+    h5 = "/root/reference/pyvibdmc/sample_potentials/TensorflowPots/sample_h4o2_nn.h5"
+    if not os.path.exists(h5):
+        pytest.skip("reference model file not present")
+    d = os.path.join(os.path.dirname(pv.__file__), "sample_potentials", "TensorflowPots")
+    spec = importlib.util.spec_from_file_location("call_sample_model_b200_t", os.path.join(d, "call_sample_model.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    w = mod.load_keras_h5(h5)
+    assert [x.shape for x in w] == [(15, 120), (120,), (120, 120), (120,), (120, 120), (120,), (120, 1), (1,)]
+    assert np.array_equal(mod._pack(h5), mod.load_packed_weights()) and np.array_equal(mod._pack(w), mod.load_packed_weights())
+    with pytest.raises(ValueError, match="15-120-120-120-1"):
+        mod._pack([np.zeros((10, 8)), np.zeros(8)])

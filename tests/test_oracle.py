@@ -227,3 +227,28 @@ def test_water_trial_analytic_derivatives(oracle):
                           equil=4, wfn_every=6, desc_steps=3, trial=tr, analytic=True)
     assert np.array_equal(out["pop"], gt["pop"])
     assert np.allclose(out["vref"], gt["vref"], rtol=1e-9) and np.allclose(out["eff_ts"], gt["eff_ts"], rtol=1e-14)
+
+
+def test_nn_float64_golden_pins_the_float32_oracle(oracle):
+    """a6: the float32 NumPy forward pass (the stand-in for TensorFlow's float32 one) against the float64 evaluation of the same
+    weights; the weights themselves are the reference's sample_h4o2_nn.h5 bit for bit when it can be read here."""
+    g = golden("nn_h4o2_f64_golden.npz")
+    p = np.load(os.path.join(os.path.dirname(__file__), "..", "pyvibdmc_b200", "sample_potentials", "TensorflowPots", "sample_h4o2_nn_packed.npy"))
+    o, w = 0, []
+    for k, m in ((15, 120), (120, 120), (120, 120), (120, 1)):
+        W = p[o:o + k * m].reshape(k, m); o += k * m
+        b = p[o:o + m]; o += m
+        w.append((W, b))
+    desc = oracle.coulomb_descriptor(g["coords"], [8, 1, 1, 8, 1, 1])
+    e64, e32 = oracle.nn_forward_f64(desc, w), oracle.nn_forward_f32(desc, w)
+    assert np.allclose(e64, g["e64"], rtol=1e-13, atol=0)
+    assert np.abs(e32 - g["e64"]).max() < 1.0e-6 * np.abs(g["e64"]).max()
+    assert abs(e64[0] / 4.556335281212229e-6 - 7.62) < 0.05        # equilibrium water dimer (reference tests/test_analysis.py:77-82)
+    h5 = "/root/reference/pyvibdmc/sample_potentials/TensorflowPots/sample_h4o2_nn.h5"
+    if os.path.exists(h5):                                          # build container only: the packed copy IS the reference's model
+        from pyvibdmc_b200.simulation_utilities import h5lite
+        ww = h5lite.read_h5(h5)
+        parts = []
+        for layer in ("dense", "dense_1", "dense_2", "dense_3"):
+            parts += [ww[f"model_weights/{layer}/{layer}/kernel:0"].ravel(), ww[f"model_weights/{layer}/{layer}/bias:0"].ravel()]
+        assert np.array_equal(np.concatenate(parts).astype(np.float32), p)
