@@ -172,3 +172,26 @@ def test_device_to_device_walker_transfer(K, oracle):
     b.run(3)                                              # the enlarged shard keeps running
     assert b.state()["step"] == 8
     a.close(); b.close()
+
+
+def test_chain_rule_helper_on_cuda_tensors():
+    """ChainRuleHelper(coords, torch) with CUDA tensors: every method runs on the device and reproduces the
+    unmodified reference class (golden vectors from imp_samp_helper.py:10-209)."""
+    import torch
+    from pyvibdmc_b200.simulation_utilities.imp_samp_helper import ChainRuleHelper
+    g = golden("chain_rule_golden.npz")
+    dev = torch.device("cuda", 0)
+    for tag in ("w", "p"):
+        cds = torch.from_numpy(g[f"{tag}_cds"]).to(dev)
+        h = ChainRuleHelper(cds, torch)
+        pairs, ang = [list(p) for p in g[f"{tag}_pairs"]], list(g[f"{tag}_ang"])
+        dr = [h.dr_dx(p) for p in pairs]
+        d2r = [h.d2r_dx2(p) for p in pairs]
+        dth, d2th = h.dth_dx(ang), h.d2th_dx2(ang)
+        dpsi, d2psi = torch.from_numpy(g[f"{tag}_dpsi"]).to(dev), torch.from_numpy(g[f"{tag}_d2psi"]).to(dev)
+        got = {"dr0": dr[0], "d2r1": d2r[1], "dc": h.dcth_dx(ang), "d2c": h.d2cth_dx2(ang), "dth": dth, "d2th": d2th,
+               "jac": h.dpsidx(dpsi, [dr[0], dr[1], dth]), "lap": h.d2psidx2(d2psi, [d2r[0], d2r[1], d2th], dpsi, [dr[0], dr[1], dth])}
+        for k, v in got.items():
+            assert v.is_cuda
+            ref = g[f"{tag}_{k}"]
+            assert np.allclose(v.cpu().numpy(), ref, rtol=1e-11, atol=1e-11 * np.abs(ref).max()), (tag, k)

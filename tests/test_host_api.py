@@ -156,3 +156,34 @@ def test_nn_model_from_keras_h5_without_tensorflow():
     assert np.array_equal(mod._pack(h5), mod.load_packed_weights()) and np.array_equal(mod._pack(w), mod.load_packed_weights())
     with pytest.raises(ValueError, match="15-120-120-120-1"):
         mod._pack([np.zeros((10, 8)), np.zeros(8)])
+
+
+def _chain_rule_check(mod, to_mod, to_np, rtol):
+    from pyvibdmc_b200.simulation_utilities.imp_samp_helper import ChainRuleHelper
+    g = golden("chain_rule_golden.npz")
+    for tag in ("w", "p"):
+        h = ChainRuleHelper(to_mod(g[f"{tag}_cds"]), mod)
+        pairs, ang = [list(p) for p in g[f"{tag}_pairs"]], list(g[f"{tag}_ang"])
+        dr = [h.dr_dx(p) for p in pairs]
+        d2r = [h.d2r_dx2(p) for p in pairs]
+        dth, d2th = h.dth_dx(ang), h.d2th_dx2(ang)
+        got = {"dr0": dr[0], "dr1": dr[1], "d2r0": d2r[0], "d2r1": d2r[1], "dc": h.dcth_dx(ang), "d2c": h.d2cth_dx2(ang),
+               "dth": dth, "d2th": d2th}
+        dpsi, d2psi = to_mod(g[f"{tag}_dpsi"]), to_mod(g[f"{tag}_d2psi"])
+        got["jac"] = h.dpsidx(dpsi, [dr[0], dr[1], dth])
+        got["lap"] = h.d2psidx2(d2psi, [d2r[0], d2r[1], d2th], dpsi, [dr[0], dr[1], dth])
+        for k, v in got.items():
+            ref = g[f"{tag}_{k}"]
+            assert np.allclose(to_np(v), ref, rtol=rtol, atol=rtol * np.abs(ref).max()), (tag, k)
+
+
+def test_chain_rule_helper_matches_reference_numpy():
+    """every method of ChainRuleHelper against the unmodified reference class (imp_samp_helper.py:10-209)."""
+    _chain_rule_check(np, lambda a: np.array(a), lambda a: np.asarray(a), 1e-12)
+
+
+def test_chain_rule_helper_torch_module_cpu():
+    """The same class on torch tensors (the `module` argument is the array module): on CUDA tensors it runs on the GPU
+    (tests/test_gpu_impext.py)."""
+    import torch
+    _chain_rule_check(torch, lambda a: torch.from_numpy(np.array(a)), lambda a: a.numpy(), 1e-12)
