@@ -287,6 +287,12 @@ int pvd_sim_dw_begin(pvd_sim *s, int64_t global_offset);
  * (n) of the uploaded walkers and the parent ensemble (n_parent, atoms, dims) [+ parent weights] back onto the device. */
 int pvd_sim_dw_resume(pvd_sim *s, const int64_t *who_from, int64_t n, const double *parent_xyz, const double *parent_w, int64_t n_parent);
 int pvd_sim_dw_end(pvd_sim *s, double *desc_wts, int64_t n_parent);
+/* The same without stopping the loop (north_star: "wavefunction dumps are async D2H on a side stream"): _begin counts the
+ * descendant weights, copies the parent ensemble and closes the window in stream order, and starts their transfer to pinned host
+ * memory on the side stream; the caller enqueues the next time steps and collects the arrays with _wait, which waits for the
+ * transfer only.  Replaces the synchronous save at pyvibdmc.py:856-872. */
+int pvd_sim_dw_end_begin(pvd_sim *s, int64_t n_parent);
+int pvd_sim_dw_end_wait(pvd_sim *s, double *desc_wts, double *parent_xyz, double *parent_w, int64_t n_parent);
 /* calc_desc_wts without closing the window (DEBUG_save_desc_wt_tracker, pyvibdmc.py:849-852) */
 int pvd_sim_dw_peek(pvd_sim *s, double *desc_wts, int64_t n_parent);
 /* DEBUG_mass_change (pyvibdmc.py:749-753): sigma = sqrt(dt / m) from new masses */

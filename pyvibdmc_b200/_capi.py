@@ -146,6 +146,8 @@ SIGNATURES = {
     "pvd_sim_last_run_ms": (C.c_int, [_P, C.POINTER(_F64)]),
     "pvd_sim_download_imp": (C.c_int, [_P, _P, _P, _P, _I64]),
     "pvd_sim_dw_resume": (C.c_int, [_P, _P, _I64, _P, _P, _I64]),
+    "pvd_sim_dw_end_begin": (C.c_int, [_P, _I64]),
+    "pvd_sim_dw_end_wait": (C.c_int, [_P, _P, _P, _P, _I64]),
     "pvd_sim_ext_move_device": (C.c_int, [_P, C.POINTER(C.c_void_p), C.POINTER(_I64)]),
     "pvd_sim_ext_finish_device": (C.c_int, [_P, _P, _I64, _I32]),
     "pvd_sim_coords_device": (C.c_int, [_P, C.POINTER(C.c_void_p), C.POINTER(_I64)]),

@@ -379,6 +379,12 @@ struct pvd_sim {
     size_t gather_smem = 0;
     DevBuf inj_disp, inj_u, inj_um, stage, stage2;   // staging for host<->device transposes / injections
     DevBuf parent_x, parent_w;
+    DevBuf dump_desc, dump_parent, dump_pw;        // wave-function dump in flight (descendant weights, parent ensemble): device copies
+    void *dump_host = nullptr;
+    size_t dump_host_bytes = 0;
+    cudaEvent_t dump_ready = nullptr, dump_done = nullptr;
+    bool dump_pending = false;
+    long long dump_n = 0;
     DevBuf xfer;                                   // packed walkers on their way to / from another shard (device-to-device rebalancing)
     DevBuf kill_idx, hist, cand, cand_sorted, bin_start, bin_fill, cont_work, copy_dst, copy_src, cont_queue, cont_root, cont_skip;
     DevBuf trial_table, acc_count;
@@ -618,6 +624,9 @@ int pvd_sim_destroy(pvd_sim *s)
     for (int r = 0; r < PVD_MAX_WORLD; ++r)
         if (s->peer_mbox[r] && s->peer_mbox[r] != s->mbox.p) cudaIpcCloseMemHandle(s->peer_mbox[r]);
     if (s->snap_host) cudaFreeHost(s->snap_host);
+    if (s->dump_host) cudaFreeHost(s->dump_host);
+    if (s->dump_ready) cudaEventDestroy(s->dump_ready);
+    if (s->dump_done) cudaEventDestroy(s->dump_done);
     if (s->snap_stream) cudaStreamDestroy(s->snap_stream);
     if (s->snap_ready) cudaEventDestroy(s->snap_ready);
     if (s->snap_done) cudaEventDestroy(s->snap_done);
@@ -1449,6 +1458,73 @@ static int dw_collect(pvd_sim *s, double *desc_wts, int64_t n_parent, bool close
     return PVD_OK;
 }
 
+__global__ void k_set_dw_active(DevState *st, int v)
+{
+    if (blockIdx.x == 0 && threadIdx.x == 0) { st[0].dw_active = v; st[1].dw_active = v; }
+}
+
+/* Closes the descendant-weighting window WITHOUT stopping the loop (wave-function dumps of the reference, pyvibdmc.py:856-872):
+ * the descendant weights are counted and the parent ensemble is copied in stream order, then travel to pinned host memory on the
+ * side stream while the compute stream goes on with the next time steps; pvd_sim_dw_end_wait hands them over. */
+int pvd_sim_dw_end_begin(pvd_sim *s, int64_t n_parent)
+{
+    SIM_CHECK(s);
+    SIM_DEVICE(s);
+    PVD_REQUIRE(n_parent >= 1 && n_parent == s->parent_n && s->parent_x.p, "pvd_sim_dw_end_begin: no window open for this parent count");
+    PVD_REQUIRE(!s->dump_pending, "a wave-function dump is already in flight: call pvd_sim_dw_end_wait first");
+    const int nc = s->nc;
+    const bool cont = s->cfg.weighting == PVD_WEIGHT_CONTINUOUS;
+    if (!s->snap_stream) PVD_CUDA(cudaStreamCreateWithFlags(&s->snap_stream, cudaStreamNonBlocking));
+    if (!s->dump_ready) {
+        PVD_CUDA(cudaEventCreateWithFlags(&s->dump_ready, cudaEventDisableTiming));
+        PVD_CUDA(cudaEventCreateWithFlags(&s->dump_done, cudaEventDisableTiming));
+    }
+    PVD_CUDA(s->dump_desc.alloc((size_t)n_parent * 8));
+    PVD_CUDA(s->dump_parent.alloc((size_t)n_parent * nc * 8));
+    if (cont) PVD_CUDA(s->dump_pw.alloc((size_t)n_parent * 8));
+    const size_t need = (size_t)n_parent * (nc + 2) * 8;
+    if (need > s->dump_host_bytes) {
+        if (s->dump_host) PVD_CUDA(cudaFreeHost(s->dump_host));
+        PVD_CUDA(cudaMallocHost(&s->dump_host, need));
+        s->dump_host_bytes = need;
+    }
+    PVD_CUDA(cudaMemsetAsync(s->dump_desc.p, 0, (size_t)n_parent * 8, s->stream));
+    k_desc_wts<<<s->grid, 256, 0, s->stream>>>(s->who[s->cur].as<int>(), cont ? s->w.as<double>() : nullptr, s->st.as<DevState>(), s->parity, 0, 0,
+                                               n_parent, s->dump_desc.as<double>());
+    PVD_CHECK_LAUNCH();
+    k_soa_to_aos<<<grid_for(n_parent * nc, 256, 16), 256, 0, s->stream>>>(s->parent_x.as<double>(), s->dump_parent.as<double>(), n_parent, nc, s->cap);
+    PVD_CHECK_LAUNCH();
+    if (cont) PVD_CUDA(cudaMemcpyAsync(s->dump_pw.p, s->parent_w.p, (size_t)n_parent * 8, cudaMemcpyDeviceToDevice, s->stream));
+    k_set_dw_active<<<1, 32, 0, s->stream>>>(s->st.as<DevState>(), 0);
+    PVD_CHECK_LAUNCH();
+    PVD_CUDA(cudaEventRecord(s->dump_ready, s->stream));
+    PVD_CUDA(cudaStreamWaitEvent(s->snap_stream, s->dump_ready, 0));
+    char *h = (char *)s->dump_host;
+    PVD_CUDA(cudaMemcpyAsync(h, s->dump_desc.p, (size_t)n_parent * 8, cudaMemcpyDeviceToHost, s->snap_stream));
+    PVD_CUDA(cudaMemcpyAsync(h + (size_t)n_parent * 8, s->dump_parent.p, (size_t)n_parent * nc * 8, cudaMemcpyDeviceToHost, s->snap_stream));
+    if (cont) PVD_CUDA(cudaMemcpyAsync(h + (size_t)n_parent * (nc + 1) * 8, s->dump_pw.p, (size_t)n_parent * 8, cudaMemcpyDeviceToHost, s->snap_stream));
+    PVD_CUDA(cudaEventRecord(s->dump_done, s->snap_stream));
+    s->dump_pending = true;
+    s->dump_n = n_parent;
+    return PVD_OK;
+}
+
+/* blocks only until the side-stream copies have landed (the compute stream is not synchronised) */
+int pvd_sim_dw_end_wait(pvd_sim *s, double *desc_wts, double *parent_xyz, double *parent_w, int64_t n_parent)
+{
+    SIM_CHECK(s);
+    SIM_DEVICE(s);
+    PVD_REQUIRE(s->dump_pending && n_parent == s->dump_n && desc_wts && parent_xyz, "pvd_sim_dw_end_wait: no dump in flight for this parent count");
+    PVD_CUDA(cudaEventSynchronize(s->dump_done));
+    const char *h = (const char *)s->dump_host;
+    const size_t n = (size_t)n_parent;
+    memcpy(desc_wts, h, n * 8);
+    memcpy(parent_xyz, h + n * 8, n * s->nc * 8);
+    if (parent_w && s->cfg.weighting == PVD_WEIGHT_CONTINUOUS) memcpy(parent_w, h + n * (s->nc + 1) * 8, n * 8);
+    s->dump_pending = false;
+    return PVD_OK;
+}
+
 int pvd_sim_dw_parent(pvd_sim *s, double *xyz, double *w, int64_t *n_parent)
 {
     SIM_CHECK(s);
@@ -1527,8 +1603,8 @@ int pvd_sim_snapshot_begin(pvd_sim *s)
     const int nc = s->nc;
     const size_t cap = (size_t)s->cap;
     const bool cont = s->w.p != nullptr;
-    if (!s->snap_stream) {
-        PVD_CUDA(cudaStreamCreateWithFlags(&s->snap_stream, cudaStreamNonBlocking));
+    if (!s->snap_stream) PVD_CUDA(cudaStreamCreateWithFlags(&s->snap_stream, cudaStreamNonBlocking));     // (shared with the wave-function dumps)
+    if (!s->snap_host) {
         PVD_CUDA(cudaEventCreateWithFlags(&s->snap_ready, cudaEventDisableTiming));
         PVD_CUDA(cudaEventCreateWithFlags(&s->snap_done, cudaEventDisableTiming));
         PVD_CUDA(s->snap_x.alloc(cap * nc * 8));

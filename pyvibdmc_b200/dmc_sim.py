@@ -453,10 +453,11 @@ class DMC_Sim:
                 events["chkpt"] = True
                 # resident single-GPU runs: the checkpoint travels to the host on a side stream while the next segment
                 # of time steps is already running; it is pickled below, after that segment has been enqueued
-                async_chk = (self._builtin and self._world == 1 and self.impsamp_manager is None and t not in wfn
+                async_chk = (self._builtin and self._world == 1 and self.impsamp_manager is None
                              and hasattr(dev, "snapshot_begin"))
                 if async_chk:
                     dev.snapshot_begin()
+                    chk_desc = self._desc_wt                     # the pickle describes the run as it was when the snapshot was taken
                 else:
                     self._pull_walkers()
                     self._write_chkpt(t)
@@ -478,14 +479,17 @@ class DMC_Sim:
             tic = time.time()
             if self._builtin:
                 dev.run(nxt - t, self.branch_every)
+                self._finish_wfn_dump(dev)                       # the previous window's dump landed while these steps were enqueued
                 if async_chk:
-                    snap = dev.snapshot_wait(who_from=self._desc_wt)
+                    snap = dev.snapshot_wait(who_from=chk_desc)
                     self._walker_coords, self._walker_pots, self._vref = snap["coords"], snap["pots"], snap["vref"]
                     if self.weighting == 'continuous':
                         self._cont_wts = snap["wts"]
-                    if self._desc_wt:
+                    if chk_desc:
                         self._who_from = snap["who_from"]
+                    now_desc, self._desc_wt = self._desc_wt, chk_desc     # (a window that opens at this very step opens after the checkpoint)
                     self._write_chkpt(t)
+                    self._desc_wt = now_desc
                 dev.sync()
             else:
                 events["pot_seconds"] = self._run_external(dev, t, nxt)
@@ -501,7 +505,13 @@ class DMC_Sim:
                                      keyz=['coords', 'pots'], valz=[out["coords"], out["pots"]])
             if self._desc_wt and self._deb_desc_wt_tracker:                        # pyvibdmc.py:849-852
                 self._desc_wt_history.append(dev.dw_peek(self._dw_n_parent))
-            if events.get("desc"):
+            if events.get("desc") and self._builtin and self._world == 1 and not self._deb_desc_wt_tracker and hasattr(dev, "dw_end_begin"):
+                # asynchronous wave-function dump: descendant weights and parents travel to the host on a side stream while
+                # the next segment of time steps runs; the file is written when they have landed (_finish_wfn_dump)
+                self._desc_wt = False
+                dev.dw_end_begin(self._dw_n_parent)
+                self._pending_wfn = f"{self.output_folder}/wfns/{self.sim_name}_wfn_{nxt - self.desc_wt_time_steps}ts.hdf5"
+            elif events.get("desc"):
                 self._desc_wt = False
                 self._desc_wts = dev.dw_end(self._dw_n_parent)
                 self._parent, self._parent_wts = dev.dw_parent()
@@ -517,7 +527,20 @@ class DMC_Sim:
                     self._desc_wt_history = []
             t = nxt
             self.cur_timestep = t - 1
+        self._finish_wfn_dump(dev)
         self._pull_walkers()
+
+    def _finish_wfn_dump(self, dev):
+        """Write the wave-function file of a window whose arrays were sent to the host asynchronously (pyvibdmc.py:861-867)."""
+        fname = getattr(self, '_pending_wfn', None)
+        if fname is None:
+            return
+        self._pending_wfn = None
+        self._desc_wts, self._parent, self._parent_wts = dev.dw_end_wait()
+        if self.weighting == 'continuous':
+            SimArchivist.save_h5(fname=fname, keyz=['coords', 'desc_wts', 'parent_wts'], valz=[self._parent, self._desc_wts, self._parent_wts])
+        else:
+            SimArchivist.save_h5(fname=fname, keyz=['coords', 'desc_wts'], valz=[self._parent, self._desc_wts])
 
     def _write_chkpt(self, t):
         if self._desc_wt and self._dev is not None and self._world == 1:

@@ -455,6 +455,19 @@ class DeviceSim:
         pw = None if parent_wts is None else f64(parent_wts)
         check(lib.pvd_sim_dw_resume(self._h, ptr(who), len(who), ptr(par), ptr(pw), len(par)))
 
+    def dw_end_begin(self, n_parent):
+        """Close the window and start the asynchronous transfer of (descendant weights, parent ensemble) to the host."""
+        check(lib.pvd_sim_dw_end_begin(self._h, int(n_parent)))
+        self._dump_n = int(n_parent)
+
+    def dw_end_wait(self):
+        """-> (desc_wts, parent coords, parent weights or None) of the dump started by dw_end_begin."""
+        n = self._dump_n
+        desc, par = np.empty(n), np.empty((n, self.natoms, self.ndim))
+        pw = np.empty(n) if self.cfg.weighting == _capi.WEIGHT_CONTINUOUS else None
+        check(lib.pvd_sim_dw_end_wait(self._h, ptr(desc), ptr(par), ptr(pw), n))
+        return desc, par, pw
+
     def dw_end(self, n_parent):
         out = np.zeros(int(n_parent))
         check(lib.pvd_sim_dw_end(self._h, ptr(out), int(n_parent)))
