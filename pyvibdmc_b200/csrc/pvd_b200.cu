@@ -812,15 +812,21 @@ struct RunVariant {
 };
 
 template <class POT, int TPB, int MINB>
-static RunVariant run_variant_rng(int rng_mode)
+static RunVariant run_variant_rng(int rng_mode, bool multi = false)
 {
     RunVariant v;
     v.tpb = TPB;
-    v.id = TPB * 8 + MINB;
+    v.id = (TPB * 8 + MINB) * 2 + (multi ? 1 : 0);
     v.smem = (size_t)(TPB / 32) * sizeof(RunWarpMem<POT::NC>);
-    if (rng_mode == PVD_RNG_FAST) v.kern = k_run_discrete<POT, PVD_RNG_FAST, TPB, MINB>;
-    else if (rng_mode == PVD_RNG_ZIGGURAT) v.kern = k_run_discrete<POT, PVD_RNG_ZIGGURAT, TPB, MINB>;
-    else v.kern = k_run_discrete<POT, PVD_RNG_FP64, TPB, MINB>;
+    if (multi) {
+        if (rng_mode == PVD_RNG_FAST) v.kern = k_run_discrete<POT, PVD_RNG_FAST, TPB, MINB, true>;
+        else if (rng_mode == PVD_RNG_ZIGGURAT) v.kern = k_run_discrete<POT, PVD_RNG_ZIGGURAT, TPB, MINB, true>;
+        else v.kern = k_run_discrete<POT, PVD_RNG_FP64, TPB, MINB, true>;
+    } else {
+        if (rng_mode == PVD_RNG_FAST) v.kern = k_run_discrete<POT, PVD_RNG_FAST, TPB, MINB, false>;
+        else if (rng_mode == PVD_RNG_ZIGGURAT) v.kern = k_run_discrete<POT, PVD_RNG_ZIGGURAT, TPB, MINB, false>;
+        else v.kern = k_run_discrete<POT, PVD_RNG_FP64, TPB, MINB, false>;
+    }
     return v;
 }
 
@@ -842,16 +848,19 @@ static RunVariant run_variant_for(const pvd_sim *s)
     case PVD_POT_H2O_PS: {
         // occupancy variants of the same kernel (A/B: PVD_RUN_VARIANT = 2562 | 2563 | 3842 | 2564 = threads per CTA, CTAs per SM)
         static const int want = [] { const char *e = getenv("PVD_RUN_VARIANT"); return e ? atoi(e) : PVD_RUN_VARIANT_H2O; }();
-        if (want == 2562) return run_variant_rng<PotH2O, 256, 2>(rng);
-        if (want == 3842) return run_variant_rng<PotH2O, 384, 2>(rng);
-        if (want == 2564) return run_variant_rng<PotH2O, 256, 4>(rng);
-        return run_variant_rng<PotH2O, 256, 3>(rng);
+        const bool multi = s->cfg.world_size > 1;
+        if (!multi) {                                   // (the A/B occupancy variants exist for one GPU only)
+            if (want == 2562) return run_variant_rng<PotH2O, 256, 2>(rng);
+            if (want == 3842) return run_variant_rng<PotH2O, 384, 2>(rng);
+            if (want == 2564) return run_variant_rng<PotH2O, 256, 4>(rng);
+        }
+        return run_variant_rng<PotH2O, 256, 3>(rng, multi);
     }
     case PVD_POT_HARMONIC:
-        if (s->nc == 1) return run_variant_rng<PotHarm<1>, 256, 4>(rng);
-        if (s->nc == 3) return run_variant_rng<PotHarm<3>, 256, 4>(rng);
+        if (s->nc == 1) return run_variant_rng<PotHarm<1>, 256, 4>(rng, s->cfg.world_size > 1);
+        if (s->nc == 3) return run_variant_rng<PotHarm<3>, 256, 4>(rng, s->cfg.world_size > 1);
         return RunVariant{};
-    case PVD_POT_MORSE1D: return run_variant_rng<PotMorse, 256, 4>(rng);
+    case PVD_POT_MORSE1D: return run_variant_rng<PotMorse, 256, 4>(rng, s->cfg.world_size > 1);
     default: return RunVariant{};
     }
 }
@@ -944,14 +953,20 @@ struct GatherVariant {
     int minb = 0, id = 0;
 };
 template <class POT, int MINB>
-static GatherVariant gather_variant_rng(int rng_mode, int pot_id)
+static GatherVariant gather_variant_rng(int rng_mode, int pot_id, bool multi)
 {
     GatherVariant v;
     v.minb = MINB;
-    v.id = pot_id * 64 + rng_mode * 8 + MINB;
-    if (rng_mode == PVD_RNG_FAST) v.kern = k_step_gather<POT, PVD_RNG_FAST, MINB>;
-    else if (rng_mode == PVD_RNG_ZIGGURAT) v.kern = k_step_gather<POT, PVD_RNG_ZIGGURAT, MINB>;
-    else v.kern = k_step_gather<POT, PVD_RNG_FP64, MINB>;
+    v.id = (pot_id * 64 + rng_mode * 8 + MINB) * 2 + (multi ? 1 : 0);
+    if (multi) {
+        if (rng_mode == PVD_RNG_FAST) v.kern = k_step_gather<POT, PVD_RNG_FAST, MINB, true>;
+        else if (rng_mode == PVD_RNG_ZIGGURAT) v.kern = k_step_gather<POT, PVD_RNG_ZIGGURAT, MINB, true>;
+        else v.kern = k_step_gather<POT, PVD_RNG_FP64, MINB, true>;
+    } else {
+        if (rng_mode == PVD_RNG_FAST) v.kern = k_step_gather<POT, PVD_RNG_FAST, MINB, false>;
+        else if (rng_mode == PVD_RNG_ZIGGURAT) v.kern = k_step_gather<POT, PVD_RNG_ZIGGURAT, MINB, false>;
+        else v.kern = k_step_gather<POT, PVD_RNG_FP64, MINB, false>;
+    }
     return v;
 }
 
@@ -965,14 +980,15 @@ static GatherVariant gather_variant_for(const pvd_sim *s, bool forced = false)
     switch (s->cfg.potential) {
     case PVD_POT_H2O_PS: {
         static const int want = [] { const char *e = getenv("PVD_GATHER_MINB"); return e ? atoi(e) : 2; }();
-        if (want == 3) return gather_variant_rng<PotH2O, 3>(rng, 1);
-        return gather_variant_rng<PotH2O, 2>(rng, 1);
+        const bool multi = s->cfg.world_size > 1;
+        if (want == 3 && !multi) return gather_variant_rng<PotH2O, 3>(rng, 1, false);      // (A/B occupancy variant: one GPU only)
+        return gather_variant_rng<PotH2O, 2>(rng, 1, multi);
     }
     case PVD_POT_HARMONIC:
-        if (s->nc == 1) return gather_variant_rng<PotHarm<1>, 4>(rng, 2);
-        if (s->nc == 3) return gather_variant_rng<PotHarm<3>, 4>(rng, 3);
+        if (s->nc == 1) return gather_variant_rng<PotHarm<1>, 4>(rng, 2, s->cfg.world_size > 1);
+        if (s->nc == 3) return gather_variant_rng<PotHarm<3>, 4>(rng, 3, s->cfg.world_size > 1);
         return GatherVariant{};
-    case PVD_POT_MORSE1D: return gather_variant_rng<PotMorse, 4>(rng, 4);
+    case PVD_POT_MORSE1D: return gather_variant_rng<PotMorse, 4>(rng, 4, s->cfg.world_size > 1);
     default: return GatherVariant{};
     }
 }

@@ -203,6 +203,7 @@ __device__ __forceinline__ int gather_sources(const GatherArgs &g, const int *s_
 // ---------------------------------------------------------------- end of a gather step
 // Chunk bookkeeping on top of cta_finish_step: this CTA's inclusive tile prefixes, and (last CTA) the scan of the per-CTA
 // totals.  Called by every thread of every CTA after its tile loop; s_ttot holds the totals of the CTA's tiles.
+template <bool MULTI>
 __device__ inline void gather_finish_step(const StepArgs &a, const GatherArgs &g, const LaneAcc &acc, long long n, int ntiles, int tpc,
                                           const int *s_ttot, int *s_scan)
 {
@@ -291,7 +292,7 @@ __device__ inline void gather_finish_step(const StepArgs &a, const GatherArgs &g
             a.st[a.parity ^ 1].n = (long long)f.c;
             if (a.world == 1) finalize_from_sums(a, false);
         }
-        if (a.world > 1 && a.mbox[0]) {
+        if constexpr (MULTI) if (a.world > 1 && a.mbox[0]) {
             mailbox_send(a, a.st[a.parity].step);
             __syncthreads();
             if (threadIdx.x < 32) mailbox_collect_and_finalize(a, false);
@@ -300,7 +301,8 @@ __device__ inline void gather_finish_step(const StepArgs &a, const GatherArgs &g
 }
 
 // ---------------------------------------------------------------- the step
-template <class POT, int RNG, int MINB>
+// MULTI: the instantiation that contains the NVLink exchange (several GPUs)
+template <class POT, int RNG, int MINB, bool MULTI>
 __global__ void __launch_bounds__(PVD_CTA, MINB) k_step_gather(const StepArgs a, const GatherArgs g)
 {
     constexpr int NC = POT::NC;
@@ -445,7 +447,7 @@ __global__ void __launch_bounds__(PVD_CTA, MINB) k_step_gather(const StepArgs a,
         }
         if (lane == 0) { acc.c = (double)csum; acc.deaths = (double)deaths; }
     }
-    gather_finish_step(a, g, acc, (long long)n, ntiles, tpc, s_ttot, s_cbase);
+    gather_finish_step<MULTI>(a, g, acc, (long long)n, ntiles, tpc, s_ttot, s_cbase);
 }
 
 // ---------------------------------------------------------------- end of a segment: deferred form -> compacted ensemble

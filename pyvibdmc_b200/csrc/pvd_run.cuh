@@ -233,7 +233,8 @@ __device__ __forceinline__ void run_publish_ready(const RunArgs &ra, int ps, int
         return;                                                                                         \
     } while (0)
 
-template <class POT, int RNG, int TPB, int MINB>
+// MULTI: the instantiation that contains the NVLink exchange (several GPUs); the single-GPU one carries none of its code or registers
+template <class POT, int RNG, int TPB, int MINB, bool MULTI>
 __global__ void __launch_bounds__(TPB, MINB) k_run_discrete(const StepArgs a, const RunArgs ra)
 {
     constexpr int NC = POT::NC;
@@ -522,7 +523,7 @@ __global__ void __launch_bounds__(TPB, MINB) k_run_discrete(const StepArgs a, co
             }
             __syncwarp();
             bool comm_ok = true;
-            if (a.world > 1 && a.mbox[0]) {
+            if constexpr (MULTI) if (a.world > 1 && a.mbox[0]) {
                 // several GPUs: the shard's sums go to every peer's mailbox, the world's sums come back (pvd_step.cuh); the
                 // other warps of the grid are busy with the move + potential of step k + 1 meanwhile
                 mailbox_post(a, ps, gstep, lane, 32);

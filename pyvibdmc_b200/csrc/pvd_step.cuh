@@ -221,18 +221,19 @@ __device__ inline void mailbox_send(const StepArgs &a, long long step)
 
 // One warp: waits for the world's messages of this step in its own mailbox, adds them in rank order into a.sums; false: a peer's
 // message did not arrive in time (a peer died or fell far behind: the device is never hung).
-__device__ inline bool mailbox_collect(const StepArgs &a, int parity, long long cur_step)
+// (out of line, scalar arguments: its polling arrays must not cost the step kernels that contain it any registers, and a
+// by-reference StepArgs would make every caller copy the kernel's parameter block onto its stack)
+__device__ __noinline__ bool mailbox_collect_impl(const unsigned long long *mine, unsigned long long want, int world, int parity,
+                                                  long long timeout_ticks, double *sums)
 {
     const int lane = threadIdx.x & 31;
-    const unsigned long long *mine = reinterpret_cast<const unsigned long long *>(a.mbox[a.rank]);
-    const unsigned long long want = mbox_stamp(a, cur_step);
-    const int nmsg = PVD_SUM_EXT + 4 * a.world;
+    const int nmsg = PVD_SUM_EXT + 4 * world;
     bool ok = true;
     const long long t0 = clock64();
     for (int k = lane; k < nmsg; k += 32) {
         // all ranks' entries of this value are requested together; only the late ones are asked for again
         unsigned long long bits[PVD_MAX_WORLD];
-        unsigned pending = (1u << a.world) - 1u;
+        unsigned pending = (1u << world) - 1u;
         while (pending) {
             unsigned long long w0[PVD_MAX_WORLD], w1[PVD_MAX_WORLD];
 #pragma unroll
@@ -242,17 +243,24 @@ __device__ inline bool mailbox_collect(const StepArgs &a, int parity, long long 
 #pragma unroll
             for (int r = 0; r < PVD_MAX_WORLD; ++r)
                 if ((pending & (1u << r)) && (w1[r] ^ w0[r]) == want) { bits[r] = w0[r]; pending &= ~(1u << r); }
-            if (pending && clock64() - t0 > a.mbox_timeout_ticks) { ok = false; break; }
+            if (pending && clock64() - t0 > timeout_ticks) { ok = false; break; }
         }
         double v = 0.0;
 #pragma unroll
         for (int r = 0; r < PVD_MAX_WORLD; ++r)
-            if (r < a.world && !(pending & (1u << r))) v += __longlong_as_double((long long)bits[r]);
-        a.sums[k] = v;
+            if (r < world && !(pending & (1u << r))) v += __longlong_as_double((long long)bits[r]);
+        sums[k] = v;
     }
     ok = __all_sync(0xffffffffu, ok);
     __syncwarp();
     return ok;
+}
+// One warp: waits for the world's messages of this step in its own mailbox, adds them in rank order into a.sums; false: a peer's
+// message did not arrive in time (a peer died or fell far behind: the device is never hung).
+__device__ __forceinline__ bool mailbox_collect(const StepArgs &a, int parity, long long cur_step)
+{
+    return mailbox_collect_impl(reinterpret_cast<const unsigned long long *>(a.mbox[a.rank]), mbox_stamp(a, cur_step), a.world, parity,
+                                a.mbox_timeout_ticks, a.sums);
 }
 
 // One warp: collect, then finalise (lane 0).
