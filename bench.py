@@ -608,8 +608,7 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel of the step (one launch per time step; a segment of steps ends with one
-    # k_gather_materialise launch, ~0.5 step's worth of time, which is inside the timed region and billed to the steps)
+    # ---- roofline of the dominant kernel of the step (one launch per time step)
     step_kernel = ("k_step_gather<PotH2O>" if n_loc > 300000 and not os.environ.get("PVD_NO_GATHER") else
                    "k_run_discrete<PotH2O>") if world == 1 or args.collective == "mailbox" else "k_step_discrete<PotH2O>"
     hbm_peak, peak_kind = load_peaks()
@@ -724,7 +723,7 @@ def main():
                        "parallelism": (f"walkers sharded over {world} GPU(s); per step {_capi.NSUMS} doubles per shard are exchanged "
                                        + ("by peer stores over NVLink from the step kernel's last CTA (mailbox), no collective kernel"
                                           if args.collective == "mailbox" else "by one NCCL all-reduce"))
-                       if world > 1 else "single GPU, one kernel launch per time step (deferred compaction: the next step gathers) + one materialisation per segment",
+                       if world > 1 else "single GPU, one kernel launch per time step (deferred compaction: the NEXT step's loads do the np.repeat gather; the output of the last step is compacted when the ensemble is next read -- pvd_sim_download in the e2e leg, one 0.05 ms kernel per read, not per step)",
                        "hardware_warmup": (f"{hw_steps} untimed steps of a scratch ensemble of the same shape before the W warm-up steps "
                                            "(SM clocks and NVLink links out of their idle states)") if hw_steps else "none"},
             "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,

@@ -376,6 +376,9 @@ struct pvd_sim {
     int run_grid = 0, run_minb = 0, run_occ = 0;                // cooperative grid (all CTAs co-resident) and the occupancy variant in use
     DevBuf g_cnt[2], g_tincl[2], g_cbase[2], g_meta[2], g_seg;  // deferred-compaction steps (pvd_gather.cuh): per ping-pong buffer
     int gather_grid = 0, gather_id = 0;
+    bool deferred = false;                         // x[cur] is in deferred form (a chain of gather steps is open: gather_flush() closes it)
+    int defer_buf0 = 0;                            // buffer the open chain started from (compacted input of its first step)
+    long long defer_steps = 0;                     // steps enqueued in the open chain
     size_t gather_smem = 0;
     DevBuf inj_disp, inj_u, inj_um, stage, stage2;   // staging for host<->device transposes / injections
     DevBuf parent_x, parent_w;
@@ -483,8 +486,17 @@ static int imp_enqueue_branch(pvd_sim *, StepArgs &);
 static int imp_initial_drift(pvd_sim *, long long first = 0, long long count = -1);
 static int nn_enqueue_discrete_step(pvd_sim *, StepArgs &);
 
+static int gather_flush(pvd_sim *s);
 #define SIM_CHECK(s) PVD_REQUIRE((s) != nullptr, "NULL simulation handle")
-#define SIM_DEVICE(s) PVD_CUDA(cudaSetDevice((s)->cfg.device))
+// Every entry point that may look at the walker arrays goes through SIM_DEVICE: an open chain of deferred-compaction steps
+// (pvd_gather.cuh) is materialised first, so nothing but pvd_sim_run / _run_mailbox / _step_injected ever sees the deferred form.
+// SIM_DEVICE_RAW: entry points that read only the state copies / log ring, or continue the chain.
+#define SIM_DEVICE_RAW(s) PVD_CUDA(cudaSetDevice((s)->cfg.device))
+#define SIM_DEVICE(s)                                                \
+    do {                                                             \
+        PVD_CUDA(cudaSetDevice((s)->cfg.device));                    \
+        if (int rc__ = gather_flush(s)) return rc__;                 \
+    } while (0)
 
 // launch the potential of the configured kind on resident SoA walkers -> v[cur]
 static int launch_pot_soa(pvd_sim *s)
@@ -650,7 +662,7 @@ int pvd_sim_set_stream(pvd_sim *s, void *cuda_stream)
 int pvd_sim_sync(pvd_sim *s)
 {
     SIM_CHECK(s);
-    SIM_DEVICE(s);
+    SIM_DEVICE_RAW(s);
     PVD_CUDA(cudaStreamSynchronize(s->stream));
     return PVD_OK;
 }
@@ -679,8 +691,9 @@ int pvd_sim_init_finalize(pvd_sim *s)
 int pvd_sim_upload(pvd_sim *s, const double *xyz, int64_t n, const double *w)
 {
     SIM_CHECK(s);
-    SIM_DEVICE(s);
+    SIM_DEVICE_RAW(s);
     PVD_REQUIRE(xyz && n >= 1 && n <= s->cap, "pvd_sim_upload: n must be in [1, capacity]");
+    s->deferred = false;                                      // whatever chain was open belonged to the ensemble that is replaced
     const int nc = s->nc;
     PVD_CUDA(cudaStreamSynchronize(s->stream));
     PVD_CUDA(s->stage.alloc((size_t)n * nc * 8));
@@ -1019,13 +1032,7 @@ static int enqueue_gather_segment(pvd_sim *s, long long nsteps, int do_branch, c
         s->gather_grid = grid;
         s->gather_id = gv.id;
     }
-    const int buf0 = s->cur;
-    MaterialiseArgs m{};
-    for (int b = 0; b < 2; ++b) {
-        m.x[b] = s->x[b].as<double>(); m.v[b] = s->v[b].as<double>(); m.who[b] = s->who[b].as<int>();
-        m.cnt[b] = s->g_cnt[b].as<int>(); m.tincl[b] = s->g_tincl[b].as<int>(); m.cbase[b] = s->g_cbase[b].as<int>();
-        m.meta[b] = s->g_meta[b].as<GatherMeta>();
-    }
+    if (!s->deferred) { s->defer_buf0 = s->cur; s->defer_steps = 0; }
     for (long long k = 0; k < nsteps; ++k) {
         StepArgs a = make_args(s, do_branch);
         a.inj_disp = inj_disp;
@@ -1036,7 +1043,7 @@ static int enqueue_gather_segment(pvd_sim *s, long long nsteps, int do_branch, c
         g.tincl_in = s->g_tincl[in].as<int>(); g.tincl_out = s->g_tincl[out].as<int>();
         g.cbase_in = s->g_cbase[in].as<int>(); g.cbase_out = s->g_cbase[out].as<int>();
         g.meta_in = s->g_meta[in].as<GatherMeta>(); g.meta_out = s->g_meta[out].as<GatherMeta>();
-        g.deferred_in = k > 0 ? 1 : 0;
+        g.deferred_in = s->defer_steps > 0 ? 1 : 0;
         static const int stagger = [] { const char *e = getenv("PVD_GATHER_STAGGER_NS"); return e ? atoi(e) : 0; }();
         g.stagger_ns = stagger;
         g.seg_step0 = s->g_seg.as<long long>();     // the step counter the segment starts from stays on the device (no host synchronisation)
@@ -1044,17 +1051,35 @@ static int enqueue_gather_segment(pvd_sim *s, long long nsteps, int do_branch, c
         PVD_CHECK_LAUNCH();
         s->cur ^= 1;
         s->parity ^= 1;
+        s->defer_steps += 1;
+        s->deferred = true;
+    }
+    return PVD_OK;
+}
+
+// Closes an open chain of deferred-compaction steps: one k_gather_materialise leaves the ensemble compacted in x[cur], exactly
+// what the same number of k_step_discrete launches would have left (also when the run died inside the chain).
+static int gather_flush(pvd_sim *s)
+{
+    if (!s->deferred) return PVD_OK;
+    MaterialiseArgs m{};
+    for (int b = 0; b < 2; ++b) {
+        m.x[b] = s->x[b].as<double>(); m.v[b] = s->v[b].as<double>(); m.who[b] = s->who[b].as<int>();
+        m.cnt[b] = s->g_cnt[b].as<int>(); m.tincl[b] = s->g_tincl[b].as<int>(); m.cbase[b] = s->g_cbase[b].as<int>();
+        m.meta[b] = s->g_meta[b].as<GatherMeta>();
     }
     m.st = s->st.as<DevState>();
     m.cap = s->cap;
     m.nc = s->nc;
     m.parity_end = s->parity;
-    m.buf0 = buf0;
+    m.buf0 = s->defer_buf0;
     m.seg_step0 = s->g_seg.as<long long>();
     const int mg = grid_for(s->cap, PVD_CTA, 8);
     PVD_CUDA(launch_pdl(k_gather_materialise, dim3((unsigned)mg), dim3(PVD_CTA), (size_t)(s->gather_grid + 2) * 4, s->stream, m));
     PVD_CHECK_LAUNCH();
     s->cur ^= 1;
+    s->deferred = false;
+    s->defer_steps = 0;
     return PVD_OK;
 }
 
@@ -1063,14 +1088,17 @@ extern "C" {
 int pvd_sim_run(pvd_sim *s, int64_t nsteps, int32_t branch_every)
 {
     SIM_CHECK(s);
-    SIM_DEVICE(s);
+    SIM_DEVICE_RAW(s);
     PVD_REQUIRE(s->uploaded, "pvd_sim_run: upload walkers first");
     PVD_REQUIRE(s->cfg.world_size == 1, "pvd_sim_run is single-shard; use step_local/step_finalize for multi-GPU");
     PVD_REQUIRE(branch_every >= 1, "branch_every must be >= 1");
     PVD_CUDA(cudaEventRecord(s->ev0, s->stream));
     const int do_branch = (branch_every == 1) ? 1 : -branch_every;       // negative: the kernel decides from its step counter
     const GatherVariant gv = gather_variant_for(s, s->resident_mode == 3);
-    if (s->resident_mode != 3 && run_variant_for(s).kern) {
+    const bool use_resident = s->resident_mode != 3 && run_variant_for(s).kern;
+    if (use_resident || !gv.kern)
+        if (int rc = gather_flush(s)) return rc;              // (an open chain of deferred-compaction steps ends here)
+    if (use_resident) {
         // discrete weighting with a built-in potential, small ensembles: the whole segment is ONE resident launch
         if (int rc = enqueue_run(s, nsteps, do_branch)) return rc;
     } else if (gv.kern) {
@@ -1096,7 +1124,7 @@ int pvd_sim_set_resident(pvd_sim *s, int32_t enable)
 int pvd_sim_last_run_ms(pvd_sim *s, double *ms)
 {
     SIM_CHECK(s);
-    SIM_DEVICE(s);
+    SIM_DEVICE_RAW(s);
     PVD_REQUIRE(ms, "NULL argument");
     PVD_CUDA(cudaEventSynchronize(s->ev1));
     float f = 0;
@@ -1108,7 +1136,9 @@ int pvd_sim_last_run_ms(pvd_sim *s, double *ms)
 int pvd_sim_step_injected(pvd_sim *s, const double *disp, const double *u_branch, const double *u_metro)
 {
     SIM_CHECK(s);
-    SIM_DEVICE(s);
+    SIM_DEVICE_RAW(s);
+    if (!(s->resident_mode == 3 && gather_variant_for(s, true).kern))
+        if (int rc = gather_flush(s)) return rc;              // (mode 3 continues an open chain: the injected steps exercise the pull)
     PVD_REQUIRE(s->uploaded && disp, "pvd_sim_step_injected: upload first / disp required");
     PVD_CUDA(cudaStreamSynchronize(s->stream));
     DevState h[2];
@@ -1330,13 +1360,15 @@ int pvd_sim_mailbox_connect(pvd_sim *s, const void *handles, int32_t n)
 int pvd_sim_run_mailbox(pvd_sim *s, int64_t nsteps, int32_t branch_every)
 {
     SIM_CHECK(s);
-    SIM_DEVICE(s);
+    SIM_DEVICE_RAW(s);
     PVD_REQUIRE(s->uploaded && s->mbox_connected, "pvd_sim_run_mailbox: upload walkers and connect the mailboxes first");
     PVD_REQUIRE(s->cfg.trial == PVD_TRIAL_NONE, "importance sampling needs two exchanges per step: use the split step with an all-reduce");
     PVD_REQUIRE(branch_every >= 1, "branch_every must be >= 1");
     const int cont = s->cfg.weighting == PVD_WEIGHT_CONTINUOUS ? 1 : 0;
     PVD_CUDA(cudaEventRecord(s->ev0, s->stream));
     const GatherVariant gv = gather_variant_for(s, s->resident_mode == 3);
+    if (!(!(s->resident_mode != 3 && run_variant_for(s).kern) && gv.kern))
+        if (int rc = gather_flush(s)) return rc;
     if (!(s->resident_mode != 3 && run_variant_for(s).kern) && gv.kern) {
         // large shards: deferred-compaction steps, the last CTA of each exchanges the sums through the mailboxes
         s->mbox_step = true;
@@ -1563,7 +1595,7 @@ int pvd_sim_dw_parent(pvd_sim *s, double *xyz, double *w, int64_t *n_parent)
 int pvd_sim_state(pvd_sim *s, int64_t *n, double *vref, int64_t *step, int32_t *err)
 {
     SIM_CHECK(s);
-    SIM_DEVICE(s);
+    SIM_DEVICE_RAW(s);
     PVD_CUDA(cudaStreamSynchronize(s->stream));
     DevState h[2];
     PVD_CUDA(cudaMemcpy(h, s->st.p, sizeof(h), cudaMemcpyDeviceToHost));
@@ -1688,7 +1720,7 @@ int pvd_sim_snapshot_wait(pvd_sim *s, double *xyz, double *pots, double *w, int6
 int pvd_sim_stats(pvd_sim *s, int64_t first_step, int64_t count, pvd_step_stats *out)
 {
     SIM_CHECK(s);
-    SIM_DEVICE(s);
+    SIM_DEVICE_RAW(s);
     PVD_REQUIRE(out && count >= 0 && count <= s->cfg.stats_ring && first_step >= 0, "pvd_sim_stats: bad range");
     PVD_CUDA(cudaStreamSynchronize(s->stream));
     const long long L = s->cfg.stats_ring;
