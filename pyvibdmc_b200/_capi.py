@@ -177,6 +177,8 @@ def load(rebuild_if_stale=True):
         except Exception as e:  # no nvcc on the box and no prebuilt library
             if not os.path.exists(path):
                 raise PvdError(f"libpvd_b200.so is missing and could not be built: {e}") from e
+            import warnings
+            warnings.warn(f"libpvd_b200.so is older than its sources and could not be rebuilt ({e}): using the stale library", RuntimeWarning)
     if not os.path.exists(path):
         raise PvdError(f"CUDA extension not found at {path}; run `python -m pyvibdmc_b200.build`")
     try:

@@ -26,25 +26,60 @@ def sources():
                   [os.path.join(HERE, "..", "include", "pvd_b200.h")])
 
 
+def source_hash():
+    """sha256 over the sources the library is built from (what decides staleness: file times do not survive a fresh checkout
+    or a snapshot to another machine)."""
+    import hashlib
+    h = hashlib.sha256()
+    for path in sources():
+        h.update(os.path.basename(path).encode())
+        with open(path, "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
 def is_stale():
     if not os.path.exists(LIB):
         return True
+    stamp = LIB + ".srchash"
+    if os.path.exists(stamp):
+        try:
+            return open(stamp).read().strip() != source_hash()
+        except OSError:
+            pass
     t = os.path.getmtime(LIB)
     return any(os.path.getmtime(s) > t for s in sources())
 
 
 def build_library(force=False, verbose=False):
-    """Compile csrc/pvd_b200.cu -> _lib/libpvd_b200.so.  nvcc cross-compiles without a GPU."""
+    """Compile csrc/pvd_b200.cu -> _lib/libpvd_b200.so.  nvcc cross-compiles without a GPU.  Safe when several processes
+    (torchrun ranks) call it at once: one of them builds, under a file lock, into a temporary file that replaces the library
+    atomically; the others wait and find it fresh."""
     if not force and not is_stale():
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
-    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
-    cmd = [_nvcc()] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, os.path.join(CSRC, "pvd_b200.cu")]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
+    import fcntl
+    with open(os.path.join(LIBDIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not is_stale():          # another process built it while this one waited
+                return LIB
+            flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+            tmp = LIB + f".tmp{os.getpid()}"
+            cmd = [_nvcc()] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp, os.path.join(CSRC, "pvd_b200.cu")]
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+            os.replace(tmp, LIB)
+            with open(LIB + ".srchash", "w") as f:
+                f.write(source_hash())
+            if verbose:
+                print(res.stderr)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB
 
 

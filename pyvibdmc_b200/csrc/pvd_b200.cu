@@ -618,8 +618,21 @@ int pvd_sim_create(const pvd_config *cfg, pvd_sim **out)
     TRY(s->sigma_dev.alloc(PVD_MAX_ATOMS * 8));
     TRY(cudaMemcpy(s->sigma_dev.p, s->sigma, PVD_MAX_ATOMS * 8, cudaMemcpyHostToDevice));
     s->nn_grid = grid_for(cap, NN_TILE, 3);
+    // staging for host <-> device transposes (uploads, downloads): allocated once, not inside a timed upload / download
+    TRY(s->stage.alloc((size_t)cap * nc * 8));
     TRY(cudaEventCreate(&s->ev0));
     TRY(cudaEventCreate(&s->ev1));
+    if (cfg->weighting == PVD_WEIGHT_DISCRETE && cfg->trial == PVD_TRIAL_NONE &&
+        (cfg->potential == PVD_POT_H2O_PS || cfg->potential == PVD_POT_HARMONIC || cfg->potential == PVD_POT_MORSE1D)) {
+        // buffers of the deferred-compaction step (pvd_gather.cuh), so that the first segment does not allocate
+        for (int b = 0; b < 2; ++b) {
+            TRY(s->g_cnt[b].alloc((size_t)cap * 4));
+            TRY(s->g_tincl[b].alloc((size_t)ntiles * 4));
+            TRY(s->g_cbase[b].alloc((size_t)(PVD_GATHER_MAX_GRID + 2) * 4));
+            TRY(s->g_meta[b].alloc(sizeof(GatherMeta)));
+        }
+        TRY(s->g_seg.alloc(16));
+    }
 #undef TRY
     *out = s;
     return PVD_OK;

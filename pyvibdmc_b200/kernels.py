@@ -265,6 +265,11 @@ class DeviceSim:
                  thresh_lower=None, thresh_upper=None, device=0, rank=0, world_size=1, stats_ring=1 << 16,
                  imp_variant=_capi.IMP_STANDARD):
         cfg = _capi.PvdConfig()
+        if not (1 <= int(natoms) <= _capi.MAX_ATOMS) or not (1 <= int(ndim) <= 3) or int(natoms) * int(ndim) > _capi.MAX_COMP:
+            raise ValueError(f"DeviceSim: {natoms} atoms x {ndim} dimensions is outside what the device path holds "
+                             f"(1..{_capi.MAX_ATOMS} atoms, 1..3 dimensions, at most {_capi.MAX_COMP} components)")
+        if len(np.asarray(masses).reshape(-1)) < int(natoms):
+            raise ValueError(f"DeviceSim: {natoms} atoms need {natoms} masses")
         cfg.natoms, cfg.ndim = int(natoms), int(ndim)
         cfg.weighting = _capi.WEIGHT_CONTINUOUS if weighting == "continuous" else _capi.WEIGHT_DISCRETE
         cfg.potential, cfg.trial, cfg.rng_mode = int(potential), int(trial), int(rng_mode)

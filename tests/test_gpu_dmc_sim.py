@@ -424,3 +424,25 @@ def test_restart_inside_descendant_weighting_window(pv, tmp_path, weighting):
         assert np.all(w['desc_wts'][~alive] == 0) and w['desc_wts'][alive].sum() == w['desc_wts'].sum()
     else:
         assert abs(w['desc_wts'].sum() - info['pop_vs_tau'][169, 1]) < 1e-6 * 2000 and 'parent_wts' in w
+
+
+def test_water_zpe_matches_shipped_reference_runs_statistically(pv):
+    """north_star: "full runs must reproduce the reference's zero-point energy within combined statistical error".  Five seeds
+    at the size of the reference's own shipped tutorial runs (8 000 walkers x 5 000 steps, dt = 5; their five
+    `tutorial_water_*_sim_info.hdf5` give 4634.1 cm-1 with a run-to-run sigma of 2.2): the means must agree within
+    three combined standard errors.  Deterministic: Philox streams and exact sums make every seed bit-reproducible."""
+    K, capi = pv.kernels, pv._capi
+    m = [pv.Constants.mass('H'), pv.Constants.mass('H'), pv.Constants.mass('O')]
+    zpes = []
+    for seed in range(5):
+        sim = K.DeviceSim(3, 3, m, 8000, 5.0, capi.POT_H2O_PS, seed=1000 + seed)
+        sim.upload(np.repeat(EQ[None] * 1.01, 8000, axis=0))
+        sim.run(5000)
+        zpes.append(sim.stats(0, 5000)["vref"][1000:].mean() / WN)
+        sim.close()
+    zpes = np.array(zpes)
+    ours, sem_ours = zpes.mean(), zpes.std(ddof=1) / np.sqrt(len(zpes))
+    ref, sem_ref = 4634.1, 2.2 / np.sqrt(5)
+    sigma = np.sqrt(sem_ours ** 2 + sem_ref ** 2)
+    assert abs(ours - ref) < 3.0 * sigma, (ours, sem_ours, zpes, sigma)
+    assert zpes.std(ddof=1) < 6.0, zpes                       # single-run scatter of the same size as the reference's (2.2)
