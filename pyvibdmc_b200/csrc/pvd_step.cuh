@@ -459,10 +459,12 @@ __device__ __forceinline__ bool step_prologue(const StepArgs &a)
         if (blockIdx.x == 0 && threadIdx.x == 0) forward_dead_state(a);
         return false;
     }
-    if (sip->n <= 0) {
+    if (sip->n <= 0 && a.world == 1) {
         if (blockIdx.x == 0 && threadIdx.x == 0) { forward_dead_state(a); a.st[a.parity ^ 1].err |= PVD_ERR_EMPTY; }
         return false;
     }
+    // (several GPUs: a shard that has run empty takes part in the step with zero tiles -- its peers wait for its message, and the
+    // next rebalancing refills it; only an empty WORLD is an error, raised by finalize_from_sums on every rank at once)
     return true;
 }
 
