@@ -26,7 +26,11 @@
 // tile's coordinates (100.8), three CTAs per SM at 80 registers with 16 bytes of spills (96.7), odd warps started half a
 // tile late (90.8 .. 94.5), and an "early start" protocol in which step k+1 starts on a software flag as soon as step k's
 // prefix is published and only its copy-count stage waits for Vref(k) (96.0: the two GPU-scope fences and the polling
-// cost more than the hardware's dependent-launch hand-over saves; it won 2 us at 200 000 walkers).
+// cost more than the hardware's dependent-launch hand-over saves; it won 2 us at 200 000 walkers).  For several GPUs a variant in which a
+// step only POSTS its sums and warp 0 of the next kernel's CTA 0 collects and finalises while every other warp already works on its first
+// tile (verdict awaited at the copy-count stage, first tile's coordinates parked in shared memory) did overlap the exchange (2 GPUs:
+// 128.6 -> 119.1 us with the same binary) but the extra state made the MULTI instantiation spill at its 128-register limit, which cost
+// more than the overlap won (105-107 us for the posted-and-collected-in-place exchange that is in the tree).
 #pragma once
 #include "pvd_step.cuh"
 
