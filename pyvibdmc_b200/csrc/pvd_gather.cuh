@@ -420,7 +420,7 @@ __global__ void __launch_bounds__(PVD_CTA, MINB) k_step_gather(const StepArgs a,
             g.cnt_out[o] = cnt;
             // running sums of this lane: the exact (fixed-point) ones live in shared memory, not in registers -- the
             // kernel is bounded by how many warps an SM holds
-            const Fx128 fv = fx_from_double(v);
+            const Fx128 fv = fx_from_double_fast(v);       // (same value as fx_from_double for every |V| >= 2^-27 Hartree: pvd_run.cuh)
             ulonglong2 sv = s_acc_v[threadIdx.x];
             const Fx128 nv = fx_add(Fx128{(long long)sv.y, sv.x}, fv);
             s_acc_v[threadIdx.x] = make_ulonglong2(nv.lo, (unsigned long long)nv.hi);
