@@ -39,6 +39,20 @@ def main():
                "pop_at_window_start": float(pop[299]), "final_walkers": int(len(walkers)), "final_pop": float(pop[-1]),
                "chkpts": sorted(os.path.basename(p) for p in glob.glob(f"{out}/chkpts/*.pickle")),
                "log_has_steps": "Time step 500" in open(f"{out}/w2_log.txt").read()}
+    # restart under torchrun: every rank reloads rank 0's checkpoint; world, rank, GPU and the scratch folder of
+    # ranks > 0 are re-detected, the continued run is sharded again
+    dist.barrier()
+    sim2 = pv.dmc_restart(potential=pot, chkpt_folder=out, sim_name="w2", additional_timesteps=100)
+    assert sim2._world == dist.get_world_size() and sim2._rank == rank and sim2._device == local
+    assert (sim2.output_folder == out) == (rank == 0)
+    sim2.run()
+    n2 = len(sim2.walkers)
+    if rank == 0:
+        info2 = h5lite.read_h5(f"{out}/w2_sim_info.hdf5")
+        res["restart_vref_shape"] = list(info2['vref_vs_tau'].shape)
+        res["restart_final_walkers"] = int(n2)
+        res["restart_final_pop"] = float(info2['pop_vs_tau'][-1, 1])
+        res["restart_zpe"] = float(info2['vref_vs_tau'][300:, 1].mean() / 4.556335281212229e-6)
         print("RESULT " + json.dumps(res))
     dist.destroy_process_group()
 

@@ -48,3 +48,5 @@ def test_two_gpu_dmc_sim_drop_in(tmp_path):
     assert r["n_parent"] == int(r["pop_at_window_start"]) and r["desc_sum"] == r["pop_at_window_end"]
     assert r["final_walkers"] == int(r["final_pop"]) and 4400 < r["zpe"] < 4850
     assert len(r["chkpts"]) >= 1
+    # dmc_restart under torchrun stays sharded (world / rank / GPU re-detected) and extends the histories
+    assert r["restart_vref_shape"] == [700, 2] and r["restart_final_walkers"] == int(r["restart_final_pop"]) and 4400 < r["restart_zpe"] < 4850
