@@ -1,6 +1,6 @@
 """ImpSamp: drift / Metropolis / local kinetic energy with the reference's call signatures
-(simulation_utilities/imp_samp.py:5-76), evaluated by the CUDA kernels for the problem shapes the
-library is built for (3 atoms x 3 dims, 1 x 1); DMC_Sim itself never calls these per step on the
+(simulation_utilities/imp_samp.py:5-76), evaluated by the CUDA kernels for any (walkers, atoms, dims) ensemble up to 16 atoms (compile-time
+instances for 3 atoms x 3 dims and 1 x 1, a run-time-shaped kernel otherwise); DMC_Sim itself never calls these per step on the
 built-in path -- the whole importance-sampled step runs in k_imp_move -- they are the plug-in level
 entry points and what the parity tests exercise."""
 import numpy as np
@@ -27,11 +27,10 @@ class ImpSamp:
     def metropolis(sigma_trip, trial_x, trial_y, disp_x, disp_y, D_x, D_y, dt):
         """Acceptance ratios (imp_samp.py:29-47).  D_x = inv_mass * f_x as in the reference."""
         x = np.asarray(disp_x, dtype=np.float64)
-        if x.ndim != 3 or x.shape[1:] not in ((3, 3), (1, 1)):
-            raise NotImplementedError("metropolis kernel is built for (N,3,3) and (N,1,1) ensembles")
-        natoms = x.shape[1]
-        sig = np.asarray(sigma_trip, dtype=np.float64).reshape(-1)
-        sig = sig[::3][:natoms] if sig.size == 3 * natoms else sig[:natoms]
+        if x.ndim != 3:
+            raise ValueError("metropolis expects (walkers, atoms, dims) arrays")
+        natoms, ndim = x.shape[1:]
+        sig = ImpSamp._per_atom(sigma_trip, natoms, ndim)
         # the kernel takes the drift f and inv_mass separately; pass D with inv_mass = 1
         return _K.metropolis(x, disp_y, D_x, D_y, np.asarray(trial_x).reshape(-1), np.asarray(trial_y).reshape(-1),
                              sig, np.ones(natoms), dt)
@@ -40,10 +39,17 @@ class ImpSamp:
     def local_kin(inv_masses_trip, sec_deriv):
         """-1/2 sum (1/m) d2psi/psi (imp_samp.py:50-53)."""
         d2 = np.asarray(sec_deriv, dtype=np.float64)
-        natoms = d2.shape[1]
-        inv_m = np.asarray(inv_masses_trip, dtype=np.float64).reshape(-1)
-        inv_m = inv_m[::3][:natoms] if inv_m.size == 3 * natoms else inv_m[:natoms]
-        return _K.local_kin(d2, inv_m)
+        natoms, ndim = d2.shape[1:]
+        return _K.local_kin(d2, ImpSamp._per_atom(inv_masses_trip, natoms, ndim))
+
+    @staticmethod
+    def _per_atom(trip, natoms, ndim):
+        """The reference carries per-atom constants repeated over the dimensions ((atoms, dims) 'trip' arrays,
+        pyvibdmc.py:236-240); the kernels take one value per atom."""
+        t = np.asarray(trip, dtype=np.float64).reshape(-1)
+        if t.size == natoms * ndim and ndim > 1:
+            return np.ascontiguousarray(t.reshape(natoms, ndim)[:, 0])
+        return np.ascontiguousarray(t[:natoms])
 
     @staticmethod
     def finite_diff(cds, trial_func):

@@ -141,6 +141,11 @@ def test_metropolis_and_local_kin_any_shape(K, oracle):
         assert np.allclose(got, ref, rtol=1e-11, atol=0), (na, nd)
         assert np.array_equal(got == 0.0, ref == 0.0)
         assert np.allclose(K.local_kin(sec, inv), oracle.local_kin(inv_trip, sec), rtol=1e-14, atol=0), (na, nd)
+        # the reference-facing class (same signature as imp_samp.py:29-53: 'trip' constants, D = inv_mass * f)
+        from pyvibdmc_b200.simulation_utilities.imp_samp import ImpSamp
+        cls = ImpSamp.metropolis(np.array(sig_trip[0]), psx, psy, x, y, inv_trip * fx, inv_trip * fy, 1.0)
+        assert np.allclose(cls, ref, rtol=1e-11, atol=0), (na, nd)
+        assert np.allclose(ImpSamp.local_kin(np.array(inv_trip[0]), sec), oracle.local_kin(inv_trip, sec), rtol=1e-14, atol=0), (na, nd)
 
 
 def test_device_to_device_walker_transfer(K, oracle):
