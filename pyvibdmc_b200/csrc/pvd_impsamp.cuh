@@ -48,16 +48,37 @@ struct TrialH2O {
     static constexpr int NC = 9;
     static constexpr int NDIM = 3;
     static constexpr bool ANALYTIC = false;
-    __device__ static __forceinline__ double psi(const double (&x)[9], const TrialParamsDev &p)
+    // a finite-difference stencil point that moves ONE hydrogen leaves the other O-H bond (its length and its table value)
+    // untouched: psi_moved<0 / 1> takes them from `keep` -- the same operations on the same operands, hence the same bits as a
+    // full evaluation -- and a third of the stencil's square roots and table look-ups disappear (trial_drift_ke)
+    static constexpr bool PARTIAL = true;
+    struct Bond { double r, t; };
+    template <int WHICH>                                 // 0: H1-O, 1: H2-O
+    __device__ static __forceinline__ Bond bond(const double (&x)[9], const TrialParamsDev &p)
+    {
+        Bond b;
+        b.r = norm3(x[3 * WHICH] - x[6], x[3 * WHICH + 1] - x[7], x[3 * WHICH + 2] - x[8]);
+        b.t = interp_table(b.r, p);
+        return b;
+    }
+    // MOVED: 0 = H1 moved since `keep` (= bond<1>) was formed, 1 = H2 moved (keep = bond<0>), 2 = evaluate everything
+    template <int MOVED>
+    __device__ static __forceinline__ double psi_moved(const double (&x)[9], const TrialParamsDev &p, const Bond &keep)
     {
         const double ax = x[0] - x[6], ay = x[1] - x[7], az = x[2] - x[8];      // H1 - O
         const double bx = x[3] - x[6], by = x[4] - x[7], bz = x[5] - x[8];      // H2 - O
-        const double r1 = norm3(ax, ay, az), r2 = norm3(bx, by, bz);
+        double r1, r2, t1, t2;
+        if (MOVED == 1) { r1 = keep.r; t1 = keep.t; } else { r1 = norm3(ax, ay, az); t1 = interp_table(r1, p); }
+        if (MOVED == 0) { r2 = keep.r; t2 = keep.t; } else { r2 = norm3(bx, by, bz); t2 = interp_table(r2, p); }
         const double dot = __dadd_rn(__dadd_rn(__dmul_rn(ax, bx), __dmul_rn(ay, by)), __dmul_rn(az, bz));
         const double th = acos(dot / __dmul_rn(r1, r2));
         const double dth = th - p.theta_eq;
         const double ang = __dmul_rn(p.ang_pref, exp(__dmul_rn(-p.ang_alpha, __dmul_rn(dth, dth)) / 2.0));
-        return __dmul_rn(__dmul_rn(interp_table(r1, p), interp_table(r2, p)), ang);
+        return __dmul_rn(__dmul_rn(t1, t2), ang);
+    }
+    __device__ static __forceinline__ double psi(const double (&x)[9], const TrialParamsDev &p)
+    {
+        return psi_moved<2>(x, p, Bond{0.0, 0.0});
     }
 };
 
@@ -68,6 +89,7 @@ struct TrialH2OAn {
     static constexpr int NC = 9;
     static constexpr int NDIM = 3;
     static constexpr bool ANALYTIC = true;
+    static constexpr bool PARTIAL = false;
     __device__ static __forceinline__ double psi(const double (&x)[9], const TrialParamsDev &p) { return TrialH2O::psi(x, p); }
     __device__ static __forceinline__ void derivs(const double (&x)[9], const TrialParamsDev &p, double &psi0, double (&d1)[9], double (&d2)[9])
     {
@@ -130,6 +152,7 @@ struct TrialHarm1D {
     static constexpr int NC = 1;
     static constexpr int NDIM = 1;
     static constexpr bool ANALYTIC = true;
+    static constexpr bool PARTIAL = false;
     __device__ static __forceinline__ double psi(const double (&x)[1], const TrialParamsDev &p)
     {
         return __dmul_rn(p.h_pref, exp(__dmul_rn(-p.h_alpha, __dmul_rn(x[0], x[0])) / 2.0));
@@ -213,6 +236,52 @@ __device__ __forceinline__ void trial_drift_ke(double (&xx)[TRIAL::NC], const Tr
         double d2[NC];
         TRIAL::derivs(xx, p, psi0, d1, d2);
         ke = local_kinetic<NC, ND>(d2, inv_mass);
+    } else if constexpr (TRIAL::PARTIAL) {
+        // atom by atom (compile time), dimension by dimension (run time): the selects that stand in for a dynamic register
+        // index span the moved atom's three coordinates only, and the bond that atom is not part of is evaluated once per atom
+        static_assert(NC == 9 && ND == 3, "partial stencil: three atoms in three dimensions");
+        psi0 = TRIAL::psi(xx, p);
+        double sd[ND] = {0.0, 0.0, 0.0};
+        typename TRIAL::Bond keep = TRIAL::template bond<1>(xx, p);
+#pragma unroll
+        for (int atom = 0; atom < 3; ++atom) {
+            if (atom == 1) keep = TRIAL::template bond<0>(xx, p);          // H1 as the walk over its coordinates left it
+#pragma unroll 1
+            for (int d = 0; d < ND; ++d) {
+                double orig = 0.0;
+#pragma unroll
+                for (int k = 0; k < ND; ++k) orig = (k == d) ? xx[3 * atom + k] : orig;
+                const double lo = orig - p.fd_dx;
+                const double hi = lo + 2.0 * p.fd_dx;
+#pragma unroll
+                for (int k = 0; k < ND; ++k) xx[3 * atom + k] = (k == d) ? lo : xx[3 * atom + k];
+                double pm, pp;
+                if (atom == 0) pm = TRIAL::template psi_moved<0>(xx, p, keep);
+                else if (atom == 1) pm = TRIAL::template psi_moved<1>(xx, p, keep);
+                else pm = TRIAL::template psi_moved<2>(xx, p, keep);
+#pragma unroll
+                for (int k = 0; k < ND; ++k) xx[3 * atom + k] = (k == d) ? hi : xx[3 * atom + k];
+                if (atom == 0) pp = TRIAL::template psi_moved<0>(xx, p, keep);
+                else if (atom == 1) pp = TRIAL::template psi_moved<1>(xx, p, keep);
+                else pp = TRIAL::template psi_moved<2>(xx, p, keep);
+#pragma unroll
+                for (int k = 0; k < ND; ++k) xx[3 * atom + k] = (k == d) ? hi - p.fd_dx : xx[3 * atom + k];   // the walked value
+                const double first = (pp - pm) / (2.0 * p.fd_dx);
+                const double sec = __dadd_rn(__dadd_rn(pm, -__dmul_rn(2.0, psi0)), pp) / p.fd_dx2;
+                const double term = __dmul_rn(inv_mass[atom], sec / psi0);
+#pragma unroll
+                for (int k = 0; k < ND; ++k) {
+                    if (k == d) {
+                        d1[3 * atom + k] = first / psi0;
+                        sd[k] = (atom == 0) ? term : __dadd_rn(sd[k], term);
+                    }
+                }
+            }
+        }
+        double tot = sd[0];
+#pragma unroll
+        for (int d = 1; d < ND; ++d) tot = __dadd_rn(tot, sd[d]);
+        ke = __dmul_rn(-0.5, tot);
     } else {
         psi0 = TRIAL::psi(xx, p);
         double sd[ND];

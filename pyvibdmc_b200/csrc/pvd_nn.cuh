@@ -185,6 +185,29 @@ __device__ __forceinline__ float swish_fast(float z)
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
     return z * r;
 }
+// Two activations with ONE reciprocal: z0 / (1 + e0) = z0 (1 + e1) / ((1 + e0)(1 + e1)): three SFU instructions per pair instead
+// of four (the XU pipe is this kernel's busiest: 58 % in profiles/r01_profiles.md) for two caps and four more FMA-pipe
+// multiplies (the exponent is capped at 60 so that the product of the denominators stays finite).  TRIED AND REJECTED
+// (profiles/r02_s3.txt): the stand-alone kernel went from 0.704 to 0.775 ms per 2e6 walkers -- the epilogue is bound by issue
+// slots and the dependency chain of a lane's 16 activations, not by the SFU's throughput.  Kept behind the switch as the record.
+#ifndef PVD_NN_SWISH_PAIR
+#define PVD_NN_SWISH_PAIR 0
+#endif
+__device__ __forceinline__ void swish_fast2(float z0, float z1, float &h0, float &h1)
+{
+#if PVD_NN_SWISH_PAIR
+    float e0, e1, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fminf(z0 * -1.4426950408889634f, 60.0f)));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fminf(z1 * -1.4426950408889634f, 60.0f)));
+    const float a0 = 1.0f + e0, a1 = 1.0f + e1;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a0 * a1));
+    h0 = (z0 * a1) * r;
+    h1 = (z1 * a0) * r;
+#else
+    h0 = swish_fast(z0);
+    h1 = swish_fast(z1);
+#endif
+}
 // eight consecutive k values of one row -> one 16-byte store per piece
 __device__ __forceinline__ void store_chunk(unsigned char *sA, uint32_t off, const float (&h)[8])
 {
@@ -507,9 +530,10 @@ k_nn_h4o2_tc2(const double *__restrict__ xyz, int soa, long long cap, const DevS
                 if (ch + 1 < COLS / 16) tmem_ld16_nowait(tD + lane_sel + (uint32_t)(col0 + 16), r[(ch + 1) & 1]);
                 float h[16];
 #pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                    h[e] = swish_fast(__uint_as_float(r[ch & 1][e]) + bias[col0 + e]);
-                    if (layer == 2) out = fmaf(h[e], s_vec[3 * 128 + col0 + e], out);
+                for (int e = 0; e < 16; e += 2) {
+                    swish_fast2(__uint_as_float(r[ch & 1][e]) + bias[col0 + e], __uint_as_float(r[ch & 1][e + 1]) + bias[col0 + e + 1],
+                                h[e], h[e + 1]);
+                    if (layer == 2) out = fmaf(h[e + 1], s_vec[3 * 128 + col0 + e + 1], fmaf(h[e], s_vec[3 * 128 + col0 + e], out));
                 }
                 if (layer < 2) {
                     uint32_t w1[8], w2[8];

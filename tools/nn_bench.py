@@ -19,7 +19,7 @@ w = np.load(os.path.join(os.path.dirname(K.__file__), "sample_potentials", "Tens
 K.nn_h4o2_set_weights(w)
 out = {}
 for mode in ("tcgen05", "cuda_cores"):
-    os.environ["PVD_NN_FP32"] = "1" if mode == "cuda_cores" else "0"
+    K.nn_config(path=mode)
     best = 1e9
     for _ in range(4):
         v = K.nn_h4o2(x)
