@@ -8,6 +8,7 @@ static ContArgs make_cont_args(pvd_sim *s)
     ca.w = s->w.as<double>();
     ca.v = s->v[s->cur].as<double>();
     ca.kill_idx = s->kill_idx.as<int>();
+    ca.kill_mask = s->kill_mask.as<unsigned>();
     ca.copy_dst = s->copy_dst.as<int>();
     ca.copy_src = s->copy_src.as<int>();
     ca.cand = s->cand.as<ContCand>();
@@ -63,7 +64,6 @@ static int cont_enqueue_branch_only(pvd_sim *s, StepArgs &a, long long *src_out)
 {
     cont_in_place(s, a);
     ContArgs ca = make_cont_args(s);
-    ca.tile = PVD_TILE * ContFromMemory::SUB;
     PVD_CUDA(launch_pdl(k_cont_update<ContFromMemory>, dim3((unsigned)s->grid_light), dim3(PVD_CTA), 0, s->stream, a, ca));
     PVD_CHECK_LAUNCH();
     return cont_launch_tail(s, a, ca, src_out);
@@ -78,9 +78,9 @@ static int cont_enqueue_step(pvd_sim *s, StepArgs &a)
 #define LAUNCH_CONT(POT)                                                                                             \
     do {                                                                                                             \
         const int gp = POT::MIN_CTAS >= 4 ? s->grid_light : s->grid;                                                 \
-        if (fast) { ca.tile = PVD_TILE * ContFused<POT, PVD_RNG_FAST>::SUB; PVD_CUDA(launch_pdl(k_cont_update<ContFused<POT, PVD_RNG_FAST>>, dim3((unsigned)gp), dim3(PVD_CTA), 0, s->stream, a, ca)); } \
-        else if (s->cfg.rng_mode == PVD_RNG_ZIGGURAT) { ca.tile = PVD_TILE * ContFused<POT, PVD_RNG_ZIGGURAT>::SUB; PVD_CUDA(launch_pdl(k_cont_update<ContFused<POT, PVD_RNG_ZIGGURAT>>, dim3((unsigned)gp), dim3(PVD_CTA), 0, s->stream, a, ca)); } \
-        else { ca.tile = PVD_TILE * ContFused<POT, PVD_RNG_FP64>::SUB; PVD_CUDA(launch_pdl(k_cont_update<ContFused<POT, PVD_RNG_FP64>>, dim3((unsigned)gp), dim3(PVD_CTA), 0, s->stream, a, ca)); }      \
+        if (fast) { PVD_CUDA(launch_pdl(k_cont_update<ContFused<POT, PVD_RNG_FAST>>, dim3((unsigned)gp), dim3(PVD_CTA), 0, s->stream, a, ca)); } \
+        else if (s->cfg.rng_mode == PVD_RNG_ZIGGURAT) { PVD_CUDA(launch_pdl(k_cont_update<ContFused<POT, PVD_RNG_ZIGGURAT>>, dim3((unsigned)gp), dim3(PVD_CTA), 0, s->stream, a, ca)); } \
+        else { PVD_CUDA(launch_pdl(k_cont_update<ContFused<POT, PVD_RNG_FP64>>, dim3((unsigned)gp), dim3(PVD_CTA), 0, s->stream, a, ca)); }      \
     } while (0)
     switch (s->cfg.potential) {
     case PVD_POT_H2O_PS: LAUNCH_CONT(PotH2O); break;

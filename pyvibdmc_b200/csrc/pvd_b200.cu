@@ -389,7 +389,7 @@ struct pvd_sim {
     bool dump_pending = false;
     long long dump_n = 0;
     DevBuf xfer;                                   // packed walkers on their way to / from another shard (device-to-device rebalancing)
-    DevBuf kill_idx, hist, cand, cand_sorted, bin_start, bin_fill, cont_work, copy_dst, copy_src, cont_queue, cont_root, cont_skip;
+    DevBuf kill_idx, kill_mask, hist, cand, cand_sorted, bin_start, bin_fill, cont_work, copy_dst, copy_src, cont_queue, cont_root, cont_skip;
     DevBuf trial_table, acc_count;
     DevBuf impx_y, impx_fy, impx_sec, impx_psiy, impx_invm;      // importance sampling with a user trial wave function (pvd_impext.cuh)
     NNDeviceWeights nn_w;
@@ -569,6 +569,7 @@ int pvd_sim_create(const pvd_config *cfg, pvd_sim **out)
     if (cfg->weighting == PVD_WEIGHT_CONTINUOUS) {
         TRY(s->w.alloc((size_t)cap * 8));
         TRY(s->kill_idx.alloc((size_t)cap * 4));
+        TRY(s->kill_mask.alloc(((size_t)cap / 32 + 16) * 4));
         TRY(s->hist.alloc(PVD_HIST_BINS * 4));
         TRY(cudaMemset(s->hist.p, 0, PVD_HIST_BINS * 4));
         TRY(s->cand.alloc((size_t)2 * cap * sizeof(ContCand)));       // candidates (fallback sort pads to a power of two)

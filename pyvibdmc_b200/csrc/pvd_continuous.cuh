@@ -4,10 +4,10 @@
 // ascending index order, overwritten by a copy of the CURRENT maximum-weight walker (first index on
 // ties), whose weight is halved and shared.  That loop is sequential by construction (argmax after
 // every halving).  Parallel-equivalent used here:
-//   1. k_cont_update   : weight update, exact sums over the surviving walkers, ascending kill list
-//                        (ticketed warp tiles + chained look-back scan, like the discrete step)
+//   1. k_cont_update   : weight update, exact sums over the surviving walkers, kill flags as one ballot word per
+//                        32 walkers (no warp waits for another: no ticket counter, no look-back scan)
 //                        and the log-spaced histogram (64 bins / octave) of the updated weights
-//   3. k_cont_prefix   : suffix sums of the histogram -> the bin that holds the K-th largest weight
+//   3. k_cont_prefix   : ascending kill list from the ballot words; suffix sums of the histogram -> the bin that holds the K-th largest weight
 //                        (K = number of kills) and, per bin, where its members start in the
 //                        candidate array
 //      k_cont_collect  : candidates = all walkers at or above that bin, bucketed by bin
@@ -49,6 +49,7 @@ struct ContArgs {
     double *w;
     const double *v;
     int *kill_idx;
+    unsigned *kill_mask;        // one ballot word per 32 walkers: who fell below the lower threshold in this step (k_cont_update)
     int *copy_dst, *copy_src;
     ContCand *cand;
     ContCand *sorted;           // candidates in (w desc, idx asc) order (ranked path)
@@ -59,7 +60,6 @@ struct ContArgs {
     long long cand_cap;
     double lower, upper;
     int has_upper;
-    int tile;                   // walkers per scan tile of the k_cont_update instance that ran
 };
 
 __device__ __forceinline__ int weight_bin(double w)
@@ -75,9 +75,8 @@ __device__ __forceinline__ double bin_lower_edge(int bin)
 }
 
 // ---- 1+2. weight update + kill list + exact sums + histogram of the updated weights (energies from memory: a.vin)
-// A tile is PVD_CONT_SUB sub-tiles of 32 walkers (lane l of sub-tile s owns walker tile*256 + s*32 + l): the
-// chained scan sustains only a few hundred tiles per microsecond, so light kernels use large tiles.  The kill
-// flags of a sub-tile are one ballot, which is also all the state the deferred scatter needs.
+// A tile is SUB sub-tiles of 32 walkers (lane l of sub-tile s owns walker tile * 32 SUB + s * 32 + l); the kill flags of a
+// sub-tile are one ballot.
 // Where the energy of walker i comes from: memory (external / NN / importance-sampled energies)...
 struct ContFromMemory {
     static constexpr int RNG_MODE = PVD_RNG_FP64;      // draws no normals
@@ -103,12 +102,17 @@ struct ContFused {
     }
 };
 
+#ifndef PVD_CONT_DYNAMIC
+#define PVD_CONT_DYNAMIC 0          // A/B: 1 = tiles from the global ticket counter (dynamic over the whole grid), 0 = contiguous chunk per CTA
+#endif
 template <class PROD>
 __global__ void __launch_bounds__(PVD_CTA, PROD::MIN_CTAS) k_cont_update(const StepArgs a, const ContArgs ca)
 {
     constexpr int SUB = PROD::SUB, TILE = PVD_TILE * SUB;
     __shared__ unsigned s_hist[PVD_HIST_BINS];
+    __shared__ unsigned s_ticket;
     for (int b = threadIdx.x; b < PVD_HIST_BINS; b += PVD_CTA) s_hist[b] = 0;
+    if (threadIdx.x == 0) s_ticket = 0u;
     if constexpr (PROD::RNG_MODE == PVD_RNG_ZIGGURAT) zig_stage();
     __syncthreads();
     pdl_wait();                                        // everything above is independent of the previous kernel
@@ -118,65 +122,59 @@ __global__ void __launch_bounds__(PVD_CTA, PROD::MIN_CTAS) k_cont_update(const S
     const double vref = sip->vref, dt = sip->dt_eff;
     const long long ntiles = (n + TILE - 1) / TILE;
     const int lane = threadIdx.x & 31;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    unsigned *tickets = step_tickets(a, a.parity);
+    // No warp waits for another: a tile leaves its kill flags as one ballot word per 32 walkers (kill_mask, bit l of word
+    // i / 32 = walker i), and the ascending kill list is made from the words afterwards (k_cont_prefix).  Tiles are dealt to
+    // CTAs in contiguous chunks, the warps of a CTA share their chunk through a shared-memory ticket: no global ticket
+    // counter (one atomic per 2.5 ns at best: 31 250 tiles of a 1e6-walker H2O step kept it busy for most of the step) and no
+    // chained look-back over tile totals, which is what the deferred-compaction step did for discrete weighting (pvd_gather.cuh).
     LaneAcc acc;
+#if PVD_CONT_DYNAMIC
+    unsigned *tickets = step_tickets(a, a.parity);
     TileFeed feed;
-    long long pend = -1;
-    int pend_total = 0;
-    unsigned pend_mask[SUB];
     long long tile = feed_next(feed, tickets, ntiles, 1);
+    while (tile >= 0) {
+        const unsigned issued = feed_issue(feed, tickets);     // the next ticket travels while this tile is computed
+#else
+    const long long t_lo = (ntiles * (long long)blockIdx.x) / gridDim.x, t_hi = (ntiles * ((long long)blockIdx.x + 1)) / gridDim.x;
     while (true) {
-        unsigned mask[SUB];
-        int total = 0;
-        unsigned issued = 0u;
-        if (tile >= 0) {
+        unsigned t = 0;
+        if (lane == 0) t = atomicAdd(&s_ticket, 1u);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        const long long tile = t_lo + t;
+        if (tile >= t_hi) break;
+#endif
 #pragma unroll
-            for (int s = 0; s < SUB; ++s) {
-                const long long i = tile * TILE + s * PVD_TILE + lane;
-                bool kill = false;
-                if (i < n) {
-                    const double v = PROD::produce(a, i, step);
-                    const double wn = __dmul_rn(ca.w[i], exp(__dmul_rn(-1.0 * (v - vref), dt)));      // :433
-                    ca.w[i] = wn;
-                    kill = wn < ca.lower;                                                             // :436
-                    atomicAdd(&s_hist[weight_bin(wn)], 1u);
-                    const Fx128 fv = fx_from_double(v);
-                    acc.v = fx_add(acc.v, fv);
-                    if (!kill) {
-                        acc.cw = fx_add(acc.cw, fx_from_double(wn));
-                        acc.cv = fx_add(acc.cv, fx_from_double(__dmul_rn(wn, v)));
-                    }
-                    acc.vmin = fmin(acc.vmin, v); acc.vmax = fmax(acc.vmax, v);
-                    acc.n_in += 1.0; acc.n_acc += 1.0;
-                    acc.births += kill ? 1.0 : 0.0;
+        for (int s = 0; s < SUB; ++s) {
+            const long long i = tile * TILE + s * PVD_TILE + lane;
+            bool kill = false;
+            if (i < n) {
+                const double v = PROD::produce(a, i, step);
+                const double wn = __dmul_rn(ca.w[i], exp(__dmul_rn(-1.0 * (v - vref), dt)));      // :433
+                ca.w[i] = wn;
+                kill = wn < ca.lower;                                                             // :436
+                atomicAdd(&s_hist[weight_bin(wn)], 1u);
+                const Fx128 fv = fx_from_double(v);
+                acc.v = fx_add(acc.v, fv);
+                if (!kill) {
+                    acc.cw = fx_add(acc.cw, fx_from_double(wn));
+                    acc.cv = fx_add(acc.cv, fx_from_double(__dmul_rn(wn, v)));
                 }
-                mask[s] = __ballot_sync(0xffffffffu, kill);
-                total += __popc(mask[s]);
+                acc.vmin = fmin(acc.vmin, v); acc.vmax = fmax(acc.vmax, v);
+                acc.n_in += 1.0; acc.n_acc += 1.0;
+                acc.births += kill ? 1.0 : 0.0;
             }
-            publish_aggregate(a.status, tile, step, total);
-            issued = feed_issue(feed, tickets);                        // the next ticket travels while the previous tile's kill list is written
+            const unsigned mask = __ballot_sync(0xffffffffu, kill);
+            if (lane == 0) ca.kill_mask[tile * SUB + s] = mask;
         }
-        if (pend >= 0) {
-            long long o = resolve_prefix(a.status, pend, step, pend_total);
-#pragma unroll
-            for (int s = 0; s < SUB; ++s) {
-                const unsigned m = pend_mask[s];
-                if ((m >> lane) & 1u) ca.kill_idx[o + __popc(m & lt_mask)] = (int)(pend * TILE + s * PVD_TILE + lane);
-                o += __popc(m);
-            }
-        }
-        if (tile < 0) break;
-        pend = tile; pend_total = total;
-#pragma unroll
-        for (int s = 0; s < SUB; ++s) pend_mask[s] = mask[s];
+#if PVD_CONT_DYNAMIC
         tile = feed_take(feed, issued, ntiles, 1);
+#endif
     }
     __syncthreads();
     for (int b = threadIdx.x; b < PVD_HIST_BINS; b += PVD_CTA)
         if (s_hist[b]) atomicAdd(&ca.hist[b], s_hist[b]);
-    // population does not change; the kill count is the inclusive prefix of the last tile
-    cta_finish_step(a, acc, ntiles, true, n, true);      // Vref is produced by k_cont_finish, after branching
+    // population does not change; Vref is produced by k_cont_finish, after branching
+    cta_finish_step(a, acc, ntiles, true, n, true);
 }
 
 // (w desc, idx asc) ordering
@@ -193,8 +191,61 @@ __global__ void __launch_bounds__(1024) k_cont_prefix(const StepArgs a, const Co
     __shared__ int s_edge;
     __shared__ unsigned s_maxbin;
     const DevState *so = &a.st[a.parity];          // continuous weighting: population and flags do not change within a step
-    const long long ntiles = (so->n + ca.tile - 1) / ca.tile;
-    const unsigned nk = so->err ? 0u : (unsigned)(ld_relaxed_u64(&a.status[ntiles - 1]) & 0xffffffffull);
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    // ascending kill list from the ballot words, in rounds of 16 words per thread: four 16-byte loads in flight per thread (the
+    // buffer is padded), the words stay in registers, one block-wide scan per round places their set bits
+    const long long nwords = so->err ? 0 : (so->n + 31) / 32;
+    unsigned base_k = 0;
+    for (long long r0 = 0; r0 < nwords; r0 += 16 * 1024) {
+        const long long w0 = r0 + 16ll * t;
+        unsigned m[16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (w0 + 4 * q < nwords) v = __ldcg(reinterpret_cast<const uint4 *>(ca.kill_mask + w0) + q);
+            m[4 * q] = v.x; m[4 * q + 1] = v.y; m[4 * q + 2] = v.z; m[4 * q + 3] = v.w;
+        }
+        unsigned mine_k = 0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            if (w0 + j >= nwords) m[j] = 0u;                  // stale words beyond the ensemble
+            mine_k += __popc(m[j]);
+        }
+        unsigned incl_k = mine_k;
+        for (int off = 1; off < 32; off <<= 1) {
+            const unsigned y = __shfl_up_sync(0xffffffffu, incl_k, off);
+            if (lane >= off) incl_k += y;
+        }
+        __syncthreads();                                      // the previous round's s_warp / s_maxbin have been read
+        if (lane == 31) s_warp[wid] = incl_k;
+        __syncthreads();
+        if (wid == 0) {
+            const unsigned v = s_warp[lane];
+            unsigned x = v;
+            for (int off = 1; off < 32; off <<= 1) {
+                const unsigned y = __shfl_up_sync(0xffffffffu, x, off);
+                if (lane >= off) x += y;
+            }
+            s_warp[lane] = x - v;
+            if (lane == 31) s_maxbin = x;                     // round total (the slot is re-initialised before its own use below)
+        }
+        __syncthreads();
+        unsigned o = base_k + s_warp[wid] + incl_k - mine_k;
+        base_k += s_maxbin;
+        if (mine_k) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                unsigned mm = m[j];
+                while (mm) {
+                    const int bit = __ffs((int)mm) - 1;
+                    ca.kill_idx[o++] = (int)((w0 + j) * 32 + bit);
+                    mm &= mm - 1u;
+                }
+            }
+        }
+    }
+    const unsigned nk = base_k;
+    __syncthreads();                                // s_warp / s_maxbin are reused by the histogram scan
     if (threadIdx.x == 0) {
         ca.work->n_kill = nk; ca.work->n_cand = 0; ca.work->n_copy = 0; ca.work->n_upper = 0; ca.work->done = 0;
         ca.work->sub_w = 0.0; ca.work->sub_wv = 0.0; ca.work->ranked = 0; ca.work->fast = 0;
@@ -203,7 +254,6 @@ __global__ void __launch_bounds__(1024) k_cont_prefix(const StepArgs a, const Co
     if (so->err || nk == 0) return;
     __syncthreads();
     constexpr int PER = PVD_HIST_BINS / 1024;                 // 4 consecutive bins per thread, highest bins first
-    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
     if (t == 0) { s_edge = -1; s_maxbin = 0u; }
     unsigned h[PER], mine = 0;
 #pragma unroll
