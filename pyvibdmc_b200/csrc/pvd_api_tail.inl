@@ -30,22 +30,21 @@ static int cont_launch_tail(pvd_sim *s, const StepArgs &a, const ContArgs &ca, l
 {
     const int g = s->grid_light;
     const bool imp = s->cfg.trial != PVD_TRIAL_NONE;
-    // seven short kernels per step: launched with programmatic stream serialisation so that each one's launch latency
+    // six kernels per step: launched with programmatic stream serialisation so that each one's launch latency
     // overlaps its predecessor's tail (every one of them starts with pdl_wait())
     PVD_CUDA(launch_pdl(k_cont_prefix, dim3(1), dim3(1024), 0, s->stream, a, ca));
     PVD_CHECK_LAUNCH();
     PVD_CUDA(launch_pdl(k_cont_collect, dim3((unsigned)g), dim3(PVD_CTA), 0, s->stream, a, ca));
     PVD_CHECK_LAUNCH();
-    PVD_CUDA(launch_pdl(k_cont_rank, dim3((unsigned)(g_num_sms > 0 ? g_num_sms : 148)), dim3(PVD_RANK_SUB), (size_t)PVD_RANK_SMEM, s->stream, a, ca));
-    PVD_CHECK_LAUNCH();
-    PVD_CUDA(launch_pdl(k_cont_assign, dim3(1), dim3(1024), 0, s->stream, a, ca, s->cont_queue.as<ContCand>(), s->cont_root.as<int>(),
-                        s->cont_skip.as<unsigned char>()));
+    // grid: CTA 0 makes the kill list, one CTA per SM orders the bins; the last one to finish assigns the donors
+    PVD_CUDA(launch_pdl(k_cont_rank, dim3((unsigned)(g_num_sms > 0 ? g_num_sms : 148) + 1u), dim3(PVD_RANK_SUB), (size_t)PVD_RANK_SMEM, s->stream, a, ca,
+                        s->cont_queue.as<ContCand>(), s->cont_root.as<int>(), s->cont_skip.as<unsigned char>()));
     PVD_CHECK_LAUNCH();
     PVD_CUDA(launch_pdl(k_cont_copy, dim3((unsigned)g), dim3(PVD_CTA), 0, s->stream, a, ca, s->x[s->cur].as<double>(), s->v[s->cur].as<double>(),
                         s->who[s->cur].as<int>(), imp ? s->f[s->cur].as<double>() : (double *)nullptr,
                         imp ? s->psi[s->cur].as<double>() : (double *)nullptr, imp ? s->lk[s->cur].as<double>() : (double *)nullptr, src_out));
     PVD_CHECK_LAUNCH();
-    PVD_CUDA(launch_pdl(k_cont_finish, dim3((unsigned)g), dim3(PVD_CTA), 0, s->stream, a, ca));
+    PVD_CUDA(launch_pdl(k_cont_finish, dim3((unsigned)(g_num_sms > 0 ? g_num_sms : 148)), dim3(1024), 0, s->stream, a, ca));
     PVD_CHECK_LAUNCH();
     return PVD_OK;
 }

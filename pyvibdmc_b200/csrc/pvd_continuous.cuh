@@ -7,7 +7,7 @@
 //   1. k_cont_update   : weight update, exact sums over the surviving walkers, kill flags as one ballot word per
 //                        32 walkers (no warp waits for another: no ticket counter, no look-back scan)
 //                        and the log-spaced histogram (64 bins / octave) of the updated weights
-//   3. k_cont_prefix   : ascending kill list from the ballot words; suffix sums of the histogram -> the bin that holds the K-th largest weight
+//   3. k_cont_prefix   : suffix sums of the histogram -> the bin that holds the K-th largest weight
 //                        (K = number of kills) and, per bin, where its members start in the
 //                        candidate array
 //      k_cont_collect  : candidates = all walkers at or above that bin, bucketed by bin
@@ -15,8 +15,9 @@
 //                        (1024 sub-buckets + all-pairs rank inside a sub-bucket) and writes it to
 //                        its place in the sorted candidate array.  If some bin is too full for that (> 8192: many
 //                        identical weights), the candidates are appended unordered instead and
-//                        k_cont_assign sorts them with a single-CTA bitonic network in global memory.
-//   4. k_cont_assign   : if the K-th largest weight is > half the largest, the K argmax steps are
+//                        the donor assignment sorts them with a single-CTA bitonic network in global memory.
+//                        CTA 0 of the same kernel makes the ascending kill list from the ballot words meanwhile.
+//   4. cont_assign     : (the last CTA of k_cont_rank to finish) if the K-th largest weight is > half the largest, the K argmax steps are
 //                        exactly "j-th largest donates to j-th kill" and are applied in parallel;
 //                        otherwise (halved pieces re-enter the top: start-up transients) the
 //                        reference loop is replayed exactly by one thread over the sorted
@@ -41,6 +42,7 @@ struct ContWork {
     int fast;               // 1/2: k_cont_copy pairs j-th largest (sorted / cand array) with the j-th kill itself
     int ranked;             // 1: candidates are bucketed by bin and ranked in parallel; 0: unordered + single-CTA sort
     unsigned done;
+    unsigned done_rank;     // CTAs of k_cont_rank that have finished (the last one assigns the donors)
     double sub_w, sub_wv;   // weight removed by upper-threshold kills (corrects the exact sums)
     unsigned long long wmax_bits, wmin_bits;
 };
@@ -192,62 +194,12 @@ __global__ void __launch_bounds__(1024) k_cont_prefix(const StepArgs a, const Co
     __shared__ unsigned s_maxbin;
     const DevState *so = &a.st[a.parity];          // continuous weighting: population and flags do not change within a step
     const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-    // ascending kill list from the ballot words, in rounds of 16 words per thread: four 16-byte loads in flight per thread (the
-    // buffer is padded), the words stay in registers, one block-wide scan per round places their set bits
-    const long long nwords = so->err ? 0 : (so->n + 31) / 32;
-    unsigned base_k = 0;
-    for (long long r0 = 0; r0 < nwords; r0 += 16 * 1024) {
-        const long long w0 = r0 + 16ll * t;
-        unsigned m[16];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (w0 + 4 * q < nwords) v = __ldcg(reinterpret_cast<const uint4 *>(ca.kill_mask + w0) + q);
-            m[4 * q] = v.x; m[4 * q + 1] = v.y; m[4 * q + 2] = v.z; m[4 * q + 3] = v.w;
-        }
-        unsigned mine_k = 0;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            if (w0 + j >= nwords) m[j] = 0u;                  // stale words beyond the ensemble
-            mine_k += __popc(m[j]);
-        }
-        unsigned incl_k = mine_k;
-        for (int off = 1; off < 32; off <<= 1) {
-            const unsigned y = __shfl_up_sync(0xffffffffu, incl_k, off);
-            if (lane >= off) incl_k += y;
-        }
-        __syncthreads();                                      // the previous round's s_warp / s_maxbin have been read
-        if (lane == 31) s_warp[wid] = incl_k;
-        __syncthreads();
-        if (wid == 0) {
-            const unsigned v = s_warp[lane];
-            unsigned x = v;
-            for (int off = 1; off < 32; off <<= 1) {
-                const unsigned y = __shfl_up_sync(0xffffffffu, x, off);
-                if (lane >= off) x += y;
-            }
-            s_warp[lane] = x - v;
-            if (lane == 31) s_maxbin = x;                     // round total (the slot is re-initialised before its own use below)
-        }
-        __syncthreads();
-        unsigned o = base_k + s_warp[wid] + incl_k - mine_k;
-        base_k += s_maxbin;
-        if (mine_k) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                unsigned mm = m[j];
-                while (mm) {
-                    const int bit = __ffs((int)mm) - 1;
-                    ca.kill_idx[o++] = (int)((w0 + j) * 32 + bit);
-                    mm &= mm - 1u;
-                }
-            }
-        }
-    }
-    const unsigned nk = base_k;
-    __syncthreads();                                // s_warp / s_maxbin are reused by the histogram scan
+    // the number of walkers below the threshold is one of the step's sums (k_cont_update's last CTA left it there; the sums stay
+    // local to the shard until k_cont_finish); the kill LIST is made from the ballot words by CTA 0 of k_cont_rank, off the
+    // critical path (nothing before the donor assignment reads it)
+    const unsigned nk = (so->err || so->n <= 0) ? 0u : (unsigned)a.sums[PVD_SUM_BIRTHS];
     if (threadIdx.x == 0) {
-        ca.work->n_kill = nk; ca.work->n_cand = 0; ca.work->n_copy = 0; ca.work->n_upper = 0; ca.work->done = 0;
+        ca.work->n_kill = nk; ca.work->n_cand = 0; ca.work->n_copy = 0; ca.work->n_upper = 0; ca.work->done = 0; ca.work->done_rank = 0;
         ca.work->sub_w = 0.0; ca.work->sub_wv = 0.0; ca.work->ranked = 0; ca.work->fast = 0;
         ca.work->wmax_bits = 0ull; ca.work->wmin_bits = 0x7FF0000000000000ull;
     }
@@ -331,69 +283,6 @@ __device__ __forceinline__ int weight_subbin(double w)
 {
     return (int)((__double_as_longlong(w) >> 36) & (PVD_RANK_SUB - 1));
 }
-__global__ void __launch_bounds__(1024) k_cont_rank(const StepArgs a, const ContArgs ca)
-{
-    pdl_wait();
-    extern __shared__ __align__(16) unsigned char s_rank_raw[];
-    ContCand *s_c = reinterpret_cast<ContCand *>(s_rank_raw);
-    unsigned *sub_cnt = reinterpret_cast<unsigned *>(s_c + PVD_RANK_MAX_BIN);
-    unsigned *sub_start = sub_cnt + PVD_RANK_SUB;
-    unsigned *sub_fill = sub_start + PVD_RANK_SUB;
-    unsigned short *perm = reinterpret_cast<unsigned short *>(sub_fill + PVD_RANK_SUB);
-    __shared__ unsigned s_warp[32];
-    const DevState *so = &a.st[a.parity];
-    if (so->err || ca.work->n_kill == 0 || !ca.work->ranked) return;
-    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-    const int edge = ca.work->edge_bin;
-    // CTAs stride over the bins from the top; each CTA needs 150 KB of shared memory, so the grid is kept small
-    for (int bin = PVD_HIST_BINS - 1 - (int)blockIdx.x; bin >= edge; bin -= (int)gridDim.x) {
-        unsigned cnt = ca.hist[bin];
-        const unsigned start = ca.bin_start[bin];
-        if (cnt == 0 || (long long)start >= ca.cand_cap) continue;
-        if ((long long)start + cnt > ca.cand_cap) cnt = (unsigned)(ca.cand_cap - start);
-        __syncthreads();                                      // previous bin's shared arrays are no longer read
-        sub_cnt[t] = 0; sub_fill[t] = 0;                      // blockDim.x == PVD_RANK_SUB
-        for (unsigned e = t; e < cnt; e += blockDim.x) s_c[e] = ca.cand[start + e];
-        __syncthreads();
-        for (unsigned e = t; e < cnt; e += blockDim.x) atomicAdd(&sub_cnt[weight_subbin(s_c[e].w)], 1u);
-        __syncthreads();
-        // members of higher sub-buckets come first: thread t owns sub-bucket 1023 - t
-        const unsigned mine = sub_cnt[PVD_RANK_SUB - 1 - t];
-        unsigned incl = mine;
-        for (int off = 1; off < 32; off <<= 1) {
-            const unsigned y = __shfl_up_sync(0xffffffffu, incl, off);
-            if (lane >= off) incl += y;
-        }
-        if (lane == 31) s_warp[wid] = incl;
-        __syncthreads();
-        if (wid == 0) {
-            const unsigned v = s_warp[lane];
-            unsigned x = v;
-            for (int off = 1; off < 32; off <<= 1) {
-                const unsigned y = __shfl_up_sync(0xffffffffu, x, off);
-                if (lane >= off) x += y;
-            }
-            s_warp[lane] = x - v;
-        }
-        __syncthreads();
-        sub_start[PVD_RANK_SUB - 1 - t] = s_warp[wid] + incl - mine;
-        __syncthreads();
-        for (unsigned e = t; e < cnt; e += blockDim.x) {
-            const int sk = weight_subbin(s_c[e].w);
-            perm[sub_start[sk] + atomicAdd(&sub_fill[sk], 1u)] = (unsigned short)e;
-        }
-        __syncthreads();
-        for (unsigned p = t; p < cnt; p += blockDim.x) {
-            const ContCand me = s_c[perm[p]];
-            const int sk = weight_subbin(me.w);
-            const unsigned s0 = sub_start[sk], c = sub_cnt[sk];
-            unsigned r = s0;
-            for (unsigned q = s0; q < s0 + c; ++q) r += cand_before(s_c[perm[q]], me) ? 1u : 0u;
-            ca.sorted[start + r] = me;
-        }
-    }
-}
-
 // block-wide argmax (first index on ties) / argmin over w[0..n) with a skip mask
 __device__ inline int block_arg_extreme(const double *w, long long n, bool want_max, const unsigned char *skip, double *s_val, int *s_idx)
 {
@@ -426,10 +315,9 @@ __device__ inline int block_arg_extreme(const double *w, long long n, bool want_
     return r;
 }
 
-// ---- 4. donor assignment (single CTA of 1024 threads)
-__global__ void __launch_bounds__(1024) k_cont_assign(const StepArgs a, const ContArgs ca, ContCand *queue, int *root, unsigned char *skip)
+// ---- 4. donor assignment (one CTA of 1024 threads: the last CTA of k_cont_rank to finish)
+__device__ __forceinline__ void cont_assign(const StepArgs &a, const ContArgs &ca, ContCand *queue, int *root, unsigned char *skip)
 {
-    pdl_wait();
     __shared__ double s_val[32];
     __shared__ int s_idx[32];
     __shared__ int s_flag;
@@ -571,6 +459,146 @@ __global__ void __launch_bounds__(1024) k_cont_assign(const StepArgs a, const Co
     for (int b = threadIdx.x; b < PVD_HIST_BINS; b += blockDim.x) { ca.hist[b] = 0; ca.bin_fill[b] = 0; }
 }
 
+// ascending kill list from the ballot words of k_cont_update (one CTA of 1024 threads), in rounds of 16 words per thread: four
+// 16-byte loads in flight per thread (the buffer is padded), the words stay in registers, one block-wide scan per round places
+// their set bits
+__device__ __forceinline__ void cont_kill_list(const ContArgs &ca, long long n, unsigned *s_warp, unsigned *s_tot)
+{
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    const long long nwords = (n + 31) / 32;
+    unsigned base_k = 0;
+    for (long long r0 = 0; r0 < nwords; r0 += 16 * 1024) {
+        const long long w0 = r0 + 16ll * t;
+        unsigned m[16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (w0 + 4 * q < nwords) v = __ldcg(reinterpret_cast<const uint4 *>(ca.kill_mask + w0) + q);
+            m[4 * q] = v.x; m[4 * q + 1] = v.y; m[4 * q + 2] = v.z; m[4 * q + 3] = v.w;
+        }
+        unsigned mine_k = 0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            if (w0 + j >= nwords) m[j] = 0u;                  // stale words beyond the ensemble
+            mine_k += __popc(m[j]);
+        }
+        unsigned incl_k = mine_k;
+        for (int off = 1; off < 32; off <<= 1) {
+            const unsigned y = __shfl_up_sync(0xffffffffu, incl_k, off);
+            if (lane >= off) incl_k += y;
+        }
+        __syncthreads();                                      // the previous round's s_warp / s_tot have been read
+        if (lane == 31) s_warp[wid] = incl_k;
+        __syncthreads();
+        if (wid == 0) {
+            const unsigned v = s_warp[lane];
+            unsigned x = v;
+            for (int off = 1; off < 32; off <<= 1) {
+                const unsigned y = __shfl_up_sync(0xffffffffu, x, off);
+                if (lane >= off) x += y;
+            }
+            s_warp[lane] = x - v;
+            if (lane == 31) *s_tot = x;
+        }
+        __syncthreads();
+        unsigned o = base_k + s_warp[wid] + incl_k - mine_k;
+        base_k += *s_tot;
+        if (mine_k) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                unsigned mm = m[j];
+                while (mm) {
+                    const int bit = __ffs((int)mm) - 1;
+                    ca.kill_idx[o++] = (int)((w0 + j) * 32 + bit);
+                    mm &= mm - 1u;
+                }
+            }
+        }
+    }
+}
+
+// ---- 3c + 4. CTA 0 makes the kill list, the others order the bins; the last CTA to finish assigns the donors
+__global__ void __launch_bounds__(1024) k_cont_rank(const StepArgs a, const ContArgs ca, ContCand *queue, int *root, unsigned char *skip)
+{
+    pdl_wait();
+    extern __shared__ __align__(16) unsigned char s_rank_raw[];
+    ContCand *s_c = reinterpret_cast<ContCand *>(s_rank_raw);
+    unsigned *sub_cnt = reinterpret_cast<unsigned *>(s_c + PVD_RANK_MAX_BIN);
+    unsigned *sub_start = sub_cnt + PVD_RANK_SUB;
+    unsigned *sub_fill = sub_start + PVD_RANK_SUB;
+    unsigned short *perm = reinterpret_cast<unsigned short *>(sub_fill + PVD_RANK_SUB);
+    __shared__ unsigned s_warp[32];
+    __shared__ unsigned s_tot, s_last;
+    const DevState *so = &a.st[a.parity];
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    const bool active = !so->err && ca.work->n_kill != 0;
+    if (blockIdx.x == 0) {
+        if (active) cont_kill_list(ca, so->n, s_warp, &s_tot);
+    } else if (active && ca.work->ranked) {
+        const int edge = ca.work->edge_bin;
+        const int nb = (int)gridDim.x - 1;
+        // CTAs stride over the bins from the top; each CTA needs 150 KB of shared memory, so the grid is kept small
+        for (int bin = PVD_HIST_BINS - 1 - ((int)blockIdx.x - 1); bin >= edge; bin -= nb) {
+            unsigned cnt = ca.hist[bin];
+            const unsigned start = ca.bin_start[bin];
+            if (cnt == 0 || (long long)start >= ca.cand_cap) continue;
+            if ((long long)start + cnt > ca.cand_cap) cnt = (unsigned)(ca.cand_cap - start);
+            __syncthreads();                                      // previous bin's shared arrays are no longer read
+            sub_cnt[t] = 0; sub_fill[t] = 0;                      // blockDim.x == PVD_RANK_SUB
+            for (unsigned e = t; e < cnt; e += blockDim.x) s_c[e] = ca.cand[start + e];
+            __syncthreads();
+            for (unsigned e = t; e < cnt; e += blockDim.x) atomicAdd(&sub_cnt[weight_subbin(s_c[e].w)], 1u);
+            __syncthreads();
+            // members of higher sub-buckets come first: thread t owns sub-bucket 1023 - t
+            const unsigned mine = sub_cnt[PVD_RANK_SUB - 1 - t];
+            unsigned incl = mine;
+            for (int off = 1; off < 32; off <<= 1) {
+                const unsigned y = __shfl_up_sync(0xffffffffu, incl, off);
+                if (lane >= off) incl += y;
+            }
+            if (lane == 31) s_warp[wid] = incl;
+            __syncthreads();
+            if (wid == 0) {
+                const unsigned v = s_warp[lane];
+                unsigned x = v;
+                for (int off = 1; off < 32; off <<= 1) {
+                    const unsigned y = __shfl_up_sync(0xffffffffu, x, off);
+                    if (lane >= off) x += y;
+                }
+                s_warp[lane] = x - v;
+            }
+            __syncthreads();
+            sub_start[PVD_RANK_SUB - 1 - t] = s_warp[wid] + incl - mine;
+            __syncthreads();
+            for (unsigned e = t; e < cnt; e += blockDim.x) {
+                const int sk = weight_subbin(s_c[e].w);
+                perm[sub_start[sk] + atomicAdd(&sub_fill[sk], 1u)] = (unsigned short)e;
+            }
+            __syncthreads();
+            for (unsigned p = t; p < cnt; p += blockDim.x) {
+                const ContCand me = s_c[perm[p]];
+                const int sk = weight_subbin(me.w);
+                const unsigned s0 = sub_start[sk], c = sub_cnt[sk];
+                unsigned r = s0;
+                for (unsigned q = s0; q < s0 + c; ++q) r += cand_before(s_c[perm[q]], me) ? 1u : 0u;
+                ca.sorted[start + r] = me;
+            }
+        }
+    }
+    // the last CTA to get here (every CTA does, whatever it had to do) assigns the donors: it sees the kill list and the sorted
+    // candidates of all the others
+    __threadfence();
+    __syncthreads();
+    if (t == 0) {
+        const unsigned d = atomicAdd(&ca.work->done_rank, 1u);
+        s_last = (d == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    cont_assign(a, ca, queue, root, skip);
+}
+
 // ---- 5. copy donor -> killed for every per-walker array (in place: donors are never kill targets)
 __global__ void __launch_bounds__(PVD_CTA) k_cont_copy(const StepArgs a, const ContArgs ca, double *x, double *v, int *who, double *f,
                                                        double *psi, double *lk, long long *src_out)
@@ -606,16 +634,18 @@ __global__ void __launch_bounds__(PVD_CTA) k_cont_copy(const StepArgs a, const C
 }
 
 // ---- 6. min / max weight after branching, upper-threshold correction of the sums, Vref + log record
-__global__ void __launch_bounds__(PVD_CTA) k_cont_finish(const StepArgs a, const ContArgs ca)
+__global__ void __launch_bounds__(1024) k_cont_finish(const StepArgs a, const ContArgs ca)
 {
+    // one CTA of 1024 threads per SM: the same loads in flight as four times as many CTAs of 256, a quarter of the atomics on
+    // the two extrema and the done counter (they serialise in L2 at ~2.5 ns each)
     pdl_wait();
-    __shared__ double s_mx[PVD_WARPS], s_mn[PVD_WARPS];
+    __shared__ double s_mx[32], s_mn[32];
     __shared__ unsigned s_last;
     const DevState *so = &a.st[a.parity];
     if (a.st[a.parity].err) return;
     const long long n = so->n;
     double mx = 0.0, mn = INFINITY;
-    for (long long i = blockIdx.x * (long long)PVD_CTA + threadIdx.x; i < n; i += (long long)gridDim.x * PVD_CTA) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const double w = ca.w[i];
         mx = fmax(mx, w); mn = fmin(mn, w);
     }
@@ -623,7 +653,7 @@ __global__ void __launch_bounds__(PVD_CTA) k_cont_finish(const StepArgs a, const
     if ((threadIdx.x & 31) == 0) { s_mx[threadIdx.x >> 5] = mx; s_mn[threadIdx.x >> 5] = mn; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int k = 1; k < PVD_WARPS; ++k) { mx = fmax(mx, s_mx[k]); mn = fmin(mn, s_mn[k]); }
+        for (int k = 1; k < (int)(blockDim.x >> 5); ++k) { mx = fmax(mx, s_mx[k]); mn = fmin(mn, s_mn[k]); }
         // positive doubles order like their bit patterns
         atomicMax(&ca.work->wmax_bits, (unsigned long long)__double_as_longlong(fmax(mx, 0.0)));
         atomicMin(&ca.work->wmin_bits, (unsigned long long)__double_as_longlong(fmax(mn, 0.0)));
