@@ -53,7 +53,7 @@ def main():
         res["restart_final_walkers"] = int(n2)
         res["restart_final_pop"] = float(info2['pop_vs_tau'][-1, 1])
         res["restart_zpe"] = float(info2['vref_vs_tau'][300:, 1].mean() / 4.556335281212229e-6)
-        print("RESULT " + json.dumps(res))
+        print("\nRESULT " + json.dumps(res) + "\n", end="", flush=True)
     dist.destroy_process_group()
 
 

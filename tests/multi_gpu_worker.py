@@ -78,12 +78,33 @@ def main():
     imp_out = {"same": imp_same, "zpe": float(ist["vref"][T1 // 2:].mean() / 4.556335281212229e-6), "dt_eff_mean": float(ist["dt_eff"][5:].mean()),
                "pop_last": float(ist["pop"][-1]), "rejected_mean": float(ist["rejected"][5:].mean())}
     imp.close()
+    # ---- continuous weighting across shards (per-shard branching; the six kernels of the branching tail and both exchanges)
+    n2, T2 = 16000, 400
+    cont = {}
+    for coll in ("mailbox", "nccl"):
+        cs = ShardedSim(3, 3, masses, n2, 5.0, _capi.POT_H2O_PS, weighting="continuous", seed=31, rebalance_every=0, collective=coll)
+        s2, c2 = shard_bounds(n2, world)[rank]
+        cs.upload(np.repeat(eq[None] * 1.01, c2, axis=0))
+        cs.run(T2)
+        torch.cuda.synchronize()
+        cst = cs.stats(0, T2)
+        cont[coll] = (cst["vref"].copy(), cst["pop"].copy(), cst["births"].copy(), cs.collective)
+        cs.close()
+    h3 = torch.tensor(np.concatenate([cont["mailbox"][0], cont["mailbox"][1]]), device=torch.device("cuda", torch.cuda.current_device()))
+    h3max, h3min = h3.clone(), h3.clone()
+    dist.all_reduce(h3max, op=dist.ReduceOp.MAX)
+    dist.all_reduce(h3min, op=dist.ReduceOp.MIN)
+    cont_out = {"same": bool(torch.equal(h3max, h3min)),
+                "mailbox_equals_nccl": bool(cont["mailbox"][3] == "mailbox" and cont["nccl"][3] == "nccl"
+                                            and all(np.array_equal(cont["mailbox"][k], cont["nccl"][k]) for k in range(3))),
+                "zpe": float(cont["mailbox"][0][T2 // 2:].mean() / 4.556335281212229e-6),
+                "pop_mean": float(cont["mailbox"][1][T2 // 2:].mean()), "branched_mean": float(cont["mailbox"][2][T2 // 2:].mean())}
     sim = None
     if rank == 0:
-        out = {"world": world, "dw_ok": dw_ok, "imp": imp_out, "mailbox_equals_nccl": same_as_nccl, "step": st["step"], "pops": pops, "global_pop_last": float(stats["pop"][-1]), "same_on_all_ranks": same,
+        out = {"world": world, "cont": cont_out, "dw_ok": dw_ok, "imp": imp_out, "mailbox_equals_nccl": same_as_nccl, "step": st["step"], "pops": pops, "global_pop_last": float(stats["pop"][-1]), "same_on_all_ranks": same,
                "zpe": float(stats["vref"][T // 2:].mean() / 4.556335281212229e-6), "births_minus_deaths_ok":
                bool(np.array_equal(np.diff(stats["pop"]), (stats["births"] - stats["deaths"])[1:]))}
-        print("RESULT " + json.dumps(out))
+        print("\nRESULT " + json.dumps(out) + "\n", end="", flush=True)
     dist.destroy_process_group()
 
 

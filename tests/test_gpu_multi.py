@@ -9,6 +9,12 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
+def _result(stdout):
+    """The worker's RESULT line; the ranks share one pipe, so another rank's output may follow on the same line."""
+    line = [l for l in stdout.splitlines() if l.startswith("RESULT ")][-1]
+    return json.JSONDecoder().raw_decode(line[7:])[0]
+
+
 def test_two_gpu_sharded_run():
     from pyvibdmc_b200 import kernels
     if kernels.device_count() < 2:
@@ -18,8 +24,7 @@ def test_two_gpu_sharded_run():
            "--master-port", "29617", os.path.join(here, "multi_gpu_worker.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
-    line = [l for l in res.stdout.splitlines() if l.startswith("RESULT ")][-1]
-    out = json.loads(line[7:])
+    out = _result(res.stdout)
     assert out["world"] == 2 and out["step"] == 600 and out["same_on_all_ranks"] and out["births_minus_deaths_ok"]
     assert sum(out["pops"]) == int(out["global_pop_last"]) and 20000 < sum(out["pops"]) < 60000
     assert abs(out["pops"][0] - out["pops"][1]) < 0.2 * sum(out["pops"])          # rebalancing keeps shards level
@@ -29,6 +34,9 @@ def test_two_gpu_sharded_run():
     imp = out["imp"]                                                             # importance sampling with the global acceptance fraction
     assert imp["same"] and 4350 < imp["zpe"] < 4900 and 0.9 < imp["dt_eff_mean"] <= 1.0 and 4000 < imp["pop_last"] < 12000
     assert 0 < imp["rejected_mean"] < 0.1 * 8000
+    cont = out["cont"]                                                           # continuous weighting, sharded: both exchanges, same bits
+    assert cont["same"] and cont["mailbox_equals_nccl"] and 4350 < cont["zpe"] < 4900
+    assert 0.9 * 16000 < cont["pop_mean"] < 1.1 * 16000 and cont["branched_mean"] > 0
 
 
 def test_two_gpu_dmc_sim_drop_in(tmp_path):
@@ -42,7 +50,7 @@ def test_two_gpu_dmc_sim_drop_in(tmp_path):
            "--master-port", "29618", os.path.join(here, "multi_gpu_dmcsim_worker.py"), out]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
-    r = json.loads([l for l in res.stdout.splitlines() if l.startswith("RESULT ")][-1][7:])
+    r = _result(res.stdout)
     assert r["world"] == 2 and r["vref_shape"] == [600, 2] and r["log_has_steps"]
     assert r["wfns"] == ["w2_wfn_100ts.hdf5", "w2_wfn_300ts.hdf5", "w2_wfn_500ts.hdf5"]
     assert r["n_parent"] == int(r["pop_at_window_start"]) and r["desc_sum"] == r["pop_at_window_end"]
