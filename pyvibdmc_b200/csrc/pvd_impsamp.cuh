@@ -51,7 +51,10 @@ struct TrialH2O {
     // a finite-difference stencil point that moves ONE hydrogen leaves the other O-H bond (its length and its table value)
     // untouched: psi_moved<0 / 1> takes them from `keep` -- the same operations on the same operands, hence the same bits as a
     // full evaluation -- and a third of the stencil's square roots and table look-ups disappear (trial_drift_ke)
-    static constexpr bool PARTIAL = true;
+#ifndef PVD_FD_PARTIAL
+#define PVD_FD_PARTIAL 1                                  // A/B switch: 0 = every stencil point evaluates both bonds
+#endif
+    static constexpr bool PARTIAL = PVD_FD_PARTIAL != 0;
     struct Bond { double r, t; };
     template <int WHICH>                                 // 0: H1-O, 1: H2-O
     __device__ static __forceinline__ Bond bond(const double (&x)[9], const TrialParamsDev &p)
@@ -61,24 +64,52 @@ struct TrialH2O {
         b.t = interp_table(b.r, p);
         return b;
     }
-    // MOVED: 0 = H1 moved since `keep` (= bond<1>) was formed, 1 = H2 moved (keep = bond<0>), 2 = evaluate everything
-    template <int MOVED>
-    __device__ static __forceinline__ double psi_moved(const double (&x)[9], const TrialParamsDev &p, const Bond &keep)
+    // MOVED: 0 = H1 moved since `keep` (= bond<1>) was formed, 1 = H2 moved (keep = bond<0>), 2 = evaluate everything.
+    // PVD_FD_NOINLINE: the evaluation is ONE out-of-line function (scalar arguments in registers, `moved` a warp-uniform run-time
+    // value) instead of a copy per call site: with the copies that inlining the stencil made, k_imp_move was 140-200 KB of code and
+    // instruction fetch was its largest stall on an equilibrated ensemble, where the warps of an SM are spread over all of it
+    // (no_instruction 1.5-2.5 stalls per issue, profiles/r02_profiles.md).
+#ifndef PVD_FD_NOINLINE
+#define PVD_FD_NOINLINE 1
+#endif
+    __device__ static __forceinline__ double psi_core(int moved, double x0, double x1, double x2, double x3, double x4, double x5,
+                                                      double x6, double x7, double x8, double keep_r, double keep_t, const TrialParamsDev &p)
     {
-        const double ax = x[0] - x[6], ay = x[1] - x[7], az = x[2] - x[8];      // H1 - O
-        const double bx = x[3] - x[6], by = x[4] - x[7], bz = x[5] - x[8];      // H2 - O
+        const double ax = x0 - x6, ay = x1 - x7, az = x2 - x8;      // H1 - O
+        const double bx = x3 - x6, by = x4 - x7, bz = x5 - x8;      // H2 - O
         double r1, r2, t1, t2;
-        if (MOVED == 1) { r1 = keep.r; t1 = keep.t; } else { r1 = norm3(ax, ay, az); t1 = interp_table(r1, p); }
-        if (MOVED == 0) { r2 = keep.r; t2 = keep.t; } else { r2 = norm3(bx, by, bz); t2 = interp_table(r2, p); }
+        if (moved == 1) { r1 = keep_r; t1 = keep_t; } else { r1 = norm3(ax, ay, az); t1 = interp_table(r1, p); }
+        if (moved == 0) { r2 = keep_r; t2 = keep_t; } else { r2 = norm3(bx, by, bz); t2 = interp_table(r2, p); }
         const double dot = __dadd_rn(__dadd_rn(__dmul_rn(ax, bx), __dmul_rn(ay, by)), __dmul_rn(az, bz));
         const double th = acos(dot / __dmul_rn(r1, r2));
         const double dth = th - p.theta_eq;
         const double ang = __dmul_rn(p.ang_pref, exp(__dmul_rn(-p.ang_alpha, __dmul_rn(dth, dth)) / 2.0));
         return __dmul_rn(__dmul_rn(t1, t2), ang);
     }
+    __device__ static __noinline__ double psi_call(int moved, double x0, double x1, double x2, double x3, double x4, double x5,
+                                                   double x6, double x7, double x8, double keep_r, double keep_t, const TrialParamsDev *p)
+    {
+        return psi_core(moved, x0, x1, x2, x3, x4, x5, x6, x7, x8, keep_r, keep_t, *p);
+    }
+    template <int MOVED>
+    __device__ static __forceinline__ double psi_moved(const double (&x)[9], const TrialParamsDev &p, const Bond &keep)
+    {
+#if PVD_FD_NOINLINE
+        return psi_call(MOVED, x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7], x[8], keep.r, keep.t, &p);
+#else
+        return psi_core(MOVED, x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7], x[8], keep.r, keep.t, p);
+#endif
+    }
     __device__ static __forceinline__ double psi(const double (&x)[9], const TrialParamsDev &p)
     {
-        return psi_moved<2>(x, p, Bond{0.0, 0.0});
+        const double ax = x[0] - x[6], ay = x[1] - x[7], az = x[2] - x[8];      // H1 - O
+        const double bx = x[3] - x[6], by = x[4] - x[7], bz = x[5] - x[8];      // H2 - O
+        const double r1 = norm3(ax, ay, az), r2 = norm3(bx, by, bz);
+        const double dot = __dadd_rn(__dadd_rn(__dmul_rn(ax, bx), __dmul_rn(ay, by)), __dmul_rn(az, bz));
+        const double th = acos(dot / __dmul_rn(r1, r2));
+        const double dth = th - p.theta_eq;
+        const double ang = __dmul_rn(p.ang_pref, exp(__dmul_rn(-p.ang_alpha, __dmul_rn(dth, dth)) / 2.0));
+        return __dmul_rn(__dmul_rn(interp_table(r1, p), interp_table(r2, p)), ang);
     }
 };
 
@@ -240,9 +271,9 @@ __device__ __forceinline__ void trial_drift_ke(double (&xx)[TRIAL::NC], const Tr
         // atom by atom (compile time), dimension by dimension (run time): the selects that stand in for a dynamic register
         // index span the moved atom's three coordinates only, and the bond that atom is not part of is evaluated once per atom
         static_assert(NC == 9 && ND == 3, "partial stencil: three atoms in three dimensions");
-        psi0 = TRIAL::psi(xx, p);
+        typename TRIAL::Bond keep = TRIAL::template bond<1>(xx, p);       // the H2-O bond, untouched while H1 is walked
+        psi0 = TRIAL::template psi_moved<2>(xx, p, keep);
         double sd[ND] = {0.0, 0.0, 0.0};
-        typename TRIAL::Bond keep = TRIAL::template bond<1>(xx, p);
 #pragma unroll
         for (int atom = 0; atom < 3; ++atom) {
             if (atom == 1) keep = TRIAL::template bond<0>(xx, p);          // H1 as the walk over its coordinates left it
@@ -253,17 +284,19 @@ __device__ __forceinline__ void trial_drift_ke(double (&xx)[TRIAL::NC], const Tr
                 for (int k = 0; k < ND; ++k) orig = (k == d) ? xx[3 * atom + k] : orig;
                 const double lo = orig - p.fd_dx;
                 const double hi = lo + 2.0 * p.fd_dx;
+                double pm = 0.0, pp = 0.0;
+#pragma unroll 1
+                for (int side = 0; side < 2; ++side) {                      // one copy of the evaluation for both stencil points
+                    const double at = side ? hi : lo;
 #pragma unroll
-                for (int k = 0; k < ND; ++k) xx[3 * atom + k] = (k == d) ? lo : xx[3 * atom + k];
-                double pm, pp;
-                if (atom == 0) pm = TRIAL::template psi_moved<0>(xx, p, keep);
-                else if (atom == 1) pm = TRIAL::template psi_moved<1>(xx, p, keep);
-                else pm = TRIAL::template psi_moved<2>(xx, p, keep);
-#pragma unroll
-                for (int k = 0; k < ND; ++k) xx[3 * atom + k] = (k == d) ? hi : xx[3 * atom + k];
-                if (atom == 0) pp = TRIAL::template psi_moved<0>(xx, p, keep);
-                else if (atom == 1) pp = TRIAL::template psi_moved<1>(xx, p, keep);
-                else pp = TRIAL::template psi_moved<2>(xx, p, keep);
+                    for (int k = 0; k < ND; ++k) xx[3 * atom + k] = (k == d) ? at : xx[3 * atom + k];
+                    double pv;
+                    if (atom == 0) pv = TRIAL::template psi_moved<0>(xx, p, keep);
+                    else if (atom == 1) pv = TRIAL::template psi_moved<1>(xx, p, keep);
+                    else pv = TRIAL::template psi_moved<2>(xx, p, keep);
+                    pm = side ? pm : pv;
+                    pp = side ? pv : pp;
+                }
 #pragma unroll
                 for (int k = 0; k < ND; ++k) xx[3 * atom + k] = (k == d) ? hi - p.fd_dx : xx[3 * atom + k];   // the walked value
                 const double first = (pp - pm) / (2.0 * p.fd_dx);
@@ -430,6 +463,16 @@ __global__ void __launch_bounds__(PVD_CTA, 2) k_imp_move(const StepArgs a, const
     __shared__ unsigned s_cnt[PVD_WARPS];
     __shared__ unsigned s_last;
     DevState *sip = &a.st[a.parity];
+#if PVD_FD_NOINLINE
+    // the out-of-line trial function takes the table description by pointer: a copy in shared memory (a pointer into the kernel's
+    // parameter block would make the compiler copy the block onto every thread's stack)
+    __shared__ TrialParamsDev s_trial;
+    if (threadIdx.x == 0) s_trial = im.trial;
+    __syncthreads();
+#define PVD_IMP_TRIAL s_trial
+#else
+#define PVD_IMP_TRIAL im.trial
+#endif
     if (sip->err || sip->n <= 0) return;           // the branching kernel forwards the dead state
     const double vref_now = sip->vref;
     const long long n = sip->n, step = sip->step;
@@ -480,7 +523,7 @@ __global__ void __launch_bounds__(PVD_CTA, 2) k_imp_move(const StepArgs a, const
 #pragma unroll
             for (int c = 0; c < NC; ++c) { xx[c] = __dadd_rn(x[c * a.cap + i], xx[c]); s_xf[c][tid] = xx[c]; }
             double f1[NC];
-            trial_drift_ke<TRIAL>(xx, im.trial, im.inv_mass, psi_x, f1, ke_x);
+            trial_drift_ke<TRIAL>(xx, PVD_IMP_TRIAL, im.inv_mass, psi_x, f1, ke_x);
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
                 xx[c] = __dadd_rn(s_xf[c][tid], __dmul_rn(__dmul_rn(im.inv_mass[c / TRIAL::NDIM], f1[c]), a.dt));
@@ -489,7 +532,7 @@ __global__ void __launch_bounds__(PVD_CTA, 2) k_imp_move(const StepArgs a, const
             }
         }
         double fy[NC], psi_y, ke_new;
-        trial_drift_ke<TRIAL>(xx, im.trial, im.inv_mass, psi_y, fy, ke_new);
+        trial_drift_ke<TRIAL>(xx, PVD_IMP_TRIAL, im.inv_mass, psi_y, fy, ke_new);
         double xo[NC], y[NC];
         double acc, vs_new = 1.0;
         {

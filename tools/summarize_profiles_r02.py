@@ -49,7 +49,7 @@ def main():
         txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         open("/tmp/_r02_gather_raw.csv", "w").write(txt)
         summ["r02_step_gather"] = raw_csv("/tmp/_r02_gather_raw.csv")
-    for name in ("r02_materialise", "r02_step_discrete"):
+    for name in ("r02_materialise", "r02_step_discrete", "r02_cont_update", "r02_imp_move_fd"):
         p = os.path.join(G, name + "_raw.csv")
         if os.path.exists(p):
             summ[name] = raw_csv(p)
