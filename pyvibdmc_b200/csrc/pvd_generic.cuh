@@ -203,7 +203,10 @@ __global__ void __launch_bounds__(256, 4) k_displace_soa(double *__restrict__ x,
 // A tile is PVD_BR_SUB sub-tiles of 32 walkers (lane l of sub-tile s owns walker tile*128 + s*32 + l); see k_cont_update.
 constexpr int PVD_BR_SUB = 4;
 constexpr int PVD_BR_TILE = PVD_TILE * PVD_BR_SUB;
-__global__ void __launch_bounds__(PVD_CTA, 2) k_branch_discrete(const StepArgs a)
+#ifndef PVD_BR_MINB
+#define PVD_BR_MINB 2               // A/B: resident CTAs per SM the register budget is cut for (2: 128 registers, 3: 80, 4: 64)
+#endif
+__global__ void __launch_bounds__(PVD_CTA, PVD_BR_MINB) k_branch_discrete(const StepArgs a)
 {
     if (!step_prologue(a)) return;
     const DevState *sip = &a.st[a.parity];

@@ -75,6 +75,9 @@ class ShardedSim:
                                      capacity=capacity or int(1.6 * local) + 4096, stats_ring=stats_ring)
         self.sim.set_stream(self.stream.cuda_stream)
         self.imp = trial != _capi.TRIAL_NONE
+        # a user potential (the reference's getpot plug-in): every rank evaluates its own shard on the host between
+        # ext_move() and ext_finish(); the per-step exchange is the NCCL all-reduce (the host is in the loop anyway)
+        self.external = int(potential) == _capi.POT_EXTERNAL
         if self.imp:
             if weighting != "discrete":
                 raise NotImplementedError("sharded importance sampling is built for discrete weighting")
@@ -84,7 +87,7 @@ class ShardedSim:
         self.sim.set_sums_ptr(self.sums.data_ptr())
         # per-step exchange: "mailbox" = peer stores over NVLink fused into the step kernel's last CTA (no collective kernel),
         # "nccl" = all-reduce between the step kernel and the finalisation.  Importance sampling needs two exchanges -> nccl.
-        self.collective = "nccl" if (self.imp or self.world == 1) else collective
+        self.collective = "nccl" if (self.imp or self.external or self.world == 1) else collective
         if self.collective == "mailbox":
             handles = [None] * self.world
             dist.all_gather_object(handles, self.sim.mailbox_handle())
@@ -96,8 +99,31 @@ class ShardedSim:
     def upload(self, coords_local, wts_local=None):
         with self.torch.cuda.stream(self.stream):
             self.sim.upload(coords_local, wts_local)
+            if self.external:
+                return                                 # the energies of the start ensemble follow: set_pots()
             self.dist.all_reduce(self.sums)
             self.sim.init_finalize()
+
+    def set_pots(self, v_local):
+        """Energies of this rank's shard of the start ensemble (user potential) -> global Vref."""
+        with self.torch.cuda.stream(self.stream):
+            self.sim.set_pots(v_local)
+            self.dist.all_reduce(self.sums)
+            self.sim.init_finalize()
+
+    def ext_move(self):
+        """Displace this rank's shard; the moved coordinates (n_local, atoms, dims) for the user potential."""
+        return self.sim.ext_move()
+
+    def ext_finish(self, v_local, do_branch=True):
+        """Energies of the moved shard -> weights / branching per shard, global Vref and population."""
+        with self.torch.cuda.stream(self.stream):
+            self.sim.ext_finish(v_local, do_branch)
+            self.dist.all_reduce(self.sums)
+            self.sim.step_finalize()
+            self.steps_done += 1
+            if self.rebalance_every and self.steps_done % self.rebalance_every == 0:
+                self.rebalance()
 
     def run(self, nsteps, branch_every=1):
         if self.collective == "mailbox":
@@ -239,8 +265,18 @@ class ShardedDevice:
         start, count = shard_bounds(len(coords), self.world)[self.rank]
         self.ss.upload(np.ascontiguousarray(coords[start:start + count]), None if wts is None else np.ascontiguousarray(wts[start:start + count]))
 
-    def set_pots(self, v):
-        raise NotImplementedError("a sharded DMC_Sim needs a built-in potential")
+    def local_slice(self, n_global):
+        """(start, count) of this rank's shard of a global start ensemble (what upload() keeps)."""
+        return shard_bounds(n_global, self.world)[self.rank]
+
+    def set_pots(self, v_local):
+        self.ss.set_pots(np.ascontiguousarray(v_local, dtype=np.float64))
+
+    def ext_move(self):
+        return self.ss.ext_move()
+
+    def ext_finish(self, v_local, do_branch=True):
+        self.ss.ext_finish(np.ascontiguousarray(v_local, dtype=np.float64), do_branch)
 
     def set_masses(self, masses):
         self.ss.sim.set_masses(masses)

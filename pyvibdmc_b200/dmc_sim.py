@@ -309,9 +309,11 @@ class DMC_Sim:
                 pot_params = [pot["de"], pot["alpha"]]
         cap = int(1.5 * max(self.num_walkers, len(self._walker_coords))) + 1024
         if self._world > 1:
-            if pot is None or self._hosted_imp:
-                raise NotImplementedError("a sharded DMC_Sim needs a built-in potential and a built-in trial wave function "
-                                          "(walkers never leave the GPUs)")
+            if self._hosted_imp:
+                raise NotImplementedError("a sharded DMC_Sim needs a built-in trial wave function")
+            if pot is None and (self.fixed_node is not None or self._deb_save_before_bod or self.impsamp_manager is not None):
+                raise NotImplementedError("a sharded DMC_Sim with a user potential runs the plain loop (no fixed node, "
+                                          "DEBUG_save_before_bod or importance sampling)")
             from .distributed import ShardedDevice
             self._dev = ShardedDevice(n_atoms, n_dim, self.masses, self.num_walkers, self.delta_t, pot_id, weighting=self.weighting,
                                       alpha=self._alpha, seed=self._seed + 7919 * int(self.cur_timestep), rng_mode=self._rng_mode,
@@ -321,10 +323,15 @@ class DMC_Sim:
                                       imp_variant=(_capi.IMP_SECOND_DISPLACEMENT if self.second_impsamp_displacement else
                                                    _capi.IMP_EXCITED_STATE if self.excited_state_imp_samp else _capi.IMP_STANDARD),
                                       trial_table=(trial["table"] if trial else None))
-            self._builtin = True
+            self._builtin = pot is not None
+            self._pot_on_device = pot is not None
             if pot_id == _capi.POT_NN_H4O2:
                 self._dev.set_nn_weights(pot["weights"])
             self._dev.upload(self._walker_coords, self._cont_wts)
+            if pot is None:
+                # user potential (getpot plug-in, potential_manager.py:71-99): every rank evaluates its own shard
+                s0, c0 = self._dev.local_slice(len(self._walker_coords))
+                self._dev.set_pots(np.asarray(self.potential(self._walker_coords[s0:s0 + c0]), dtype=np.float64))
             self._dev_step0 = int(self.cur_timestep)
             self._host_stale = False
             return self._dev

@@ -19,6 +19,8 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     rank = dist.get_rank()
     out = sys.argv[1]
+    if len(sys.argv) > 2 and sys.argv[2] == "ext":
+        return ext_main(pv, h5lite, dist, rank, out)
     eq = np.array([[1.81005599, 0., 0.], [-0.45344658, 1.75233806, 0.], [0., 0., 0.]])
     d = os.path.join(os.path.dirname(pv.__file__), "sample_potentials", "FortPots", "Partridge_Schwenke_H2O")
     pot = pv.Potential(potential_function='water_pot', python_file='h2o_potential.py', potential_directory=d, num_cores=1)
@@ -53,6 +55,40 @@ def main():
         res["restart_final_walkers"] = int(n2)
         res["restart_final_pop"] = float(info2['pop_vs_tau'][-1, 1])
         res["restart_zpe"] = float(info2['vref_vs_tau'][300:, 1].mean() / 4.556335281212229e-6)
+        print("\nRESULT " + json.dumps(res) + "\n", end="", flush=True)
+    dist.destroy_process_group()
+
+
+def ext_main(pv, h5lite, dist, rank, out):
+    """A user potential callable (the reference's getpot plug-in) on a sharded run: every rank evaluates its own shard."""
+    wn = 4.556335281212229e-6
+    mass = pv.Constants.reduced_mass('O-H')        # omega = 3700 cm-1: the sample harmonic oscillator (harmonicOscillator1D.py)
+    calls = []
+
+    def user_pot(cds):
+        calls.append(len(cds))
+        return (0.5 * mass * (3700.0 * wn) ** 2 * cds ** 2).reshape(len(cds))
+    res = {"world": dist.get_world_size()}
+    for weighting in ("discrete", "continuous"):
+        del calls[:]
+        sim = pv.DMC_Sim(sim_name=weighting, output_folder=out, weighting=weighting, num_walkers=20000, num_timesteps=1500,
+                         equil_steps=300, chkpt_every=700, wfn_every=500, desc_wt_steps=50, atoms=['O-H'], delta_t=10,
+                         potential=pv.Potential_Direct(potential_function=user_pot), start_structures=np.zeros((1, 1, 1)),
+                         log_every=500, seed=21)
+        assert sim._world == dist.get_world_size()
+        sim.run()
+        n = len(sim.walkers)
+        if rank == 0:
+            info = h5lite.read_h5(f"{out}/{weighting}_sim_info.hdf5")
+            w = h5lite.read_h5(f"{out}/wfns/{weighting}_wfn_800ts.hdf5")
+            pop = info['pop_vs_tau'][:, 1]
+            res[weighting] = {"zpe": float(info['vref_vs_tau'][400:, 1].mean() / wn), "final_walkers": int(n), "final_pop": float(pop[-1]),
+                              "pop_min": float(pop.min()), "pop_max": float(pop.max()), "calls": len(calls),
+                              "shard_fraction": float(np.mean(calls)) / float(pop.mean()),
+                              "desc_sum": float(w['desc_wts'].sum()), "pop_at_window_end": float(pop[849]),
+                              "vref_shape": list(info['vref_vs_tau'].shape)}
+        dist.barrier()
+    if rank == 0:
         print("\nRESULT " + json.dumps(res) + "\n", end="", flush=True)
     dist.destroy_process_group()
 

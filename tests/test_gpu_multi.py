@@ -58,3 +58,27 @@ def test_two_gpu_dmc_sim_drop_in(tmp_path):
     assert len(r["chkpts"]) >= 1
     # dmc_restart under torchrun stays sharded (world / rank / GPU re-detected) and extends the histories
     assert r["restart_vref_shape"] == [700, 2] and r["restart_final_walkers"] == int(r["restart_final_pop"]) and 4400 < r["restart_zpe"] < 4850
+
+
+def test_two_gpu_dmc_sim_user_potential(tmp_path):
+    """A user potential callable (getpot plug-in, potential_manager.py:71-99) on a sharded run: each rank's callable sees its own
+    shard of the moved walkers once per step, Vref and the population are global."""
+    from pyvibdmc_b200 import kernels
+    if kernels.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    here = os.path.dirname(os.path.abspath(__file__))
+    out = str(tmp_path / "e2")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29619", os.path.join(here, "multi_gpu_dmcsim_worker.py"), out, "ext"]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
+    r = _result(res.stdout)
+    assert r["world"] == 2
+    for weighting in ("discrete", "continuous"):
+        w = r[weighting]
+        assert w["vref_shape"] == [1500, 2] and abs(w["zpe"] - 1852.5) < 15, w       # HO 1850 cm-1 + time-step bias (config 1)
+        assert w["calls"] == 1501 and 0.4 < w["shard_fraction"] < 0.6, w             # start ensemble + one call per step, half the walkers
+        assert 15000 < w["pop_min"] and w["pop_max"] < 25000, w
+        assert abs(w["desc_sum"] - w["pop_at_window_end"]) < 1e-6 * 20000, w
+    assert r["discrete"]["final_walkers"] == int(r["discrete"]["final_pop"])
+    assert r["continuous"]["final_walkers"] == 20000
