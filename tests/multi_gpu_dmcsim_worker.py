@@ -77,13 +77,15 @@ def ext_main(pv, h5lite, dist, rank, out):
                          log_every=500, seed=21)
         assert sim._world == dist.get_world_size()
         sim.run()
-        n = len(sim.walkers)
+        walkers = sim.walkers                     # continuous weighting: (coords, weights), as in the reference
+        n = len(walkers[0]) if weighting == "continuous" else len(walkers)
+        wsum = float(walkers[1].sum()) if weighting == "continuous" else float(n)
         if rank == 0:
             info = h5lite.read_h5(f"{out}/{weighting}_sim_info.hdf5")
             w = h5lite.read_h5(f"{out}/wfns/{weighting}_wfn_800ts.hdf5")
             pop = info['pop_vs_tau'][:, 1]
             res[weighting] = {"zpe": float(info['vref_vs_tau'][400:, 1].mean() / wn), "final_walkers": int(n), "final_pop": float(pop[-1]),
-                              "pop_min": float(pop.min()), "pop_max": float(pop.max()), "calls": len(calls),
+                              "weight_sum": wsum, "pop_min": float(pop.min()), "pop_max": float(pop.max()), "calls": len(calls),
                               "shard_fraction": float(np.mean(calls)) / float(pop.mean()),
                               "desc_sum": float(w['desc_wts'].sum()), "pop_at_window_end": float(pop[849]),
                               "vref_shape": list(info['vref_vs_tau'].shape)}

@@ -81,4 +81,4 @@ def test_two_gpu_dmc_sim_user_potential(tmp_path):
         assert 15000 < w["pop_min"] and w["pop_max"] < 25000, w
         assert abs(w["desc_sum"] - w["pop_at_window_end"]) < 1e-6 * 20000, w
     assert r["discrete"]["final_walkers"] == int(r["discrete"]["final_pop"])
-    assert r["continuous"]["final_walkers"] == 20000
+    assert r["continuous"]["final_walkers"] == 20000 and abs(r["continuous"]["weight_sum"] - r["continuous"]["final_pop"]) < 1e-6 * 20000
