@@ -57,7 +57,7 @@ class ShardedSim:
 
     def __init__(self, natoms, ndim, masses, num_walkers, delta_t, potential, weighting="discrete", seed=0,
                  rng_mode=_capi.RNG_DEFAULT, pot_params=None, thresh_lower=None, thresh_upper=None, rebalance_every=250,
-                 capacity=None, stats_ring=1 << 14, trial=_capi.TRIAL_NONE, trial_table=None, collective="mailbox"):
+                 capacity=None, stats_ring=1 << 14, trial=_capi.TRIAL_NONE, trial_table=None, collective="mailbox", alpha=None):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
@@ -68,7 +68,7 @@ class ShardedSim:
         self.stream = torch.cuda.Stream(device=self.device)
         self.num_walkers = int(num_walkers)
         local = -(-self.num_walkers // self.world)
-        self.sim = kernels.DeviceSim(natoms, ndim, masses, num_walkers, delta_t, potential, weighting=weighting,
+        self.sim = kernels.DeviceSim(natoms, ndim, masses, num_walkers, delta_t, potential, weighting=weighting, alpha=alpha,
                                      seed=int(seed) + 1000003 * self.rank, rng_mode=rng_mode, pot_params=pot_params,
                                      thresh_lower=thresh_lower, thresh_upper=thresh_upper, device=self.local_rank,
                                      rank=self.rank, world_size=self.world, trial=trial,
@@ -195,11 +195,12 @@ class ShardedSim:
         self._dw_total = sum(pops)
         return offset, self._dw_total
 
-    def dw_end(self):
-        """Close the window: descendant weights of ALL parents, identical on every rank (pyvibdmc.py:663-672, 856-869)."""
+    def dw_end(self, close_window=True):
+        """Close the window: descendant weights of ALL parents, identical on every rank (pyvibdmc.py:663-672, 856-869).
+        close_window=False: the same sums with the window left open (DEBUG_save_desc_wt_tracker, pyvibdmc.py:849-852)."""
         torch = self.torch
         with torch.cuda.stream(self.stream):
-            local = self.sim.dw_end(self._dw_total)
+            local = self.sim.dw_end(self._dw_total) if close_window else self.sim.dw_peek(self._dw_total)
             t = torch.from_numpy(local).to(self.device)
             self.dist.all_reduce(t)
         self.stream.synchronize()
@@ -227,13 +228,11 @@ class ShardedDevice:
     def __init__(self, natoms, ndim, masses, num_walkers, delta_t, potential, weighting="discrete", alpha=None, capacity=None,
                  seed=0, rng_mode=_capi.RNG_DEFAULT, trial=_capi.TRIAL_NONE, pot_params=None, thresh_lower=None, thresh_upper=None,
                  device=0, stats_ring=1 << 16, imp_variant=_capi.IMP_STANDARD, trial_table=None, rebalance_every=250):
-        if alpha is not None and abs(alpha - 1.0 / (2.0 * delta_t)) > 1e-15:
-            raise NotImplementedError("DEBUG_alpha with a sharded run")
         if imp_variant != _capi.IMP_STANDARD:
             raise NotImplementedError("importance-sampling move variants with a sharded run")
         self.ss = ShardedSim(natoms, ndim, masses, num_walkers, delta_t, potential, weighting=weighting, seed=seed, rng_mode=rng_mode,
                              pot_params=pot_params, thresh_lower=thresh_lower, thresh_upper=thresh_upper, stats_ring=stats_ring,
-                             trial=trial, trial_table=trial_table, rebalance_every=rebalance_every)
+                             trial=trial, trial_table=trial_table, rebalance_every=rebalance_every, alpha=alpha)     # alpha: DEBUG_alpha (Vref feedback)
         self.natoms, self.ndim, self.cfg = natoms, ndim, self.ss.sim.cfg
         self.rank, self.world = self.ss.rank, self.ss.world
 
@@ -296,7 +295,7 @@ class ShardedDevice:
         return self.ss.dw_end()
 
     def dw_peek(self, n_parent):
-        raise NotImplementedError("DEBUG_save_desc_wt_tracker with a sharded run")
+        return self.ss.dw_end(close_window=False)
 
     def dw_parent(self):
         xyz, w = self.ss.dw_parent()

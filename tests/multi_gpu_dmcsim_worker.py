@@ -74,7 +74,10 @@ def ext_main(pv, h5lite, dist, rank, out):
         sim = pv.DMC_Sim(sim_name=weighting, output_folder=out, weighting=weighting, num_walkers=20000, num_timesteps=1500,
                          equil_steps=300, chkpt_every=700, wfn_every=500, desc_wt_steps=50, atoms=['O-H'], delta_t=10,
                          potential=pv.Potential_Direct(potential_function=user_pot), start_structures=np.zeros((1, 1, 1)),
-                         log_every=500, seed=21)
+                         log_every=500, seed=21,
+                         # the sharded run also takes the reference's debug switches: the per-step descendant-weight tracker
+                         # (pyvibdmc.py:849-852, 868-870) and a non-default Vref feedback strength (DEBUG_alpha, pyvibdmc.py:651-661)
+                         **({"DEBUG_save_desc_wt_tracker": True} if weighting == "discrete" else {"DEBUG_alpha": 0.03}))
         assert sim._world == dist.get_world_size()
         sim.run()
         walkers = sim.walkers                     # continuous weighting: (coords, weights), as in the reference
@@ -89,6 +92,12 @@ def ext_main(pv, h5lite, dist, rank, out):
                               "shard_fraction": float(np.mean(calls)) / float(pop.mean()),
                               "desc_sum": float(w['desc_wts'].sum()), "pop_at_window_end": float(pop[849]),
                               "vref_shape": list(info['vref_vs_tau'].shape)}
+            if weighting == "discrete":
+                tr = np.load(f"{out}/wfns/discrete_desc_wt_tracker_800ts.npy")
+                res[weighting]["tracker_ok"] = bool(tr.shape == (50, len(w['desc_wts'])) and np.array_equal(tr[-1], w['desc_wts'])
+                                                    and np.array_equal(tr.sum(axis=1), pop[800:850]))
+            else:
+                res[weighting]["alpha"] = float(sim._alpha)
         dist.barrier()
     if rank == 0:
         print("\nRESULT " + json.dumps(res) + "\n", end="", flush=True)

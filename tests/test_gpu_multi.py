@@ -81,4 +81,5 @@ def test_two_gpu_dmc_sim_user_potential(tmp_path):
         assert 15000 < w["pop_min"] and w["pop_max"] < 25000, w
         assert abs(w["desc_sum"] - w["pop_at_window_end"]) < 1e-6 * 20000, w
     assert r["discrete"]["final_walkers"] == int(r["discrete"]["final_pop"])
+    assert r["discrete"]["tracker_ok"] and r["continuous"]["alpha"] == 0.03        # DEBUG_save_desc_wt_tracker / DEBUG_alpha, sharded
     assert r["continuous"]["final_walkers"] == 20000 and abs(r["continuous"]["weight_sum"] - r["continuous"]["final_pop"]) < 1e-6 * 20000
