@@ -57,7 +57,8 @@ class ShardedSim:
 
     def __init__(self, natoms, ndim, masses, num_walkers, delta_t, potential, weighting="discrete", seed=0,
                  rng_mode=_capi.RNG_DEFAULT, pot_params=None, thresh_lower=None, thresh_upper=None, rebalance_every=250,
-                 capacity=None, stats_ring=1 << 14, trial=_capi.TRIAL_NONE, trial_table=None, collective="mailbox", alpha=None):
+                 capacity=None, stats_ring=1 << 14, trial=_capi.TRIAL_NONE, trial_table=None, collective="mailbox", alpha=None,
+                 imp_variant=_capi.IMP_STANDARD):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
@@ -71,7 +72,7 @@ class ShardedSim:
         self.sim = kernels.DeviceSim(natoms, ndim, masses, num_walkers, delta_t, potential, weighting=weighting, alpha=alpha,
                                      seed=int(seed) + 1000003 * self.rank, rng_mode=rng_mode, pot_params=pot_params,
                                      thresh_lower=thresh_lower, thresh_upper=thresh_upper, device=self.local_rank,
-                                     rank=self.rank, world_size=self.world, trial=trial,
+                                     rank=self.rank, world_size=self.world, trial=trial, imp_variant=imp_variant,
                                      capacity=capacity or int(1.6 * local) + 4096, stats_ring=stats_ring)
         self.sim.set_stream(self.stream.cuda_stream)
         self.imp = trial != _capi.TRIAL_NONE
@@ -228,11 +229,11 @@ class ShardedDevice:
     def __init__(self, natoms, ndim, masses, num_walkers, delta_t, potential, weighting="discrete", alpha=None, capacity=None,
                  seed=0, rng_mode=_capi.RNG_DEFAULT, trial=_capi.TRIAL_NONE, pot_params=None, thresh_lower=None, thresh_upper=None,
                  device=0, stats_ring=1 << 16, imp_variant=_capi.IMP_STANDARD, trial_table=None, rebalance_every=250):
-        if imp_variant != _capi.IMP_STANDARD:
-            raise NotImplementedError("importance-sampling move variants with a sharded run")
+        if imp_variant == _capi.IMP_EXCITED_STATE:
+            raise NotImplementedError("excited_state_imp_samp with a sharded run")
         self.ss = ShardedSim(natoms, ndim, masses, num_walkers, delta_t, potential, weighting=weighting, seed=seed, rng_mode=rng_mode,
                              pot_params=pot_params, thresh_lower=thresh_lower, thresh_upper=thresh_upper, stats_ring=stats_ring,
-                             trial=trial, trial_table=trial_table, rebalance_every=rebalance_every, alpha=alpha)     # alpha: DEBUG_alpha (Vref feedback)
+                             trial=trial, trial_table=trial_table, rebalance_every=rebalance_every, imp_variant=imp_variant, alpha=alpha)     # alpha: DEBUG_alpha (Vref feedback)
         self.natoms, self.ndim, self.cfg = natoms, ndim, self.ss.sim.cfg
         self.rank, self.world = self.ss.rank, self.ss.world
 

@@ -21,6 +21,8 @@ def main():
     out = sys.argv[1]
     if len(sys.argv) > 2 and sys.argv[2] == "ext":
         return ext_main(pv, h5lite, dist, rank, out)
+    if len(sys.argv) > 2 and sys.argv[2] == "imp2":
+        return imp2_main(pv, dist, rank, out)
     eq = np.array([[1.81005599, 0., 0.], [-0.45344658, 1.75233806, 0.], [0., 0., 0.]])
     d = os.path.join(os.path.dirname(pv.__file__), "sample_potentials", "FortPots", "Partridge_Schwenke_H2O")
     pot = pv.Potential(potential_function='water_pot', python_file='h2o_potential.py', potential_directory=d, num_cores=1)
@@ -55,6 +57,30 @@ def main():
         res["restart_final_walkers"] = int(n2)
         res["restart_final_pop"] = float(info2['pop_vs_tau'][-1, 1])
         res["restart_zpe"] = float(info2['vref_vs_tau'][300:, 1].mean() / 4.556335281212229e-6)
+        print("\nRESULT " + json.dumps(res) + "\n", end="", flush=True)
+    dist.destroy_process_group()
+
+
+def imp2_main(pv, dist, rank, out):
+    """second_impsamp_displacement (pyvibdmc.py:614-649) on a sharded run: with the exact trial function the local energy is the
+    eigenvalue for every walker on every rank -> Vref is exact and nobody branches, for the standard and the second move type."""
+    wn = 4.556335281212229e-6
+    d = os.path.join(os.path.dirname(pv.__file__), "sample_potentials", "PythonPots")
+    res = {"world": dist.get_world_size()}
+    for tag, second in (("std", False), ("second", True)):
+        imp = pv.ImpSampManager_NoMP(trial_function='trial_harm', trial_directory=d, python_file='harm_trial_wfn.py',
+                                     deriv_function='derivative')
+        pot = pv.Potential(potential_function='oh_stretch_harm', python_file='harmonicOscillator1D.py', potential_directory=d, num_cores=1)
+        sim = pv.DMC_Sim(sim_name=tag, output_folder=out, num_walkers=4000, num_timesteps=300, equil_steps=100, chkpt_every=200,
+                         wfn_every=100, desc_wt_steps=20, atoms=['O-H'], delta_t=5, potential=pot, start_structures=np.zeros((1, 1, 1)),
+                         imp_samp=imp, imp_samp_oned=True, second_impsamp_displacement=second, seed=2)
+        assert sim._world == dist.get_world_size()
+        sim.run()
+        walkers = sim.walkers
+        res[tag] = {"vref_max_dev_cm1": float(np.abs(sim._vref_vs_tau / wn - 1850.0).max()), "pop_constant": bool((sim._pop_vs_tau == 4000).all()),
+                    "walker_std": float(walkers.std()), "n": int(len(walkers))}
+        dist.barrier()
+    if rank == 0:
         print("\nRESULT " + json.dumps(res) + "\n", end="", flush=True)
     dist.destroy_process_group()
 

@@ -83,3 +83,19 @@ def test_two_gpu_dmc_sim_user_potential(tmp_path):
     assert r["discrete"]["final_walkers"] == int(r["discrete"]["final_pop"])
     assert r["discrete"]["tracker_ok"] and r["continuous"]["alpha"] == 0.03        # DEBUG_save_desc_wt_tracker / DEBUG_alpha, sharded
     assert r["continuous"]["final_walkers"] == 20000 and abs(r["continuous"]["weight_sum"] - r["continuous"]["final_pop"]) < 1e-6 * 20000
+
+
+def test_two_gpu_second_impsamp_displacement(tmp_path):
+    """pyvibdmc.py:614-649 sharded: exact trial function => zero-variance estimator on both ranks, standard and second move type."""
+    from pyvibdmc_b200 import kernels
+    if kernels.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    here = os.path.dirname(os.path.abspath(__file__))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29620", os.path.join(here, "multi_gpu_dmcsim_worker.py"), str(tmp_path / "i2"), "imp2"]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
+    r = _result(res.stdout)
+    assert r["world"] == 2
+    for tag in ("std", "second"):
+        assert r[tag]["vref_max_dev_cm1"] < 1e-6 and r[tag]["pop_constant"] and r[tag]["n"] == 4000 and r[tag]["walker_std"] > 0.05, r
