@@ -80,8 +80,6 @@ class ShardedSim:
         # ext_move() and ext_finish(); the per-step exchange is the NCCL all-reduce (the host is in the loop anyway)
         self.external = int(potential) == _capi.POT_EXTERNAL
         if self.imp:
-            if weighting != "discrete":
-                raise NotImplementedError("sharded importance sampling is built for discrete weighting")
             self.sim.set_trial_table(trial_table)
         self.sums = torch.zeros(_capi.NSUMS, dtype=torch.float64, device=self.device)
         self._gate = torch.zeros(1, dtype=torch.float64, device=self.device)

@@ -80,6 +80,24 @@ def imp2_main(pv, dist, rank, out):
         res[tag] = {"vref_max_dev_cm1": float(np.abs(sim._vref_vs_tau / wn - 1850.0).max()), "pop_constant": bool((sim._pop_vs_tau == 4000).all()),
                     "walker_std": float(walkers.std()), "n": int(len(walkers))}
         dist.barrier()
+    # a trial function that is NOT the eigenfunction (harmonic Gaussian on the Morse oscillator): walkers branch, with discrete and
+    # with continuous weighting; E0 = omega/2 - omega_x/4 = 1833.4 cm-1
+    for weighting in ("discrete", "continuous"):
+        imp = pv.ImpSampManager_NoMP(trial_function='trial_harm', trial_directory=d, python_file='harm_trial_wfn.py',
+                                     deriv_function='derivative')
+        pot = pv.Potential(potential_function='oh_stretch_morse', python_file='morse_osc_1d.py', potential_directory=d, num_cores=1)
+        sim = pv.DMC_Sim(sim_name="m" + weighting, output_folder=out, weighting=weighting, num_walkers=20000, num_timesteps=1200,
+                         equil_steps=200, chkpt_every=600, wfn_every=400, desc_wt_steps=20, atoms=['O-H'], delta_t=5, potential=pot,
+                         start_structures=np.zeros((1, 1, 1)), imp_samp=imp, imp_samp_oned=True, seed=8)
+        sim.run()
+        walkers = sim.walkers
+        cds = walkers[0] if weighting == "continuous" else walkers
+        pop = sim._pop_vs_tau
+        res["morse_" + weighting] = {"zpe": float(sim._vref_vs_tau[300:].mean() / wn), "vref_std": float(sim._vref_vs_tau[300:].std() / wn),
+                                     "pop_min": float(pop.min()), "pop_max": float(pop.max()), "n": int(len(cds)),
+                                     "weight_sum": float(walkers[1].sum()) if weighting == "continuous" else float(len(cds)),
+                                     "final_pop": float(pop[-1])}
+        dist.barrier()
     if rank == 0:
         print("\nRESULT " + json.dumps(res) + "\n", end="", flush=True)
     dist.destroy_process_group()

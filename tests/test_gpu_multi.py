@@ -99,3 +99,9 @@ def test_two_gpu_second_impsamp_displacement(tmp_path):
     assert r["world"] == 2
     for tag in ("std", "second"):
         assert r[tag]["vref_max_dev_cm1"] < 1e-6 and r[tag]["pop_constant"] and r[tag]["n"] == 4000 and r[tag]["walker_std"] > 0.05, r
+    # harmonic trial function on the Morse oscillator: branching under importance sampling, discrete and continuous, sharded
+    for weighting in ("discrete", "continuous"):
+        m = r["morse_" + weighting]
+        assert abs(m["zpe"] - 1833.4) < 6 and m["vref_std"] > 0, m
+        assert 17000 < m["pop_min"] and m["pop_max"] < 23000 and abs(m["weight_sum"] - m["final_pop"]) < 1e-6 * 20000, m
+    assert r["morse_continuous"]["n"] == 20000 and r["morse_discrete"]["n"] == int(r["morse_discrete"]["final_pop"])
