@@ -227,8 +227,6 @@ class ShardedDevice:
     def __init__(self, natoms, ndim, masses, num_walkers, delta_t, potential, weighting="discrete", alpha=None, capacity=None,
                  seed=0, rng_mode=_capi.RNG_DEFAULT, trial=_capi.TRIAL_NONE, pot_params=None, thresh_lower=None, thresh_upper=None,
                  device=0, stats_ring=1 << 16, imp_variant=_capi.IMP_STANDARD, trial_table=None, rebalance_every=250):
-        if imp_variant == _capi.IMP_EXCITED_STATE:
-            raise NotImplementedError("excited_state_imp_samp with a sharded run")
         self.ss = ShardedSim(natoms, ndim, masses, num_walkers, delta_t, potential, weighting=weighting, seed=seed, rng_mode=rng_mode,
                              pot_params=pot_params, thresh_lower=thresh_lower, thresh_upper=thresh_upper, stats_ring=stats_ring,
                              trial=trial, trial_table=trial_table, rebalance_every=rebalance_every, imp_variant=imp_variant, alpha=alpha)     # alpha: DEBUG_alpha (Vref feedback)

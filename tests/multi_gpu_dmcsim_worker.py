@@ -21,6 +21,8 @@ def main():
     out = sys.argv[1]
     if len(sys.argv) > 2 and sys.argv[2] == "ext":
         return ext_main(pv, h5lite, dist, rank, out)
+    if len(sys.argv) > 2 and sys.argv[2] == "exc":
+        return exc_main(pv, dist, rank, out)
     if len(sys.argv) > 2 and sys.argv[2] == "imp2":
         return imp2_main(pv, dist, rank, out)
     eq = np.array([[1.81005599, 0., 0.], [-0.45344658, 1.75233806, 0.], [0., 0., 0.]])
@@ -57,6 +59,35 @@ def main():
         res["restart_final_walkers"] = int(n2)
         res["restart_final_pop"] = float(info2['pop_vs_tau'][-1, 1])
         res["restart_zpe"] = float(info2['vref_vs_tau'][300:, 1].mean() / 4.556335281212229e-6)
+        print("\nRESULT " + json.dumps(res) + "\n", end="", flush=True)
+    dist.destroy_process_group()
+
+
+def exc_main(pv, dist, rank, out):
+    """excited_state_imp_samp (pyvibdmc.py:562-591, 608-611, 810-811) on a sharded run next to the same run on one GPU (rank 0)."""
+    wn = 4.556335281212229e-6
+    eq = np.array([[1.81005599, 0., 0.], [-0.45344658, 1.75233806, 0.], [0., 0., 0.]])
+    hd = os.path.join(os.path.dirname(pv.__file__), "sample_potentials", "FortPots", "Partridge_Schwenke_H2O")
+    kw = {'dists': [[0, 2], [2, 1]], 'angs': [[0, 2, 1]]}
+    res = {"world": dist.get_world_size()}
+
+    def run(tag, distributed):
+        pot = pv.Potential(potential_function='water_pot', python_file='h2o_potential.py', potential_directory=hd, num_cores=1)
+        wimp = pv.ImpSampManager(trial_function='trial_wavefunction', trial_directory=hd, python_file='call_trl_h2o.py', pot_manager=pot,
+                                 deriv_function='dpsi_dx', trial_kwargs=kw, deriv_kwargs=kw)
+        sim = pv.DMC_Sim(sim_name=tag, output_folder=os.path.join(out, tag), num_walkers=8000, num_timesteps=700, equil_steps=100,
+                         chkpt_every=400, wfn_every=300, desc_wt_steps=20, atoms=['H', 'H', 'O'], delta_t=1, potential=pot,
+                         start_structures=eq[None] * 1.01, imp_samp=wimp, excited_state_imp_samp=True, seed=4, distributed=distributed)
+        sim.run()
+        pop = sim._pop_vs_tau
+        return {"world": int(sim._world), "zpe": float(sim._vref_vs_tau[300:].mean() / wn), "pop_min": float(pop.min()),
+                "pop_max": float(pop.max()), "n": int(len(sim.walkers)), "final_pop": float(pop[-1])}
+    res["sharded"] = run("sh", None)
+    dist.barrier()
+    if rank == 0:
+        res["single"] = run("one", False)
+    dist.barrier()
+    if rank == 0:
         print("\nRESULT " + json.dumps(res) + "\n", end="", flush=True)
     dist.destroy_process_group()
 

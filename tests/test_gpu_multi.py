@@ -105,3 +105,20 @@ def test_two_gpu_second_impsamp_displacement(tmp_path):
         assert abs(m["zpe"] - 1833.4) < 6 and m["vref_std"] > 0, m
         assert 17000 < m["pop_min"] and m["pop_max"] < 23000 and abs(m["weight_sum"] - m["final_pop"]) < 1e-6 * 20000, m
     assert r["morse_continuous"]["n"] == 20000 and r["morse_discrete"]["n"] == int(r["morse_discrete"]["final_pop"])
+
+
+def test_two_gpu_excited_state_imp_samp(tmp_path):
+    """excited_state_imp_samp (pyvibdmc.py:562-591, 608-611, 810-811) sharded over 2 GPUs agrees with the same run on one GPU."""
+    from pyvibdmc_b200 import kernels
+    if kernels.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    here = os.path.dirname(os.path.abspath(__file__))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29621", os.path.join(here, "multi_gpu_dmcsim_worker.py"), str(tmp_path / "ex"), "exc"]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
+    r = _result(res.stdout)
+    sh, one = r["sharded"], r["single"]
+    assert sh["world"] == 2 and one["world"] == 1, r
+    assert abs(sh["zpe"] - one["zpe"]) < 25 and 4500 < sh["zpe"] < 4800, r
+    assert sh["n"] == int(sh["final_pop"]) and 6000 < sh["pop_min"] and sh["pop_max"] < 10000, r
