@@ -326,7 +326,10 @@ int pvd_sim_download_imp(pvd_sim *s, double *fx, double *psi, double *sec, int64
  *             pvd_sim_imp_ext_finish(V or NULL, n, do_branch)   E_L = V + T_L (:807-809), weighting / branching, Vref
  * V = NULL evaluates the configured built-in potential on the GPU; with PVD_POT_EXTERNAL the caller downloads the accepted
  * coordinates (pvd_sim_download) and passes getpot's result.  disp / u_metro / u_branch: injected displacements (n, atoms, dims,
- * already scaled by sigma), Metropolis and birth/death uniforms -- replays of reference trajectories in the parity tests -- or NULL. */
+ * already scaled by sigma), Metropolis and birth/death uniforms -- replays of reference trajectories in the parity tests -- or NULL.
+ * Sharded (world_size > 1): every call works on this rank's walkers; the caller all-reduces the shared sums (pvd_sim_set_sums_ptr)
+ * after _init (then pvd_sim_init_finalize), after _accept (global acceptance fraction -> dt_eff, pyvibdmc.py:372-378) and after
+ * _finish (then pvd_sim_step_finalize). */
 int pvd_sim_imp_ext_init(pvd_sim *s, const double *fx, const double *psi, const double *sec, const double *v_or_null);
 int pvd_sim_imp_ext_propose(pvd_sim *s, const double *disp_or_null, double *xyz_out, int64_t *n_out);
 int pvd_sim_imp_ext_accept(pvd_sim *s, const double *fy, const double *psi_y, const double *sec_y, int64_t n, const double *u_metro_or_null);

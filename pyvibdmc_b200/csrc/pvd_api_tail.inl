@@ -470,7 +470,6 @@ int pvd_sim_imp_ext_init(pvd_sim *s, const double *fx, const double *psi, const 
     SIM_CHECK(s);
     SIM_DEVICE(s);
     PVD_REQUIRE(s->cfg.trial == PVD_TRIAL_EXTERNAL && s->uploaded, "pvd_sim_imp_ext_init: needs trial = PVD_TRIAL_EXTERNAL and uploaded walkers");
-    PVD_REQUIRE(s->cfg.world_size == 1, "importance sampling with a user trial wave function is single-GPU");
     PVD_REQUIRE(fx && psi && sec && (v || s->cfg.potential != PVD_POT_EXTERNAL), "pvd_sim_imp_ext_init: NULL argument");
     if (int rc = impx_buffers(s)) return rc;
     const long long n = s->n_uploaded;
@@ -489,7 +488,8 @@ int pvd_sim_imp_ext_init(pvd_sim *s, const double *fx, const double *psi, const 
     PVD_CHECK_LAUNCH();
     PVD_CUDA(cudaStreamSynchronize(s->stream));
     if (int rc = sim_init_sums(s)) return rc;
-    return pvd_sim_init_finalize(s);
+    if (s->cfg.world_size == 1) return pvd_sim_init_finalize(s);
+    return PVD_OK;                     // sharded: the caller all-reduces the sums, then pvd_sim_init_finalize
 }
 
 int pvd_sim_imp_ext_propose(pvd_sim *s, const double *disp, double *xyz_out, int64_t *n_out)
@@ -579,6 +579,11 @@ int pvd_sim_imp_ext_finish(pvd_sim *s, const double *v, int64_t n, int32_t do_br
         if (!s->inj_u.p) PVD_CUDA(s->inj_u.alloc((size_t)s->cap * 8));
         PVD_CUDA(cudaMemcpyAsync(s->inj_u.p, u_branch, (size_t)h0[s->parity].n * 8, cudaMemcpyHostToDevice, s->stream));
         a.inj_u = s->inj_u.as<double>();
+    }
+    if (s->cfg.world_size > 1) {
+        // sharded: k_impx_accept published (accepted, walkers) of this shard, the caller all-reduced them: global acceptance -> dt_eff
+        k_imp_set_dt<<<1, 32, 0, s->stream>>>(s->st.as<DevState>(), s->parity, a.sums, s->cfg.delta_t);
+        PVD_CHECK_LAUNCH();
     }
     if (int rc = imp_enqueue_branch(s, a)) return rc;
     s->parity ^= 1;

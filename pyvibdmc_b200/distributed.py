@@ -79,7 +79,8 @@ class ShardedSim:
         # a user potential (the reference's getpot plug-in): every rank evaluates its own shard on the host between
         # ext_move() and ext_finish(); the per-step exchange is the NCCL all-reduce (the host is in the loop anyway)
         self.external = int(potential) == _capi.POT_EXTERNAL
-        if self.imp:
+        self.hosted = trial == _capi.TRIAL_EXTERNAL
+        if self.imp and not self.hosted:
             self.sim.set_trial_table(trial_table)
         self.sums = torch.zeros(_capi.NSUMS, dtype=torch.float64, device=self.device)
         self._gate = torch.zeros(1, dtype=torch.float64, device=self.device)
@@ -98,8 +99,8 @@ class ShardedSim:
     def upload(self, coords_local, wts_local=None):
         with self.torch.cuda.stream(self.stream):
             self.sim.upload(coords_local, wts_local)
-            if self.external:
-                return                                 # the energies of the start ensemble follow: set_pots()
+            if self.external or self.hosted:
+                return                                 # the energies / drift terms of the start ensemble follow: set_pots() / imp_ext_init()
             self.dist.all_reduce(self.sums)
             self.sim.init_finalize()
 
@@ -118,6 +119,31 @@ class ShardedSim:
         """Energies of the moved shard -> weights / branching per shard, global Vref and population."""
         with self.torch.cuda.stream(self.stream):
             self.sim.ext_finish(v_local, do_branch)
+            self.dist.all_reduce(self.sums)
+            self.sim.step_finalize()
+            self.steps_done += 1
+            if self.rebalance_every and self.steps_done % self.rebalance_every == 0:
+                self.rebalance()
+
+    # -- importance sampling with a user trial wave function (PVD_TRIAL_EXTERNAL): every rank's impsamp.drift sees its own shard
+    def imp_ext_init(self, fx, psi, sec, v=None):
+        with self.torch.cuda.stream(self.stream):
+            self.sim.imp_ext_init(fx, psi, sec, v)
+            self.dist.all_reduce(self.sums)
+            self.sim.init_finalize()
+
+    def imp_ext_propose(self):
+        return self.sim.imp_ext_propose()
+
+    def imp_ext_accept(self, fy, psi_y, sec_y):
+        """Metropolis step per shard; the acceptance fraction that scales the time step is global (pyvibdmc.py:372-378, 603)."""
+        with self.torch.cuda.stream(self.stream):
+            self.sim.imp_ext_accept(fy, psi_y, sec_y)
+            self.dist.all_reduce(self.sums)
+
+    def imp_ext_finish(self, v=None, do_branch=True):
+        with self.torch.cuda.stream(self.stream):
+            self.sim.imp_ext_finish(v, do_branch)
             self.dist.all_reduce(self.sums)
             self.sim.step_finalize()
             self.steps_done += 1
@@ -270,6 +296,22 @@ class ShardedDevice:
 
     def ext_move(self):
         return self.ss.ext_move()
+
+    def imp_ext_init(self, fx, psi, sec, v=None):
+        self.ss.imp_ext_init(fx, psi, sec, v)
+
+    def imp_ext_propose(self):
+        return self.ss.imp_ext_propose()
+
+    def imp_ext_accept(self, fy, psi_y, sec_y):
+        self.ss.imp_ext_accept(fy, psi_y, sec_y)
+
+    def imp_ext_finish(self, v=None, do_branch=True):
+        self.ss.imp_ext_finish(v, do_branch)
+
+    def download_local(self):
+        """This rank's shard (what a user potential / trial function is evaluated on)."""
+        return self.ss.sim.download()
 
     def ext_finish(self, v_local, do_branch=True):
         self.ss.ext_finish(np.ascontiguousarray(v_local, dtype=np.float64), do_branch)

@@ -309,11 +309,8 @@ class DMC_Sim:
                 pot_params = [pot["de"], pot["alpha"]]
         cap = int(1.5 * max(self.num_walkers, len(self._walker_coords))) + 1024
         if self._world > 1:
-            if self._hosted_imp:
-                raise NotImplementedError("a sharded DMC_Sim needs a built-in trial wave function")
-            if pot is None and (self.fixed_node is not None or self._deb_save_before_bod or self.impsamp_manager is not None):
-                raise NotImplementedError("a sharded DMC_Sim with a user potential runs the plain loop (no fixed node, "
-                                          "DEBUG_save_before_bod or importance sampling)")
+            if pot is None and (self.fixed_node is not None or self._deb_save_before_bod):
+                raise NotImplementedError("a sharded DMC_Sim with a user potential has no fixed node / DEBUG_save_before_bod")
             from .distributed import ShardedDevice
             self._dev = ShardedDevice(n_atoms, n_dim, self.masses, self.num_walkers, self.delta_t, pot_id, weighting=self.weighting,
                                       alpha=self._alpha, seed=self._seed + 7919 * int(self.cur_timestep), rng_mode=self._rng_mode,
@@ -323,12 +320,20 @@ class DMC_Sim:
                                       imp_variant=(_capi.IMP_SECOND_DISPLACEMENT if self.second_impsamp_displacement else
                                                    _capi.IMP_EXCITED_STATE if self.excited_state_imp_samp else _capi.IMP_STANDARD),
                                       trial_table=(trial["table"] if trial else None))
-            self._builtin = pot is not None
+            self._builtin = pot is not None and not self._hosted_imp
             self._pot_on_device = pot is not None
             if pot_id == _capi.POT_NN_H4O2:
                 self._dev.set_nn_weights(pot["weights"])
             self._dev.upload(self._walker_coords, self._cont_wts)
-            if pot is None:
+            if self._hosted_imp:
+                # user trial / derivative functions (imp_samp_manager.py:92-139): every rank's impsamp.drift sees its own shard;
+                # first-step exception (pyvibdmc.py:760-769) as on one GPU
+                s0, c0 = self._dev.local_slice(len(self._walker_coords))
+                mine = self._walker_coords[s0:s0 + c0]
+                f_x, psi_1, sec = self.impsamp.drift(mine)
+                v0 = None if self._pot_on_device else np.asarray(self.potential(mine), dtype=np.float64)
+                self._dev.imp_ext_init(f_x, psi_1, sec, v0)
+            elif pot is None:
                 # user potential (getpot plug-in, potential_manager.py:71-99): every rank evaluates its own shard
                 s0, c0 = self._dev.local_slice(len(self._walker_coords))
                 self._dev.set_pots(np.asarray(self.potential(self._walker_coords[s0:s0 + c0]), dtype=np.float64))
@@ -572,7 +577,7 @@ class DMC_Sim:
                 if self._pot_on_device:
                     dev.imp_ext_finish(None, do_branch)
                 else:
-                    cds = dev.download()["coords"]
+                    cds = (dev.download_local() if self._world > 1 else dev.download())["coords"]      # sharded: this rank's walkers
                     if step in self._log_set:
                         v, pot_seconds[step] = self.potential(cds, timeit=True)
                     else:

@@ -21,6 +21,8 @@ def main():
     out = sys.argv[1]
     if len(sys.argv) > 2 and sys.argv[2] == "ext":
         return ext_main(pv, h5lite, dist, rank, out)
+    if len(sys.argv) > 2 and sys.argv[2] == "uimp":
+        return uimp_main(pv, dist, rank, out)
     if len(sys.argv) > 2 and sys.argv[2] == "exc":
         return exc_main(pv, dist, rank, out)
     if len(sys.argv) > 2 and sys.argv[2] == "imp2":
@@ -59,6 +61,57 @@ def main():
         res["restart_final_walkers"] = int(n2)
         res["restart_final_pop"] = float(info2['pop_vs_tau'][-1, 1])
         res["restart_zpe"] = float(info2['vref_vs_tau'][300:, 1].mean() / 4.556335281212229e-6)
+        print("\nRESULT " + json.dumps(res) + "\n", end="", flush=True)
+    dist.destroy_process_group()
+
+
+USER_TRIAL = """
+import numpy as np
+
+ALPHA = 1.4 * %r          # a Gaussian that is NOT the exact ground state: the estimator has a variance, walkers branch
+
+
+def my_trial(cds):
+    return np.exp(-0.5 * ALPHA * cds ** 2).squeeze()
+
+
+def my_derivs(cds):
+    x = cds
+    return -ALPHA * x, (ALPHA ** 2 * x ** 2 - ALPHA)
+"""
+
+
+def uimp_main(pv, dist, rank, out):
+    """A user trial wave function / derivative function (imp_samp_manager.py:92-139, 197-224) on a sharded run: every rank's
+    impsamp.drift sees its own shard once per step, the acceptance fraction and Vref are global."""
+    wn = 4.556335281212229e-6
+    m, om = pv.Constants.reduced_mass('O-H'), 3700.0 * wn
+    mine = os.path.join(out, f"trial_rank{rank}")
+    os.makedirs(mine, exist_ok=True)
+    with open(os.path.join(mine, "my_trial.py"), "w") as fh:
+        fh.write(USER_TRIAL % (m * om))
+    d = os.path.join(os.path.dirname(pv.__file__), "sample_potentials", "PythonPots")
+    res = {"world": dist.get_world_size()}
+    for tag, user_potential, derivs in (("builtin_pot", False, 'my_derivs'), ("user_pot", True, None)):
+        imp = pv.ImpSampManager_NoMP(trial_function='my_trial', trial_directory=mine, python_file='my_trial.py', deriv_function=derivs)
+        pot = pv.Potential_Direct(potential_function=lambda c: (0.5 * m * om ** 2 * c ** 2).reshape(len(c))) if user_potential else \
+            pv.Potential(potential_function='oh_stretch_harm', python_file='harmonicOscillator1D.py', potential_directory=d, num_cores=1)
+        sim = pv.DMC_Sim(sim_name=tag, output_folder=os.path.join(out, tag), num_walkers=6000, num_timesteps=700, equil_steps=100,
+                         chkpt_every=350, wfn_every=300, desc_wt_steps=20, atoms=['O-H'], delta_t=5, potential=pot,
+                         start_structures=np.zeros((1, 1, 1)), imp_samp=imp, imp_samp_oned=True, seed=3)
+        assert sim._world == dist.get_world_size()
+        sim.run()
+        pop = sim._pop_vs_tau
+        if rank == 0:
+            from pyvibdmc_b200.simulation_utilities import h5lite
+            tau = h5lite.read_h5(os.path.join(out, tag, f"{tag}_sim_info.hdf5"))['vref_vs_tau'][:, 0]      # effective time axis
+        else:
+            tau = np.arange(2.0)
+        res[tag] = {"zpe": float(sim._vref_vs_tau[200:].mean() / wn), "pop_min": float(pop.min()), "pop_max": float(pop.max()),
+                    "pop_std": float(pop.std()), "n": int(len(sim.walkers)), "final_pop": float(pop[-1]),
+                    "tau_increasing": bool(np.all(np.diff(tau) > 0)), "tau_last": float(tau[-1]), "hosted": bool(sim._hosted_imp)}
+        dist.barrier()
+    if rank == 0:
         print("\nRESULT " + json.dumps(res) + "\n", end="", flush=True)
     dist.destroy_process_group()
 

@@ -122,3 +122,23 @@ def test_two_gpu_excited_state_imp_samp(tmp_path):
     assert sh["world"] == 2 and one["world"] == 1, r
     assert abs(sh["zpe"] - one["zpe"]) < 25 and 4500 < sh["zpe"] < 4800, r
     assert sh["n"] == int(sh["final_pop"]) and 6000 < sh["pop_min"] and sh["pop_max"] < 10000, r
+
+
+def test_two_gpu_user_trial_function(tmp_path):
+    """Any trial / derivative callable through ImpSampManager (imp_samp_manager.py:92-139, 197-224) on a sharded run, with a shipped
+    and with a user potential: drift terms per shard from the host, global acceptance fraction, global Vref."""
+    from pyvibdmc_b200 import kernels
+    if kernels.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    here = os.path.dirname(os.path.abspath(__file__))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29622", os.path.join(here, "multi_gpu_dmcsim_worker.py"), str(tmp_path / "ui"), "uimp"]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
+    r = _result(res.stdout)
+    assert r["world"] == 2
+    for tag in ("builtin_pot", "user_pot"):
+        w = r[tag]
+        assert w["hosted"] and abs(w["zpe"] - 1850.0) < 25, r
+        assert 4000 < w["pop_min"] and w["pop_max"] < 8000 and w["pop_std"] > 0 and w["n"] == int(w["final_pop"]), r
+        assert w["tau_increasing"] and w["tau_last"] <= 3500.0, r                   # effective time axis (rejections shorten the step)
